@@ -1,0 +1,80 @@
+"""Small model builders shared by the golden-vector generator and the tests (TEST INFRASTRUCTURE)."""
+
+import torch
+from torch import nn
+
+
+def mlp_c1(classes: int = 10, width: int = 64) -> nn.Sequential:
+    """BASELINE.json configs[0]: D=64, 4 Linear + ReLU, 13,130 parameters."""
+    return nn.Sequential(
+        nn.Linear(width, width), nn.ReLU(), nn.Linear(width, width), nn.ReLU(),
+        nn.Linear(width, width), nn.ReLU(), nn.Linear(width, classes),
+    )
+
+
+class BasicBlock(nn.Module):
+    """torchvision-style residual block (conv-bn-relu-conv-bn + shortcut, relu)."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False),
+                                            nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + idt)
+
+
+class MiniResNet(nn.Module):
+    """A ResNet-18-shaped network at toy size: 7x7/2 stem, maxpool(3,2,1), two stages."""
+
+    def __init__(self, width=8, classes=10):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, width, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = nn.Sequential(BasicBlock(width, width, 1))
+        self.layer2 = nn.Sequential(BasicBlock(width, 2 * width, 2))
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(2 * width, classes)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer2(self.layer1(x))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def randomize_bn_(model: nn.Module, gen: torch.Generator) -> None:
+    """Give eval-mode BatchNorm non-trivial running statistics and affine parameters."""
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.copy_(0.3 * torch.randn(m.num_features, generator=gen))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=gen))
+            with torch.no_grad():
+                m.weight.copy_(0.5 + torch.rand(m.num_features, generator=gen))
+                m.bias.copy_(0.2 * torch.randn(m.num_features, generator=gen))
+
+
+class ConvNetBias(nn.Module):
+    """Plain CNN with conv biases, stride/padding variety and flatten->Linear (KFAC cases)."""
+
+    def __init__(self, classes=5):
+        super().__init__()
+        self.c1 = nn.Conv2d(3, 6, 3, 1, 1)
+        self.c2 = nn.Conv2d(6, 8, 3, 2, 0)
+        self.fc = nn.Linear(8 * 3 * 3, classes)
+
+    def forward(self, x):
+        x = torch.relu(self.c1(x))
+        x = torch.relu(self.c2(x))
+        return self.fc(torch.flatten(x, 1))
