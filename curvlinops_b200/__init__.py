@@ -1,0 +1,17 @@
+"""curvlinops_b200: B200-native engine for the curvature-matvec hot path of f-dangel/curvlinops.
+
+Drop-in operator classes (same names / constructor arguments as the reference):
+``HessianLinearOperator``, ``GGNLinearOperator``, ``KFACLinearOperator``, ``EKFACLinearOperator`` and the
+structured operators they are assembled from.  All arithmetic runs in hand-written sm_100a CUDA kernels
+behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
+"""
+
+from .curvature import CurvatureLinearOperator, GGNLinearOperator, HessianLinearOperator
+from .linop import PyTorchLinearOperator
+
+__all__ = [
+    "PyTorchLinearOperator",
+    "CurvatureLinearOperator",
+    "GGNLinearOperator",
+    "HessianLinearOperator",
+]

@@ -1,0 +1,304 @@
+"""Model -> static layer program.
+
+The reference differentiates an opaque ``(params, X) -> prediction`` function with ``torch.func``
+(``curvlinops/ggn.py:61-71``, ``curvlinops/hessian.py:66``).  This engine instead traces that function
+once per input shape into ATen ops (the same ``make_fx(functionalize(f))`` trace the reference's own
+KFAC IO collector uses, ``curvlinops/computers/io_collector/collector.py:107``) and lowers the graph to
+the fixed op set the CUDA kernels implement.  Anything outside that set raises
+``NotImplementedError`` -- there is no autograd / CPU fallback.
+
+Supported ATen ops: convolution (groups=1, dilation=1), addmm / mm (+t) i.e. ``nn.Linear`` on 2-d
+inputs, native_batch_norm in eval mode, relu / sigmoid / tanh, add.Tensor (residual), max_pool2d,
+mean over (H, W) / adaptive_avg_pool2d(1), view / flatten / reshape between 4-d and 2-d, detach.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+from torch import Tensor
+from torch.func import functionalize
+from torch.fx.experimental.proxy_tensor import make_fx
+
+from . import _capi as capi
+
+aten = torch.ops.aten
+
+
+@dataclass
+class LayerProgram:
+    """Host-side description handed to ``curv_program_create``."""
+
+    values: list = field(default_factory=list)  # (C, H, W, has_tangent)
+    nodes: list = field(default_factory=list)   # dicts with NodeDesc fields
+    consts: list = field(default_factory=list)  # constant tensors referenced by c0..c3
+    conv_nodes: dict = field(default_factory=dict)  # weight param name -> node index
+    out_features: int = 0
+
+    def add_value(self, C, H, W, tan):
+        self.values.append([int(C), int(H), int(W), bool(tan)])
+        return len(self.values) - 1
+
+    def add_const(self, t: Tensor) -> int:
+        self.consts.append(t.detach().to(torch.float32).contiguous())
+        return len(self.consts) - 1
+
+    def add_node(self, op, in0=-1, in1=-1, out=-1, p0=-1, p1=-1, c0=-1, c1=-1, c2=-1, c3=-1,
+                 kh=1, kw=1, sh=1, sw=1, ph=0, pw=0, eps=0.0):
+        self.nodes.append(dict(op=op, in0=in0, in1=in1, out=out, p0=p0, p1=p1, c0=c0, c1=c1, c2=c2,
+                               c3=c3, kh=kh, kw=kw, sh=sh, sw=sw, ph=ph, pw=pw, eps=eps))
+        return len(self.nodes) - 1
+
+
+class _Ref:
+    """What an FX node evaluates to during lowering."""
+
+    def __init__(self, kind, **kw):
+        self.kind = kind  # "act" | "param" | "const" | "paramT" | "constT" | "tuple"
+        self.__dict__.update(kw)
+
+
+def _pair(x):
+    return (int(x[0]), int(x[1])) if len(x) == 2 else (int(x[0]), int(x[0]))
+
+
+def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
+    """Trace ``model_func(params, X)`` and lower it to a :class:`LayerProgram`.
+
+    ``params`` are the *differentiated* tensors (the operator's ``params`` dict, in order); every other
+    tensor the function touches becomes a constant, exactly like ``functional_call`` falls back to the
+    module's own parameters and buffers (reference ``curvlinops/utils.py:267-297``).
+    """
+    if not isinstance(X, Tensor) or X.ndim not in (2, 4):
+        raise NotImplementedError(
+            f"The B200 engine supports tensor inputs of shape [B, C] or [B, C, H, W]; got {type(X).__name__}"
+            + (f" {tuple(X.shape)}" if isinstance(X, Tensor) else "") + "."
+        )
+    names = list(params.keys())
+
+    def f(p, x):
+        return model_func(p, x)
+
+    with torch.no_grad():
+        gm = make_fx(functionalize(f), tracing_mode="real")(params, X)
+
+    prog = LayerProgram()
+    env: dict = {}
+    placeholders = [n for n in gm.graph.nodes if n.op == "placeholder"]
+    if len(placeholders) != len(names) + 1:
+        raise NotImplementedError("Unexpected trace signature (non-tensor leaves in params?).")
+    for i, n in enumerate(placeholders[:-1]):
+        env[n] = _Ref("param", index=i, shape=tuple(params[names[i]].shape))
+    xin = placeholders[-1]
+    if X.ndim == 4:
+        v = prog.add_value(X.shape[1], X.shape[2], X.shape[3], False)
+    else:
+        v = prog.add_value(X.shape[1], 1, 1, False)
+    prog.add_node(capi.OP_INPUT, out=v)
+    env[xin] = _Ref("act", value=v, flat=False)
+
+    # liveness: only lower nodes the output depends on
+    out_node = [n for n in gm.graph.nodes if n.op == "output"][0]
+    live = set()
+    stack = list(out_node.all_input_nodes)
+    while stack:
+        n = stack.pop()
+        if not isinstance(n, torch.fx.Node) or n in live:
+            continue
+        live.add(n)
+        stack.extend(a for a in n.all_input_nodes)
+
+    def shape_of(ref):
+        return prog.values[ref.value]
+
+    def tan_of(*refs):
+        return any(prog.values[r.value][3] for r in refs if r is not None and r.kind == "act")
+
+    def unsupported(node, why=""):
+        raise NotImplementedError(
+            f"Operation {node.target} is not supported by the B200 curvature engine"
+            f"{': ' + why if why else ''}. Supported layers: Linear, Conv2d, BatchNorm2d (eval), ReLU,"
+            " Sigmoid, Tanh, MaxPool2d, global average pooling, residual adds, flatten."
+        )
+
+    def weight_slots(ref):
+        """(param index or -1, const index or -1) for a weight-like reference."""
+        if ref is None:
+            return -1, -1
+        if ref.kind == "param":
+            return ref.index, -1
+        if ref.kind == "const":
+            return -1, prog.add_const(ref.tensor)
+        raise NotImplementedError("Parameters must be used directly by a supported layer.")
+
+    def emit_conv(node, xr, wref, bref, kh, kw, sh, sw, ph, pw, cout, ho, wo):
+        p0, c0 = weight_slots(wref)
+        p1, c1 = weight_slots(bref)
+        tan = tan_of(xr) or p0 >= 0 or p1 >= 0
+        ov = prog.add_value(cout, ho, wo, tan)
+        ni = prog.add_node(capi.OP_CONV, in0=xr.value, out=ov, p0=p0, p1=p1, c0=c0, c1=c1, kh=kh, kw=kw,
+                           sh=sh, sw=sw, ph=ph, pw=pw)
+        if p0 >= 0:
+            prog.conv_nodes[names[p0]] = ni
+        return _Ref("act", value=ov, flat=False)
+
+    def emit_linear(node, xr, wref, bref):
+        """x [B, in] @ W^T + b, W stored [out, in] (nn.Linear)."""
+        if wref.kind not in ("paramT", "constT"):
+            unsupported(node, "matmul operand must be a transposed 2-d weight")
+        w = wref.base
+        C, H, W, _ = shape_of(xr)
+        wshape = w.shape if w.kind == "param" else tuple(w.tensor.shape)
+        if len(wshape) != 2 or wshape[1] != C * H * W:
+            unsupported(node, f"weight shape {wshape} does not match input features {C * H * W}")
+        if (H, W) != (1, 1) and not xr.flat:
+            unsupported(node, "Linear on a non-flattened >2-d tensor")
+        # Linear after flatten of a [C, H, W] map == 'valid' HxW convolution (NCHW flatten order
+        # (c, h, w) is exactly the conv weight layout [out, C, H, W]).
+        return emit_conv(node, xr, w, bref, H, W, 1, 1, 0, 0, wshape[0], 1, 1)
+
+    for node in gm.graph.nodes:
+        if node.op in ("placeholder", "output") or node not in live:
+            continue
+        if node.op == "get_attr":
+            env[node] = _Ref("const", tensor=getattr(gm, node.target))
+            continue
+        t = node.target
+        a = [env.get(x, x) if isinstance(x, torch.fx.Node) else x for x in node.args]
+        if t in (aten.detach.default, aten.alias.default, aten.clone.default, aten.contiguous.default):
+            env[node] = a[0]
+        elif t == aten.t.default or (t == aten.transpose.int and a[0].kind in ("param", "const")):
+            if a[0].kind not in ("param", "const"):
+                unsupported(node, "transpose of an activation")
+            env[node] = _Ref(a[0].kind + "T", base=a[0])
+        elif t == aten.convolution.default:
+            xr, wref, bref, stride, padding, dilation, transposed, _outpad, groups = a
+            if xr.kind != "act" or transposed or groups != 1 or _pair(dilation) != (1, 1):
+                unsupported(node, "only plain 2-d convolutions (groups=1, dilation=1)")
+            wshape = wref.shape if wref.kind == "param" else tuple(wref.tensor.shape)
+            if len(wshape) != 4:
+                unsupported(node, "only 2-d convolutions")
+            (sh, sw), (ph, pw) = _pair(stride), _pair(padding)
+            C, H, W, _ = shape_of(xr)
+            ho = (H + 2 * ph - wshape[2]) // sh + 1
+            wo = (W + 2 * pw - wshape[3]) // sw + 1
+            env[node] = emit_conv(node, xr, wref, bref, wshape[2], wshape[3], sh, sw, ph, pw, wshape[0],
+                                  ho, wo)
+        elif t == aten.addmm.default:
+            bref, xr, wref = a[0], a[1], a[2]
+            if xr.kind != "act" or bref.kind not in ("param", "const"):
+                unsupported(node)
+            env[node] = emit_linear(node, xr, wref, bref)
+        elif t == aten.mm.default:
+            xr, wref = a[0], a[1]
+            if xr.kind != "act":
+                unsupported(node)
+            env[node] = emit_linear(node, xr, wref, None)
+        elif t in (aten.native_batch_norm.default, aten._native_batch_norm_legit_no_training.default,
+                   aten._native_batch_norm_legit.default, aten.cudnn_batch_norm.default):
+            if t == aten._native_batch_norm_legit_no_training.default:
+                xr, wref, bref, rm, rv, _mom, eps = a
+                training = False
+            elif t == aten.cudnn_batch_norm.default:
+                xr, wref, bref, rm, rv, training, _mom, eps = a
+            else:
+                xr, wref, bref, rm, rv, training, _mom, eps = a
+            if training or rm is None or rv is None:
+                raise NotImplementedError(
+                    "BatchNorm in training mode couples the samples of a mini-batch; put the model in"
+                    " eval() mode (the reference's determinism check rejects it as well)."
+                )
+            p0, c0 = weight_slots(wref)
+            p1, c1 = weight_slots(bref)
+            C, H, W, _ = shape_of(xr)
+            tan = tan_of(xr) or p0 >= 0 or p1 >= 0
+            ov = prog.add_value(C, H, W, tan)
+            prog.add_node(capi.OP_AFFINE, in0=xr.value, out=ov, p0=p0, p1=p1, c0=c0, c1=c1,
+                          c2=prog.add_const(rm.tensor), c3=prog.add_const(rv.tensor), eps=float(eps))
+            env[node] = _Ref("tuple", items=[_Ref("act", value=ov, flat=False), None, None])
+        elif t.__name__ == "getitem" or str(t) == "<built-in function getitem>":
+            src, idx = a
+            if src.kind != "tuple":
+                unsupported(node)
+            env[node] = src.items[idx]
+        elif t in (aten.relu.default, aten.sigmoid.default, aten.tanh.default):
+            xr = a[0]
+            op = {aten.relu.default: capi.OP_RELU, aten.sigmoid.default: capi.OP_SIGMOID,
+                  aten.tanh.default: capi.OP_TANH}[t]
+            C, H, W, tan = shape_of(xr)
+            ov = prog.add_value(C, H, W, tan)
+            prog.add_node(op, in0=xr.value, out=ov)
+            env[node] = _Ref("act", value=ov, flat=xr.flat)
+        elif t == aten.add.Tensor:
+            xr, yr = a[0], a[1]
+            alpha = node.kwargs.get("alpha", 1)
+            if not (isinstance(xr, _Ref) and isinstance(yr, _Ref) and xr.kind == yr.kind == "act") \
+                    or alpha != 1 or shape_of(xr)[:3] != shape_of(yr)[:3]:
+                unsupported(node, "only additions of two activations of equal shape")
+            C, H, W, _ = shape_of(xr)
+            ov = prog.add_value(C, H, W, tan_of(xr, yr))
+            prog.add_node(capi.OP_ADD, in0=xr.value, in1=yr.value, out=ov)
+            env[node] = _Ref("act", value=ov, flat=xr.flat)
+        elif t == aten.max_pool2d_with_indices.default:
+            xr = a[0]
+            ks = _pair(a[1])
+            st = _pair(a[2]) if len(a) > 2 and a[2] else ks
+            pd = _pair(a[3]) if len(a) > 3 else (0, 0)
+            if len(a) > 4 and _pair(a[4]) != (1, 1) or (len(a) > 5 and a[5]):
+                unsupported(node, "dilated / ceil_mode pooling")
+            C, H, W, tan = shape_of(xr)
+            ho = (H + 2 * pd[0] - ks[0]) // st[0] + 1
+            wo = (W + 2 * pd[1] - ks[1]) // st[1] + 1
+            ov = prog.add_value(C, ho, wo, tan)
+            prog.add_node(capi.OP_MAXPOOL, in0=xr.value, out=ov, kh=ks[0], kw=ks[1], sh=st[0], sw=st[1],
+                          ph=pd[0], pw=pd[1])
+            env[node] = _Ref("tuple", items=[_Ref("act", value=ov, flat=False), None])
+        elif t in (aten.mean.dim, aten._adaptive_avg_pool2d.default, aten.adaptive_avg_pool2d.default):
+            xr = a[0]
+            C, H, W, tan = shape_of(xr)
+            if t == aten.mean.dim:
+                dims = sorted(d % 4 for d in a[1])
+                if dims != [2, 3]:
+                    unsupported(node, "mean over dims other than (H, W)")
+                keep = bool(a[2]) if len(a) > 2 else False
+            else:
+                if _pair(a[1]) != (1, 1):
+                    unsupported(node, "adaptive pooling to sizes other than 1x1")
+                keep = True
+            ov = prog.add_value(C, 1, 1, tan)
+            prog.add_node(capi.OP_AVGPOOL, in0=xr.value, out=ov)
+            env[node] = _Ref("act", value=ov, flat=not keep)
+        elif t in (aten.view.default, aten._unsafe_view.default, aten.reshape.default,
+                   aten.flatten.using_ints):
+            xr = a[0]
+            if xr.kind != "act":
+                unsupported(node, "view of a parameter")
+            C, H, W, _ = shape_of(xr)
+            oshape = tuple(node.meta["val"].shape) if "val" in node.meta else None
+            if oshape is None:
+                unsupported(node, "missing shape metadata")
+            if len(oshape) == 2 and oshape[1] == C * H * W:
+                env[node] = _Ref("act", value=xr.value, flat=True)
+            elif len(oshape) == 4 and tuple(oshape[1:]) == (C, H, W):
+                env[node] = _Ref("act", value=xr.value, flat=False)
+            else:
+                unsupported(node, f"reshape to {oshape}")
+        else:
+            unsupported(node)
+
+    res = out_node.args[0]
+    if isinstance(res, (list, tuple)):
+        if len(res) != 1:
+            raise NotImplementedError("The model must return a single tensor.")
+        res = res[0]
+    ref = env[res]
+    if ref.kind != "act":
+        raise NotImplementedError("The model output must be an activation tensor.")
+    C, H, W, _ = shape_of(ref)
+    if (H, W) != (1, 1):
+        raise NotImplementedError("The B200 engine needs a 2-d prediction [batch, C].")
+    if prog.nodes[-1]["out"] != ref.value:
+        raise NotImplementedError("The model output must be produced by the last layer of the trace.")
+    prog.out_features = C
+    return prog

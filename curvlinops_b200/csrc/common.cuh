@@ -1,0 +1,61 @@
+// Shared declarations of the curvb200 engine (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace curv {
+
+// Geometry of one implicit-GEMM convolution (all tensors NHWC, channels padded to 4).
+//   source tensor  : [B][Hs][Ws][Cs]            (what is gathered)
+//   destination    : [B][Hd][Wd][Nd]            (one GEMM row per destination pixel)
+//   mode 0 (forward / wgrad gather): source pixel = dest*stride - pad + tap
+//   mode 1 (dgrad gather)          : source pixel = (dest + pad - tap)/stride, if divisible
+struct Geom {
+  int B, Hs, Ws, Cs;
+  int Hd, Wd;
+  int KH, KW, sh, sw, ph, pw;
+  int mode;
+  int N;   // valid rows of the weight matrix (real destination channels)
+  int Nd;  // padded destination channels (row stride of the destination)
+  int Kd;  // KH*KW*Cs, reduction length
+  int M;   // B*Hd*Wd
+};
+
+// Slot algebra shared by all bilinear ops:  slot 0 = primal,  slot k>=1 = k-th tangent/cotangent.
+//   out_0 = op(A_0, W)
+//   out_k = op(A_k, W) [if A has slots]  +  op(A_0, Wt_k) [if Wt != null]
+struct GatherGemmArgs {
+  Geom g;
+  const float* A;
+  long long A_slot;
+  int a_has_slots;
+  const float* W;
+  const float* Wt;
+  long long Wt_slot;
+  const float* bias;    // [Nd] added to slot 0 (may be null)
+  const float* bias_t;  // [(k-1)*bias_slot + n] added to slot k (may be null)
+  long long bias_slot;
+  float* out;
+  long long out_slot;
+  int slot0;  // first slot computed; gridDim.y = number of slots
+  int accumulate;
+};
+
+// wgrad:  D_k[n][tap][c] = sum_m G_k[m][n] * In_0[src(m,tap)][c]   (+ G_0 * In_k in R-op mode)
+struct WgradArgs {
+  Geom g;  // mode 0 geometry of the forward conv; (Hd,Wd) is the grid of G
+  const float* G;
+  long long G_slot;
+  int Ng;  // padded channels of G
+  const float* In;
+  long long In_slot;
+  int second_seg;  // 1: add (G_0, In_k) (Hessian R-op); needs In slots
+  float* partial;  // [split][nslots][N][Kd]
+  int nsplit, nslots, slot0;
+  int m_per_split;
+};
+
+inline __host__ __device__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline __host__ __device__ int pad4(int c) { return (c + 3) & ~3; }
+
+}  // namespace curv

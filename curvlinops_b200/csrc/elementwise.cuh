@@ -1,0 +1,583 @@
+// Streaming (HBM-bound) kernels of the layer program: layout conversion, parameter packing,
+// BatchNorm(eval)/activation/pooling/residual forward+tangent and adjoint passes, loss-Hessian
+// apply and the deterministic finishing reductions.  All tensors are [slot][rows][Cp] fp32 with
+// Cp % 4 == 0, so every access is a coalesced float4.
+#pragma once
+#include "common.cuh"
+
+namespace curv {
+
+enum ActKind { ACT_RELU = 0, ACT_SIGMOID = 1, ACT_TANH = 2 };
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+// ------------------------------------------------------------------ layout / packing
+// X [B][C][H][W] -> out [B][H][W][Cp]
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int C,
+                                    int H, int W, int Cp) {
+  long long total = (long long)B * H * W * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long long pix = i / Cp;
+    int w = (int)(pix % W);
+    long long r = pix / W;
+    int h = (int)(r % H);
+    int b = (int)(r / H);
+    out[i] = c < C ? __ldg(X + (((long long)b * C + c) * H + h) * W + w) : 0.f;
+  }
+}
+
+// out[b][c][k] (ldk) <- act[slot k][b][c]   (JVP output)
+__global__ void export_pred_kernel(const float* __restrict__ act, long long slot_stride, int slot0,
+                                   float* __restrict__ out, int B, int C, int Cp, int K, int ldk, int k0) {
+  long long total = (long long)B * C * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    long long r = i / K;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    out[((long long)b * C + c) * ldk + k0 + k] = act[(slot0 + k) * slot_stride + (long long)b * Cp + c];
+  }
+}
+// act[slot k][b][c] <- in[b][c][k]  (VJP seed), pad lanes zeroed
+__global__ void import_pred_kernel(float* __restrict__ act, long long slot_stride, int slot0,
+                                   const float* __restrict__ in, int B, int C, int Cp, int K, int ldk, int k0) {
+  long long total = (long long)B * Cp * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long long r = i / Cp;
+    int b = (int)(r % B);
+    int k = (int)(r / B);
+    act[(slot0 + k) * slot_stride + (long long)b * Cp + c] =
+        c < C ? __ldg(in + ((long long)b * C + c) * ldk + k0 + k) : 0.f;
+  }
+}
+
+// Weight [N][C][KH][KW] (element stride `es`, e.g. ldk for a column of V) ->
+//   Wk [n][tap][cp]   (rows = N,  row length = taps*Cp)      if transposed == 0
+//   Wt [c][tap][np]   (rows = C,  row length = taps*Np)      if transposed == 1
+// grid.y = column index k (src += k, dst += k*dst_slot)
+__global__ void pack_weight_kernel(const float* __restrict__ src, long long es, float* __restrict__ dst,
+                                   long long dst_slot, int N, int C, int KH, int KW, int Cp, int Np,
+                                   int transposed) {
+  const int taps = KH * KW;
+  const long long total = transposed ? (long long)C * taps * Np : (long long)N * taps * Cp;
+  src += blockIdx.y;
+  dst += blockIdx.y * dst_slot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n, c, tap;
+    if (!transposed) {
+      c = (int)(i % Cp); long long r = i / Cp; tap = (int)(r % taps); n = (int)(r / taps);
+    } else {
+      n = (int)(i % Np); long long r = i / Np; tap = (int)(r % taps); c = (int)(r / taps);
+    }
+    float v = 0.f;
+    if (n < N && c < C) v = __ldg(src + (((long long)n * C + c) * taps + tap) * es);
+    dst[i] = v;
+  }
+}
+
+// vector [n] (element stride es) -> dst[k][Np] zero padded.  grid.y = k
+__global__ void pack_vec_kernel(const float* __restrict__ src, long long es, float* __restrict__ dst,
+                                long long dst_slot, int N, int Np) {
+  src += blockIdx.y;
+  dst += blockIdx.y * dst_slot;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x)
+    dst[i] = i < N ? __ldg(src + (long long)i * es) : 0.f;
+}
+
+// BatchNorm(eval) coefficients.  coef layout: [(1+K)][2][Cp]:
+//   slot 0: (s, t) with s = gamma*invstd, t = beta - mean*s
+//   slot k: (sdot_k, tdot_k) = (gdot_k*invstd, bdot_k - mean*sdot_k)
+// aux [2][Cp] = (invstd, mean).   gamma/beta null -> 1 / 0.  gdot/bdot: columns of V (stride ldk).
+__global__ void affine_prep_kernel(const float* gamma, const float* beta, const float* mean,
+                                   const float* var, float eps, const float* gdot, const float* bdot,
+                                   long long ldk, int K, int C, int Cp, float* coef, float* aux) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Cp; c += gridDim.x * blockDim.x) {
+    float invstd = 0.f, mu = 0.f, s = 0.f, tt = 0.f;
+    if (c < C) {
+      invstd = 1.0f / sqrtf(var[c] + eps);
+      mu = mean[c];
+      float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      s = g * invstd;
+      tt = b - mu * s;
+    }
+    coef[c] = s; coef[Cp + c] = tt;
+    aux[c] = invstd; aux[Cp + c] = mu;
+    for (int k = 0; k < K; ++k) {
+      float sd = 0.f, td = 0.f;
+      if (c < C) {
+        sd = gdot ? gdot[(long long)c * ldk + k] * invstd : 0.f;
+        td = (bdot ? bdot[(long long)c * ldk + k] : 0.f) - mu * sd;
+      }
+      coef[(long long)(1 + k) * 2 * Cp + c] = sd;
+      coef[(long long)(1 + k) * 2 * Cp + Cp + c] = td;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward + tangent
+// y_0 = s*x_0 + t ;  y_k = s*x_k + sdot_k*x_0 + tdot_k     grid.y = slot
+__global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
+                                  const float* __restrict__ coef, int coef_has_tan,
+                                  float* __restrict__ y, long long y_slot, long long rows, int Cp) {
+  const int slot = blockIdx.y;
+  const int C4 = Cp >> 2;
+  const long long total = rows * C4;
+  const float4* x0 = reinterpret_cast<const float4*>(x);
+  const float4* xk = reinterpret_cast<const float4*>(x + slot * x_slot);
+  float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
+  const float4* s4 = reinterpret_cast<const float4*>(coef);
+  const float4* t4 = reinterpret_cast<const float4*>(coef + Cp);
+  const float4* sd4 = reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp);
+  const float4* td4 = reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp + Cp);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    float4 r;
+    if (slot == 0) {
+      r = f4fma(__ldg(s4 + c4), __ldg(x0 + i), __ldg(t4 + c4));
+    } else {
+      r = f4zero();
+      if (x_has_slots) r = f4mul(__ldg(s4 + c4), __ldg(xk + i));
+      if (coef_has_tan) r = f4add(r, f4fma(__ldg(sd4 + c4), __ldg(x0 + i), __ldg(td4 + c4)));
+    }
+    yo[i] = r;
+  }
+}
+
+__device__ __forceinline__ float act_apply(int kind, float x) {
+  if (kind == ACT_RELU) return fmaxf(x, 0.f);
+  if (kind == ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  return tanhf(x);
+}
+// derivative expressed through the OUTPUT y = phi(x)
+__device__ __forceinline__ float act_d1(int kind, float y) {
+  if (kind == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (kind == ACT_SIGMOID) return y * (1.f - y);
+  return 1.f - y * y;
+}
+__device__ __forceinline__ float act_d2(int kind, float y) {
+  if (kind == ACT_RELU) return 0.f;
+  if (kind == ACT_SIGMOID) return y * (1.f - y) * (1.f - 2.f * y);
+  return -2.f * y * (1.f - y * y);
+}
+
+// y_0 = phi(x_0);  y_k = phi'(x_0) * x_k.   Slot 0 must be computed before slots >= 1:
+// launch 1 handles slot 0 (grid.y = 1, slot0 = 0), launch 2 the tangents (slot0 = 1).
+__global__ void act_fwd_kernel(int kind, const float* __restrict__ x, long long x_slot,
+                               float* __restrict__ y, long long y_slot, long long n4, int slot0) {
+  const int slot = slot0 + blockIdx.y;
+  const float4* xs = reinterpret_cast<const float4*>(x + slot * x_slot);
+  const float4* y0 = reinterpret_cast<const float4*>(y);
+  float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(xs + i);
+    if (slot == 0) {
+      v = make_float4(act_apply(kind, v.x), act_apply(kind, v.y), act_apply(kind, v.z), act_apply(kind, v.w));
+    } else {
+      float4 p = y0[i];
+      v = make_float4(v.x * act_d1(kind, p.x), v.y * act_d1(kind, p.y), v.z * act_d1(kind, p.z),
+                      v.w * act_d1(kind, p.w));
+    }
+    yo[i] = v;
+  }
+}
+
+// gx_k (+)= phi'(y_0) * gy_k   [+ phi''(y_0) * xdot_k * gy_0  (R-op, slot >= 1, kind != relu)]
+__global__ void act_bwd_kernel(int kind, const float* __restrict__ gy, long long gy_slot,
+                               const float* __restrict__ y0, float* __restrict__ gx, long long gx_slot,
+                               const float* __restrict__ xdot, long long xdot_slot,
+                               long long n4, int slot0, int accumulate) {
+  const int slot = slot0 + blockIdx.y;
+  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+  const float4* g0 = reinterpret_cast<const float4*>(gy);
+  const float4* p4 = reinterpret_cast<const float4*>(y0);
+  const float4* xd = xdot ? reinterpret_cast<const float4*>(xdot + slot * xdot_slot) : nullptr;
+  float4* o = reinterpret_cast<float4*>(gx + slot * gx_slot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(g + i), p = __ldg(p4 + i);
+    float4 r = make_float4(v.x * act_d1(kind, p.x), v.y * act_d1(kind, p.y), v.z * act_d1(kind, p.z),
+                           v.w * act_d1(kind, p.w));
+    if (xd != nullptr && slot > 0 && kind != ACT_RELU) {
+      float4 d = __ldg(xd + i), q = __ldg(g0 + i);
+      r.x += act_d2(kind, p.x) * d.x * q.x; r.y += act_d2(kind, p.y) * d.y * q.y;
+      r.z += act_d2(kind, p.z) * d.z * q.z; r.w += act_d2(kind, p.w) * d.w * q.w;
+    }
+    if (accumulate) r = f4add(r, o[i]);
+    o[i] = r;
+  }
+}
+
+// dst_slot (+)= scale * src_slot  (residual add forward/backward, copies).  grid.y = slot
+__global__ void axpy_slots_kernel(const float* __restrict__ src, long long src_slot,
+                                  float* __restrict__ dst, long long dst_slot, long long n4, int slot0,
+                                  float scale, int accumulate) {
+  const int slot = slot0 + blockIdx.y;
+  const float4* s = reinterpret_cast<const float4*>(src + slot * src_slot);
+  float4* d = reinterpret_cast<float4*>(dst + slot * dst_slot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(s + i);
+    v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    if (accumulate) v = f4add(v, d[i]);
+    d[i] = v;
+  }
+}
+
+__global__ void zero_slots_kernel(float* __restrict__ dst, long long dst_slot, long long n4, int slot0) {
+  float4* d = reinterpret_cast<float4*>(dst + (slot0 + blockIdx.y) * dst_slot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    d[i] = f4zero();
+}
+
+// max pooling: slot 0 computes max + argmax tap (uint8 per element); slot k gathers x_k[argmax].
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot, float* __restrict__ y,
+                                   long long y_slot, unsigned char* __restrict__ idx, int B, int Hs,
+                                   int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh, int sw, int ph,
+                                   int pw, int slot0) {
+  const int slot = slot0 + blockIdx.y;
+  const float* xs = x + slot * x_slot;
+  float* ys = y + slot * y_slot;
+  const long long total = (long long)B * Hd * Wd * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long long pix = i / Cp;
+    int wd = (int)(pix % Wd);
+    long long r = pix / Wd;
+    int hd = (int)(r % Hd);
+    int b = (int)(r / Hd);
+    if (slot == 0) {
+      float best = -INFINITY;
+      int bi = 255;
+      for (int kh = 0; kh < KH; ++kh) {
+        int hs = hd * sh - ph + kh;
+        if (hs < 0 || hs >= Hs) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          int ws = wd * sw - pw + kw;
+          if (ws < 0 || ws >= Ws) continue;
+          float v = __ldg(xs + (((long long)b * Hs + hs) * Ws + ws) * Cp + c);
+          if (v > best || bi == 255) { best = v; bi = kh * KW + kw; }
+        }
+      }
+      ys[i] = best;
+      idx[i] = (unsigned char)bi;
+    } else {
+      int bi = idx[i];
+      int kh = bi / KW, kw = bi - kh * KW;
+      int hs = hd * sh - ph + kh, ws = wd * sw - pw + kw;
+      ys[i] = __ldg(xs + (((long long)b * Hs + hs) * Ws + ws) * Cp + c);
+    }
+  }
+}
+
+// gx[pixel] (+)= sum over output windows whose argmax is this pixel of gy (gather form: deterministic)
+__global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                   float* __restrict__ gx, long long gx_slot,
+                                   const unsigned char* __restrict__ idx, int B, int Hs, int Ws, int Hd,
+                                   int Wd, int Cp, int KH, int KW, int sh, int sw, int ph, int pw,
+                                   int slot0, int accumulate) {
+  const int slot = slot0 + blockIdx.y;
+  const float* g = gy + slot * gy_slot;
+  float* o = gx + slot * gx_slot;
+  const long long total = (long long)B * Hs * Ws * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long long pix = i / Cp;
+    int ws = (int)(pix % Ws);
+    long long r = pix / Ws;
+    int hs = (int)(r % Hs);
+    int b = (int)(r / Hs);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      int th = hs + ph - kh;
+      if (th < 0 || th % sh != 0) continue;
+      int hd = th / sh;
+      if (hd >= Hd) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        int tw = ws + pw - kw;
+        if (tw < 0 || tw % sw != 0) continue;
+        int wd = tw / sw;
+        if (wd >= Wd) continue;
+        long long oi = (((long long)b * Hd + hd) * Wd + wd) * Cp + c;
+        if (idx[oi] == kh * KW + kw) acc += __ldg(g + oi);
+      }
+    }
+    if (accumulate) acc += o[i];
+    o[i] = acc;
+  }
+}
+
+// global average pool: y[b][c] = mean_{hw} x[b][hw][c].  one thread per (b, c4).  grid.y = slot
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, long long x_slot, float* __restrict__ y,
+                                   long long y_slot, int B, int HW, int Cp, int slot0) {
+  const int slot = slot0 + blockIdx.y;
+  const int C4 = Cp >> 2;
+  const float4* xs = reinterpret_cast<const float4*>(x + slot * x_slot);
+  float4* ys = reinterpret_cast<float4*>(y + slot * y_slot);
+  const float inv = 1.f / (float)HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * C4; i += gridDim.x * blockDim.x) {
+    int c4 = i % C4, b = i / C4;
+    float4 acc = f4zero();
+    for (int p = 0; p < HW; ++p) acc = f4add(acc, __ldg(xs + ((long long)b * HW + p) * C4 + c4));
+    ys[i] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                   float* __restrict__ gx, long long gx_slot, int B, int HW, int Cp,
+                                   int slot0, int accumulate) {
+  const int slot = slot0 + blockIdx.y;
+  const int C4 = Cp >> 2;
+  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+  float4* o = reinterpret_cast<float4*>(gx + slot * gx_slot);
+  const float inv = 1.f / (float)HW;
+  const long long total = (long long)B * HW * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    int b = (int)(i / ((long long)HW * C4));
+    float4 v = __ldg(g + (long long)b * C4 + c4);
+    v = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    if (accumulate) v = f4add(v, o[i]);
+    o[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ adjoint of the affine map + reductions
+// Deterministic column reduction helper: every thread owns a fixed channel group c4 = t % C4 and
+// walks rows  rl, rl+RPP, ...  of its CTA's row range; the CTA then sums its row lanes in order.
+// partial layout: [chunk][slot_idx][NV][Cp]
+//
+// affine_bwd:  gx_k (+)= s * gy_k  [+ sdot_k * gy_0 (R-op)];
+//              partial v0 = sum gy_k * xhat_0 [+ gy_0 * xdot_k * invstd (R-op)]  (gamma grad)
+//              partial v1 = sum gy_k                                             (beta grad)
+// colsum (bias grad): same kernel with coef == nullptr: only v1 is produced, gx untouched.
+__global__ void __launch_bounds__(256) affine_bwd_kernel(
+    const float* __restrict__ gy, long long gy_slot, const float* __restrict__ x0,
+    const float* __restrict__ xdot, long long xdot_slot, const float* __restrict__ coef,
+    const float* __restrict__ aux, float* __restrict__ gx, long long gx_slot, int write_gx,
+    float* __restrict__ partial, int want_partial, long long rows, int Cp, int rows_per_cta,
+    int slot0, int nslots, int rop, int accumulate) {
+  extern __shared__ float red[];  // [RPP][2][ctile*4]
+  const int C4 = Cp >> 2;
+  const int ctile4 = min(C4, 256);
+  const int RPP = 256 / ctile4;
+  const int t = threadIdx.x;
+  const int rl = t / ctile4, cl = t - rl * ctile4;
+  const bool active = rl < RPP;
+  const int slot_idx = blockIdx.y;
+  const int slot = slot0 + slot_idx;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+  const float4* g0 = reinterpret_cast<const float4*>(gy);
+  const float4* xp = reinterpret_cast<const float4*>(x0);
+  const float4* xd = (rop && xdot) ? reinterpret_cast<const float4*>(xdot + slot * xdot_slot) : nullptr;
+  float4* o = write_gx ? reinterpret_cast<float4*>(gx + slot * gx_slot) : nullptr;
+  for (int cbase = 0; cbase < C4; cbase += ctile4) {
+    const int c4 = cbase + cl;
+    const bool cok = active && c4 < C4;
+    float4 s = f4zero(), sd = f4zero(), istd = f4zero(), mu = f4zero();
+    if (cok && coef) {
+      s = __ldg(reinterpret_cast<const float4*>(coef) + c4);
+      istd = __ldg(reinterpret_cast<const float4*>(aux) + c4);
+      mu = __ldg(reinterpret_cast<const float4*>(aux + Cp) + c4);
+      if (rop && slot > 0) sd = __ldg(reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp) + c4);
+    }
+    float4 a0 = f4zero(), a1 = f4zero();
+    if (cok) {
+      for (long long r = r0 + rl; r < r1; r += RPP) {
+        long long i = r * C4 + c4;
+        float4 v = __ldg(g + i);
+        a1 = f4add(a1, v);
+        if (coef) {
+          float4 xv = __ldg(xp + i);
+          float4 xh = make_float4((xv.x - mu.x) * istd.x, (xv.y - mu.y) * istd.y, (xv.z - mu.z) * istd.z,
+                                  (xv.w - mu.w) * istd.w);
+          a0 = f4fma(v, xh, a0);
+          float4 rr = f4mul(s, v);
+          if (rop && slot > 0) {
+            float4 q = __ldg(g0 + i);
+            rr = f4fma(sd, q, rr);
+            if (xd) a0 = f4fma(q, f4mul(__ldg(xd + i), istd), a0);
+          }
+          if (o) {
+            if (accumulate) rr = f4add(rr, o[i]);
+            o[i] = rr;
+          }
+        }
+      }
+    }
+    if (want_partial) {
+      // ordered in-CTA reduction over row lanes
+      if (active) {
+        float* r0p = red + ((rl * 2 + 0) * ctile4 + cl) * 4;
+        float* r1p = red + ((rl * 2 + 1) * ctile4 + cl) * 4;
+        r0p[0] = a0.x; r0p[1] = a0.y; r0p[2] = a0.z; r0p[3] = a0.w;
+        r1p[0] = a1.x; r1p[1] = a1.y; r1p[2] = a1.z; r1p[3] = a1.w;
+      }
+      __syncthreads();
+      if (rl == 0 && cok) {
+        float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+        for (int q = 0; q < RPP; ++q)
+          for (int e = 0; e < 4; ++e) {
+            s0[e] += red[((q * 2 + 0) * ctile4 + cl) * 4 + e];
+            s1[e] += red[((q * 2 + 1) * ctile4 + cl) * 4 + e];
+          }
+        float* pp = partial + (((long long)blockIdx.x * nslots + slot_idx) * 2) * Cp;
+        for (int e = 0; e < 4; ++e) { pp[c4 * 4 + e] = s0[e]; pp[Cp + c4 * 4 + e] = s1[e]; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// out[(off + c)*ldk + k0 + k] += alpha * sum_chunks partial[chunk][k][which][c]
+// (slot indices kskip .. nslots-1 of the partial buffer map to columns 0 .. nslots-kskip-1)
+__global__ void vec_grad_finish_kernel(const float* __restrict__ partial, int nchunks, int nslots,
+                                       int kskip, int which, int C, int Cp, float* __restrict__ out,
+                                       long long off, int ldk, int k0, float alpha) {
+  int nk = nslots - kskip;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * nk) return;
+  int k = i % nk, c = i / nk;
+  float s = 0.f;
+  for (int ch = 0; ch < nchunks; ++ch)
+    s += partial[(((long long)ch * nslots + kskip + k) * 2 + which) * Cp + c];
+  out[(off + c) * ldk + k0 + k] += alpha * s;
+}
+
+// out[(off + ((n*C + c)*taps + tap))*ldk + k0 + k] += alpha * sum_splits partial[split][k][n][tap][cp]
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nsplit, int nslots,
+                                    int kskip, int N, int C, int Cp, int taps, float* __restrict__ out,
+                                    long long off, int ldk, int k0, float alpha) {
+  const long long per = (long long)N * taps * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    if (c >= C) continue;
+    long long r = i / Cp;
+    int tap = (int)(r % taps);
+    int n = (int)(r / taps);
+    float* o = out + (off + ((long long)n * C + c) * taps + tap) * ldk + k0;
+    for (int k = kskip; k < nslots; ++k) {
+      float s = 0.f;
+      for (int sp = 0; sp < nsplit; ++sp) s += __ldg(partial + ((long long)sp * nslots + k) * per + i);
+      o[k - kskip] += alpha * s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ loss Hessian apply
+// One CTA (128 threads) per sample.  f = logits slot 0 [B][Cp]; u_k = slot k (Jv); result written to
+// g (+ slot stride) slot k in place of the tangent:   hu_k = scale * (p*u - p*(p.u))      (CE)
+//                                                     hu_k = 2*scale*u                     (MSE)
+//                                                     hu_k = scale*s(1-s)*u                (BCE)
+//                                                     hu_k = scale * sum_m g_m (g_m . u)   (MC)
+// Hessian mode additionally writes slot 0 of g: dl/df = scale*(p - onehot(y)) etc.
+__device__ __forceinline__ float block_reduce_sum128(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0] + sh[1] + sh[2] + sh[3];
+  return r;
+}
+__device__ __forceinline__ float block_reduce_max128(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fmaxf(fmaxf(sh[0], sh[1]), fmaxf(sh[2], sh[3]));
+}
+
+__global__ void __launch_bounds__(128) loss_hessian_kernel(
+    int loss, int mc_samples, const float* __restrict__ f, const float* __restrict__ u,
+    long long u_slot, float* __restrict__ g, long long g_slot, const void* __restrict__ y,
+    const float* __restrict__ mc_grad, int C, int Cp, int K, float scale, int write_grad0) {
+  __shared__ float sh[4];
+  extern __shared__ float prob[];  // [Cp]
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* fb = f + (long long)b * Cp;
+  if (loss == 0 /*CE*/) {
+    float mx = -INFINITY;
+    for (int c = t; c < C; c += 128) mx = fmaxf(mx, fb[c]);
+    mx = block_reduce_max128(mx, sh);
+    float sum = 0.f;
+    for (int c = t; c < C; c += 128) { float e = expf(fb[c] - mx); prob[c] = e; sum += e; }
+    sum = block_reduce_sum128(sum, sh);
+    float inv = 1.f / sum;
+    for (int c = t; c < C; c += 128) prob[c] *= inv;
+  } else if (loss == 2 /*BCE*/) {
+    for (int c = t; c < C; c += 128) prob[c] = 1.f / (1.f + expf(-fb[c]));
+  }
+  __syncthreads();
+  if (write_grad0) {
+    float* g0 = g + (long long)b * Cp;
+    if (loss == 0) {
+      long long lab = reinterpret_cast<const long long*>(y)[b];
+      for (int c = t; c < Cp; c += 128) g0[c] = c < C ? scale * (prob[c] - (c == lab ? 1.f : 0.f)) : 0.f;
+    } else if (loss == 1) {
+      const float* yb = reinterpret_cast<const float*>(y) + (long long)b * C;
+      for (int c = t; c < Cp; c += 128) g0[c] = c < C ? 2.f * scale * (fb[c] - yb[c]) : 0.f;
+    } else {
+      const float* yb = reinterpret_cast<const float*>(y) + (long long)b * C;
+      for (int c = t; c < Cp; c += 128) g0[c] = c < C ? scale * (prob[c] - yb[c]) : 0.f;
+    }
+  }
+  for (int k = 1; k <= K; ++k) {
+    const float* uk = u + k * u_slot + (long long)b * Cp;
+    float* gk = g + k * g_slot + (long long)b * Cp;
+    if (mc_samples > 0) {
+      // rank-M estimate; accumulate into registers per channel owned by this thread
+      // (C <= 128*8 channels per thread loop handled generically through a second pass)
+      // NOTE: u_k and g_k alias in GGN mode, so all dots are computed before any write.
+      // dots for all m are computed first and kept in shared memory (M <= 32).
+      __shared__ float dots[32];
+      for (int m = 0; m < mc_samples; ++m) {
+        const float* gm = mc_grad + ((long long)b * mc_samples + m) * C;
+        float d = 0.f;
+        for (int c = t; c < C; c += 128) d += gm[c] * uk[c];
+        d = block_reduce_sum128(d, sh);
+        if (t == 0) dots[m] = d;
+      }
+      __syncthreads();
+      for (int c = t; c < Cp; c += 128) {
+        float r = 0.f;
+        if (c < C)
+          for (int m = 0; m < mc_samples; ++m) r += mc_grad[((long long)b * mc_samples + m) * C + c] * dots[m];
+        gk[c] = scale * r;
+      }
+    } else if (loss == 0) {
+      float d = 0.f;
+      for (int c = t; c < C; c += 128) d += prob[c] * uk[c];
+      d = block_reduce_sum128(d, sh);
+      for (int c = t; c < Cp; c += 128) gk[c] = c < C ? scale * prob[c] * (uk[c] - d) : 0.f;
+    } else if (loss == 1) {
+      for (int c = t; c < Cp; c += 128) gk[c] = c < C ? 2.f * scale * uk[c] : 0.f;
+    } else {
+      for (int c = t; c < Cp; c += 128) gk[c] = c < C ? scale * prob[c] * (1.f - prob[c]) * uk[c] : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace curv

@@ -1,0 +1,740 @@
+// curvb200 engine: layer program, workspace plan and the two fused sweeps
+//   forward + Jv      (primal slot 0, tangent slots 1..K)
+//   backward + J^T    (cotangent slots 1..K, written over the dead tangents in GGN mode)
+// behind the C ABI of include/curvb200.h.  Host code only plans and launches; all arithmetic is in the
+// kernels of gemm_simt.cuh / tc_gemm.cuh / elementwise.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/curvb200.h"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "tc_gemm.cuh"
+
+using namespace curv;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static long long g_launches = 0;
+static int g_tc_mode = 1;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CHECK_CUDA(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(CURV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+#define LAUNCH_CHECK()                                                                        \
+  do {                                                                                        \
+    ++g_launches;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(CURV_ERR_CUDA, std::string("kernel launch failed at ") + __FILE__ + ":" +   \
+                                     std::to_string(__LINE__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline int grid1d(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Value {
+  int C, Cp, H, W;
+  bool tan;
+  long long slot_elems;  // B*H*W*Cp
+  int nslots;
+  long long act_off;   // float offset in the workspace
+  long long grad_off;  // == act_off in GGN mode
+};
+
+struct Node {
+  curv_node_desc d;
+  // CONV
+  Geom fwd, dgr;
+  long long wk_off = -1, wt_off = -1, wkt_off = -1, wtt_off = -1;  // packed weight, transposed, tangents
+  long long wsize = 0, wtsize = 0;
+  long long bias_off = -1, biast_off = -1;
+  int nsplit = 1, m_per_split = 0;
+  int wbm = 64, wbn = 64;
+  // AFFINE
+  long long coef_off = -1, aux_off = -1;
+  int rows_per_cta = 0, nchunks = 0;
+  // MAXPOOL
+  long long idx_off = -1;  // float offset
+};
+
+struct curv_program {
+  int B, kmax, hessian;
+  std::vector<Value> values;
+  std::vector<Node> nodes;
+  std::vector<curv_param_desc> params;
+  long long scratch_off = 0, scratch_elems = 0;
+  size_t ws_bytes = 0;
+};
+
+static long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
+extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
+extern "C" long long curv_launch_count(void) { return g_launches; }
+extern "C" int curv_set_tensor_core_mode(int mode) {
+  int old = g_tc_mode;
+  g_tc_mode = mode;
+  return old;
+}
+
+extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
+                                   const curv_node_desc* nodes, int n_nodes,
+                                   const curv_param_desc* params, int n_params, int batch, int kmax,
+                                   int hessian, curv_program** out) {
+  if (!values || !nodes || !out || n_values < 1 || n_nodes < 1 || batch < 1 || kmax < 1 || kmax > 32)
+    return fail(CURV_ERR_INVALID, "curv_program_create: bad arguments (need 1 <= kmax <= 32)");
+  auto* P = new curv_program();
+  P->B = batch; P->kmax = kmax; P->hessian = hessian;
+  P->params.assign(params, params + n_params);
+  long long off = 0;  // in floats
+  auto alloc = [&](long long elems) { long long o = off; off = align_up(off + elems, 64); return o; };
+  for (int i = 0; i < n_values; ++i) {
+    Value v;
+    v.C = values[i].C; v.H = values[i].H; v.W = values[i].W; v.Cp = pad4(v.C);
+    v.tan = values[i].has_tangent != 0;
+    if (v.C < 1 || v.H < 1 || v.W < 1) { delete P; return fail(CURV_ERR_INVALID, "bad value shape"); }
+    v.slot_elems = (long long)batch * v.H * v.W * v.Cp;
+    v.nslots = v.tan ? 1 + kmax : 1;
+    v.act_off = alloc(v.slot_elems * v.nslots);
+    v.grad_off = (hessian && v.tan) ? alloc(v.slot_elems * v.nslots) : v.act_off;
+    P->values.push_back(v);
+  }
+  long long scratch = 64;
+  for (int i = 0; i < n_nodes; ++i) {
+    Node n;
+    n.d = nodes[i];
+    const curv_node_desc& d = n.d;
+    auto bad_id = [&](int id) { return id < 0 || id >= n_values; };
+    if (d.op != CURV_OP_INPUT && (bad_id(d.in0) || bad_id(d.out))) {
+      delete P; return fail(CURV_ERR_INVALID, "node references an unknown value");
+    }
+    if (d.op == CURV_OP_CONV) {
+      const Value& vi = P->values[d.in0];
+      const Value& vo = P->values[d.out];
+      Geom g;
+      g.B = batch; g.Hs = vi.H; g.Ws = vi.W; g.Cs = vi.Cp; g.Hd = vo.H; g.Wd = vo.W;
+      g.KH = d.kh; g.KW = d.kw; g.sh = d.sh; g.sw = d.sw; g.ph = d.ph; g.pw = d.pw; g.mode = 0;
+      g.N = vo.C; g.Nd = vo.Cp; g.Kd = d.kh * d.kw * vi.Cp; g.M = batch * vo.H * vo.W;
+      if ((vi.H + 2 * d.ph - d.kh) / d.sh + 1 != vo.H || (vi.W + 2 * d.pw - d.kw) / d.sw + 1 != vo.W) {
+        delete P; return fail(CURV_ERR_INVALID, "conv geometry does not match value shapes");
+      }
+      n.fwd = g;
+      Geom q = g;  // dgrad: source = grad of out, destination = grad of in
+      q.Hs = vo.H; q.Ws = vo.W; q.Cs = vo.Cp; q.Hd = vi.H; q.Wd = vi.W; q.mode = 1;
+      q.N = vi.C; q.Nd = vi.Cp; q.Kd = d.kh * d.kw * vo.Cp; q.M = batch * vi.H * vi.W;
+      n.dgr = q;
+      n.wsize = (long long)g.N * g.Kd;
+      n.wtsize = (long long)q.N * q.Kd;
+      n.wk_off = alloc(n.wsize);
+      if (vi.tan) n.wt_off = alloc(n.wtsize);
+      if (d.p0 >= 0) {
+        n.wkt_off = alloc(n.wsize * kmax);
+        if (hessian && vi.tan) n.wtt_off = alloc(n.wtsize * kmax);
+      }
+      if (d.p1 >= 0 || d.c1 >= 0) n.bias_off = alloc(vo.Cp);
+      if (d.p1 >= 0) n.biast_off = alloc((long long)vo.Cp * kmax);
+      // wgrad tiling / split plan
+      if (d.p0 >= 0) {
+        n.wbm = g.N > 64 ? 128 : 64;
+        n.wbn = g.Kd > 64 ? 128 : 64;
+        int nsl = kmax + (hessian ? 1 : 0);
+        long long tiles = (long long)ceil_div(g.N, n.wbm) * ceil_div(g.Kd, n.wbn) * nsl;
+        int want = (int)((2 * 148 + tiles - 1) / tiles);
+        int maxsplit = ceil_div(g.M, 256);
+        n.nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+        if (n.nsplit > 64) n.nsplit = 64;
+        n.m_per_split = (ceil_div(g.M, n.nsplit) + 15) / 16 * 16;
+        n.nsplit = ceil_div(g.M, n.m_per_split);
+        long long need = (long long)n.nsplit * nsl * n.wsize;
+        if (need > scratch) scratch = need;
+      }
+      if (d.p1 >= 0) {  // bias grad = column sum of the output cotangent
+        long long rows = g.M;
+        n.rows_per_cta = (int)((rows + 2 * 148 - 1) / (2 * 148));
+        if (n.rows_per_cta < 64) n.rows_per_cta = 64;
+        n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
+        long long need = (long long)n.nchunks * (kmax + 1) * 2 * vo.Cp;
+        if (need > scratch) scratch = need;
+      }
+    } else if (d.op == CURV_OP_AFFINE) {
+      const Value& vi = P->values[d.in0];
+      n.coef_off = alloc((long long)(1 + kmax) * 2 * vi.Cp);
+      n.aux_off = alloc(2LL * vi.Cp);
+      long long rows = (long long)batch * vi.H * vi.W;
+      n.rows_per_cta = (int)((rows + 2 * 148 - 1) / (2 * 148));
+      if (n.rows_per_cta < 64) n.rows_per_cta = 64;
+      n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
+      long long need = (long long)n.nchunks * (kmax + 1) * 2 * vi.Cp;
+      if (need > scratch) scratch = need;
+    } else if (d.op == CURV_OP_MAXPOOL) {
+      const Value& vo = P->values[d.out];
+      n.idx_off = alloc((vo.slot_elems + 3) / 4);  // float offset of a byte buffer (1 byte per element)
+    } else if (d.op == CURV_OP_ADD) {
+      if (bad_id(d.in1)) { delete P; return fail(CURV_ERR_INVALID, "add node needs two inputs"); }
+    }
+    P->nodes.push_back(n);
+  }
+  {
+    const Value& last = P->values[P->nodes.back().d.out];
+    if (last.H != 1 || last.W != 1) {
+      delete P; return fail(CURV_ERR_UNSUPPORTED, "prediction must be [batch, C] (H = W = 1)");
+    }
+  }
+  P->scratch_elems = scratch;
+  P->scratch_off = alloc(scratch);
+  P->ws_bytes = (size_t)off * sizeof(float);
+  *out = P;
+  return CURV_OK;
+}
+
+extern "C" void curv_program_destroy(curv_program* p) { delete p; }
+extern "C" size_t curv_program_workspace_bytes(const curv_program* p) { return p ? p->ws_bytes : 0; }
+extern "C" int curv_program_value_layout(const curv_program* p, int id, size_t* byte_offset,
+                                         size_t* slot_bytes, int* cp) {
+  if (!p || id < 0 || id >= (int)p->values.size()) return fail(CURV_ERR_INVALID, "bad value id");
+  const Value& v = p->values[id];
+  if (byte_offset) *byte_offset = (size_t)v.act_off * 4;
+  if (slot_bytes) *slot_bytes = (size_t)v.slot_elems * 4;
+  if (cp) *cp = v.Cp;
+  return CURV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
+  if (nslots <= 0) return CURV_OK;
+  const Geom& g = a.g;
+  if (g_tc_mode && tc_gather_eligible(g)) {
+    int rc = tc_launch_gather_gemm(a, nslots, st);
+    if (rc == 0) { ++g_launches; return CURV_OK; }
+    if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
+    // rc < 0: not eligible after all -> SIMT
+  }
+  if (g.M >= 4096 && g.Nd > 64) {
+    dim3 grid(ceil_div(g.M, 128) * ceil_div(g.Nd, 128), nslots);
+    gather_gemm_simt<128, 128><<<grid, 256, 0, st>>>(a);
+  } else if (g.M >= 4096) {
+    dim3 grid(ceil_div(g.M, 128) * ceil_div(g.Nd, 64), nslots);
+    gather_gemm_simt<128, 64><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid(ceil_div(g.M, 64) * ceil_div(g.Nd, 64), nslots);
+    gather_gemm_simt<64, 64><<<grid, 256, 0, st>>>(a);
+  }
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
+
+static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st) {
+  const Geom& g = a.g;
+  dim3 grid(ceil_div(g.N, bm) * ceil_div(g.Kd, bn), a.nslots, a.nsplit);
+  if (bm == 128 && bn == 128) wgrad_gemm_simt<128, 128><<<grid, 256, 0, st>>>(a);
+  else if (bm == 128) wgrad_gemm_simt<128, 64><<<grid, 256, 0, st>>>(a);
+  else if (bn == 128) wgrad_gemm_simt<64, 128><<<grid, 256, 0, st>>>(a);
+  else wgrad_gemm_simt<64, 64><<<grid, 256, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
+
+struct Ctx {
+  curv_program* P;
+  float* ws;
+  const void* const* pp;  // differentiated parameter pointers
+  const void* const* cp;  // constant pointers
+  const float* V;
+  float* out;
+  int K, ldk, k0;
+  float alpha;
+  cudaStream_t st;
+  int kind;
+  bool rop;  // Hessian R-op: slot 0 of the cotangent storage holds the plain backward
+  float* act(int v, int slot = 0) const {
+    const Value& x = P->values[v];
+    return ws + x.act_off + (long long)slot * x.slot_elems;
+  }
+  float* grad(int v, int slot = 0) const {
+    const Value& x = P->values[v];
+    return ws + x.grad_off + (long long)slot * x.slot_elems;
+  }
+  const float* param(int i) const { return (const float*)pp[i]; }
+  const float* cst(int i) const { return (const float*)cp[i]; }
+  const float* vcol(int p) const { return V + P->params[p].offset * ldk + k0; }
+  float* ocol(int p) const { return out + P->params[p].offset * ldk + k0; }
+};
+
+// pack parameters (and, if with_tangents, the K columns of V) into the engine's layouts
+static int prepare_params(const Ctx& c, bool with_tangents) {
+  curv_program* P = c.P;
+  cudaStream_t st = c.st;
+  for (Node& n : P->nodes) {
+    const curv_node_desc& d = n.d;
+    if (d.op == CURV_OP_CONV) {
+      const Geom& g = n.fwd;
+      const Value& vi = P->values[d.in0];
+      const float* w = d.p0 >= 0 ? c.param(d.p0) : c.cst(d.c0);
+      int Cin = vi.C;
+      pack_weight_kernel<<<dim3(grid1d(n.wsize), 1), 256, 0, st>>>(w, 1, c.ws + n.wk_off, 0, g.N, Cin, g.KH,
+                                                                  g.KW, vi.Cp, g.Nd, 0);
+      LAUNCH_CHECK();
+      if (n.wt_off >= 0) {
+        pack_weight_kernel<<<dim3(grid1d(n.wtsize), 1), 256, 0, st>>>(w, 1, c.ws + n.wt_off, 0, g.N, Cin,
+                                                                     g.KH, g.KW, vi.Cp, g.Nd, 1);
+        LAUNCH_CHECK();
+      }
+      if (with_tangents && d.p0 >= 0) {
+        pack_weight_kernel<<<dim3(grid1d(n.wsize), c.K), 256, 0, st>>>(
+            c.vcol(d.p0), c.ldk, c.ws + n.wkt_off, n.wsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 0);
+        LAUNCH_CHECK();
+        if (n.wtt_off >= 0) {
+          pack_weight_kernel<<<dim3(grid1d(n.wtsize), c.K), 256, 0, st>>>(
+              c.vcol(d.p0), c.ldk, c.ws + n.wtt_off, n.wtsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 1);
+          LAUNCH_CHECK();
+        }
+      }
+      if (n.bias_off >= 0) {
+        const float* b = d.p1 >= 0 ? c.param(d.p1) : c.cst(d.c1);
+        pack_vec_kernel<<<dim3(grid1d(g.Nd), 1), 256, 0, st>>>(b, 1, c.ws + n.bias_off, 0, g.N, g.Nd);
+        LAUNCH_CHECK();
+      }
+      if (with_tangents && n.biast_off >= 0) {
+        pack_vec_kernel<<<dim3(grid1d(g.Nd), c.K), 256, 0, st>>>(c.vcol(d.p1), c.ldk, c.ws + n.biast_off,
+                                                                g.Nd, g.N, g.Nd);
+        LAUNCH_CHECK();
+      }
+    } else if (d.op == CURV_OP_AFFINE) {
+      const Value& vi = P->values[d.in0];
+      const float* gamma = d.p0 >= 0 ? c.param(d.p0) : (d.c0 >= 0 ? c.cst(d.c0) : nullptr);
+      const float* beta = d.p1 >= 0 ? c.param(d.p1) : (d.c1 >= 0 ? c.cst(d.c1) : nullptr);
+      const float* gd = (with_tangents && d.p0 >= 0) ? c.vcol(d.p0) : nullptr;
+      const float* bd = (with_tangents && d.p1 >= 0) ? c.vcol(d.p1) : nullptr;
+      affine_prep_kernel<<<grid1d(vi.Cp), 256, 0, st>>>(gamma, beta, c.cst(d.c2), c.cst(d.c3), d.eps, gd, bd,
+                                                       c.ldk, with_tangents ? c.K : 0, vi.C, vi.Cp,
+                                                       c.ws + n.coef_off, c.ws + n.aux_off);
+      LAUNCH_CHECK();
+    }
+  }
+  return CURV_OK;
+}
+
+// forward sweep: primal only (K = 0) or primal + K tangents
+static int forward(const Ctx& c, const void* X, int K) {
+  curv_program* P = c.P;
+  cudaStream_t st = c.st;
+  for (Node& n : P->nodes) {
+    const curv_node_desc& d = n.d;
+    if (d.op == CURV_OP_INPUT) {
+      const Value& v = P->values[d.out];
+      nchw_to_nhwc_kernel<<<grid1d(v.slot_elems), 256, 0, st>>>((const float*)X, c.act(d.out), P->B, v.C,
+                                                                v.H, v.W, v.Cp);
+      LAUNCH_CHECK();
+      continue;
+    }
+    const Value& vi = P->values[d.in0];
+    const Value& vo = P->values[d.out];
+    const int nsl = (vo.tan && K > 0) ? 1 + K : 1;
+    switch (d.op) {
+      case CURV_OP_CONV: {
+        GatherGemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.g = n.fwd;
+        a.A = c.act(d.in0); a.A_slot = vi.slot_elems; a.a_has_slots = vi.tan ? 1 : 0;
+        a.W = c.ws + n.wk_off;
+        a.Wt = (d.p0 >= 0) ? c.ws + n.wkt_off : nullptr; a.Wt_slot = n.wsize;
+        a.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
+        a.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; a.bias_slot = vo.Cp;
+        a.out = c.act(d.out); a.out_slot = vo.slot_elems;
+        a.slot0 = 0; a.accumulate = 0;
+        int rc = launch_gather_gemm(a, nsl, st);
+        if (rc) return rc;
+        break;
+      }
+      case CURV_OP_AFFINE: {
+        long long rows = (long long)P->B * vi.H * vi.W;
+        affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
+            c.act(d.out), vo.slot_elems, rows, vi.Cp);
+        LAUNCH_CHECK();
+        break;
+      }
+      case CURV_OP_RELU:
+      case CURV_OP_SIGMOID:
+      case CURV_OP_TANH: {
+        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID : ACT_TANH);
+        long long n4 = vo.slot_elems / 4;
+        act_fwd_kernel<<<dim3(grid1d(n4), 1), 256, 0, st>>>(kind, c.act(d.in0), vi.slot_elems, c.act(d.out),
+                                                            vo.slot_elems, n4, 0);
+        LAUNCH_CHECK();
+        if (nsl > 1) {
+          act_fwd_kernel<<<dim3(grid1d(n4), nsl - 1), 256, 0, st>>>(kind, c.act(d.in0), vi.slot_elems,
+                                                                    c.act(d.out), vo.slot_elems, n4, 1);
+          LAUNCH_CHECK();
+        }
+        break;
+      }
+      case CURV_OP_ADD: {
+        const Value& vj = P->values[d.in1];
+        long long n4 = vo.slot_elems / 4;
+        // primal
+        axpy_slots_kernel<<<dim3(grid1d(n4), 1), 256, 0, st>>>(c.act(d.in0), vi.slot_elems, c.act(d.out),
+                                                               vo.slot_elems, n4, 0, 1.f, 0);
+        LAUNCH_CHECK();
+        axpy_slots_kernel<<<dim3(grid1d(n4), 1), 256, 0, st>>>(c.act(d.in1), vj.slot_elems, c.act(d.out),
+                                                               vo.slot_elems, n4, 0, 1.f, 1);
+        LAUNCH_CHECK();
+        if (nsl > 1) {
+          bool first = true;
+          if (vi.tan) {
+            axpy_slots_kernel<<<dim3(grid1d(n4), nsl - 1), 256, 0, st>>>(
+                c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, n4, 1, 1.f, 0);
+            LAUNCH_CHECK();
+            first = false;
+          }
+          if (vj.tan) {
+            axpy_slots_kernel<<<dim3(grid1d(n4), nsl - 1), 256, 0, st>>>(
+                c.act(d.in1), vj.slot_elems, c.act(d.out), vo.slot_elems, n4, 1, 1.f, first ? 0 : 1);
+            LAUNCH_CHECK();
+          }
+        }
+        break;
+      }
+      case CURV_OP_MAXPOOL: {
+        unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
+        maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems), 1), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
+            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 0);
+        LAUNCH_CHECK();
+        if (nsl > 1) {
+          maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems), nsl - 1), 256, 0, st>>>(
+              c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
+              vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1);
+          LAUNCH_CHECK();
+        }
+        break;
+      }
+      case CURV_OP_AVGPOOL: {
+        avgpool_fwd_kernel<<<dim3(grid1d((long long)P->B * vo.Cp / 4), nsl), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, P->B, vi.H * vi.W, vi.Cp, 0);
+        LAUNCH_CHECK();
+        break;
+      }
+      default:
+        return fail(CURV_ERR_UNSUPPORTED, "unsupported op in forward sweep");
+    }
+  }
+  return CURV_OK;
+}
+
+// backward sweep over cotangent slots [s0, s0+ns) of the grad storage.
+//   GGN / VJP: s0 = 1, ns = K.      Hessian R-op: s0 = 0, ns = K+1 (slot 0 = plain backward).
+//   param_out: accumulate parameter-space results into c.out (columns k0..k0+K-1)
+static int backward(const Ctx& c, int K) {
+  curv_program* P = c.P;
+  cudaStream_t st = c.st;
+  const bool rop = c.rop;
+  const int s0 = rop ? 0 : 1;
+  const int ns = rop ? K + 1 : K;
+  const int kskip = rop ? 1 : 0;
+  std::vector<char> ginit(P->values.size(), 0);
+  ginit[P->nodes.back().d.out] = 1;
+  float* scratch = c.ws + P->scratch_off;
+  for (int ni = (int)P->nodes.size() - 1; ni >= 0; --ni) {
+    Node& n = P->nodes[ni];
+    const curv_node_desc& d = n.d;
+    if (d.op == CURV_OP_INPUT) continue;
+    const Value& vi = P->values[d.in0];
+    const Value& vo = P->values[d.out];
+    if (!vo.tan) continue;
+    if (!ginit[d.out]) continue;  // value does not influence the prediction (dead branch)
+    switch (d.op) {
+      case CURV_OP_CONV: {
+        const Geom& g = n.fwd;
+        if (d.p0 >= 0) {  // weight gradient
+          WgradArgs a;
+          memset(&a, 0, sizeof(a));
+          a.g = g;
+          a.G = c.grad(d.out); a.G_slot = vo.slot_elems; a.Ng = vo.Cp;
+          a.In = c.act(d.in0); a.In_slot = vi.slot_elems;
+          a.second_seg = (rop && vi.tan) ? 1 : 0;
+          a.partial = scratch; a.nsplit = n.nsplit; a.nslots = ns; a.slot0 = s0;
+          a.m_per_split = n.m_per_split;
+          int rc = launch_wgrad(a, n.wbm, n.wbn, st);
+          if (rc) return rc;
+          wgrad_finish_kernel<<<grid1d(n.wsize), 256, 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
+                                                              vi.Cp, g.KH * g.KW, c.out,
+                                                              P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
+          LAUNCH_CHECK();
+        }
+        if (d.p1 >= 0) {  // bias gradient: column sums of the cotangent
+          long long rows = g.M;
+          affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
+              c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
+              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0);
+          LAUNCH_CHECK();
+          vec_grad_finish_kernel<<<ceil_div(vo.C * K, 256), 256, 0, st>>>(
+              scratch, n.nchunks, ns, kskip, 1, vo.C, vo.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
+              c.alpha);
+          LAUNCH_CHECK();
+        }
+        if (vi.tan) {  // data gradient
+          GatherGemmArgs a;
+          memset(&a, 0, sizeof(a));
+          a.g = n.dgr;
+          a.A = c.grad(d.out); a.A_slot = vo.slot_elems; a.a_has_slots = 1;
+          a.W = c.ws + n.wt_off;
+          a.Wt = (rop && n.wtt_off >= 0) ? c.ws + n.wtt_off : nullptr; a.Wt_slot = n.wtsize;
+          a.out = c.grad(d.in0); a.out_slot = vi.slot_elems;
+          a.slot0 = s0; a.accumulate = ginit[d.in0];
+          int rc = launch_gather_gemm(a, ns, st);
+          if (rc) return rc;
+          ginit[d.in0] = 1;
+        }
+        break;
+      }
+      case CURV_OP_AFFINE: {
+        long long rows = (long long)P->B * vi.H * vi.W;
+        int want_partial = (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0;
+        if (!vi.tan && !want_partial) break;
+        affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
+            c.grad(d.out), vo.slot_elems, c.act(d.in0), (rop && vi.tan) ? c.act(d.in0) : nullptr,
+            vi.slot_elems, c.ws + n.coef_off, c.ws + n.aux_off, vi.tan ? c.grad(d.in0) : nullptr,
+            vi.slot_elems, vi.tan ? 1 : 0, scratch, want_partial, rows, vi.Cp, n.rows_per_cta, s0, ns,
+            rop ? 1 : 0, ginit[d.in0]);
+        LAUNCH_CHECK();
+        if (vi.tan) ginit[d.in0] = 1;
+        if (d.p0 >= 0) {
+          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+              scratch, n.nchunks, ns, kskip, 0, vi.C, vi.Cp, c.out, P->params[d.p0].offset, c.ldk, c.k0,
+              c.alpha);
+          LAUNCH_CHECK();
+        }
+        if (d.p1 >= 0) {
+          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+              scratch, n.nchunks, ns, kskip, 1, vi.C, vi.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
+              c.alpha);
+          LAUNCH_CHECK();
+        }
+        break;
+      }
+      case CURV_OP_RELU:
+      case CURV_OP_SIGMOID:
+      case CURV_OP_TANH: {
+        if (!vi.tan) break;
+        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID : ACT_TANH);
+        long long n4 = vo.slot_elems / 4;
+        act_bwd_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(
+            kind, c.grad(d.out), vo.slot_elems, c.act(d.out), c.grad(d.in0), vi.slot_elems,
+            rop ? c.act(d.in0) : nullptr, vi.slot_elems, n4, s0, ginit[d.in0]);
+        LAUNCH_CHECK();
+        ginit[d.in0] = 1;
+        break;
+      }
+      case CURV_OP_ADD: {
+        const Value& vj = P->values[d.in1];
+        long long n4 = vo.slot_elems / 4;
+        if (vi.tan) {
+          axpy_slots_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(c.grad(d.out), vo.slot_elems, c.grad(d.in0),
+                                                                  vi.slot_elems, n4, s0, 1.f, ginit[d.in0]);
+          LAUNCH_CHECK();
+          ginit[d.in0] = 1;
+        }
+        if (vj.tan) {
+          axpy_slots_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(c.grad(d.out), vo.slot_elems, c.grad(d.in1),
+                                                                  vj.slot_elems, n4, s0, 1.f, ginit[d.in1]);
+          LAUNCH_CHECK();
+          ginit[d.in1] = 1;
+        }
+        break;
+      }
+      case CURV_OP_MAXPOOL: {
+        if (!vi.tan) break;
+        unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
+        maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems), ns), 256, 0, st>>>(
+            c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
+            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ginit[d.in0]);
+        LAUNCH_CHECK();
+        ginit[d.in0] = 1;
+        break;
+      }
+      case CURV_OP_AVGPOOL: {
+        if (!vi.tan) break;
+        avgpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems / 4), ns), 256, 0, st>>>(
+            c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, P->B, vi.H * vi.W, vi.Cp, s0,
+            ginit[d.in0]);
+        LAUNCH_CHECK();
+        ginit[d.in0] = 1;
+        break;
+      }
+      default:
+        return fail(CURV_ERR_UNSUPPORTED, "unsupported op in backward sweep");
+    }
+  }
+  return CURV_OK;
+}
+
+extern "C" int curv_matmat_batch(curv_program* P, int kind, int loss, const void* const* param_ptrs,
+                                 const void* const* const_ptrs, const void* X, const void* y,
+                                 const float* mc_grad, int mc_samples, const float* V, float* out, int K,
+                                 int ldk, int k0, float loss_scale, float alpha, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!P) return fail(CURV_ERR_INVALID, "null program");
+  if (kind != CURV_KIND_FORWARD && (K < 1 || K > P->kmax))
+    return fail(CURV_ERR_INVALID, "K must be in [1, kmax]");
+  if (workspace_bytes < P->ws_bytes || !workspace) return fail(CURV_ERR_WORKSPACE, "workspace too small");
+  if (kind == CURV_KIND_HESSIAN && !P->hessian)
+    return fail(CURV_ERR_INVALID, "program was not created with hessian=1");
+  if (kind == CURV_KIND_GGN_MC && (mc_samples < 1 || mc_samples > 32 || !mc_grad))
+    return fail(CURV_ERR_INVALID, "MC mode needs 1 <= mc_samples <= 32 and mc_grad");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CURV_ERR_CUDA, "no CUDA device: curvb200 has no CPU fallback");
+  Ctx c;
+  c.P = P; c.ws = (float*)workspace; c.pp = param_ptrs; c.cp = const_ptrs; c.V = V; c.out = out;
+  c.K = K; c.ldk = ldk; c.k0 = k0; c.alpha = alpha; c.st = (cudaStream_t)stream; c.kind = kind;
+  c.rop = kind == CURV_KIND_HESSIAN;
+  const int last = P->nodes.back().d.out;
+  const Value& vl = P->values[last];
+  int rc;
+  if (kind == CURV_KIND_FORWARD) {
+    if ((rc = prepare_params(c, false))) return rc;
+    return forward(c, X, 0);
+  }
+  if (!vl.tan) return CURV_OK;  // prediction independent of the selected parameters: zero matrix
+  if (kind == CURV_KIND_VJP) {
+    if ((rc = prepare_params(c, false))) return rc;
+    if ((rc = forward(c, X, 0))) return rc;
+    import_pred_kernel<<<grid1d((long long)P->B * vl.Cp * K), 256, 0, c.st>>>(
+        c.grad(last), vl.slot_elems, 1, V, P->B, vl.C, vl.Cp, K, ldk, k0);
+    LAUNCH_CHECK();
+    return backward(c, K);
+  }
+  if ((rc = prepare_params(c, true))) return rc;
+  if ((rc = forward(c, X, K))) return rc;
+  if (kind == CURV_KIND_JVP) {
+    export_pred_kernel<<<grid1d((long long)P->B * vl.C * K), 256, 0, c.st>>>(
+        c.act(last), vl.slot_elems, 1, out, P->B, vl.C, vl.Cp, K, ldk, k0);
+    LAUNCH_CHECK();
+    return CURV_OK;
+  }
+  loss_hessian_kernel<<<P->B, 128, vl.Cp * sizeof(float), c.st>>>(
+      loss, kind == CURV_KIND_GGN_MC ? mc_samples : 0, c.act(last), c.act(last), vl.slot_elems, c.grad(last),
+      vl.slot_elems, y, mc_grad, vl.C, vl.Cp, K, loss_scale, c.rop ? 1 : 0);
+  LAUNCH_CHECK();
+  return backward(c, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense helpers (Kronecker / eigen-basis apply)
+// ------------------------------------------------------------------------------------------------
+static int dense_gemm(int tA, int tB, int M, int N, int Kd, float alpha, const float* A, int lda,
+                      const float* B, int ldb, float beta, float* C, int ldc, int batch, long long sA,
+                      long long sB, long long sC, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return CURV_OK;
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
+  dense_gemm_simt<<<grid, 256, 0, st>>>(tA, tB, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, sA, sB, sC);
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
+
+extern "C" int curv_gemm(int transA, int transB, int M, int N, int Kd, float alpha, const float* A,
+                         int lda, const float* B, int ldb, float beta, float* C, int ldc, void* stream) {
+  return dense_gemm(transA, transB, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, 1, 0, 0, 0,
+                    (cudaStream_t)stream);
+}
+
+// X, Y: [d_out][d_in][K] (K minor).  Y = G X A^T per column.
+//   step 1: T[a][(b,z)] = sum_a' G[a][a'] X[a'][(b,z)]           plain GEMM, N = d_in*K
+//   step 2: Y[a][B][z]  = sum_b  A[B][b] T[a][b][z]              batched over a: A (d_in x d_in) @ T_a (d_in x K)
+extern "C" int curv_kron_apply(const float* G, const float* A, int d_out, int d_in, int K, const float* X,
+                               float* Y, float* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* T = X;
+  int rc;
+  if (G) {
+    float* dst = A ? tmp : Y;
+    if ((rc = dense_gemm(0, 0, d_out, d_in * K, d_out, 1.f, G, d_out, X, d_in * K, 0.f, dst, d_in * K, 1, 0, 0,
+                         0, st)))
+      return rc;
+    T = dst;
+  }
+  if (A) {
+    if ((rc = dense_gemm(0, 0, d_in, K, d_in, 1.f, A, d_in, T, K, 0.f, Y, K, d_out, 0, (long long)d_in * K,
+                         (long long)d_in * K, st)))
+      return rc;
+  } else if (!G) {
+    CHECK_CUDA(cudaMemcpyAsync(Y, X, sizeof(float) * d_out * d_in * K, cudaMemcpyDeviceToDevice, st));
+  }
+  return CURV_OK;
+}
+
+__global__ void eig_scale_kernel(float* __restrict__ T, const float* __restrict__ lam, float damping,
+                                 int inverse, long long n, int K) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * K;
+       i += (long long)gridDim.x * blockDim.x) {
+    float l = lam[i / K];
+    T[i] *= inverse ? 1.f / (l + damping) : l;
+  }
+}
+
+// Y = (Qg (x) Qa) diag(scale(lambda)) (Qg (x) Qa)^T X   with lambda [d_out][d_in]
+extern "C" int curv_eigh_apply(const float* Qg, const float* Qa, const float* lambda, float damping,
+                               int inverse, int d_out, int d_in, int K, const float* X, float* Y,
+                               float* tmp, float* tmp2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  // T1 = Qg^T X  (rows)
+  const float* cur = X;
+  if (Qg) {
+    if ((rc = dense_gemm(1, 0, d_out, d_in * K, d_out, 1.f, Qg, d_out, cur, d_in * K, 0.f, tmp, d_in * K, 1, 0,
+                         0, 0, st)))
+      return rc;
+    cur = tmp;
+  }
+  // T2_a = Qa^T T1_a
+  if (Qa) {
+    if ((rc = dense_gemm(1, 0, d_in, K, d_in, 1.f, Qa, d_in, cur, K, 0.f, tmp2, K, d_out, 0,
+                         (long long)d_in * K, (long long)d_in * K, st)))
+      return rc;
+  } else {
+    CHECK_CUDA(cudaMemcpyAsync(tmp2, cur, sizeof(float) * d_out * d_in * K, cudaMemcpyDeviceToDevice, st));
+  }
+  eig_scale_kernel<<<grid1d((long long)d_out * d_in * K), 256, 0, st>>>(tmp2, lambda, damping, inverse,
+                                                                       (long long)d_out * d_in, K);
+  LAUNCH_CHECK();
+  // back: T3_a = Qa T2_a ; Y = Qg T3
+  const float* back = tmp2;
+  if (Qa) {
+    float* dst = Qg ? tmp : Y;
+    if ((rc = dense_gemm(0, 0, d_in, K, d_in, 1.f, Qa, d_in, back, K, 0.f, dst, K, d_out, 0,
+                         (long long)d_in * K, (long long)d_in * K, st)))
+      return rc;
+    back = dst;
+  }
+  if (Qg) {
+    if ((rc = dense_gemm(0, 0, d_out, d_in * K, d_out, 1.f, Qg, d_out, back, d_in * K, 0.f, Y, d_in * K, 1, 0,
+                         0, 0, st)))
+      return rc;
+  } else if (back != Y) {
+    CHECK_CUDA(cudaMemcpyAsync(Y, back, sizeof(float) * d_out * d_in * K, cudaMemcpyDeviceToDevice, st));
+  }
+  return CURV_OK;
+}
+
+#include "kfac.cuh"

@@ -1,0 +1,317 @@
+"""Curvature linear operators backed by the CUDA engine.
+
+Same constructor signatures, attributes and error behaviour as the reference's
+``CurvatureLinearOperator`` (``curvlinops/_torch_base.py:817-1007``) with its empirical-risk mixin
+(``curvlinops/_empirical_risk.py:20-439``), ``GGNLinearOperator`` (``curvlinops/ggn.py:171-366``) and
+``HessianLinearOperator`` (``curvlinops/hessian.py:72-145``).  What differs is *how* a mini-batch
+product is computed: instead of ``vmap(jvp/vjp)`` through autograd, ``_matmat`` hands the whole
+``[P, K]`` matrix to ``curv_matmat_batch`` (``include/curvb200.h``), which runs the fused
+forward+Jv / backward+J^T sweeps.  With ``torch.distributed`` initialised, each rank processes its
+slice of every mini-batch and the ``[P, K]`` result is summed with one NCCL all-reduce
+(linearity of the data sum, ``_torch_base.py:937-944``).
+"""
+
+from __future__ import annotations
+
+from collections.abc import Callable, Iterable, MutableMapping
+
+import torch
+from torch import Tensor
+from torch.nn import BCEWithLogitsLoss, CrossEntropyLoss, Module, MSELoss
+
+from . import _capi as capi
+from . import dist as cdist
+from .engine import Engine
+from .linop import PyTorchLinearOperator, report_allclose
+
+
+def make_functional_call(module: Module) -> Callable:
+    """``(params, X) -> module(X)`` with ``params`` overriding the module's own tensors
+    (role of ``curvlinops/utils.py:267-297``)."""
+
+    def call(params: dict[str, Tensor], *inputs):
+        return torch.func.functional_call(module, params, inputs)
+
+    return call
+
+
+class CurvatureLinearOperator(PyTorchLinearOperator):
+    """Base class of the engine-backed curvature matrices.
+
+    Attributes:
+        FIXED_DATA_ORDER: the data loader must yield identical batches in identical order.
+        KIND: which product ``curv_matmat_batch`` computes.
+    """
+
+    FIXED_DATA_ORDER: bool = False
+    NEEDS_NUM_PER_EXAMPLE_LOSS_TERMS: bool = False
+    KIND: int = capi.KIND_GGN
+    SELF_ADJOINT: bool = True
+
+    def __init__(
+        self,
+        model_func: Module | Callable[[dict[str, Tensor], Tensor | MutableMapping], Tensor],
+        loss_func: Callable[[Tensor, Tensor], Tensor] | None,
+        params: dict[str, Tensor],
+        data: Iterable[tuple[Tensor | MutableMapping, Tensor]],
+        progressbar: bool = False,
+        check_deterministic: bool = True,
+        num_data: int | None = None,
+        num_per_example_loss_terms: int | None = None,
+        batch_size_fn: Callable[[MutableMapping | Tensor], int] | None = None,
+    ):
+        if isinstance(next(iter(data))[0], MutableMapping) and batch_size_fn is None:
+            raise ValueError("When using dict-like custom data, `batch_size_fn` is required.")
+        if not isinstance(params, dict):
+            raise TypeError(
+                f"params must be a dict[str, Tensor], got {type(params).__name__}. "
+                "Use dict(model.named_parameters()) instead of list(model.parameters())."
+            )
+        if isinstance(model_func, Module):
+            self._model_func = make_functional_call(model_func)
+        elif callable(model_func):
+            self._model_func = model_func
+        else:
+            raise ValueError(
+                f"model_func must be an nn.Module or a callable, got {type(model_func).__name__}."
+            )
+        self._params = params
+        self._loss_func = loss_func
+        self._data = data
+        self._progressbar = progressbar
+        self._batch_size_fn = (lambda X: X.shape[0]) if batch_size_fn is None else batch_size_fn
+        self._engine = Engine(self._model_func, loss_func, params)
+        self._N_data, self._num_per_example_loss_terms = self._get_data_statistics(
+            num_data, num_per_example_loss_terms
+        )
+        if check_deterministic:
+            self._check_deterministic()
+        shapes = [tuple(p.shape) for p in params.values()]
+        PyTorchLinearOperator.__init__(self, shapes, shapes)
+        if check_deterministic:
+            self._check_deterministic_matvec()
+
+    # ---- properties ----------------------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        devs = {p.device for p in self._params.values()}
+        if len(devs) != 1:
+            raise RuntimeError(f"Could not infer device. Parameters live on {devs}.")
+        return devs.pop()
+
+    @property
+    def dtype(self) -> torch.dtype:
+        dts = {p.dtype for p in self._params.values()}
+        if len(dts) != 1:
+            raise RuntimeError(f"Could not infer data type. Parameters have types {dts}.")
+        return dts.pop()
+
+    # ---- data loop (reference _empirical_risk.py:121-177, 311-352) --------------------------------
+    def _get_data_statistics(self, num_data, num_per_example_loss_terms):
+        need_n = num_data is None
+        need_t = (self.NEEDS_NUM_PER_EXAMPLE_LOSS_TERMS and self._loss_func is not None
+                  and num_per_example_loss_terms is None)
+        if not need_n and not need_t:
+            return num_data, num_per_example_loss_terms
+        n_acc, t_acc = 0, 0
+        for X, y in self._loop_over_data(desc="data_statistics"):
+            n_acc += self._batch_size_fn(X)
+            t_acc += y.numel() if isinstance(self._loss_func, CrossEntropyLoss) else y.shape[:-1].numel()
+        N = n_acc if need_n else num_data
+        if need_t:
+            if t_acc % N != 0:
+                raise ValueError(
+                    "The number of loss terms must be divisible by the number of data points; "
+                    f"num_loss_terms={t_acc}, N_data={N}."
+                )
+            num_per_example_loss_terms = t_acc // N
+        return N, num_per_example_loss_terms
+
+    def _loop_over_data(self, desc: str | None = None):
+        it = self._data
+        dev = self.device
+        if self._progressbar:
+            from tqdm import tqdm
+
+            it = tqdm(it, desc=f"{self.__class__.__name__}{'' if desc is None else '.' + desc} (on {dev})")
+        for X, y in it:
+            if isinstance(X, Tensor):
+                X = X.to(dev)
+            yield X, y.to(dev)
+
+    def _get_normalization_factor(self, X, y) -> float:
+        return {"sum": 1.0, "mean": self._batch_size_fn(X) / self._N_data}[self._loss_func.reduction]
+
+    # ---- gradient / loss through the engine (reference _empirical_risk.py:354-439) -----------------
+    def _batch_prediction_loss_gradient(self, X, y):
+        """prediction, weighted loss and weighted parameter gradient of one mini-batch:
+        the gradient is ``J^T (dl/df)`` with ``J^T`` applied by the engine (CURV_KIND_VJP)."""
+        pred = self._engine.predict(X)
+        if self._loss_func is None:
+            return pred, None, None
+        w = self._get_normalization_factor(X, y)
+        f = pred.detach().requires_grad_(True)
+        with torch.enable_grad():
+            loss = self._loss_func(f, y) * w
+            (gf,) = torch.autograd.grad(loss, f)
+        P = sum(p.numel() for p in self._params.values())
+        out = torch.zeros(P, 1, device=pred.device, dtype=torch.float32)
+        self._engine.matmat_batch(capi.KIND_VJP, X, None, gf.reshape(*gf.shape, 1).contiguous(), out, 1.0)
+        grads = [g.reshape(p.shape) for g, p in zip(out[:, 0].split([p.numel() for p in self._params.values()]),
+                                                    self._params.values())]
+        return pred, loss.detach(), grads
+
+    def _check_deterministic(self, rtol: float = 5e-5, atol: float = 1e-6):
+        """Two passes over the data must give the same total loss / gradient (and, with
+        ``FIXED_DATA_ORDER``, the same batches): reference ``_empirical_risk.py:179-291``."""
+        has_loss = self._loss_func is not None
+        tot = [None, None]
+        for (X1, y1), (X2, y2) in zip(self._loop_over_data(), self._loop_over_data()):
+            r1 = self._batch_prediction_loss_gradient(X1, y1)
+            r2 = self._batch_prediction_loss_gradient(X2, y2)
+            if self.FIXED_DATA_ORDER:
+                if isinstance(X1, Tensor) and not report_allclose(X1, X2, rtol=rtol, atol=atol):
+                    raise RuntimeError("Check for deterministic X failed.")
+                if not report_allclose(y1, y2, rtol=rtol, atol=atol):
+                    raise RuntimeError("Check for deterministic y failed.")
+                if not report_allclose(r1[0], r2[0], rtol=rtol, atol=atol):
+                    raise RuntimeError("Check for deterministic batch prediction failed.")
+                if has_loss:
+                    if not report_allclose(r1[1], r2[1], rtol=rtol, atol=atol):
+                        raise RuntimeError("Check for deterministic batch loss failed.")
+                    if any(not report_allclose(a, b, rtol=rtol, atol=atol) for a, b in zip(r1[2], r2[2])):
+                        raise RuntimeError("Check for deterministic batch gradient failed.")
+            if has_loss:
+                for j, r in enumerate((r1, r2)):
+                    if tot[j] is None:
+                        tot[j] = [r[1].clone(), [g.clone() for g in r[2]]]
+                    else:
+                        tot[j][0] += r[1]
+                        for a, b in zip(tot[j][1], r[2]):
+                            a += b
+        if has_loss and tot[0] is not None:
+            if not report_allclose(tot[0][0], tot[1][0], rtol=rtol, atol=atol):
+                raise RuntimeError("Check for deterministic total loss failed.")
+            if any(not report_allclose(a, b, rtol=rtol, atol=atol) for a, b in zip(tot[0][1], tot[1][1])):
+                raise RuntimeError("Check for deterministic total gradient failed.")
+
+    def _gradient_and_loss(self) -> tuple[list[Tensor], Tensor]:
+        if self._loss_func is None:
+            raise ValueError("No loss function specified.")
+        total_loss, total_grad = None, None
+        for X, y in self._loop_over_data(desc="gradient_and_loss"):
+            _, loss, grads = self._batch_prediction_loss_gradient(X, y)
+            if total_grad is None:
+                total_loss, total_grad = loss.clone(), [g.clone() for g in grads]
+            else:
+                total_loss += loss
+                for a, b in zip(total_grad, grads):
+                    a += b
+        return total_grad, total_loss
+
+    # ---- the product (reference _torch_base.py:923-944) -------------------------------------------
+    def _flat_matrix(self, M: list[Tensor]) -> Tensor:
+        K = M[0].shape[-1]
+        return torch.cat([m.reshape(-1, K) for m in M]).to(torch.float32).contiguous()
+
+    def _unflatten(self, out: Tensor, like: list[Tensor]) -> list[Tensor]:
+        K = out.shape[1]
+        parts = out.split([s.numel() for s in self._out_shape])
+        return [p.reshape(*s, K).to(m.dtype) for p, s, m in zip(parts, self._out_shape, like)]
+
+    def _batch_call(self, X, y, V: Tensor, out: Tensor, alpha: float):
+        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha)
+
+    def _matmat(self, M: list[Tensor]) -> list[Tensor]:
+        V = self._flat_matrix(M)
+        out = torch.zeros_like(V)
+        rank, world = cdist.rank_world()
+        for X, y in self._loop_over_data(desc="_matmat"):
+            alpha = self._get_normalization_factor(X, y)
+            if world > 1:  # data-parallel shard of this mini-batch, weights stay global
+                Xs, ys, scale = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
+                if Xs is not None:
+                    self._batch_call_sharded(Xs, ys, V, out, alpha, scale)
+            else:
+                if not isinstance(X, Tensor):
+                    raise NotImplementedError("The B200 engine needs tensor inputs X.")
+                self._batch_call(X, y, V, out, alpha)
+        if world > 1:
+            cdist.all_reduce_sum(out)
+        return self._unflatten(out, M)
+
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
+        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0])
+
+    def __getstate__(self):
+        # compiled programs / workspaces are per-process handles: rebuild lazily after unpickling
+        st = self.__dict__.copy()
+        st["_engine"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._engine = Engine(self._model_func, self._loss_func, self._params)
+
+
+class GGNLinearOperator(CurvatureLinearOperator):
+    r"""Generalized Gauss-Newton matrix :math:`c\sum_n J_n^\top \nabla^2_{f_n}\ell\, J_n` of an empirical
+    risk, or its Monte-Carlo (Fisher) approximation when ``mc_samples > 0``
+    (reference ``curvlinops/ggn.py:171-366``)."""
+
+    SELF_ADJOINT = True
+    KIND = capi.KIND_GGN
+    MC_SUPPORTED_LOSSES = (MSELoss, CrossEntropyLoss, BCEWithLogitsLoss)
+
+    def __init__(self, model_func, loss_func, params, data, progressbar=False, check_deterministic=True,
+                 num_data=None, batch_size_fn=None, mc_samples: int = 0, seed: int = 2147483647):
+        self._mc_samples = mc_samples
+        self._mc_grad_override = None  # tests: list of [B, M, C] tensors, one per mini-batch
+        if mc_samples > 0:
+            if not isinstance(loss_func, self.MC_SUPPORTED_LOSSES):
+                raise NotImplementedError(
+                    f"MC-GGN requires loss in {self.MC_SUPPORTED_LOSSES}. Got: {loss_func}."
+                )
+            self.FIXED_DATA_ORDER = True
+            self._seed = seed
+        super().__init__(model_func, loss_func, params, data, progressbar=progressbar,
+                         check_deterministic=check_deterministic, num_data=num_data,
+                         batch_size_fn=batch_size_fn)
+
+    def _matmat(self, M):
+        if self._mc_samples > 0:
+            self._batch_index = 0
+            dev = self.device
+            with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
+                torch.manual_seed(self._seed)  # same stream as the reference (ggn.py:337-341)
+                return super()._matmat(M)
+        return super()._matmat(M)
+
+    def _mc_scale(self, batch: int) -> float:
+        return 1.0 / batch if self._loss_func.reduction == "mean" else 1.0
+
+    def _batch_call(self, X, y, V, out, alpha):
+        if self._mc_samples == 0:
+            return super()._batch_call(X, y, V, out, alpha)
+        if self._mc_grad_override is not None:
+            g = self._mc_grad_override[self._batch_index].to(X.device)
+        else:
+            g = self._engine.mc_grad_outputs(X, self._mc_samples)
+        self._batch_index += 1
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
+                                  scale=self._mc_scale(X.shape[0]))
+
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
+        if self._mc_samples == 0:
+            return super()._batch_call_sharded(X, y, V, out, alpha, scale)
+        g = self._engine.mc_grad_outputs(X, self._mc_samples)
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1])
+
+
+class HessianLinearOperator(CurvatureLinearOperator):
+    r"""Hessian :math:`c\sum_n \nabla^2_\theta \ell(f_\theta(x_n), y_n)` of an empirical risk
+    (reference ``curvlinops/hessian.py:72-145``), applied with a hand-written R-op
+    (forward + tangent sweep, plain backward, R-backward) instead of forward-over-reverse autograd."""
+
+    SELF_ADJOINT = True
+    KIND = capi.KIND_HESSIAN

@@ -1,0 +1,60 @@
+"""Data-parallel sharding of the mini-batch sum (new functionality, the reference is single-device).
+
+``G V = sum_b alpha_b sum_{n in batch b} (...)`` is linear in the data (reference
+``curvlinops/_torch_base.py:937-944``; no cross-sample coupling with BatchNorm in eval mode), so each
+rank processes a contiguous slice of every mini-batch with the *global* normalisation
+(``1/B_global`` inside the loss Hessian, ``B_global/N`` outside) and the flat ``[P, K]`` result (or the
+Kronecker factors) is summed with ONE all-reduce -- NCCL over NVLink on the GPU box, gloo in the CPU tests.
+Opt-in: call :func:`enable` after ``torch.distributed.init_process_group``.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+from torch.nn import CrossEntropyLoss
+
+_enabled = False
+_group = None
+
+
+def enable(flag: bool = True, group=None) -> None:
+    """Turn batch sharding + all-reduce on/off for all engine-backed operators of this process."""
+    global _enabled, _group
+    _enabled, _group = flag, group
+
+
+def rank_world() -> tuple[int, int]:
+    if _enabled and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(_group), dist.get_world_size(_group)
+    return 0, 1
+
+
+def shard_bounds(batch: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous slice ``[lo, hi)`` of a mini-batch owned by ``rank`` (sizes differ by at most 1)."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(X: Tensor, y: Tensor, rank: int, world: int, loss_func, engine=None):
+    """Local slice of ``(X, y)`` and the loss-Hessian constants ``(exact, mc)`` of the GLOBAL batch."""
+    if not isinstance(X, Tensor):
+        raise NotImplementedError("Data-parallel sharding needs tensor inputs X.")
+    B = X.shape[0]
+    lo, hi = shard_bounds(B, rank, world)
+    if loss_func is None or loss_func.reduction == "sum":
+        scales = (1.0, 1.0)
+    elif isinstance(loss_func, CrossEntropyLoss):
+        scales = (1.0 / B, 1.0 / B)
+    else:
+        scales = (1.0 / (B * y.shape[-1]), 1.0 / B)
+    if hi == lo:
+        return None, None, scales
+    return X[lo:hi], y[lo:hi], scales
+
+
+def all_reduce_sum(t: Tensor) -> None:
+    """In-place sum over ranks (one collective per matmat / factor build)."""
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)

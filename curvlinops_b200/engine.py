@@ -1,0 +1,206 @@
+"""Host-side driver of the CUDA engine: program cache, workspace, per-mini-batch calls.
+
+This is the piece that replaces ``self._mp(X, y, M)`` -- the vmapped ``torch.func`` product of the
+reference (``curvlinops/_torch_base.py:946-989``) -- by calls into ``libcurvb200.so``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import Tensor
+from torch.nn import BCEWithLogitsLoss, CrossEntropyLoss, MSELoss
+
+from . import _capi as capi
+from .capture import LayerProgram, capture
+
+#: number of columns processed per sweep (tangent slots held in the workspace)
+MAX_COLUMNS_PER_SWEEP = 8
+
+
+def _loss_code(loss_func) -> int:
+    if isinstance(loss_func, CrossEntropyLoss):
+        if loss_func.weight is not None or loss_func.label_smoothing != 0.0 or loss_func.ignore_index >= 0:
+            raise NotImplementedError("CrossEntropyLoss options (weight/label_smoothing/ignore_index).")
+        return capi.LOSS_CE
+    if isinstance(loss_func, MSELoss):
+        return capi.LOSS_MSE
+    if isinstance(loss_func, BCEWithLogitsLoss):
+        if loss_func.weight is not None or loss_func.pos_weight is not None:
+            raise NotImplementedError("BCEWithLogitsLoss weights.")
+        return capi.LOSS_BCE
+    raise NotImplementedError(
+        f"Loss {loss_func} is not supported by the B200 engine (MSELoss, CrossEntropyLoss, BCEWithLogitsLoss)."
+    )
+
+
+def loss_scale(loss_func, batch: int, classes: int) -> float:
+    """Reduction constant of the mini-batch loss Hessian (``ggn_utils.py:116-124`` times the batch mean)."""
+    if loss_func.reduction == "sum":
+        return 1.0
+    if loss_func.reduction != "mean":
+        raise ValueError(f"Unsupported reduction {loss_func.reduction!r}.")
+    return 1.0 / batch if isinstance(loss_func, CrossEntropyLoss) else 1.0 / (batch * classes)
+
+
+class CompiledProgram:
+    """A layer program planned for one (input shape, kmax, hessian) combination."""
+
+    def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool):
+        self.lp: LayerProgram = capture(model_func, params, X)
+        self.kmax = kmax
+        self.batch = X.shape[0]
+        self.device = X.device
+        lp = self.lp
+        vals = (capi.ValueDesc * len(lp.values))(*[capi.ValueDesc(c, h, w, int(t)) for c, h, w, t in lp.values])
+        nodes = (capi.NodeDesc * len(lp.nodes))(*[capi.NodeDesc(**n) for n in lp.nodes])
+        offs, o = [], 0
+        for p in params.values():
+            offs.append(o)
+            o += p.numel()
+        self.P = o
+        pds = (capi.ParamDesc * max(1, len(offs)))(*[capi.ParamDesc(p.numel(), off)
+                                                     for p, off in zip(params.values(), offs)])
+        handle = C.c_void_p()
+        capi.check(capi.lib().curv_program_create(vals, len(lp.values), nodes, len(lp.nodes), pds, len(offs),
+                                                  self.batch, kmax, int(hessian), C.byref(handle)))
+        self.handle = handle
+        self.ws_bytes = capi.lib().curv_program_workspace_bytes(handle)
+        self.consts = [t.to(self.device) for t in lp.consts]
+        self.const_ptrs = capi.ptr_array([t.data_ptr() for t in self.consts])
+        self.out_value = lp.nodes[-1]["out"]
+        self.classes = lp.out_features
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                capi.lib().curv_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def value_view(self, ws: Tensor, value_id: int, nslots: int) -> Tensor:
+        """``[nslots, B, H, W, Cp]`` view of a value's storage inside the workspace (tests / MC draw)."""
+        off, sb, cp = C.c_size_t(), C.c_size_t(), C.c_int()
+        capi.check(capi.lib().curv_program_value_layout(self.handle, value_id, C.byref(off), C.byref(sb),
+                                                        C.byref(cp)))
+        c, h, w, _ = self.lp.values[value_id]
+        n = sb.value // 4
+        flat = ws.view(torch.float32)[off.value // 4: off.value // 4 + n * nslots]
+        return flat.view(nslots, self.batch, h, w, cp.value)
+
+
+class Engine:
+    """Runs curvature matmats of one operator through the CUDA library."""
+
+    def __init__(self, model_func, loss_func, params: dict[str, Tensor]):
+        self.model_func = model_func
+        self.loss_func = loss_func
+        self.params = params
+        self._programs: dict = {}
+        self._ws: Tensor | None = None
+        capi.lib()  # fail loudly if the CUDA library has not been built
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check_supported(self):
+        for n, p in self.params.items():
+            if p.dtype != torch.float32:
+                raise NotImplementedError(
+                    f"The B200 engine computes in float32; parameter {n!r} has dtype {p.dtype}."
+                )
+            if p.device.type != "cuda":
+                raise RuntimeError(
+                    "curvlinops_b200 runs on CUDA devices only (no CPU fallback); parameter "
+                    f"{n!r} lives on {p.device}."
+                )
+
+    def program(self, X: Tensor, kmax: int, hessian: bool) -> CompiledProgram:
+        key = (tuple(X.shape), hessian)
+        prog = self._programs.get(key)
+        if prog is None or prog.kmax < kmax:
+            prog = CompiledProgram(self.model_func, self.params, X, kmax, hessian)
+            self._programs[key] = prog
+        return prog
+
+    def workspace(self, nbytes: int, device) -> Tensor:
+        if self._ws is None or self._ws.numel() * 4 < nbytes or self._ws.device != device:
+            self._ws = None
+            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        return self._ws
+
+    def _param_ptrs(self):
+        ps = [p if p.is_contiguous() else p.contiguous() for p in self.params.values()]
+        return ps, capi.ptr_array([p.data_ptr() for p in ps])
+
+    # -- the hot call ----------------------------------------------------------------------------
+    def matmat_batch(self, kind: int, X: Tensor, y: Tensor | None, V: Tensor, out: Tensor, alpha: float,
+                     mc_grad: Tensor | None = None, scale: float | None = None) -> None:
+        """``out += alpha * (mini-batch matrix) @ V`` with ``V``/``out`` flat ``[P, K]`` fp32 on device."""
+        self._check_supported()
+        K = V.shape[1]
+        kc = min(K, MAX_COLUMNS_PER_SWEEP)
+        X = X.to(torch.float32).contiguous()
+        prog = self.program(X, kc, kind == capi.KIND_HESSIAN)
+        ws = self.workspace(prog.ws_bytes, X.device)
+        keep, pptrs = self._param_ptrs()
+        loss = 0
+        if kind in (capi.KIND_GGN, capi.KIND_GGN_MC, capi.KIND_HESSIAN):
+            loss = _loss_code(self.loss_func)
+            if scale is None:
+                scale = loss_scale(self.loss_func, X.shape[0], prog.classes)
+            if loss == capi.LOSS_CE:
+                if y.dtype != torch.int64 or y.ndim != 1:
+                    raise NotImplementedError("CrossEntropyLoss needs int64 class labels of shape [batch].")
+            else:
+                y = y.to(torch.float32)
+            y = y.contiguous()
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        M = 0
+        if mc_grad is not None:
+            mc_grad = mc_grad.to(torch.float32).contiguous()
+            M = mc_grad.shape[1]
+        for k0 in range(0, K, kc):
+            kk = min(kc, K - k0)
+            capi.check(capi.lib().curv_matmat_batch(
+                prog.handle, kind, loss, pptrs, prog.const_ptrs, X.data_ptr(),
+                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
+                V.data_ptr(), out.data_ptr(), kk, V.shape[1], k0, float(scale or 1.0), float(alpha),
+                ws.data_ptr(), ws.numel() * 4, stream))
+        del keep
+
+    def predict(self, X: Tensor) -> Tensor:
+        """Primal forward through the engine; returns the prediction ``[B, C]`` (a copy)."""
+        self._check_supported()
+        X = X.to(torch.float32).contiguous()
+        prog = self.program(X, 1, False)
+        ws = self.workspace(prog.ws_bytes, X.device)
+        keep, pptrs = self._param_ptrs()
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        capi.check(capi.lib().curv_matmat_batch(
+            prog.handle, capi.KIND_FORWARD, 0, pptrs, prog.const_ptrs, X.data_ptr(), 0, 0, 0, 0, 0, 0, 1, 0,
+            1.0, 1.0, ws.data_ptr(), ws.numel() * 4, stream))
+        del keep
+        return prog.value_view(ws, prog.out_value, 1)[0, :, 0, 0, : prog.classes].clone()
+
+    def mc_grad_outputs(self, X: Tensor, mc_samples: int) -> Tensor:
+        """Would-be gradients ``[B, M, C] / sqrt(M)`` drawn from the global RNG with the reference's own
+        calls (``ggn_utils.py:220-262,369-372``), on the operator's device."""
+        f = self.predict(X)
+        B, Cc = f.shape
+        lf = self.loss_func
+        if isinstance(lf, CrossEntropyLoss):
+            p = torch.softmax(f, dim=1)
+            yhat = p.multinomial(mc_samples, replacement=True)
+            g = p.unsqueeze(1) - torch.nn.functional.one_hot(yhat, num_classes=Cc).to(f.dtype)
+        elif isinstance(lf, MSELoss):
+            c = 1.0 / Cc if lf.reduction == "mean" else 1.0
+            g = torch.normal(torch.zeros(B, mc_samples, Cc, dtype=f.dtype, device=f.device), math.sqrt(2 * c))
+        elif isinstance(lf, BCEWithLogitsLoss):
+            c = 1.0 / Cc if lf.reduction == "mean" else 1.0
+            s = torch.sigmoid(f).unsqueeze(1).expand(B, mc_samples, Cc)
+            g = math.sqrt(c) * (s - s.bernoulli())
+        else:
+            raise NotImplementedError(f"MC sampling for {lf}.")
+        return g / math.sqrt(mc_samples)

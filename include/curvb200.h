@@ -1,0 +1,177 @@
+/*
+ * curvb200.h -- C ABI of the B200-native curvature-matvec engine.
+ *
+ * The reference (f-dangel/curvlinops, pure Python) has no FFI; its seam for this hot path is the
+ * Python subclass contract
+ *     CurvatureLinearOperator._matmat / _matmat_batch      curvlinops/_torch_base.py:923-989
+ *     make_ggn_vector_product (Jv -> H_loss -> J^T)        curvlinops/ggn.py:42-72
+ *     make_batch_ggn_mc_vector_product                     curvlinops/ggn.py:100-168
+ *     make_batch_hessian_vector_product                    curvlinops/hessian.py:13-69
+ *     HooksKFACComputer._compute_kronecker_factors         curvlinops/computers/kfac_hooks.py:176-393
+ *     KroneckerProductLinearOperator._matmat / inverse     curvlinops/kronecker.py:141-171,250-373
+ *     EighDecomposedLinearOperator._matmat                 curvlinops/eigh.py:84-104
+ * Each entry point below replaces the per-mini-batch body of one of those; the Python operators
+ * in curvlinops_b200/ keep the reference's class names, constructor arguments and error behaviour
+ * and call this library through ctypes.
+ *
+ * Rules
+ *  - plain C types only: device pointers are void* / float*, sizes are int / long long / size_t,
+ *    the stream is passed as void* (a cudaStream_t);
+ *  - every device buffer (parameters, X, y, V, out, factors, workspace) is allocated and owned by the
+ *    caller (PyTorch); the library never allocates device memory after curv_program_create (which
+ *    allocates none either -- plans are host-side);
+ *  - all work is enqueued on the given stream, no host synchronisation, no hidden streams/threads;
+ *  - return value 0 = success; otherwise a CURV_ERR_* code, text via curv_last_error();
+ *  - results are run-to-run deterministic (no floating-point atomics; split reductions are summed in
+ *    a fixed order);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef CURVB200_H
+#define CURVB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CURV_ABI_VERSION 1
+
+enum curv_status {
+  CURV_OK = 0,
+  CURV_ERR_INVALID = 1,     /* bad argument / unsupported configuration -> ValueError        */
+  CURV_ERR_UNSUPPORTED = 2, /* op outside the supported layer set -> NotImplementedError     */
+  CURV_ERR_WORKSPACE = 3,   /* workspace too small -> RuntimeError                           */
+  CURV_ERR_CUDA = 4         /* CUDA runtime error (no device, launch failure) -> RuntimeError */
+};
+
+/* node kinds of the layer program */
+enum curv_op {
+  CURV_OP_INPUT = 0,    /* network input X, NCHW fp32 in caller memory -> internal NHWC            */
+  CURV_OP_CONV = 1,     /* Conv2d / Linear (Linear = 1x1 conv on a 1x1 map, or HxW "valid" conv
+                           when it follows a flatten): aten.convolution / aten.addmm / aten.mm      */
+  CURV_OP_AFFINE = 2,   /* BatchNorm2d in eval mode: y = (x-mean)/sqrt(var+eps)*gamma+beta          */
+  CURV_OP_RELU = 3,
+  CURV_OP_ADD = 4,      /* residual join                                                           */
+  CURV_OP_MAXPOOL = 5,
+  CURV_OP_AVGPOOL = 6,  /* global average pool (AdaptiveAvgPool2d(1) / mean over H,W)               */
+  CURV_OP_SIGMOID = 7,
+  CURV_OP_TANH = 8
+};
+
+enum curv_loss { CURV_LOSS_CE = 0, CURV_LOSS_MSE = 1, CURV_LOSS_BCE = 2 };
+
+/* which matrix the matmat entry point applies */
+enum curv_kind {
+  CURV_KIND_GGN = 0,     /* exact GGN:  J^T H_loss J                 (ggn.py:42-72)                 */
+  CURV_KIND_GGN_MC = 1,  /* MC-Fisher:  H_loss ~ sum_m g_m g_m^T     (ggn.py:100-168)               */
+  CURV_KIND_HESSIAN = 2, /* full Hessian via R-op (Pearlmutter)      (hessian.py:13-69)             */
+  CURV_KIND_JVP = 3,     /* out_pred = J V   (jacobian.py:30-48)                                    */
+  CURV_KIND_VJP = 4,     /* out = J^T W      (jacobian.py:77-94)                                    */
+  CURV_KIND_FORWARD = 5  /* primal forward only; the prediction is then readable through
+                            curv_program_value_layout (used to draw the MC samples, ggn.py:157)     */
+};
+
+/* An activation of the network for ONE sample: C channels on an HxW map ([B,C] tensors: H=W=1).
+   Internally stored NHWC with C padded to a multiple of 4 (pad lanes are kept at zero). */
+typedef struct curv_value_desc {
+  int C, H, W;
+  int has_tangent; /* 1 if the value depends on a parameter of the operator's `params`          */
+} curv_value_desc;
+
+/* One differentiated parameter tensor (an entry of the operator's `params` dict, in dict order). */
+typedef struct curv_param_desc {
+  long long numel;
+  long long offset; /* row offset in the flat [P, K] matrices V / out                              */
+} curv_param_desc;
+
+typedef struct curv_node_desc {
+  int op;            /* enum curv_op                                                              */
+  int in0, in1, out; /* value ids (in1 = -1 unless CURV_OP_ADD)                                   */
+  /* parameter slots: index into `params` (differentiated), or -1 (constant / absent).
+     CONV: p0 = weight, p1 = bias.  AFFINE: p0 = gamma, p1 = beta.                                */
+  int p0, p1;
+  /* const slots: index into the per-call `const_ptrs` array for tensors that are NOT
+     differentiated (-1 = absent).  CONV: c0 = weight, c1 = bias (when not in params).
+     AFFINE: c0 = gamma, c1 = beta (when not in params), c2 = running_mean, c3 = running_var.     */
+  int c0, c1, c2, c3;
+  int kh, kw, sh, sw, ph, pw; /* CONV / MAXPOOL geometry                                           */
+  float eps;                  /* AFFINE                                                            */
+} curv_node_desc;
+
+typedef struct curv_program curv_program;
+
+/* Build the execution plan (host side only) for mini-batches of `batch` samples and up to `kmax`
+   simultaneous columns.  `hessian` != 0 reserves the extra cotangent storage the R-op needs.
+   values[0] must be the network input; nodes are in topological order; the last node's `out` is the
+   prediction and must have H=W=1. */
+int curv_program_create(const curv_value_desc* values, int n_values, const curv_node_desc* nodes,
+                        int n_nodes, const curv_param_desc* params, int n_params, int batch, int kmax,
+                        int hessian, curv_program** out);
+void curv_program_destroy(curv_program* prog);
+size_t curv_program_workspace_bytes(const curv_program* prog);
+
+/* Debug / test access: location of a value's activation storage inside the workspace.
+   Layout: [slot][batch][H][W][Cp] fp32, slot 0 = primal, slot k = k-th tangent (later cotangent). */
+int curv_program_value_layout(const curv_program* prog, int value_id, size_t* byte_offset,
+                              size_t* slot_bytes, int* cp);
+
+/* out[:, k0:k0+K] += alpha * (mini-batch matrix) @ V[:, k0:k0+K]        (_torch_base.py:937-944)
+ *
+ *  param_ptrs[n_params]  device pointers of the differentiated parameters (fp32, contiguous)
+ *  const_ptrs[]          device pointers of constant tensors referenced by c0..c3
+ *  X                     [batch, C, H, W] fp32 NCHW (or [batch, C]), contiguous
+ *  y                     labels: int64 [batch] (CE) or fp32 [batch, C] (MSE/BCE)
+ *  mc_grad               CURV_KIND_GGN_MC only: [batch, mc_samples, C] fp32 would-be gradients,
+ *                        already divided by sqrt(mc_samples) (ggn_utils.py:369-372)
+ *  V, out                [P, ldk] fp32 row-major (K minor, as the reference's [*shape, K] tensors)
+ *  loss_scale            reduction constant c of the mini-batch loss Hessian (1/B for CE-mean, ...)
+ *  alpha                 mini-batch weight (1 or B/N_data, _empirical_risk.py:340-352)
+ *  For CURV_KIND_JVP `out` is [batch, C_out, ldk]; for CURV_KIND_VJP `V` is [batch, C_out, ldk].
+ */
+int curv_matmat_batch(curv_program* prog, int kind, int loss, const void* const* param_ptrs,
+                      const void* const* const_ptrs, const void* X, const void* y,
+                      const float* mc_grad, int mc_samples, const float* V, float* out, int K, int ldk,
+                      int k0, float loss_scale, float alpha, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* KFAC-expand factor accumulation for one mini-batch (kfac_hooks.py:176-393):
+ *   A_l += wA * sum_{n,s} a~ a~^T        a~ = im2col patch of the layer input (+1 if joint bias)
+ *   G_l += wG * sum_{v,n,s} g g^T        g  = backpropagated grad_outputs[v]
+ *  layer_nodes[n_layers]   node ids of the CONV nodes to collect
+ *  A_ptrs / G_ptrs         fp32 device matrices [d_in(+1), d_in(+1)] / [d_out, d_out], patch order
+ *                          channel-major (c, kh, kw) like F.unfold (kfac_utils.py:120-121)
+ *  joint_bias[n_layers]    1: append the ones column
+ *  grad_outputs            [V, batch, C] fp32 seeds (already scaled by the caller), may be NULL if V=0
+ */
+int curv_kfac_accumulate_batch(curv_program* prog, const void* const* param_ptrs,
+                               const void* const* const_ptrs, const void* X, const int* layer_nodes,
+                               int n_layers, float* const* A_ptrs, float* const* G_ptrs,
+                               const int* joint_bias, const float* grad_outputs, int V, float wA,
+                               float wG, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Y[d_out, d_in, K] = G[d_out,d_out] . X[d_out, d_in, K] . A[d_in,d_in]^T  per column
+   (kronecker.py:141-153 'abZ,Aa,Bb->ABZ').  tmp needs d_out*d_in*K floats.  A or G may be NULL
+   (identity).  If lambda != NULL this is the eigen-basis apply of eigh.py:98-104:
+   Y = Qg ( (Qg^T X Qa) * scale(lambda) ) Qa^T with scale = lambda or 1/(lambda+damping). */
+int curv_kron_apply(const float* G, const float* A, int d_out, int d_in, int K, const float* X,
+                    float* Y, float* tmp, void* stream);
+int curv_eigh_apply(const float* Qg, const float* Qa, const float* lambda, float damping, int inverse,
+                    int d_out, int d_in, int K, const float* X, float* Y, float* tmp, float* tmp2,
+                    void* stream);
+
+/* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major, hand-written kernels (no cuBLAS).  */
+int curv_gemm(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, void* stream);
+
+const char* curv_last_error(void);
+int curv_abi_version(void);
+/* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
+long long curv_launch_count(void);
+/* 0: SIMT fp32 contraction kernels, 1: tcgen05 (3xTF32 split) tensor-core kernels where eligible */
+int curv_set_tensor_core_mode(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURVB200_H */

@@ -1,0 +1,125 @@
+"""GPU parity tests: engine (through the C ABI) vs the reference-generated golden fixtures and vs
+the CPU oracle.  Tolerance (BASELINE.json north_star): rtol = 1e-4 for fp32; atol = 1e-5 * max|ref|
+absorbs entries that are ~0 relative to the matrix scale (the fixtures are float64)."""
+import pytest
+import torch
+
+from curvlinops_b200 import GGNLinearOperator, HessianLinearOperator
+from oracle import curvature_oracle as orc
+from tests.golden_utils import flat, load_case, split_like
+
+pytestmark = pytest.mark.gpu
+CASES = ["mlp_c1_ce_mean", "mlp_c1_ce_sum", "mlp_c1_mse_mean", "miniresnet_ce_mean"]
+RTOL = 1e-4
+
+
+def assert_parity(got, ref, params=None, rtol=RTOL):
+    got, ref = got.detach().double().cpu(), ref.double().cpu()
+    atol = 1e-5 * ref.abs().max().item()
+    ok = torch.allclose(got, ref, rtol=rtol, atol=atol)
+    if not ok and params is not None:  # per-parameter report to localise a failing layer
+        o = 0
+        for n, p in params.items():
+            g, r = got[o:o + p.numel()], ref[o:o + p.numel()]
+            print(f"{n:32s} max|ref|={r.abs().max():.3e} max|err|={(g - r).abs().max():.3e}")
+            o += p.numel()
+    assert ok, f"max abs err {(got - ref).abs().max():.3e} vs max|ref| {ref.abs().max():.3e}"
+
+
+def _setup(name):
+    model, loss, data, fx = load_case(name, dtype=torch.float32, device="cuda")
+    return model, loss, data, fx, dict(model.named_parameters())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ggn_matches_reference_golden(name):
+    model, loss, data, fx, params = _setup(name)
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(G @ fx["V"].float().cuda(), fx["ggn"], params)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_hessian_matches_reference_golden(name):
+    model, loss, data, fx, params = _setup(name)
+    H = HessianLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(H @ fx["V"].float().cuda(), fx["hessian"], params)
+
+
+@pytest.mark.parametrize("name", ["mlp_c1_ce_mean", "miniresnet_ce_mean"])
+def test_formats_and_determinism(name):
+    model, loss, data, fx, params = _setup(name)
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=True)  # runs the probes
+    V = fx["V"].float().cuda()
+    ref = G @ V
+    assert torch.equal(ref, G @ V), "two matmats must be bit-identical"
+    # vector, list and numpy formats, left multiplication (self-adjoint)
+    torch.testing.assert_close(G @ V[:, 0], ref[:, 0], rtol=1e-5, atol=1e-8)
+    lst = G @ split_like(V, params)
+    torch.testing.assert_close(flat(lst), ref, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close((V.T @ G).T, ref, rtol=1e-5, atol=1e-8)
+    got_np = G.to_scipy() @ V.double().cpu().numpy()
+    torch.testing.assert_close(torch.from_numpy(got_np), ref.double().cpu(), rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["mlp_c1_ce_mean", "mlp_c1_mse_mean", "miniresnet_ce_mean"])
+@pytest.mark.parametrize("M", [1, 3])
+def test_mc_ggn_with_reference_samples(name, M):
+    """MC-GGN with the would-be gradients the reference drew (same seed => same stream on CPU);
+    the engine is handed those samples, so the comparison is exact rather than in expectation."""
+    model, loss, data, fx, params = _setup(name)
+    cpu_model = load_case(name)[0]
+    gs = []
+    with torch.random.fork_rng():
+        torch.manual_seed(1234)
+        for X, _ in data:
+            gs.append(orc.mc_grad_outputs(loss, cpu_model(X.double().cpu()).detach(), M).float())
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=M, seed=1234)
+    G._mc_grad_override = gs
+    assert_parity(G @ fx["V"].float().cuda(), fx[f"ggn_mc{M}"], params)
+
+
+def test_mc_ggn_own_sampler_is_seeded_and_unbiased():
+    model, loss, data, fx, params = _setup("mlp_c1_ce_mean")
+    V = fx["V"].float().cuda()[:, :1]
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=2, seed=5)
+    a, b = G @ V, G @ V
+    assert torch.equal(a, b)
+    state = torch.cuda.get_rng_state()
+    G @ V
+    assert torch.equal(state, torch.cuda.get_rng_state()), "global RNG must not be advanced"
+    acc = torch.zeros_like(a)
+    reps = 300
+    for s in range(reps):
+        G._seed = s
+        acc += G @ V
+    exact = fx["ggn"][:, :1].float().cuda()
+    rel = (acc / reps - exact).norm() / exact.norm()
+    assert rel < 0.1, rel
+
+
+def test_param_subset_and_order():
+    model, loss, data, fx, _ = _setup("miniresnet_ce_mean")
+    names = ["fc.bias", "layer2.0.conv1.weight", "bn1.weight", "layer1.0.bn2.bias", "conv1.weight"]
+    params = {n: dict(model.named_parameters())[n] for n in names}
+    cpu_model = load_case("miniresnet_ce_mean")[0]
+    p64 = {n: dict(cpu_model.named_parameters())[n] for n in names}
+    data64 = [(X.double().cpu(), y.cpu()) for X, y in data]
+    torch.manual_seed(0)
+    V = torch.rand(sum(p.numel() for p in params.values()), 2, dtype=torch.float64)
+    ref = flat(orc.ggn_matmat(cpu_model, loss, p64, data64, split_like(V, p64)))
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(G @ V.float().cuda(), ref, params)
+    refh = flat(orc.hessian_matmat(cpu_model, loss, p64, data64, split_like(V, p64)))
+    H = HessianLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(H @ V.float().cuda(), refh, params)
+
+
+def test_wide_matrix_is_chunked():
+    """K larger than the engine's column chunk (multiplying onto many columns, test/utils.py:153)."""
+    model, loss, data, fx, params = _setup("mlp_c1_ce_mean")
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    torch.manual_seed(1)
+    V = torch.rand(G.shape[1], 19, device="cuda")
+    wide = G @ V
+    for k in (0, 7, 8, 18):
+        torch.testing.assert_close(wide[:, k], G @ V[:, k], rtol=1e-5, atol=1e-7)

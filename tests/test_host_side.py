@@ -1,0 +1,170 @@
+"""CPU-only tests: C-ABI exports, capture/planning (host side, no kernels), operator format handling."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+from torch import nn
+
+from curvlinops_b200 import _capi as capi
+from curvlinops_b200.capture import capture
+from curvlinops_b200.curvature import make_functional_call
+from curvlinops_b200.engine import CompiledProgram, loss_scale
+from curvlinops_b200.linop import PyTorchLinearOperator
+from oracle.models import ConvNetBias, MiniResNet, mlp_c1
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "curvb200.h")).read()
+    declared = set(re.findall(r"\b(curv_[a-z_0-9]+)\s*\(", header))
+    L = capi.lib()
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in curvb200.h but not exported"
+    assert set(capi.EXPORTS) <= declared
+    assert L.curv_abi_version() == 1
+
+
+def test_compute_call_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model = mlp_c1()
+    params = dict(model.named_parameters())
+    prog = CompiledProgram(make_functional_call(model), params, torch.randn(4, 64), 2, False)
+    ws = torch.empty(prog.ws_bytes // 4 + 1)
+    pp = capi.ptr_array([p.data_ptr() for p in params.values()])
+    rc = capi.lib().curv_matmat_batch(prog.handle, capi.KIND_GGN, 0, pp, prog.const_ptrs, 0, 0, 0, 0, 0, 0, 1,
+                                      1, 0, 1.0, 1.0, ws.data_ptr(), ws.numel() * 4, 0)
+    assert rc == capi.ERR_CUDA
+    assert b"no CPU fallback" in capi.lib().curv_last_error()
+
+
+def test_capture_mlp():
+    model = mlp_c1()
+    params = dict(model.named_parameters())
+    lp = capture(make_functional_call(model), params, torch.randn(5, 64))
+    ops = [n["op"] for n in lp.nodes]
+    assert ops == [capi.OP_INPUT, capi.OP_CONV, capi.OP_RELU, capi.OP_CONV, capi.OP_RELU, capi.OP_CONV,
+                   capi.OP_RELU, capi.OP_CONV]
+    assert lp.out_features == 10
+    assert [n["p0"] for n in lp.nodes if n["op"] == capi.OP_CONV] == [0, 2, 4, 6]
+    assert [n["p1"] for n in lp.nodes if n["op"] == capi.OP_CONV] == [1, 3, 5, 7]
+
+
+def test_capture_resnet_and_param_subset():
+    model = MiniResNet().eval()
+    allp = dict(model.named_parameters())
+    lp = capture(make_functional_call(model), allp, torch.rand(2, 3, 32, 32))
+    kinds = [n["op"] for n in lp.nodes]
+    assert kinds.count(capi.OP_CONV) == 7 and kinds.count(capi.OP_AFFINE) == 6
+    assert kinds.count(capi.OP_ADD) == 2 and kinds.count(capi.OP_MAXPOOL) == 1
+    # subset + reordering: excluded parameters become constants, early values carry no tangent
+    sub = {k: allp[k] for k in ["fc.bias", "layer2.0.conv1.weight"]}
+    lp2 = capture(make_functional_call(model), sub, torch.rand(2, 3, 32, 32))
+    convs = [n for n in lp2.nodes if n["op"] == capi.OP_CONV]
+    assert sum(n["p0"] >= 0 for n in convs) == 1 and sum(n["p1"] >= 0 for n in convs) == 1
+    assert not lp2.values[convs[0]["out"]][3]  # stem output does not depend on the selected params
+    assert lp2.values[lp2.nodes[-1]["out"]][3]
+
+
+def test_capture_flatten_linear_becomes_valid_conv():
+    model = ConvNetBias().eval()
+    lp = capture(make_functional_call(model), dict(model.named_parameters()), torch.rand(2, 3, 8, 8))
+    last = lp.nodes[-1]
+    assert last["op"] == capi.OP_CONV and (last["kh"], last["kw"]) == (3, 3)
+
+
+def test_capture_rejects_unsupported():
+    model = nn.Sequential(nn.Linear(4, 4), nn.GELU(), nn.Linear(4, 2))
+    with pytest.raises(NotImplementedError, match="not supported by the B200"):
+        capture(make_functional_call(model), dict(model.named_parameters()), torch.rand(2, 4))
+    bn = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4)).train()
+    with pytest.raises(NotImplementedError, match="eval"):
+        capture(make_functional_call(bn), dict(bn.named_parameters()), torch.rand(2, 3, 8, 8))
+
+
+def test_program_plan_host_only():
+    model = MiniResNet().eval()
+    params = dict(model.named_parameters())
+    prog = CompiledProgram(make_functional_call(model), params, torch.rand(3, 3, 32, 32), 4, False)
+    progh = CompiledProgram(make_functional_call(model), params, torch.rand(3, 3, 32, 32), 4, True)
+    assert 0 < prog.ws_bytes < progh.ws_bytes
+    assert prog.P == sum(p.numel() for p in params.values())
+
+
+def test_loss_scale():
+    assert loss_scale(nn.CrossEntropyLoss(), 8, 10) == 1 / 8
+    assert loss_scale(nn.MSELoss(), 8, 10) == 1 / 80
+    assert loss_scale(nn.MSELoss(reduction="sum"), 8, 10) == 1.0
+
+
+class _Dense(PyTorchLinearOperator):
+    """Mock operator: block matrix given densely (pattern of reference test__torch_base.py:17-128)."""
+
+    def __init__(self, A, in_shape, out_shape):
+        super().__init__(in_shape, out_shape)
+        self.A = A
+
+    device = property(lambda self: self.A.device)
+    dtype = property(lambda self: self.A.dtype)
+
+    def _matmat(self, X):
+        K = X[0].shape[-1]
+        flat = torch.cat([x.reshape(-1, K) for x in X])
+        Y = self.A @ flat
+        return [y.reshape(*s, K) for y, s in zip(Y.split(self._out_shape_flat), self._out_shape)]
+
+    def _adjoint(self):
+        return _Dense(self.A.T, self._out_shape, self._in_shape)
+
+
+def test_linop_formats_and_errors():
+    torch.manual_seed(0)
+    in_shape, out_shape = [(2, 3), (4,)], [(5,), (1, 2)]
+    A = torch.rand(7, 10, dtype=torch.float64)
+    op = _Dense(A, in_shape, out_shape)
+    assert op.shape == (7, 10)
+    x = torch.rand(10, dtype=torch.float64)
+    Xm = torch.rand(10, 3, dtype=torch.float64)
+    torch.testing.assert_close(op @ x, A @ x)
+    torch.testing.assert_close(op @ Xm, A @ Xm)
+    xl = [x[:6].reshape(2, 3), x[6:]]
+    yl = op @ xl
+    assert [tuple(y.shape) for y in yl] == [(5,), (1, 2)]
+    torch.testing.assert_close(torch.cat([y.flatten() for y in yl]), A @ x)
+    Xl = [Xm[:6].reshape(2, 3, 3), Xm[6:].reshape(4, 3)]
+    Yl = op @ Xl
+    torch.testing.assert_close(torch.cat([y.reshape(-1, 3) for y in Yl]), A @ Xm)
+    # left multiplication (leading K)
+    z = torch.rand(7, dtype=torch.float64)
+    Z = torch.rand(2, 7, dtype=torch.float64)
+    torch.testing.assert_close(z @ op, z @ A)
+    torch.testing.assert_close(Z @ op, Z @ A)
+    # scipy export
+    S = op.to_scipy()
+    assert S.dtype == "float64"
+    torch.testing.assert_close(torch.from_numpy(S @ Xm.numpy()), A @ Xm)
+    torch.testing.assert_close(torch.from_numpy(S.rmatvec(z.numpy())), A.T @ z)
+    # algebra
+    torch.testing.assert_close((2 * op + op / 2 - op) @ x, 1.5 * (A @ x))
+    chain = op.adjoint() @ op
+    torch.testing.assert_close(chain @ x, A.T @ (A @ x))
+    assert len(chain) == 2
+    # errors
+    with pytest.raises(ValueError, match="must be non-empty."):
+        _Dense(A, [], out_shape)
+    with pytest.raises(ValueError, match="Input must be tensor or list of tensors."):
+        op @ x.numpy()
+    with pytest.raises(ValueError, match="Input list must contain tensors with shapes"):
+        op @ [torch.rand(2, 3), torch.rand(5)]
+    with pytest.raises(ValueError, match="Input tensor must have shape"):
+        op @ torch.rand(11)
+    with pytest.raises(ValueError, match="Input list must have 2 tensors. Got 1."):
+        op @ [torch.rand(2, 3)]
+    with pytest.raises(ValueError, match="Shape mismatch"):
+        op @ op
+    with pytest.raises(ValueError, match="Dtype mismatch"):
+        op + _Dense(A.float(), in_shape, out_shape)
