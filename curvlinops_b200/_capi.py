@@ -40,7 +40,7 @@ EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
-    "curv_launch_count", "curv_set_tensor_core_mode",
+    "curv_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
 ]
 
 _lib = None
@@ -89,6 +89,10 @@ def lib() -> C.CDLL:
     L.curv_launch_count.restype = ll
     L.curv_set_tensor_core_mode.argtypes = [i]
     L.curv_set_tensor_core_mode.restype = i
+    L.curv_profile_enable.argtypes = [i]
+    L.curv_profile_enable.restype = i
+    L.curv_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
+    L.curv_profile_read.restype = i
     _lib = L
     return L
 

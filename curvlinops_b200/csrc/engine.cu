@@ -220,9 +220,51 @@ extern "C" int curv_program_value_layout(const curv_program* p, int id, size_t* 
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
+// Optional per-launch timing of the contraction kernels with CUDA events on the launching stream
+// (bench.py `roofline`): class 0 = gather GEMM (forward / dgrad), 1 = wgrad GEMM.
+struct ProfRec { int cls; double flops; cudaEvent_t e0, e1; };
+static int g_profile = 0;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  ProfRec r; bool on; cudaStream_t st;
+  ProfScope(int cls, double flops, cudaStream_t s) : on(g_profile != 0), st(s) {
+    if (!on) return;
+    r.cls = cls; r.flops = flops;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    g_prof.push_back(r);
+  }
+};
+extern "C" int curv_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_profile = on;
+  return CURV_OK;
+}
+// sums over the launches recorded since curv_profile_enable(1): ms[c], flops[c], count[c] for c = 0, 1
+extern "C" int curv_profile_read(double* ms, double* flops, long long* count) {
+  for (int c = 0; c < 2; ++c) { ms[c] = 0; flops[c] = 0; count[c] = 0; }
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(CURV_ERR_CUDA, "profile event sync failed");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.cls] += t; flops[r.cls] += r.flops; count[r.cls] += 1;
+  }
+  return CURV_OK;
+}
+// algorithmic FLOPs of one (slot, segment) contraction of a conv with forward geometry f
+static double conv_flops(const Geom& f, int cin_real) {
+  return 2.0 * (double)f.M * f.N * f.KH * f.KW * cin_real;
+}
+
+static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st, double flops = 0) {
   if (nslots <= 0) return CURV_OK;
   const Geom& g = a.g;
+  ProfScope prof(0, flops, st);
   if (g_tc_mode && tc_gather_eligible(g)) {
     int rc = tc_launch_gather_gemm(a, nslots, st);
     if (rc == 0) { ++g_launches; return CURV_OK; }
@@ -243,8 +285,9 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   return CURV_OK;
 }
 
-static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st) {
+static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, double flops = 0) {
   const Geom& g = a.g;
+  ProfScope prof(1, flops, st);
   dim3 grid(ceil_div(g.N, bm) * ceil_div(g.Kd, bn), a.nslots, a.nsplit);
   if (bm == 128 && bn == 128) wgrad_gemm_simt<128, 128><<<grid, 256, 0, st>>>(a);
   else if (bm == 128) wgrad_gemm_simt<128, 64><<<grid, 256, 0, st>>>(a);
@@ -362,7 +405,9 @@ static int forward(const Ctx& c, const void* X, int K) {
         a.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; a.bias_slot = vo.Cp;
         a.out = c.act(d.out); a.out_slot = vo.slot_elems;
         a.slot0 = 0; a.accumulate = 0;
-        int rc = launch_gather_gemm(a, nsl, st);
+        double fl = conv_flops(n.fwd, vi.C) *
+                    (1 + (nsl - 1) * ((vi.tan ? 1 : 0) + (d.p0 >= 0 ? 1 : 0)));
+        int rc = launch_gather_gemm(a, nsl, st, fl);
         if (rc) return rc;
         break;
       }
@@ -475,7 +520,7 @@ static int backward(const Ctx& c, int K) {
           a.second_seg = (rop && vi.tan) ? 1 : 0;
           a.partial = scratch; a.nsplit = n.nsplit; a.nslots = ns; a.slot0 = s0;
           a.m_per_split = n.m_per_split;
-          int rc = launch_wgrad(a, n.wbm, n.wbn, st);
+          int rc = launch_wgrad(a, n.wbm, n.wbn, st, conv_flops(g, vi.C) * ns * (a.second_seg ? 2 : 1));
           if (rc) return rc;
           wgrad_finish_kernel<<<grid1d(n.wsize), 256, 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
                                                               vi.Cp, g.KH * g.KW, c.out,
@@ -502,7 +547,7 @@ static int backward(const Ctx& c, int K) {
           a.Wt = (rop && n.wtt_off >= 0) ? c.ws + n.wtt_off : nullptr; a.Wt_slot = n.wtsize;
           a.out = c.grad(d.in0); a.out_slot = vi.slot_elems;
           a.slot0 = s0; a.accumulate = ginit[d.in0];
-          int rc = launch_gather_gemm(a, ns, st);
+          int rc = launch_gather_gemm(a, ns, st, conv_flops(g, vi.C) * ns * (a.Wt ? 2 : 1));
           if (rc) return rc;
           ginit[d.in0] = 1;
         }

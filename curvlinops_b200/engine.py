@@ -139,7 +139,7 @@ class Engine:
                      mc_grad: Tensor | None = None, scale: float | None = None) -> None:
         """``out += alpha * (mini-batch matrix) @ V`` with ``V``/``out`` flat ``[P, K]`` fp32 on device."""
         self._check_supported()
-        K = V.shape[1]
+        K = V.shape[-1]
         kc = min(K, MAX_COLUMNS_PER_SWEEP)
         X = X.to(torch.float32).contiguous()
         prog = self.program(X, kc, kind == capi.KIND_HESSIAN)
@@ -166,7 +166,7 @@ class Engine:
             capi.check(capi.lib().curv_matmat_batch(
                 prog.handle, kind, loss, pptrs, prog.const_ptrs, X.data_ptr(),
                 0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
-                V.data_ptr(), out.data_ptr(), kk, V.shape[1], k0, float(scale or 1.0), float(alpha),
+                V.data_ptr(), out.data_ptr(), kk, K, k0, float(scale or 1.0), float(alpha),
                 ws.data_ptr(), ws.numel() * 4, stream))
         del keep
 

@@ -168,6 +168,11 @@ const char* curv_last_error(void);
 int curv_abi_version(void);
 /* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
 long long curv_launch_count(void);
+/* Per-launch CUDA-event timing of the contraction kernels (class 0: gather GEMM = forward/dgrad,
+   class 1: wgrad GEMM).  enable(1) clears and starts recording, read() synchronises on the recorded
+   events and returns summed milliseconds, algorithmic FLOPs and launch counts per class. */
+int curv_profile_enable(int on);
+int curv_profile_read(double* ms, double* flops, long long* count);
 /* 0: SIMT fp32 contraction kernels, 1: tcgen05 (3xTF32 split) tensor-core kernels where eligible */
 int curv_set_tensor_core_mode(int mode);
 
