@@ -265,7 +265,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   if (nslots <= 0) return CURV_OK;
   const Geom& g = a.g;
   ProfScope prof(0, flops, st);
-  if (g_tc_mode && tc_gather_eligible(g)) {
+  if (g_tc_mode && tc_gather_eligible(g, g_tc_mode)) {
     int rc = tc_launch_gather_gemm(a, nslots, st);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");

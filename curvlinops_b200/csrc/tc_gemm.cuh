@@ -1,7 +1,408 @@
-// tcgen05 tensor-core path (placeholder until the kernel lands): nothing is eligible.
+// tcgen05 tensor-core path of the gather GEMM (forward conv + K tangents, dgrad), sm_100a only.
+//
+//   out[m][n] = sum_seg sum_r gather(A_seg)[m][r] * W_seg[n][r]        (same contract as gemm_simt.cuh)
+//
+// fp32 in, fp32 out, fp32-grade accuracy on the TF32 tensor pipe by the 3xTF32 split
+//   a = a_hi + a_lo,  b = b_hi + b_lo   (hi = top 19 bits, lo = remainder, both exactly TF32)
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo            (dropped a_lo*b_lo ~ 2^-22 relative)
+// accumulated in fp32 in tensor memory.
+//
+// Persistent, warp-specialised CTA (416 threads, one CTA per SM):
+//   warps 0-3   epilogue : tcgen05.ld accumulator -> registers -> (+bias, +=) -> global
+//   warp  4     MMA      : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), 12 per stage
+//   warps 5-12  producers: implicit-im2col gather, global -> registers -> hi/lo split ->
+//                          st.shared into the 128B-swizzled K-major UMMA layout (software "TMA":
+//                          the gather is per 16-byte channel group, which TMA tiles cannot express
+//                          for padded / strided / transposed-stride convolutions)
+// Pipelines: smem ring (full/empty mbarriers, STAGES deep), TMEM double buffer (tmem_full/empty).
+// Every mbarrier wait is bounded and traps instead of hanging the GPU.
 #pragma once
 #include "common.cuh"
+
 namespace curv {
-static inline bool tc_gather_eligible(const Geom&) { return false; }
+
+#ifndef CURV_DISABLE_TC
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
+constexpr int TC_THREADS = 416;
+constexpr int TC_PRODUCERS = 256;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (CUDA error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_async_proxy() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_tf32_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
+  auto h = [](float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); };
+  hi = make_float4(h(v.x), h(v.y), h(v.z), h(v.w));
+  lo = make_float4(h(v.x - hi.x), h(v.y - hi.y), h(v.z - hi.z), h(v.w - hi.w));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = ceil_div(g.Nd, BN);
+  const int tiles_m = ceil_div(g.M, TC_BM);
+  const int ntiles = tiles_m * tiles_n * nslots;
+  const int nchunks = ceil_div(g.Kd, TC_BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode_tile = [&](int tile, int& slot, int& m0, int& n0) {
+    int si = tile % nslots;
+    int rest = tile / nslots;
+    int tn = rest % tiles_n;
+    int tm = rest / tiles_n;
+    slot = p.slot0 + si; m0 = tm * TC_BM; n0 = tn * BN;
+  };
+  auto segments = [&](int slot, const float* (&segA)[2], const float* (&segB)[2]) {
+    int nseg = 0;
+    if (slot == 0) { segA[0] = p.A; segB[0] = p.W; nseg = 1; }
+    else {
+      if (p.a_has_slots) { segA[nseg] = p.A + (long long)slot * p.A_slot; segB[nseg] = p.W; ++nseg; }
+      if (p.Wt != nullptr) { segA[nseg] = p.A; segB[nseg] = p.Wt + (long long)(slot - 1) * p.Wt_slot; ++nseg; }
+    }
+    return nseg;
+  };
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ producers
+    const int pt = threadIdx.x - 5 * 32;          // 0..255
+    const int a_row = pt >> 1, a_c0 = (pt & 1) * 4;  // 4 of the 8 16-byte chunks of an A row
+    constexpr int BCH = BN / 32;                  // B chunks per thread (4 or 2)
+    const int b_row = (BN == 128) ? (pt >> 1) : (pt >> 2);
+    const int b_c0 = (BN == 128) ? (pt & 1) * 4 : (pt & 3) * 2;
+    const uint32_t a_off = (uint32_t)((a_row >> 3) * 1024 + (a_row & 7) * 128);
+    const uint32_t b_off = (uint32_t)((b_row >> 3) * 1024 + (b_row & 7) * 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot, m0, n0;
+      decode_tile(tile, slot, m0, n0);
+      const float* segA[2];
+      const float* segB[2];
+      const int nseg = segments(slot, segA, segB);
+      // A row -> destination pixel
+      const int m = m0 + a_row;
+      const bool m_ok = m < g.M;
+      const int mm = m_ok ? m : 0;
+      const int bimg = mm / (g.Hd * g.Wd);
+      const int rem = mm - bimg * (g.Hd * g.Wd);
+      const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+      const int ah = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
+      const int aw = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
+      const long long abase = (long long)bimg * g.Hs * g.Ws;
+      const int n = n0 + b_row;
+      const bool n_ok = n < g.N;
+      for (int seg = 0; seg < nseg; ++seg) {
+        const float* Ap = segA[seg];
+        const float* Bp = segB[seg] + (long long)(n_ok ? n : 0) * g.Kd;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          float4 va[4], vb[BCH];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = kc * TC_BK + (a_c0 + j) * 4;
+            bool ok = m_ok && r < g.Kd;
+            const int tap = r / g.Cs;
+            const int c = r - tap * g.Cs;
+            const int kh = tap / g.KW, kw = tap - kh * g.KW;
+            int hs, ws;
+            if (g.mode == 0) { hs = ah + kh; ws = aw + kw; }
+            else {
+              const int th = ah - kh, tw = aw - kw;
+              ok = ok && th >= 0 && tw >= 0;
+              hs = th / g.sh; ws = tw / g.sw;
+              ok = ok && hs * g.sh == th && ws * g.sw == tw;
+            }
+            ok = ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+            va[j] = ok ? __ldg(reinterpret_cast<const float4*>(
+                             Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + c)))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < BCH; ++j) {
+            const int r = kc * TC_BK + (b_c0 + j) * 4;
+            vb[j] = (n_ok && r < g.Kd) ? __ldg(reinterpret_cast<const float4*>(Bp + r))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 hi, lo;
+            split_tf32(va[j], hi, lo);
+            const uint32_t o = a_off + (uint32_t)(((a_c0 + j) ^ (a_row & 7)) << 4);
+            sts128(sA + o, hi);
+            sts128(sA + Cfg::A_BYTES + o, lo);
+          }
+#pragma unroll
+          for (int j = 0; j < BCH; ++j) {
+            float4 hi, lo;
+            split_tf32(vb[j], hi, lo);
+            const uint32_t o = b_off + (uint32_t)(((b_c0 + j) ^ (b_row & 7)) << 4);
+            sts128(sB + o, hi);
+            sts128(sB + Cfg::B_BYTES + o, lo);
+          }
+          fence_async_proxy();
+          mbar_arrive(full_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_tf32_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int slot, m0, n0;
+        decode_tile(tile, slot, m0, n0);
+        const float* segA[2];
+        const float* segB[2];
+        const int T = segments(slot, segA, segB) * nchunks;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int it = 0; it < T; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
+          const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
+          const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes per K=8 step
+            tc_mma_tf32(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            tc_mma_tf32(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot, m0, n0;
+      decode_tile(tile, slot, m0, n0);
+      const float* bias = (slot == 0) ? p.bias
+                                      : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
+      float* outp = p.out + (long long)slot * p.out_slot;
+      const int m = m0 + warp * 32 + lane;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
+        tc_ld32(taddr, r);
+        if (m < g.M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + c0 + j * 4;
+            if (n >= g.Nd) continue;
+            float4 v = make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]),
+                                   __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
+            if (bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(outp + (long long)m * g.Nd + n);
+            if (p.accumulate) {
+              const float4 o = *dst;
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+static inline bool tc_gather_eligible(const Geom& g, int mode) {
+  if (mode >= 2) return true;  // forced (tests): every shape is legal, small ones just waste tiles
+  // big enough to fill 128-row tiles; everything else stays on the SIMT kernels
+  return g.M >= 1024 && g.Kd >= 32 && g.Nd >= 16;
+}
+
+// returns 0 on success, >0 on a CUDA error, <0 if the problem should use the SIMT path
+static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
+  static int sm_count = 0;
+  static bool attr_set = false;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 1;
+    if (prop.major != 10) return -1;  // tcgen05 needs sm_100
+    sm_count = prop.multiProcessorCount;
+  }
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TcCfg<128>::SMEM_BYTES) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TcCfg<64>::SMEM_BYTES) != cudaSuccess) return 1;
+    attr_set = true;
+  }
+  const Geom& g = a.g;
+  if (g.Nd > 64) {
+    int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
+    int grid = ntiles < sm_count ? ntiles : sm_count;
+    gather_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+  } else {
+    int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
+    int grid = ntiles < sm_count ? ntiles : sm_count;
+    gather_gemm_tc<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+#else
+static inline bool tc_gather_eligible(const Geom&, int) { return false; }
 static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t) { return -1; }
+#endif
+
 }  // namespace curv

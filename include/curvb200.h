@@ -173,7 +173,8 @@ long long curv_launch_count(void);
    events and returns summed milliseconds, algorithmic FLOPs and launch counts per class. */
 int curv_profile_enable(int on);
 int curv_profile_read(double* ms, double* flops, long long* count);
-/* 0: SIMT fp32 contraction kernels, 1: tcgen05 (3xTF32 split) tensor-core kernels where eligible */
+/* 0: SIMT fp32 contraction kernels only, 1 (default): tcgen05 (3xTF32 split) tensor-core kernels for
+   layers large enough to fill 128-row tiles, 2: tcgen05 for every contraction (tests). Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);
 
 #ifdef __cplusplus

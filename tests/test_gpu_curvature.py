@@ -123,3 +123,50 @@ def test_wide_matrix_is_chunked():
     wide = G @ V
     for k in (0, 7, 8, 18):
         torch.testing.assert_close(wide[:, k], G @ V[:, k], rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 (3xTF32) contraction kernels: forced onto every layer, must agree with the fp32 SIMT kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture
+def force_tensor_cores():
+    from curvlinops_b200 import _capi as capi
+
+    old = capi.lib().curv_set_tensor_core_mode(2)
+    yield
+    capi.lib().curv_set_tensor_core_mode(old)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tcgen05_path_matches_reference_golden(name, force_tensor_cores):
+    model, loss, data, fx, params = _setup(name)
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(G @ fx["V"].float().cuda(), fx["ggn"], params)
+    H = HessianLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(H @ fx["V"].float().cuda(), fx["hessian"], params)
+
+
+def test_tcgen05_vs_simt_on_wide_convnet():
+    """Layers large enough for full 128x128 tiles, several K chunks, stride-2 dgrad, 2 segments."""
+    from curvlinops_b200 import _capi as capi
+    from torch import nn
+
+    torch.manual_seed(0)
+    model = nn.Sequential(
+        nn.Conv2d(3, 64, 3, 1, 1), nn.ReLU(), nn.Conv2d(64, 160, 3, 2, 1), nn.ReLU(),
+        nn.Conv2d(160, 96, 1, 1, 0, bias=False), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+        nn.Linear(96, 10)).cuda().eval()
+    params = dict(model.named_parameters())
+    X, y = torch.rand(6, 3, 24, 24, device="cuda"), torch.randint(0, 10, (6,), device="cuda")
+    G = GGNLinearOperator(model, nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False)
+    V = torch.rand(G.shape[1], 3, device="cuda")
+    old = capi.lib().curv_set_tensor_core_mode(0)
+    try:
+        ref = G @ V
+        capi.lib().curv_set_tensor_core_mode(2)
+        got = G @ V
+        assert torch.equal(got, G @ V), "tcgen05 path must be run-to-run deterministic"
+    finally:
+        capi.lib().curv_set_tensor_core_mode(old)
+    err = (got - ref).abs().max() / ref.abs().max()
+    assert err < 2e-5, err
