@@ -32,6 +32,10 @@ struct GatherGemmArgs {
   const float* W;
   const float* Wt;
   long long Wt_slot;
+  // tcgen05 path only: pre-split / pre-swizzled images of W and Wt (tc_gemm.cuh), null -> SIMT path
+  const float* W_img;
+  const float* Wt_img;
+  long long Wt_img_slot;
   const float* bias;    // [Nd] added to slot 0 (may be null)
   const float* bias_t;  // [(k-1)*bias_slot + n] added to slot k (may be null)
   long long bias_slot;

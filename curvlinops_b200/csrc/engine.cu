@@ -65,6 +65,9 @@ struct Node {
   Geom fwd, dgr;
   long long wk_off = -1, wt_off = -1, wkt_off = -1, wtt_off = -1;  // packed weight, transposed, tangents
   long long wsize = 0, wtsize = 0;
+  // tcgen05 weight images (forward geometry: W, tangents; dgrad geometry: W^T, tangents)
+  long long wimg_off = -1, wimgt_off = -1, wtimg_off = -1, wtimgt_off = -1;
+  long long wimg_size = 0, wtimg_size = 0;
   long long bias_off = -1, biast_off = -1;
   int nsplit = 1, m_per_split = 0;
   int wbm = 64, wbn = 64;
@@ -148,6 +151,16 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       if (d.p0 >= 0) {
         n.wkt_off = alloc(n.wsize * kmax);
         if (hessian && vi.tan) n.wtt_off = alloc(n.wtsize * kmax);
+      }
+      n.wimg_size = tc_image_elems(g.N, g.Nd, g.Kd);
+      n.wtimg_size = tc_image_elems(q.N, q.Nd, q.Kd);
+      if (n.wimg_size > 0) {
+        n.wimg_off = alloc(n.wimg_size);
+        if (vi.tan) n.wtimg_off = alloc(n.wtimg_size);
+        if (d.p0 >= 0) {
+          n.wimgt_off = alloc(n.wimg_size * kmax);
+          if (hessian && vi.tan) n.wtimgt_off = alloc(n.wtimg_size * kmax);
+        }
       }
       if (d.p1 >= 0 || d.c1 >= 0) n.bias_off = alloc(vo.Cp);
       if (d.p1 >= 0) n.biast_off = alloc((long long)vo.Cp * kmax);
@@ -265,7 +278,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   if (nslots <= 0) return CURV_OK;
   const Geom& g = a.g;
   ProfScope prof(0, flops, st);
-  if (g_tc_mode && tc_gather_eligible(g, g_tc_mode)) {
+  if (g_tc_mode && a.W_img != nullptr) {
     int rc = tc_launch_gather_gemm(a, nslots, st);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
@@ -288,6 +301,11 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
 static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, double flops = 0) {
   const Geom& g = a.g;
   ProfScope prof(1, flops, st);
+  if (g_tc_mode && tc_wgrad_eligible(g, g_tc_mode)) {
+    int rc = tc_launch_wgrad(a, st);
+    if (rc == 0) { ++g_launches; return CURV_OK; }
+    if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 wgrad GEMM launch failed");
+  }
   dim3 grid(ceil_div(g.N, bm) * ceil_div(g.Kd, bn), a.nslots, a.nsplit);
   if (bm == 128 && bn == 128) wgrad_gemm_simt<128, 128><<<grid, 256, 0, st>>>(a);
   else if (bm == 128) wgrad_gemm_simt<128, 64><<<grid, 256, 0, st>>>(a);
@@ -352,6 +370,29 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
           LAUNCH_CHECK();
         }
       }
+      if (g_tc_mode && n.wimg_off >= 0) {  // tcgen05 weight images
+        const Geom& q = n.dgr;
+        int bad = 0;
+        if (tc_gather_eligible(g, g_tc_mode)) {
+          bad |= tc_pack_image(c.ws + n.wk_off, 0, c.ws + n.wimg_off, 0, g.N, g.Nd, g.Kd, 1, st) > 0;
+          ++g_launches;
+          if (with_tangents && d.p0 >= 0) {
+            bad |= tc_pack_image(c.ws + n.wkt_off, n.wsize, c.ws + n.wimgt_off, n.wimg_size, g.N, g.Nd, g.Kd,
+                                 c.K, st) > 0;
+            ++g_launches;
+          }
+        }
+        if (n.wtimg_off >= 0 && tc_gather_eligible(q, g_tc_mode)) {
+          bad |= tc_pack_image(c.ws + n.wt_off, 0, c.ws + n.wtimg_off, 0, q.N, q.Nd, q.Kd, 1, st) > 0;
+          ++g_launches;
+          if (with_tangents && n.wtimgt_off >= 0) {
+            bad |= tc_pack_image(c.ws + n.wtt_off, n.wtsize, c.ws + n.wtimgt_off, n.wtimg_size, q.N, q.Nd,
+                                 q.Kd, c.K, st) > 0;
+            ++g_launches;
+          }
+        }
+        if (bad) return fail(CURV_ERR_CUDA, "tcgen05 weight image packing failed");
+      }
       if (n.bias_off >= 0) {
         const float* b = d.p1 >= 0 ? c.param(d.p1) : c.cst(d.c1);
         pack_vec_kernel<<<dim3(grid1d(g.Nd), 1), 256, 0, st>>>(b, 1, c.ws + n.bias_off, 0, g.N, g.Nd);
@@ -401,6 +442,10 @@ static int forward(const Ctx& c, const void* X, int K) {
         a.A = c.act(d.in0); a.A_slot = vi.slot_elems; a.a_has_slots = vi.tan ? 1 : 0;
         a.W = c.ws + n.wk_off;
         a.Wt = (d.p0 >= 0) ? c.ws + n.wkt_off : nullptr; a.Wt_slot = n.wsize;
+        if (g_tc_mode && n.wimg_off >= 0 && tc_gather_eligible(n.fwd, g_tc_mode)) {
+          a.W_img = c.ws + n.wimg_off;
+          a.Wt_img = (d.p0 >= 0 && K > 0) ? c.ws + n.wimgt_off : nullptr; a.Wt_img_slot = n.wimg_size;
+        }
         a.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
         a.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; a.bias_slot = vo.Cp;
         a.out = c.act(d.out); a.out_slot = vo.slot_elems;
@@ -545,6 +590,10 @@ static int backward(const Ctx& c, int K) {
           a.A = c.grad(d.out); a.A_slot = vo.slot_elems; a.a_has_slots = 1;
           a.W = c.ws + n.wt_off;
           a.Wt = (rop && n.wtt_off >= 0) ? c.ws + n.wtt_off : nullptr; a.Wt_slot = n.wtsize;
+          if (g_tc_mode && n.wtimg_off >= 0 && tc_gather_eligible(n.dgr, g_tc_mode)) {
+            a.W_img = c.ws + n.wtimg_off;
+            a.Wt_img = (rop && n.wtimgt_off >= 0) ? c.ws + n.wtimgt_off : nullptr; a.Wt_img_slot = n.wtimg_size;
+          }
           a.out = c.grad(d.in0); a.out_slot = vi.slot_elems;
           a.slot0 = s0; a.accumulate = ginit[d.in0];
           int rc = launch_gather_gemm(a, ns, st, conv_flops(g, vi.C) * ns * (a.Wt ? 2 : 1));

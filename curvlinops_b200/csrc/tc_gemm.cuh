@@ -113,6 +113,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled operand tile: smem row = one reduction index (8-row groups of 1024 bytes =
+// one K=8 MMA step), 128 bytes = 32 MN-contiguous fp32; 32-wide MN atoms are 4096 bytes apart
+// (a stage holds 32 reduction rows = 4 groups).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: stride between MN atoms
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
 __host__ __device__ constexpr uint32_t make_tf32_idesc(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -129,36 +141,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
                : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// shared CTA prologue / epilogue pieces
+// ---------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
+struct TcSmem {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint32_t base, bar_base;
+  __device__ explicit TcSmem(uint8_t* raw) {
+    base = (smem_u32(raw) + 1023u) & ~1023u;
+    bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  }
+  __device__ uint32_t full(int s) const { return bar_base + 8u * s; }
+  __device__ uint32_t empty(int s) const { return bar_base + 8u * (Cfg::STAGES + s); }
+  __device__ uint32_t tfull(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + a); }
+  __device__ uint32_t tempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); }
+  __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * Cfg::STAGES + 4); }
+  __device__ uint32_t stageA(int s) const { return base + s * Cfg::STAGE_BYTES; }
+  __device__ uint32_t stageB(int s) const { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; }
+};
 
-  const Geom& g = p.g;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = ceil_div(g.Nd, BN);
-  const int tiles_m = ceil_div(g.M, TC_BM);
-  const int ntiles = tiles_m * tiles_n * nslots;
-  const int nchunks = ceil_div(g.Kd, TC_BK);
-
+// barrier init + TMEM allocation; returns the TMEM base address.  full_count = arrivals per stage.
+template <int BN>
+__device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* raw, int full_count) {
+  using Cfg = TcCfg<BN>;
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(S.full(s), full_count); mbar_init(S.empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(S.tmem_slot()),
                  "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -166,145 +180,217 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  return *reinterpret_cast<volatile uint32_t*>(raw + (S.tmem_slot() - smem_u32(raw)));
+}
+template <int BN>
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TcCfg<BN>::TMEM_COLS)
+                 : "memory");
+  }
+}
 
-  auto decode_tile = [&](int tile, int& slot, int& m0, int& n0) {
+// MMA issuer loop body for one tile of T stages: 3xTF32 = 12 MMAs per 32-deep stage.
+// DESC(addr) builds the smem descriptor; K_ADV = descriptor start-address advance (16-byte units) per K=8.
+template <int BN, bool MN_MAJOR>
+__device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tmem, int T, int& stage,
+                                              uint32_t& phase) {
+  using Cfg = TcCfg<BN>;
+  constexpr uint32_t idesc = make_tf32_idesc(BN) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
+  for (int it = 0; it < T; ++it) {
+    mbar_wait(S.full(stage), phase);
+    tc_fence_after();
+    const uint32_t sA = S.stageA(stage), sB = S.stageB(stage);
+    uint64_t dAh, dAl, dBh, dBl;
+    if (MN_MAJOR) {
+      dAh = make_mnmajor_sw128_desc(sA); dAl = make_mnmajor_sw128_desc(sA + Cfg::A_BYTES);
+      dBh = make_mnmajor_sw128_desc(sB); dBl = make_mnmajor_sw128_desc(sB + Cfg::B_BYTES);
+    } else {
+      dAh = make_kmajor_sw128_desc(sA); dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
+      dBh = make_kmajor_sw128_desc(sB); dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
+    }
+#pragma unroll
+    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+      // K-major: +32 bytes inside the 128-byte row; MN-major: next 8-row group (+1024 bytes)
+      const uint64_t adv = (uint64_t)((MN_MAJOR ? ks * 1024 : ks * 32) >> 4);
+      tc_mma_tf32(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+      tc_mma_tf32(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+      tc_mma_tf32(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+    }
+    tc_commit(S.empty(stage));  // frees the smem stage when these MMAs retire
+    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gather GEMM (forward conv + tangents, dgrad):  out[m][n] = sum_seg sum_r gather(A)[m][r] * W[n][r]
+// A: gathered by the producer warps (hi/lo split on the fly).  W: pre-split, pre-swizzled "UMMA image"
+// (pack_umma_kmajor_kernel), one cp.async.bulk per stage straight into shared memory.
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const TcSmem<BN> S(smem_raw);
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = ceil_div(g.Nd, BN);
+  const int tiles_m = ceil_div(g.M, TC_BM);
+  const int ntiles = tiles_m * tiles_n * nslots;
+  const int nchunks = ceil_div(g.Kd, TC_BK);
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
+
+  auto decode_tile = [&](int tile, int& slot, int& m0, int& tn) {
     int si = tile % nslots;
     int rest = tile / nslots;
-    int tn = rest % tiles_n;
-    int tm = rest / tiles_n;
-    slot = p.slot0 + si; m0 = tm * TC_BM; n0 = tn * BN;
+    tn = rest % tiles_n;
+    slot = p.slot0 + si; m0 = (rest / tiles_n) * TC_BM;
   };
-  auto segments = [&](int slot, const float* (&segA)[2], const float* (&segB)[2]) {
-    int nseg = 0;
-    if (slot == 0) { segA[0] = p.A; segB[0] = p.W; nseg = 1; }
-    else {
-      if (p.a_has_slots) { segA[nseg] = p.A + (long long)slot * p.A_slot; segB[nseg] = p.W; ++nseg; }
-      if (p.Wt != nullptr) { segA[nseg] = p.A; segB[nseg] = p.Wt + (long long)(slot - 1) * p.Wt_slot; ++nseg; }
+  // segment s of a slot: activation base and weight image base
+  auto segment = [&](int slot, int s, const float*& A, const float*& Wimg) {
+    const bool first_is_act = (slot == 0) || p.a_has_slots;
+    if (s == 0 && first_is_act) {
+      A = p.A + (long long)slot * p.A_slot; Wimg = p.W_img;
+    } else {
+      A = p.A; Wimg = p.Wt_img + (long long)(slot - 1) * p.Wt_img_slot;
     }
-    return nseg;
+  };
+  auto num_segments = [&](int slot) {
+    return slot == 0 ? 1 : (p.a_has_slots ? 1 : 0) + (p.Wt_img != nullptr ? 1 : 0);
   };
 
   if (warp >= 5) {
     // ------------------------------------------------------------------ producers
-    const int pt = threadIdx.x - 5 * 32;          // 0..255
+    const int pt = threadIdx.x - 5 * 32;             // 0..255
     const int a_row = pt >> 1, a_c0 = (pt & 1) * 4;  // 4 of the 8 16-byte chunks of an A row
-    constexpr int BCH = BN / 32;                  // B chunks per thread (4 or 2)
-    const int b_row = (BN == 128) ? (pt >> 1) : (pt >> 2);
-    const int b_c0 = (BN == 128) ? (pt & 1) * 4 : (pt & 3) * 2;
     const uint32_t a_off = (uint32_t)((a_row >> 3) * 1024 + (a_row & 7) * 128);
-    const uint32_t b_off = (uint32_t)((b_row >> 3) * 1024 + (b_row & 7) * 128);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int slot, m0, n0;
-      decode_tile(tile, slot, m0, n0);
-      const float* segA[2];
-      const float* segB[2];
-      const int nseg = segments(slot, segA, segB);
-      // A row -> destination pixel
+    const bool fast = (g.Cs % TC_BK) == 0;  // a 128-byte K row never straddles two filter taps
+    // iteration state
+    int tile = blockIdx.x, slot = 0, m0 = 0, tn = 0, nseg = 0, seg = 0, kc = 0;
+    int kh = 0, kw = 0, cb = 0;
+    bool m_ok = false;
+    int ah = 0, aw = 0;
+    long long abase = 0;
+    const float* Ap = nullptr;
+    const float* Wimg = nullptr;
+    auto enter_tile = [&]() {
+      decode_tile(tile, slot, m0, tn);
+      nseg = num_segments(slot);
       const int m = m0 + a_row;
-      const bool m_ok = m < g.M;
+      m_ok = m < g.M;
       const int mm = m_ok ? m : 0;
       const int bimg = mm / (g.Hd * g.Wd);
       const int rem = mm - bimg * (g.Hd * g.Wd);
       const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
-      const int ah = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
-      const int aw = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
-      const long long abase = (long long)bimg * g.Hs * g.Ws;
-      const int n = n0 + b_row;
-      const bool n_ok = n < g.N;
-      for (int seg = 0; seg < nseg; ++seg) {
-        const float* Ap = segA[seg];
-        const float* Bp = segB[seg] + (long long)(n_ok ? n : 0) * g.Kd;
-        for (int kc = 0; kc < nchunks; ++kc) {
-          float4 va[4], vb[BCH];
+      ah = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
+      aw = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
+      abase = (long long)bimg * g.Hs * g.Ws;
+      seg = 0; kc = 0; kh = 0; kw = 0; cb = 0;
+      segment(slot, 0, Ap, Wimg);
+    };
+    auto source_pixel = [&](int kh_, int kw_, int& hs, int& ws) -> bool {
+      bool ok = m_ok;
+      if (g.mode == 0) { hs = ah + kh_; ws = aw + kw_; }
+      else {
+        const int th = ah - kh_, tw = aw - kw_;
+        ok = ok && th >= 0 && tw >= 0;
+        hs = th / g.sh; ws = tw / g.sw;
+        ok = ok && hs * g.sh == th && ws * g.sw == tw;
+      }
+      return ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+    };
+    auto issue = [&](float4 (&v)[4]) {
+      if (fast) {
+        int hs, ws;
+        const bool ok = source_pixel(kh, kw, hs, ws);
+        const float* rowp = Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + cb + a_c0 * 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = kc * TC_BK + (a_c0 + j) * 4;
-            bool ok = m_ok && r < g.Kd;
-            const int tap = r / g.Cs;
-            const int c = r - tap * g.Cs;
-            const int kh = tap / g.KW, kw = tap - kh * g.KW;
-            int hs, ws;
-            if (g.mode == 0) { hs = ah + kh; ws = aw + kw; }
-            else {
-              const int th = ah - kh, tw = aw - kw;
-              ok = ok && th >= 0 && tw >= 0;
-              hs = th / g.sh; ws = tw / g.sw;
-              ok = ok && hs * g.sh == th && ws * g.sw == tw;
-            }
-            ok = ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
-            va[j] = ok ? __ldg(reinterpret_cast<const float4*>(
-                             Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + c)))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int j = 0; j < 4; ++j)
+          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(rowp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
 #pragma unroll
-          for (int j = 0; j < BCH; ++j) {
-            const int r = kc * TC_BK + (b_c0 + j) * 4;
-            vb[j] = (n_ok && r < g.Kd) ? __ldg(reinterpret_cast<const float4*>(Bp + r))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 hi, lo;
-            split_tf32(va[j], hi, lo);
-            const uint32_t o = a_off + (uint32_t)(((a_c0 + j) ^ (a_row & 7)) << 4);
-            sts128(sA + o, hi);
-            sts128(sA + Cfg::A_BYTES + o, lo);
-          }
-#pragma unroll
-          for (int j = 0; j < BCH; ++j) {
-            float4 hi, lo;
-            split_tf32(vb[j], hi, lo);
-            const uint32_t o = b_off + (uint32_t)(((b_c0 + j) ^ (b_row & 7)) << 4);
-            sts128(sB + o, hi);
-            sts128(sB + Cfg::B_BYTES + o, lo);
-          }
-          fence_async_proxy();
-          mbar_arrive(full_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int j = 0; j < 4; ++j) {
+          const int r = kc * TC_BK + (a_c0 + j) * 4;
+          const int tap = r / g.Cs;
+          const int c = r - tap * g.Cs;
+          const int kh_ = tap / g.KW, kw_ = tap - kh_ * g.KW;
+          int hs, ws;
+          const bool ok = r < g.Kd && source_pixel(kh_, kw_, hs, ws);
+          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(
+                          Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + c)))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    };
+    // advance to the next (tile, seg, kc); returns false when this CTA is done
+    auto advance = [&]() -> bool {
+      ++kc;
+      cb += TC_BK;
+      if (cb >= g.Cs) { cb = 0; if (++kw == g.KW) { kw = 0; ++kh; } }
+      if (kc < nchunks) return true;
+      kc = 0; kh = 0; kw = 0; cb = 0;
+      if (++seg < nseg) { segment(slot, seg, Ap, Wimg); return true; }
+      tile += gridDim.x;
+      if (tile >= ntiles) return false;
+      enter_tile();
+      return true;
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    bool have = tile < ntiles;
+    float4 cur[4], nxt[4];
+    if (have) { enter_tile(); issue(cur); }
+    while (have) {
+      // weight block of the current iteration (captured before the state advances)
+      const float* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK);
+      const bool have_next = advance();
+      if (have_next) issue(nxt);  // prefetch: next stage's loads are in flight while we store
+      mbar_wait(S.empty(stage), phase ^ 1);
+      const uint32_t sA = S.stageA(stage);
+      if (pt == 0) {
+        const uint32_t bytes = 2 * Cfg::B_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                S.stageB(stage)),
+            "l"(wsrc), "r"(bytes), "r"(S.full(stage))
+            : "memory");
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 hi, lo;
+        split_tf32(cur[j], hi, lo);
+        const uint32_t o = a_off + (uint32_t)(((a_c0 + j) ^ (a_row & 7)) << 4);
+        sts128(sA + o, hi);
+        sts128(sA + Cfg::A_BYTES + o, lo);
+      }
+      fence_async_proxy();
+      mbar_arrive(S.full(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      have = have_next;
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_tf32_idesc(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int slot, m0, n0;
-        decode_tile(tile, slot, m0, n0);
-        const float* segA[2];
-        const float* segB[2];
-        const int T = segments(slot, segA, segB) * nchunks;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        int slot, m0, tn;
+        decode_tile(tile, slot, m0, tn);
+        const int T = num_segments(slot) * nchunks;
+        mbar_wait(S.tempty(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int it = 0; it < T; ++it) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + 2 * Cfg::A_BYTES;
-          const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
-          const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes per K=8 step
-            tc_mma_tf32(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-            tc_mma_tf32(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-            tc_mma_tf32(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
-          }
-          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), T, stage, phase);
+        tc_commit(S.tfull(acc));  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -314,19 +400,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int slot, m0, n0;
-      decode_tile(tile, slot, m0, n0);
+      int slot, m0, tn;
+      decode_tile(tile, slot, m0, tn);
+      const int n0 = tn * BN;
       const float* bias = (slot == 0) ? p.bias
                                       : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
       float* outp = p.out + (long long)slot * p.out_slot;
       const int m = m0 + warp * 32 + lane;
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(S.tfull(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
-        tc_ld32(taddr, r);
+        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         if (m < g.M) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -348,61 +434,331 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      mbar_arrive(S.tempty(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  tc_teardown<BN>(tmem_base);
+}
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
+// Pre-split, pre-swizzled weight image for gather_gemm_tc:
+//   block (tn, kc) = [hi plane: BN rows x 128 B, 128B-swizzled][lo plane], blocks ordered tn-major.
+// src: [N][Kd] row-major (the SIMT-layout packed weights).  grid.y = slot.
+__global__ void pack_umma_kmajor_kernel(const float* __restrict__ src, long long src_slot,
+                                        float* __restrict__ dst, long long dst_slot, int N, int Kd, int BN,
+                                        int tiles_n, int nchunks) {
+  src += blockIdx.y * src_slot;
+  dst += blockIdx.y * dst_slot;
+  const long long total = (long long)tiles_n * nchunks * BN * 8;  // 16-byte chunks per plane
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    long long t = e >> 3;
+    const int r = (int)(t % BN); t /= BN;
+    const int kc = (int)(t % nchunks);
+    const int tn = (int)(t / nchunks);
+    const int n = tn * BN + r, k = kc * TC_BK + c * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N && k < Kd) v = __ldg(reinterpret_cast<const float4*>(src + (long long)n * Kd + k));
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    float* blk = dst + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 2;
+    *reinterpret_cast<float4*>(blk + o) = hi;
+    *reinterpret_cast<float4*>(blk + BN * TC_BK + o) = lo;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// wgrad GEMM on tcgen05:  D[i][j] = sum_m P[m][i] * Q[m][j]  over a split of the pixel range,
+// both operands MN-major (the reduction index m = pixel is the smem row).
+//   swap == 0:  P = G (i = output channel n, 128 per tile),  Q = gathered input (j = tap*Cs + c)
+//   swap == 1:  P = gathered input (i = tap*Cs + c),         Q = G (j = n)      [for C_out <= 64]
+// partial[(split*nslots + slot_idx)][n][tap*Cs + c]
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p, int swap) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const TcSmem<BN> S(smem_raw);
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile grid: i over (channels | Kd) in 128s, j over (Kd | channels) in BNs
+  const int ext_i = swap ? g.Kd : g.N;
+  const int ext_j = swap ? p.Ng : g.Kd;
+  const int tiles_i = ceil_div(ext_i, TC_BM), tiles_j = ceil_div(ext_j, BN);
+  const int ntiles = tiles_i * tiles_j * p.nslots * p.nsplit;
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS);
+
+  auto decode_tile = [&](int tile, int& slot_idx, int& split, int& i0, int& j0) {
+    slot_idx = tile % p.nslots;
+    int rest = tile / p.nslots;
+    const int tj = rest % tiles_j; rest /= tiles_j;
+    const int ti = rest % tiles_i;
+    split = rest / tiles_i;
+    i0 = ti * TC_BM; j0 = tj * BN;
+  };
+  auto num_segments = [&](int slot) { return (p.second_seg && slot > 0) ? 2 : 1; };
+  auto stages_of = [&](int split) {
+    const int mb = split * p.m_per_split;
+    const int me = min(g.M, mb + p.m_per_split);
+    return ceil_div(max(0, me - mb), TC_BK);
+  };
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ producers
+    const int pt = threadIdx.x - 5 * 32;
+    const int krow = pt >> 3;            // pixel row of the 32-pixel stage
+    const int cg = pt & 7;               // chunk group: chunks cg*4 .. cg*4+3 of a 128-wide operand
+    // channel-operand (G) and gather-operand (In) extents in this tile
+    constexpr int GCH = 4;               // chunks per thread for a 128-wide operand
+    // smem offsets of this thread's chunks inside an MN-major plane
+    auto smem_off = [&](int c) {         // c = 16-byte chunk index along MN (0..31)
+      return (uint32_t)((c >> 3) * 4096 + (krow >> 3) * 1024 + (krow & 7) * 128 + (((c & 7) ^ (krow & 7)) << 4));
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot_idx, split, i0, j0;
+      decode_tile(tile, slot_idx, split, i0, j0);
+      const int slot = p.slot0 + slot_idx;
+      const int mb = split * p.m_per_split;
+      const int me = min(g.M, mb + p.m_per_split);
+      const int nst = stages_of(split);
+      const int nseg = num_segments(slot);
+      // G operand: channel offset / width of this tile;  In operand: reduction-column offset
+      const int ch0 = swap ? j0 : i0;          // first channel
+      const int chw = swap ? BN : TC_BM;       // channels in the tile (operand width)
+      const int col0 = swap ? i0 : j0;         // first tap*Cs+c column
+      const int colw = swap ? TC_BM : BN;
+      const uint32_t planeG = swap ? 2 * Cfg::A_BYTES : 0;     // G goes to the B planes when swapped
+      const uint32_t planeI = swap ? 0 : 2 * Cfg::A_BYTES;
+      const uint32_t loG = swap ? Cfg::B_BYTES : Cfg::A_BYTES;
+      const uint32_t loI = swap ? Cfg::A_BYTES : Cfg::B_BYTES;
+      // gather-operand chunk descriptors of this thread (fixed for the tile)
+      int ikh[GCH], ikw[GCH], ic[GCH];
+      bool iok[GCH];
+#pragma unroll
+      for (int q = 0; q < GCH; ++q) {
+        const int c = cg * 4 + q;                  // chunk index in the operand (0..31)
+        const int col = col0 + c * 4;
+        iok[q] = (c * 4 < colw) && col < g.Kd;
+        const int tap = iok[q] ? col / g.Cs : 0;
+        ic[q] = col - tap * g.Cs;
+        ikh[q] = tap / g.KW; ikw[q] = tap - ikh[q] * g.KW;
+      }
+      for (int seg = 0; seg < nseg; ++seg) {
+        const float* Gp = (seg == 0) ? p.G + (long long)slot * p.G_slot : p.G;
+        const float* Ip = (seg == 0) ? p.In : p.In + (long long)slot * p.In_slot;
+        for (int st = 0; st < nst; ++st) {
+          const int m = mb + st * TC_BK + krow;
+          const bool mok = m < me;
+          float4 vg[GCH], vi[GCH];
+          // G chunks (pure streaming)
+#pragma unroll
+          for (int q = 0; q < GCH; ++q) {
+            const int c = cg * 4 + q;
+            const int ch = ch0 + c * 4;
+            const bool ok = mok && (c * 4 < chw) && ch < p.Ng;
+            vg[q] = ok ? __ldg(reinterpret_cast<const float4*>(Gp + (long long)m * p.Ng + ch))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          // gathered input chunks
+          const int mm = mok ? m : 0;
+          const int bimg = mm / (g.Hd * g.Wd);
+          const int rem = mm - bimg * (g.Hd * g.Wd);
+          const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+          const int h0 = hd * g.sh - g.ph, w0 = wd * g.sw - g.pw;
+#pragma unroll
+          for (int q = 0; q < GCH; ++q) {
+            const int hs = h0 + ikh[q], ws = w0 + ikw[q];
+            const bool ok = mok && iok[q] && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+            vi[q] = ok ? __ldg(reinterpret_cast<const float4*>(
+                             Ip + ((((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + ic[q])))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          mbar_wait(S.empty(stage), phase ^ 1);
+          const uint32_t sbase = S.stageA(stage);
+#pragma unroll
+          for (int q = 0; q < GCH; ++q) {
+            const int c = cg * 4 + q;
+            float4 hi, lo;
+            if (c * 4 < chw) {
+              split_tf32(vg[q], hi, lo);
+              const uint32_t o = smem_off(c);
+              sts128(sbase + planeG + o, hi);
+              sts128(sbase + planeG + loG + o, lo);
+            }
+            if (c * 4 < colw) {
+              split_tf32(vi[q], hi, lo);
+              const uint32_t o = smem_off(c);
+              sts128(sbase + planeI + o, hi);
+              sts128(sbase + planeI + loI + o, lo);
+            }
+          }
+          fence_async_proxy();
+          mbar_arrive(S.full(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int slot_idx, split, i0, j0;
+        decode_tile(tile, slot_idx, split, i0, j0);
+        const int T = num_segments(p.slot0 + slot_idx) * stages_of(split);
+        mbar_wait(S.tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        tc_issue_tile<BN, true>(S, tmem_base + (uint32_t)(acc * BN), T, stage, phase);
+        tc_commit(S.tfull(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot_idx, split, i0, j0;
+      decode_tile(tile, slot_idx, split, i0, j0);
+      const bool empty_tile = stages_of(split) == 0;
+      float* outp = p.partial + ((long long)split * p.nslots + slot_idx) * (long long)g.N * g.Kd;
+      const int i = i0 + warp * 32 + lane;
+      mbar_wait(S.tfull(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if (empty_tile) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;  // no MMA was issued: accumulator content is stale
+        }
+        if (!swap) {
+          if (i < g.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = j0 + c0 + j * 4;
+              if (col >= g.Kd) continue;
+              *reinterpret_cast<float4*>(outp + (long long)i * g.Kd + col) =
+                  make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]),
+                              __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
+            }
+          }
+        } else {
+          if (i < g.Kd) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = j0 + c0 + j;
+              if (n < g.N) outp[(long long)n * g.Kd + i] = __uint_as_float(r[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(S.tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_teardown<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static inline int tc_bn(int width) { return width > 64 ? 128 : 64; }
 
 static inline bool tc_gather_eligible(const Geom& g, int mode) {
   if (mode >= 2) return true;  // forced (tests): every shape is legal, small ones just waste tiles
   // big enough to fill 128-row tiles; everything else stays on the SIMT kernels
   return g.M >= 1024 && g.Kd >= 32 && g.Nd >= 16;
 }
+static inline bool tc_wgrad_eligible(const Geom& g, int mode) {
+  if (mode >= 2) return true;
+  return g.M >= 2048 && g.Kd >= 32 && g.N >= 16;
+}
+// size (floats) of the UMMA weight image of an [N][Kd] matrix
+static inline long long tc_image_elems(int N, int Nd, int Kd) {
+  const int BN = tc_bn(Nd);
+  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, TC_BK) * (2 * BN * TC_BK);
+}
+
+static int tc_sm_count() {
+  static int sm_count = -1;
+  if (sm_count == -1) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    sm_count = prop.major == 10 ? prop.multiProcessorCount : 0;  // tcgen05 needs sm_100
+    if (sm_count > 0) {
+      bool ok = cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<128>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<128>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      if (!ok) sm_count = 0;
+    }
+  }
+  return sm_count;
+}
+
+// pack [N][Kd] (slots along grid.y) into the UMMA image layout used by gather_gemm_tc
+static inline int tc_pack_image(const float* src, long long src_slot, float* dst, long long dst_slot, int N,
+                                int Nd, int Kd, int nslots, cudaStream_t st) {
+  const int BN = tc_bn(Nd);
+  const int tiles_n = ceil_div(Nd, BN), nchunks = ceil_div(Kd, TC_BK);
+  long long total = (long long)tiles_n * nchunks * BN * 8;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_umma_kmajor_kernel<<<dim3(blocks, nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
+                                                              tiles_n, nchunks);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 // returns 0 on success, >0 on a CUDA error, <0 if the problem should use the SIMT path
 static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 1;
-    if (prop.major != 10) return -1;  // tcgen05 needs sm_100
-    sm_count = prop.multiProcessorCount;
-  }
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TcCfg<128>::SMEM_BYTES) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TcCfg<64>::SMEM_BYTES) != cudaSuccess) return 1;
-    attr_set = true;
-  }
+  const int sms = tc_sm_count();
+  if (sms <= 0 || a.W_img == nullptr) return -1;
   const Geom& g = a.g;
-  if (g.Nd > 64) {
+  if (tc_bn(g.Nd) == 128) {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
-    int grid = ntiles < sm_count ? ntiles : sm_count;
-    gather_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    gather_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
   } else {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
-    int grid = ntiles < sm_count ? ntiles : sm_count;
-    gather_gemm_tc<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    gather_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+static inline int tc_launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  const int sms = tc_sm_count();
+  if (sms <= 0) return -1;
+  const Geom& g = a.g;
+  const int swap = g.N <= 64 ? 1 : 0;
+  if (swap) {
+    int ntiles = ceil_div(g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nslots * a.nsplit;
+    wgrad_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, 1);
+  } else {
+    int ntiles = ceil_div(g.N, TC_BM) * ceil_div(g.Kd, 128) * a.nslots * a.nsplit;
+    wgrad_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, 0);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 #else
 static inline bool tc_gather_eligible(const Geom&, int) { return false; }
+static inline bool tc_wgrad_eligible(const Geom&, int) { return false; }
+static inline long long tc_image_elems(int, int, int) { return 0; }
+static inline int tc_pack_image(const float*, long long, float*, long long, int, int, int, int, cudaStream_t) { return -1; }
 static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t) { return -1; }
+static inline int tc_launch_wgrad(const WgradArgs&, cudaStream_t) { return -1; }
 #endif
 
 }  // namespace curv
