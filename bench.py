@@ -209,6 +209,13 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
 
+    # self-check outside the timed region: tcgen05 (3xTF32) path vs the exact-fp32 SIMT kernels, full size
+    got = G @ Vd[:, :2]
+    old_mode = capi.lib().curv_set_tensor_core_mode(0)
+    ref = G @ Vd[:, :2]
+    capi.lib().curv_set_tensor_core_mode(old_mode)
+    self_check = float((got - ref).abs().max() / ref.abs().max())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -244,6 +251,7 @@ def main():
                 "h2d_bytes_per_step": int(X_host.numel() * 4 + y_host.numel() * 8 + V_host.numel() * 4),
                 "d2h_bytes_per_step": int(P * K * 4)},
         "roofline": roof,
+        "self_check": {"tcgen05_vs_fp32_simt_max_rel_err": self_check, "columns": 2},
     }
     if not args.no_cpu_baseline and world == 1:
         value, t_full, cb = cpu_reference_run(torch, 1, 0)

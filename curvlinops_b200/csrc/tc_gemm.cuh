@@ -113,16 +113,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
-// MN-major, 128B-swizzled operand tile: smem row = one reduction index (8-row groups of 1024 bytes =
-// one K=8 MMA step), 128 bytes = 32 MN-contiguous fp32; 32-wide MN atoms are 4096 bytes apart
-// (a stage holds 32 reduction rows = 4 groups).
+// MN-major tf32 operand tile.  For 32-bit MN-major operands the only legal swizzled layout is
+// SWIZZLE_128B_BASE32B (CUTLASS sm100_common.inl:92): atoms of 4 reduction rows x 128 bytes (32
+// MN-contiguous fp32), XOR of the 32-byte chunk index (address bits 5-6) with the row-in-atom (bits 7-8).
+// A stage holds 32 reduction rows: row r of MN atom a lives at a*4096 + r*128 (K atoms 512 B apart).
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: stride between MN atoms
-  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: stride between 8-row K groups
+  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: stride between 32-wide MN atoms
+  d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: stride between 4-row K atoms
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;            // SWIZZLE_128B_BASE32B
   return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
@@ -515,7 +516,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
     constexpr int GCH = 4;               // chunks per thread for a 128-wide operand
     // smem offsets of this thread's chunks inside an MN-major plane
     auto smem_off = [&](int c) {         // c = 16-byte chunk index along MN (0..31)
-      return (uint32_t)((c >> 3) * 4096 + (krow >> 3) * 1024 + (krow & 7) * 128 + (((c & 7) ^ (krow & 7)) << 4));
+      const int c8 = c & 7;
+      const int csw = ((((c8 >> 1) ^ (krow & 3)) << 1) | (c8 & 1));  // Swizzle<2,5,2>
+      return (uint32_t)((c >> 3) * 4096 + krow * 128 + (csw << 4));
     };
     int stage = 0;
     uint32_t phase = 0;
