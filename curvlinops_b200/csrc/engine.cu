@@ -21,7 +21,8 @@ using namespace curv;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static long long g_launches = 0;
-static int g_tc_mode = 1;
+static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
+static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -93,8 +94,9 @@ extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
 extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
 extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
-  int old = g_tc_mode;
-  g_tc_mode = mode;
+  int old = g_tc_mode | (g_tc_disable << 4);
+  g_tc_mode = mode & 3;
+  g_tc_disable = (mode >> 4) & 3;
   return old;
 }
 
@@ -301,7 +303,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
 static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, double flops = 0) {
   const Geom& g = a.g;
   ProfScope prof(1, flops, st);
-  if (g_tc_mode && tc_wgrad_eligible(g, g_tc_mode)) {
+  if (g_tc_mode && !(g_tc_disable & 2) && tc_wgrad_eligible(g, g_tc_mode)) {
     int rc = tc_launch_wgrad(a, st);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 wgrad GEMM launch failed");
@@ -442,7 +444,7 @@ static int forward(const Ctx& c, const void* X, int K) {
         a.A = c.act(d.in0); a.A_slot = vi.slot_elems; a.a_has_slots = vi.tan ? 1 : 0;
         a.W = c.ws + n.wk_off;
         a.Wt = (d.p0 >= 0) ? c.ws + n.wkt_off : nullptr; a.Wt_slot = n.wsize;
-        if (g_tc_mode && n.wimg_off >= 0 && tc_gather_eligible(n.fwd, g_tc_mode)) {
+        if (g_tc_mode && !(g_tc_disable & 1) && n.wimg_off >= 0 && tc_gather_eligible(n.fwd, g_tc_mode)) {
           a.W_img = c.ws + n.wimg_off;
           a.Wt_img = (d.p0 >= 0 && K > 0) ? c.ws + n.wimgt_off : nullptr; a.Wt_img_slot = n.wimg_size;
         }
@@ -590,7 +592,7 @@ static int backward(const Ctx& c, int K) {
           a.A = c.grad(d.out); a.A_slot = vo.slot_elems; a.a_has_slots = 1;
           a.W = c.ws + n.wt_off;
           a.Wt = (rop && n.wtt_off >= 0) ? c.ws + n.wtt_off : nullptr; a.Wt_slot = n.wtsize;
-          if (g_tc_mode && n.wtimg_off >= 0 && tc_gather_eligible(n.dgr, g_tc_mode)) {
+          if (g_tc_mode && !(g_tc_disable & 1) && n.wtimg_off >= 0 && tc_gather_eligible(n.dgr, g_tc_mode)) {
             a.W_img = c.ws + n.wtimg_off;
             a.Wt_img = (rop && n.wtimgt_off >= 0) ? c.ws + n.wtimgt_off : nullptr; a.Wt_img_slot = n.wtimg_size;
           }

@@ -7,14 +7,21 @@
 //   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo            (dropped a_lo*b_lo ~ 2^-22 relative)
 // accumulated in fp32 in tensor memory.
 //
-// Persistent, warp-specialised CTA (416 threads, one CTA per SM):
-//   warps 0-3   epilogue : tcgen05.ld accumulator -> registers -> (+bias, +=) -> global
-//   warp  4     MMA      : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), 12 per stage
-//   warps 5-12  producers: implicit-im2col gather, global -> registers -> hi/lo split ->
-//                          st.shared into the 128B-swizzled K-major UMMA layout (software "TMA":
-//                          the gather is per 16-byte channel group, which TMA tiles cannot express
-//                          for padded / strided / transposed-stride convolutions)
+// Persistent, warp-specialised CTA (544 threads, one CTA per SM):
+//   warps 0-3, 13-16  epilogue: two groups of 4 warps, each owning half of the BN accumulator columns
+//   warp  4           MMA     : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), 12 per stage
+//   warps 5-12        producers: implicit-im2col gather, global -> registers -> hi/lo split ->
+//                          st.shared into the 128B-swizzled UMMA layout (software "TMA": the gather is per
+//                          16-byte channel group, which TMA tiles cannot express for padded / strided /
+//                          transposed-stride convolutions); weights arrive by cp.async.bulk
 // Pipelines: smem ring (full/empty mbarriers, STAGES deep), TMEM double buffer (tmem_full/empty).
+//
+// Accuracy: the tensor core adds into its fp32 accumulator with truncation, one truncation per MMA.
+// Left alone that is a bias of ~0.5 ulp(D) per instruction, ~1e-5 relative for a 3x3x64 reduction, and it
+// compounds over the ~60 layer applications of a GGN product (measured 4e-4 on ResNet-18).  Therefore a
+// TMEM accumulator only ever holds TC_FLUSH stages (64 reduction elements): the epilogue warps drain each
+// chunk with tcgen05.ld and sum the chunks in registers with round-to-nearest fp32 adds, overlapped with
+// the MMAs of the next chunk through the TMEM double buffer.
 // Every mbarrier wait is bounded and traps instead of hanging the GPU.
 #pragma once
 #include "common.cuh"
@@ -25,7 +32,8 @@ namespace curv {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
-constexpr int TC_THREADS = 416;
+constexpr int TC_THREADS = 544;   // 17 warps, see the role table below
+constexpr int TC_FLUSH = 2;       // smem stages per TMEM accumulation chunk (see tc epilogue)
 constexpr int TC_PRODUCERS = 256;
 
 template <int BN>
@@ -103,6 +111,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -169,7 +190,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* ra
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(S.full(s), full_count); mbar_init(S.empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
     return slot == 0 ? 1 : (p.a_has_slots ? 1 : 0) + (p.Wt_img != nullptr ? 1 : 0);
   };
 
-  if (warp >= 5) {
+  if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;             // 0..255
     const int a_row = pt >> 1, a_c0 = (pt & 1) * 4;  // 4 of the 8 16-byte chunks of an A row
@@ -388,55 +409,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         int slot, m0, tn;
         decode_tile(tile, slot, m0, tn);
         const int T = num_segments(slot) * nchunks;
-        mbar_wait(S.tempty(acc), acc_phase ^ 1);
-        tc_fence_after();
-        tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), T, stage, phase);
-        tc_commit(S.tfull(acc));  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
+          mbar_wait(S.tempty(acc), acc_phase ^ 1);
+          tc_fence_after();
+          tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
+          tc_commit(S.tfull(acc));  // chunk complete -> epilogue
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    // ------------------------------------------------------------------ epilogue (warps 0-3, 13-16)
+    constexpr int HALF = BN / 2;
+    const int egrp = warp >= 13 ? 1 : 0;     // which half of the accumulator columns
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int slot, m0, tn;
       decode_tile(tile, slot, m0, tn);
-      const int n0 = tn * BN;
+      const int n0 = tn * BN + egrp * HALF;
+      const int T = num_segments(slot) * nchunks;
+      float accv[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
+      for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {
+        mbar_wait(S.tfull(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + egrp * HALF + c0), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) accv[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(S.tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
       const float* bias = (slot == 0) ? p.bias
                                       : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
       float* outp = p.out + (long long)slot * p.out_slot;
-      const int m = m0 + warp * 32 + lane;
-      mbar_wait(S.tfull(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        if (m < g.M) {
+      const int m = m0 + quad * 32 + lane;
+      if (m < g.M) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = n0 + c0 + j * 4;
-            if (n >= g.Nd) continue;
-            float4 v = make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]),
-                                   __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
-            if (bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            }
-            float4* dst = reinterpret_cast<float4*>(outp + (long long)m * g.Nd + n);
-            if (p.accumulate) {
-              const float4 o = *dst;
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *dst = v;
+        for (int j = 0; j < HALF / 4; ++j) {
+          const int n = n0 + j * 4;
+          if (n >= g.Nd) continue;
+          float4 v = make_float4(accv[j * 4 + 0], accv[j * 4 + 1], accv[j * 4 + 2], accv[j * 4 + 3]);
+          if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           }
+          float4* dst = reinterpret_cast<float4*>(outp + (long long)m * g.Nd + n);
+          if (p.accumulate) {
+            const float4 o = *dst;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *dst = v;
         }
       }
-      tc_fence_before();
-      mbar_arrive(S.tempty(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_teardown<BN>(tmem_base);
@@ -507,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
     return ceil_div(max(0, me - mb), TC_BK);
   };
 
-  if (warp >= 5) {
+  if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;
     const int krow = pt >> 3;            // pixel row of the 32-pixel stage
@@ -614,57 +647,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
         int slot_idx, split, i0, j0;
         decode_tile(tile, slot_idx, split, i0, j0);
         const int T = num_segments(p.slot0 + slot_idx) * stages_of(split);
-        mbar_wait(S.tempty(acc), acc_phase ^ 1);
-        tc_fence_after();
-        tc_issue_tile<BN, true>(S, tmem_base + (uint32_t)(acc * BN), T, stage, phase);
-        tc_commit(S.tfull(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {
+          mbar_wait(S.tempty(acc), acc_phase ^ 1);
+          tc_fence_after();
+          tc_issue_tile<BN, true>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
+          tc_commit(S.tfull(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
       }
     }
     __syncwarp();
   } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3, 13-16)
+    constexpr int HALF = BN / 2;
+    const int egrp = warp >= 13 ? 1 : 0;
+    const int quad = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int slot_idx, split, i0, j0;
       decode_tile(tile, slot_idx, split, i0, j0);
-      const bool empty_tile = stages_of(split) == 0;
-      float* outp = p.partial + ((long long)split * p.nslots + slot_idx) * (long long)g.N * g.Kd;
-      const int i = i0 + warp * 32 + lane;
-      mbar_wait(S.tfull(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        if (empty_tile) {
+      const int T = num_segments(p.slot0 + slot_idx) * stages_of(split);
+      float accv[HALF];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;  // no MMA was issued: accumulator content is stale
+      for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
+      for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {
+        mbar_wait(S.tfull(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + egrp * HALF + c0), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) accv[c0 + j] += __uint_as_float(r[j]);
         }
-        if (!swap) {
-          if (i < g.N) {
+        tc_fence_before();
+        mbar_arrive(S.tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      float* outp = p.partial + ((long long)split * p.nslots + slot_idx) * (long long)g.N * g.Kd;
+      const int i = i0 + quad * 32 + lane;
+      const int jbase = j0 + egrp * HALF;
+      if (!swap) {
+        if (i < g.N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = j0 + c0 + j * 4;
-              if (col >= g.Kd) continue;
-              *reinterpret_cast<float4*>(outp + (long long)i * g.Kd + col) =
-                  make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]),
-                              __uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3]));
-            }
+          for (int j = 0; j < HALF / 4; ++j) {
+            const int col = jbase + j * 4;
+            if (col >= g.Kd) continue;
+            *reinterpret_cast<float4*>(outp + (long long)i * g.Kd + col) =
+                make_float4(accv[j * 4 + 0], accv[j * 4 + 1], accv[j * 4 + 2], accv[j * 4 + 3]);
           }
-        } else {
-          if (i < g.Kd) {
+        }
+      } else {
+        if (i < g.Kd) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = j0 + c0 + j;
-              if (n < g.N) outp[(long long)n * g.Kd + i] = __uint_as_float(r[j]);
-            }
+          for (int j = 0; j < HALF; ++j) {
+            const int n = jbase + j;
+            if (n < g.N) outp[(long long)n * g.Kd + i] = accv[j];
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(S.tempty(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_teardown<BN>(tmem_base);
