@@ -7,11 +7,24 @@ behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
 """
 
 from .curvature import CurvatureLinearOperator, GGNLinearOperator, HessianLinearOperator
+from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
 from .linop import PyTorchLinearOperator
+from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
+                         FromCanonicalLinearOperator, KroneckerProductLinearOperator,
+                         ToCanonicalLinearOperator)
 
 __all__ = [
     "PyTorchLinearOperator",
     "CurvatureLinearOperator",
     "GGNLinearOperator",
     "HessianLinearOperator",
+    "KFACLinearOperator",
+    "EKFACLinearOperator",
+    "FisherType",
+    "KFACType",
+    "KroneckerProductLinearOperator",
+    "EighDecomposedLinearOperator",
+    "BlockDiagonalLinearOperator",
+    "ToCanonicalLinearOperator",
+    "FromCanonicalLinearOperator",
 ]

@@ -34,7 +34,9 @@ class LayerProgram:
     nodes: list = field(default_factory=list)   # dicts with NodeDesc fields
     consts: list = field(default_factory=list)  # constant tensors referenced by c0..c3
     conv_nodes: dict = field(default_factory=dict)  # weight param name -> node index
+    bias_nodes: dict = field(default_factory=dict)  # bias param name -> node index
     out_features: int = 0
+    tied: set = field(default_factory=set)  # parameters used by more than one layer
 
     def add_value(self, C, H, W, tan):
         self.values.append([int(C), int(H), int(W), bool(tan)])
@@ -140,7 +142,11 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
         ni = prog.add_node(capi.OP_CONV, in0=xr.value, out=ov, p0=p0, p1=p1, c0=c0, c1=c1, kh=kh, kw=kw,
                            sh=sh, sw=sw, ph=ph, pw=pw)
         if p0 >= 0:
+            if names[p0] in prog.conv_nodes:
+                prog.tied.add(names[p0])
             prog.conv_nodes[names[p0]] = ni
+        if p1 >= 0:
+            prog.bias_nodes[names[p1]] = ni
         return _Ref("act", value=ov, flat=False)
 
     def emit_linear(node, xr, wref, bref):

@@ -90,6 +90,19 @@ struct curv_program {
 
 static long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 
+// split count / scratch need of a Gram matrix X^T X (X: rows x widthp, `width` real columns); kfac.cuh
+static int gram_nsplit(long long rows, int width, int widthp) {
+  const int bm = width > 64 ? 128 : 64, bn = widthp > 64 ? 128 : 64;
+  long long tiles = (long long)ceil_div(width, bm) * ceil_div(widthp, bn);
+  long long want = (2 * 148 + tiles - 1) / tiles;
+  long long maxsplit = (rows + 511) / 512;
+  long long ns = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+  return (int)(ns > 32 ? 32 : (ns < 1 ? 1 : ns));
+}
+static long long gram_partial_elems(long long rows, int width, int widthp) {
+  return (long long)gram_nsplit(rows, width, widthp) * width * widthp + 64;
+}
+
 extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
 extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
 extern "C" long long curv_launch_count(void) { return g_launches; }
@@ -119,7 +132,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
     v.slot_elems = (long long)batch * v.H * v.W * v.Cp;
     v.nslots = v.tan ? 1 + kmax : 1;
     v.act_off = alloc(v.slot_elems * v.nslots);
-    v.grad_off = (hessian && v.tan) ? alloc(v.slot_elems * v.nslots) : v.act_off;
+    v.grad_off = ((hessian & 1) && v.tan) ? alloc(v.slot_elems * v.nslots) : v.act_off;
     P->values.push_back(v);
   }
   long long scratch = 64;
@@ -152,7 +165,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       if (vi.tan) n.wt_off = alloc(n.wtsize);
       if (d.p0 >= 0) {
         n.wkt_off = alloc(n.wsize * kmax);
-        if (hessian && vi.tan) n.wtt_off = alloc(n.wtsize * kmax);
+        if ((hessian & 1) && vi.tan) n.wtt_off = alloc(n.wtsize * kmax);
       }
       n.wimg_size = tc_image_elems(g.N, g.Nd, g.Kd);
       n.wtimg_size = tc_image_elems(q.N, q.Nd, q.Kd);
@@ -161,7 +174,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         if (vi.tan) n.wtimg_off = alloc(n.wtimg_size);
         if (d.p0 >= 0) {
           n.wimgt_off = alloc(n.wimg_size * kmax);
-          if (hessian && vi.tan) n.wtimgt_off = alloc(n.wtimg_size * kmax);
+          if ((hessian & 1) && vi.tan) n.wtimgt_off = alloc(n.wtimg_size * kmax);
         }
       }
       if (d.p1 >= 0 || d.c1 >= 0) n.bias_off = alloc(vo.Cp);
@@ -170,7 +183,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       if (d.p0 >= 0) {
         n.wbm = g.N > 64 ? 128 : 64;
         n.wbn = g.Kd > 64 ? 128 : 64;
-        int nsl = kmax + (hessian ? 1 : 0);
+        int nsl = kmax + ((hessian & 1) ? 1 : 0);
         long long tiles = (long long)ceil_div(g.N, n.wbm) * ceil_div(g.Kd, n.wbn) * nsl;
         int want = (int)((2 * 148 + tiles - 1) / tiles);
         int maxsplit = ceil_div(g.M, 256);
@@ -180,6 +193,13 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         n.nsplit = ceil_div(g.M, n.m_per_split);
         long long need = (long long)n.nsplit * nsl * n.wsize;
         if (need > scratch) scratch = need;
+      }
+      if (hessian & 2) {  // KFAC: patch matrix + Gram partials (A factor), Gram partials of the cotangents (G)
+        const int width = vi.C * d.kh * d.kw + 1, widthp = pad4(width);
+        long long needA = align_up((long long)g.M * widthp, 64) + gram_partial_elems(g.M, width, widthp);
+        long long needG = gram_partial_elems((long long)g.M * kmax, vo.C, vo.Cp);
+        if (needA > scratch) scratch = needA;
+        if (needG > scratch) scratch = needG;
       }
       if (d.p1 >= 0) {  // bias grad = column sum of the output cotangent
         long long rows = g.M;
@@ -329,6 +349,8 @@ struct Ctx {
   cudaStream_t st;
   int kind;
   bool rop;  // Hessian R-op: slot 0 of the cotangent storage holds the plain backward
+  float** kfac_G = nullptr;  // KFAC mode: per node, the G factor to accumulate into (or null); no param grads
+  float kfac_wG = 0.f;
   float* act(int v, int slot = 0) const {
     const Value& x = P->values[v];
     return ws + x.act_off + (long long)slot * x.slot_elems;
@@ -534,6 +556,9 @@ static int forward(const Ctx& c, const void* X, int K) {
   return CURV_OK;
 }
 
+static int gram_accumulate(const float* X, long long rows, int width, int widthp, float* F, float w,
+                           float* partial, long long partial_elems, cudaStream_t st);
+
 // backward sweep over cotangent slots [s0, s0+ns) of the grad storage.
 //   GGN / VJP: s0 = 1, ns = K.      Hessian R-op: s0 = 0, ns = K+1 (slot 0 = plain backward).
 //   param_out: accumulate parameter-space results into c.out (columns k0..k0+K-1)
@@ -558,7 +583,13 @@ static int backward(const Ctx& c, int K) {
     switch (d.op) {
       case CURV_OP_CONV: {
         const Geom& g = n.fwd;
-        if (d.p0 >= 0) {  // weight gradient
+        if (c.kfac_G != nullptr) {  // KFAC: Gram matrix of the K stacked cotangent slots, no parameter grads
+          if (c.kfac_G[ni] != nullptr) {
+            int rc = gram_accumulate(c.grad(d.out, 1), (long long)K * g.M, vo.C, vo.Cp, c.kfac_G[ni],
+                                     c.kfac_wG, scratch, P->scratch_elems, st);
+            if (rc) return rc;
+          }
+        } else if (d.p0 >= 0) {  // weight gradient
           WgradArgs a;
           memset(&a, 0, sizeof(a));
           a.g = g;
@@ -574,7 +605,7 @@ static int backward(const Ctx& c, int K) {
                                                               P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
           LAUNCH_CHECK();
         }
-        if (d.p1 >= 0) {  // bias gradient: column sums of the cotangent
+        if (c.kfac_G == nullptr && d.p1 >= 0) {  // bias gradient: column sums of the cotangent
           long long rows = g.M;
           affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
               c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
@@ -694,7 +725,7 @@ extern "C" int curv_matmat_batch(curv_program* P, int kind, int loss, const void
   if (kind != CURV_KIND_FORWARD && (K < 1 || K > P->kmax))
     return fail(CURV_ERR_INVALID, "K must be in [1, kmax]");
   if (workspace_bytes < P->ws_bytes || !workspace) return fail(CURV_ERR_WORKSPACE, "workspace too small");
-  if (kind == CURV_KIND_HESSIAN && !P->hessian)
+  if (kind == CURV_KIND_HESSIAN && !(P->hessian & 1))
     return fail(CURV_ERR_INVALID, "program was not created with hessian=1");
   if (kind == CURV_KIND_GGN_MC && (mc_samples < 1 || mc_samples > 32 || !mc_grad))
     return fail(CURV_ERR_INVALID, "MC mode needs 1 <= mc_samples <= 32 and mc_grad");

@@ -1,0 +1,457 @@
+"""KFAC / EKFAC linear operators with engine-computed Kronecker factors.
+
+``KFACLinearOperator = P @ blockdiag(G_l (x) A_l) @ P^T`` with the constructor arguments, iteration
+protocol (``P, K, PT = op``), properties and ``inverse`` of the reference
+(``curvlinops/kfac.py:43-350``, ``curvlinops/ekfac.py:13-86``).  The factors are accumulated by
+``curv_kfac_accumulate_batch`` (``include/curvb200.h``) instead of forward/backward hooks
+(``curvlinops/computers/kfac_hooks.py:176-393``); conventions (checked against reference-generated
+fixtures, ``tests/golden/kfac_*.npz``):
+
+* ``A = sum a~ a~^T / (N S)``: im2col patches in ``F.unfold`` order, a ones column for joint weight+bias,
+* ``G = corr * sum g g^T`` with seeds scaled by ``1/(B T)`` and ``corr = (B T)^2 / (T N)`` for mean
+  reduction (``kfac_math.py:172-203``), seeds = columns of the loss-Hessian square root (TYPE2), sampled
+  would-be gradients (MC), or the loss gradient (EMPIRICAL); ``G = I`` for FORWARD_ONLY,
+* factors are accumulated in fp32.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections.abc import Callable, Iterable, MutableMapping
+from enum import Enum, EnumMeta
+
+import torch
+from torch import Tensor
+from torch.nn import BCEWithLogitsLoss, Conv2d, CrossEntropyLoss, Linear, Module, MSELoss
+
+from . import _capi as capi
+from . import dist as cdist
+from .curvature import CurvatureLinearOperator
+from .engine import CompiledProgram
+from .linop import _ChainPyTorchLinearOperator
+from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
+                         KroneckerProductLinearOperator, ToCanonicalLinearOperator, dense_matmul)
+
+
+class _MetaEnum(EnumMeta):
+    def __contains__(cls, item):
+        try:
+            cls(item)
+        except ValueError:
+            return False
+        return True
+
+
+class FisherType(str, Enum, metaclass=_MetaEnum):
+    """Which Fisher/GGN flavour the gradient covariance uses (reference ``kfac_utils.py:39-60``)."""
+
+    TYPE2 = "type-2"
+    MC = "mc"
+    EMPIRICAL = "empirical"
+    FORWARD_ONLY = "forward-only"
+
+
+class KFACType(str, Enum, metaclass=_MetaEnum):
+    EXPAND = "expand"
+    REDUCE = "reduce"
+
+
+class KFACComputer(CurvatureLinearOperator):
+    """Accumulates the Kronecker factors of all supported layers with the CUDA engine.
+
+    Reuses the data loop / normalisation / determinism probes of :class:`CurvatureLinearOperator`
+    (the reference's computers inherit the same mixin, ``computers/_base.py:33-179``).
+    """
+
+    _SUPPORTED_LOSSES = (MSELoss, CrossEntropyLoss, BCEWithLogitsLoss)
+    _SUPPORTED_MODULES = (Linear, Conv2d)
+    _SUPPORTED_FISHER_TYPE = tuple(FisherType)
+    NEEDS_NUM_PER_EXAMPLE_LOSS_TERMS = True
+    _TEST_GRAD_OUTPUTS = None
+
+    def __init__(self, model_func, loss_func, params, data, progressbar=False, check_deterministic=True,
+                 seed: int = 2_147_483_647, fisher_type: str = FisherType.MC, mc_samples: int = 1,
+                 kfac_approx: str = KFACType.EXPAND, num_per_example_loss_terms: int | None = None,
+                 separate_weight_and_bias: bool = True, num_data: int | None = None, batch_size_fn=None):
+        if not isinstance(loss_func, self._SUPPORTED_LOSSES):
+            raise ValueError(f"Invalid loss: {loss_func}. Supported: {self._SUPPORTED_LOSSES}.")
+        if fisher_type not in self._SUPPORTED_FISHER_TYPE:
+            raise ValueError(
+                f"Invalid fisher_type: {fisher_type}. Supported: {self._SUPPORTED_FISHER_TYPE}."
+            )
+        if fisher_type != FisherType.MC and mc_samples != 1:
+            raise ValueError(
+                f"Invalid mc_samples: {mc_samples}. "
+                "Only mc_samples=1 is supported for `fisher_type != FisherType.MC`."
+            )
+        if kfac_approx not in KFACType:
+            raise ValueError(f"Invalid kfac_approx: {kfac_approx}. Supported: {tuple(KFACType)}.")
+        if KFACType(kfac_approx) != KFACType.EXPAND:
+            raise NotImplementedError("The B200 engine implements KFAC-expand only.")
+        if not isinstance(model_func, Module):
+            raise ValueError("The KFAC computer requires an nn.Module (as the reference's hooks backend).")
+        self._model_module = model_func
+        self._seed = seed
+        self._fisher_type = FisherType(fisher_type)
+        self._mc_samples = mc_samples
+        self._separate_weight_and_bias = separate_weight_and_bias
+        # tests: list of [V, B, C] tensors, one per mini-batch (class attribute so that it can be injected
+        # before KFACLinearOperator builds its computer)
+        self._grad_outputs_override = type(self)._TEST_GRAD_OUTPUTS
+        self._mapping = self.compute_parameter_groups(params, model_func, separate_weight_and_bias)
+        super().__init__(model_func, loss_func, params, data, progressbar=progressbar,
+                         check_deterministic=check_deterministic, num_data=num_data,
+                         num_per_example_loss_terms=num_per_example_loss_terms, batch_size_fn=batch_size_fn)
+
+    def _check_deterministic_matvec(self, *a, **k):  # the computer is not itself an operator
+        return None
+
+    @classmethod
+    def compute_parameter_groups(cls, params: dict[str, Tensor], model: Module,
+                                 separate_weight_and_bias: bool = True) -> list[dict[str, str]]:
+        """Group parameters by layer (reference ``kfac_hooks.py:395-451``)."""
+        role = {"weight": "W", "bias": "b"}
+        names, seen, groups = set(params), set(), []
+        for mod_name, mod in model.named_modules():
+            if not isinstance(mod, cls._SUPPORTED_MODULES):
+                continue
+            roles = {}
+            for p_name, _ in mod.named_parameters(recurse=False):
+                full = f"{mod_name}.{p_name}" if mod_name else p_name
+                if full in names:
+                    roles[role[p_name]] = full
+                    seen.add(full)
+            if roles:
+                groups.extend([{r: n} for r, n in roles.items()] if separate_weight_and_bias else [roles])
+        if unsupported := names - seen:
+            raise NotImplementedError(
+                f"Parameters {unsupported} are not in supported layers ({cls._SUPPORTED_MODULES})."
+            )
+        return groups
+
+    # ---- seeds for the backward passes (reference ggn_utils.py:274-376) -----------------------------
+    def _grad_outputs(self, f: Tensor, y: Tensor, gen: torch.Generator | None) -> Tensor:
+        """Per-datum vectors ``[V, B, C]`` whose outer products sum to the loss Hessian (unscaled)."""
+        B, Cc = f.shape
+        lf, ft = self._loss_func, self._fisher_type
+        c = 1.0 / Cc if (lf.reduction == "mean" and not isinstance(lf, CrossEntropyLoss)) else 1.0
+        if ft == FisherType.FORWARD_ONLY:
+            return f.new_empty(0, B, Cc)
+        if ft == FisherType.TYPE2:
+            if isinstance(lf, CrossEntropyLoss):
+                p = torch.softmax(f, 1)
+                S = torch.diag_embed(p.sqrt()) - p.unsqueeze(2) * p.sqrt().unsqueeze(1)  # [B, C, C']
+                return S.permute(2, 0, 1).contiguous()
+            if isinstance(lf, MSELoss):
+                return (math.sqrt(2 * c) * torch.eye(Cc, dtype=f.dtype, device=f.device)
+                        ).unsqueeze(1).expand(Cc, B, Cc).contiguous()
+            s = torch.sigmoid(f)
+            return (math.sqrt(c) * torch.diag_embed((s * (1 - s)).sqrt())).permute(2, 0, 1).contiguous()
+        if ft == FisherType.MC:
+            M = self._mc_samples
+            if isinstance(lf, CrossEntropyLoss):
+                p = torch.softmax(f, 1)
+                yhat = p.multinomial(M, replacement=True, generator=gen)
+                g = p.unsqueeze(1) - torch.nn.functional.one_hot(yhat, Cc).to(f.dtype)
+            elif isinstance(lf, MSELoss):
+                g = torch.normal(torch.zeros(B, M, Cc, dtype=f.dtype, device=f.device), math.sqrt(2 * c),
+                                 generator=gen)
+            else:
+                s = torch.sigmoid(f).unsqueeze(1).expand(B, M, Cc)
+                g = math.sqrt(c) * (s - s.bernoulli(generator=gen))
+            return (g / math.sqrt(M)).permute(1, 0, 2).contiguous()
+        # EMPIRICAL: gradient of the per-datum loss, with the sqrt(C) fix-up of ggn_utils.py:319-345
+        with torch.enable_grad():
+            ff = f.detach().requires_grad_(True)
+            scale = math.sqrt(Cc) if (lf.reduction == "mean" and not isinstance(lf, CrossEntropyLoss)) else 1.0
+            per_datum = type(lf)(reduction="sum")(ff, y)
+            (g,) = torch.autograd.grad(per_datum, ff)
+        return (g * (scale / Cc if (lf.reduction == "mean" and not isinstance(lf, CrossEntropyLoss)) else 1.0)
+                ).unsqueeze(0).contiguous()
+
+    # ---- factor accumulation -----------------------------------------------------------------------
+    def compute(self):
+        """-> ``(input_covariances, gradient_covariances, mapping)`` keyed by ``tuple(group.values())``."""
+        dev = self.device
+        eng = self._engine
+        eng._check_supported()
+        rank, world = cdist.rank_world()
+        A: dict = {}
+        G: dict = {}
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(self._seed)
+        N, T = self._N_data, (self._num_per_example_loss_terms or 1)
+        if T != 1:
+            raise NotImplementedError("The B200 engine supports one loss term per example (2-d outputs).")
+        for bi, (X, y) in enumerate(self._loop_over_data(desc="KFAC matrices")):
+            if not isinstance(X, Tensor):
+                raise NotImplementedError("The B200 engine needs tensor inputs X.")
+            B_glob = X.shape[0]
+            if world > 1:
+                lo, hi = cdist.shard_bounds(B_glob, rank, world)
+                if hi == lo:
+                    continue
+                X, y = X[lo:hi], y[lo:hi]
+            X = X.to(torch.float32).contiguous()
+            prog = self._kfac_program(X)
+            ws = eng.workspace(prog.ws_bytes, dev)
+            f = eng.predict(X) if self._fisher_type != FisherType.FORWARD_ONLY else None
+            if f is not None and f.ndim != 2:
+                raise ValueError(f"Only 2d output and 1d/2d target are supported. Got {f.ndim=} and {y.ndim=}.")
+            if self._grad_outputs_override is not None:
+                gos = self._grad_outputs_override[bi].to(dev).float()
+                if world > 1:
+                    gos = gos[:, lo:hi]
+            elif f is not None:
+                gos = self._grad_outputs(f, y, gen)
+            else:
+                gos = None
+            red = self._loss_func.reduction
+            scale = 1.0 / (B_glob * T) if red == "mean" else 1.0
+            corr = (B_glob * T) ** 2 / (T * N) if red == "mean" else 1.0
+            self._accumulate(prog, ws, X, gos, scale, corr, A, G)
+        if world > 1:  # one all-reduce over the concatenated factors
+            flat = torch.cat([t.reshape(-1) for t in list(A.values()) + list(G.values())])
+            cdist.all_reduce_sum(flat)
+            o = 0
+            for t in list(A.values()) + list(G.values()):
+                t.copy_(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+        if self._fisher_type == FisherType.FORWARD_ONLY:
+            for group in self._mapping:
+                p = self._params[next(iter(group.values()))]
+                G[tuple(group.values())] = torch.eye(p.shape[0], dtype=p.dtype, device=dev)
+        dt = self.dtype
+        return ({k: v.to(dt) for k, v in A.items()}, {k: v.to(dt) for k, v in G.items()}, self._mapping)
+
+    def _kfac_program(self, X: Tensor) -> CompiledProgram:
+        eng = self._engine
+        key = (tuple(X.shape), "kfac")
+        prog = eng._programs.get(key)
+        if prog is None:
+            prog = CompiledProgram(eng.model_func, eng.params, X, 8, 2)
+            eng._programs[key] = prog
+            if prog.lp.tied:
+                raise NotImplementedError(
+                    f"Weight tying ({sorted(prog.lp.tied)}) is not supported by the KFAC factor kernels."
+                )
+        return prog
+
+    def _group_node(self, prog: CompiledProgram, group: dict[str, str]) -> int:
+        lp = prog.lp
+        if "W" in group:
+            return lp.conv_nodes[group["W"]]
+        return lp.bias_nodes[group["b"]]
+
+    def _accumulate(self, prog, ws, X, gos, scale, corr, A, G):
+        dev = X.device
+        L = capi.lib()
+        nodes, a_ptrs, g_ptrs, joint = [], [], [], []
+        per_node_G: dict = {}
+        for group in self._mapping:
+            key = tuple(group.values())
+            ni = self._group_node(prog, group)
+            node = prog.lp.nodes[ni]
+            cin, _, _, _ = prog.lp.values[node["in0"]]
+            cout = prog.lp.values[node["out"]][0]
+            has_joint = "W" in group and "b" in group
+            if "W" in group:
+                width = cin * node["kh"] * node["kw"] + (1 if has_joint else 0)
+                if key not in A:
+                    A[key] = torch.zeros(width, width, device=dev, dtype=torch.float32)
+                a_ptr = A[key].data_ptr()
+            else:
+                a_ptr = 0
+            if key not in G:
+                G[key] = torch.zeros(cout, cout, device=dev, dtype=torch.float32)
+            # the weight and the bias group of a layer share one G: accumulate once, copy afterwards
+            if ni in per_node_G:
+                g_ptr = 0
+            else:
+                per_node_G[ni] = key
+                g_ptr = G[key].data_ptr()
+            nodes.append(ni); a_ptrs.append(a_ptr); g_ptrs.append(g_ptr); joint.append(int(has_joint))
+        before = {ni: G[key].clone() for ni, key in per_node_G.items()}
+        V = 0 if gos is None else gos.shape[0]
+        if V > 0:
+            seeds = (gos * scale).permute(1, 2, 0).contiguous()  # [B, C, V]
+        n = len(nodes)
+        keep, pptrs = self._engine._param_ptrs()
+        rc = L.curv_kfac_accumulate_batch(
+            prog.handle, pptrs, prog.const_ptrs, X.data_ptr(), (C.c_int * n)(*nodes), n,
+            capi.ptr_array(a_ptrs), capi.ptr_array(g_ptrs), (C.c_int * n)(*joint),
+            seeds.data_ptr() if V > 0 else 0, V, 1.0 / self._N_data, float(corr), ws.data_ptr(),
+            ws.numel() * 4, torch.cuda.current_stream(dev).cuda_stream)
+        capi.check(rc)
+        del keep
+        for group in self._mapping:  # second group of a layer: add the same increment
+            key = tuple(group.values())
+            ni = self._group_node(prog, group)
+            if per_node_G[ni] != key:
+                G[key] += G[per_node_G[ni]] - before[ni]
+
+
+class KFACLinearOperator(_ChainPyTorchLinearOperator):
+    r"""Kronecker-factored approximate curvature ``P (blockdiag_l G_l \otimes A_l) P^T``."""
+
+    SELF_ADJOINT: bool = True
+    _COMPUTER = KFACComputer
+    _BACKENDS = ("hooks", "make_fx")  # accepted for API compatibility; both map onto the CUDA engine
+
+    def __init__(self, model_func, loss_func, params, data, progressbar: bool = False,
+                 check_deterministic: bool = True, seed: int = 2_147_483_647,
+                 fisher_type: str = FisherType.MC, mc_samples: int = 1, kfac_approx: str = KFACType.EXPAND,
+                 num_per_example_loss_terms: int | None = None, separate_weight_and_bias: bool = True,
+                 num_data: int | None = None, batch_size_fn: Callable | None = None, backend: str = "hooks"):
+        if backend not in self._BACKENDS:
+            raise ValueError(f"Invalid backend: {backend!r}. Supported: {tuple(self._BACKENDS)}.")
+        computer = self._COMPUTER(
+            model_func, loss_func, params, data, progressbar=progressbar,
+            check_deterministic=check_deterministic, seed=seed, fisher_type=fisher_type,
+            mc_samples=mc_samples, kfac_approx=kfac_approx,
+            num_per_example_loss_terms=num_per_example_loss_terms,
+            separate_weight_and_bias=separate_weight_and_bias, num_data=num_data, batch_size_fn=batch_size_fn)
+        K, mapping = self._compute_canonical_op(computer)
+        PT = ToCanonicalLinearOperator({n: p.shape for n, p in params.items()}, mapping, computer.device,
+                                       computer.dtype)
+        super().__init__(PT.adjoint(), K, PT)
+
+    @staticmethod
+    def _compute_canonical_op(computer):
+        A, G, mapping = computer.compute()
+        blocks = []
+        for group in mapping:
+            key = tuple(group.values())
+            aaT, ggT = A.get(key), G[key]
+            blocks.append(KroneckerProductLinearOperator(*([ggT, aaT] if aaT is not None else [ggT])))
+        return BlockDiagonalLinearOperator(blocks), mapping
+
+    def trace(self) -> Tensor:
+        return self[1].trace()
+
+    def det(self) -> Tensor:
+        return self[1].det()
+
+    def logdet(self) -> Tensor:
+        return self[1].logdet()
+
+    def frobenius_norm(self) -> Tensor:
+        return self[1].frobenius_norm()
+
+    def inverse(self, damping: float = 0.0, use_heuristic_damping: bool = False, min_damping: float = 1e-8,
+                use_exact_damping: bool = False, retry_double_precision: bool = True):
+        """``P K^-1 P^T`` with each Kronecker block inverted factor-wise (reference ``kfac.py:311-350``)."""
+        P, K, PT = self
+        K_inv = BlockDiagonalLinearOperator([
+            block.inverse(damping=damping, use_heuristic_damping=use_heuristic_damping,
+                          min_damping=min_damping, use_exact_damping=use_exact_damping,
+                          retry_double_precision=retry_double_precision)
+            for block in K
+        ])
+        return _ChainPyTorchLinearOperator(P, K_inv, PT)
+
+
+class EKFACComputer(KFACComputer):
+    """KFAC factors -> eigenvectors, then a second data pass for the eigenvalue correction
+    ``lambda[i, j] = corr * sum_{v,n} (Q_g^T (sum_s g a~^T) Q_a)[i, j]^2``
+    (reference ``computers/ekfac_hooks.py:25-238, 241-458``)."""
+
+    _SUPPORTED_FISHER_TYPE = (FisherType.TYPE2, FisherType.MC, FisherType.EMPIRICAL)
+
+    def compute(self):
+        A, G, mapping = super().compute()
+        QA = {k: torch.linalg.eigh(v.float()).eigenvectors for k, v in A.items()}
+        QG = {k: torch.linalg.eigh(v.float()).eigenvectors for k, v in G.items()}
+        lam = self._eigenvalue_correction(QA, QG, mapping)
+        dt = self.dtype
+        return ({k: v.to(dt) for k, v in QA.items()}, {k: v.to(dt) for k, v in QG.items()},
+                {k: v.to(dt) for k, v in lam.items()}, mapping)
+
+    def _eigenvalue_correction(self, QA, QG, mapping):
+        """Second pass: per-example gradients in the Kronecker eigenbasis, squared and summed.
+
+        The rotations ``g Q_g`` and ``a~ Q_a`` and the per-example contraction over the shared positions run
+        through ``curv_gemm``; layer inputs / output cotangents are read from the engine's workspace after a
+        VJP sweep (the engine keeps the cotangent of every layer output in its slot storage)."""
+        dev = self.device
+        eng = self._engine
+        lam = {}
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(self._seed)
+        N = self._N_data
+        for bi, (X, y) in enumerate(self._loop_over_data(desc="EKFAC eigenvalue correction")):
+            X = X.to(torch.float32).contiguous()
+            B = X.shape[0]
+            f = eng.predict(X)
+            gos = (self._grad_outputs_override[bi].to(dev).float() if self._grad_outputs_override is not None
+                   else self._grad_outputs(f, y, gen))
+            red = self._loss_func.reduction
+            scale = 1.0 / B if red == "mean" else 1.0
+            corr = B * B / N if red == "mean" else 1.0
+            for v in range(gos.shape[0]):
+                acts, grads, prog = self._layer_io(X, gos[v] * scale)
+                for group in mapping:
+                    key = tuple(group.values())
+                    ni = self._group_node(prog, group)
+                    g = grads[ni]                                   # [B, S, d_out]
+                    gt = dense_matmul(g.reshape(-1, g.shape[-1]), QG[key]).reshape(g.shape)
+                    if "W" in group:
+                        a = acts[ni]                                # [B, S, d_in]
+                        if "b" in group:
+                            a = torch.cat([a, a.new_ones(*a.shape[:-1], 1)], dim=-1)
+                        at = dense_matmul(a.reshape(-1, a.shape[-1]), QA[key]).reshape(a.shape)
+                        # per-example gradient in the eigenbasis: E_n = gt_n^T at_n  (sum over S)
+                        E = torch.stack([dense_matmul(gt[n].t().contiguous(), at[n]) for n in range(B)]) \
+                            if gt.shape[1] > 1 else gt[:, 0, :, None] * at[:, 0, None, :]
+                    else:
+                        E = gt.sum(1)
+                    cur = (E ** 2).sum(0) * corr
+                    lam[key] = cur if key not in lam else lam[key] + cur
+        return lam
+
+    def _layer_io(self, X: Tensor, seed: Tensor):
+        """Layer inputs as patch matrices ``[B, S, d_in]`` and output cotangents ``[B, S, d_out]`` of every
+        grouped layer for one backpropagated vector, read back from the engine workspace."""
+        eng = self._engine
+        prog = eng.program(X, 1, False)
+        ws = eng.workspace(prog.ws_bytes, X.device)
+        P = sum(p.numel() for p in self._params.values())
+        out = torch.zeros(P, 1, device=X.device)
+        eng.matmat_batch(capi.KIND_VJP, X, None, seed.reshape(*seed.shape, 1).contiguous(), out, 1.0)
+        acts, grads = {}, {}
+        for group in self._mapping:
+            ni = self._group_node(prog, group)
+            if ni in grads:
+                continue
+            node = prog.lp.nodes[ni]
+            cin = prog.lp.values[node["in0"]][0]
+            cout = prog.lp.values[node["out"]][0]
+            xin = prog.value_view(ws, node["in0"], 1)[0][..., :cin].permute(0, 3, 1, 2)  # NCHW view
+            patches = torch.nn.functional.unfold(xin, (node["kh"], node["kw"]), padding=(node["ph"], node["pw"]),
+                                                 stride=(node["sh"], node["sw"])).transpose(1, 2)
+            acts[ni] = patches.contiguous()
+            g = prog.value_view(ws, node["out"], 2)[1][..., :cout]       # cotangent slot 1: [B, H, W, C]
+            grads[ni] = g.reshape(g.shape[0], -1, cout).contiguous()
+        return acts, grads, prog
+
+
+class EKFACLinearOperator(KFACLinearOperator):
+    r"""Eigenvalue-corrected KFAC ``P blockdiag(Q_l diag(lambda_l) Q_l^T) P^T`` with ``Q_l = Q_g \otimes Q_a``."""
+
+    _COMPUTER = EKFACComputer
+
+    @staticmethod
+    def _compute_canonical_op(computer):
+        QA, QG, lam, mapping = computer.compute()
+        blocks = []
+        for group in mapping:
+            key = tuple(group.values())
+            basis = [QG[key], QA[key]] if key in QA else [QG[key]]
+            blocks.append(EighDecomposedLinearOperator(lam[key].flatten(), KroneckerProductLinearOperator(*basis)))
+        return BlockDiagonalLinearOperator(blocks), mapping
+
+    def inverse(self, damping: float = 0.0):
+        P, K, PT = self
+        return _ChainPyTorchLinearOperator(P, BlockDiagonalLinearOperator([b.inverse(damping=damping) for b in K]),
+                                           PT)

@@ -252,10 +252,14 @@ def kfac_factors(model: torch.nn.Module, loss_func, layer_names: list[str],
     gen.manual_seed(seed)
     for bi, (X, y) in enumerate(data):
         store_in, store_out, hooks = {}, {}, []
+        def make_hook(n):
+            def hook(m, i, o):
+                store_in[n] = i[0].detach()
+                store_out[n] = o
+            return hook
+
         for n in layer_names:
-            hooks.append(mods[n].register_forward_hook(
-                lambda m, i, o, n=n: (store_in.__setitem__(n, i[0].detach()),
-                                      store_out.__setitem__(n, o))))
+            hooks.append(mods[n].register_forward_hook(make_hook(n)))
         out = model(X)
         for h in hooks:
             h.remove()
@@ -311,6 +315,30 @@ def kfac_factors(model: torch.nn.Module, loss_func, layer_names: list[str],
                 cur = torch.einsum("bsi,bsj->ij", g2, g2) * corr
                 G[n] = cur if G[n] is None else G[n] + cur
     return A, G
+
+
+def kfac_grad_outputs(model, loss_func, data, fisher_type="mc", mc_samples=1, seed=2147483647):
+    """The unscaled per-datum seed vectors ``[V, B, C]`` per mini-batch that :func:`kfac_factors` back-propagates
+    (same draws: dedicated generator, per-datum multinomial).  Used to hand the engine identical samples."""
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    res = []
+    for X, y in data:
+        f = model(X).detach()
+        B, C = f.shape
+        if fisher_type == "mc":
+            p = torch.softmax(f, 1)
+            yhat = torch.stack([p[b:b + 1].multinomial(mc_samples, replacement=True, generator=gen)[0]
+                                for b in range(B)])
+            g = p.unsqueeze(1) - torch.nn.functional.one_hot(yhat, C).to(f.dtype)
+            res.append(g.permute(1, 0, 2) / math.sqrt(mc_samples))
+        elif fisher_type == "empirical":
+            ff = f.clone().requires_grad_(True)
+            (g,) = torch.autograd.grad(type(loss_func)(reduction="sum")(ff, y), ff)
+            res.append(g.unsqueeze(0))
+        else:
+            raise NotImplementedError(fisher_type)
+    return res
 
 
 def damped_inverse(S: Tensor, damping: float) -> Tensor:
