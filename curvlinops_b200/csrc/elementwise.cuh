@@ -288,40 +288,47 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot
   }
 }
 
-// gx[pixel] (+)= sum over output windows whose argmax is this pixel of gy (gather form: deterministic)
+// gx[pixel] (+)= sum over output windows whose argmax is this pixel of gy (gather form: deterministic).
+// One thread per (input pixel, 4 channels); only the <= ceil(K/s)^2 windows that contain the pixel are visited.
 __global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
                                    float* __restrict__ gx, long long gx_slot,
                                    const unsigned char* __restrict__ idx, int B, int Hs, int Ws, int Hd,
                                    int Wd, int Cp, int KH, int KW, int sh, int sw, int ph, int pw,
                                    int slot0, int accumulate) {
   const int slot = slot0 + blockIdx.y;
-  const float* g = gy + slot * gy_slot;
-  float* o = gx + slot * gx_slot;
-  const long long total = (long long)B * Hs * Ws * Cp;
+  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+  float4* o = reinterpret_cast<float4*>(gx + slot * gx_slot);
+  const uchar4* ix = reinterpret_cast<const uchar4*>(idx);
+  const int C4 = Cp >> 2;
+  const long long total = (long long)B * Hs * Ws * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % Cp);
-    long long pix = i / Cp;
-    int ws = (int)(pix % Ws);
+    const int c4 = (int)(i % C4);
+    long long pix = i / C4;
+    const int ws = (int)(pix % Ws);
     long long r = pix / Ws;
-    int hs = (int)(r % Hs);
-    int b = (int)(r / Hs);
-    float acc = 0.f;
-    for (int kh = 0; kh < KH; ++kh) {
-      int th = hs + ph - kh;
-      if (th < 0 || th % sh != 0) continue;
-      int hd = th / sh;
-      if (hd >= Hd) continue;
-      for (int kw = 0; kw < KW; ++kw) {
-        int tw = ws + pw - kw;
-        if (tw < 0 || tw % sw != 0) continue;
-        int wd = tw / sw;
-        if (wd >= Wd) continue;
-        long long oi = (((long long)b * Hd + hd) * Wd + wd) * Cp + c;
-        if (idx[oi] == kh * KW + kw) acc += __ldg(g + oi);
+    const int hs = (int)(r % Hs);
+    const int b = (int)(r / Hs);
+    // windows hd with hd*sh - ph <= hs <= hd*sh - ph + KH - 1
+    int hd_lo = hs + ph - KH + 1; hd_lo = hd_lo <= 0 ? 0 : (hd_lo + sh - 1) / sh;
+    int hd_hi = (hs + ph) / sh; if (hd_hi > Hd - 1) hd_hi = Hd - 1;
+    int wd_lo = ws + pw - KW + 1; wd_lo = wd_lo <= 0 ? 0 : (wd_lo + sw - 1) / sw;
+    int wd_hi = (ws + pw) / sw; if (wd_hi > Wd - 1) wd_hi = Wd - 1;
+    float4 acc = f4zero();
+    for (int hd = hd_lo; hd <= hd_hi; ++hd) {
+      const int kh = hs + ph - hd * sh;
+      for (int wd = wd_lo; wd <= wd_hi; ++wd) {
+        const int tap = kh * KW + (ws + pw - wd * sw);
+        const long long oi = (((long long)b * Hd + hd) * Wd + wd) * C4 + c4;
+        const uchar4 t = __ldg(ix + oi);
+        const float4 v = __ldg(g + oi);
+        if (t.x == tap) acc.x += v.x;
+        if (t.y == tap) acc.y += v.y;
+        if (t.z == tap) acc.z += v.z;
+        if (t.w == tap) acc.w += v.w;
       }
     }
-    if (accumulate) acc += o[i];
+    if (accumulate) acc = f4add(acc, o[i]);
     o[i] = acc;
   }
 }

@@ -693,7 +693,7 @@ static int backward(const Ctx& c, int K) {
       case CURV_OP_MAXPOOL: {
         if (!vi.tan) break;
         unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
-        maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems), ns), 256, 0, st>>>(
+        maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems / 4), ns), 256, 0, st>>>(
             c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
             vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ginit[d.in0]);
         LAUNCH_CHECK();
