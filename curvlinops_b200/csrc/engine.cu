@@ -185,8 +185,10 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         n.wbn = g.Kd > 64 ? 128 : 64;
         int nsl = kmax + ((hessian & 1) ? 1 : 0);
         long long tiles = (long long)ceil_div(g.N, n.wbm) * ceil_div(g.Kd, n.wbn) * nsl;
+        if (!(hessian & 1))  // multi-slot tcgen05 wgrad: the slots live inside one tile
+          tiles = (long long)ceil_div(g.Kd, 128) * ceil_div(vo.Cp, 64);
         int want = (int)((2 * 148 + tiles - 1) / tiles);
-        int maxsplit = ceil_div(g.M, 256);
+        int maxsplit = ceil_div(g.M, 512);
         n.nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
         if (n.nsplit > 64) n.nsplit = 64;
         n.m_per_split = (ceil_div(g.M, n.nsplit) + 15) / 16 * 16;

@@ -713,6 +713,232 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Multi-slot wgrad (the GGN/VJP case: one segment):  D_k[i][n] = sum_m In[m][i] * G_k[m][n]  for ALL slots k
+// of a tile at once.  The gathered-input operand (128 columns of tap*Cs+c, the expensive im2col gather) is
+// staged ONCE per 16-pixel stage and multiplied against the 64-channel G tile of every slot: the NS <= 8
+// accumulators [128 x 64] fill the 512 TMEM columns exactly.  Operand traffic per FLOP drops 2.5x versus one
+// slot per tile (the previous kernel was bound by operand re-reads: 21 FLOP per loaded byte).
+//   smem stage (80 KB, 2 stages): In hi/lo 2 x 8 KB, then per slot G hi/lo 2 x 4 KB
+//   MN-major SWIZZLE_128B_BASE32B: chunk c (16 B) of pixel row r at (c>>3)*2048 + r*128 + swz*16
+// TMEM is single-buffered (all 512 columns hold accumulators): the epilogue of a tile delays the first MMA
+// of the next one by a few microseconds out of ~1 ms; accumulation is not chunked (wgrad errors do not
+// compound through layers; measured against fp64 in tools/gpu_fullsize_parity.py).
+// ---------------------------------------------------------------------------------------------------
+constexpr int MS_ROWS = 16;                                  // pixels per stage
+constexpr int MS_A_BYTES = 128 * MS_ROWS * 4;                // 8 KB per plane
+constexpr int MS_B_BYTES = 64 * MS_ROWS * 4;                 // 4 KB per plane and slot
+constexpr int MS_STAGE_BYTES = 2 * MS_A_BYTES + 8 * 2 * MS_B_BYTES;  // 80 KB
+constexpr int MS_STAGES = 2;
+constexpr int MS_SMEM_BYTES = MS_STAGES * MS_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint64_t make_mnmajor_b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;  // stride between 32-wide MN atoms
+  d |= (uint64_t)(512 >> 4) << 32;        // stride between 4-row K atoms
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc_ms(const WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + MS_STAGES * MS_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MS_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * MS_STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * MS_STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MS_STAGES + 2);
+
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NS = p.nslots;  // 1..8 slots, all resident in TMEM
+  const int tiles_i = ceil_div(g.Kd, TC_BM), tiles_j = ceil_div(p.Ng, 64);
+  const int ntiles = tiles_i * tiles_j * p.nsplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MS_STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  auto decode_tile = [&](int tile, int& split, int& i0, int& j0) {
+    const int tj = tile % tiles_j;
+    int rest = tile / tiles_j;
+    const int ti = rest % tiles_i;
+    split = rest / tiles_i;
+    i0 = ti * TC_BM; j0 = tj * 64;
+  };
+  auto stages_of = [&](int split) {
+    const int mb = split * p.m_per_split;
+    const int me = min(g.M, mb + p.m_per_split);
+    return ceil_div(max(0, me - mb), MS_ROWS);
+  };
+
+  if (warp >= 5 && warp < 13) {
+    // ------------------------------------------------------------------ producers
+    const int pt = threadIdx.x - 5 * 32;
+    const int krow = pt >> 4;            // pixel row of the 16-pixel stage
+    const int cq = pt & 15;              // G: chunk cq (16 chunks = 64 channels); In: chunks 2cq, 2cq+1
+    auto smem_off = [&](int c) {         // c = 16-byte chunk index along MN
+      const int c8 = c & 7;
+      const int csw = ((((c8 >> 1) ^ (krow & 3)) << 1) | (c8 & 1));  // Swizzle<2,5,2>
+      return (uint32_t)((c >> 3) * 2048 + krow * 128 + (csw << 4));
+    };
+    const uint32_t offI0 = smem_off(2 * cq), offI1 = smem_off(2 * cq + 1), offG = smem_off(cq);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int split, i0, j0;
+      decode_tile(tile, split, i0, j0);
+      const int mb = split * p.m_per_split;
+      const int me = min(g.M, mb + p.m_per_split);
+      const int nst = stages_of(split);
+      // gathered-input chunks of this thread: columns i0 + (2cq + q)*4
+      int ikh[2], ikw[2], ic[2];
+      bool iok[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int col = i0 + (2 * cq + q) * 4;
+        iok[q] = col < g.Kd;
+        const int tap = iok[q] ? col / g.Cs : 0;
+        ic[q] = col - tap * g.Cs;
+        ikh[q] = tap / g.KW; ikw[q] = tap - ikh[q] * g.KW;
+      }
+      const int ch = j0 + cq * 4;
+      const bool chok = ch < p.Ng;
+      for (int st = 0; st < nst; ++st) {
+        const int m = mb + st * MS_ROWS + krow;
+        const bool mok = m < me;
+        float4 vi[2], vg[8];
+        const int mm = mok ? m : 0;
+        const int bimg = mm / (g.Hd * g.Wd);
+        const int rem = mm - bimg * (g.Hd * g.Wd);
+        const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+        const int h0 = hd * g.sh - g.ph, w0 = wd * g.sw - g.pw;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int hs = h0 + ikh[q], ws = w0 + ikw[q];
+          const bool ok = mok && iok[q] && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+          vi[q] = ok ? __ldg(reinterpret_cast<const float4*>(
+                           p.In + ((((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + ic[q])))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float* grow = p.G + (long long)p.slot0 * p.G_slot + (long long)mm * p.Ng + ch;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          vg[s] = (s < NS && mok && chok) ? __ldg(reinterpret_cast<const float4*>(grow + (long long)s * p.G_slot))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sA = sbase + stage * MS_STAGE_BYTES;
+        const uint32_t sB = sA + 2 * MS_A_BYTES;
+        float4 hi, lo;
+        split_tf32(vi[0], hi, lo);
+        sts128(sA + offI0, hi); sts128(sA + MS_A_BYTES + offI0, lo);
+        split_tf32(vi[1], hi, lo);
+        sts128(sA + offI1, hi); sts128(sA + MS_A_BYTES + offI1, lo);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < NS) {
+            split_tf32(vg[s], hi, lo);
+            sts128(sB + s * 2 * MS_B_BYTES + offG, hi);
+            sts128(sB + s * 2 * MS_B_BYTES + MS_B_BYTES + offG, lo);
+          }
+        }
+        fence_async_proxy();
+        mbar_arrive(full_bar(stage));
+        if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_tf32_idesc(64) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int split, i0, j0;
+        decode_tile(tile, split, i0, j0);
+        const int nst = stages_of(split);
+        mbar_wait(tempty_bar, tphase ^ 1);  // previous tile drained
+        tc_fence_after();
+        for (int st = 0; st < nst; ++st) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = sbase + stage * MS_STAGE_BYTES;
+          const uint32_t sB = sA + 2 * MS_A_BYTES;
+          const uint64_t dAh = make_mnmajor_b32_desc(sA, 2048), dAl = make_mnmajor_b32_desc(sA + MS_A_BYTES, 2048);
+#pragma unroll
+          for (int ks = 0; ks < MS_ROWS / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
+            for (int s = 0; s < NS; ++s) {
+              const uint64_t dBh = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES, 2048);
+              const uint64_t dBl = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES + MS_B_BYTES, 2048);
+              const uint32_t d = tmem_base + (uint32_t)(s * 64);
+              tc_mma_tf32(d, dAl + adv, dBh + adv, idesc, (st | ks) != 0 ? 1u : 0u);
+              tc_mma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
+              tc_mma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
+            }
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar);
+        tphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3, 13-16)
+    const int egrp = warp >= 13 ? 1 : 0;  // slots with (s & 1) == egrp
+    const int quad = warp & 3;
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int split, i0, j0;
+      decode_tile(tile, split, i0, j0);
+      const bool empty_tile = stages_of(split) == 0;
+      const int i = i0 + quad * 32 + lane;
+      mbar_wait(tfull_bar, tphase);
+      tc_fence_after();
+      for (int s = egrp; s < NS; s += 2) {
+        float* outp = p.partial + ((long long)split * p.nslots + s) * (long long)g.N * g.Kd;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 64 + c0), r);
+          if (i < g.Kd) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = j0 + c0 + j;
+              if (n < g.N) outp[(long long)n * g.Kd + i] = empty_tile ? 0.f : __uint_as_float(r[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static inline int tc_bn(int width) { return width > 64 ? 128 : 64; }
@@ -748,6 +974,8 @@ static int tc_sm_count() {
                                       TcCfg<128>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc_ms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      MS_SMEM_BYTES) == cudaSuccess;
       if (!ok) sm_count = 0;
     }
   }
@@ -786,6 +1014,11 @@ static inline int tc_launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   const int sms = tc_sm_count();
   if (sms <= 0) return -1;
   const Geom& g = a.g;
+  if (!a.second_seg && a.nslots >= 2 && a.nslots <= 8) {  // all slots of a tile resident in TMEM
+    int ntiles = ceil_div(g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nsplit;
+    wgrad_gemm_tc_ms<<<ntiles < sms ? ntiles : sms, TC_THREADS, MS_SMEM_BYTES, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
   const int swap = g.N <= 64 ? 1 : 0;
   if (swap) {
     int ntiles = ceil_div(g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nslots * a.nsplit;

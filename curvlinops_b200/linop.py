@@ -177,11 +177,23 @@ class PyTorchLinearOperator:
     def _numpy_bridge(self, f: Callable[[Tensor], Tensor]):
         dev, dt = self.device, self.dtype
 
+        staging: dict = {}  # pinned host buffers, reused across matvecs (ARPACK calls this in a loop)
+
         def call(X: numpy.ndarray) -> numpy.ndarray:
             Y = f(torch.as_tensor(X, dtype=dt, device=dev))
             if Y.dtype == torch.bfloat16:  # NumPy has no bf16
                 Y = Y.float()
-            return Y.detach().cpu().numpy().astype(X.dtype)
+            Y = Y.detach()
+            if Y.device.type == "cuda":
+                key = (tuple(Y.shape), Y.dtype)
+                if key not in staging:
+                    staging.clear()
+                    staging[key] = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True)
+                host = staging[key]
+                host.copy_(Y, non_blocking=True)
+                torch.cuda.current_stream(Y.device).synchronize()
+                return host.numpy().astype(X.dtype)  # astype copies out of the staging buffer
+            return Y.cpu().numpy().astype(X.dtype)
 
         return call
 
