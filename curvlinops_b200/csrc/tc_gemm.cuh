@@ -720,15 +720,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
 // slot per tile (the previous kernel was bound by operand re-reads: 21 FLOP per loaded byte).
 //   smem stage (80 KB, 2 stages): In hi/lo 2 x 8 KB, then per slot G hi/lo 2 x 4 KB
 //   MN-major SWIZZLE_128B_BASE32B: chunk c (16 B) of pixel row r at (c>>3)*2048 + r*128 + swz*16
-// TMEM is single-buffered (all 512 columns hold accumulators): the epilogue of a tile delays the first MMA
-// of the next one by a few microseconds out of ~1 ms; accumulation is not chunked (wgrad errors do not
-// compound through layers; measured against fp64 in tools/gpu_fullsize_parity.py).
+// TMEM is single-buffered (all 512 columns hold accumulators), so draining it stalls the MMAs for a few
+// microseconds; the accumulation is therefore chunked coarsely: every MS_FLUSH = 128 stages (2048 pixels,
+// 768 MMAs per accumulator) the epilogue adds the chunk into the split's partial in global memory with
+// round-to-nearest adds (same thread, same address, fixed order).  That bounds the tensor core's
+// truncation bias (one ~0.5 ulp truncation per MMA; unchunked it reached 9e-5 at B=128).
 // ---------------------------------------------------------------------------------------------------
 constexpr int MS_ROWS = 16;                                  // pixels per stage
 constexpr int MS_A_BYTES = 128 * MS_ROWS * 4;                // 8 KB per plane
 constexpr int MS_B_BYTES = 64 * MS_ROWS * 4;                 // 4 KB per plane and slot
 constexpr int MS_STAGE_BYTES = 2 * MS_A_BYTES + 8 * 2 * MS_B_BYTES;  // 80 KB
 constexpr int MS_STAGES = 2;
+constexpr int MS_FLUSH = 128;                                // stages per TMEM accumulation chunk (2048 pixels)
 constexpr int MS_SMEM_BYTES = MS_STAGES * MS_STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint64_t make_mnmajor_b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -871,31 +874,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc_ms(const WgradArg
         int split, i0, j0;
         decode_tile(tile, split, i0, j0);
         const int nst = stages_of(split);
-        mbar_wait(tempty_bar, tphase ^ 1);  // previous tile drained
-        tc_fence_after();
-        for (int st = 0; st < nst; ++st) {
-          mbar_wait(full_bar(stage), phase);
+        // accumulation chunks of MS_FLUSH stages: bounded truncation chains (see header), an empty tile
+        // still signals once so that the epilogue writes its zeros
+        for (int c0 = 0; c0 < max(nst, 1); c0 += MS_FLUSH) {
+          mbar_wait(tempty_bar, tphase ^ 1);  // previous chunk / tile drained
           tc_fence_after();
-          const uint32_t sA = sbase + stage * MS_STAGE_BYTES;
-          const uint32_t sB = sA + 2 * MS_A_BYTES;
-          const uint64_t dAh = make_mnmajor_b32_desc(sA, 2048), dAl = make_mnmajor_b32_desc(sA + MS_A_BYTES, 2048);
+          const int cend = min(nst, c0 + MS_FLUSH);
+          for (int st = c0; st < cend; ++st) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sA = sbase + stage * MS_STAGE_BYTES;
+            const uint32_t sB = sA + 2 * MS_A_BYTES;
+            const uint64_t dAh = make_mnmajor_b32_desc(sA, 2048), dAl = make_mnmajor_b32_desc(sA + MS_A_BYTES, 2048);
 #pragma unroll
-          for (int ks = 0; ks < MS_ROWS / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
-            for (int s = 0; s < NS; ++s) {
-              const uint64_t dBh = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES, 2048);
-              const uint64_t dBl = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES + MS_B_BYTES, 2048);
-              const uint32_t d = tmem_base + (uint32_t)(s * 64);
-              tc_mma_tf32(d, dAl + adv, dBh + adv, idesc, (st | ks) != 0 ? 1u : 0u);
-              tc_mma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
-              tc_mma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
+            for (int ks = 0; ks < MS_ROWS / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 1024) >> 4);
+              for (int s = 0; s < NS; ++s) {
+                const uint64_t dBh = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES, 2048);
+                const uint64_t dBl = make_mnmajor_b32_desc(sB + s * 2 * MS_B_BYTES + MS_B_BYTES, 2048);
+                const uint32_t d = tmem_base + (uint32_t)(s * 64);
+                tc_mma_tf32(d, dAl + adv, dBh + adv, idesc, ((st - c0) | ks) != 0 ? 1u : 0u);
+                tc_mma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
+                tc_mma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
+              }
             }
+            tc_commit(empty_bar(stage));
+            if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(empty_bar(stage));
-          if (++stage == MS_STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(tfull_bar);
+          tphase ^= 1;
         }
-        tc_commit(tfull_bar);
-        tphase ^= 1;
       }
     }
     __syncwarp();
@@ -907,28 +915,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc_ms(const WgradArg
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int split, i0, j0;
       decode_tile(tile, split, i0, j0);
-      const bool empty_tile = stages_of(split) == 0;
+      const int nst = stages_of(split);
       const int i = i0 + quad * 32 + lane;
-      mbar_wait(tfull_bar, tphase);
-      tc_fence_after();
-      for (int s = egrp; s < NS; s += 2) {
-        float* outp = p.partial + ((long long)split * p.nslots + s) * (long long)g.N * g.Kd;
+      for (int c0 = 0; c0 < max(nst, 1); c0 += MS_FLUSH) {
+        mbar_wait(tfull_bar, tphase);
+        tc_fence_after();
+        for (int s = egrp; s < NS; s += 2) {
+          float* outp = p.partial + ((long long)split * p.nslots + s) * (long long)g.N * g.Kd;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t r[16];
-          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 64 + c0), r);
-          if (i < g.Kd) {
+          for (int cc = 0; cc < 64; cc += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 64 + cc), r);
+            if (i < g.Kd) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = j0 + c0 + j;
-              if (n < g.N) outp[(long long)n * g.Kd + i] = empty_tile ? 0.f : __uint_as_float(r[j]);
+              for (int j = 0; j < 16; ++j) {
+                const int n = j0 + cc + j;
+                if (n < g.N) {
+                  float* dst = outp + (long long)n * g.Kd + i;
+                  float v = nst == 0 ? 0.f : __uint_as_float(r[j]);
+                  if (c0 > 0) v += *dst;  // same thread wrote it in the previous chunk: fixed order
+                  *dst = v;
+                }
+              }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(tempty_bar);
+        tphase ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar);
-      tphase ^= 1;
     }
   }
   tc_fence_before();
