@@ -95,6 +95,25 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column per reduction element)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> 32 lanes x 16 consecutive columns of tensor memory
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -185,7 +204,8 @@ struct TcSmem {
 
 // barrier init + TMEM allocation; returns the TMEM base address.  full_count = arrivals per stage.
 template <int BN>
-__device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* raw, int full_count) {
+__device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* raw, int full_count,
+                                                uint32_t tmem_cols = TcCfg<BN>::TMEM_COLS) {
   using Cfg = TcCfg<BN>;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -195,7 +215,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* ra
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(S.tmem_slot()),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -205,18 +225,41 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* ra
   return *reinterpret_cast<volatile uint32_t*>(raw + (S.tmem_slot() - smem_u32(raw)));
 }
 template <int BN>
-__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, uint32_t tmem_cols = TcCfg<BN>::TMEM_COLS) {
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)TcCfg<BN>::TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
                  : "memory");
   }
 }
 
 // MMA issuer loop body for one tile of T stages: 3xTF32 = 12 MMAs per 32-deep stage.
 // DESC(addr) builds the smem descriptor; K_ADV = descriptor start-address advance (16-byte units) per K=8.
+// TS variant: A (hi/lo) lives in tensor memory columns a_tmem0 + stage*64 (+32 for lo), B in shared memory.
+template <int BN>
+__device__ __forceinline__ void tc_issue_tile_ts(const TcSmem<BN>& S, uint32_t d_tmem, uint32_t a_tmem0, int T,
+                                                 int& stage, uint32_t& phase) {
+  using Cfg = TcCfg<BN>;
+  constexpr uint32_t idesc = make_tf32_idesc(BN);
+  for (int it = 0; it < T; ++it) {
+    mbar_wait(S.full(stage), phase);
+    tc_fence_after();
+    const uint32_t sB = S.stageB(stage);
+    const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
+    const uint32_t aH = a_tmem0 + (uint32_t)(stage * 64), aL = aH + 32u;
+#pragma unroll
+    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+      const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+      tc_mma_tf32_ts(d_tmem, aL + ks * 8, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+      tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBl + adv, idesc, 1u);
+      tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBh + adv, idesc, 1u);
+    }
+    tc_commit(S.empty(stage));
+    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
 template <int BN, bool MN_MAJOR>
 __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tmem, int T, int& stage,
                                               uint32_t& phase) {
@@ -252,10 +295,16 @@ __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tm
 // A: gathered by the producer warps (hi/lo split on the fly).  W: pre-split, pre-swizzled "UMMA image"
 // (pack_umma_kmajor_kernel), one cp.async.bulk per stage straight into shared memory.
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+// TS = true: the gathered A operand (hi/lo) is written by the producers straight into TENSOR MEMORY
+// (tcgen05.st, lane = row) and the MMAs read it from there; only the weights go through shared memory.
+// That removes 2/3 of the shared-memory traffic of a stage (A plane writes + 12 A reads), which is what
+// bounds the SS variant (160 KB per 768-cycle stage against 128 B/clk).
+template <int BN, bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t TMEM_COLS = TS ? 512u : (uint32_t)Cfg::TMEM_COLS;
+  constexpr uint32_t A_TMEM0 = 2 * BN;  // first tensor-memory column of the A stages (TS)
   extern __shared__ uint8_t smem_raw[];
   const TcSmem<BN> S(smem_raw);
   const Geom& g = p.g;
@@ -264,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   const int tiles_m = ceil_div(g.M, TC_BM);
   const int ntiles = tiles_m * tiles_n * nslots;
   const int nchunks = ceil_div(g.Kd, TC_BK);
-  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1, TMEM_COLS);
 
   auto decode_tile = [&](int tile, int& slot, int& m0, int& tn) {
     int si = tile % nslots;
@@ -288,7 +337,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;             // 0..255
-    const int a_row = pt >> 1, a_c0 = (pt & 1) * 4;  // 4 of the 8 16-byte chunks of an A row
+    // SS: two threads per row (4 of the 8 16-byte chunks each).  TS: a warp may only touch its own TMEM lane
+    // quadrant (warp % 4), so row = quadrant*32 + lane and warps 5-8 / 9-12 take reduction columns 0-15 / 16-31.
+    const int a_row = TS ? (warp & 3) * 32 + lane : pt >> 1;
+    const int a_c0 = TS ? ((warp - 5) >> 2) * 4 : (pt & 1) * 4;
     const uint32_t a_off = (uint32_t)((a_row >> 3) * 1024 + (a_row & 7) * 128);
     const bool fast = (g.Cs % TC_BK) == 0;  // a 128-byte K row never straddles two filter taps
     // iteration state
@@ -385,15 +437,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
             "l"(wsrc), "r"(bytes), "r"(S.full(stage))
             : "memory");
       }
+      if (TS) {
+        float vh[16], vl[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 hi, lo;
-        split_tf32(cur[j], hi, lo);
-        const uint32_t o = a_off + (uint32_t)(((a_c0 + j) ^ (a_row & 7)) << 4);
-        sts128(sA + o, hi);
-        sts128(sA + Cfg::A_BYTES + o, lo);
+        for (int j = 0; j < 4; ++j) {
+          float4 hi, lo;
+          split_tf32(cur[j], hi, lo);
+          vh[4 * j] = hi.x; vh[4 * j + 1] = hi.y; vh[4 * j + 2] = hi.z; vh[4 * j + 3] = hi.w;
+          vl[4 * j] = lo.x; vl[4 * j + 1] = lo.y; vl[4 * j + 2] = lo.z; vl[4 * j + 3] = lo.w;
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_TMEM0 +
+                            (uint32_t)(stage * 64 + a_c0 * 4);
+        tc_st16(ta, vh);
+        tc_st16(ta + 32u, vl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 hi, lo;
+          split_tf32(cur[j], hi, lo);
+          const uint32_t o = a_off + (uint32_t)(((a_c0 + j) ^ (a_row & 7)) << 4);
+          sts128(sA + o, hi);
+          sts128(sA + Cfg::A_BYTES + o, lo);
+        }
+        fence_async_proxy();
       }
-      fence_async_proxy();
       mbar_arrive(S.full(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
@@ -412,7 +481,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
           mbar_wait(S.tempty(acc), acc_phase ^ 1);
           tc_fence_after();
-          tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
+          if (TS)
+            tc_issue_tile_ts<BN>(S, tmem_base + (uint32_t)(acc * BN), tmem_base + A_TMEM0, min(TC_FLUSH, T - t0),
+                                 stage, phase);
+          else
+            tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
           tc_commit(S.tfull(acc));  // chunk complete -> epilogue
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -472,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       }
     }
   }
-  tc_teardown<BN>(tmem_base);
+  tc_teardown<BN>(tmem_base, TMEM_COLS);
 }
 
 // Pre-split, pre-swizzled weight image for gather_gemm_tc:
@@ -721,8 +794,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
 //   smem stage (80 KB, 2 stages): In hi/lo 2 x 8 KB, then per slot G hi/lo 2 x 4 KB
 //   MN-major SWIZZLE_128B_BASE32B: chunk c (16 B) of pixel row r at (c>>3)*2048 + r*128 + swz*16
 // TMEM is single-buffered (all 512 columns hold accumulators), so draining it stalls the MMAs for a few
-// microseconds; the accumulation is therefore chunked coarsely: every MS_FLUSH = 128 stages (2048 pixels,
-// 768 MMAs per accumulator) the epilogue adds the chunk into the split's partial in global memory with
+// microseconds; the accumulation is therefore chunked coarsely: every MS_FLUSH = 256 stages (4096 pixels,
+// 1536 MMAs per accumulator) the epilogue adds the chunk into the split's partial in global memory with
 // round-to-nearest adds (same thread, same address, fixed order).  That bounds the tensor core's
 // truncation bias (one ~0.5 ulp truncation per MMA; unchunked it reached 9e-5 at B=128).
 // ---------------------------------------------------------------------------------------------------
@@ -731,7 +804,7 @@ constexpr int MS_A_BYTES = 128 * MS_ROWS * 4;                // 8 KB per plane
 constexpr int MS_B_BYTES = 64 * MS_ROWS * 4;                 // 4 KB per plane and slot
 constexpr int MS_STAGE_BYTES = 2 * MS_A_BYTES + 8 * 2 * MS_B_BYTES;  // 80 KB
 constexpr int MS_STAGES = 2;
-constexpr int MS_FLUSH = 128;                                // stages per TMEM accumulation chunk (2048 pixels)
+constexpr int MS_FLUSH = 256;                                // stages per TMEM accumulation chunk (2048 pixels)
 constexpr int MS_SMEM_BYTES = MS_STAGES * MS_STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint64_t make_mnmajor_b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -981,9 +1054,13 @@ static int tc_sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
     sm_count = prop.major == 10 ? prop.multiProcessorCount : 0;  // tcgen05 needs sm_100
     if (sm_count > 0) {
-      bool ok = cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      bool ok = cudaFuncSetAttribute(gather_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TcCfg<128>::SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<128>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<64>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<128>::SMEM_BYTES) == cudaSuccess;
@@ -1011,16 +1088,20 @@ static inline int tc_pack_image(const float* src, long long src_slot, float* dst
 }
 
 // returns 0 on success, >0 on a CUDA error, <0 if the problem should use the SIMT path
-static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
+static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st, bool ts) {
   const int sms = tc_sm_count();
   if (sms <= 0 || a.W_img == nullptr) return -1;
   const Geom& g = a.g;
   if (tc_bn(g.Nd) == 128) {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
-    gather_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    int grid = ntiles < sms ? ntiles : sms;
+    if (ts) gather_gemm_tc<128, true><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    else gather_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
   } else {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
-    gather_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    int grid = ntiles < sms ? ntiles : sms;
+    if (ts) gather_gemm_tc<64, true><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    else gather_gemm_tc<64, false><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -1050,7 +1131,7 @@ static inline bool tc_gather_eligible(const Geom&, int) { return false; }
 static inline bool tc_wgrad_eligible(const Geom&, int) { return false; }
 static inline long long tc_image_elems(int, int, int) { return 0; }
 static inline int tc_pack_image(const float*, long long, float*, long long, int, int, int, int, cudaStream_t) { return -1; }
-static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t) { return -1; }
+static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t, bool) { return -1; }
 static inline int tc_launch_wgrad(const WgradArgs&, cudaStream_t) { return -1; }
 #endif
 

@@ -9,7 +9,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-struct Variant { int layout_type; int lbo, sbo; int writer; int a_major, b_major; };
+struct Variant { int layout_type; int lbo, sbo; int writer; int a_major, b_major; int ts; };
 
 // writer: byte offset of element (mn, k) inside an operand tile with MN extent `mnext`
 __device__ __host__ inline int elem_off(int writer, int mn, int k, int lbo, int sbo) {
@@ -53,13 +53,26 @@ __global__ void probe(Variant v, const float* A, const float* B, float* D) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem = tmem_slot;
+  if (v.ts) {  // A operand from tensor memory: lane = row m, columns 64..71 = k
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    uint32_t r[8];
+    for (int k = 0; k < 8; ++k) r[k] = __float_as_uint(A[(w * 32 + l) * 8 + k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(
+                     tmem + ((uint32_t)(w * 32) << 16) + 64u),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   if (threadIdx.x == 0) {
     auto desc = [&](uint32_t addr) {
       uint64_t d = 0;
@@ -73,9 +86,15 @@ __global__ void probe(Variant v, const float* A, const float* B, float* D) {
     uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)v.a_major << 15) | ((uint32_t)v.b_major << 16) |
                      ((64u >> 3) << 17) | ((128u >> 4) << 24);
     uint64_t da = desc(base), db = desc(base + 32768);
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db),
-                 "r"(idesc), "r"(0u) : "memory");
+    if (v.ts) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(tmem + 64u),
+                   "l"(db), "r"(idesc), "r"(0u) : "memory");
+    } else {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db),
+                   "r"(idesc), "r"(0u) : "memory");
+    }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
   // wait
@@ -97,7 +116,7 @@ __global__ void probe(Variant v, const float* A, const float* B, float* D) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem));
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
 int main() {
@@ -112,15 +131,16 @@ int main() {
   cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
   Variant vs[] = {
-      {2, 16, 1024, 0, 0, 0},      // control: K-major SW128
-      {2, 4096, 1024, 1, 1, 1},    // MN SW128, lbo = atom stride, sbo = k-group stride
-      {2, 1024, 4096, 1, 1, 1},    //   (writer uses lbo for atoms; try both orders)
-      {1, 4096, 512, 2, 1, 1},     // MN SW128_BASE32B
-      {1, 512, 4096, 2, 1, 1},
-      {0, 128, 256, 3, 1, 1},      // MN no swizzle: sbo between mn cores (128 B apart), lbo between k groups
-      {0, 4096, 128, 3, 1, 1},
-      {0, 128, 4096, 4, 1, 1},
-      {0, 256, 128, 4, 1, 1},
+      {2, 16, 1024, 0, 0, 0, 0},   // control: K-major SW128
+      {2, 16, 1024, 0, 0, 0, 1},   // TS mode: A from TMEM (lane = row, column = k), B K-major SW128
+      {2, 4096, 1024, 1, 1, 1, 0},    // MN SW128, lbo = atom stride, sbo = k-group stride
+      {2, 1024, 4096, 1, 1, 1, 0},    //   (writer uses lbo for atoms; try both orders)
+      {1, 4096, 512, 2, 1, 1, 0},     // MN SW128_BASE32B
+      {1, 512, 4096, 2, 1, 1, 0},
+      {0, 128, 256, 3, 1, 1, 0},      // MN no swizzle: sbo between mn cores (128 B apart), lbo between k groups
+      {0, 4096, 128, 3, 1, 1, 0},
+      {0, 128, 4096, 4, 1, 1, 0},
+      {0, 256, 128, 4, 1, 1, 0},
   };
   for (auto& v : vs) {
     cudaMemset(dD, 0, D.size() * 4);
@@ -129,8 +149,8 @@ int main() {
     cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
     double err = 0, nz = 0;
     for (int i = 0; i < 128 * 64; ++i) { err = fmax(err, fabs(D[i] - R[i])); nz += D[i] != 0; }
-    printf("type=%d lbo=%d sbo=%d writer=%d major=%d%d : %s max_err=%g nonzero=%g  D[0..3]=%g %g %g %g ref=%g %g %g %g\n",
-           v.layout_type, v.lbo, v.sbo, v.writer, v.a_major, v.b_major, cudaGetErrorString(e), err, nz, D[0], D[1], D[2], D[3],
+    printf("ts=%d type=%d lbo=%d sbo=%d writer=%d major=%d%d : %s max_err=%g nonzero=%g  D[0..3]=%g %g %g %g ref=%g %g %g %g\n",
+           v.ts, v.layout_type, v.lbo, v.sbo, v.writer, v.a_major, v.b_major, cudaGetErrorString(e), err, nz, D[0], D[1], D[2], D[3],
            R[0], R[1], R[2], R[3]);
     if (e != cudaSuccess) break;
   }
