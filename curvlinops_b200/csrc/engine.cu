@@ -304,7 +304,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   const Geom& g = a.g;
   ProfScope prof(0, flops, st);
   if (g_tc_mode && a.W_img != nullptr) {
-    int rc = tc_launch_gather_gemm(a, nslots, st, !(g_tc_disable & 4));
+    int rc = tc_launch_gather_gemm(a, nslots, st);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
     // rc < 0: not eligible after all -> SIMT
