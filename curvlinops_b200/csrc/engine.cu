@@ -22,8 +22,7 @@ using namespace curv;
 static thread_local std::string g_err;
 static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
-static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
-                                // 4 = gather GEMM with the A operand in shared memory (SS) instead of TMEM (TS)
+static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -110,7 +109,7 @@ extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 7;
+  g_tc_disable = (mode >> 4) & 3;
   return old;
 }
 

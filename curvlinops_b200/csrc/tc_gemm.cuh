@@ -95,25 +95,6 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// same with the A operand in tensor memory (lane = row, one 32-bit column per reduction element)
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                               uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// registers -> 32 lanes x 16 consecutive columns of tensor memory
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
-        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
-      : "memory");
-}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -204,8 +185,7 @@ struct TcSmem {
 
 // barrier init + TMEM allocation; returns the TMEM base address.  full_count = arrivals per stage.
 template <int BN>
-__device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* raw, int full_count,
-                                                uint32_t tmem_cols = TcCfg<BN>::TMEM_COLS) {
+__device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* raw, int full_count) {
   using Cfg = TcCfg<BN>;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -215,7 +195,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* ra
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(S.tmem_slot()),
-                 "r"(tmem_cols)
+                 "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -225,41 +205,18 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcSmem<BN>& S, uint8_t* ra
   return *reinterpret_cast<volatile uint32_t*>(raw + (S.tmem_slot() - smem_u32(raw)));
 }
 template <int BN>
-__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, uint32_t tmem_cols = TcCfg<BN>::TMEM_COLS) {
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TcCfg<BN>::TMEM_COLS)
                  : "memory");
   }
 }
 
 // MMA issuer loop body for one tile of T stages: 3xTF32 = 12 MMAs per 32-deep stage.
 // DESC(addr) builds the smem descriptor; K_ADV = descriptor start-address advance (16-byte units) per K=8.
-// TS variant: A (hi/lo) lives in tensor memory columns a_tmem0 + stage*64 (+32 for lo), B in shared memory.
-template <int BN>
-__device__ __forceinline__ void tc_issue_tile_ts(const TcSmem<BN>& S, uint32_t d_tmem, uint32_t a_tmem0, int T,
-                                                 int& stage, uint32_t& phase) {
-  using Cfg = TcCfg<BN>;
-  constexpr uint32_t idesc = make_tf32_idesc(BN);
-  for (int it = 0; it < T; ++it) {
-    mbar_wait(S.full(stage), phase);
-    tc_fence_after();
-    const uint32_t sB = S.stageB(stage);
-    const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
-    const uint32_t aH = a_tmem0 + (uint32_t)(stage * 64), aL = aH + 32u;
-#pragma unroll
-    for (int ks = 0; ks < TC_BK / 8; ++ks) {
-      const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-      tc_mma_tf32_ts(d_tmem, aL + ks * 8, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-      tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBl + adv, idesc, 1u);
-      tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBh + adv, idesc, 1u);
-    }
-    tc_commit(S.empty(stage));
-    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-  }
-}
-
 template <int BN, bool MN_MAJOR>
 __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tmem, int T, int& stage,
                                               uint32_t& phase) {
@@ -292,63 +249,22 @@ __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tm
 
 // ---------------------------------------------------------------------------------------------------
 // gather GEMM (forward conv + tangents, dgrad):  out[m][n] = sum_seg sum_r gather(A)[m][r] * W[n][r]
-//
-// Operand paths (chosen after measuring that the SS variant was bound by L2 -> SM operand traffic, ~6.9 TB/s,
-// not by the tensor pipe or shared memory):
-//   A (gathered activations): producers load 64 B per thread, split hi/lo in registers and write BOTH planes
-//     straight into TENSOR MEMORY (tcgen05.st, lane = row); the MMAs take A from TMEM (TS form).  No shared
-//     memory traffic for A at all.
-//   W (weights): the RAW fp32 [BN x 32] block of the stage arrives with one cp.async.bulk (16 KB instead of
-//     the 32 KB of a pre-split image: half the L2 traffic), issued one iteration ahead; the producers then
-//     split it shared -> registers -> shared into the swizzled hi/lo planes the MMAs read.
+// A: gathered by the producer warps (hi/lo split on the fly).  W: pre-split, pre-swizzled "UMMA image"
+// (pack_umma_kmajor_kernel), one cp.async.bulk per stage straight into shared memory.
 // ---------------------------------------------------------------------------------------------------
 template <int BN>
-struct GtCfg {
-  static constexpr int STAGES = 4;
-  static constexpr int B_BYTES = BN * 128;               // one plane, also the raw block
-  static constexpr int STAGE_BYTES = 3 * B_BYTES;        // [hi][lo][raw]
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr uint32_t A_TMEM0 = 2 * BN;            // A stages: 64 columns each (hi 32 | lo 32)
-};
-
-template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
-  using Cfg = GtCfg<BN>;
+  using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = sbase + STAGES * Cfg::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };                  // planes + TMEM A ready
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };      // MMAs of the stage retired
-  auto raw_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };    // raw weight block landed
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
-  auto stageB = [&](int s) { return sbase + (uint32_t)(s * Cfg::STAGE_BYTES); };
-
+  const TcSmem<BN> S(smem_raw);
   const Geom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = ceil_div(g.Nd, BN);
   const int tiles_m = ceil_div(g.M, TC_BM);
   const int ntiles = tiles_m * tiles_n * nslots;
   const int nchunks = ceil_div(g.Kd, TC_BK);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); mbar_init(raw_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
 
   auto decode_tile = [&](int tile, int& slot, int& m0, int& tn) {
     int si = tile % nslots;
@@ -372,45 +288,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;  // 0..255
-    // a warp may only touch its own TMEM lane quadrant (warp % 4): row = quadrant*32 + lane; warps 5-8 /
-    // 9-12 take reduction columns 0-15 / 16-31 of the 32-wide stage (64 contiguous bytes per thread)
-    const int quad = warp & 3;
-    const int a_row = quad * 32 + lane;
-    const int a_c0 = ((warp - 5) >> 2) * 4;
-    // weight conversion: BN rows x 8 chunks, (BN/32) chunks per thread
-    constexpr int BCH = BN / 32;
-    const int b_row = (BN == 128) ? (pt >> 1) : (pt >> 2);
-    const int b_c0 = (BN == 128) ? (pt & 1) * 4 : (pt & 3) * 2;
-    const uint32_t b_swz = (uint32_t)((b_row >> 3) * 1024 + (b_row & 7) * 128);
+    // Coalesced gather: 8 consecutive lanes read the 8 16-byte chunks of ONE 128-byte K row, a warp request
+    // covers 4 rows = 4 cache lines (ncu on the one-row-per-lane mapping: 31.5 sectors per request and the
+    // LSU data pipe at 83 % -- the kernel was bound by L1TEX wavefronts, not by L2, smem or the tensor pipe).
+    // Thread -> chunk a_c of rows a_r0 + 32 i, i = 0..3.
+    const int a_c = pt & 7, a_r0 = pt >> 3;
+    const uint32_t a_off = (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4));
     const bool fast = (g.Cs % TC_BK) == 0;  // a 128-byte K row never straddles two filter taps
     // iteration state
     int tile = blockIdx.x, slot = 0, m0 = 0, tn = 0, nseg = 0, seg = 0, kc = 0;
     int kh = 0, kw = 0, cb = 0;
-    bool m_ok = false;
-    int ah = 0, aw = 0;
-    long long abase = 0;
+    bool m_ok[4];
+    int ah[4], aw[4];
+    long long abase[4];
     const float* Ap = nullptr;
     const float* Wimg = nullptr;
     auto enter_tile = [&]() {
       decode_tile(tile, slot, m0, tn);
       nseg = num_segments(slot);
-      const int m = m0 + a_row;
-      m_ok = m < g.M;
-      const int mm = m_ok ? m : 0;
-      const int bimg = mm / (g.Hd * g.Wd);
-      const int rem = mm - bimg * (g.Hd * g.Wd);
-      const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
-      ah = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
-      aw = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
-      abase = (long long)bimg * g.Hs * g.Ws;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + a_r0 + 32 * i;
+        m_ok[i] = m < g.M;
+        const int mm = m_ok[i] ? m : 0;
+        const int bimg = mm / (g.Hd * g.Wd);
+        const int rem = mm - bimg * (g.Hd * g.Wd);
+        const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+        ah[i] = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
+        aw[i] = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
+        abase[i] = (long long)bimg * g.Hs * g.Ws;
+      }
       seg = 0; kc = 0; kh = 0; kw = 0; cb = 0;
       segment(slot, 0, Ap, Wimg);
     };
-    auto source_pixel = [&](int kh_, int kw_, int& hs, int& ws) -> bool {
-      bool ok = m_ok;
-      if (g.mode == 0) { hs = ah + kh_; ws = aw + kw_; }
+    auto source_pixel = [&](int i, int kh_, int kw_, int& hs, int& ws) -> bool {
+      bool ok = m_ok[i];
+      if (g.mode == 0) { hs = ah[i] + kh_; ws = aw[i] + kw_; }
       else {
-        const int th = ah - kh_, tw = aw - kw_;
+        const int th = ah[i] - kh_, tw = aw[i] - kw_;
         ok = ok && th >= 0 && tw >= 0;
         hs = th / g.sh; ws = tw / g.sw;
         ok = ok && hs * g.sh == th && ws * g.sw == tw;
@@ -418,26 +333,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       return ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
     };
     auto issue = [&](float4 (&v)[4]) {
-      if (fast) {
+      int kh_ = kh, kw_ = kw, c = cb + a_c * 4;
+      bool rok = true;
+      if (!fast) {  // the 16-byte chunk decides its own filter tap (C_in not a multiple of 32, e.g. the stem)
+        const int r = kc * TC_BK + a_c * 4;
+        const int tap = r / g.Cs;
+        c = r - tap * g.Cs;
+        kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
+        rok = r < g.Kd;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         int hs, ws;
-        const bool ok = source_pixel(kh, kw, hs, ws);
-        const float* rowp = Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + cb + a_c0 * 4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(rowp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = kc * TC_BK + (a_c0 + j) * 4;
-          const int tap = r / g.Cs;
-          const int c = r - tap * g.Cs;
-          const int kh_ = tap / g.KW, kw_ = tap - kh_ * g.KW;
-          int hs, ws;
-          const bool ok = r < g.Kd && source_pixel(kh_, kw_, hs, ws);
-          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(
-                          Ap + ((abase + (long long)hs * g.Ws + ws) * g.Cs + c)))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const bool ok = rok && source_pixel(i, kh_, kw_, hs, ws);
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(
+                        Ap + ((abase[i] + (long long)hs * g.Ws + ws) * g.Cs + c)))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     // advance to the next (tile, seg, kc); returns false when this CTA is done
@@ -453,85 +364,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       enter_tile();
       return true;
     };
-    auto weight_block = [&]() { return Wimg + ((long long)tn * nchunks + kc) * (BN * TC_BK); };
-    // thread 0: request the raw weight block of an iteration into stage s (after the stage was released)
-    auto request_weights = [&](const float* src, int s, uint32_t ph) {
-      mbar_wait(empty_bar(s), ph ^ 1);
-      const uint32_t bytes = Cfg::B_BYTES;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(raw_bar(s)), "r"(bytes)
-                   : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              stageB(s) + 2 * Cfg::B_BYTES),
-          "l"(src), "r"(bytes), "r"(raw_bar(s))
-          : "memory");
-    };
 
     int stage = 0;
     uint32_t phase = 0;
     bool have = tile < ntiles;
     float4 cur[4], nxt[4];
-    if (have) {
-      enter_tile();
-      issue(cur);
-      if (pt == 0) request_weights(weight_block(), 0, 0);
-    }
+    if (have) { enter_tile(); issue(cur); }
     while (have) {
+      // weight block of the current iteration (captured before the state advances)
+      const float* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK);
       const bool have_next = advance();
-      const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
-      const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
-      if (have_next) {
-        issue(nxt);  // prefetch: next stage's activation loads are in flight while this one is processed
-        if (pt == 0) request_weights(weight_block(), nstage, nphase);  // weights one iteration ahead
+      if (have_next) issue(nxt);  // prefetch: next stage's loads are in flight while we store
+      mbar_wait(S.empty(stage), phase ^ 1);
+      const uint32_t sA = S.stageA(stage);
+      if (pt == 0) {
+        const uint32_t bytes = 2 * Cfg::B_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                S.stageB(stage)),
+            "l"(wsrc), "r"(bytes), "r"(S.full(stage))
+            : "memory");
       }
-      mbar_wait(empty_bar(stage), phase ^ 1);
-      // ---- A: split in registers, write hi / lo planes to tensor memory
-      {
-        float vh[16], vl[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 hi, lo;
-          split_tf32(cur[j], hi, lo);
-          vh[4 * j] = hi.x; vh[4 * j + 1] = hi.y; vh[4 * j + 2] = hi.z; vh[4 * j + 3] = hi.w;
-          vl[4 * j] = lo.x; vl[4 * j + 1] = lo.y; vl[4 * j + 2] = lo.z; vl[4 * j + 3] = lo.w;
-        }
-        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::A_TMEM0 +
-                            (uint32_t)(stage * 64 + a_c0 * 4);
-        tc_st16(ta, vh);
-        tc_st16(ta + 32u, vl);
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        split_tf32(cur[i], hi, lo);
+        const uint32_t o = a_off + (uint32_t)(i * 4096);  // row + 32 i: four 8-row groups further
+        sts128(sA + o, hi);
+        sts128(sA + Cfg::A_BYTES + o, lo);
       }
-      // ---- W: raw block (shared) -> hi / lo swizzled planes (shared)
-      mbar_wait(raw_bar(stage), phase);
-      {
-        const uint32_t sB = stageB(stage);
-#pragma unroll
-        for (int j = 0; j < BCH; ++j) {
-          float4 v;
-          const uint32_t src = sB + 2 * Cfg::B_BYTES + (uint32_t)(b_row * 128 + (b_c0 + j) * 16);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(src)
-                       : "memory");
-          float4 hi, lo;
-          split_tf32(v, hi, lo);
-          const uint32_t o = b_swz + (uint32_t)(((b_c0 + j) ^ (b_row & 7)) << 4);
-          sts128(sB + o, hi);
-          sts128(sB + Cfg::B_BYTES + o, lo);
-        }
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_async_proxy();
-      tc_fence_before();
-      mbar_arrive(full_bar(stage));
-      stage = nstage; phase = nphase;
+      mbar_arrive(S.full(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
       have = have_next;
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_tf32_idesc(BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -539,27 +413,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         decode_tile(tile, slot, m0, tn);
         const int T = num_segments(slot) * nchunks;
         for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          mbar_wait(S.tempty(acc), acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-          const int tend = min(T, t0 + TC_FLUSH);
-          for (int it = t0; it < tend; ++it) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sB = stageB(stage);
-            const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
-            const uint32_t aH = tmem_base + Cfg::A_TMEM0 + (uint32_t)(stage * 64), aL = aH + 32u;
-#pragma unroll
-            for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-              tc_mma_tf32_ts(d_tmem, aL + ks * 8, dBh + adv, idesc, ((it - t0) | ks) != 0 ? 1u : 0u);
-              tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBl + adv, idesc, 1u);
-              tc_mma_tf32_ts(d_tmem, aH + ks * 8, dBh + adv, idesc, 1u);
-            }
-            tc_commit(empty_bar(stage));
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-          tc_commit(tfull_bar(acc));  // chunk complete -> epilogue
+          tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
+          tc_commit(S.tfull(acc));  // chunk complete -> epilogue
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -581,7 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
 #pragma unroll
       for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
       for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait(S.tfull(acc), acc_phase);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 16) {
@@ -591,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
           for (int j = 0; j < 16; ++j) accv[c0 + j] += __uint_as_float(r[j]);
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        mbar_arrive(S.tempty(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       const float* bias = (slot == 0) ? p.bias
@@ -618,21 +475,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
+  tc_teardown<BN>(tmem_base);
 }
 
-// Block-tiled RAW weight image for gather_gemm_tc: block (tn, kc) = BN rows x 32 fp32 (128 B per row),
-// blocks ordered tn-major, zero padded; one block = one cp.async.bulk.  src: [N][Kd] row-major.  grid.y = slot.
-__global__ void pack_weight_blocks_kernel(const float* __restrict__ src, long long src_slot,
-                                          float* __restrict__ dst, long long dst_slot, int N, int Kd, int BN,
-                                          int tiles_n, int nchunks) {
+// Pre-split, pre-swizzled weight image for gather_gemm_tc:
+//   block (tn, kc) = [hi plane: BN rows x 128 B, 128B-swizzled][lo plane], blocks ordered tn-major.
+// src: [N][Kd] row-major (the SIMT-layout packed weights).  grid.y = slot.
+__global__ void pack_umma_kmajor_kernel(const float* __restrict__ src, long long src_slot,
+                                        float* __restrict__ dst, long long dst_slot, int N, int Kd, int BN,
+                                        int tiles_n, int nchunks) {
   src += blockIdx.y * src_slot;
   dst += blockIdx.y * dst_slot;
-  const long long total = (long long)tiles_n * nchunks * BN * 8;  // 16-byte chunks
+  const long long total = (long long)tiles_n * nchunks * BN * 8;  // 16-byte chunks per plane
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e & 7);
@@ -643,7 +497,12 @@ __global__ void pack_weight_blocks_kernel(const float* __restrict__ src, long lo
     const int n = tn * BN + r, k = kc * TC_BK + c * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N && k < Kd) v = __ldg(reinterpret_cast<const float4*>(src + (long long)n * Kd + k));
-    reinterpret_cast<float4*>(dst)[e] = v;
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    float* blk = dst + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 2;
+    *reinterpret_cast<float4*>(blk + o) = hi;
+    *reinterpret_cast<float4*>(blk + BN * TC_BK + o) = lo;
   }
 }
 
@@ -1114,7 +973,7 @@ static inline bool tc_wgrad_eligible(const Geom& g, int mode) {
 // size (floats) of the UMMA weight image of an [N][Kd] matrix
 static inline long long tc_image_elems(int N, int Nd, int Kd) {
   const int BN = tc_bn(Nd);
-  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, TC_BK) * (BN * TC_BK);
+  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, TC_BK) * (2 * BN * TC_BK);
 }
 
 static int tc_sm_count() {
@@ -1126,9 +985,9 @@ static int tc_sm_count() {
     sm_count = prop.major == 10 ? prop.multiProcessorCount : 0;  // tcgen05 needs sm_100
     if (sm_count > 0) {
       bool ok = cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     GtCfg<128>::SMEM_BYTES) == cudaSuccess;
+                                     TcCfg<128>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      GtCfg<64>::SMEM_BYTES) == cudaSuccess;
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<128>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1149,7 +1008,7 @@ static inline int tc_pack_image(const float* src, long long src_slot, float* dst
   long long total = (long long)tiles_n * nchunks * BN * 8;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weight_blocks_kernel<<<dim3(blocks, nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
+  pack_umma_kmajor_kernel<<<dim3(blocks, nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
                                                               tiles_n, nchunks);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -1161,10 +1020,10 @@ static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cud
   const Geom& g = a.g;
   if (tc_bn(g.Nd) == 128) {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
-    gather_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, GtCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    gather_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
   } else {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
-    gather_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, GtCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    gather_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
