@@ -22,7 +22,8 @@ using namespace curv;
 static thread_local std::string g_err;
 static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
-static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM
+static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
+                                // 4 = gather GEMM with the 8-lanes-per-row (coalesced) producer mapping
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -109,7 +110,7 @@ extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 3;
+  g_tc_disable = (mode >> 4) & 7;
   return old;
 }
 
@@ -303,7 +304,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   const Geom& g = a.g;
   ProfScope prof(0, flops, st);
   if (g_tc_mode && a.W_img != nullptr) {
-    int rc = tc_launch_gather_gemm(a, nslots, st);
+    int rc = tc_launch_gather_gemm(a, nslots, st, (g_tc_disable & 4) != 0);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
     // rc < 0: not eligible after all -> SIMT

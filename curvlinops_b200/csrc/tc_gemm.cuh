@@ -252,7 +252,7 @@ __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tm
 // A: gathered by the producer warps (hi/lo split on the fly).  W: pre-split, pre-swizzled "UMMA image"
 // (pack_umma_kmajor_kernel), one cp.async.bulk per stage straight into shared memory.
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool COAL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemmArgs p, int nslots) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -288,27 +288,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;  // 0..255
-    // Coalesced gather: 8 consecutive lanes read the 8 16-byte chunks of ONE 128-byte K row, a warp request
-    // covers 4 rows = 4 cache lines (ncu on the one-row-per-lane mapping: 31.5 sectors per request and the
-    // LSU data pipe at 83 % -- the kernel was bound by L1TEX wavefronts, not by L2, smem or the tensor pipe).
-    // Thread -> chunk a_c of rows a_r0 + 32 i, i = 0..3.
-    const int a_c = pt & 7, a_r0 = pt >> 3;
-    const uint32_t a_off = (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4));
+    // Two thread -> data mappings (template COAL):
+    //  COAL: 8 consecutive lanes read the 8 16-byte chunks of ONE 128-byte K row (a warp request = 4 rows =
+    //        4 cache lines); thread -> chunk a_c of rows a_r0 + 32 i, i = 0..3.
+    //  !COAL: two threads per row, 4 consecutive chunks (64 B) each; fewer address computations per thread,
+    //        but 31.5 sectors per warp request (ncu).
+    constexpr int NR = COAL ? 4 : 1;               // rows per thread
+    const int a_c = pt & 7, a_r0 = pt >> 3;         // COAL
+    const int a_row = pt >> 1, a_c0 = (pt & 1) * 4; // !COAL
+    const uint32_t a_off = COAL ? (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4))
+                                : (uint32_t)((a_row >> 3) * 1024 + (a_row & 7) * 128);
     const bool fast = (g.Cs % TC_BK) == 0;  // a 128-byte K row never straddles two filter taps
     // iteration state
     int tile = blockIdx.x, slot = 0, m0 = 0, tn = 0, nseg = 0, seg = 0, kc = 0;
     int kh = 0, kw = 0, cb = 0;
-    bool m_ok[4];
-    int ah[4], aw[4];
-    long long abase[4];
+    bool m_ok[NR];
+    int ah[NR], aw[NR];
+    long long abase[NR];
     const float* Ap = nullptr;
     const float* Wimg = nullptr;
     auto enter_tile = [&]() {
       decode_tile(tile, slot, m0, tn);
       nseg = num_segments(slot);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = m0 + a_r0 + 32 * i;
+      for (int i = 0; i < NR; ++i) {
+        const int m = m0 + (COAL ? a_r0 + 32 * i : a_row);
         m_ok[i] = m < g.M;
         const int mm = m_ok[i] ? m : 0;
         const int bimg = mm / (g.Hd * g.Wd);
@@ -333,22 +337,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       return ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
     };
     auto issue = [&](float4 (&v)[4]) {
-      int kh_ = kh, kw_ = kw, c = cb + a_c * 4;
-      bool rok = true;
-      if (!fast) {  // the 16-byte chunk decides its own filter tap (C_in not a multiple of 32, e.g. the stem)
-        const int r = kc * TC_BK + a_c * 4;
-        const int tap = r / g.Cs;
-        c = r - tap * g.Cs;
-        kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
-        rok = r < g.Kd;
-      }
+      if (COAL) {
+        int kh_ = kh, kw_ = kw, c = cb + a_c * 4;
+        bool rok = true;
+        if (!fast) {  // the 16-byte chunk decides its own filter tap (C_in not a multiple of 32: the stem)
+          const int r = kc * TC_BK + a_c * 4;
+          const int tap = r / g.Cs;
+          c = r - tap * g.Cs;
+          kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
+          rok = r < g.Kd;
+        }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {
+          int hs, ws;
+          const bool ok = rok && source_pixel(i % NR, kh_, kw_, hs, ws);
+          v[i] = ok ? __ldg(reinterpret_cast<const float4*>(
+                          Ap + ((abase[i % NR] + (long long)hs * g.Ws + ws) * g.Cs + c)))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else if (fast) {
         int hs, ws;
-        const bool ok = rok && source_pixel(i, kh_, kw_, hs, ws);
-        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(
-                        Ap + ((abase[i] + (long long)hs * g.Ws + ws) * g.Cs + c)))
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = source_pixel(0, kh, kw, hs, ws);
+        const float* rowp = Ap + ((abase[0] + (long long)hs * g.Ws + ws) * g.Cs + cb + a_c0 * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(rowp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = kc * TC_BK + (a_c0 + j) * 4;
+          const int tap = r / g.Cs;
+          const int c = r - tap * g.Cs;
+          const int kh_ = tap / g.KW, kw_ = tap - kh_ * g.KW;
+          int hs, ws;
+          const bool ok = r < g.Kd && source_pixel(0, kh_, kw_, hs, ws);
+          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(
+                          Ap + ((abase[0] + (long long)hs * g.Ws + ws) * g.Cs + c)))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     // advance to the next (tile, seg, kc); returns false when this CTA is done
@@ -365,16 +391,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       return true;
     };
 
+    // Software pipeline, TWO iterations deep in registers: the producers are bound by global-load latency
+    // (ncu: long-scoreboard stalls dominate), one stage of lookahead is shorter than an L2 miss.
+    auto wblock = [&]() { return Wimg + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK); };
     int stage = 0;
     uint32_t phase = 0;
-    bool have = tile < ntiles;
-    float4 cur[4], nxt[4];
-    if (have) { enter_tile(); issue(cur); }
-    while (have) {
-      // weight block of the current iteration (captured before the state advances)
-      const float* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * TC_BK);
-      const bool have_next = advance();
-      if (have_next) issue(nxt);  // prefetch: next stage's loads are in flight while we store
+    float4 q0[4], q1[4], q2[4];
+    const float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+    bool h0 = tile < ntiles, h1 = false, h2 = false;
+    if (h0) {
+      enter_tile();
+      w0 = wblock(); issue(q0);
+      h1 = advance();
+      if (h1) { w1 = wblock(); issue(q1); }
+    }
+    while (h0) {
+      h2 = h1 ? advance() : false;
+      if (h2) { w2 = wblock(); issue(q2); }
       mbar_wait(S.empty(stage), phase ^ 1);
       const uint32_t sA = S.stageA(stage);
       if (pt == 0) {
@@ -385,14 +418,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                 S.stageB(stage)),
-            "l"(wsrc), "r"(bytes), "r"(S.full(stage))
+            "l"(w0), "r"(bytes), "r"(S.full(stage))
             : "memory");
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 hi, lo;
-        split_tf32(cur[i], hi, lo);
-        const uint32_t o = a_off + (uint32_t)(i * 4096);  // row + 32 i: four 8-row groups further
+        split_tf32(q0[i], hi, lo);
+        const uint32_t o = COAL ? a_off + (uint32_t)(i * 4096)
+                                : a_off + (uint32_t)(((a_c0 + i) ^ (a_row & 7)) << 4);
         sts128(sA + o, hi);
         sts128(sA + Cfg::A_BYTES + o, lo);
       }
@@ -400,8 +434,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       mbar_arrive(S.full(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-      have = have_next;
+      for (int i = 0; i < 4; ++i) { q0[i] = q1[i]; q1[i] = q2[i]; }
+      w0 = w1; w1 = w2; h0 = h1; h1 = h2;
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
@@ -984,9 +1018,13 @@ static int tc_sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
     sm_count = prop.major == 10 ? prop.multiProcessorCount : 0;  // tcgen05 needs sm_100
     if (sm_count > 0) {
-      bool ok = cudaFuncSetAttribute(gather_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      bool ok = cudaFuncSetAttribute(gather_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TcCfg<128>::SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<128>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<64>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<128>::SMEM_BYTES) == cudaSuccess;
@@ -1014,16 +1052,20 @@ static inline int tc_pack_image(const float* src, long long src_slot, float* dst
 }
 
 // returns 0 on success, >0 on a CUDA error, <0 if the problem should use the SIMT path
-static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st) {
+static inline int tc_launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t st, bool coal) {
   const int sms = tc_sm_count();
   if (sms <= 0 || a.W_img == nullptr) return -1;
   const Geom& g = a.g;
   if (tc_bn(g.Nd) == 128) {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
-    gather_gemm_tc<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    int grid = ntiles < sms ? ntiles : sms;
+    if (coal) gather_gemm_tc<128, true><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    else gather_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
   } else {
     int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
-    gather_gemm_tc<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    int grid = ntiles < sms ? ntiles : sms;
+    if (coal) gather_gemm_tc<64, true><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    else gather_gemm_tc<64, false><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -1053,7 +1095,7 @@ static inline bool tc_gather_eligible(const Geom&, int) { return false; }
 static inline bool tc_wgrad_eligible(const Geom&, int) { return false; }
 static inline long long tc_image_elems(int, int, int) { return 0; }
 static inline int tc_pack_image(const float*, long long, float*, long long, int, int, int, int, cudaStream_t) { return -1; }
-static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t) { return -1; }
+static inline int tc_launch_gather_gemm(const GatherGemmArgs&, int, cudaStream_t, bool) { return -1; }
 static inline int tc_launch_wgrad(const WgradArgs&, cudaStream_t) { return -1; }
 #endif
 
