@@ -65,8 +65,11 @@ def _pair(x):
     return (int(x[0]), int(x[1])) if len(x) == 2 else (int(x[0]), int(x[0]))
 
 
-def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
+def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = True) -> LayerProgram:
     """Trace ``model_func(params, X)`` and lower it to a :class:`LayerProgram`.
+
+    ``fuse_relu``: a ReLU whose only producer is a BatchNorm or a residual add (and which is that value's only
+    consumer) is folded into the producing node (``kh = 2``): one streaming pass instead of two.
 
     ``params`` are the *differentiated* tensors (the operator's ``params`` dict, in order); every other
     tensor the function touches becomes a constant, exactly like ``functional_call`` falls back to the
@@ -87,6 +90,7 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
 
     prog = LayerProgram()
     env: dict = {}
+    producer: dict = {}  # value id -> index of the node that writes it
     placeholders = [n for n in gm.graph.nodes if n.op == "placeholder"]
     if len(placeholders) != len(names) + 1:
         raise NotImplementedError("Unexpected trace signature (non-tensor leaves in params?).")
@@ -170,6 +174,8 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
         if node.op == "get_attr":
             env[node] = _Ref("const", tensor=getattr(gm, node.target))
             continue
+        for ni_, nd_ in enumerate(prog.nodes[len(producer):], start=len(producer)):
+            producer[nd_["out"]] = ni_
         t = node.target
         a = [env.get(x, x) if isinstance(x, torch.fx.Node) else x for x in node.args]
         if t in (aten.detach.default, aten.alias.default, aten.clone.default, aten.contiguous.default):
@@ -230,6 +236,13 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor) -> LayerProgram:
             env[node] = src.items[idx]
         elif t in (aten.relu.default, aten.sigmoid.default, aten.tanh.default):
             xr = a[0]
+            src = node.args[0]
+            prod = producer.get(xr.value) if xr.kind == "act" else None
+            if (fuse_relu and t == aten.relu.default and prod is not None and len(src.users) == 1
+                    and prog.nodes[prod]["op"] in (capi.OP_AFFINE, capi.OP_ADD) and prog.nodes[prod]["kh"] != 2):
+                prog.nodes[prod]["kh"] = 2  # fused: the producing node now writes relu(...)
+                env[node] = _Ref("act", value=xr.value, flat=xr.flat)
+                continue
             op = {aten.relu.default: capi.OP_RELU, aten.sigmoid.default: capi.OP_SIGMOID,
                   aten.tanh.default: capi.OP_TANH}[t]
             C, H, W, tan = shape_of(xr)

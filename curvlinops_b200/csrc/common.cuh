@@ -43,6 +43,7 @@ struct GatherGemmArgs {
   long long out_slot;
   int slot0;  // first slot computed; gridDim.y = number of slots
   int accumulate;
+  int debug;  // perf experiments only: 1 = producers skip the global loads, 2 = skip split + smem stores
 };
 
 // wgrad:  D_k[n][tap][c] = sum_m G_k[m][n] * In_0[src(m,tap)][c]   (+ G_0 * In_k in R-op mode)

@@ -133,7 +133,8 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
 // y_0 = s*x_0 + t ;  y_k = s*x_k + sdot_k*x_0 + tdot_k     grid.y = slot
 __global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
                                   const float* __restrict__ coef, int coef_has_tan,
-                                  float* __restrict__ y, long long y_slot, long long rows, int Cp) {
+                                  float* __restrict__ y, long long y_slot, long long rows, int Cp,
+                                  int relu) {
   const int slot = blockIdx.y;
   const int C4 = Cp >> 2;
   const long long total = rows * C4;
@@ -150,10 +151,16 @@ __global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot,
     float4 r;
     if (slot == 0) {
       r = f4fma(__ldg(s4 + c4), __ldg(x0 + i), __ldg(t4 + c4));
+      if (relu) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
     } else {
       r = f4zero();
       if (x_has_slots) r = f4mul(__ldg(s4 + c4), __ldg(xk + i));
       if (coef_has_tan) r = f4add(r, f4fma(__ldg(sd4 + c4), __ldg(x0 + i), __ldg(td4 + c4)));
+      if (relu) {  // fused ReLU: mask with the sign of the primal pre-activation (recomputed, not re-read)
+        const float4 pre = f4fma(__ldg(s4 + c4), __ldg(x0 + i), __ldg(t4 + c4));
+        r = make_float4(pre.x > 0.f ? r.x : 0.f, pre.y > 0.f ? r.y : 0.f, pre.z > 0.f ? r.z : 0.f,
+                        pre.w > 0.f ? r.w : 0.f);
+      }
     }
     yo[i] = r;
   }
@@ -237,6 +244,51 @@ __global__ void axpy_slots_kernel(const float* __restrict__ src, long long src_s
     v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
     if (accumulate) v = f4add(v, d[i]);
     d[i] = v;
+  }
+}
+
+// fused residual join + ReLU:  y_0 = relu(a_0 + b_0),  y_k = [a_0 + b_0 > 0] (a_k + b_k).  grid.y = slot
+__global__ void add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot, int a_has_slots,
+                                    const float* __restrict__ b, long long b_slot, int b_has_slots,
+                                    float* __restrict__ y, long long y_slot, long long n4) {
+  const int slot = blockIdx.y;
+  const float4* a0 = reinterpret_cast<const float4*>(a);
+  const float4* b0 = reinterpret_cast<const float4*>(b);
+  const float4* ak = reinterpret_cast<const float4*>(a + slot * a_slot);
+  const float4* bk = reinterpret_cast<const float4*>(b + slot * b_slot);
+  float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 p = f4add(__ldg(a0 + i), __ldg(b0 + i));
+    float4 r;
+    if (slot == 0) {
+      r = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(p.z, 0.f), fmaxf(p.w, 0.f));
+    } else {
+      r = f4zero();
+      if (a_has_slots) r = __ldg(ak + i);
+      if (b_has_slots) r = f4add(r, __ldg(bk + i));
+      r = make_float4(p.x > 0.f ? r.x : 0.f, p.y > 0.f ? r.y : 0.f, p.z > 0.f ? r.z : 0.f, p.w > 0.f ? r.w : 0.f);
+    }
+    yo[i] = r;
+  }
+}
+// adjoint: g = [y_0 > 0] gy_k ;  ga_k (+)= g ;  gb_k (+)= g   (either destination may be null)
+__global__ void add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                    const float* __restrict__ y0, float* __restrict__ ga, long long ga_slot,
+                                    int acc_a, float* __restrict__ gb, long long gb_slot, int acc_b,
+                                    long long n4, int slot0) {
+  const int slot = slot0 + blockIdx.y;
+  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+  const float4* p4 = reinterpret_cast<const float4*>(y0);
+  float4* oa = ga ? reinterpret_cast<float4*>(ga + slot * ga_slot) : nullptr;
+  float4* ob = gb ? reinterpret_cast<float4*>(gb + slot * gb_slot) : nullptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g + i), p = __ldg(p4 + i);
+    const float4 r = make_float4(p.x > 0.f ? v.x : 0.f, p.y > 0.f ? v.y : 0.f, p.z > 0.f ? v.z : 0.f,
+                                 p.w > 0.f ? v.w : 0.f);
+    if (oa) oa[i] = acc_a ? f4add(r, oa[i]) : r;
+    if (ob) ob[i] = acc_b ? f4add(r, ob[i]) : r;
   }
 }
 
@@ -382,7 +434,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
     const float* __restrict__ xdot, long long xdot_slot, const float* __restrict__ coef,
     const float* __restrict__ aux, float* __restrict__ gx, long long gx_slot, int write_gx,
     float* __restrict__ partial, int want_partial, long long rows, int Cp, int rows_per_cta,
-    int slot0, int nslots, int rop, int accumulate) {
+    int slot0, int nslots, int rop, int accumulate, int relu) {
   extern __shared__ float red[];  // [RPP][2][ctile*4]
   const int C4 = Cp >> 2;
   const int ctile4 = min(C4, 256);
@@ -402,9 +454,10 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
   for (int cbase = 0; cbase < C4; cbase += ctile4) {
     const int c4 = cbase + cl;
     const bool cok = active && c4 < C4;
-    float4 s = f4zero(), sd = f4zero(), istd = f4zero(), mu = f4zero();
+    float4 s = f4zero(), sd = f4zero(), istd = f4zero(), mu = f4zero(), tt = f4zero();
     if (cok && coef) {
       s = __ldg(reinterpret_cast<const float4*>(coef) + c4);
+      tt = __ldg(reinterpret_cast<const float4*>(coef + Cp) + c4);
       istd = __ldg(reinterpret_cast<const float4*>(aux) + c4);
       mu = __ldg(reinterpret_cast<const float4*>(aux + Cp) + c4);
       if (rop && slot > 0) sd = __ldg(reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp) + c4);
@@ -414,6 +467,11 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
       for (long long r = r0 + rl; r < r1; r += RPP) {
         long long i = r * C4 + c4;
         float4 v = __ldg(g + i);
+        if (relu && coef) {  // fused ReLU adjoint: cotangent passes where the primal pre-activation is > 0
+          const float4 pre = f4fma(s, __ldg(xp + i), tt);
+          v = make_float4(pre.x > 0.f ? v.x : 0.f, pre.y > 0.f ? v.y : 0.f, pre.z > 0.f ? v.z : 0.f,
+                          pre.w > 0.f ? v.w : 0.f);
+        }
         a1 = f4add(a1, v);
         if (coef) {
           float4 xv = __ldg(xp + i);

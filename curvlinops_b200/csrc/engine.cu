@@ -110,7 +110,7 @@ extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 7;
+  g_tc_disable = (mode >> 4) & 31;
   return old;
 }
 
@@ -228,6 +228,9 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
     } else if (d.op == CURV_OP_ADD) {
       if (bad_id(d.in1)) { delete P; return fail(CURV_ERR_INVALID, "add node needs two inputs"); }
     }
+    if ((d.op == CURV_OP_ADD || d.op == CURV_OP_AFFINE) && d.kh == 2 && (hessian & 1)) {
+      delete P; return fail(CURV_ERR_INVALID, "fused ReLU nodes are not supported by the Hessian R-op program");
+    }
     P->nodes.push_back(n);
   }
   {
@@ -304,7 +307,9 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   const Geom& g = a.g;
   ProfScope prof(0, flops, st);
   if (g_tc_mode && a.W_img != nullptr) {
-    int rc = tc_launch_gather_gemm(a, nslots, st, (g_tc_disable & 4) != 0);
+    GatherGemmArgs a2 = a;
+    a2.debug = (g_tc_disable >> 3) & 3;
+    int rc = tc_launch_gather_gemm(a2, nslots, st, (g_tc_disable & 4) != 0);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
     // rc < 0: not eligible after all -> SIMT
@@ -487,7 +492,7 @@ static int forward(const Ctx& c, const void* X, int K) {
         long long rows = (long long)P->B * vi.H * vi.W;
         affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
-            c.act(d.out), vo.slot_elems, rows, vi.Cp);
+            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0);
         LAUNCH_CHECK();
         break;
       }
@@ -509,6 +514,13 @@ static int forward(const Ctx& c, const void* X, int K) {
       case CURV_OP_ADD: {
         const Value& vj = P->values[d.in1];
         long long n4 = vo.slot_elems / 4;
+        if (d.kh == 2) {  // fused residual join + ReLU
+          add_relu_fwd_kernel<<<dim3(grid1d(n4), nsl), 256, 0, st>>>(
+              c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.act(d.in1), vj.slot_elems, vj.tan ? 1 : 0,
+              c.act(d.out), vo.slot_elems, n4);
+          LAUNCH_CHECK();
+          break;
+        }
         // primal
         axpy_slots_kernel<<<dim3(grid1d(n4), 1), 256, 0, st>>>(c.act(d.in0), vi.slot_elems, c.act(d.out),
                                                                vo.slot_elems, n4, 0, 1.f, 0);
@@ -612,7 +624,7 @@ static int backward(const Ctx& c, int K) {
           long long rows = g.M;
           affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
               c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
-              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0);
+              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0);
           LAUNCH_CHECK();
           vec_grad_finish_kernel<<<ceil_div(vo.C * K, 256), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 1, vo.C, vo.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
@@ -646,7 +658,7 @@ static int backward(const Ctx& c, int K) {
             c.grad(d.out), vo.slot_elems, c.act(d.in0), (rop && vi.tan) ? c.act(d.in0) : nullptr,
             vi.slot_elems, c.ws + n.coef_off, c.ws + n.aux_off, vi.tan ? c.grad(d.in0) : nullptr,
             vi.slot_elems, vi.tan ? 1 : 0, scratch, want_partial, rows, vi.Cp, n.rows_per_cta, s0, ns,
-            rop ? 1 : 0, ginit[d.in0]);
+            rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0);
         LAUNCH_CHECK();
         if (vi.tan) ginit[d.in0] = 1;
         if (d.p0 >= 0) {
@@ -679,6 +691,15 @@ static int backward(const Ctx& c, int K) {
       case CURV_OP_ADD: {
         const Value& vj = P->values[d.in1];
         long long n4 = vo.slot_elems / 4;
+        if (d.kh == 2) {  // fused residual join + ReLU
+          add_relu_bwd_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(
+              c.grad(d.out), vo.slot_elems, c.act(d.out), vi.tan ? c.grad(d.in0) : nullptr, vi.slot_elems,
+              ginit[d.in0], vj.tan ? c.grad(d.in1) : nullptr, vj.slot_elems, ginit[d.in1], n4, s0);
+          LAUNCH_CHECK();
+          if (vi.tan) ginit[d.in0] = 1;
+          if (vj.tan) ginit[d.in1] = 1;
+          break;
+        }
         if (vi.tan) {
           axpy_slots_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(c.grad(d.out), vo.slot_elems, c.grad(d.in0),
                                                                   vi.slot_elems, n4, s0, 1.f, ginit[d.in0]);

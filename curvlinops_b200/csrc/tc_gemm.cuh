@@ -337,6 +337,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       return ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
     };
     auto issue = [&](float4 (&v)[4]) {
+      if (p.debug & 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        return;
+      }
       if (COAL) {
         int kh_ = kh, kw_ = kw, c = cb + a_c * 4;
         bool rok = true;
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        if (p.debug & 2) continue;
         float4 hi, lo;
         split_tf32(q0[i], hi, lo);
         const uint32_t o = COAL ? a_off + (uint32_t)(i * 4096)

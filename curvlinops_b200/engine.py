@@ -49,7 +49,7 @@ class CompiledProgram:
     """A layer program planned for one (input shape, kmax, hessian) combination."""
 
     def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool):
-        self.lp: LayerProgram = capture(model_func, params, X)
+        self.lp: LayerProgram = capture(model_func, params, X, fuse_relu=not (int(hessian) & 1))
         self.kmax = kmax
         self.batch = X.shape[0]
         self.device = X.device

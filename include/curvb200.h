@@ -95,7 +95,8 @@ typedef struct curv_node_desc {
      differentiated (-1 = absent).  CONV: c0 = weight, c1 = bias (when not in params).
      AFFINE: c0 = gamma, c1 = beta (when not in params), c2 = running_mean, c3 = running_var.     */
   int c0, c1, c2, c3;
-  int kh, kw, sh, sw, ph, pw; /* CONV / MAXPOOL geometry                                           */
+  int kh, kw, sh, sw, ph, pw; /* CONV / MAXPOOL geometry.  AFFINE / ADD: kh == 2 fuses a following ReLU
+                                 (out = relu(...)); not allowed in programs created with hessian=1     */
   float eps;                  /* AFFINE                                                            */
 } curv_node_desc;
 
