@@ -7,6 +7,7 @@ behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
 """
 
 from .curvature import CurvatureLinearOperator, GGNLinearOperator, HessianLinearOperator
+from .jacobian import JacobianLinearOperator, TransposedJacobianLinearOperator
 from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
 from .linop import PyTorchLinearOperator
 from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
@@ -18,6 +19,8 @@ __all__ = [
     "CurvatureLinearOperator",
     "GGNLinearOperator",
     "HessianLinearOperator",
+    "JacobianLinearOperator",
+    "TransposedJacobianLinearOperator",
     "KFACLinearOperator",
     "EKFACLinearOperator",
     "FisherType",

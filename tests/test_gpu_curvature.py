@@ -170,3 +170,33 @@ def test_tcgen05_vs_simt_on_wide_convnet():
         capi.lib().curv_set_tensor_core_mode(old)
     err = (got - ref).abs().max() / ref.abs().max()
     assert err < 2e-5, err
+
+
+def test_jacobian_operators_match_oracle():
+    """J and J^T (reference curvlinops/jacobian.py) against the oracle's double-vjp / vjp restatement."""
+    from curvlinops_b200 import JacobianLinearOperator, TransposedJacobianLinearOperator
+
+    model, loss, data, fx, params = _setup("miniresnet_ce_mean")
+    cpu_model, _, cpu_data, _ = load_case("miniresnet_ce_mean")
+    p64 = dict(cpu_model.named_parameters())
+    J = JacobianLinearOperator(model, params, data, check_deterministic=False)
+    N = sum(X.shape[0] for X, _ in data)
+    assert J.shape == (N * 10, sum(p.numel() for p in params.values()))
+    V = fx["V"][:, :2]
+    got = J @ V.float().cuda()
+    f_fn = orc._as_callable(cpu_model)
+    ref = torch.cat([torch.stack([orc.jacobian_vector_product(f_fn, p64, X, [v[..., k] for v in split_like(V, p64)])[1]
+                                  for k in range(2)], dim=-1) for X, _ in cpu_data]).reshape(-1, 2)
+    assert_parity(got, ref)
+    JT = J.adjoint()
+    assert isinstance(JT, TransposedJacobianLinearOperator)
+    torch.manual_seed(0)
+    W = torch.rand(N * 10, 2, dtype=torch.float64)
+    refT = torch.zeros(J.shape[1], 2, dtype=torch.float64)
+    pos = 0
+    for X, _ in cpu_data:
+        for k in range(2):
+            w = W[pos * 10:(pos + X.shape[0]) * 10, k].reshape(X.shape[0], 10)
+            refT[:, k] += torch.cat([g.flatten() for g in orc.transposed_jacobian_vector_product(f_fn, p64, X, w)])
+        pos += X.shape[0]
+    assert_parity(JT @ W.float().cuda(), refT, params)
