@@ -23,7 +23,7 @@ static thread_local std::string g_err;
 static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
 static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
-                                // 4 = gather GEMM with the 8-lanes-per-row (coalesced) producer mapping
+                                // 4 = gather GEMM with the old two-threads-per-row producer mapping
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -309,7 +309,7 @@ static int launch_gather_gemm(const GatherGemmArgs& a, int nslots, cudaStream_t 
   if (g_tc_mode && a.W_img != nullptr) {
     GatherGemmArgs a2 = a;
     a2.debug = (g_tc_disable >> 3) & 3;
-    int rc = tc_launch_gather_gemm(a2, nslots, st, (g_tc_disable & 4) != 0);
+    int rc = tc_launch_gather_gemm(a2, nslots, st, (g_tc_disable & 4) == 0);
     if (rc == 0) { ++g_launches; return CURV_OK; }
     if (rc > 0) return fail(CURV_ERR_CUDA, "tcgen05 gather GEMM launch failed");
     // rc < 0: not eligible after all -> SIMT

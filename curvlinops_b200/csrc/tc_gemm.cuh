@@ -288,23 +288,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
   if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 5 * 32;  // 0..255
-    // Two thread -> data mappings (template COAL):
+    // Thread -> data mapping (template COAL):
     //  COAL: 8 consecutive lanes read the 8 16-byte chunks of ONE 128-byte K row (a warp request = 4 rows =
-    //        4 cache lines); thread -> chunk a_c of rows a_r0 + 32 i, i = 0..3.
-    //  !COAL: two threads per row, 4 consecutive chunks (64 B) each; fewer address computations per thread,
-    //        but 31.5 sectors per warp request (ncu).
+    //        4 cache lines instead of 32 sectors in 16-32 lines); thread -> chunk a_c of rows a_r0 + 32 i.
+    //        Addresses are LINEAR in (row, tap): element offset = rowoff_i + tapoff with
+    //        rowoff_i = ((b*Hs + ah_i)*Ws + aw_i)*Cs fixed per tile and tapoff = +-(kh*Ws + kw)*Cs + c per
+    //        stage (uniform over rows), so a load costs one add and a bounds test on the packed (ah, aw).
+    //        Strided dgrad ((dest + pad - tap)/stride) is not linear and takes the generic path.
+    //  !COAL: two threads per row, 4 consecutive chunks (64 B) each (kept for A/B measurements).
     constexpr int NR = COAL ? 4 : 1;               // rows per thread
     const int a_c = pt & 7, a_r0 = pt >> 3;         // COAL
     const int a_row = pt >> 1, a_c0 = (pt & 1) * 4; // !COAL
     const uint32_t a_off = COAL ? (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4))
                                 : (uint32_t)((a_row >> 3) * 1024 + (a_row & 7) * 128);
     const bool fast = (g.Cs % TC_BK) == 0;  // a 128-byte K row never straddles two filter taps
+    const bool linear = g.mode == 0 || (g.sh == 1 && g.sw == 1);
     // iteration state
     int tile = blockIdx.x, slot = 0, m0 = 0, tn = 0, nseg = 0, seg = 0, kc = 0;
     int kh = 0, kw = 0, cb = 0;
     bool m_ok[NR];
     int ah[NR], aw[NR];
-    long long abase[NR];
+    int rowoff[NR];  // element offset of (b, ah, aw, channel 0) inside the slot (fits 32 bits: checked on the host)
     const float* Ap = nullptr;
     const float* Wimg = nullptr;
     auto enter_tile = [&]() {
@@ -320,11 +324,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
         ah[i] = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
         aw[i] = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
-        abase[i] = (long long)bimg * g.Hs * g.Ws;
+        rowoff[i] = linear ? ((bimg * g.Hs + ah[i]) * g.Ws + aw[i]) * g.Cs : bimg * g.Hs * g.Ws;
+        if (!m_ok[i]) ah[i] = -(1 << 20);  // fails every bounds test
       }
       seg = 0; kc = 0; kh = 0; kw = 0; cb = 0;
       segment(slot, 0, Ap, Wimg);
     };
+    // generic (non-linear) source pixel of row i for tap (kh_, kw_)
     auto source_pixel = [&](int i, int kh_, int kw_, int& hs, int& ws) -> bool {
       bool ok = m_ok[i];
       if (g.mode == 0) { hs = ah[i] + kh_; ws = aw[i] + kw_; }
@@ -352,22 +358,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
           kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
           rok = r < g.Kd;
         }
+        if (linear) {
+          const int sgn = g.mode == 0 ? 1 : -1;
+          const int tapoff = sgn * (kh_ * g.Ws + kw_) * g.Cs + c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int hs, ws;
-          const bool ok = rok && source_pixel(i % NR, kh_, kw_, hs, ws);
-          v[i] = ok ? __ldg(reinterpret_cast<const float4*>(
-                          Ap + ((abase[i % NR] + (long long)hs * g.Ws + ws) * g.Cs + c)))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) {
+            const int hs = ah[i % NR] + sgn * kh_, ws = aw[i % NR] + sgn * kw_;
+            const bool ok = rok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
+            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(Ap + (rowoff[i % NR] + tapoff)))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int hs, ws;
+            const bool ok = rok && source_pixel(i % NR, kh_, kw_, hs, ws);
+            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(
+                            Ap + ((long long)(rowoff[i % NR] + hs * g.Ws + ws) * g.Cs + c)))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       } else if (fast) {
         int hs, ws;
         const bool ok = source_pixel(0, kh, kw, hs, ws);
-        const float* rowp = Ap + ((abase[0] + (long long)hs * g.Ws + ws) * g.Cs + cb + a_c0 * 4);
+        const long long pix = linear ? (long long)(rowoff[0] / g.Cs) - (long long)(ah[0] * g.Ws + aw[0]) : rowoff[0];
+        const float* rowp = Ap + ((pix + (long long)hs * g.Ws + ws) * g.Cs + cb + a_c0 * 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           v[j] = ok ? __ldg(reinterpret_cast<const float4*>(rowp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
+        const long long pix = linear ? (long long)(rowoff[0] / g.Cs) - (long long)(ah[0] * g.Ws + aw[0]) : rowoff[0];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = kc * TC_BK + (a_c0 + j) * 4;
@@ -376,8 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
           const int kh_ = tap / g.KW, kw_ = tap - kh_ * g.KW;
           int hs, ws;
           const bool ok = r < g.Kd && source_pixel(0, kh_, kw_, hs, ws);
-          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(
-                          Ap + ((abase[0] + (long long)hs * g.Ws + ws) * g.Cs + c)))
+          v[j] = ok ? __ldg(reinterpret_cast<const float4*>(Ap + ((pix + (long long)hs * g.Ws + ws) * g.Cs + c)))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -1002,6 +1021,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc_ms(const WgradArg
 static inline int tc_bn(int width) { return width > 64 ? 128 : 64; }
 
 static inline bool tc_gather_eligible(const Geom& g, int mode) {
+  if ((long long)g.B * g.Hs * g.Ws * g.Cs >= (1LL << 31) - (1LL << 24)) return false;  // 32-bit row offsets
   if (mode >= 2) return true;  // forced (tests): every shape is legal, small ones just waste tiles
   // big enough to fill 128-row tiles; everything else stays on the SIMT kernels
   return g.M >= 1024 && g.Kd >= 32 && g.Nd >= 16;
