@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
+#include "hs_gemm.cuh"
 
 using namespace curv;
 
@@ -23,7 +25,9 @@ static thread_local std::string g_err;
 static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
 static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
-                                // 4 = gather GEMM with the old two-threads-per-row producer mapping
+                                // 4 = gather GEMM with the old two-threads-per-row producer mapping,
+                                // 8, 16 = producer experiments, 32 = no half-split (fp16 hi/lo) kernels:
+                                // everything eligible runs the 3xTF32 kernels instead
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -86,6 +90,11 @@ struct curv_program {
   std::vector<Node> nodes;
   std::vector<curv_param_desc> params;
   long long scratch_off = 0, scratch_elems = 0;
+  // half-split path (hs_gemm.cuh): plane scratch R1 (all slots of one tensor), R2 (one primal slot), both in
+  // floats (hi + lo fp16 planes = 4 bytes per element), and the absmax bit patterns:
+  //   value v, act slot s  -> bits[(2 v) (1+kmax) + s],  grad slot s -> bits[(2 v + 1) (1+kmax) + s]
+  //   conv node i, weight 0 / tangent k -> bits[(2 nvalues + i) (1+kmax) + k]
+  long long hs1_off = 0, hs1_elems = 0, hs2_off = 0, hs2_elems = 0, hsbits_off = 0, hsbits_count = 0;
   size_t ws_bytes = 0;
 };
 
@@ -110,7 +119,7 @@ extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 31;
+  g_tc_disable = (mode >> 4) & 63;
   return old;
 }
 
@@ -241,6 +250,24 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
   }
   P->scratch_elems = scratch;
   P->scratch_off = alloc(scratch);
+  if (!(hessian & 1)) {  // half-split planes for the GGN / JVP / VJP sweeps
+    for (const Node& n : P->nodes) {
+      if (n.d.op != CURV_OP_CONV) continue;
+      const Value& vi = P->values[n.d.in0];
+      const Value& vo = P->values[n.d.out];
+      if (!hs_gather_shape_ok(n.fwd)) continue;
+      const long long fwd_need = vi.slot_elems * vi.nslots;
+      const long long bwd_need = (vo.Cp % 8 == 0) ? vo.slot_elems * kmax : 0;
+      P->hs1_elems = std::max(P->hs1_elems, std::max(fwd_need, bwd_need));
+      P->hs2_elems = std::max(P->hs2_elems, vi.slot_elems);
+    }
+    if (P->hs1_elems > 0) {
+      P->hs1_off = alloc(P->hs1_elems);
+      P->hs2_off = alloc(P->hs2_elems);
+      P->hsbits_count = (long long)(2 * n_values + n_nodes) * (1 + kmax);
+      P->hsbits_off = alloc(P->hsbits_count);
+    }
+  }
   P->ws_bytes = (size_t)off * sizeof(float);
   *out = P;
   return CURV_OK;
@@ -293,7 +320,20 @@ extern "C" int curv_profile_read(double* ms, double* flops, long long* count) {
     if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(CURV_ERR_CUDA, "profile event sync failed");
     float t = 0.f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (r.cls > 1) continue;
     ms[r.cls] += t; flops[r.cls] += r.flops; count[r.cls] += 1;
+  }
+  return CURV_OK;
+}
+// same for one class: 0 gather GEMM, 1 wgrad GEMM, 2 half-split absmax/split passes
+extern "C" int curv_profile_read_class(int cls, double* ms, double* flops, long long* count) {
+  *ms = 0; *flops = 0; *count = 0;
+  for (auto& r : g_prof) {
+    if (r.cls != cls) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(CURV_ERR_CUDA, "profile event sync failed");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    *ms += t; *flops += r.flops; *count += 1;
   }
   return CURV_OK;
 }
@@ -359,6 +399,17 @@ struct Ctx {
   bool rop;  // Hessian R-op: slot 0 of the cotangent storage holds the plain backward
   float** kfac_G = nullptr;  // KFAC mode: per node, the G factor to accumulate into (or null); no param grads
   float kfac_wG = 0.f;
+  // half-split path: enabled per call; hs_valid[e] = absmax entry e already computed in this call
+  bool hs = false;
+  std::vector<char>* hs_valid = nullptr;
+  uint32_t* hsbits() const { return reinterpret_cast<uint32_t*>(ws + P->hsbits_off); }
+  int bits_act(int v) const { return (2 * v) * (1 + P->kmax); }
+  int bits_grad(int v) const { return (2 * v + 1) * (1 + P->kmax); }
+  int bits_node(int ni) const { return (2 * (int)P->values.size() + ni) * (1 + P->kmax); }
+  __half* hs1_hi() const { return reinterpret_cast<__half*>(ws + P->hs1_off); }
+  __half* hs1_lo() const { return reinterpret_cast<__half*>(ws + P->hs1_off) + P->hs1_elems; }
+  __half* hs2_hi() const { return reinterpret_cast<__half*>(ws + P->hs2_off); }
+  __half* hs2_lo() const { return reinterpret_cast<__half*>(ws + P->hs2_off) + P->hs2_elems; }
   float* act(int v, int slot = 0) const {
     const Value& x = P->values[v];
     return ws + x.act_off + (long long)slot * x.slot_elems;
@@ -372,6 +423,39 @@ struct Ctx {
   const float* vcol(int p) const { return V + P->params[p].offset * ldk + k0; }
   float* ocol(int p) const { return out + P->params[p].offset * ldk + k0; }
 };
+
+// ---- half-split path: which contractions of a conv node run on the fp16 hi/lo kernels (hs_gemm.cuh)
+static bool hs_fwd_ok(const Ctx& c, const Node& n) {
+  return c.hs && n.wimg_off >= 0 && hs_gather_shape_ok(n.fwd) && tc_gather_eligible(n.fwd, g_tc_mode);
+}
+static bool hs_dgr_ok(const Ctx& c, const Node& n) {
+  return c.hs && n.wtimg_off >= 0 && hs_gather_shape_ok(n.dgr) && tc_gather_eligible(n.dgr, g_tc_mode);
+}
+static bool hs_wgr_ok(const Ctx& c, const Node& n, int ns) {
+  const Value& vo = c.P->values[n.d.out];
+  return c.hs && !(g_tc_disable & 2) && ns >= 1 && ns <= 8 && hs_wgrad_shape_ok(n.fwd, vo.Cp) &&
+         tc_wgrad_eligible(n.fwd, g_tc_mode);
+}
+// absmax of `count` slots (x = first of them) into bits entries [entry, entry + count), once per call
+static int hs_absmax(const Ctx& c, const float* x, long long slot_stride, long long n, int entry, int count) {
+  bool need = false;
+  for (int i = 0; i < count; ++i) need = need || !(*c.hs_valid)[entry + i];
+  if (!need) return CURV_OK;
+  ProfScope prof(2, 0, c.st);
+  if (hs_launch_absmax(x, slot_stride, n, c.hsbits() + entry, count, c.st))
+    return fail(CURV_ERR_CUDA, "half-split absmax launch failed");
+  ++g_launches;
+  for (int i = 0; i < count; ++i) (*c.hs_valid)[entry + i] = 1;
+  return CURV_OK;
+}
+static int hs_split(const Ctx& c, const float* x, long long slot_stride, long long n, __half* hi, __half* lo,
+                    int entry, int count) {
+  ProfScope prof(2, 0, c.st);
+  if (hs_launch_split(x, slot_stride, n, hi, lo, n, c.hsbits() + entry, count, c.st))
+    return fail(CURV_ERR_CUDA, "half-split split launch failed");
+  ++g_launches;
+  return CURV_OK;
+}
 
 // pack parameters (and, if with_tangents, the K columns of V) into the engine's layouts
 static int prepare_params(const Ctx& c, bool with_tangents) {
@@ -402,10 +486,38 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
           LAUNCH_CHECK();
         }
       }
-      if (g_tc_mode && n.wimg_off >= 0) {  // tcgen05 weight images
+      const int ni = (int)(&n - P->nodes.data());
+      const bool hsf = hs_fwd_ok(c, n), hsd = vi.tan && hs_dgr_ok(c, n);
+      if (hsf || hsd) {  // fp16 hi/lo weight images (scale = one power of two per weight tensor / tangent)
+        const int e0 = c.bits_node(ni);
+        const bool wt = with_tangents && d.p0 >= 0;
+        int rc = hs_absmax(c, c.ws + n.wk_off, 0, n.wsize, e0, 1);
+        if (!rc && wt && hsf) rc = hs_absmax(c, c.ws + n.wkt_off, n.wsize, n.wsize, e0 + 1, c.K);
+        if (rc) return rc;
+        int bad = 0;
+        if (hsf) {
+          bad |= hs_launch_pack_image(c.ws + n.wk_off, 0, reinterpret_cast<__half*>(c.ws + n.wimg_off), 0, g.N,
+                                      g.Nd, g.Kd, 1, c.hsbits() + e0, st);
+          ++g_launches;
+          if (wt) {
+            bad |= hs_launch_pack_image(c.ws + n.wkt_off, n.wsize, reinterpret_cast<__half*>(c.ws + n.wimgt_off),
+                                        hs_image_halves(g.Nd, g.Kd), g.N, g.Nd, g.Kd, c.K, c.hsbits() + e0 + 1,
+                                        st);
+            ++g_launches;
+          }
+        }
+        if (hsd) {
+          const Geom& q = n.dgr;
+          bad |= hs_launch_pack_image(c.ws + n.wt_off, 0, reinterpret_cast<__half*>(c.ws + n.wtimg_off), 0, q.N,
+                                      q.Nd, q.Kd, 1, c.hsbits() + e0, st);
+          ++g_launches;
+        }
+        if (bad) return fail(CURV_ERR_CUDA, "half-split weight image packing failed");
+      }
+      if (g_tc_mode && n.wimg_off >= 0 && !(hsf && (hsd || !vi.tan))) {  // 3xTF32 tcgen05 weight images
         const Geom& q = n.dgr;
         int bad = 0;
-        if (tc_gather_eligible(g, g_tc_mode)) {
+        if (!hsf && tc_gather_eligible(g, g_tc_mode)) {
           bad |= tc_pack_image(c.ws + n.wk_off, 0, c.ws + n.wimg_off, 0, g.N, g.Nd, g.Kd, 1, st) > 0;
           ++g_launches;
           if (with_tangents && d.p0 >= 0) {
@@ -414,7 +526,7 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
             ++g_launches;
           }
         }
-        if (n.wtimg_off >= 0 && tc_gather_eligible(q, g_tc_mode)) {
+        if (!hsd && n.wtimg_off >= 0 && tc_gather_eligible(q, g_tc_mode)) {
           bad |= tc_pack_image(c.ws + n.wt_off, 0, c.ws + n.wtimg_off, 0, q.N, q.Nd, q.Kd, 1, st) > 0;
           ++g_launches;
           if (with_tangents && n.wtimgt_off >= 0) {
@@ -468,6 +580,31 @@ static int forward(const Ctx& c, const void* X, int K) {
     const int nsl = (vo.tan && K > 0) ? 1 + K : 1;
     switch (d.op) {
       case CURV_OP_CONV: {
+        double fl = conv_flops(n.fwd, vi.C) *
+                    (1 + (nsl - 1) * ((vi.tan ? 1 : 0) + (d.p0 >= 0 ? 1 : 0)));
+        if (hs_fwd_ok(c, n)) {  // fp16 hi/lo planes of the input slots, then the half-split gather GEMM
+          const int nin = (vi.tan && K > 0) ? 1 + K : 1;
+          const int ea = c.bits_act(d.in0);
+          int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, ea, nin);
+          if (!rc) rc = hs_split(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.hs1_hi(), c.hs1_lo(), ea, nin);
+          if (rc) return rc;
+          HsGatherArgs h;
+          memset(&h, 0, sizeof(h));
+          h.g = n.fwd;
+          h.Ah = c.hs1_hi(); h.Al = c.hs1_lo(); h.A_slot = vi.slot_elems; h.a_slot_base = 0;
+          h.a_has_slots = vi.tan ? 1 : 0; h.a_bits = c.hsbits() + ea;
+          h.W_img = reinterpret_cast<const __half*>(c.ws + n.wimg_off);
+          h.Wt_img = (d.p0 >= 0 && K > 0) ? reinterpret_cast<const __half*>(c.ws + n.wimgt_off) : nullptr;
+          h.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd);
+          h.w_bits = c.hsbits() + c.bits_node((int)(&n - P->nodes.data()));
+          h.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
+          h.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; h.bias_slot = vo.Cp;
+          h.out = c.act(d.out); h.out_slot = vo.slot_elems; h.slot0 = 0; h.accumulate = 0;
+          ProfScope prof(0, fl, st);
+          if (hs_launch_gather_gemm(h, nsl, st)) return fail(CURV_ERR_CUDA, "half-split gather GEMM launch failed");
+          ++g_launches;
+          break;
+        }
         GatherGemmArgs a;
         memset(&a, 0, sizeof(a));
         a.g = n.fwd;
@@ -482,8 +619,6 @@ static int forward(const Ctx& c, const void* X, int K) {
         a.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; a.bias_slot = vo.Cp;
         a.out = c.act(d.out); a.out_slot = vo.slot_elems;
         a.slot0 = 0; a.accumulate = 0;
-        double fl = conv_flops(n.fwd, vi.C) *
-                    (1 + (nsl - 1) * ((vi.tan ? 1 : 0) + (d.p0 >= 0 ? 1 : 0)));
         int rc = launch_gather_gemm(a, nsl, st, fl);
         if (rc) return rc;
         break;
@@ -604,7 +739,38 @@ static int backward(const Ctx& c, int K) {
                                      c.kfac_wG, scratch, P->scratch_elems, st);
             if (rc) return rc;
           }
-        } else if (d.p0 >= 0) {  // weight gradient
+        }
+        const int nidx = ni;
+        const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, ns);
+        const bool hs_d = vi.tan && hs_dgr_ok(c, n);
+        const int eg = c.bits_grad(d.out);
+        if (hs_w || hs_d) {  // fp16 hi/lo planes of the cotangent slots, shared by wgrad and dgrad
+          int rc = hs_absmax(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, eg + s0, ns);
+          if (!rc) rc = hs_split(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, c.hs1_hi(), c.hs1_lo(),
+                                 eg + s0, ns);
+          if (rc) return rc;
+        }
+        if (hs_w) {  // weight gradients of all slots on the half-split kernel
+          const int ea = c.bits_act(d.in0);
+          int rc = hs_absmax(c, c.act(d.in0), 0, vi.slot_elems, ea, 1);
+          if (!rc) rc = hs_split(c, c.act(d.in0), 0, vi.slot_elems, c.hs2_hi(), c.hs2_lo(), ea, 1);
+          if (rc) return rc;
+          HsWgradArgs h;
+          memset(&h, 0, sizeof(h));
+          h.g = g;
+          h.Gh = c.hs1_hi(); h.Gl = c.hs1_lo(); h.G_slot = vo.slot_elems; h.Ng = vo.Cp; h.g_bits = c.hsbits() + eg;
+          h.Ih = c.hs2_hi(); h.Il = c.hs2_lo(); h.i_bits = c.hsbits() + ea;
+          h.partial = scratch; h.nsplit = n.nsplit; h.nslots = ns; h.slot0 = s0; h.m_per_split = n.m_per_split;
+          {
+            ProfScope prof(1, conv_flops(g, vi.C) * ns, st);
+            if (hs_launch_wgrad(h, st)) return fail(CURV_ERR_CUDA, "half-split wgrad GEMM launch failed");
+            ++g_launches;
+          }
+          wgrad_finish_kernel<<<grid1d(n.wsize), 256, 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
+                                                              vi.Cp, g.KH * g.KW, c.out,
+                                                              P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
+          LAUNCH_CHECK();
+        } else if (c.kfac_G == nullptr && d.p0 >= 0) {  // weight gradient
           WgradArgs a;
           memset(&a, 0, sizeof(a));
           a.g = g;
@@ -631,7 +797,22 @@ static int backward(const Ctx& c, int K) {
               c.alpha);
           LAUNCH_CHECK();
         }
-        if (vi.tan) {  // data gradient
+        if (hs_d) {  // data gradient on the half-split kernel
+          HsGatherArgs h;
+          memset(&h, 0, sizeof(h));
+          h.g = n.dgr;
+          h.Ah = c.hs1_hi(); h.Al = c.hs1_lo(); h.A_slot = vo.slot_elems; h.a_slot_base = s0; h.a_has_slots = 1;
+          h.a_bits = c.hsbits() + eg;
+          h.W_img = reinterpret_cast<const __half*>(c.ws + n.wtimg_off);
+          h.w_bits = c.hsbits() + c.bits_node(nidx);
+          h.out = c.grad(d.in0); h.out_slot = vi.slot_elems; h.slot0 = s0; h.accumulate = ginit[d.in0];
+          {
+            ProfScope prof(0, conv_flops(g, vi.C) * ns, st);
+            if (hs_launch_gather_gemm(h, ns, st)) return fail(CURV_ERR_CUDA, "half-split dgrad GEMM launch failed");
+            ++g_launches;
+          }
+          ginit[d.in0] = 1;
+        } else if (vi.tan) {  // data gradient
           GatherGemmArgs a;
           memset(&a, 0, sizeof(a));
           a.g = n.dgr;
@@ -760,6 +941,13 @@ extern "C" int curv_matmat_batch(curv_program* P, int kind, int loss, const void
   c.P = P; c.ws = (float*)workspace; c.pp = param_ptrs; c.cp = const_ptrs; c.V = V; c.out = out;
   c.K = K; c.ldk = ldk; c.k0 = k0; c.alpha = alpha; c.st = (cudaStream_t)stream; c.kind = kind;
   c.rop = kind == CURV_KIND_HESSIAN;
+  std::vector<char> hs_valid;
+  if (g_tc_mode && !(g_tc_disable & 32) && !c.rop && P->hs1_elems > 0 && hs_ready() > 0) {
+    c.hs = true;
+    hs_valid.assign((size_t)P->hsbits_count, 0);
+    c.hs_valid = &hs_valid;
+    CHECK_CUDA(cudaMemsetAsync(c.hsbits(), 0, (size_t)P->hsbits_count * sizeof(uint32_t), c.st));
+  }
   const int last = P->nodes.back().d.out;
   const Value& vl = P->values[last];
   int rc;

@@ -1,0 +1,762 @@
+// "Half-split" tcgen05 path: fp32-grade contractions on the fp16 tensor pipe (kind::f16), sm_100a only.
+//
+// Every fp32 operand x of a contraction is stored as two fp16 planes of the power-of-two scaled value,
+//     s*x = hi + lo,   hi = rn_fp16(s*x),  lo = rn_fp16(s*x - hi)          (22 significant bits)
+// with one scale s = 2^sh per (tensor, slot), chosen from the slot's absolute maximum so that
+// max|s*x| lies in [2^14, 2^15).  The product is evaluated as
+//     a*b ~= (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) / (s_a*s_b)               (dropped lo*lo ~ 2^-22)
+// i.e. three fp16 MMAs accumulated in fp32 tensor memory - the same error budget as the 3xTF32 scheme of
+// tc_gemm.cuh at twice the MMA rate and half the shared-memory / L2 operand bytes per reduction element.
+// Elements smaller than 2^-17 of their slot's maximum lose relative (not absolute) accuracy: the absolute
+// error of an operand is bounded by 2^-39 of the slot maximum.
+//
+// Because the operands are already in their final format in global memory, the producers are pure copies:
+// 16-byte cp.async with zero fill (padding / ragged edges) straight into the swizzled UMMA layout, completion
+// signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) - no register staging, no ALU work.
+//
+//   hs_absmax_kernel / hs_split_kernel   fp32 [slot][n] -> scale bits + hi/lo planes
+//   hs_pack_image_kernel                 packed fp32 weights [N][Kd] -> K-major SWIZZLE_128B image (hi, lo)
+//   gather_gemm_hs<BN>                   forward conv + tangents, dgrad   (contract of gather_gemm_tc)
+//   wgrad_gemm_hs                        weight gradients of all K slots  (contract of wgrad_gemm_tc_ms)
+#pragma once
+#include <cuda_fp16.h>
+
+#include "tc_gemm.cuh"
+
+namespace curv {
+
+#ifndef CURV_DISABLE_TC
+
+constexpr int HS_BK = 64;        // fp16 reduction elements per stage = one 128-byte swizzle row
+constexpr int HS_SH_TARGET = 14;  // scaled maximum in [2^14, 2^15)
+constexpr int HS_SH_CLAMP = 60;   // |sh| <= 60: products of two inverse scales stay normal floats
+
+// scale exponent sh (s = 2^sh) from the bit pattern of the slot's absolute maximum
+__host__ __device__ inline int hs_shift_from_bits(uint32_t bits) {
+  if (bits == 0u) return 0;  // all-zero slot
+  const int e = (int)((bits >> 23) & 0xffu) - 127;
+  int sh = HS_SH_TARGET - e;
+  if (sh > HS_SH_CLAMP) sh = HS_SH_CLAMP;
+  if (sh < -HS_SH_CLAMP) sh = -HS_SH_CLAMP;
+  return sh;
+}
+__host__ __device__ inline float hs_pow2(int sh) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((uint32_t)(sh + 127) << 23);
+#else
+  union { uint32_t u; float f; } c;
+  c.u = (uint32_t)(sh + 127) << 23;
+  return c.f;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// absmax + split (streaming, HBM-bound)
+// ---------------------------------------------------------------------------------------------------
+// bits[blockIdx.y] = max over slot blockIdx.y of |x| (as the uint bit pattern; atomicMax on non-negative
+// floats is order independent, hence deterministic).  bits must be zero before the first use.
+__global__ void __launch_bounds__(256) hs_absmax_kernel(const float* __restrict__ x, long long slot_stride,
+                                                        long long n4, uint32_t* __restrict__ bits) {
+  const int slot = blockIdx.y;
+  const float4* p = reinterpret_cast<const float4*>(x + (long long)slot * slot_stride);
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    if (m > 0.f) atomicMax(bits + slot, __float_as_uint(m));
+  }
+}
+
+__device__ __forceinline__ uint32_t hs_pack2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// 8 consecutive floats -> one 16-byte chunk of the hi plane and one of the lo plane
+__device__ __forceinline__ void hs_split8(const float4& v0, const float4& v1, float s, uint4& hi, uint4& lo) {
+  const float x[8] = {v0.x * s, v0.y * s, v0.z * s, v0.w * s, v1.x * s, v1.y * s, v1.z * s, v1.w * s};
+  __half h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(x[i]);
+    l[i] = __float2half_rn(x[i] - __half2float(h[i]));
+  }
+  hi = make_uint4(hs_pack2(h[0], h[1]), hs_pack2(h[2], h[3]), hs_pack2(h[4], h[5]), hs_pack2(h[6], h[7]));
+  lo = make_uint4(hs_pack2(l[0], l[1]), hs_pack2(l[2], l[3]), hs_pack2(l[4], l[5]), hs_pack2(l[6], l[7]));
+}
+
+// x [slot][n] fp32 -> hi/lo [slot][n] fp16 (n = 8*n8), scale from bits[slot].  grid.y = slots
+__global__ void __launch_bounds__(256) hs_split_kernel(const float* __restrict__ x, long long slot_stride,
+                                                       __half* __restrict__ hi, __half* __restrict__ lo,
+                                                       long long out_slot_stride, long long n8,
+                                                       const uint32_t* __restrict__ bits) {
+  const int slot = blockIdx.y;
+  const float s = hs_pow2(hs_shift_from_bits(bits[slot]));
+  const float4* p = reinterpret_cast<const float4*>(x + (long long)slot * slot_stride);
+  uint4* ph = reinterpret_cast<uint4*>(hi + (long long)blockIdx.y * out_slot_stride);
+  uint4* pl = reinterpret_cast<uint4*>(lo + (long long)blockIdx.y * out_slot_stride);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v0 = __ldg(p + 2 * i), v1 = __ldg(p + 2 * i + 1);
+    uint4 h, l;
+    hs_split8(v0, v1, s, h, l);
+    ph[i] = h;
+    pl[i] = l;
+  }
+}
+
+// Weight image for gather_gemm_hs: src [N][Kd] fp32 row-major (slots along grid.y, scale bits[slot]).
+//   block (tn, kc) = [hi plane: BN rows x 128 B (64 fp16), 128B-swizzled][lo plane], blocks ordered tn-major.
+__global__ void hs_pack_image_kernel(const float* __restrict__ src, long long src_slot,
+                                     __half* __restrict__ dst, long long dst_slot, int N, int Kd, int BN,
+                                     int tiles_n, int nchunks, const uint32_t* __restrict__ bits) {
+  src += blockIdx.y * src_slot;
+  dst += blockIdx.y * dst_slot;
+  const float s = hs_pow2(hs_shift_from_bits(bits[blockIdx.y]));
+  const long long total = (long long)tiles_n * nchunks * BN * 8;  // 16-byte chunks per plane
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    long long t = e >> 3;
+    const int r = (int)(t % BN); t /= BN;
+    const int kc = (int)(t % nchunks);
+    const int tn = (int)(t / nchunks);
+    const int n = tn * BN + r, k = kc * HS_BK + c * 8;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (n < N && k < Kd) {
+      const float4* q = reinterpret_cast<const float4*>(src + (long long)n * Kd + k);
+      v0 = __ldg(q);
+      if (k + 4 < Kd) v1 = __ldg(q + 1);
+    }
+    uint4 h, l;
+    hs_split8(v0, v1, s, h, l);
+    __half* blk = dst + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 1;  // in halves
+    *reinterpret_cast<uint4*>(blk + o) = h;
+    *reinterpret_cast<uint4*>(blk + BN * HS_BK + o) = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+// 16-byte async copy global -> shared, zero fill when !ok (the source address is then never dereferenced)
+__device__ __forceinline__ void hs_cp16(uint32_t dst, const void* src, bool ok) {
+  const uint32_t n = ok ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+// this thread's prior cp.async complete -> one (pre-counted) arrival on the mbarrier
+__device__ __forceinline__ void hs_cp_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void hs_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: D = f32, A = B = f16, M = 128, N; majors: 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t hs_idesc(int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+// MN-major 16-bit operand, SWIZZLE_128B: atoms of 8 reduction rows x 128 bytes (64 MN-contiguous fp16),
+// 16-byte chunk index XOR row-in-atom.  lbo = stride between 64-wide MN atoms, sbo = between 8-row K atoms.
+__device__ __forceinline__ uint64_t hs_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct HsGatherArgs {
+  Geom g;
+  const __half* Ah;       // hi plane of the gathered tensor, [slot][B*Hs*Ws*Cs]
+  const __half* Al;       // lo plane
+  long long A_slot;       // elements between slots
+  int a_slot_base;        // absolute slot index of the first slot stored in the planes
+  int a_has_slots;
+  const uint32_t* a_bits;  // absmax bits of the gathered tensor, indexed by absolute slot
+  const __half* W_img;     // image of W (hs_pack_image_kernel)
+  const __half* Wt_img;    // images of the tangent weights, slot k at (k-1)*Wt_img_slot (may be null)
+  long long Wt_img_slot;   // halves
+  const uint32_t* w_bits;  // [0] = W, [k] = tangent weight k
+  const float* bias;
+  const float* bias_t;
+  long long bias_slot;
+  float* out;
+  long long out_slot;
+  int slot0;
+  int accumulate;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// gather GEMM:  out[m][n] = sum_seg (1 / (s_A s_W)) sum_r gather(A_seg)[m][r] * W_seg[n][r]
+// Same CTA organisation as gather_gemm_tc (17 warps, persistent, smem ring + TMEM double buffer); a TMEM
+// accumulation chunk (TC_FLUSH stages) never straddles two segments because they carry different scales.
+// Requires Cs % 8 == 0 (a 16-byte chunk = 8 channels of one filter tap).
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherArgs p, int nslots) {
+  using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const TcSmem<BN> S(smem_raw);
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = ceil_div(g.Nd, BN);
+  const int tiles_m = ceil_div(g.M, TC_BM);
+  const int ntiles = tiles_m * tiles_n * nslots;
+  const int nchunks = ceil_div(g.Kd, HS_BK);
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
+
+  auto decode_tile = [&](int tile, int& slot, int& m0, int& tn) {
+    const int si = tile % nslots;
+    const int rest = tile / nslots;
+    tn = rest % tiles_n;
+    slot = p.slot0 + si; m0 = (rest / tiles_n) * TC_BM;
+  };
+  auto num_segments = [&](int slot) {
+    return slot == 0 ? 1 : (p.a_has_slots ? 1 : 0) + (p.Wt_img != nullptr ? 1 : 0);
+  };
+  // segment s of a slot: which A slot is gathered, which weight (0 = W, k = tangent k)
+  auto segment_ids = [&](int slot, int s, int& a_slot, int& w_id) {
+    const bool first_is_act = (slot == 0) || p.a_has_slots;
+    if (s == 0 && first_is_act) { a_slot = slot; w_id = 0; }
+    else { a_slot = 0; w_id = slot; }
+  };
+
+  if (warp >= 5 && warp < 13) {
+    // ------------------------------------------------------------------ producers (pure cp.async)
+    const int pt = threadIdx.x - 5 * 32;     // 0..255
+    const int a_c = pt & 7, a_r0 = pt >> 3;  // chunk a_c (8 channels) of rows a_r0 + 32 i
+    const uint32_t a_off = (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4));
+    const bool fast = (g.Cs % HS_BK) == 0;  // a 128-byte K row never straddles two filter taps
+    const bool linear = g.mode == 0 || (g.sh == 1 && g.sw == 1);
+    const int sgn = g.mode == 0 ? 1 : -1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot, m0, tn;
+      decode_tile(tile, slot, m0, tn);
+      const int nseg = num_segments(slot);
+      bool m_ok[4];
+      int ah[4], aw[4], rowoff[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + a_r0 + 32 * i;
+        m_ok[i] = m < g.M;
+        const int mm = m_ok[i] ? m : 0;
+        const int bimg = mm / (g.Hd * g.Wd);
+        const int rem = mm - bimg * (g.Hd * g.Wd);
+        const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+        ah[i] = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
+        aw[i] = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
+        // linear: element offset of (b, ah, aw, 0); generic: pixel offset of image b
+        rowoff[i] = linear ? ((bimg * g.Hs + ah[i]) * g.Ws + aw[i]) * g.Cs : bimg * g.Hs * g.Ws;
+        if (!m_ok[i]) ah[i] = -(1 << 20);  // fails every bounds test
+      }
+      for (int seg = 0; seg < nseg; ++seg) {
+        int a_slot, w_id;
+        segment_ids(slot, seg, a_slot, w_id);
+        const __half* Ah = p.Ah + (long long)(a_slot - p.a_slot_base) * p.A_slot;
+        const __half* Al = p.Al + (long long)(a_slot - p.a_slot_base) * p.A_slot;
+        const __half* Wimg = (w_id == 0) ? p.W_img : p.Wt_img + (long long)(w_id - 1) * p.Wt_img_slot;
+        int kh = 0, kw = 0, cb = 0;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          int kh_ = kh, kw_ = kw, c = cb + a_c * 8;
+          bool rok = true;
+          if (!fast) {  // the 16-byte chunk decides its own filter tap
+            const int r = kc * HS_BK + a_c * 8;
+            const int tap = r / g.Cs;
+            c = r - tap * g.Cs;
+            kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
+            rok = r < g.Kd;
+          }
+          mbar_wait(S.empty(stage), phase ^ 1);
+          const uint32_t sA = S.stageA(stage);
+          if (pt == 0) {
+            const uint32_t bytes = 2 * Cfg::B_BYTES;
+            const __half* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
+                         "r"(bytes)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    S.stageB(stage)),
+                "l"(wsrc), "r"(bytes), "r"(S.full(stage))
+                : "memory");
+          }
+          if (linear) {
+            const int tapoff = sgn * (kh_ * g.Ws + kw_) * g.Cs + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int hs = ah[i] + sgn * kh_, ws = aw[i] + sgn * kw_;
+              const bool ok = rok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
+              const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
+              const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
+              hs_cp16(o, Ah + eo, ok);
+              hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
+            }
+          } else {  // strided dgrad: source pixel = (dest + pad - tap) / stride when divisible
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int th = ah[i] - kh_, tw = aw[i] - kw_;
+              bool ok = rok && m_ok[i] && th >= 0 && tw >= 0;
+              const int hs = th / g.sh, ws = tw / g.sw;
+              ok = ok && hs * g.sh == th && ws * g.sw == tw && hs < g.Hs && ws < g.Ws;
+              const long long eo = ok ? ((long long)(rowoff[i] + hs * g.Ws + ws) * g.Cs + c) : 0;
+              const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
+              hs_cp16(o, Ah + eo, ok);
+              hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
+            }
+          }
+          hs_cp_arrive(S.full(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          cb += HS_BK;
+          if (cb >= g.Cs) { cb = 0; if (++kw == g.KW) { kw = 0; ++kh; } }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = hs_idesc(BN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int slot, m0, tn;
+        decode_tile(tile, slot, m0, tn);
+        const int nseg = num_segments(slot);
+        for (int seg = 0; seg < nseg; ++seg) {
+          for (int t0 = 0; t0 < nchunks; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
+            mbar_wait(S.tempty(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            const int T = min(TC_FLUSH, nchunks - t0);
+            for (int it = 0; it < T; ++it) {
+              mbar_wait(S.full(stage), phase);
+              fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+              tc_fence_after();
+              const uint32_t sA = S.stageA(stage), sB = S.stageB(stage);
+              const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
+              const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < HS_BK / 16; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
+                hs_mma_f16(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+                hs_mma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+                hs_mma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+              }
+              tc_commit(S.empty(stage));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(S.tfull(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3, 13-16)
+    constexpr int HALF = BN / 2;
+    const int egrp = warp >= 13 ? 1 : 0;
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int slot, m0, tn;
+      decode_tile(tile, slot, m0, tn);
+      const int n0 = tn * BN + egrp * HALF;
+      const int nseg = num_segments(slot);
+      float accv[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
+      for (int seg = 0; seg < nseg; ++seg) {
+        int a_slot, w_id;
+        segment_ids(slot, seg, a_slot, w_id);
+        const float inv = hs_pow2(-hs_shift_from_bits(__ldg(p.a_bits + a_slot)) -
+                                  hs_shift_from_bits(__ldg(p.w_bits + w_id)));
+        for (int t0 = 0; t0 < nchunks; t0 += TC_FLUSH) {
+          mbar_wait(S.tfull(acc), acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < HALF; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + egrp * HALF + c0), r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) accv[c0 + j] = fmaf(__uint_as_float(r[j]), inv, accv[c0 + j]);
+          }
+          tc_fence_before();
+          mbar_arrive(S.tempty(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+      const float* bias = (slot == 0) ? p.bias
+                                      : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
+      float* outp = p.out + (long long)slot * p.out_slot;
+      const int m = m0 + quad * 32 + lane;
+      if (m < g.M) {
+#pragma unroll
+        for (int j = 0; j < HALF / 4; ++j) {
+          const int n = n0 + j * 4;
+          if (n >= g.Nd) continue;
+          float4 v = make_float4(accv[j * 4 + 0], accv[j * 4 + 1], accv[j * 4 + 2], accv[j * 4 + 3]);
+          if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          float4* dst = reinterpret_cast<float4*>(outp + (long long)m * g.Nd + n);
+          if (p.accumulate) {
+            const float4 o = *dst;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *dst = v;
+        }
+      }
+    }
+  }
+  tc_teardown<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-slot wgrad:  D_k[i][n] = (1 / (s_In s_Gk)) sum_m In[m][i] * G_k[m][n]   for ALL slots k of a tile.
+//   tile = 128 columns i (tap*Cs + c) x 64 channels n x one split of the pixel range
+//   A operand (M = 128): gathered primal input, MN-major;  B operand: the 64-channel G tiles of up to 4 slots
+//   side by side (N = 64 * slots-in-group <= 256), MN-major, so ONE MMA feeds 4 accumulators and the A tile
+//   is read from shared memory once per 4 slots.  The 8 accumulators [128 x 64] fill the 512 TMEM columns.
+//   stage = 16 pixels (one K = 16 MMA step), 40 KB:
+//     [In hi 4K][In lo 4K][G hi grp0 8K][G lo grp0 8K][G hi grp1 8K][G lo grp1 8K]
+//   MN-major SWIZZLE_128B: chunk c (16 B = 8 elements) of pixel row r of MN atom a (64 elements) at
+//     a*2048 + (r>>3)*1024 + (r&7)*128 + ((c ^ (r&7)) << 4)          (LBO = 2048, SBO = 1024)
+// TMEM is single-buffered; every HSW_FLUSH stages (4096 pixels) the epilogue adds the chunk into the split's
+// partial in global memory (same thread, same address, fixed order) - bounds the truncation-bias chain.
+// Requires Cs % 8 == 0 and Ng % 8 == 0.
+// ---------------------------------------------------------------------------------------------------
+struct HsWgradArgs {
+  Geom g;                  // mode 0 geometry of the forward conv; (Hd, Wd) is the grid of G
+  const __half* Gh;        // cotangent planes [slot - slot0][M*Ng]  (slot0 first)
+  const __half* Gl;
+  long long G_slot;        // elements
+  int Ng;
+  const uint32_t* g_bits;  // indexed by absolute slot
+  const __half* Ih;        // primal input planes [B*Hs*Ws*Cs]
+  const __half* Il;
+  const uint32_t* i_bits;  // [0]
+  float* partial;          // [split][nslots][N][Kd]
+  int nsplit, nslots, slot0, m_per_split;
+};
+
+constexpr int HSW_ROWS = 16;
+constexpr int HSW_A_BYTES = 128 * HSW_ROWS * 2;   // 4 KB per plane
+constexpr int HSW_B_BYTES = 256 * HSW_ROWS * 2;   // 8 KB per plane and slot group
+constexpr int HSW_STAGE_BYTES = 2 * HSW_A_BYTES + 4 * HSW_B_BYTES;  // 40 KB
+constexpr int HSW_STAGES = 5;
+constexpr int HSW_FLUSH = 256;
+constexpr int HSW_SMEM_BYTES = HSW_STAGES * HSW_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + HSW_STAGES * HSW_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (HSW_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * HSW_STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * HSW_STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * HSW_STAGES + 2);
+
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NS = p.nslots;  // 1..8
+  const int tiles_i = ceil_div(g.Kd, TC_BM), tiles_j = ceil_div(p.Ng, 64);
+  const int ntiles = tiles_i * tiles_j * p.nsplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HSW_STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  auto decode_tile = [&](int tile, int& split, int& i0, int& j0) {
+    const int tj = tile % tiles_j;
+    const int rest = tile / tiles_j;
+    const int ti = rest % tiles_i;
+    split = rest / tiles_i;
+    i0 = ti * TC_BM; j0 = tj * 64;
+  };
+  auto stages_of = [&](int split) {
+    const int mb = split * p.m_per_split;
+    const int me = min(g.M, mb + p.m_per_split);
+    return ceil_div(max(0, me - mb), HSW_ROWS);
+  };
+
+  if (warp >= 5 && warp < 13) {
+    // ------------------------------------------------------------------ producers (pure cp.async)
+    const int pt = threadIdx.x - 5 * 32;
+    // In operand: pixel row ir = pt >> 4, chunk ic = pt & 15 (columns i0 + 8 ic .. +7), both planes
+    const int ir = pt >> 4, ic = pt & 15;
+    const uint32_t offI = (uint32_t)((ic >> 3) * 2048 + (ir >> 3) * 1024 + (ir & 7) * 128 + (((ic & 7) ^ (ir & 7)) << 4));
+    // G operand: plane gp = pt >> 7 (0 hi, 1 lo), pixel row gr = (pt >> 3) & 15, chunk gc = pt & 7 (8 channels)
+    const int gp = pt >> 7, gr = (pt >> 3) & 15, gc = pt & 7;
+    const uint32_t offG = (uint32_t)((gr >> 3) * 1024 + (gr & 7) * 128 + ((gc ^ (gr & 7)) << 4));
+    const __half* Gplane = gp ? p.Gl : p.Gh;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int split, i0, j0;
+      decode_tile(tile, split, i0, j0);
+      const int mb = split * p.m_per_split;
+      const int me = min(g.M, mb + p.m_per_split);
+      const int nst = stages_of(split);
+      const int col = i0 + ic * 8;
+      const bool iok = col < g.Kd;
+      const int tap = iok ? col / g.Cs : 0;
+      const int icn = col - tap * g.Cs;
+      const int ikh = tap / g.KW, ikw = tap - ikh * g.KW;
+      const int ch = j0 + gc * 8;
+      const bool chok = ch < p.Ng;
+      for (int st = 0; st < nst; ++st) {
+        // gathered input pixel of this thread's In row
+        const int mi = mb + st * HSW_ROWS + ir;
+        bool okI = iok && mi < me;
+        long long eoI = 0;
+        if (okI) {
+          const int bimg = mi / (g.Hd * g.Wd);
+          const int rem = mi - bimg * (g.Hd * g.Wd);
+          const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+          const int hs = hd * g.sh - g.ph + ikh, ws = wd * g.sw - g.pw + ikw;
+          okI = hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+          if (okI) eoI = (((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + icn;
+        }
+        const int mg = mb + st * HSW_ROWS + gr;
+        const bool okG = chok && mg < me;
+        const long long eoG = okG ? (long long)mg * p.Ng + ch : 0;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
+        const uint32_t sB = sA + 2 * HSW_A_BYTES;
+        hs_cp16(sA + offI, p.Ih + eoI, okI);
+        hs_cp16(sA + HSW_A_BYTES + offI, p.Il + eoI, okI);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < NS) {
+            // slot s: group s >> 2, MN atom s & 3 inside the group's plane
+            const uint32_t o = sB + (uint32_t)((s >> 2) * 2 * HSW_B_BYTES + gp * HSW_B_BYTES + (s & 3) * 2048) + offG;
+            hs_cp16(o, Gplane + (long long)s * p.G_slot + eoG, okG);
+          }
+        }
+        hs_cp_arrive(full_bar(stage));
+        if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const int n0 = NS >= 4 ? 256 : 64 * NS;            // N of slot group 0
+      const int n1 = NS > 4 ? 64 * (NS - 4) : 0;         // N of slot group 1
+      const uint32_t idesc0 = hs_idesc(n0, 1, 1);
+      const uint32_t idesc1 = hs_idesc(n1 > 0 ? n1 : 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int split, i0, j0;
+        decode_tile(tile, split, i0, j0);
+        const int nst = stages_of(split);
+        for (int c0 = 0; c0 < max(nst, 1); c0 += HSW_FLUSH) {
+          mbar_wait(tempty_bar, tphase ^ 1);  // previous chunk / tile drained
+          tc_fence_after();
+          const int cend = min(nst, c0 + HSW_FLUSH);
+          for (int st = c0; st < cend; ++st) {
+            mbar_wait(full_bar(stage), phase);
+            fence_async_proxy();
+            tc_fence_after();
+            const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
+            const uint32_t sB = sA + 2 * HSW_A_BYTES;
+            const uint64_t dAh = hs_mnmajor_desc(sA, 2048, 1024), dAl = hs_mnmajor_desc(sA + HSW_A_BYTES, 2048, 1024);
+            const uint32_t accf = st != c0 ? 1u : 0u;
+            {
+              const uint64_t dBh = hs_mnmajor_desc(sB, 2048, 1024), dBl = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
+              hs_mma_f16(tmem_base, dAl, dBh, idesc0, accf);
+              hs_mma_f16(tmem_base, dAh, dBl, idesc0, 1u);
+              hs_mma_f16(tmem_base, dAh, dBh, idesc0, 1u);
+            }
+            if (n1 > 0) {
+              const uint64_t dBh = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
+              const uint64_t dBl = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
+              hs_mma_f16(tmem_base + 256u, dAl, dBh, idesc1, accf);
+              hs_mma_f16(tmem_base + 256u, dAh, dBl, idesc1, 1u);
+              hs_mma_f16(tmem_base + 256u, dAh, dBh, idesc1, 1u);
+            }
+            tc_commit(empty_bar(stage));
+            if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(tfull_bar);
+          tphase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3, 13-16)
+    const int egrp = warp >= 13 ? 1 : 0;  // slots with (s & 1) == egrp
+    const int quad = warp & 3;
+    const int sh_in = hs_shift_from_bits(__ldg(p.i_bits));
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int split, i0, j0;
+      decode_tile(tile, split, i0, j0);
+      const int nst = stages_of(split);
+      const int i = i0 + quad * 32 + lane;
+      for (int c0 = 0; c0 < max(nst, 1); c0 += HSW_FLUSH) {
+        mbar_wait(tfull_bar, tphase);
+        tc_fence_after();
+        for (int s = egrp; s < NS; s += 2) {
+          const float inv = hs_pow2(-sh_in - hs_shift_from_bits(__ldg(p.g_bits + p.slot0 + s)));
+          float* outp = p.partial + ((long long)split * p.nslots + s) * (long long)g.N * g.Kd;
+#pragma unroll 1
+          for (int cc = 0; cc < 64; cc += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 64 + cc), r);
+            if (i < g.Kd) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = j0 + cc + j;
+                if (n < g.N) {
+                  float* dst = outp + (long long)n * g.Kd + i;
+                  float v = nst == 0 ? 0.f : __uint_as_float(r[j]) * inv;
+                  if (c0 > 0) v += *dst;  // same thread wrote it in the previous chunk: fixed order
+                  *dst = v;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar);
+        tphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+// shapes the half-split kernels accept (the engine decides *when* to use them)
+static inline bool hs_gather_shape_ok(const Geom& g) {
+  if (g.Cs % 8 != 0 || g.Nd % 4 != 0) return false;
+  if ((long long)g.B * g.Hs * g.Ws * g.Cs >= (1LL << 31) - (1LL << 24)) return false;  // 32-bit row offsets
+  return true;
+}
+static inline bool hs_wgrad_shape_ok(const Geom& g, int Ng) { return g.Cs % 8 == 0 && Ng % 8 == 0; }
+// size (halves) of the weight image of an [N][Kd] matrix
+static inline long long hs_image_halves(int Nd, int Kd) {
+  const int BN = tc_bn(Nd);
+  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, HS_BK) * (2 * BN * HS_BK);
+}
+
+static int hs_ready() {
+  static int ready = -1;
+  if (ready == -1) {
+    ready = 0;
+    if (tc_sm_count() > 0) {
+      bool ok = cudaFuncSetAttribute(gather_gemm_hs<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<128>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_hs<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(wgrad_gemm_hs, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HSW_SMEM_BYTES) == cudaSuccess;
+      ready = ok ? 1 : 0;
+    }
+  }
+  return ready;
+}
+
+static inline int hs_grid(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+// absmax of nslots slots (x = first slot, n elements each) into bits[0..nslots); bits must have been zeroed
+static inline int hs_launch_absmax(const float* x, long long slot_stride, long long n, uint32_t* bits,
+                                   int nslots, cudaStream_t st) {
+  hs_absmax_kernel<<<dim3(hs_grid(n / 4), nslots), 256, 0, st>>>(x, slot_stride, n / 4, bits);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+// split nslots slots (x = first slot, scale bits[slot]) into planes
+static inline int hs_launch_split(const float* x, long long slot_stride, long long n, __half* hi, __half* lo,
+                                  long long out_slot_stride, const uint32_t* bits, int nslots, cudaStream_t st) {
+  hs_split_kernel<<<dim3(hs_grid(n / 8), nslots), 256, 0, st>>>(x, slot_stride, hi, lo, out_slot_stride, n / 8,
+                                                                bits);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+// pack [N][Kd] fp32 (nslots matrices src_slot apart, scales bits[slot]) into weight images
+static inline int hs_launch_pack_image(const float* src, long long src_slot, __half* dst, long long dst_slot,
+                                       int N, int Nd, int Kd, int nslots, const uint32_t* bits,
+                                       cudaStream_t st) {
+  const int BN = tc_bn(Nd);
+  const int tiles_n = ceil_div(Nd, BN), nchunks = ceil_div(Kd, HS_BK);
+  const long long total = (long long)tiles_n * nchunks * BN * 8;
+  hs_pack_image_kernel<<<dim3(hs_grid(total), nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
+                                                                    tiles_n, nchunks, bits);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// returns 0 on success, >0 on a CUDA error, <0 if unavailable
+static inline int hs_launch_gather_gemm(const HsGatherArgs& a, int nslots, cudaStream_t st) {
+  if (hs_ready() <= 0) return -1;
+  const int sms = tc_sm_count();
+  const Geom& g = a.g;
+  if (tc_bn(g.Nd) == 128) {
+    const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
+    gather_gemm_hs<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+  } else {
+    const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
+    gather_gemm_hs<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+static inline int hs_launch_wgrad(const HsWgradArgs& a, cudaStream_t st) {
+  if (hs_ready() <= 0) return -1;
+  if (a.nslots < 1 || a.nslots > 8) return -1;
+  const int sms = tc_sm_count();
+  const int ntiles = ceil_div(a.g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nsplit;
+  wgrad_gemm_hs<<<ntiles < sms ? ntiles : sms, TC_THREADS, HSW_SMEM_BYTES, st>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+#endif  // CURV_DISABLE_TC
+
+}  // namespace curv

@@ -174,8 +174,12 @@ long long curv_launch_count(void);
    events and returns summed milliseconds, algorithmic FLOPs and launch counts per class. */
 int curv_profile_enable(int on);
 int curv_profile_read(double* ms, double* flops, long long* count);
-/* 0: SIMT fp32 contraction kernels only, 1 (default): tcgen05 (3xTF32 split) tensor-core kernels for
-   layers large enough to fill 128-row tiles, 2: tcgen05 for every contraction (tests). Returns the old mode. */
+/* one class at a time; class 2 = the absmax / fp16 hi-lo split passes feeding the half-split kernels */
+int curv_profile_read_class(int cls, double* ms, double* flops, long long* count);
+/* 0: SIMT fp32 contraction kernels only, 1 (default): tcgen05 tensor-core kernels (fp16 hi/lo "half-split"
+   where the channel count allows it, 3xTF32 split otherwise) for layers large enough to fill 128-row
+   tiles, 2: tcgen05 for every contraction (tests).  Bits 4.. are debug switches: 0x10 no tcgen05 gather GEMM,
+   0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead).  Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);
 
 #ifdef __cplusplus
