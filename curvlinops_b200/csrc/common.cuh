@@ -5,7 +5,8 @@
 
 namespace curv {
 
-// Geometry of one implicit-GEMM convolution (all tensors NHWC, channels padded to 4).
+// Geometry of one implicit-GEMM convolution (all tensors NHWC, channels padded to a multiple of 8:
+// one 16-byte chunk of an fp16 plane = 8 channels of one pixel, see hs_gemm.cuh).
 //   source tensor  : [B][Hs][Ws][Cs]            (what is gathered)
 //   destination    : [B][Hd][Wd][Nd]            (one GEMM row per destination pixel)
 //   mode 0 (forward / wgrad gather): source pixel = dest*stride - pad + tap
@@ -62,5 +63,6 @@ struct WgradArgs {
 
 inline __host__ __device__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline __host__ __device__ int pad4(int c) { return (c + 3) & ~3; }
+inline __host__ __device__ int pad8(int c) { return (c + 7) & ~7; }
 
 }  // namespace curv

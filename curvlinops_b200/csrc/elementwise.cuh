@@ -300,42 +300,58 @@ __global__ void zero_slots_kernel(float* __restrict__ dst, long long dst_slot, l
 }
 
 // max pooling: slot 0 computes max + argmax tap (uint8 per element); slot k gathers x_k[argmax].
+// One thread per (output pixel, 4 channels), 32-bit index arithmetic (the host checks the element count).
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot, float* __restrict__ y,
                                    long long y_slot, unsigned char* __restrict__ idx, int B, int Hs,
                                    int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh, int sw, int ph,
                                    int pw, int slot0) {
   const int slot = slot0 + blockIdx.y;
-  const float* xs = x + slot * x_slot;
-  float* ys = y + slot * y_slot;
-  const long long total = (long long)B * Hd * Wd * Cp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % Cp);
-    long long pix = i / Cp;
-    int wd = (int)(pix % Wd);
-    long long r = pix / Wd;
-    int hd = (int)(r % Hd);
-    int b = (int)(r / Hd);
+  const float4* xs = reinterpret_cast<const float4*>(x + slot * x_slot);
+  float4* ys = reinterpret_cast<float4*>(y + slot * y_slot);
+  uchar4* ix = reinterpret_cast<uchar4*>(idx);
+  const unsigned C4 = (unsigned)Cp >> 2;
+  const unsigned total = (unsigned)B * Hd * Wd * C4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4;
+    unsigned pix = i / C4;
+    const int wd = (int)(pix % (unsigned)Wd);
+    pix /= (unsigned)Wd;
+    const int hd = (int)(pix % (unsigned)Hd);
+    const unsigned b = pix / (unsigned)Hd;
+    const int h0 = hd * sh - ph, w0 = wd * sw - pw;
     if (slot == 0) {
-      float best = -INFINITY;
-      int bi = 255;
+      float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      uchar4 bi = make_uchar4(255, 255, 255, 255);
       for (int kh = 0; kh < KH; ++kh) {
-        int hs = hd * sh - ph + kh;
+        const int hs = h0 + kh;
         if (hs < 0 || hs >= Hs) continue;
         for (int kw = 0; kw < KW; ++kw) {
-          int ws = wd * sw - pw + kw;
+          const int ws = w0 + kw;
           if (ws < 0 || ws >= Ws) continue;
-          float v = __ldg(xs + (((long long)b * Hs + hs) * Ws + ws) * Cp + c);
-          if (v > best || bi == 255) { best = v; bi = kh * KW + kw; }
+          const float4 v = __ldg(xs + ((size_t)(b * Hs + hs) * Ws + ws) * C4 + c4);
+          const unsigned char tap = (unsigned char)(kh * KW + kw);
+          if (v.x > best.x || bi.x == 255) { best.x = v.x; bi.x = tap; }
+          if (v.y > best.y || bi.y == 255) { best.y = v.y; bi.y = tap; }
+          if (v.z > best.z || bi.z == 255) { best.z = v.z; bi.z = tap; }
+          if (v.w > best.w || bi.w == 255) { best.w = v.w; bi.w = tap; }
         }
       }
       ys[i] = best;
-      idx[i] = (unsigned char)bi;
+      ix[i] = bi;
     } else {
-      int bi = idx[i];
-      int kh = bi / KW, kw = bi - kh * KW;
-      int hs = hd * sh - ph + kh, ws = wd * sw - pw + kw;
-      ys[i] = __ldg(xs + (((long long)b * Hs + hs) * Ws + ws) * Cp + c);
+      const uchar4 bi = ix[i];
+      auto pick = [&](unsigned char t, int lane) {
+        const int kh = t / KW, kw = t - kh * KW;
+        return __ldg(reinterpret_cast<const float*>(xs + ((size_t)(b * Hs + h0 + kh) * Ws + w0 + kw) * C4 + c4) + lane);
+      };
+      float4 v;
+      if (bi.x == bi.y && bi.x == bi.z && bi.x == bi.w) {  // common case: one tap wins all four channels
+        const int kh = bi.x / KW, kw = bi.x - kh * KW;
+        v = __ldg(xs + ((size_t)(b * Hs + h0 + kh) * Ws + w0 + kw) * C4 + c4);
+      } else {
+        v = make_float4(pick(bi.x, 0), pick(bi.y, 1), pick(bi.z, 2), pick(bi.w, 3));
+      }
+      ys[i] = v;
     }
   }
 }
@@ -351,16 +367,15 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_sl
   const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
   float4* o = reinterpret_cast<float4*>(gx + slot * gx_slot);
   const uchar4* ix = reinterpret_cast<const uchar4*>(idx);
-  const int C4 = Cp >> 2;
-  const long long total = (long long)B * Hs * Ws * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long pix = i / C4;
-    const int ws = (int)(pix % Ws);
-    long long r = pix / Ws;
-    const int hs = (int)(r % Hs);
-    const int b = (int)(r / Hs);
+  const unsigned C4 = (unsigned)Cp >> 2;
+  const unsigned total = (unsigned)B * Hs * Ws * C4;  // 32-bit index arithmetic (checked on the host)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4;
+    unsigned pix = i / C4;
+    const int ws = (int)(pix % (unsigned)Ws);
+    pix /= (unsigned)Ws;
+    const int hs = (int)(pix % (unsigned)Hs);
+    const unsigned b = pix / (unsigned)Hs;
     // windows hd with hd*sh - ph <= hs <= hd*sh - ph + KH - 1
     int hd_lo = hs + ph - KH + 1; hd_lo = hd_lo <= 0 ? 0 : (hd_lo + sh - 1) / sh;
     int hd_hi = (hs + ph) / sh; if (hd_hi > Hd - 1) hd_hi = Hd - 1;
@@ -371,7 +386,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_sl
       const int kh = hs + ph - hd * sh;
       for (int wd = wd_lo; wd <= wd_hi; ++wd) {
         const int tap = kh * KW + (ws + pw - wd * sw);
-        const long long oi = (((long long)b * Hd + hd) * Wd + wd) * C4 + c4;
+        const size_t oi = ((size_t)(b * Hd + hd) * Wd + wd) * C4 + c4;
         const uchar4 t = __ldg(ix + oi);
         const float4 v = __ldg(g + oi);
         if (t.x == tap) acc.x += v.x;

@@ -136,7 +136,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
   auto alloc = [&](long long elems) { long long o = off; off = align_up(off + elems, 64); return o; };
   for (int i = 0; i < n_values; ++i) {
     Value v;
-    v.C = values[i].C; v.H = values[i].H; v.W = values[i].W; v.Cp = pad4(v.C);
+    v.C = values[i].C; v.H = values[i].H; v.W = values[i].W; v.Cp = pad8(v.C);
     v.tan = values[i].has_tangent != 0;
     if (v.C < 1 || v.H < 1 || v.W < 1) { delete P; return fail(CURV_ERR_INVALID, "bad value shape"); }
     v.slot_elems = (long long)batch * v.H * v.W * v.Cp;
@@ -681,12 +681,14 @@ static int forward(const Ctx& c, const void* X, int K) {
       }
       case CURV_OP_MAXPOOL: {
         unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
-        maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems), 1), 256, 0, st>>>(
+        if (vi.slot_elems / 4 >= (1LL << 31) || vo.slot_elems / 4 >= (1LL << 31))
+          return fail(CURV_ERR_UNSUPPORTED, "max-pool tensors beyond 2^33 elements per slot are not supported");
+        maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems / 4), 1), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
             vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 0);
         LAUNCH_CHECK();
         if (nsl > 1) {
-          maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems), nsl - 1), 256, 0, st>>>(
+          maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems / 4), nsl - 1), 256, 0, st>>>(
               c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
               vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1);
           LAUNCH_CHECK();

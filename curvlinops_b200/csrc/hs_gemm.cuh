@@ -20,6 +20,7 @@
 //   wgrad_gemm_hs                        weight gradients of all K slots  (contract of wgrad_gemm_tc_ms)
 #pragma once
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "tc_gemm.cuh"
 
@@ -183,6 +184,21 @@ __device__ __forceinline__ uint64_t hs_mnmajor_desc(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Strided dgrad (mode 1, stride > 1): of the KH*KW filter taps only those with kh = (hd + ph) mod sh and
+// kw = (wd + pw) mod sw reach a source pixel, so the destination pixels fall into sh*sw parity classes,
+// each with its own (smaller) tap list.  In class coordinates (hd = sh*i + oh, wd = sw*j + ow) the gather is
+// a stride-1 gather source(i + dh, j + dw): the kernel runs one dense GEMM per class instead of multiplying
+// 1 - 1/(sh*sw) zeros.  Built on the host by hs_make_parity; needs Cs % 64 == 0 (one tap per K stage).
+constexpr int HS_PAR_TAPS = 16;
+struct HsParity {
+  int nclass;  // 0: off
+  int oh[4], ow[4], Hc[4], Wc[4];
+  int tile0[5];  // first m-tile of each class (prefix sums), tile0[nclass] = total
+  int ntap[4];
+  signed char dh[4][HS_PAR_TAPS], dw[4][HS_PAR_TAPS];
+  unsigned char tap[4][HS_PAR_TAPS];  // index of the tap in the weight image (kh*KW + kw)
+};
+
 struct HsGatherArgs {
   Geom g;
   const __half* Ah;       // hi plane of the gathered tensor, [slot][B*Hs*Ws*Cs]
@@ -202,6 +218,8 @@ struct HsGatherArgs {
   long long out_slot;
   int slot0;
   int accumulate;
+  int debug;  // perf experiments only: 1 = producers skip the copies, 2 = the MMA lane skips the MMAs
+  HsParity par;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -210,6 +228,8 @@ struct HsGatherArgs {
 // accumulation chunk (TC_FLUSH stages) never straddles two segments because they carry different scales.
 // Requires Cs % 8 == 0 (a 16-byte chunk = 8 channels of one filter tap).
 // ---------------------------------------------------------------------------------------------------
+struct HsTile { int slot, m0, tn, cls, T; };  // T = K stages per segment
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherArgs p, int nslots) {
   using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
@@ -217,18 +237,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
   extern __shared__ uint8_t smem_raw[];
   const TcSmem<BN> S(smem_raw);
   const Geom& g = p.g;
+  const HsParity& par = p.par;
+  const bool parity = par.nclass > 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = ceil_div(g.Nd, BN);
-  const int tiles_m = ceil_div(g.M, TC_BM);
+  const int tiles_m = parity ? par.tile0[par.nclass] : ceil_div(g.M, TC_BM);
   const int ntiles = tiles_m * tiles_n * nslots;
   const int nchunks = ceil_div(g.Kd, HS_BK);
+  const int cpt = g.Cs / HS_BK;  // K stages per filter tap (parity mode)
   const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
 
-  auto decode_tile = [&](int tile, int& slot, int& m0, int& tn) {
+  auto decode_tile = [&](int tile, HsTile& t) {
     const int si = tile % nslots;
     const int rest = tile / nslots;
-    tn = rest % tiles_n;
-    slot = p.slot0 + si; m0 = (rest / tiles_n) * TC_BM;
+    t.tn = rest % tiles_n;
+    const int mt = rest / tiles_n;
+    t.slot = p.slot0 + si;
+    if (parity) {
+      int cls = 0;
+      while (cls + 1 < par.nclass && mt >= par.tile0[cls + 1]) ++cls;
+      t.cls = cls; t.m0 = (mt - par.tile0[cls]) * TC_BM; t.T = par.ntap[cls] * cpt;
+    } else {
+      t.cls = 0; t.m0 = mt * TC_BM; t.T = nchunks;
+    }
   };
   auto num_segments = [&](int slot) {
     return slot == 0 ? 1 : (p.a_has_slots ? 1 : 0) + (p.Wt_img != nullptr ? 1 : 0);
@@ -246,52 +277,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
     const int a_c = pt & 7, a_r0 = pt >> 3;  // chunk a_c (8 channels) of rows a_r0 + 32 i
     const uint32_t a_off = (uint32_t)((a_r0 >> 3) * 1024 + (a_r0 & 7) * 128 + ((a_c ^ (a_r0 & 7)) << 4));
     const bool fast = (g.Cs % HS_BK) == 0;  // a 128-byte K row never straddles two filter taps
-    const bool linear = g.mode == 0 || (g.sh == 1 && g.sw == 1);
+    const bool linear = parity || g.mode == 0 || (g.sh == 1 && g.sw == 1);
     const int sgn = g.mode == 0 ? 1 : -1;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int slot, m0, tn;
-      decode_tile(tile, slot, m0, tn);
-      const int nseg = num_segments(slot);
+      HsTile t;
+      decode_tile(tile, t);
+      const int nseg = num_segments(t.slot);
       bool m_ok[4];
       int ah[4], aw[4], rowoff[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = m0 + a_r0 + 32 * i;
-        m_ok[i] = m < g.M;
-        const int mm = m_ok[i] ? m : 0;
-        const int bimg = mm / (g.Hd * g.Wd);
-        const int rem = mm - bimg * (g.Hd * g.Wd);
-        const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
-        ah[i] = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
-        aw[i] = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
-        // linear: element offset of (b, ah, aw, 0); generic: pixel offset of image b
-        rowoff[i] = linear ? ((bimg * g.Hs + ah[i]) * g.Ws + aw[i]) * g.Cs : bimg * g.Hs * g.Ws;
+        const int m = t.m0 + a_r0 + 32 * i;
+        if (parity) {
+          const int hw = par.Hc[t.cls] * par.Wc[t.cls];
+          m_ok[i] = m < g.B * hw;
+          const int mm = m_ok[i] ? m : 0;
+          const int bimg = mm / hw;
+          const int rem = mm - bimg * hw;
+          ah[i] = rem / par.Wc[t.cls]; aw[i] = rem - ah[i] * par.Wc[t.cls];
+          rowoff[i] = ((bimg * g.Hs + ah[i]) * g.Ws + aw[i]) * g.Cs;
+        } else {
+          m_ok[i] = m < g.M;
+          const int mm = m_ok[i] ? m : 0;
+          const int bimg = mm / (g.Hd * g.Wd);
+          const int rem = mm - bimg * (g.Hd * g.Wd);
+          const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+          ah[i] = g.mode == 0 ? hd * g.sh - g.ph : hd + g.ph;
+          aw[i] = g.mode == 0 ? wd * g.sw - g.pw : wd + g.pw;
+          // linear: element offset of (b, ah, aw, 0); generic: pixel offset of image b
+          rowoff[i] = linear ? ((bimg * g.Hs + ah[i]) * g.Ws + aw[i]) * g.Cs : bimg * g.Hs * g.Ws;
+        }
         if (!m_ok[i]) ah[i] = -(1 << 20);  // fails every bounds test
       }
       for (int seg = 0; seg < nseg; ++seg) {
         int a_slot, w_id;
-        segment_ids(slot, seg, a_slot, w_id);
+        segment_ids(t.slot, seg, a_slot, w_id);
         const __half* Ah = p.Ah + (long long)(a_slot - p.a_slot_base) * p.A_slot;
         const __half* Al = p.Al + (long long)(a_slot - p.a_slot_base) * p.A_slot;
         const __half* Wimg = (w_id == 0) ? p.W_img : p.Wt_img + (long long)(w_id - 1) * p.Wt_img_slot;
-        int kh = 0, kw = 0, cb = 0;
-        for (int kc = 0; kc < nchunks; ++kc) {
-          int kh_ = kh, kw_ = kw, c = cb + a_c * 8;
+        int kh = 0, kw = 0, cb = 0, ti = 0;  // ti: position in the class tap list (parity mode)
+        for (int kc = 0; kc < t.T; ++kc) {
+          // (dy, dx): pixel displacement of this stage's tap, c: first channel of this thread's chunk,
+          // wblk: K-block of the weight image
+          int dy, dx, c = cb + a_c * 8, wblk = kc;
           bool rok = true;
-          if (!fast) {  // the 16-byte chunk decides its own filter tap
+          if (parity) {
+            dy = par.dh[t.cls][ti]; dx = par.dw[t.cls][ti];
+            wblk = par.tap[t.cls][ti] * cpt + cb / HS_BK;
+          } else if (fast) {
+            dy = sgn * kh; dx = sgn * kw;
+          } else {  // the 16-byte chunk decides its own filter tap
             const int r = kc * HS_BK + a_c * 8;
             const int tap = r / g.Cs;
             c = r - tap * g.Cs;
-            kh_ = tap / g.KW; kw_ = tap - kh_ * g.KW;
+            const int kh_ = tap / g.KW;
+            dy = sgn * kh_; dx = sgn * (tap - kh_ * g.KW);
             rok = r < g.Kd;
           }
           mbar_wait(S.empty(stage), phase ^ 1);
           const uint32_t sA = S.stageA(stage);
           if (pt == 0) {
             const uint32_t bytes = 2 * Cfg::B_BYTES;
-            const __half* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+            const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (2 * BN * HS_BK);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
                          "r"(bytes)
                          : "memory");
@@ -301,21 +350,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
                 "l"(wsrc), "r"(bytes), "r"(S.full(stage))
                 : "memory");
           }
+          if (p.debug & 1) {
+            mbar_arrive(S.full(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            cb += HS_BK;
+            if (cb >= g.Cs) { cb = 0; ++ti; if (++kw == g.KW) { kw = 0; ++kh; } }
+            continue;
+          }
           if (linear) {
-            const int tapoff = sgn * (kh_ * g.Ws + kw_) * g.Cs + c;
+            const int tapoff = (dy * g.Ws + dx) * g.Cs + c;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int hs = ah[i] + sgn * kh_, ws = aw[i] + sgn * kw_;
+              const int hs = ah[i] + dy, ws = aw[i] + dx;
               const bool ok = rok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
               const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
               const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
               hs_cp16(o, Ah + eo, ok);
               hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
             }
-          } else {  // strided dgrad: source pixel = (dest + pad - tap) / stride when divisible
+          } else {  // strided dgrad, generic: source pixel = (dest + pad - tap) / stride when divisible
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int th = ah[i] - kh_, tw = aw[i] - kw_;
+              const int th = ah[i] + dy, tw = aw[i] + dx;  // dy, dx = -kh, -kw
               bool ok = rok && m_ok[i] && th >= 0 && tw >= 0;
               const int hs = th / g.sh, ws = tw / g.sw;
               ok = ok && hs * g.sh == th && ws * g.sw == tw && hs < g.Hs && ws < g.Ws;
@@ -328,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
           hs_cp_arrive(S.full(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           cb += HS_BK;
-          if (cb >= g.Cs) { cb = 0; if (++kw == g.KW) { kw = 0; ++kh; } }
+          if (cb >= g.Cs) { cb = 0; ++ti; if (++kw == g.KW) { kw = 0; ++kh; } }
         }
       }
     }
@@ -339,15 +395,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int slot, m0, tn;
-        decode_tile(tile, slot, m0, tn);
-        const int nseg = num_segments(slot);
+        HsTile t;
+        decode_tile(tile, t);
+        const int nseg = num_segments(t.slot);
         for (int seg = 0; seg < nseg; ++seg) {
-          for (int t0 = 0; t0 < nchunks; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
+          for (int t0 = 0; t0 < t.T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
             mbar_wait(S.tempty(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            const int T = min(TC_FLUSH, nchunks - t0);
+            const int T = min(TC_FLUSH, t.T - t0);
             for (int it = 0; it < T; ++it) {
               mbar_wait(S.full(stage), phase);
               fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
@@ -357,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
               const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
 #pragma unroll
               for (int ks = 0; ks < HS_BK / 16; ++ks) {
+                if (p.debug & 2) break;
                 const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
                 hs_mma_f16(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
                 hs_mma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
@@ -380,19 +437,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int slot, m0, tn;
-      decode_tile(tile, slot, m0, tn);
-      const int n0 = tn * BN + egrp * HALF;
-      const int nseg = num_segments(slot);
+      HsTile t;
+      decode_tile(tile, t);
+      const int n0 = t.tn * BN + egrp * HALF;
+      const int nseg = num_segments(t.slot);
       float accv[HALF];
 #pragma unroll
       for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
       for (int seg = 0; seg < nseg; ++seg) {
         int a_slot, w_id;
-        segment_ids(slot, seg, a_slot, w_id);
+        segment_ids(t.slot, seg, a_slot, w_id);
         const float inv = hs_pow2(-hs_shift_from_bits(__ldg(p.a_bits + a_slot)) -
                                   hs_shift_from_bits(__ldg(p.w_bits + w_id)));
-        for (int t0 = 0; t0 < nchunks; t0 += TC_FLUSH) {
+        for (int t0 = 0; t0 < t.T; t0 += TC_FLUSH) {
           mbar_wait(S.tfull(acc), acc_phase);
           tc_fence_after();
 #pragma unroll
@@ -407,11 +464,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
-      const float* bias = (slot == 0) ? p.bias
-                                      : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
-      float* outp = p.out + (long long)slot * p.out_slot;
-      const int m = m0 + quad * 32 + lane;
-      if (m < g.M) {
+      const float* bias = (t.slot == 0) ? p.bias
+                                        : (p.bias_t ? p.bias_t + (long long)(t.slot - 1) * p.bias_slot : nullptr);
+      float* outp = p.out + (long long)t.slot * p.out_slot;
+      int m = t.m0 + quad * 32 + lane;  // GEMM row -> destination pixel
+      bool m_ok = m < g.M;
+      if (parity) {
+        const int hw = par.Hc[t.cls] * par.Wc[t.cls];
+        m_ok = m < g.B * hw;
+        const int mm = m_ok ? m : 0;
+        const int bimg = mm / hw;
+        const int rem = mm - bimg * hw;
+        const int i = rem / par.Wc[t.cls], j = rem - i * par.Wc[t.cls];
+        m = (bimg * g.Hd + g.sh * i + par.oh[t.cls]) * g.Wd + g.sw * j + par.ow[t.cls];
+      }
+      if (m_ok) {
 #pragma unroll
         for (int j = 0; j < HALF / 4; ++j) {
           const int n = n0 + j * 4;
@@ -432,6 +499,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
     }
   }
   tc_teardown<BN>(tmem_base);
+}
+
+// host: parity classes of a strided dgrad geometry; returns false (par.nclass = 0) when not applicable
+static inline bool hs_make_parity(const Geom& g, HsParity& par) {
+  memset(&par, 0, sizeof(par));
+  if (g.mode != 1 || (g.sh == 1 && g.sw == 1) || g.sh * g.sw > 4 || g.Cs % HS_BK != 0) return false;
+  struct Cls { int oh, ow, Hc, Wc, ntap; signed char dh[HS_PAR_TAPS], dw[HS_PAR_TAPS]; unsigned char tap[HS_PAR_TAPS]; };
+  Cls cls[4];
+  int nc = 0;
+  for (int ch = 0; ch < g.sh; ++ch)
+    for (int cw = 0; cw < g.sw; ++cw) {
+      Cls c;
+      memset(&c, 0, sizeof(c));
+      c.oh = ((ch - g.ph) % g.sh + g.sh) % g.sh;
+      c.ow = ((cw - g.pw) % g.sw + g.sw) % g.sw;
+      c.Hc = c.oh < g.Hd ? (g.Hd - c.oh + g.sh - 1) / g.sh : 0;
+      c.Wc = c.ow < g.Wd ? (g.Wd - c.ow + g.sw - 1) / g.sw : 0;
+      if (c.Hc == 0 || c.Wc == 0) continue;
+      for (int kh = ch; kh < g.KH; kh += g.sh)
+        for (int kw = cw; kw < g.KW; kw += g.sw) {
+          if (c.ntap == HS_PAR_TAPS) return false;
+          const int dh = (c.oh + g.ph - kh) / g.sh, dw = (c.ow + g.pw - kw) / g.sw;  // exact divisions
+          if (dh < -127 || dh > 127 || dw < -127 || dw > 127) return false;
+          c.dh[c.ntap] = (signed char)dh; c.dw[c.ntap] = (signed char)dw;
+          c.tap[c.ntap] = (unsigned char)(kh * g.KW + kw);
+          ++c.ntap;
+        }
+      cls[nc++] = c;
+    }
+  if (nc == 0) return false;
+  for (int a = 0; a < nc; ++a)  // heaviest classes first (static round-robin tile schedule)
+    for (int b = a + 1; b < nc; ++b)
+      if (cls[b].ntap > cls[a].ntap) { Cls tmp = cls[a]; cls[a] = cls[b]; cls[b] = tmp; }
+  par.nclass = nc;
+  int tiles = 0;
+  for (int a = 0; a < nc; ++a) {
+    par.oh[a] = cls[a].oh; par.ow[a] = cls[a].ow; par.Hc[a] = cls[a].Hc; par.Wc[a] = cls[a].Wc;
+    par.ntap[a] = cls[a].ntap;
+    memcpy(par.dh[a], cls[a].dh, HS_PAR_TAPS); memcpy(par.dw[a], cls[a].dw, HS_PAR_TAPS);
+    memcpy(par.tap[a], cls[a].tap, HS_PAR_TAPS);
+    par.tile0[a] = tiles;
+    tiles += ceil_div(g.B * cls[a].Hc * cls[a].Wc, TC_BM);
+  }
+  par.tile0[nc] = tiles;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -460,6 +572,7 @@ struct HsWgradArgs {
   const uint32_t* i_bits;  // [0]
   float* partial;          // [split][nslots][N][Kd]
   int nsplit, nslots, slot0, m_per_split;
+  int debug;               // perf experiments only: 1 = producers skip the copies, 2 = no MMAs
 };
 
 constexpr int HSW_ROWS = 16;
@@ -559,6 +672,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
         const uint32_t sB = sA + 2 * HSW_A_BYTES;
+        if (p.debug & 1) {
+          mbar_arrive(full_bar(stage));
+          if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         hs_cp16(sA + offI, p.Ih + eoI, okI);
         hs_cp16(sA + HSW_A_BYTES + offI, p.Il + eoI, okI);
 #pragma unroll
@@ -598,13 +716,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
             const uint32_t sB = sA + 2 * HSW_A_BYTES;
             const uint64_t dAh = hs_mnmajor_desc(sA, 2048, 1024), dAl = hs_mnmajor_desc(sA + HSW_A_BYTES, 2048, 1024);
             const uint32_t accf = st != c0 ? 1u : 0u;
-            {
+            if (!(p.debug & 2)) {
               const uint64_t dBh = hs_mnmajor_desc(sB, 2048, 1024), dBl = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
               hs_mma_f16(tmem_base, dAl, dBh, idesc0, accf);
               hs_mma_f16(tmem_base, dAh, dBl, idesc0, 1u);
               hs_mma_f16(tmem_base, dAh, dBh, idesc0, 1u);
             }
-            if (n1 > 0) {
+            if (n1 > 0 && !(p.debug & 2)) {
               const uint64_t dBh = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
               const uint64_t dBl = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
               hs_mma_f16(tmem_base + 256u, dAl, dBh, idesc1, accf);
@@ -734,15 +852,19 @@ static inline int hs_launch_pack_image(const float* src, long long src_slot, __h
 }
 
 // returns 0 on success, >0 on a CUDA error, <0 if unavailable
-static inline int hs_launch_gather_gemm(const HsGatherArgs& a, int nslots, cudaStream_t st) {
+static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cudaStream_t st,
+                                        bool allow_parity = true) {
   if (hs_ready() <= 0) return -1;
   const int sms = tc_sm_count();
+  HsGatherArgs a = a_in;
   const Geom& g = a.g;
+  if (!allow_parity || !hs_make_parity(g, a.par)) a.par.nclass = 0;
+  const int tiles_m = a.par.nclass > 0 ? a.par.tile0[a.par.nclass] : ceil_div(g.M, TC_BM);
   if (tc_bn(g.Nd) == 128) {
-    const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 128) * nslots;
+    const int ntiles = tiles_m * ceil_div(g.Nd, 128) * nslots;
     gather_gemm_hs<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
   } else {
-    const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, 64) * nslots;
+    const int ntiles = tiles_m * ceil_div(g.Nd, 64) * nslots;
     gather_gemm_hs<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -1,0 +1,31 @@
+"""Per-kernel time breakdown of ONE C2 step (GPU box) via CUPTI activity records (torch.profiler): every kernel
+on the device is recorded, including the library's own launches.  usage: python tools/gpu_step_profile.py [mode]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torchvision
+from torch.profiler import profile, ProfilerActivity
+from curvlinops_b200 import GGNLinearOperator, _capi as capi
+
+mode = int(sys.argv[1], 0) if len(sys.argv) > 1 else 1
+B, K = 128, 8
+torch.manual_seed(0)
+dev = torch.device("cuda")
+model = torchvision.models.resnet18().eval().to(dev)
+X, y = torch.rand(B, 3, 224, 224, device=dev), torch.randint(0, 1000, (B,), device=dev)
+params = dict(model.named_parameters())
+P = sum(p.numel() for p in params.values())
+V = torch.rand(P, K, device=dev)
+G = GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=B)
+capi.lib().curv_set_tensor_core_mode(mode)
+for _ in range(2):
+    out = G @ V
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    out = G @ V
+    torch.cuda.synchronize()
+rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
+rows.sort(key=lambda r: -r[2])
+tot = sum(r[2] for r in rows)
+print(f"# one C2 step (ResNet-18, B=128, K=8, fp32), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
+for k, n, ms in rows[:40]:
+    print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:110]}")

@@ -218,6 +218,8 @@ static void test_wgrad(const char* name, Geom g, int NS, int slot0, int nsplit) 
 }
 
 // timing of the kernels at ResNet-18 shapes (B = 128, K = 8); no reference, prints ms and algorithmic TFLOP/s
+static int g_debug = 0;
+static int g_reps = 3;  // 0: one launch per kernel, no warm-up (ncu capture)
 static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, int stride) {
   const int K = 8, pad = k / 2;
   Geom f = conv_geom(B, H, H, C, Cout, k, stride, pad);
@@ -245,12 +247,13 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto timeit = [&](auto fn) {
-    fn(); CK(cudaDeviceSynchronize());
+    if (g_reps > 0) { fn(); CK(cudaDeviceSynchronize()); }
+    const int reps = g_reps > 0 ? g_reps : 1;
     cudaEventRecord(e0);
-    for (int i = 0; i < 3; ++i) fn();
+    for (int i = 0; i < reps; ++i) fn();
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    return ms / 3;
+    return ms / reps;
   };
   const double F = 2.0 * f.M * Cout * f.Kd;
   // split pass (absmax + split of 1+K input slots)
@@ -261,17 +264,17 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
   HsGatherArgs a;
   memset(&a, 0, sizeof(a));
   a.g = f; a.Ah = Ah; a.Al = Al; a.A_slot = a_elems; a.a_has_slots = 1; a.a_bits = abits; a.W_img = Wimg;
-  a.Wt_img = Wimg + img; a.Wt_img_slot = img; a.w_bits = wbits; a.out = dO; a.out_slot = o_elems;
+  a.Wt_img = Wimg + img; a.Wt_img_slot = img; a.w_bits = wbits; a.out = dO; a.out_slot = o_elems; a.debug = g_debug;
   float t_fwd = timeit([&] { hs_launch_gather_gemm(a, 1 + K, 0); });
   HsGatherArgs d;
   memset(&d, 0, sizeof(d));
   d.g = q; d.Ah = Oh; d.Al = Ol; d.A_slot = o_elems; d.a_slot_base = 1; d.a_has_slots = 1; d.a_bits = obits;
-  d.W_img = Wtimg; d.w_bits = wbits; d.out = dA; d.out_slot = a_elems; d.slot0 = 1;
+  d.W_img = Wtimg; d.w_bits = wbits; d.out = dA; d.out_slot = a_elems; d.slot0 = 1; d.debug = g_debug;
   float t_dgr = timeit([&] { hs_launch_gather_gemm(d, K, 0); });
   HsWgradArgs w;
   memset(&w, 0, sizeof(w));
   w.g = f; w.Gh = Oh; w.Gl = Ol; w.G_slot = o_elems; w.Ng = Cout; w.g_bits = obits; w.Ih = Ah; w.Il = Al;
-  w.i_bits = abits; w.partial = dpart; w.nslots = K; w.slot0 = 1; w.m_per_split = mps; w.nsplit = ceil_div(f.M, mps);
+  w.i_bits = abits; w.partial = dpart; w.nslots = K; w.slot0 = 1; w.m_per_split = mps; w.nsplit = ceil_div(f.M, mps); w.debug = g_debug;
   float t_wgr = timeit([&] { hs_launch_wgrad(w, 0); });
   printf("%-28s split %6.3f ms | fwd(1+2K) %7.3f ms %6.1f TF/s | dgrad(K) %7.3f ms %6.1f TF/s | wgrad(K) %7.3f ms %6.1f TF/s\n",
          name, t_split, t_fwd, F * (1 + 2 * K) / t_fwd / 1e9, t_dgr, F * K / t_dgr / 1e9, t_wgr, F * K / t_wgr / 1e9);
@@ -281,6 +284,8 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
 
 int main(int argc, char** argv) {
   const int which = argc > 1 ? atoi(argv[1]) : 3;
+  g_debug = argc > 2 ? atoi(argv[2]) : 0;
+  if (g_debug) printf("debug knob = %d (timings only, results invalid)\n", g_debug);
   if (hs_ready() <= 0) { printf("half-split kernels unavailable on this device\n"); return 1; }
   if (which & 1) {
     // forward, Cin = 64 (fast path), BN = 64: primal + 2 tangents with both segments
@@ -298,6 +303,8 @@ int main(int argc, char** argv) {
     // dgrad stride 2 (generic addressing), accumulate
     test_gather("dgrad 3x3 s2 C64<-128, slots 1..2, acc", dgrad_geom(conv_geom(2, 14, 14, 64, 128, 3, 2, 1)), 2, 1, 0, 1, 1, 0);
     test_gather("dgrad 1x1 s2 C64<-128, slots 1..2", dgrad_geom(conv_geom(2, 14, 14, 64, 128, 1, 2, 0)), 2, 1, 0, 1, 0, 0);
+    test_gather("dgrad 3x3 s2 C24<-40 (generic strided)", dgrad_geom(conv_geom(2, 11, 11, 24, 40, 3, 2, 1)), 2, 1, 0, 1, 0, 0);
+    test_gather("dgrad 3x3 s2 p1 C64<-64 odd size, parity", dgrad_geom(conv_geom(2, 15, 13, 64, 64, 3, 2, 1)), 2, 1, 0, 1, 1, 0);
     // many tiles: persistent loop with more tiles than SMs
     test_gather("fwd 3x3 s1 C64->64, K=8, big M", conv_geom(8, 28, 28, 64, 64, 3, 1, 1), 8, 1, 1, 0, 0, 0);
   }
@@ -308,6 +315,11 @@ int main(int argc, char** argv) {
     test_wgrad("wgrad 1x1 s2 C64->128 NS=4", conv_geom(2, 14, 14, 64, 128, 1, 2, 0), 4, 0, 2);
     test_wgrad("wgrad 3x3 s1 C24->40 NS=1 (ragged)", conv_geom(2, 9, 9, 24, 40, 3, 1, 1), 1, 1, 2);
     test_wgrad("wgrad 3x3 s1 C64->64 NS=8 long (flush)", conv_geom(8, 36, 36, 64, 64, 3, 1, 1), 8, 1, 2);
+  }
+  if (which & 8) {  // ncu capture: one launch per kernel
+    g_reps = 0;
+    bench_layer("layer1 3x3 C64->64 @56", 128, 56, 64, 64, 3, 1);
+    bench_layer("layer3 3x3 C256->256 @14", 128, 14, 256, 256, 3, 1);
   }
   if (which & 4) {
     bench_layer("layer1 3x3 C64->64 @56", 128, 56, 64, 64, 3, 1);
