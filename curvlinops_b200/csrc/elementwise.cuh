@@ -549,20 +549,28 @@ __global__ void vec_grad_finish_kernel(const float* __restrict__ partial, int nc
 __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nsplit, int nslots,
                                     int kskip, int N, int C, int Cp, int taps, float* __restrict__ out,
                                     long long off, int ldk, int k0, float alpha) {
+  // block = (32 weight elements, nslots - kskip columns): a warp reads 128 contiguous bytes of one slot's
+  // partial per split; the splits are summed in a fixed order with four independent chains (deterministic).
   const long long per = (long long)N * taps * Cp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
-       i += (long long)gridDim.x * blockDim.x) {
+  const int k = kskip + threadIdx.y;
+  const long long stride = (long long)nslots * per;
+  for (long long i = blockIdx.x * 32LL + threadIdx.x; i < per; i += (long long)gridDim.x * 32) {
     int c = (int)(i % Cp);
     if (c >= C) continue;
     long long r = i / Cp;
     int tap = (int)(r % taps);
     int n = (int)(r / taps);
-    float* o = out + (off + ((long long)n * C + c) * taps + tap) * ldk + k0;
-    for (int k = kskip; k < nslots; ++k) {
-      float s = 0.f;
-      for (int sp = 0; sp < nsplit; ++sp) s += __ldg(partial + ((long long)sp * nslots + k) * per + i);
-      o[k - kskip] += alpha * s;
+    const float* q = partial + (long long)k * per + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= nsplit; sp += 4) {
+      s0 += __ldg(q + (long long)sp * stride);
+      s1 += __ldg(q + (long long)(sp + 1) * stride);
+      s2 += __ldg(q + (long long)(sp + 2) * stride);
+      s3 += __ldg(q + (long long)(sp + 3) * stride);
     }
+    for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
+    out[(off + ((long long)n * C + c) * taps + tap) * ldk + k0 + k - kskip] += alpha * ((s0 + s1) + (s2 + s3));
   }
 }
 

@@ -201,6 +201,12 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         int maxsplit = ceil_div(g.M, 512);
         n.nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
         if (n.nsplit > 64) n.nsplit = 64;
+        if (!(hessian & 1)) {
+          // multi-slot kernels: at most 2048 pixels (384 MMAs per accumulator on the fp16 path) per split, so the
+          // tensor core's truncating accumulation stays below ~1e-5 and no tile needs an in-kernel TMEM flush
+          const int by_len = ceil_div(g.M, 2048);
+          if (by_len > n.nsplit) n.nsplit = by_len;
+        }
         n.m_per_split = (ceil_div(g.M, n.nsplit) + 15) / 16 * 16;
         n.nsplit = ceil_div(g.M, n.m_per_split);
         long long need = (long long)n.nsplit * nsl * n.wsize;
@@ -768,7 +774,7 @@ static int backward(const Ctx& c, int K) {
             if (hs_launch_wgrad(h, st)) return fail(CURV_ERR_CUDA, "half-split wgrad GEMM launch failed");
             ++g_launches;
           }
-          wgrad_finish_kernel<<<grid1d(n.wsize), 256, 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
+          wgrad_finish_kernel<<<grid1d(n.wsize, 32), dim3(32, ns - kskip), 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
                                                               vi.Cp, g.KH * g.KW, c.out,
                                                               P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
           LAUNCH_CHECK();
@@ -783,7 +789,7 @@ static int backward(const Ctx& c, int K) {
           a.m_per_split = n.m_per_split;
           int rc = launch_wgrad(a, n.wbm, n.wbn, st, conv_flops(g, vi.C) * ns * (a.second_seg ? 2 : 1));
           if (rc) return rc;
-          wgrad_finish_kernel<<<grid1d(n.wsize), 256, 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
+          wgrad_finish_kernel<<<grid1d(n.wsize, 32), dim3(32, ns - kskip), 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
                                                               vi.Cp, g.KH * g.KW, c.out,
                                                               P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
           LAUNCH_CHECK();

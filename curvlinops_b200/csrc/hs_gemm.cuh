@@ -19,6 +19,7 @@
 //   gather_gemm_hs<BN>                   forward conv + tangents, dgrad   (contract of gather_gemm_tc)
 //   wgrad_gemm_hs                        weight gradients of all K slots  (contract of wgrad_gemm_tc_ms)
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -553,7 +554,7 @@ static inline bool hs_make_parity(const Geom& g, HsParity& par) {
 //   side by side (N = 64 * slots-in-group <= 256), MN-major, so ONE MMA feeds 4 accumulators and the A tile
 //   is read from shared memory once per 4 slots.  The 8 accumulators [128 x 64] fill the 512 TMEM columns.
 //   stage = 16 pixels (one K = 16 MMA step), 40 KB:
-//     [In hi 4K][In lo 4K][G hi grp0 8K][G lo grp0 8K][G hi grp1 8K][G lo grp1 8K]
+//     [In hi 4K][In lo 4K][G hi: 8 slots x 2K][G lo: 8 slots x 2K]      (slot group g = slots 4g .. 4g+3)
 //   MN-major SWIZZLE_128B: chunk c (16 B = 8 elements) of pixel row r of MN atom a (64 elements) at
 //     a*2048 + (r>>3)*1024 + (r&7)*128 + ((c ^ (r&7)) << 4)          (LBO = 2048, SBO = 1024)
 // TMEM is single-buffered; every HSW_FLUSH stages (4096 pixels) the epilogue adds the chunk into the split's
@@ -573,6 +574,11 @@ struct HsWgradArgs {
   float* partial;          // [split][nslots][N][Kd]
   int nsplit, nslots, slot0, m_per_split;
   int debug;               // perf experiments only: 1 = producers skip the copies, 2 = no MMAs
+  // TMA path of the G operand (set by hs_launch_wgrad): 3-d tiled maps (Ng, M, slots) of the two planes, box
+  // (64 channels, 16 pixels, all slots) with SWIZZLE_128B = per slot one MN atom x two K atoms of the stage.
+  int use_tma;
+  alignas(64) CUtensorMap tmGh;
+  alignas(64) CUtensorMap tmGl;
 };
 
 constexpr int HSW_ROWS = 16;
@@ -583,7 +589,16 @@ constexpr int HSW_STAGES = 5;
 constexpr int HSW_FLUSH = 256;
 constexpr int HSW_SMEM_BYTES = HSW_STAGES * HSW_STAGE_BYTES + 1024 + 256;
 
-__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs p) {
+// 3-d tiled TMA load global -> shared, completion on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void hs_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_constant__ HsWgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = sbase + HSW_STAGES * HSW_STAGE_BYTES;
@@ -600,7 +615,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
   const int ntiles = tiles_i * tiles_j * p.nsplit;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < HSW_STAGES; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < HSW_STAGES; ++s) {
+      // TMA mode: 32 lanes of the stage's gather warp + the expect_tx arrival of the TMA issuer
+      mbar_init(full_bar(s), p.use_tma ? 33 : TC_PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -628,7 +647,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
     return ceil_div(max(0, me - mb), HSW_ROWS);
   };
 
-  if (warp >= 5 && warp < 13) {
+  if (warp >= 5 && warp < 13 && p.use_tma) {
+    // ------------------------------------------------------------------ producers, TMA mode
+    // warp 5, lane 0: the G tiles of every stage by TMA (one box per plane: 64 channels x 16 pixels x NS slots).
+    // warps 6-10    : the gathered-input tile, ONE WARP PER RING SLOT (stage q of this CTA belongs to warp
+    //                 q % HSW_STAGES, i.e. a warp always refills the same smem slot: it sees every phase of that
+    //                 slot's barriers in order, which parity waits require), so the address arithmetic of a
+    //                 stage (pixel decode, bounds) is paid once per 16 copies and a warp has HSW_STAGES stage
+    //                 periods to hide its latency.  Warps 11-12 idle.
+    //                 lane -> pixel row lane >> 1, column half lane & 1 (64 columns = 8 chunks, both planes).
+    if (warp == 5) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)NS * 2u * 2048u;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          int split, i0, j0;
+          decode_tile(tile, split, i0, j0);
+          const int mb = split * p.m_per_split;
+          const int nst = stages_of(split);
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sB = sbase + stage * HSW_STAGE_BYTES + 2 * HSW_A_BYTES;
+            if (p.debug & 1) {
+              mbar_arrive(full_bar(stage));
+            } else {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)),
+                           "r"(bytes)
+                           : "memory");
+              hs_tma_load_3d(sB, &p.tmGh, j0, mb + st * HSW_ROWS, 0, full_bar(stage));
+              hs_tma_load_3d(sB + 2 * HSW_B_BYTES, &p.tmGl, j0, mb + st * HSW_ROWS, 0, full_bar(stage));
+            }
+            if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp < 6 + HSW_STAGES) {
+      const int gw = warp - 6;               // ring slot owned by this warp
+      const int ir = lane >> 1, half = lane & 1;
+      const bool uniform = (g.Cs % 64) == 0;  // the 64 columns of a half lie inside one filter tap
+      const uint32_t offRow = (uint32_t)(half * 2048 + (ir >> 3) * 1024 + (ir & 7) * 128);
+      int q0 = 0;  // stages of this CTA before the current tile
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int split, i0, j0;
+        decode_tile(tile, split, i0, j0);
+        const int mb = split * p.m_per_split;
+        const int me = min(g.M, mb + p.m_per_split);
+        const int nst = stages_of(split);
+        const int col0 = i0 + half * 64;
+        int tap0 = 0, ic0 = 0, kh0 = 0, kw0 = 0;
+        if (uniform && col0 < g.Kd) { tap0 = col0 / g.Cs; ic0 = col0 - tap0 * g.Cs; kh0 = tap0 / g.KW; kw0 = tap0 - kh0 * g.KW; }
+        int st = (gw - q0 % HSW_STAGES + HSW_STAGES) % HSW_STAGES;  // first stage of this tile owned by this warp
+        for (; st < nst; st += HSW_STAGES) {
+          const int q = q0 + st;
+          const int stage = gw;
+          const uint32_t phase = (uint32_t)((q / HSW_STAGES) & 1);
+          const int mi = mb + st * HSW_ROWS + ir;
+          const bool mok = mi < me;
+          const int mm = mok ? mi : 0;
+          const int bimg = mm / (g.Hd * g.Wd);
+          const int rem = mm - bimg * (g.Hd * g.Wd);
+          const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+          const int h0 = hd * g.sh - g.ph, w0 = wd * g.sw - g.pw;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sA = sbase + stage * HSW_STAGE_BYTES + offRow;
+          if (p.debug & 1) {
+            mbar_arrive(full_bar(stage));
+            continue;
+          }
+          if (uniform) {
+            const int hs = h0 + kh0, ws = w0 + kw0;
+            const bool ok = mok && col0 < g.Kd && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+            const long long eo = ok ? (((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + ic0 : 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t o = sA + (uint32_t)((c ^ (ir & 7)) << 4);
+              hs_cp16(o, p.Ih + eo + (ok ? c * 8 : 0), ok);
+              hs_cp16(o + HSW_A_BYTES, p.Il + eo + (ok ? c * 8 : 0), ok);
+            }
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              const int col = col0 + c * 8;
+              const int tap = col / g.Cs;
+              const int ic = col - tap * g.Cs;
+              const int kh = tap / g.KW, kw = tap - kh * g.KW;
+              const int hs = h0 + kh, ws = w0 + kw;
+              const bool ok = mok && col < g.Kd && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+              const long long eo = ok ? (((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + ic : 0;
+              const uint32_t o = sA + (uint32_t)((c ^ (ir & 7)) << 4);
+              hs_cp16(o, p.Ih + eo, ok);
+              hs_cp16(o + HSW_A_BYTES, p.Il + eo, ok);
+            }
+          }
+          hs_cp_arrive(full_bar(stage));
+        }
+        q0 += nst;
+      }
+    }
+  } else if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers (pure cp.async)
     const int pt = threadIdx.x - 5 * 32;
     // In operand: pixel row ir = pt >> 4, chunk ic = pt & 15 (columns i0 + 8 ic .. +7), both planes
@@ -683,7 +801,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
         for (int s = 0; s < 8; ++s) {
           if (s < NS) {
             // slot s: group s >> 2, MN atom s & 3 inside the group's plane
-            const uint32_t o = sB + (uint32_t)((s >> 2) * 2 * HSW_B_BYTES + gp * HSW_B_BYTES + (s & 3) * 2048) + offG;
+            const uint32_t o = sB + (uint32_t)(gp * 2 * HSW_B_BYTES + s * 2048) + offG;
             hs_cp16(o, Gplane + (long long)s * p.G_slot + eoG, okG);
           }
         }
@@ -717,17 +835,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const HsWgradArgs
             const uint64_t dAh = hs_mnmajor_desc(sA, 2048, 1024), dAl = hs_mnmajor_desc(sA + HSW_A_BYTES, 2048, 1024);
             const uint32_t accf = st != c0 ? 1u : 0u;
             if (!(p.debug & 2)) {
-              const uint64_t dBh = hs_mnmajor_desc(sB, 2048, 1024), dBl = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
-              hs_mma_f16(tmem_base, dAl, dBh, idesc0, accf);
-              hs_mma_f16(tmem_base, dAh, dBl, idesc0, 1u);
-              hs_mma_f16(tmem_base, dAh, dBh, idesc0, 1u);
-            }
-            if (n1 > 0 && !(p.debug & 2)) {
-              const uint64_t dBh = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
-              const uint64_t dBl = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
-              hs_mma_f16(tmem_base + 256u, dAl, dBh, idesc1, accf);
-              hs_mma_f16(tmem_base + 256u, dAh, dBl, idesc1, 1u);
-              hs_mma_f16(tmem_base + 256u, dAh, dBh, idesc1, 1u);
+              // the two slot groups accumulate into independent TMEM regions: interleave them so that consecutive
+              // MMAs never depend on each other's accumulator
+              const uint64_t dBh0 = hs_mnmajor_desc(sB, 2048, 1024), dBl0 = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
+              const uint64_t dBh1 = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
+              const uint64_t dBl1 = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
+              hs_mma_f16(tmem_base, dAl, dBh0, idesc0, accf);
+              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAl, dBh1, idesc1, accf);
+              hs_mma_f16(tmem_base, dAh, dBl0, idesc0, 1u);
+              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBl1, idesc1, 1u);
+              hs_mma_f16(tmem_base, dAh, dBh0, idesc0, 1u);
+              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBh1, idesc1, 1u);
             }
             tc_commit(empty_bar(stage));
             if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
@@ -870,10 +988,52 @@ static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cu
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-static inline int hs_launch_wgrad(const HsWgradArgs& a, cudaStream_t st) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda,
+// so the library still loads (and reports "no CUDA device") on a machine without a driver
+typedef CUresult (*hs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill);
+static inline hs_encode_tiled_fn hs_encode_tiled() {
+  static hs_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<hs_encode_tiled_fn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 3-d tiled tensor map over an fp16 plane [slots][rows][width] with box (64, 16, slots), SWIZZLE_128B
+static inline bool hs_make_plane_map(CUtensorMap* map, const __half* base, int width, long long rows, int slots,
+                                     long long slot_stride_elems) {
+  hs_encode_tiled_fn enc = hs_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)slots};
+  const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)slot_stride_elems * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)HSW_ROWS, (cuuint32_t)slots};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (slots > 1 && strides[1] % 16 != 0) return false;
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline int hs_launch_wgrad(const HsWgradArgs& a_in, cudaStream_t st, bool allow_tma = true) {
   if (hs_ready() <= 0) return -1;
-  if (a.nslots < 1 || a.nslots > 8) return -1;
+  if (a_in.nslots < 1 || a_in.nslots > 8) return -1;
   const int sms = tc_sm_count();
+  HsWgradArgs a = a_in;
+  a.use_tma = 0;
+  if (allow_tma && a.g.M >= HSW_ROWS &&
+      hs_make_plane_map(&a.tmGh, a.Gh, a.Ng, a.g.M, a.nslots, a.G_slot) &&
+      hs_make_plane_map(&a.tmGl, a.Gl, a.Ng, a.g.M, a.nslots, a.G_slot))
+    a.use_tma = 1;
   const int ntiles = ceil_div(a.g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nsplit;
   wgrad_gemm_hs<<<ntiles < sms ? ntiles : sms, TC_THREADS, HSW_SMEM_BYTES, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
