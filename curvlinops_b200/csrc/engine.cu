@@ -607,7 +607,7 @@ static int forward(const Ctx& c, const void* X, int K) {
           h.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; h.bias_slot = vo.Cp;
           h.out = c.act(d.out); h.out_slot = vo.slot_elems; h.slot0 = 0; h.accumulate = 0;
           ProfScope prof(0, fl, st);
-          if (hs_launch_gather_gemm(h, nsl, st)) return fail(CURV_ERR_CUDA, "half-split gather GEMM launch failed");
+          if (hs_launch_gather_gemm(h, nsl, st, true, nin)) return fail(CURV_ERR_CUDA, "half-split gather GEMM launch failed");
           ++g_launches;
           break;
         }
@@ -816,7 +816,7 @@ static int backward(const Ctx& c, int K) {
           h.out = c.grad(d.in0); h.out_slot = vi.slot_elems; h.slot0 = s0; h.accumulate = ginit[d.in0];
           {
             ProfScope prof(0, conv_flops(g, vi.C) * ns, st);
-            if (hs_launch_gather_gemm(h, ns, st)) return fail(CURV_ERR_CUDA, "half-split dgrad GEMM launch failed");
+            if (hs_launch_gather_gemm(h, ns, st, true, ns)) return fail(CURV_ERR_CUDA, "half-split dgrad GEMM launch failed");
             ++g_launches;
           }
           ginit[d.in0] = 1;

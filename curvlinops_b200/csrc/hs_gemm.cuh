@@ -23,6 +23,8 @@
 #include <cuda_fp16.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "tc_gemm.cuh"
 
 namespace curv {
@@ -221,6 +223,15 @@ struct HsGatherArgs {
   int accumulate;
   int debug;  // perf experiments only: 1 = producers skip the copies, 2 = the MMA lane skips the MMAs
   HsParity par;
+  // TMA im2col path of the gathered operand (set by hs_launch_gather_gemm when Cs % 64 == 0): 4-d im2col maps
+  // (C, W, H, slots*B) of the two planes, one pair per parity class (class 0 = the whole tensor otherwise):
+  // box = 64 channels x 128 pixels, SWIZZLE_128B = exactly the K-major A tile of a stage.  The tile's first
+  // pixel is (w, h) = (tma_w0 + x*tma_sw, tma_h0 + y*tma_sh) for destination / class coordinates (x, y);
+  // the filter tap enters as the instruction's im2col offsets (tma_offw/h; per class in parity mode).
+  int use_tma;
+  int tma_w0[4], tma_h0[4], tma_sw, tma_sh;
+  unsigned char tma_offw[4][HS_PAR_TAPS], tma_offh[4][HS_PAR_TAPS];
+  alignas(64) CUtensorMap tmA[4][2];  // [class][plane]
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -231,8 +242,18 @@ struct HsGatherArgs {
 // ---------------------------------------------------------------------------------------------------
 struct HsTile { int slot, m0, tn, cls, T; };  // T = K stages per segment
 
+// 4-d im2col TMA load global -> shared, completion on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void hs_tma_load_im2col(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n,
+                                                   unsigned short offw, unsigned short offh, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"(offw), "h"(offh)
+      : "memory");
+}
+
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherArgs p, int nslots) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_constant__ HsGatherArgs p, int nslots) {
   using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -246,7 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
   const int ntiles = tiles_m * tiles_n * nslots;
   const int nchunks = ceil_div(g.Kd, HS_BK);
   const int cpt = g.Cs / HS_BK;  // K stages per filter tap (parity mode)
-  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, TC_PRODUCERS + 1);
+  // full barrier: TMA mode = the single expect_tx arrival of the issuing thread
+  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
 
   auto decode_tile = [&](int tile, HsTile& t) {
     const int si = tile % nslots;
@@ -272,7 +294,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
     else { a_slot = 0; w_id = slot; }
   };
 
-  if (warp >= 5 && warp < 13) {
+  if (warp >= 5 && warp < 13 && p.use_tma == 1) {
+    // ------------------------------------------------------------------ producer, TMA mode: ONE thread
+    // per stage: two im2col boxes (hi / lo plane: 128 pixels x 64 channels of one filter tap) + the weight block
+    if (warp == 5 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = 2 * Cfg::A_BYTES + 2 * Cfg::B_BYTES;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        HsTile t;
+        decode_tile(tile, t);
+        const int nseg = num_segments(t.slot);
+        // first pixel of the tile in destination (or class) coordinates
+        int x, y, bimg;
+        if (parity) {
+          const int hw = par.Hc[t.cls] * par.Wc[t.cls];
+          bimg = t.m0 / hw;
+          const int rem = t.m0 - bimg * hw;
+          y = rem / par.Wc[t.cls]; x = rem - y * par.Wc[t.cls];
+        } else {
+          bimg = t.m0 / (g.Hd * g.Wd);
+          const int rem = t.m0 - bimg * (g.Hd * g.Wd);
+          y = rem / g.Wd; x = rem - y * g.Wd;
+        }
+        const int w0 = p.tma_w0[t.cls] + x * p.tma_sw, h0 = p.tma_h0[t.cls] + y * p.tma_sh;
+        for (int seg = 0; seg < nseg; ++seg) {
+          int a_slot, w_id;
+          segment_ids(t.slot, seg, a_slot, w_id);
+          const int n0 = (a_slot - p.a_slot_base) * g.B + bimg;
+          const __half* Wimg = (w_id == 0) ? p.W_img : p.Wt_img + (long long)(w_id - 1) * p.Wt_img_slot;
+          int ti = 0, cb = 0;  // tap position (in the class list / kh*KW + kw), channel chunk
+          for (int kc = 0; kc < t.T; ++kc) {
+            const int wblk = parity ? par.tap[t.cls][ti] * cpt + cb / HS_BK : kc;
+            mbar_wait(S.empty(stage), phase ^ 1);
+            if (p.debug & 1) {
+              mbar_arrive(S.full(stage));
+            } else {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
+                           "r"(bytes)
+                           : "memory");
+              const uint32_t sA = S.stageA(stage);
+              const unsigned short ow = p.tma_offw[t.cls][ti], oh = p.tma_offh[t.cls][ti];
+              hs_tma_load_im2col(sA, &p.tmA[t.cls][0], cb, w0, h0, n0, ow, oh, S.full(stage));
+              hs_tma_load_im2col(sA + Cfg::A_BYTES, &p.tmA[t.cls][1], cb, w0, h0, n0, ow, oh, S.full(stage));
+              const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (2 * BN * HS_BK);
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      S.stageB(stage)),
+                  "l"(wsrc), "r"((uint32_t)(2 * Cfg::B_BYTES)), "r"(S.full(stage))
+                  : "memory");
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            cb += HS_BK;
+            if (cb >= g.Cs) { cb = 0; ++ti; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 5 && warp < 13) {
     // ------------------------------------------------------------------ producers (pure cp.async)
     const int pt = threadIdx.x - 5 * 32;     // 0..255
     const int a_c = pt & 7, a_r0 = pt >> 3;  // chunk a_c (8 channels) of rows a_r0 + 32 i
@@ -312,6 +392,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
         }
         if (!m_ok[i]) ah[i] = -(1 << 20);  // fails every bounds test
       }
+      // hybrid mode (use_tma == 2): the hi plane of the stage comes by TMA im2col (thread 0), only the lo plane
+      // by cp.async: the two paths have separate throughput limits (TMA row rate / LSU miss path)
+      const bool hybrid = p.use_tma == 2;
+      int tw0 = 0, th0 = 0, tb = 0;
+      if (hybrid && pt == 0) {
+        int x, y;
+        if (parity) {
+          const int hw = par.Hc[t.cls] * par.Wc[t.cls];
+          tb = t.m0 / hw;
+          const int rem = t.m0 - tb * hw;
+          y = rem / par.Wc[t.cls]; x = rem - y * par.Wc[t.cls];
+        } else {
+          tb = t.m0 / (g.Hd * g.Wd);
+          const int rem = t.m0 - tb * (g.Hd * g.Wd);
+          y = rem / g.Wd; x = rem - y * g.Wd;
+        }
+        tw0 = p.tma_w0[t.cls] + x * p.tma_sw; th0 = p.tma_h0[t.cls] + y * p.tma_sh;
+      }
       for (int seg = 0; seg < nseg; ++seg) {
         int a_slot, w_id;
         segment_ids(t.slot, seg, a_slot, w_id);
@@ -343,8 +441,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
             const uint32_t bytes = 2 * Cfg::B_BYTES;
             const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (2 * BN * HS_BK);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
-                         "r"(bytes)
+                         "r"(bytes + (hybrid ? (uint32_t)Cfg::A_BYTES : 0u))
                          : "memory");
+            if (hybrid)
+              hs_tma_load_im2col(sA, &p.tmA[t.cls][0], cb, tw0, th0, (a_slot - p.a_slot_base) * g.B + tb,
+                                 p.tma_offw[t.cls][ti], p.tma_offh[t.cls][ti], S.full(stage));
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                     S.stageB(stage)),
@@ -366,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
               const bool ok = rok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
               const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
               const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
-              hs_cp16(o, Ah + eo, ok);
+              if (!hybrid) hs_cp16(o, Ah + eo, ok);
               hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
             }
           } else {  // strided dgrad, generic: source pixel = (dest + pad - tap) / stride when divisible
@@ -407,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const HsGatherAr
             const int T = min(TC_FLUSH, t.T - t0);
             for (int it = 0; it < T; ++it) {
               mbar_wait(S.full(stage), phase);
-              fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+              if (p.use_tma != 1) fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core reads
               tc_fence_after();
               const uint32_t sA = S.stageA(stage), sB = S.stageB(stage);
               const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
@@ -970,13 +1071,107 @@ static inline int hs_launch_pack_image(const float* src, long long src_slot, __h
 }
 
 // returns 0 on success, >0 on a CUDA error, <0 if unavailable
+typedef CUresult (*hs_encode_im2col_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline hs_encode_im2col_fn hs_encode_im2col() {
+  static hs_encode_im2col_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<hs_encode_im2col_fn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+// im2col map over an fp16 plane [images][H][W][C]: box = 64 channels x 128 pixels, base pixels inside
+// [lower, dim + upper) traversed with the given strides
+static inline bool hs_make_im2col_map(CUtensorMap* map, const __half* base, int C, int W, int H, long long images,
+                                      int lw, int lh, int uw, int uh, int sw, int sh) {
+  hs_encode_im2col_fn enc = hs_encode_im2col();
+  if (!enc) return false;
+  if (lw < -128 || lw > 127 || lh < -128 || lh > 127 || uw < -128 || uw > 127 || uh < -128 || uh > 127) return false;
+  if (sw < 1 || sw > 8 || sh < 1 || sh > 8 || images < 1 || images >= (1LL << 31)) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)images};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const int lower[2] = {lw, lh}, upper[2] = {uw, uh};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, lower, upper, 64,
+             TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fills the TMA fields of a (parity-resolved) argument block; false -> the cp.async producers are used
+static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
+  const Geom& g = a.g;
+  a.use_tma = 0;
+  if (g.Cs % HS_BK != 0 || a.A_slot != (long long)g.B * g.Hs * g.Ws * g.Cs) return false;
+  const long long images = (long long)a_plane_slots * g.B;
+  if (a.par.nclass > 0) {
+    for (int c = 0; c < a.par.nclass; ++c) {
+      if (a.par.ntap[c] == 0) continue;  // class without taps: never loaded
+      int lh = 127, lw = 127;
+      for (int t = 0; t < a.par.ntap[c]; ++t) { lh = std::min(lh, (int)a.par.dh[c][t]); lw = std::min(lw, (int)a.par.dw[c][t]); }
+      for (int t = 0; t < a.par.ntap[c]; ++t) {
+        a.tma_offh[c][t] = (unsigned char)(a.par.dh[c][t] - lh);
+        a.tma_offw[c][t] = (unsigned char)(a.par.dw[c][t] - lw);
+      }
+      a.tma_w0[c] = lw; a.tma_h0[c] = lh;
+      const int uw = a.par.Wc[c] - g.Ws + lw, uh = a.par.Hc[c] - g.Hs + lh;
+      for (int pl = 0; pl < 2; ++pl)
+        if (!hs_make_im2col_map(&a.tmA[c][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, lw, lh, uw, uh, 1, 1))
+          return false;
+    }
+    a.tma_sw = 1; a.tma_sh = 1;
+  } else if (g.mode == 0) {
+    if (g.KH * g.KW > HS_PAR_TAPS) return false;
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) { a.tma_offh[0][kh * g.KW + kw] = (unsigned char)kh; a.tma_offw[0][kh * g.KW + kw] = (unsigned char)kw; }
+    a.tma_w0[0] = -g.pw; a.tma_h0[0] = -g.ph; a.tma_sw = g.sw; a.tma_sh = g.sh;
+    for (int pl = 0; pl < 2; ++pl)
+      if (!hs_make_im2col_map(&a.tmA[0][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, -g.pw, -g.ph,
+                              g.pw - (g.KW - 1), g.ph - (g.KH - 1), g.sw, g.sh))
+        return false;
+  } else if (g.sh == 1 && g.sw == 1) {  // stride-1 dgrad: source = dest + pad - tap = (dest + lower) + (K-1-tap)
+    if (g.KH * g.KW > HS_PAR_TAPS) return false;
+    const int lw = -(g.KW - 1 - g.pw), lh = -(g.KH - 1 - g.ph);
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        a.tma_offh[0][kh * g.KW + kw] = (unsigned char)(g.KH - 1 - kh);
+        a.tma_offw[0][kh * g.KW + kw] = (unsigned char)(g.KW - 1 - kw);
+      }
+    a.tma_w0[0] = lw; a.tma_h0[0] = lh; a.tma_sw = 1; a.tma_sh = 1;
+    for (int pl = 0; pl < 2; ++pl)
+      if (!hs_make_im2col_map(&a.tmA[0][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, lw, lh, g.Wd - g.Ws + lw,
+                              g.Hd - g.Hs + lh, 1, 1))
+        return false;
+  } else {
+    return false;
+  }
+  a.use_tma = 1;
+  return true;
+}
+
+// producer mode of the gathered operand when TMA applies: 1 = both planes by TMA im2col, 2 = hybrid (hi plane by
+// TMA, lo plane by cp.async), 0 = cp.async only
+static int g_hs_gather_tma_mode = 1;
+
+// a_plane_slots: number of slots stored in the planes (bounds the TMA tensor); 0 -> no TMA
 static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cudaStream_t st,
-                                        bool allow_parity = true) {
+                                        bool allow_parity = true, int a_plane_slots = 0) {
   if (hs_ready() <= 0) return -1;
   const int sms = tc_sm_count();
   HsGatherArgs a = a_in;
   const Geom& g = a.g;
   if (!allow_parity || !hs_make_parity(g, a.par)) a.par.nclass = 0;
+  a.use_tma = 0;
+  if (a_plane_slots > 0 && g_hs_gather_tma_mode > 0 && hs_setup_gather_tma(a, a_plane_slots))
+    a.use_tma = g_hs_gather_tma_mode;
   const int tiles_m = a.par.nclass > 0 ? a.par.tile0[a.par.nclass] : ceil_div(g.M, TC_BM);
   if (tc_bn(g.Nd) == 128) {
     const int ntiles = tiles_m * ceil_div(g.Nd, 128) * nslots;

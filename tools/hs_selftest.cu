@@ -100,7 +100,7 @@ static void test_gather(const char* name, Geom g, int K, int a_has_slots, int wi
   a.a_bits = abits; a.W_img = Wimg; a.Wt_img = with_wt ? Wimg + img : nullptr; a.Wt_img_slot = img;
   a.w_bits = wbits; a.bias = with_bias ? dbias : nullptr; a.bias_t = with_bias ? dbias + g.Nd : nullptr;
   a.bias_slot = g.Nd; a.out = dout; a.out_slot = o_elems; a.slot0 = slot0; a.accumulate = accumulate;
-  int rc = hs_launch_gather_gemm(a, nslots, 0);
+  int rc = hs_launch_gather_gemm(a, nslots, 0, true, g_tma ? a_cnt : 0);
   if (rc) { printf("%s: launch rc=%d\n", name, rc); exit(3); }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(4); }
@@ -266,12 +266,12 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
   memset(&a, 0, sizeof(a));
   a.g = f; a.Ah = Ah; a.Al = Al; a.A_slot = a_elems; a.a_has_slots = 1; a.a_bits = abits; a.W_img = Wimg;
   a.Wt_img = Wimg + img; a.Wt_img_slot = img; a.w_bits = wbits; a.out = dO; a.out_slot = o_elems; a.debug = g_debug;
-  float t_fwd = timeit([&] { hs_launch_gather_gemm(a, 1 + K, 0); });
+  float t_fwd = timeit([&] { hs_launch_gather_gemm(a, 1 + K, 0, true, g_tma ? 1 + K : 0); });
   HsGatherArgs d;
   memset(&d, 0, sizeof(d));
   d.g = q; d.Ah = Oh; d.Al = Ol; d.A_slot = o_elems; d.a_slot_base = 1; d.a_has_slots = 1; d.a_bits = obits;
   d.W_img = Wtimg; d.w_bits = wbits; d.out = dA; d.out_slot = a_elems; d.slot0 = 1; d.debug = g_debug;
-  float t_dgr = timeit([&] { hs_launch_gather_gemm(d, K, 0); });
+  float t_dgr = timeit([&] { hs_launch_gather_gemm(d, K, 0, true, g_tma ? K : 0); });
   HsWgradArgs w;
   memset(&w, 0, sizeof(w));
   w.g = f; w.Gh = Oh; w.Gl = Ol; w.G_slot = o_elems; w.Ng = Cout; w.g_bits = obits; w.Ih = Ah; w.Il = Al;
@@ -287,6 +287,7 @@ int main(int argc, char** argv) {
   const int which = argc > 1 ? atoi(argv[1]) : 3;
   g_debug = argc > 2 ? atoi(argv[2]) : 0;
   g_tma = argc > 3 ? atoi(argv[3]) != 0 : true;
+  if (argc > 3) g_hs_gather_tma_mode = atoi(argv[3]);
   if (g_debug) printf("debug knob = %d (timings only, results invalid)\n", g_debug);
   if (hs_ready() <= 0) { printf("half-split kernels unavailable on this device\n"); return 1; }
   if (which & 1) {
