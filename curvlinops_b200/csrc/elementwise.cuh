@@ -20,6 +20,25 @@ __device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
   return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
 }
 
+// Fused absolute-maximum tracking for the half-split GEMM path (hs_gemm.cuh): a kernel that produces a GEMM operand
+// folds max|value| of everything it wrote into dst (uint bit pattern of a non-negative float; atomicMax is order
+// independent, hence deterministic).  One atomic per CTA.  Must be reached by all threads of the block.
+__device__ __forceinline__ float f4absmax(float m, const float4& v) {
+  return fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+__device__ __forceinline__ void block_absmax_commit(float m, unsigned int* dst) {
+  __shared__ float absmax_red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) absmax_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 1; w < nw; ++w) m = fmaxf(m, absmax_red[w]);
+    if (m > 0.f) atomicMax(dst, __float_as_uint(m));
+  }
+}
+
 // ------------------------------------------------------------------ layout / packing
 // X [B][C][H][W] -> out [B][H][W][Cp]
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int C,
@@ -134,8 +153,9 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
 __global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
                                   const float* __restrict__ coef, int coef_has_tan,
                                   float* __restrict__ y, long long y_slot, long long rows, int Cp,
-                                  int relu) {
+                                  int relu, unsigned int* __restrict__ amax) {
   const int slot = blockIdx.y;
+  float am = 0.f;
   const int C4 = Cp >> 2;
   const long long total = rows * C4;
   const float4* x0 = reinterpret_cast<const float4*>(x);
@@ -163,7 +183,9 @@ __global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot,
       }
     }
     yo[i] = r;
+    am = f4absmax(am, r);
   }
+  if (amax) block_absmax_commit(am, amax + slot);
 }
 
 __device__ __forceinline__ float act_apply(int kind, float x) {
@@ -250,8 +272,10 @@ __global__ void axpy_slots_kernel(const float* __restrict__ src, long long src_s
 // fused residual join + ReLU:  y_0 = relu(a_0 + b_0),  y_k = [a_0 + b_0 > 0] (a_k + b_k).  grid.y = slot
 __global__ void add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot, int a_has_slots,
                                     const float* __restrict__ b, long long b_slot, int b_has_slots,
-                                    float* __restrict__ y, long long y_slot, long long n4) {
+                                    float* __restrict__ y, long long y_slot, long long n4,
+                                    unsigned int* __restrict__ amax) {
   const int slot = blockIdx.y;
+  float am = 0.f;
   const float4* a0 = reinterpret_cast<const float4*>(a);
   const float4* b0 = reinterpret_cast<const float4*>(b);
   const float4* ak = reinterpret_cast<const float4*>(a + slot * a_slot);
@@ -270,7 +294,9 @@ __global__ void add_relu_fwd_kernel(const float* __restrict__ a, long long a_slo
       r = make_float4(p.x > 0.f ? r.x : 0.f, p.y > 0.f ? r.y : 0.f, p.z > 0.f ? r.z : 0.f, p.w > 0.f ? r.w : 0.f);
     }
     yo[i] = r;
+    am = f4absmax(am, r);
   }
+  if (amax) block_absmax_commit(am, amax + slot);
 }
 // adjoint: g = [y_0 > 0] gy_k ;  ga_k (+)= g ;  gb_k (+)= g   (either destination may be null)
 __global__ void add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
@@ -304,8 +330,9 @@ __global__ void zero_slots_kernel(float* __restrict__ dst, long long dst_slot, l
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot, float* __restrict__ y,
                                    long long y_slot, unsigned char* __restrict__ idx, int B, int Hs,
                                    int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh, int sw, int ph,
-                                   int pw, int slot0) {
+                                   int pw, int slot0, unsigned int* __restrict__ amax) {
   const int slot = slot0 + blockIdx.y;
+  float am = 0.f;
   const float4* xs = reinterpret_cast<const float4*>(x + slot * x_slot);
   float4* ys = reinterpret_cast<float4*>(y + slot * y_slot);
   uchar4* ix = reinterpret_cast<uchar4*>(idx);
@@ -338,6 +365,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot
       }
       ys[i] = best;
       ix[i] = bi;
+      am = f4absmax(am, best);
     } else {
       const uchar4 bi = ix[i];
       auto pick = [&](unsigned char t, int lane) {
@@ -352,20 +380,27 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot
         v = make_float4(pick(bi.x, 0), pick(bi.y, 1), pick(bi.z, 2), pick(bi.w, 3));
       }
       ys[i] = v;
+      am = f4absmax(am, v);
     }
   }
+  if (amax) block_absmax_commit(am, amax + slot);
 }
 
 // gx[pixel] (+)= sum over output windows whose argmax is this pixel of gy (gather form: deterministic).
-// One thread per (input pixel, 4 channels); only the <= ceil(K/s)^2 windows that contain the pixel are visited.
-__global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
-                                   float* __restrict__ gx, long long gx_slot,
-                                   const unsigned char* __restrict__ idx, int B, int Hs, int Ws, int Hd,
-                                   int Wd, int Cp, int KH, int KW, int sh, int sw, int ph, int pw,
-                                   int slot0, int accumulate) {
-  const int slot = slot0 + blockIdx.y;
-  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
-  float4* o = reinterpret_cast<float4*>(gx + slot * gx_slot);
+// One thread per (input pixel, 4 channels) and up to 8 cotangent slots (grid.y = groups of 8 slots): the window
+// arithmetic and the argmax bytes are shared by the slots; only the <= ceil(K/s)^2 windows that contain the
+// pixel are visited.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                                          float* __restrict__ gx, long long gx_slot,
+                                                          const unsigned char* __restrict__ idx, int B, int Hs,
+                                                          int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh,
+                                                          int sw, int ph, int pw, int slot0, int nslots,
+                                                          int accumulate) {
+  const int sfirst = blockIdx.y * 8;
+  const int ns = min(8, nslots - sfirst);
+  const float4* g = reinterpret_cast<const float4*>(gy + (long long)(slot0 + sfirst) * gy_slot);
+  float4* o = reinterpret_cast<float4*>(gx + (long long)(slot0 + sfirst) * gx_slot);
+  const long long g4 = gy_slot >> 2, o4 = gx_slot >> 2;
   const uchar4* ix = reinterpret_cast<const uchar4*>(idx);
   const unsigned C4 = (unsigned)Cp >> 2;
   const unsigned total = (unsigned)B * Hs * Ws * C4;  // 32-bit index arithmetic (checked on the host)
@@ -381,22 +416,36 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_sl
     int hd_hi = (hs + ph) / sh; if (hd_hi > Hd - 1) hd_hi = Hd - 1;
     int wd_lo = ws + pw - KW + 1; wd_lo = wd_lo <= 0 ? 0 : (wd_lo + sw - 1) / sw;
     int wd_hi = (ws + pw) / sw; if (wd_hi > Wd - 1) wd_hi = Wd - 1;
-    float4 acc = f4zero();
+    float4 acc[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) acc[s] = f4zero();
     for (int hd = hd_lo; hd <= hd_hi; ++hd) {
       const int kh = hs + ph - hd * sh;
       for (int wd = wd_lo; wd <= wd_hi; ++wd) {
         const int tap = kh * KW + (ws + pw - wd * sw);
         const size_t oi = ((size_t)(b * Hd + hd) * Wd + wd) * C4 + c4;
         const uchar4 t = __ldg(ix + oi);
-        const float4 v = __ldg(g + oi);
-        if (t.x == tap) acc.x += v.x;
-        if (t.y == tap) acc.y += v.y;
-        if (t.z == tap) acc.z += v.z;
-        if (t.w == tap) acc.w += v.w;
+        if (t.x != tap && t.y != tap && t.z != tap && t.w != tap) continue;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < ns) {
+            const float4 v = __ldg(g + s * g4 + oi);
+            if (t.x == tap) acc[s].x += v.x;
+            if (t.y == tap) acc[s].y += v.y;
+            if (t.z == tap) acc[s].z += v.z;
+            if (t.w == tap) acc[s].w += v.w;
+          }
+        }
       }
     }
-    if (accumulate) acc = f4add(acc, o[i]);
-    o[i] = acc;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (s < ns) {
+        float4 a = acc[s];
+        if (accumulate) a = f4add(a, o[s * o4 + i]);
+        o[s * o4 + i] = a;
+      }
+    }
   }
 }
 
@@ -449,8 +498,9 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
     const float* __restrict__ xdot, long long xdot_slot, const float* __restrict__ coef,
     const float* __restrict__ aux, float* __restrict__ gx, long long gx_slot, int write_gx,
     float* __restrict__ partial, int want_partial, long long rows, int Cp, int rows_per_cta,
-    int slot0, int nslots, int rop, int accumulate, int relu) {
+    int slot0, int nslots, int rop, int accumulate, int relu, unsigned int* __restrict__ amax) {
   extern __shared__ float red[];  // [RPP][2][ctile*4]
+  float am = 0.f;  // max |gx| written by this thread (amax: fused absmax for the half-split GEMMs)
   const int C4 = Cp >> 2;
   const int ctile4 = min(C4, 256);
   const int RPP = 256 / ctile4;
@@ -502,6 +552,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
           if (o) {
             if (accumulate) rr = f4add(rr, o[i]);
             o[i] = rr;
+            am = f4absmax(am, rr);
           }
         }
       }
@@ -528,6 +579,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
       __syncthreads();
     }
   }
+  if (amax) block_absmax_commit(am, amax + slot);
 }
 
 // out[(off + c)*ldk + k0 + k] += alpha * sum_chunks partial[chunk][k][which][c]

@@ -454,6 +454,13 @@ static int hs_absmax(const Ctx& c, const float* x, long long slot_stride, long l
   for (int i = 0; i < count; ++i) (*c.hs_valid)[entry + i] = 1;
   return CURV_OK;
 }
+// absmax entries [entry, entry + count) will be produced by the kernel about to be launched (fused tracking):
+// returns the bits pointer to hand to it (nullptr when the half-split path is off)
+static unsigned int* hs_fused_absmax(const Ctx& c, int entry, int count) {
+  if (!c.hs) return nullptr;
+  for (int i = 0; i < count; ++i) (*c.hs_valid)[entry + i] = 1;
+  return c.hsbits() + entry;
+}
 static int hs_split(const Ctx& c, const float* x, long long slot_stride, long long n, __half* hi, __half* lo,
                     int entry, int count) {
   ProfScope prof(2, 0, c.st);
@@ -633,7 +640,8 @@ static int forward(const Ctx& c, const void* X, int K) {
         long long rows = (long long)P->B * vi.H * vi.W;
         affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
-            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0);
+            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0,
+            hs_fused_absmax(c, c.bits_act(d.out), nsl));
         LAUNCH_CHECK();
         break;
       }
@@ -658,7 +666,7 @@ static int forward(const Ctx& c, const void* X, int K) {
         if (d.kh == 2) {  // fused residual join + ReLU
           add_relu_fwd_kernel<<<dim3(grid1d(n4), nsl), 256, 0, st>>>(
               c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.act(d.in1), vj.slot_elems, vj.tan ? 1 : 0,
-              c.act(d.out), vo.slot_elems, n4);
+              c.act(d.out), vo.slot_elems, n4, hs_fused_absmax(c, c.bits_act(d.out), nsl));
           LAUNCH_CHECK();
           break;
         }
@@ -691,12 +699,12 @@ static int forward(const Ctx& c, const void* X, int K) {
           return fail(CURV_ERR_UNSUPPORTED, "max-pool tensors beyond 2^33 elements per slot are not supported");
         maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems / 4), 1), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
-            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 0);
+            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 0, hs_fused_absmax(c, c.bits_act(d.out), nsl));
         LAUNCH_CHECK();
         if (nsl > 1) {
           maxpool_fwd_kernel<<<dim3(grid1d(vo.slot_elems / 4), nsl - 1), 256, 0, st>>>(
               c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
-              vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1);
+              vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1, c.hs ? c.hsbits() + c.bits_act(d.out) : nullptr);
           LAUNCH_CHECK();
         }
         break;
@@ -798,7 +806,7 @@ static int backward(const Ctx& c, int K) {
           long long rows = g.M;
           affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
               c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
-              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0);
+              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0, nullptr);
           LAUNCH_CHECK();
           vec_grad_finish_kernel<<<ceil_div(vo.C * K, 256), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 1, vo.C, vo.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
@@ -843,11 +851,18 @@ static int backward(const Ctx& c, int K) {
         long long rows = (long long)P->B * vi.H * vi.W;
         int want_partial = (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0;
         if (!vi.tan && !want_partial) break;
+        // the cotangent written here is final when this is its first (and then only) writer: its absmax feeds
+        // the half-split GEMMs of the producing conv (kernel indexes the bits by absolute slot)
+        unsigned int* amax = nullptr;
+        if (c.hs && vi.tan && !ginit[d.in0]) {
+          hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns);
+          amax = c.hsbits() + c.bits_grad(d.in0);
+        }
         affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
             c.grad(d.out), vo.slot_elems, c.act(d.in0), (rop && vi.tan) ? c.act(d.in0) : nullptr,
             vi.slot_elems, c.ws + n.coef_off, c.ws + n.aux_off, vi.tan ? c.grad(d.in0) : nullptr,
             vi.slot_elems, vi.tan ? 1 : 0, scratch, want_partial, rows, vi.Cp, n.rows_per_cta, s0, ns,
-            rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0);
+            rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0, amax);
         LAUNCH_CHECK();
         if (vi.tan) ginit[d.in0] = 1;
         if (d.p0 >= 0) {
@@ -906,9 +921,9 @@ static int backward(const Ctx& c, int K) {
       case CURV_OP_MAXPOOL: {
         if (!vi.tan) break;
         unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
-        maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems / 4), ns), 256, 0, st>>>(
+        maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems / 4), (ns + 7) / 8), 256, 0, st>>>(
             c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
-            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ginit[d.in0]);
+            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ns, ginit[d.in0]);
         LAUNCH_CHECK();
         ginit[d.in0] = 1;
         break;
