@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -151,6 +152,18 @@ __global__ void hs_pack_image_kernel(const float* __restrict__ src, long long sr
 // ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
+// one lane of the (converged) warp, chosen by the hardware: tcgen05.mma / commit are issued under this predicate
+// from warp-uniform control flow, which lets the compiler emit them without per-lane uniformisation loops
+__device__ __forceinline__ bool hs_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // 16-byte async copy global -> shared, zero fill when !ok (the source address is then never dereferenced)
 __device__ __forceinline__ void hs_cp16(uint32_t dst, const void* src, bool ok) {
   const uint32_t n = ok ? 16u : 0u;
@@ -222,6 +235,7 @@ struct HsGatherArgs {
   int slot0;
   int accumulate;
   int debug;  // perf experiments only: 1 = producers skip the copies, 2 = the MMA lane skips the MMAs
+  int flush;  // K stages per TMEM accumulation chunk (set by the launcher: g_hs_flush)
   HsParity par;
   // TMA im2col path of the gathered operand (set by hs_launch_gather_gemm when Cs % 64 == 0): 4-d im2col maps
   // (C, W, H, slots*B) of the two planes, one pair per parity class (class 0 = the whole tensor otherwise):
@@ -242,6 +256,56 @@ struct HsGatherArgs {
 // ---------------------------------------------------------------------------------------------------
 struct HsTile { int slot, m0, tn, cls, T; };  // T = K stages per segment
 
+// Shared-memory map of gather_gemm_hs: the stage ring of TcCfg<BN> plus a ring of NBUF = 512 / BN TMEM
+// accumulation buffers (all 512 tensor-memory columns): a chunk is drained by the epilogue while the MMAs of the
+// next NBUF - 1 chunks proceed, so the short accumulation chunks (TC_FLUSH stages, see tc_gemm.cuh) cost no
+// tensor-pipe time.
+template <int BN>
+struct HsSmem {
+  using Cfg = TcCfg<BN>;
+  static constexpr int NBUF = 512 / BN;
+  uint32_t base, bar_base;
+  __device__ explicit HsSmem(uint8_t* raw) {
+    base = (smem_u32(raw) + 1023u) & ~1023u;
+    bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  }
+  __device__ uint32_t full(int s) const { return bar_base + 8u * s; }
+  __device__ uint32_t empty(int s) const { return bar_base + 8u * (Cfg::STAGES + s); }
+  __device__ uint32_t tfull(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + a); }
+  __device__ uint32_t tempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + NBUF + a); }
+  __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NBUF); }
+  __device__ uint32_t stageA(int s) const { return base + s * Cfg::STAGE_BYTES; }
+  __device__ uint32_t stageB(int s) const { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; }
+};
+static_assert(8 * (2 * 4 + 2 * 8 + 1) <= 256, "barrier block of HsSmem must fit the 256 bytes reserved by TcCfg");
+
+template <int BN>
+__device__ __forceinline__ uint32_t hs_prologue(const HsSmem<BN>& S, uint8_t* raw, int full_count) {
+  using Cfg = TcCfg<BN>;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(S.full(s), full_count); mbar_init(S.empty(s), 1); }
+    for (int a = 0; a < HsSmem<BN>::NBUF; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(S.tmem_slot()), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(raw + (S.tmem_slot() - smem_u32(raw)));
+}
+__device__ __forceinline__ void hs_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // 4-d im2col TMA load global -> shared, completion on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void hs_tma_load_im2col(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int n,
                                                    unsigned short offw, unsigned short offh, uint32_t bar) {
@@ -256,8 +320,9 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_constant__ HsGatherArgs p, int nslots) {
   using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NBUF = HsSmem<BN>::NBUF;
   extern __shared__ uint8_t smem_raw[];
-  const TcSmem<BN> S(smem_raw);
+  const HsSmem<BN> S(smem_raw);
   const Geom& g = p.g;
   const HsParity& par = p.par;
   const bool parity = par.nclass > 0;
@@ -268,7 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
   const int nchunks = ceil_div(g.Kd, HS_BK);
   const int cpt = g.Cs / HS_BK;  // K stages per filter tap (parity mode)
   // full barrier: TMA mode = the single expect_tx arrival of the issuing thread
-  const uint32_t tmem_base = tc_prologue<BN>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
+  const uint32_t tmem_base = hs_prologue<BN>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
 
   auto decode_tile = [&](int tile, HsTile& t) {
     const int si = tile % nslots;
@@ -492,7 +557,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (uniform) loop and waits on the barriers; one elected lane issues the MMAs and
+    // the commits of a stage in one predicated block.
+    {
       constexpr uint32_t idesc = hs_idesc(BN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -501,31 +568,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
         decode_tile(tile, t);
         const int nseg = num_segments(t.slot);
         for (int seg = 0; seg < nseg; ++seg) {
-          for (int t0 = 0; t0 < t.T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
+          for (int t0 = 0; t0 < t.T; t0 += p.flush) {  // one TMEM accumulation chunk
             mbar_wait(S.tempty(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            const int T = min(TC_FLUSH, t.T - t0);
+            const int T = min(p.flush, t.T - t0);
             for (int it = 0; it < T; ++it) {
               mbar_wait(S.full(stage), phase);
-              if (p.use_tma != 1) fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core reads
               tc_fence_after();
               const uint32_t sA = S.stageA(stage), sB = S.stageB(stage);
               const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
               const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
+              if (hs_elect_one()) {
+                if (p.use_tma != 1) fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core reads
+                if (!(p.debug & 2)) {
 #pragma unroll
-              for (int ks = 0; ks < HS_BK / 16; ++ks) {
-                if (p.debug & 2) break;
-                const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
-                hs_mma_f16(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-                hs_mma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-                hs_mma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+                  for (int ks = 0; ks < HS_BK / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
+                    hs_mma_f16(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+                    hs_mma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+                    hs_mma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+                  }
+                }
+                tc_commit(S.empty(stage));                       // frees the smem stage when these MMAs retire
+                if (it + 1 == T) tc_commit(S.tfull(acc));        // chunk complete -> epilogue
               }
-              tc_commit(S.empty(stage));
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(S.tfull(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
           }
         }
       }
@@ -551,7 +622,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
         segment_ids(t.slot, seg, a_slot, w_id);
         const float inv = hs_pow2(-hs_shift_from_bits(__ldg(p.a_bits + a_slot)) -
                                   hs_shift_from_bits(__ldg(p.w_bits + w_id)));
-        for (int t0 = 0; t0 < t.T; t0 += TC_FLUSH) {
+        for (int t0 = 0; t0 < t.T; t0 += p.flush) {
           mbar_wait(S.tfull(acc), acc_phase);
           tc_fence_after();
 #pragma unroll
@@ -563,7 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
           }
           tc_fence_before();
           mbar_arrive(S.tempty(acc));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
         }
       }
       const float* bias = (t.slot == 0) ? p.bias
@@ -600,7 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
       }
     }
   }
-  tc_teardown<BN>(tmem_base);
+  hs_teardown(tmem_base);
 }
 
 // host: parity classes of a strided dgrad geometry; returns false (par.nclass = 0) when not applicable
@@ -912,7 +983,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // whole warp in the uniform loop, one elected lane issues the MMAs + commits of a stage (see gather_gemm_hs)
+    {
       const int n0 = NS >= 4 ? 256 : 64 * NS;            // N of slot group 0
       const int n1 = NS > 4 ? 64 * (NS - 4) : 0;         // N of slot group 1
       const uint32_t idesc0 = hs_idesc(n0, 1, 1);
@@ -929,29 +1001,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
           const int cend = min(nst, c0 + HSW_FLUSH);
           for (int st = c0; st < cend; ++st) {
             mbar_wait(full_bar(stage), phase);
-            fence_async_proxy();
             tc_fence_after();
             const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
             const uint32_t sB = sA + 2 * HSW_A_BYTES;
             const uint64_t dAh = hs_mnmajor_desc(sA, 2048, 1024), dAl = hs_mnmajor_desc(sA + HSW_A_BYTES, 2048, 1024);
+            // the two slot groups accumulate into independent TMEM regions: interleave them so that consecutive
+            // MMAs never depend on each other's accumulator
+            const uint64_t dBh0 = hs_mnmajor_desc(sB, 2048, 1024), dBl0 = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
+            const uint64_t dBh1 = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
+            const uint64_t dBl1 = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
             const uint32_t accf = st != c0 ? 1u : 0u;
-            if (!(p.debug & 2)) {
-              // the two slot groups accumulate into independent TMEM regions: interleave them so that consecutive
-              // MMAs never depend on each other's accumulator
-              const uint64_t dBh0 = hs_mnmajor_desc(sB, 2048, 1024), dBl0 = hs_mnmajor_desc(sB + 2 * HSW_B_BYTES, 2048, 1024);
-              const uint64_t dBh1 = hs_mnmajor_desc(sB + HSW_B_BYTES, 2048, 1024);
-              const uint64_t dBl1 = hs_mnmajor_desc(sB + 3 * HSW_B_BYTES, 2048, 1024);
-              hs_mma_f16(tmem_base, dAl, dBh0, idesc0, accf);
-              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAl, dBh1, idesc1, accf);
-              hs_mma_f16(tmem_base, dAh, dBl0, idesc0, 1u);
-              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBl1, idesc1, 1u);
-              hs_mma_f16(tmem_base, dAh, dBh0, idesc0, 1u);
-              if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBh1, idesc1, 1u);
+            if (hs_elect_one()) {
+              fence_async_proxy();  // cp.async (generic proxy) writes of the gathered tile -> tensor-core reads
+              if (!(p.debug & 2)) {
+                hs_mma_f16(tmem_base, dAl, dBh0, idesc0, accf);
+                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAl, dBh1, idesc1, accf);
+                hs_mma_f16(tmem_base, dAh, dBl0, idesc0, 1u);
+                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBl1, idesc1, 1u);
+                hs_mma_f16(tmem_base, dAh, dBh0, idesc0, 1u);
+                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBh1, idesc1, 1u);
+              }
+              tc_commit(empty_bar(stage));
+              if (st + 1 == cend) tc_commit(tfull_bar);
             }
-            tc_commit(empty_bar(stage));
+            __syncwarp();
             if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(tfull_bar);
+          if (cend <= c0 && hs_elect_one()) tc_commit(tfull_bar);  // empty tile: the epilogue still writes zeros
+          __syncwarp();
           tphase ^= 1;
         }
       }
@@ -1160,6 +1237,18 @@ static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
 // producer mode of the gathered operand when TMA applies: 1 = both planes by TMA im2col, 2 = hybrid (hi plane by
 // TMA, lo plane by cp.async), 0 = cp.async only
 static int g_hs_gather_tma_mode = 1;
+// K stages (64 reduction elements each) per TMEM accumulation chunk of gather_gemm_hs: a chunk is one chain of
+// 12 * flush truncating tensor-core accumulations; chunks are summed in registers with round-to-nearest adds.
+// Environment override CURV_HS_FLUSH (accuracy / speed experiments).
+static int hs_flush() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("CURV_HS_FLUSH");
+    v = e ? atoi(e) : TC_FLUSH;
+    if (v < 1 || v > 64) v = TC_FLUSH;
+  }
+  return v;
+}
 
 // a_plane_slots: number of slots stored in the planes (bounds the TMA tensor); 0 -> no TMA
 static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cudaStream_t st,
@@ -1170,6 +1259,7 @@ static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cu
   const Geom& g = a.g;
   if (!allow_parity || !hs_make_parity(g, a.par)) a.par.nclass = 0;
   a.use_tma = 0;
+  a.flush = hs_flush();
   if (a_plane_slots > 0 && g_hs_gather_tma_mode > 0 && hs_setup_gather_tma(a, a_plane_slots))
     a.use_tma = g_hs_gather_tma_mode;
   const int tiles_m = a.par.nclass > 0 ? a.par.tile0[a.par.nclass] : ceil_div(g.M, TC_BM);
