@@ -41,7 +41,7 @@ EXPORTS = [
     "curv_program_value_layout", "curv_matmat_batch", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
-    "curv_profile_read_class",
+    "curv_profile_read_class", "curv_launch_config",
 ]
 
 _lib = None
@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
     L.curv_profile_read.restype = i
     L.curv_profile_read_class.argtypes = [i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
     L.curv_profile_read_class.restype = i
+    L.curv_launch_config.argtypes = []
+    L.curv_launch_config.restype = i
     _lib = L
     return L
 

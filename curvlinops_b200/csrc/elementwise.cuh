@@ -591,9 +591,17 @@ __global__ void vec_grad_finish_kernel(const float* __restrict__ partial, int nc
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * nk) return;
   int k = i % nk, c = i / nk;
-  float s = 0.f;
-  for (int ch = 0; ch < nchunks; ++ch)
-    s += partial[(((long long)ch * nslots + kskip + k) * 2 + which) * Cp + c];
+  // eight independent chains (fixed order => deterministic): the loop is pure load latency otherwise
+  const float* q = partial + ((long long)(kskip + k) * 2 + which) * Cp + c;
+  const long long stride = (long long)nslots * 2 * Cp;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int ch = 0;
+  for (; ch + 8 <= nchunks; ch += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += __ldg(q + (long long)(ch + j) * stride);
+  }
+  for (; ch < nchunks; ++ch) a[0] += __ldg(q + (long long)ch * stride);
+  const float s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   out[(off + c) * ldk + k0 + k] += alpha * s;
 }
 

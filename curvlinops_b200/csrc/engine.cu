@@ -123,6 +123,10 @@ extern "C" int curv_set_tensor_core_mode(int mode) {
   return old;
 }
 
+// state that changes which kernels a call launches (host mirrors key their CUDA-graph caches on it):
+// tensor-core mode word (as accepted by curv_set_tensor_core_mode) | profiling flag << 16
+extern "C" int curv_launch_config(void);
+
 extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
                                    const curv_node_desc* nodes, int n_nodes,
                                    const curv_param_desc* params, int n_params, int batch, int kmax,
@@ -313,6 +317,7 @@ struct ProfScope {
     g_prof.push_back(r);
   }
 };
+extern "C" int curv_launch_config(void) { return g_tc_mode | (g_tc_disable << 4) | (g_profile ? (1 << 16) : 0); }
 extern "C" int curv_profile_enable(int on) {
   for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   g_prof.clear();

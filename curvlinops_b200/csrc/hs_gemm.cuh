@@ -33,6 +33,7 @@ namespace curv {
 #ifndef CURV_DISABLE_TC
 
 constexpr int HS_BK = 64;        // fp16 reduction elements per stage = one 128-byte swizzle row
+constexpr int HS_FLUSH = 6;      // K stages per main accumulation chunk of gather_gemm_hs (24 MMAs per chain)
 constexpr int HS_SH_TARGET = 14;  // scaled maximum in [2^14, 2^15)
 constexpr int HS_SH_CLAMP = 60;   // |sh| <= 60: products of two inverse scales stay normal floats
 
@@ -256,14 +257,20 @@ struct HsGatherArgs {
 // ---------------------------------------------------------------------------------------------------
 struct HsTile { int slot, m0, tn, cls, T; };  // T = K stages per segment
 
-// Shared-memory map of gather_gemm_hs: the stage ring of TcCfg<BN> plus a ring of NBUF = 512 / BN TMEM
-// accumulation buffers (all 512 tensor-memory columns): a chunk is drained by the epilogue while the MMAs of the
-// next NBUF - 1 chunks proceed, so the short accumulation chunks (TC_FLUSH stages, see tc_gemm.cuh) cost no
-// tensor-pipe time.
+// Shared-memory map of gather_gemm_hs: the stage ring of TcCfg<BN> plus the barriers of the TMEM accumulators.
+// All 512 tensor-memory columns are used, as 512 / BN buffers of BN columns:
+//   buffers 0, 1        "cross" accumulators  D_x += a_lo b_hi + a_hi b_lo   (one per segment, double buffered)
+//   buffers 2 .. NB-1   "main" accumulator ring  D_m += a_hi b_hi            (one per chunk of `flush` stages)
+// Why two kinds: the tensor core truncates when it adds into the fp32 accumulator (~0.25 ulp(D) of bias per MMA,
+// compounding over the ~60 layer applications of a product), so an accumulation CHAIN must stay short.  The
+// cross terms are 2^-10 of the result: their chain may span a whole segment (drained once), and keeping them out
+// of the main accumulator cuts the main chain to one MMA per K step - chunks can be 3x longer for the same bias,
+// and draining a chunk (64 KB of TMEM reads that compete with the MMAs) happens 3x less often.
 template <int BN>
 struct HsSmem {
   using Cfg = TcCfg<BN>;
-  static constexpr int NBUF = 512 / BN;
+  static constexpr int NB = 512 / BN;
+  static constexpr int NM = NB - 2;  // main ring
   uint32_t base, bar_base;
   __device__ explicit HsSmem(uint8_t* raw) {
     base = (smem_u32(raw) + 1023u) & ~1023u;
@@ -272,12 +279,14 @@ struct HsSmem {
   __device__ uint32_t full(int s) const { return bar_base + 8u * s; }
   __device__ uint32_t empty(int s) const { return bar_base + 8u * (Cfg::STAGES + s); }
   __device__ uint32_t tfull(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + a); }
-  __device__ uint32_t tempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + NBUF + a); }
-  __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NBUF); }
+  __device__ uint32_t tempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + NM + a); }
+  __device__ uint32_t cfull(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NM + a); }
+  __device__ uint32_t cempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NM + 2 + a); }
+  __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NM + 4); }
   __device__ uint32_t stageA(int s) const { return base + s * Cfg::STAGE_BYTES; }
   __device__ uint32_t stageB(int s) const { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; }
 };
-static_assert(8 * (2 * 4 + 2 * 8 + 1) <= 256, "barrier block of HsSmem must fit the 256 bytes reserved by TcCfg");
+static_assert(8 * (2 * 4 + 2 * 6 + 4 + 1) <= 256, "barrier block of HsSmem must fit the 256 bytes reserved by TcCfg");
 
 template <int BN>
 __device__ __forceinline__ uint32_t hs_prologue(const HsSmem<BN>& S, uint8_t* raw, int full_count) {
@@ -285,7 +294,8 @@ __device__ __forceinline__ uint32_t hs_prologue(const HsSmem<BN>& S, uint8_t* ra
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(S.full(s), full_count); mbar_init(S.empty(s), 1); }
-    for (int a = 0; a < HsSmem<BN>::NBUF; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
+    for (int a = 0; a < HsSmem<BN>::NM; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(S.cfull(a), 1); mbar_init(S.cempty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -320,7 +330,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_constant__ HsGatherArgs p, int nslots) {
   using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NBUF = HsSmem<BN>::NBUF;
+  constexpr int NM = HsSmem<BN>::NM;  // main accumulator ring (TMEM buffers 2..), buffers 0/1 = cross terms
   extern __shared__ uint8_t smem_raw[];
   const HsSmem<BN> S(smem_raw);
   const Geom& g = p.g;
@@ -561,17 +571,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
     // the commits of a stage in one predicated block.
     {
       constexpr uint32_t idesc = hs_idesc(BN, 0, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0, xb = 0;
+      uint32_t phase = 0, acc_phase = 0, xb_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         HsTile t;
         decode_tile(tile, t);
         const int nseg = num_segments(t.slot);
-        for (int seg = 0; seg < nseg; ++seg) {
-          for (int t0 = 0; t0 < t.T; t0 += p.flush) {  // one TMEM accumulation chunk
+        for (int seg = 0; seg < nseg && t.T > 0; ++seg) {
+          mbar_wait(S.cempty(xb), xb_phase ^ 1);  // cross accumulator of this segment drained
+          const uint32_t d_cross = tmem_base + (uint32_t)(xb * BN);
+          for (int t0 = 0; t0 < t.T; t0 += p.flush) {  // one chunk of the main accumulation
             mbar_wait(S.tempty(acc), acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            const uint32_t d_main = tmem_base + (uint32_t)((2 + acc) * BN);
             const int T = min(p.flush, t.T - t0);
             for (int it = 0; it < T; ++it) {
               mbar_wait(S.full(stage), phase);
@@ -585,19 +597,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
 #pragma unroll
                   for (int ks = 0; ks < HS_BK / 16; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
-                    hs_mma_f16(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-                    hs_mma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-                    hs_mma_f16(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+                    hs_mma_f16(d_main, dAh + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+                    hs_mma_f16(d_cross, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
+                    hs_mma_f16(d_cross, dAh + adv, dBl + adv, idesc, 1u);
                   }
                 }
                 tc_commit(S.empty(stage));                       // frees the smem stage when these MMAs retire
-                if (it + 1 == T) tc_commit(S.tfull(acc));        // chunk complete -> epilogue
+                if (it + 1 == T) {
+                  tc_commit(S.tfull(acc));                       // main chunk complete -> epilogue
+                  if (t0 + T == t.T) tc_commit(S.cfull(xb));     // segment complete -> cross terms to the epilogue
+                }
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NM) { acc = 0; acc_phase ^= 1; }
           }
+          if (++xb == 2) { xb = 0; xb_phase ^= 1; }
         }
       }
     }
@@ -607,8 +623,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
     constexpr int HALF = BN / 2;
     const int egrp = warp >= 13 ? 1 : 0;
     const int quad = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int acc = 0, xb = 0;
+    uint32_t acc_phase = 0, xb_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       HsTile t;
       decode_tile(tile, t);
@@ -617,7 +633,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
       float accv[HALF];
 #pragma unroll
       for (int j = 0; j < HALF; ++j) accv[j] = 0.f;
-      for (int seg = 0; seg < nseg; ++seg) {
+      // drain one TMEM buffer (this warp's 32 lanes x HALF columns) into accv, scaled by the segment's inverse scale
+      auto drain = [&](int buf, float inv) {
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + egrp * HALF + c0), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) accv[c0 + j] = fmaf(__uint_as_float(r[j]), inv, accv[c0 + j]);
+        }
+        tc_fence_before();
+      };
+      for (int seg = 0; seg < nseg && t.T > 0; ++seg) {
         int a_slot, w_id;
         segment_ids(t.slot, seg, a_slot, w_id);
         const float inv = hs_pow2(-hs_shift_from_bits(__ldg(p.a_bits + a_slot)) -
@@ -625,17 +652,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
         for (int t0 = 0; t0 < t.T; t0 += p.flush) {
           mbar_wait(S.tfull(acc), acc_phase);
           tc_fence_after();
-#pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 16) {
-            uint32_t r[16];
-            tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + egrp * HALF + c0), r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) accv[c0 + j] = fmaf(__uint_as_float(r[j]), inv, accv[c0 + j]);
-          }
-          tc_fence_before();
+          drain(2 + acc, inv);
           mbar_arrive(S.tempty(acc));
-          if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
+          if (++acc == NM) { acc = 0; acc_phase ^= 1; }
         }
+        mbar_wait(S.cfull(xb), xb_phase);
+        tc_fence_after();
+        drain(xb, inv);
+        mbar_arrive(S.cempty(xb));
+        if (++xb == 2) { xb = 0; xb_phase ^= 1; }
       }
       const float* bias = (t.slot == 0) ? p.bias
                                         : (p.bias_t ? p.bias_t + (long long)(t.slot - 1) * p.bias_slot : nullptr);
@@ -1244,8 +1269,8 @@ static int hs_flush() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("CURV_HS_FLUSH");
-    v = e ? atoi(e) : TC_FLUSH;
-    if (v < 1 || v > 64) v = TC_FLUSH;
+    v = e ? atoi(e) : HS_FLUSH;
+    if (v < 1 || v > 64) v = HS_FLUSH;
   }
   return v;
 }

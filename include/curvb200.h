@@ -181,6 +181,9 @@ int curv_profile_read_class(int cls, double* ms, double* flops, long long* count
    tiles, 2: tcgen05 for every contraction (tests).  Bits 4.. are debug switches: 0x10 no tcgen05 gather GEMM,
    0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead).  Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);
+/* Everything global that changes which kernels a call launches: the mode word above | (profiling enabled) << 16.
+   Host mirrors that replay captured CUDA graphs of curv_matmat_batch key their caches on it. */
+int curv_launch_config(void);
 
 #ifdef __cplusplus
 }
