@@ -436,16 +436,19 @@ struct Ctx {
 };
 
 // ---- half-split path: which contractions of a conv node run on the fp16 hi/lo kernels (hs_gemm.cuh)
+// size thresholds of the half-split kernels: two full 128-row tiles are enough (a mini-batch sharded over 8 GPUs
+// leaves 16 x 7 x 7 = 784 rows in the last ResNet stage); smaller problems (fc, MLPs) stay on the SIMT kernels
+static bool hs_big_enough(const Geom& g) { return g_tc_mode >= 2 || (g.M >= 256 && g.Kd >= 64 && g.N >= 16); }
 static bool hs_fwd_ok(const Ctx& c, const Node& n) {
-  return c.hs && n.wimg_off >= 0 && hs_gather_shape_ok(n.fwd) && tc_gather_eligible(n.fwd, g_tc_mode);
+  return c.hs && n.wimg_off >= 0 && hs_gather_shape_ok(n.fwd) && hs_big_enough(n.fwd);
 }
 static bool hs_dgr_ok(const Ctx& c, const Node& n) {
-  return c.hs && n.wtimg_off >= 0 && hs_gather_shape_ok(n.dgr) && tc_gather_eligible(n.dgr, g_tc_mode);
+  return c.hs && n.wtimg_off >= 0 && hs_gather_shape_ok(n.dgr) && hs_big_enough(n.dgr);
 }
 static bool hs_wgr_ok(const Ctx& c, const Node& n, int ns) {
   const Value& vo = c.P->values[n.d.out];
   return c.hs && !(g_tc_disable & 2) && ns >= 1 && ns <= 8 && hs_wgrad_shape_ok(n.fwd, vo.Cp) &&
-         tc_wgrad_eligible(n.fwd, g_tc_mode);
+         hs_big_enough(n.fwd);
 }
 // absmax of `count` slots (x = first of them) into bits entries [entry, entry + count), once per call
 static int hs_absmax(const Ctx& c, const float* x, long long slot_stride, long long n, int entry, int count) {

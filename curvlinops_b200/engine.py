@@ -27,6 +27,9 @@ MAX_COLUMNS_PER_SWEEP = 8
 #: Set to False to launch eagerly (per-launch profiling does so automatically).
 CUDA_GRAPHS = os.environ.get("CURV_CUDA_GRAPHS", "1") != "0"
 _MAX_GRAPHS = 8
+#: products whose V is larger than this run eagerly: their kernels are long enough to hide the launches, and
+#: the static-buffer copies of a replay would cost more than they save
+_GRAPH_MAX_V_BYTES = 32 << 20
 
 
 def _loss_code(loss_func) -> int:
@@ -181,7 +184,8 @@ class Engine:
                     ws.data_ptr(), ws.numel() * 4, strm))
 
         cfg = capi.lib().curv_launch_config()
-        if not CUDA_GRAPHS or (cfg >> 16) or torch.cuda.is_current_stream_capturing():
+        if (not CUDA_GRAPHS or (cfg >> 16) or V.numel() * 4 > _GRAPH_MAX_V_BYTES
+                or torch.cuda.is_current_stream_capturing()):
             launch(V, out, stream)
             del keep
             return

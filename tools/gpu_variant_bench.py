@@ -5,7 +5,7 @@ import torch, torchvision
 from curvlinops_b200 import GGNLinearOperator, _capi as capi
 
 modes = [int(m, 0) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1"])]
-B, K = 128, 8
+B, K = int(os.environ.get("CURV_B", 128)), 8  # CURV_B = 16 emulates one rank of an 8-GPU run
 torch.manual_seed(0)
 dev = torch.device("cuda")
 model = torchvision.models.resnet18().eval().to(dev)
