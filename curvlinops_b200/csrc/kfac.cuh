@@ -99,6 +99,15 @@ extern "C" int curv_kfac_accumulate_batch(curv_program* P, const void* const* pa
   c.rop = false;
   cudaStream_t st = c.st;
   int rc;
+  // the forward convolutions and the dgrad of the seed back-propagation run on the half-split kernels; the Gram
+  // matrices (one slot, patch matrix operand) stay on the 3xTF32 / SIMT wgrad kernels
+  std::vector<char> hs_valid;
+  if (g_tc_mode && !(g_tc_disable & 32) && P->hs1_elems > 0 && hs_ready() > 0) {
+    c.hs = true;
+    hs_valid.assign((size_t)P->hsbits_count, 0);
+    c.hs_valid = &hs_valid;
+    CHECK_CUDA(cudaMemsetAsync(c.hsbits(), 0, (size_t)P->hsbits_count * sizeof(uint32_t), c.st));
+  }
   if ((rc = prepare_params(c, false))) return rc;
   if ((rc = forward(c, X, 0))) return rc;
   float* scratch = c.ws + P->scratch_off;
@@ -138,6 +147,10 @@ extern "C" int curv_kfac_accumulate_batch(curv_program* P, const void* const* pa
       c.K = kk;
       c.kfac_G = gmap.data();
       c.kfac_wG = wG;
+      if (c.hs) {  // new seeds: the cotangent maxima must be recomputed (atomicMax over the old words = valid bounds)
+        for (size_t v = 0; v < P->values.size(); ++v)
+          for (int sl = 0; sl <= P->kmax; ++sl) hs_valid[(size_t)c.bits_grad((int)v) + sl] = 0;
+      }
       if ((rc = backward(c, kk))) return rc;
     }
   }

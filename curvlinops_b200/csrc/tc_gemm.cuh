@@ -85,6 +85,18 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// One lane of the (converged) warp, chosen by the hardware.  tcgen05.mma / commit are issued under this predicate
+// from warp-uniform control flow: issued from inside `if (lane == 0)` nvcc wraps every UTCxMMA in an
+// ELECT / BRA.U.ANY uniformisation loop and the single issuing thread becomes the bottleneck.
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                             uint32_t idesc, uint32_t accumulate) {
@@ -215,11 +227,12 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
   }
 }
 
-// MMA issuer loop body for one tile of T stages: 3xTF32 = 12 MMAs per 32-deep stage.
+// MMA issuer loop body for one chunk of T stages (whole warp, one elected lane issues): 3xTF32 = 12 MMAs per
+// 32-deep stage; the last stage also commits the chunk's tfull barrier.
 // DESC(addr) builds the smem descriptor; K_ADV = descriptor start-address advance (16-byte units) per K=8.
 template <int BN, bool MN_MAJOR>
 __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tmem, int T, int& stage,
-                                              uint32_t& phase) {
+                                              uint32_t& phase, uint32_t tfull_bar) {
   using Cfg = TcCfg<BN>;
   constexpr uint32_t idesc = make_tf32_idesc(BN) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
   for (int it = 0; it < T; ++it) {
@@ -234,15 +247,19 @@ __device__ __forceinline__ void tc_issue_tile(const TcSmem<BN>& S, uint32_t d_tm
       dAh = make_kmajor_sw128_desc(sA); dAl = make_kmajor_sw128_desc(sA + Cfg::A_BYTES);
       dBh = make_kmajor_sw128_desc(sB); dBl = make_kmajor_sw128_desc(sB + Cfg::B_BYTES);
     }
+    if (tc_elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < TC_BK / 8; ++ks) {
-      // K-major: +32 bytes inside the 128-byte row; MN-major: next 8-row group (+1024 bytes)
-      const uint64_t adv = (uint64_t)((MN_MAJOR ? ks * 1024 : ks * 32) >> 4);
-      tc_mma_tf32(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-      tc_mma_tf32(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-      tc_mma_tf32(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+      for (int ks = 0; ks < TC_BK / 8; ++ks) {
+        // K-major: +32 bytes inside the 128-byte row; MN-major: next 8-row group (+1024 bytes)
+        const uint64_t adv = (uint64_t)((MN_MAJOR ? ks * 1024 : ks * 32) >> 4);
+        tc_mma_tf32(d_tmem, dAl + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+        tc_mma_tf32(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+        tc_mma_tf32(d_tmem, dAh + adv, dBh + adv, idesc, 1u);
+      }
+      tc_commit(S.empty(stage));  // frees the smem stage when these MMAs retire
+      if (it + 1 == T) tc_commit(tfull_bar);  // chunk complete -> epilogue
     }
-    tc_commit(S.empty(stage));  // frees the smem stage when these MMAs retire
+    __syncwarp();
     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
   }
 }
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -474,8 +491,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc(const GatherGemm
         for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {  // one TMEM accumulation chunk
           mbar_wait(S.tempty(acc), acc_phase ^ 1);
           tc_fence_after();
-          tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
-          tc_commit(S.tfull(acc));  // chunk complete -> epilogue
+          tc_issue_tile<BN, false>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase,
+                                   S.tfull(acc));  // chunk complete -> epilogue
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -702,7 +719,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -712,8 +729,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_tc(const WgradArgs p
         for (int t0 = 0; t0 < T; t0 += TC_FLUSH) {
           mbar_wait(S.tempty(acc), acc_phase ^ 1);
           tc_fence_after();
-          tc_issue_tile<BN, true>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase);
-          tc_commit(S.tfull(acc));
+          tc_issue_tile<BN, true>(S, tmem_base + (uint32_t)(acc * BN), min(TC_FLUSH, T - t0), stage, phase,
+                                   S.tfull(acc));
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }

@@ -120,3 +120,23 @@ def test_unsupported_params_raise():
         KFACLinearOperator(net, loss, dict(net.named_parameters()), [(X, y)], check_deterministic=False)
     with pytest.raises(ValueError, match="Invalid fisher_type"):
         KFACLinearOperator(model, loss, dict(model.named_parameters()), data, fisher_type="nope")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kfac_type2_on_tensor_core_kernels(name):
+    """Same factors with every contraction forced onto the tcgen05 kernels (half-split forward / dgrad sweeps,
+    3xTF32 Gram matrices): exercises the tensor-core paths at the fixtures' small shapes."""
+    from curvlinops_b200 import _capi as capi
+
+    model, loss, data, fx, params = setup(name)
+    old = capi.lib().curv_set_tensor_core_mode(2)
+    try:
+        Kop = KFACLinearOperator(model, loss, params, data, fisher_type="type-2", separate_weight_and_bias=False,
+                                 check_deterministic=False)
+        P, K, PT = Kop
+        for bi, block in enumerate(K):
+            for fi, fac in enumerate(block):
+                close(fac, fx[f"factor_type2_joint_{bi}_{fi}"])
+        close(Kop @ fx["v"].float().cuda(), fx["kfac_type2_joint"])
+    finally:
+        capi.lib().curv_set_tensor_core_mode(old)
