@@ -1,12 +1,14 @@
 """curvlinops_b200: B200-native engine for the curvature-matvec hot path of f-dangel/curvlinops.
 
 Drop-in operator classes (same names / constructor arguments as the reference):
-``HessianLinearOperator``, ``GGNLinearOperator``, ``KFACLinearOperator``, ``EKFACLinearOperator`` and the
+``HessianLinearOperator``, ``GGNLinearOperator``, ``EFLinearOperator``, ``KFACLinearOperator``,
+``EKFACLinearOperator``, the Jacobian operators and the
 structured operators they are assembled from.  All arithmetic runs in hand-written sm_100a CUDA kernels
 behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
 """
 
-from .curvature import CurvatureLinearOperator, GGNLinearOperator, HessianLinearOperator
+from .curvature import (CurvatureLinearOperator, EFLinearOperator, GGNLinearOperator,
+                        HessianLinearOperator)
 from .jacobian import JacobianLinearOperator, TransposedJacobianLinearOperator
 from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
 from .linop import PyTorchLinearOperator
@@ -18,6 +20,7 @@ __all__ = [
     "PyTorchLinearOperator",
     "CurvatureLinearOperator",
     "GGNLinearOperator",
+    "EFLinearOperator",
     "HessianLinearOperator",
     "JacobianLinearOperator",
     "TransposedJacobianLinearOperator",

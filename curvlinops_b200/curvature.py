@@ -308,6 +308,51 @@ class GGNLinearOperator(CurvatureLinearOperator):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1])
 
 
+class EFLinearOperator(CurvatureLinearOperator):
+    r"""Uncentered gradient covariance ('empirical Fisher') :math:`c\sum_n \nabla_\theta\ell_n
+    \nabla_\theta\ell_n^\top` (reference ``curvlinops/gradient_moments.py:90-151``).
+
+    The reference evaluates it as the GGN of the pseudo-loss :math:`\frac{1}{2c}\sum_n\langle f_n, g_n\rangle^2`
+    with :math:`g_n = \partial\ell_n/\partial f_n` (``gradient_moments.py:48-86``); here that is the engine's two
+    sweeps with the rank-one per-sample loss term :math:`g_n g_n^\top / c` (the Monte-Carlo kind with one
+    deterministic 'sample'): one primal forward for :math:`g_n`, then forward + Jv and backward + J^T."""
+
+    SELF_ADJOINT = True
+    KIND = capi.KIND_GGN_MC
+    SUPPORTED_LOSSES = (MSELoss, CrossEntropyLoss, BCEWithLogitsLoss)
+
+    def __init__(self, model_func, loss_func, params, data, progressbar=False, check_deterministic=True,
+                 num_data=None, batch_size_fn=None):
+        if not isinstance(loss_func, self.SUPPORTED_LOSSES):
+            raise NotImplementedError(f"Loss must be one of {self.SUPPORTED_LOSSES}. Got: {loss_func}.")
+        super().__init__(model_func, loss_func, params, data, progressbar=progressbar,
+                         check_deterministic=check_deterministic, num_data=num_data,
+                         batch_size_fn=batch_size_fn)
+
+    def _grad_outputs(self, X, y) -> Tensor:
+        """``[B, 1, C]`` per-sample gradients of the unreduced loss w.r.t. the prediction."""
+        f = self._engine.predict(X)
+        lf = self._loss_func
+        if isinstance(lf, CrossEntropyLoss):
+            g = torch.softmax(f, dim=1) - torch.nn.functional.one_hot(y, f.shape[1]).to(f.dtype)
+        elif isinstance(lf, MSELoss):
+            g = 2.0 * (f - y.to(f.dtype))
+        else:
+            g = torch.sigmoid(f) - y.to(f.dtype)
+        return g.unsqueeze(1)
+
+    def _batch_call(self, X, y, V, out, alpha):
+        from .engine import loss_scale
+
+        g = self._grad_outputs(X, y)
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
+                                  scale=loss_scale(self._loss_func, X.shape[0], g.shape[-1]))
+
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=self._grad_outputs(X, y),
+                                  scale=scale[0])
+
+
 class HessianLinearOperator(CurvatureLinearOperator):
     r"""Hessian :math:`c\sum_n \nabla^2_\theta \ell(f_\theta(x_n), y_n)` of an empirical risk
     (reference ``curvlinops/hessian.py:72-145``), applied with a hand-written R-op

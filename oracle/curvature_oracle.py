@@ -169,6 +169,46 @@ def ggn_matmat(model_func, loss_func, params: dict[str, Tensor],
     return out
 
 
+
+def loss_grad_outputs(loss_func, f: Tensor, y: Tensor) -> Tensor:
+    """Per-sample gradient of the UNREDUCED loss w.r.t. the prediction, ``g_n = d l(f_n, y_n) / d f_n`` -- what
+    ``grad(c_flat)(output) * reduction_factor`` evaluates to in the reference's empirical-Fisher pseudo-loss
+    (``curvlinops/gradient_moments.py:65-80``)."""
+    if isinstance(loss_func, torch.nn.CrossEntropyLoss):
+        return torch.softmax(f, dim=1) - torch.nn.functional.one_hot(y, f.shape[1]).to(f.dtype)
+    if isinstance(loss_func, torch.nn.MSELoss):
+        return 2.0 * (f - y)
+    if isinstance(loss_func, torch.nn.BCEWithLogitsLoss):
+        return torch.sigmoid(f) - y
+    raise NotImplementedError(f"loss {loss_func}")
+
+
+def ef_matmat(model_func, loss_func, params: dict[str, Tensor], data: Iterable[tuple[Tensor, Tensor]],
+              V: list[Tensor], n_data: int | None = None) -> list[Tensor]:
+    """``EF @ V`` (uncentered gradient covariance, ``curvlinops/gradient_moments.py:15-151``): the GGN of the
+    pseudo-loss ``1/(2c) sum_n <f_n, g_n>^2``, i.e. the two sweeps with the rank-one per-sample "loss Hessian"
+    ``g_n g_n^T / c`` (c = number of loss terms of a mean reduction, 1 for sum)."""
+    f_fn = _as_callable(model_func)
+    data = list(data)
+    if n_data is None:
+        n_data = sum(X.shape[0] for X, _ in data)
+    K = V[0].shape[-1]
+    out = [torch.zeros_like(v) for v in V]
+    for X, y in data:
+        alpha = _normalization(loss_func, X.shape[0], n_data)
+        for k in range(K):
+            vk = [v[..., k] for v in V]
+            f, jv = jacobian_vector_product(f_fn, params, X, vk)
+            g = loss_grad_outputs(loss_func, f.detach(), y)
+            if loss_func.reduction == "mean":
+                red = f.shape[0] if isinstance(loss_func, torch.nn.CrossEntropyLoss) else f.numel()
+            else:
+                red = 1.0
+            hjv = g * (g * jv).sum(dim=1, keepdim=True) / red
+            for o, gr in zip(out, transposed_jacobian_vector_product(f_fn, params, X, hjv)):
+                o[..., k].add_(gr, alpha=alpha)
+    return out
+
 def hessian_matmat(model_func, loss_func, params: dict[str, Tensor],
                    data: Iterable[tuple[Tensor, Tensor]], V: list[Tensor],
                    n_data: int | None = None) -> list[Tensor]:

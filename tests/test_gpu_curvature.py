@@ -200,3 +200,22 @@ def test_jacobian_operators_match_oracle():
             refT[:, k] += torch.cat([g.flatten() for g in orc.transposed_jacobian_vector_product(f_fn, p64, X, w)])
         pos += X.shape[0]
     assert_parity(JT @ W.float().cuda(), refT, params)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_empirical_fisher_matches_reference_golden(name):
+    """EFLinearOperator vs the reference's own EFLinearOperator output (tests/golden/ef.npz)."""
+    import os
+
+    import numpy as np
+
+    from curvlinops_b200 import EFLinearOperator
+    from tests.golden_utils import GOLDEN
+
+    model, loss, data, fx = load_case(name, dtype=torch.float32, device="cuda")
+    params = dict(model.named_parameters())
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "ef.npz"))[name])
+    E = EFLinearOperator(model, loss, params, data, check_deterministic=False)
+    got = (E @ fx["V"].float().cuda()).double().cpu()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4, err  # BASELINE tolerance: rtol 1e-4 (fp32 engine vs float64 reference)

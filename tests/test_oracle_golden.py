@@ -28,3 +28,19 @@ def test_mc_ggn_matches_reference_stream(name, M):
     V = split_like(fx["V"], params)
     got = flat(orc.ggn_matmat(model, loss, params, data, V, mc_samples=M, seed=1234))
     torch.testing.assert_close(got, fx[f"ggn_mc{M}"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_empirical_fisher_matches_reference(name):
+    """Fixture tests/golden/ef.npz = the reference's EFLinearOperator on the same parameters / data / V
+    (oracle/make_golden_ef.py)."""
+    import numpy as np
+    import os
+
+    from tests.golden_utils import GOLDEN
+
+    model, loss, data, fx = load_case(name)
+    params = dict(model.named_parameters())
+    V = split_like(fx["V"], params)
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "ef.npz"))[name])
+    torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), ref, rtol=1e-9, atol=1e-12)
