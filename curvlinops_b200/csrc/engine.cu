@@ -609,6 +609,25 @@ static int forward(const Ctx& c, const void* X, int K) {
           int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, ea, nin);
           if (!rc) rc = hs_split(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.hs1_hi(), c.hs1_lo(), ea, nin);
           if (rc) return rc;
+          if (!vi.tan && nsl > 1 && d.p0 >= 0) {
+            // the layer input carries no tangent (the stem): every slot gathers the same operand -> N-stacked
+            // kernel, the gather is staged once per group of 256 / BN slots
+            HsStackArgs q;
+            memset(&q, 0, sizeof(q));
+            q.g = n.fwd;
+            q.Ah = c.hs1_hi(); q.Al = c.hs1_lo(); q.a_bits = c.hsbits() + ea;
+            q.W_img = reinterpret_cast<const __half*>(c.ws + n.wimg_off);
+            q.Wt_img = reinterpret_cast<const __half*>(c.ws + n.wimgt_off);
+            q.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd);
+            q.w_bits = c.hsbits() + c.bits_node((int)(&n - P->nodes.data()));
+            q.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
+            q.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; q.bias_slot = vo.Cp;
+            q.out = c.act(d.out); q.out_slot = vo.slot_elems; q.slot_lo = 0; q.nslots = nsl; q.accumulate = 0;
+            ProfScope prof(0, fl, st);
+            if (hs_launch_gather_stack(q, st)) return fail(CURV_ERR_CUDA, "half-split stacked gather GEMM launch failed");
+            ++g_launches;
+            break;
+          }
           HsGatherArgs h;
           memset(&h, 0, sizeof(h));
           h.g = n.fwd;

@@ -699,6 +699,283 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
   hs_teardown(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N-stacked gather GEMM for the SHARED-activation segment:  out_k[m][n] (+)= sum_r gather(A_0)[m][r] * W_k[n][r]
+// for a GROUP of slots k at once (the tangent term conv(a, Wdot_k) of every layer, and all slots of a layer whose
+// input carries no tangent - the stem).  The gathered tile of the one shared operand is staged ONCE per group and
+// multiplied against the weight blocks of the group's slots stacked along N (N = slots * BN <= 256): the
+// activation gather - the measured limit of the C_out = 64 layers - is paid once per 256 / BN slots, and one
+// N = 256 MMA reads the A tile from shared memory once for all of them.
+//   tile    = 128 rows x (group of G = 256 / BN slots) x one n-tile of BN channels; K stage = 64
+//   smem    = 2 stages x (A hi/lo 32 KB + B hi/lo 64 KB)
+//   TMEM    = main accumulator (hi*hi, columns 0..255) + cross accumulator (lo*hi + hi*lo, columns 256..511):
+//             main is drained every `flush` stages (short truncation chains, see HsSmem), cross once per tile
+//   warps   = 0-15 epilogue (TMEM lane quadrant w & 3, column group w >> 2 of 64 columns), 16 MMA,
+//             17-19 producers (16-byte cp.async with zero fill; weights by cp.async.bulk, 2 per slot)
+// Forward geometry (mode 0) only.  Requires Cs % 8 == 0.
+// ---------------------------------------------------------------------------------------------------
+struct HsStackArgs {
+  Geom g;
+  const __half* Ah;        // planes of the shared operand (ONE slot)
+  const __half* Al;
+  const uint32_t* a_bits;  // [0]
+  const __half* W_img;     // image of W (slot 0)
+  const __half* Wt_img;    // images of the tangent weights, slot k at (k-1)*Wt_img_slot
+  long long Wt_img_slot;
+  const uint32_t* w_bits;  // [0] = W, [k] = tangent weight k
+  const float* bias;
+  const float* bias_t;
+  long long bias_slot;
+  float* out;
+  long long out_slot;
+  int slot_lo, nslots;     // slots slot_lo .. slot_lo + nslots - 1
+  int accumulate;
+  int flush;
+};
+
+constexpr int HSN_THREADS = 20 * 32;  // 20 warps: 65536 / 640 leaves 96 registers per thread for the epilogue
+constexpr int HSN_PRODUCERS = 96;
+constexpr int HSN_STAGES = 2;
+constexpr int HSN_A_BYTES = TC_BM * 128;            // per plane
+constexpr int HSN_B_BYTES = 256 * 128;              // per plane (up to 256 stacked rows)
+constexpr int HSN_STAGE_BYTES = 2 * HSN_A_BYTES + 2 * HSN_B_BYTES;  // 96 KB
+constexpr int HSN_SMEM_BYTES = HSN_STAGES * HSN_STAGE_BYTES + 1024 + 256;
+
+template <int BN>
+__global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsStackArgs p) {
+  constexpr int G = 256 / BN;  // slots per group
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + HSN_STAGES * HSN_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (HSN_STAGES + s); };
+  const uint32_t tfull = bar_base + 8u * (2 * HSN_STAGES), tempty = tfull + 8u, cfull = tfull + 16u,
+                 cempty = tfull + 24u, tmem_slot = tfull + 32u;
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = ceil_div(g.Nd, BN);
+  const int tiles_m = ceil_div(g.M, TC_BM);
+  const int ngroups = ceil_div(p.nslots, G);
+  const int ntiles = tiles_m * tiles_n * ngroups;
+  const int nchunks = ceil_div(g.Kd, HS_BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HSN_STAGES; ++s) { mbar_init(full_bar(s), HSN_PRODUCERS + 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 512); mbar_init(cfull, 1); mbar_init(cempty, 512);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  // tile -> (group, m0, tn); the groups of one (m-tile, n-tile) are adjacent: they gather the same rows
+  auto decode_tile = [&](int tile, int& grp, int& m0, int& tn) {
+    grp = tile % ngroups;
+    const int rest = tile / ngroups;
+    tn = rest % tiles_n;
+    m0 = (rest / tiles_n) * TC_BM;
+  };
+
+  if (warp >= 17) {
+    // ------------------------------------------------------------------ producers
+    const int pt = threadIdx.x - 17 * 32;     // 0..95
+    const int a_c = pt & 7, a_r0 = pt >> 3;   // chunk a_c (8 channels) of rows a_r0 + 12 i < 128, i < 11
+    constexpr int NR = 11;
+    const bool fast = (g.Cs % HS_BK) == 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int grp, m0, tn;
+      decode_tile(tile, grp, m0, tn);
+      const int s_first = p.slot_lo + grp * G;
+      const int cnt = min(G, p.slot_lo + p.nslots - s_first);
+      int ah[NR], aw[NR], rowoff[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int m = m0 + a_r0 + 12 * i;
+        const bool ok = m < g.M && a_r0 + 12 * i < TC_BM;
+        const int mm = ok ? m : 0;
+        const int bimg = mm / (g.Hd * g.Wd);
+        const int rem = mm - bimg * (g.Hd * g.Wd);
+        const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+        ah[i] = ok ? hd * g.sh - g.ph : -(1 << 20);  // a row beyond M fails every bounds test
+        aw[i] = wd * g.sw - g.pw;
+        rowoff[i] = ((bimg * g.Hs + hd * g.sh - g.ph) * g.Ws + aw[i]) * g.Cs;
+      }
+      int kh = 0, kw = 0, cb = 0;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        int dy = kh, dx = kw, c = cb + a_c * 8;
+        bool rok = true;
+        if (!fast) {  // the 16-byte chunk decides its own filter tap
+          const int r = kc * HS_BK + a_c * 8;
+          const int tap = r / g.Cs;
+          c = r - tap * g.Cs;
+          dy = tap / g.KW; dx = tap - dy * g.KW;
+          rok = r < g.Kd;
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sA = sbase + stage * HSN_STAGE_BYTES;
+        const uint32_t sB = sA + 2 * HSN_A_BYTES;
+        if (pt == 0) {  // weight blocks of the group's slots, stacked along N: hi planes, then lo planes
+          const uint32_t blk = (uint32_t)BN * 128u;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)),
+                       "r"(2u * blk * (uint32_t)cnt)
+                       : "memory");
+          for (int j = 0; j < cnt; ++j) {
+            const int s = s_first + j;
+            const __half* Wimg = (s == 0) ? p.W_img : p.Wt_img + (long long)(s - 1) * p.Wt_img_slot;
+            const __half* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    sB + (uint32_t)j * blk),
+                "l"(wsrc), "r"(blk), "r"(full_bar(stage))
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    sB + (uint32_t)HSN_B_BYTES + (uint32_t)j * blk),
+                "l"(wsrc + BN * HS_BK), "r"(blk), "r"(full_bar(stage))
+                : "memory");
+          }
+        }
+        const int tapoff = (dy * g.Ws + dx) * g.Cs + c;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int r = a_r0 + 12 * i;
+          if (r >= TC_BM) continue;
+          const int hs = ah[i] + dy, ws = aw[i] + dx;
+          const bool ok = rok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
+          const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
+          const uint32_t o = sA + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((a_c ^ (r & 7)) << 4));
+          hs_cp16(o, p.Ah + eo, ok);
+          hs_cp16(o + HSN_A_BYTES, p.Al + eo, ok);
+        }
+        hs_cp_arrive(full_bar(stage));
+        if (++stage == HSN_STAGES) { stage = 0; phase ^= 1; }
+        cb += HS_BK;
+        if (cb >= g.Cs) { cb = 0; if (++kw == g.KW) { kw = 0; ++kh; } }
+      }
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ MMA issuer (uniform loop, elected lane)
+    int stage = 0;
+    uint32_t phase = 0, tphase = 0, cphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int grp, m0, tn;
+      decode_tile(tile, grp, m0, tn);
+      const int cnt = min(G, p.nslots - grp * G);
+      const uint32_t idesc = hs_idesc(cnt * BN, 0, 0);
+      mbar_wait(cempty, cphase ^ 1);  // cross accumulator of the previous tile drained
+      for (int t0 = 0; t0 < nchunks; t0 += p.flush) {
+        mbar_wait(tempty, tphase ^ 1);  // main accumulator of the previous chunk drained
+        tc_fence_after();
+        const int T = min(p.flush, nchunks - t0);
+        for (int it = 0; it < T; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = sbase + stage * HSN_STAGE_BYTES, sB = sA + 2 * HSN_A_BYTES;
+          const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + HSN_A_BYTES);
+          const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + HSN_B_BYTES);
+          if (hs_elect_one()) {
+            fence_async_proxy();  // cp.async (generic proxy) writes -> tensor-core reads
+#pragma unroll
+            for (int ks = 0; ks < HS_BK / 16; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              hs_mma_f16(tmem_base, dAh + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
+              hs_mma_f16(tmem_base + 256u, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
+              hs_mma_f16(tmem_base + 256u, dAh + adv, dBl + adv, idesc, 1u);
+            }
+            tc_commit(empty_bar(stage));
+            if (it + 1 == T) {
+              tc_commit(tfull);
+              if (t0 + T == nchunks) tc_commit(cfull);
+            }
+          }
+          __syncwarp();
+          if (++stage == HSN_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tphase ^= 1;
+      }
+      cphase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-15)
+    const int quad = warp & 3, cg = warp >> 2;  // TMEM lanes 32*quad.., accumulator columns 64*cg .. +63
+    const int j = (cg * 64) / BN;               // slot of the group these columns belong to
+    const int ncol = (cg * 64) % BN;            // first channel inside the slot's n-tile
+    const int sh_a = hs_shift_from_bits(__ldg(p.a_bits));
+    uint32_t tphase = 0, cphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int grp, m0, tn;
+      decode_tile(tile, grp, m0, tn);
+      const int s_first = p.slot_lo + grp * G;
+      const int cnt = min(G, p.slot_lo + p.nslots - s_first);
+      const bool active = j < cnt;
+      const int slot = s_first + (active ? j : 0);
+      const float inv = hs_pow2(-sh_a - hs_shift_from_bits(__ldg(p.w_bits + slot)));
+      float accv[64];
+#pragma unroll
+      for (int q = 0; q < 64; ++q) accv[q] = 0.f;
+      auto drain = [&](uint32_t col0) {
+        if (active) {
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + col0 + (uint32_t)(cg * 64 + c0), r);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) accv[c0 + q] = fmaf(__uint_as_float(r[q]), inv, accv[c0 + q]);
+          }
+        }
+        tc_fence_before();
+      };
+      for (int t0 = 0; t0 < nchunks; t0 += p.flush) {
+        mbar_wait(tfull, tphase);
+        tc_fence_after();
+        drain(0u);
+        mbar_arrive(tempty);
+        tphase ^= 1;
+      }
+      mbar_wait(cfull, cphase);
+      tc_fence_after();
+      drain(256u);
+      mbar_arrive(cempty);
+      cphase ^= 1;
+      if (!active) continue;
+      const float* bias = (slot == 0) ? p.bias : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
+      float* outp = p.out + (long long)slot * p.out_slot;
+      const int m = m0 + quad * 32 + lane;
+      if (m < g.M) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int n = tn * BN + ncol + q * 4;
+          if (n >= g.Nd) continue;
+          float4 v = make_float4(accv[q * 4 + 0], accv[q * 4 + 1], accv[q * 4 + 2], accv[q * 4 + 3]);
+          if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          float4* dst = reinterpret_cast<float4*>(outp + (long long)m * g.Nd + n);
+          if (p.accumulate) {
+            const float4 o = *dst;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *dst = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // host: parity classes of a strided dgrad geometry; returns false (par.nclass = 0) when not applicable
 static inline bool hs_make_parity(const Geom& g, HsParity& par) {
   memset(&par, 0, sizeof(par));
@@ -1134,6 +1411,10 @@ static int hs_ready() {
                                       TcCfg<64>::SMEM_BYTES) == cudaSuccess;
       ok = ok && cudaFuncSetAttribute(wgrad_gemm_hs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       HSW_SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_hs_stack<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HSN_SMEM_BYTES) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(gather_gemm_hs_stack<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HSN_SMEM_BYTES) == cudaSuccess;
       ready = ok ? 1 : 0;
     }
   }
@@ -1332,6 +1613,22 @@ static inline bool hs_make_plane_map(CUtensorMap* map, const __half* base, int w
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// shared-activation segment of slots [slot_lo, slot_lo + nslots): returns 0 on success, >0 on a CUDA error
+static inline int hs_launch_gather_stack(const HsStackArgs& a_in, cudaStream_t st) {
+  if (hs_ready() <= 0) return -1;
+  const int sms = tc_sm_count();
+  HsStackArgs a = a_in;
+  a.flush = hs_flush();
+  const Geom& g = a.g;
+  if (g.mode != 0 || g.Cs % 8 != 0 || a.nslots < 1) return -1;
+  if (ceil_div(g.Kd, HS_BK) <= 8) a.flush = 8;  // short reductions: one main chunk per tile (<= 32 MMAs per chain)
+  const int BN = tc_bn(g.Nd), G = 256 / BN;
+  const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, BN) * ceil_div(a.nslots, G);
+  if (BN == 128) gather_gemm_hs_stack<128><<<ntiles < sms ? ntiles : sms, HSN_THREADS, HSN_SMEM_BYTES, st>>>(a);
+  else gather_gemm_hs_stack<64><<<ntiles < sms ? ntiles : sms, HSN_THREADS, HSN_SMEM_BYTES, st>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 static inline int hs_launch_wgrad(const HsWgradArgs& a_in, cudaStream_t st, bool allow_tma = true) {

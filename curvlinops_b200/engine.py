@@ -23,13 +23,10 @@ MAX_COLUMNS_PER_SWEEP = 8
 #: Replay the launches of a mini-batch product as one CUDA graph.  A product is a fixed sequence of ~450 kernel
 #: launches (plus tensor-map encodes) whose arguments depend only on pointers and shapes, so the second call
 #: with the same (program, data, parameter, column-count) key is captured and later calls replay it: the
-#: launch gaps (≈5 % of a ResNet-18 step, most of an MLP step) disappear.  V / out go through static buffers.
+#: launch gaps (a few % of a ResNet-18 step, most of an MLP step) disappear.
 #: Set to False to launch eagerly (per-launch profiling does so automatically).
 CUDA_GRAPHS = os.environ.get("CURV_CUDA_GRAPHS", "1") != "0"
 _MAX_GRAPHS = 8
-#: products whose V is larger than this run eagerly: their kernels are long enough to hide the launches, and
-#: the static-buffer copies of a replay would cost more than they save
-_GRAPH_MAX_V_BYTES = 32 << 20
 
 
 def _loss_code(loss_func) -> int:
@@ -113,7 +110,7 @@ class Engine:
         self.params = params
         self._programs: dict = {}
         self._ws: Tensor | None = None
-        self._graphs: dict = {}    # key -> [sightings, CUDAGraph | None, V_static, out_static]
+        self._graphs: dict = {}    # key (all baked-in pointers) -> [CUDAGraph | None]
         capi.lib()  # fail loudly if the CUDA library has not been built
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -184,34 +181,31 @@ class Engine:
                     ws.data_ptr(), ws.numel() * 4, strm))
 
         cfg = capi.lib().curv_launch_config()
-        if (not CUDA_GRAPHS or (cfg >> 16) or V.numel() * 4 > _GRAPH_MAX_V_BYTES
-                or torch.cuda.is_current_stream_capturing()):
+        if not CUDA_GRAPHS or (cfg >> 16) or torch.cuda.is_current_stream_capturing():
             launch(V, out, stream)
             del keep
             return
+        # The graph is keyed on every pointer it bakes in - including V and out: in steady state the caching
+        # allocator hands a caller that builds V / out per product the same blocks again, so replays need no
+        # staging copies; a different address is simply another key (eager first, captured on its second sighting).
         key = (id(prog), kind, loss, K, float(scale or 1.0), float(alpha), X.data_ptr(),
                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
-               tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg)
+               tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg, V.data_ptr(), out.data_ptr())
         entry = self._graphs.get(key)
         if entry is None:  # first sighting: eager (also warms up one-time initialisation inside the library)
             if len(self._graphs) >= _MAX_GRAPHS:
                 self._graphs.pop(next(iter(self._graphs)))
-            self._graphs[key] = [1, None, None, None]
+            self._graphs[key] = [None]
             launch(V, out, stream)
             del keep
             return
-        if entry[1] is None:  # second sighting: capture
-            Vs, outs = torch.empty_like(V), torch.empty_like(out)
+        if entry[0] is None:  # second sighting: capture (records the launches, does not run them)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(X.device)
             with torch.cuda.graph(g):
-                launch(Vs, outs, torch.cuda.current_stream(X.device).cuda_stream)
-            entry[1:] = [g, Vs, outs]
-        _, g, Vs, outs = entry
-        Vs.copy_(V)
-        outs.copy_(out)
-        g.replay()
-        out.copy_(outs)
+                launch(V, out, torch.cuda.current_stream(X.device).cuda_stream)
+            entry[0] = g
+        entry[0].replay()
         del keep
 
     def predict(self, X: Tensor) -> Tensor:

@@ -29,3 +29,10 @@ tot = sum(r[2] for r in rows)
 print(f"# one C2 step (ResNet-18, B={B}, K=8, fp32), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
 for k, n, ms in rows[:40]:
     print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:110]}")
+# per-launch durations of the contraction kernels, in launch order (layer attribution by position)
+evs = [e for e in prof.events() if e.device_time_total > 0 and ("gemm" in e.name)]
+evs.sort(key=lambda e: e.time_range.start)
+print("# contraction launches in order: name, ms")
+for e in evs:
+    nm = "gather128" if "hs<128>" in e.name else "gather64" if "hs<64>" in e.name else "wgrad_hs" if "wgrad_gemm_hs" in e.name else e.name[:40]
+    print(f"{nm:12s} {e.device_time_total / 1e3:7.3f}")

@@ -154,6 +154,73 @@ static Geom dgrad_geom(const Geom& f) {  // source = grad of out, destination = 
   return q;
 }
 
+// N-stacked shared-activation kernel: out_k = gather(A_0) W_k^T for slots slot_lo .. slot_lo + nslots - 1
+static void test_stack(const char* name, Geom g, int K, int slot_lo, int nslots, int accumulate, int with_bias) {
+  const long long a_elems = (long long)g.B * g.Hs * g.Ws * g.Cs;
+  const long long w_elems = (long long)g.N * g.Kd;
+  const long long o_elems = (long long)g.M * g.Nd;
+  std::vector<float> A(a_elems), W(w_elems * (1 + K)), out0(o_elems * (1 + K)), bias(g.Nd * (1 + K));
+  for (auto& v : A) v = frand() * 2.f;
+  for (int s = 0; s <= K; ++s) {
+    const float sc = 0.05f * powf(9.f, (float)(s % 4)) * (s == 2 ? 1e-6f : 1.f);
+    for (long long i = 0; i < w_elems; ++i) W[s * w_elems + i] = frand() * sc;
+  }
+  for (auto& v : out0) v = frand();
+  for (auto& v : bias) v = frand();
+  float *dA = dev(A), *dW = dev(W), *dout = dev(out0), *dbias = dev(bias);
+  std::vector<uint32_t> zero(64, 0);
+  uint32_t *abits = dev(zero), *wbits = dev(zero);
+  __half *Ah, *Al, *Wimg;
+  CK(cudaMalloc(&Ah, a_elems * 2 + 256)); CK(cudaMalloc(&Al, a_elems * 2 + 256));
+  const long long img = hs_image_halves(g.Nd, g.Kd);
+  CK(cudaMalloc(&Wimg, img * (1 + K) * 2 + 256));
+  if (hs_launch_absmax(dA, 0, a_elems, abits, 1, 0)) exit(3);
+  if (hs_launch_split(dA, 0, a_elems, Ah, Al, 0, abits, 1, 0)) exit(3);
+  if (hs_launch_absmax(dW, w_elems, w_elems, wbits, 1 + K, 0)) exit(3);
+  if (hs_launch_pack_image(dW, w_elems, Wimg, img, g.N, g.Nd, g.Kd, 1 + K, wbits, 0)) exit(3);
+  HsStackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g; a.Ah = Ah; a.Al = Al; a.a_bits = abits; a.W_img = Wimg; a.Wt_img = Wimg + img; a.Wt_img_slot = img;
+  a.w_bits = wbits; a.bias = with_bias ? dbias : nullptr; a.bias_t = with_bias ? dbias + g.Nd : nullptr;
+  a.bias_slot = g.Nd; a.out = dout; a.out_slot = o_elems; a.slot_lo = slot_lo; a.nslots = nslots;
+  a.accumulate = accumulate;
+  int rc = hs_launch_gather_stack(a, 0);
+  if (rc) { printf("%s: launch rc=%d\n", name, rc); exit(3); }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(4); }
+  std::vector<float> got(out0.size());
+  CK(cudaMemcpy(got.data(), dout, got.size() * 4, cudaMemcpyDeviceToHost));
+  double worst = 0;
+  std::vector<double> row(g.Kd);
+  for (int slot = 0; slot <= K; ++slot) {
+    const bool touched = slot >= slot_lo && slot < slot_lo + nslots;
+    double maxref = 0, maxerr = 0;
+    for (int m = 0; m < g.M; ++m) {
+      for (int r = 0; r < g.Kd; ++r) row[r] = gather_ref(g, A.data(), m, r);
+      for (int n = 0; n < g.N; ++n) {
+        double acc = 0;
+        if (touched) {
+          for (int r = 0; r < g.Kd; ++r) acc += row[r] * W[slot * w_elems + (long long)n * g.Kd + r];
+          if (with_bias) acc += bias[slot * g.Nd + n];
+          if (accumulate) acc += out0[slot * o_elems + (long long)m * g.Nd + n];
+        } else {
+          acc = out0[slot * o_elems + (long long)m * g.Nd + n];  // untouched slots must stay as they were
+        }
+        const double gv = got[slot * o_elems + (long long)m * g.Nd + n];
+        maxref = fmax(maxref, fabs(acc));
+        maxerr = fmax(maxerr, fabs(acc - gv));
+      }
+    }
+    worst = fmax(worst, maxerr / (maxref + 1e-300));
+  }
+  const bool ok = worst < 2e-6;
+  printf("%-44s M=%6d N=%4d Kd=%5d slots=%d..%d  max rel err %.3e  %s\n", name, g.M, g.N, g.Kd, slot_lo,
+         slot_lo + nslots - 1, worst, ok ? "PASS" : "FAIL");
+  if (!ok) ++n_fail;
+  cudaFree(dA); cudaFree(dW); cudaFree(dout); cudaFree(dbias); cudaFree(abits); cudaFree(wbits);
+  cudaFree(Ah); cudaFree(Al); cudaFree(Wimg);
+}
+
 static void test_wgrad(const char* name, Geom g, int NS, int slot0, int nsplit, double tol = 2e-6) {
   const long long i_elems = (long long)g.B * g.Hs * g.Ws * g.Cs;
   const int Ng = g.Nd;
@@ -311,6 +378,14 @@ int main(int argc, char** argv) {
     // many tiles: persistent loop with more tiles than SMs
     test_gather("fwd 3x3 s1 C64->64, K=8, big M", conv_geom(8, 28, 28, 64, 64, 3, 1, 1), 8, 1, 1, 0, 0, 0);
   }
+  if (which & 32) {
+    test_stack("stack 7x7 s2 C8->64 slots 0..8 (stem)", conv_geom(2, 30, 30, 8, 64, 7, 2, 3), 8, 0, 9, 0, 1);
+    test_stack("stack 3x3 s1 C64->64 slots 1..8 acc", conv_geom(2, 12, 12, 64, 64, 3, 1, 1), 8, 1, 8, 1, 0);
+    test_stack("stack 3x3 s2 C64->256 slots 1..5", conv_geom(3, 13, 13, 64, 256, 3, 2, 1), 5, 1, 5, 0, 0);
+    test_stack("stack 3x3 s1 C24->40 slots 0..2 bias", conv_geom(2, 9, 9, 24, 40, 3, 1, 1), 2, 0, 3, 0, 1);
+    test_stack("stack 3x3 s1 C128->64 slots 2..3 long K", conv_geom(1, 20, 20, 128, 64, 3, 1, 1), 4, 2, 2, 1, 0);
+    test_stack("stack 3x3 s1 C64->64 slots 1..8 big M", conv_geom(8, 28, 28, 64, 64, 3, 1, 1), 8, 1, 8, 0, 0);
+  }
   if (which & 2) {
     test_wgrad("wgrad 3x3 s1 C64->64 NS=8", conv_geom(2, 12, 12, 64, 64, 3, 1, 1), 8, 1, 2);
     test_wgrad("wgrad 3x3 s1 C64->128 NS=3", conv_geom(2, 12, 12, 64, 128, 3, 1, 1), 3, 1, 3);
@@ -326,6 +401,37 @@ int main(int argc, char** argv) {
     g_reps = 0;
     bench_layer("layer1 3x3 C64->64 @56", 128, 56, 64, 64, 3, 1);
     bench_layer("layer3 3x3 C256->256 @14", 128, 14, 256, 256, 3, 1);
+  }
+  if (which & 64) {  // N-stacked kernel at the stem / layer1 shapes (zero data)
+    auto bench_stack = [&](const char* name, int B, int H, int C, int Cout, int k, int s, int slot_lo, int ns) {
+      const int K = 8;
+      Geom f = conv_geom(B, H, H, C, Cout, k, s, k / 2);
+      const long long a_elems = (long long)B * H * H * C, o_elems = (long long)f.M * Cout;
+      const long long img = hs_image_halves(f.Nd, f.Kd);
+      __half *Ah, *Al, *Wimg; float* dO;
+      CK(cudaMalloc(&Ah, a_elems * 2)); CK(cudaMalloc(&Al, a_elems * 2)); CK(cudaMalloc(&Wimg, img * (1 + K) * 2));
+      CK(cudaMalloc(&dO, o_elems * (1 + K) * 4));
+      CK(cudaMemset(Ah, 0, a_elems * 2)); CK(cudaMemset(Al, 0, a_elems * 2)); CK(cudaMemset(Wimg, 0, img * (1 + K) * 2));
+      std::vector<uint32_t> zero(64, 0);
+      uint32_t *abits = dev(zero), *wbits = dev(zero);
+      HsStackArgs a;
+      memset(&a, 0, sizeof(a));
+      a.g = f; a.Ah = Ah; a.Al = Al; a.a_bits = abits; a.W_img = Wimg; a.Wt_img = Wimg + img; a.Wt_img_slot = img;
+      a.w_bits = wbits; a.out = dO; a.out_slot = o_elems; a.slot_lo = slot_lo; a.nslots = ns;
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      hs_launch_gather_stack(a, 0); CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      for (int i = 0; i < 3; ++i) hs_launch_gather_stack(a, 0);
+      cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+      const double F = 2.0 * f.M * Cout * (double)(k * k * C) * ns;
+      printf("%-34s %7.3f ms  %6.1f TF/s executed\n", name, ms, F / ms / 1e9);
+      cudaFree(Ah); cudaFree(Al); cudaFree(Wimg); cudaFree(dO); cudaFree(abits); cudaFree(wbits);
+    };
+    bench_stack("stem 7x7 s2 C8->64 @224, 9 slots", 128, 224, 8, 64, 7, 2, 0, 9);
+    bench_stack("layer1 3x3 C64->64 @56, slots 1..8", 128, 56, 64, 64, 3, 1, 1, 8);
+    bench_stack("layer2 3x3 C128->128 @28, slots 1..8", 128, 28, 128, 128, 3, 1, 1, 8);
+    bench_stack("layer3 3x3 C256->256 @14, slots 1..8", 128, 14, 256, 256, 3, 1, 1, 8);
   }
   if (which & 4) {
     bench_layer("layer1 3x3 C64->64 @56", 128, 56, 64, 64, 3, 1);
