@@ -81,6 +81,28 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic_per_launch():
+    """Mean dram__bytes_read + dram__bytes_write per launch of the gather GEMM kernels, from the committed
+    `ncu --set full` capture of one C2 step (profiles/r1_s2_hs_kernels_ncu_full_final.txt; tools/gpu_one_step.py)."""
+    import re
+
+    path = os.path.join(ROOT, "profiles", "r1_s2_hs_kernels_ncu_full_final.txt")
+    try:
+        blocks = open(path).read().split("---")
+    except OSError:
+        return None
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    tot, n = 0.0, 0
+    for b in blocks:
+        if "gather_gemm_hs<" not in b:
+            continue
+        vals = [re.search(name + r"\s+([\d.]+)\s+(\w+)", b) for name in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
+        if all(vals):
+            tot += sum(float(v.group(1)) * unit.get(v.group(2), 1.0) for v in vals)
+            n += 1
+    return tot / n if n else None
+
+
 def cpu_reference_run(torch, steps, warmup, sample_batch=32, sample_k=2):
     """Oracle port of the reference's CPU path on a bounded sample: `sample_batch` of the 128 samples and
     `sample_k` of the 8 columns; throughput extrapolated linearly in batch and columns
@@ -237,12 +259,15 @@ def main():
     ach = (fl[dom] / 1e12) / (ms[dom] / 1e3) if ms[dom] > 0 else 0.0
     roof = {
         "bound": "tensor", "kernel": ["gather_gemm (forward + dgrad)", "wgrad_gemm"][dom],
-        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+        "traffic": ncu_traffic_per_launch(),
         "peak_source": peak_src, "launches_timed": int(cnt[dom]),
         "share_of_step": (ms[dom] / nprof) / ms_step,
         "note": "fp32-grade result: every product is 3 fp16 tcgen05 MMAs on hi/lo split operands (half-split), "
                 "so the tensor-pipe ceiling for algorithmic FLOPs is peak/3; peak is the measured dense bf16/fp16 rate",
         "frac_of_split_ceiling": ach / (peak_tf / 3.0),
+        "traffic_note": "bytes of DRAM traffic per gather-GEMM launch (ncu, forward launches of one step; equals the "
+                        "algorithmic bytes of those launches: fp16 hi/lo planes in, fp32 result out, nothing re-read)",
         "other": {"kernel": ["gather_gemm", "wgrad_gemm"][1 - dom],
                   "tflops": (fl[1 - dom] / 1e12) / (ms[1 - dom] / 1e3) if ms[1 - dom] > 0 else 0.0,
                   "share_of_step": (ms[1 - dom] / nprof) / ms_step},

@@ -410,6 +410,11 @@ struct Ctx {
   bool rop;  // Hessian R-op: slot 0 of the cotangent storage holds the plain backward
   float** kfac_G = nullptr;  // KFAC mode: per node, the G factor to accumulate into (or null); no param grads
   float kfac_wG = 0.f;
+  // streaming calls (curv_matmat_batch_sync): per-parameter events.  v_ready[p]: the rows of V of parameter p are
+  // on the device (waited for before the node that owns p is prepared, lazily, inside the forward sweep);
+  // out_done[p]: recorded once the rows of `out` of parameter p are final (after the node's finish kernels).
+  void* const* v_ready = nullptr;
+  void* const* out_done = nullptr;
   // half-split path: enabled per call; hs_valid[e] = absmax entry e already computed in this call
   bool hs = false;
   std::vector<char>* hs_valid = nullptr;
@@ -479,11 +484,16 @@ static int hs_split(const Ctx& c, const float* x, long long slot_stride, long lo
 }
 
 // pack parameters (and, if with_tangents, the K columns of V) into the engine's layouts
-static int prepare_params(const Ctx& c, bool with_tangents) {
+static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
   curv_program* P = c.P;
   cudaStream_t st = c.st;
-  for (Node& n : P->nodes) {
+  {
     const curv_node_desc& d = n.d;
+    if (c.v_ready && with_tangents) {  // streaming call: the columns of V of this node's parameters must have landed
+      for (int p : {d.p0, d.p1})
+        if ((d.op == CURV_OP_CONV || d.op == CURV_OP_AFFINE) && p >= 0 && c.v_ready[p])
+          CHECK_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)c.v_ready[p], 0));
+    }
     if (d.op == CURV_OP_CONV) {
       const Geom& g = n.fwd;
       const Value& vi = P->values[d.in0];
@@ -582,6 +592,24 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
   }
   return CURV_OK;
 }
+// all nodes up front (default), or lazily node by node inside the forward sweep (streaming calls, so that the
+// upload of later parameters' columns overlaps the first layers)
+static int prepare_params(const Ctx& c, bool with_tangents) {
+  if (c.v_ready) return CURV_OK;  // lazily, in forward()
+  for (Node& n : c.P->nodes) {
+    int rc = prepare_node(c, n, with_tangents);
+    if (rc) return rc;
+  }
+  return CURV_OK;
+}
+// parameter rows of `out` owned by node n are final: signal the streaming caller
+static int signal_out_done(const Ctx& c, const Node& n) {
+  if (!c.out_done) return CURV_OK;
+  for (int p : {n.d.p0, n.d.p1})
+    if ((n.d.op == CURV_OP_CONV || n.d.op == CURV_OP_AFFINE) && p >= 0 && c.out_done[p])
+      CHECK_CUDA(cudaEventRecord((cudaEvent_t)c.out_done[p], c.st));
+  return CURV_OK;
+}
 
 // forward sweep: primal only (K = 0) or primal + K tangents
 static int forward(const Ctx& c, const void* X, int K) {
@@ -599,6 +627,10 @@ static int forward(const Ctx& c, const void* X, int K) {
     const Value& vi = P->values[d.in0];
     const Value& vo = P->values[d.out];
     const int nsl = (vo.tan && K > 0) ? 1 + K : 1;
+    if (c.v_ready) {
+      int rc = prepare_node(c, n, K > 0);
+      if (rc) return rc;
+    }
     switch (d.op) {
       case CURV_OP_CONV: {
         double fl = conv_flops(n.fwd, vi.C) *
@@ -967,15 +999,49 @@ static int backward(const Ctx& c, int K) {
       default:
         return fail(CURV_ERR_UNSUPPORTED, "unsupported op in backward sweep");
     }
+    {
+      int rc = signal_out_done(c, n);
+      if (rc) return rc;
+    }
   }
   return CURV_OK;
 }
+
+static int matmat_batch_impl(curv_program* P, int kind, int loss, const void* const* param_ptrs,
+                             const void* const* const_ptrs, const void* X, const void* y, const float* mc_grad,
+                             int mc_samples, const float* V, float* out, int K, int ldk, int k0, float loss_scale,
+                             float alpha, void* workspace, size_t workspace_bytes, void* stream,
+                             void* const* v_ready, void* const* out_done);
 
 extern "C" int curv_matmat_batch(curv_program* P, int kind, int loss, const void* const* param_ptrs,
                                  const void* const* const_ptrs, const void* X, const void* y,
                                  const float* mc_grad, int mc_samples, const float* V, float* out, int K,
                                  int ldk, int k0, float loss_scale, float alpha, void* workspace,
                                  size_t workspace_bytes, void* stream) {
+  return matmat_batch_impl(P, kind, loss, param_ptrs, const_ptrs, X, y, mc_grad, mc_samples, V, out, K, ldk, k0,
+                           loss_scale, alpha, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+// Streaming variant: v_ready[p] / out_done[p] are cudaEvent_t handles per parameter (either array or single entries
+// may be NULL).  The columns of V of parameter p are only read after v_ready[p] (the node that owns p is prepared
+// lazily inside the forward sweep), and out_done[p] is recorded on `stream` as soon as the rows of parameter p in
+// `out` are final, so a caller can overlap the upload of V and the download of the result with the sweeps.
+extern "C" int curv_matmat_batch_sync(curv_program* P, int kind, int loss, const void* const* param_ptrs,
+                                      const void* const* const_ptrs, const void* X, const void* y,
+                                      const float* mc_grad, int mc_samples, const float* V, float* out, int K,
+                                      int ldk, int k0, float loss_scale, float alpha, void* workspace,
+                                      size_t workspace_bytes, void* stream, void* const* v_ready,
+                                      void* const* out_done) {
+  return matmat_batch_impl(P, kind, loss, param_ptrs, const_ptrs, X, y, mc_grad, mc_samples, V, out, K, ldk, k0,
+                           loss_scale, alpha, workspace, workspace_bytes, stream, v_ready, out_done);
+}
+
+static int matmat_batch_impl(curv_program* P, int kind, int loss, const void* const* param_ptrs,
+                                 const void* const* const_ptrs, const void* X, const void* y,
+                                 const float* mc_grad, int mc_samples, const float* V, float* out, int K,
+                                 int ldk, int k0, float loss_scale, float alpha, void* workspace,
+                                 size_t workspace_bytes, void* stream, void* const* v_ready,
+                                 void* const* out_done) {
   if (!P) return fail(CURV_ERR_INVALID, "null program");
   if (kind != CURV_KIND_FORWARD && (K < 1 || K > P->kmax))
     return fail(CURV_ERR_INVALID, "K must be in [1, kmax]");
@@ -991,6 +1057,7 @@ extern "C" int curv_matmat_batch(curv_program* P, int kind, int loss, const void
   c.P = P; c.ws = (float*)workspace; c.pp = param_ptrs; c.cp = const_ptrs; c.V = V; c.out = out;
   c.K = K; c.ldk = ldk; c.k0 = k0; c.alpha = alpha; c.st = (cudaStream_t)stream; c.kind = kind;
   c.rop = kind == CURV_KIND_HESSIAN;
+  c.v_ready = v_ready; c.out_done = out_done;
   std::vector<char> hs_valid;
   if (g_tc_mode && !(g_tc_disable & 32) && !c.rop && P->hs1_elems > 0 && hs_ready() > 0) {
     c.hs = true;
