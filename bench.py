@@ -8,7 +8,8 @@ X = rand(128, 3, 224, 224), y = randint(1000), V = rand(P, 8), fp32, CrossEntrop
 ``value`` = P*K / t_step (param-dim x vectors per second), inputs resident in HBM.  With N > 1 the
 mini-batch is sharded over the ranks (strong scaling: total work fixed) and the [P, K] result is summed
 with one NCCL all-reduce.  ``e2e`` is the same product through the public operator API with HOST
-buffers (pinned X and V copied to the device and the result copied back inside the timed region).
+buffers (``matmat_pinned``: pinned X, y and V copied to the device and the result copied back inside the timed
+region, V / result pipelined in parameter buckets against the sweeps).
 ``--impl reference`` times the CPU oracle port (the reference is pure Python and cannot travel to the
 GPU box) on the host cores, on a bounded sample of the same workload.
 """
@@ -205,7 +206,9 @@ def main():
     out_host = torch.empty(P, K).pin_memory()
 
     def step_e2e():
-        out_host.copy_(G_host @ V_host.to(dev, non_blocking=True), non_blocking=True)
+        # public host-operand API: V (pinned) in, result (pinned) out, X / y uploaded from pinned memory inside;
+        # the upload of V and the download of the result are pipelined against the sweeps in parameter buckets
+        G_host.matmat_pinned(V_host, out_host)
         torch.cuda.current_stream().synchronize()  # the result is on the host when the step ends
         return out_host
 

@@ -38,7 +38,7 @@ class NodeDesc(C.Structure):
 
 EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
-    "curv_program_value_layout", "curv_matmat_batch", "curv_kfac_accumulate_batch",
+    "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
     L.curv_matmat_batch.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, i, vp, vp,
                                     i, i, i, f, f, vp, C.c_size_t, vp]
     L.curv_matmat_batch.restype = i
+    L.curv_matmat_batch_sync.argtypes = L.curv_matmat_batch.argtypes + [C.POINTER(vp), C.POINTER(vp)]
+    L.curv_matmat_batch_sync.restype = i
     L.curv_kfac_accumulate_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(i), i,
                                              C.POINTER(vp), C.POINTER(vp), C.POINTER(i), vp, i, f, f,
                                              vp, C.c_size_t, vp]

@@ -243,10 +243,99 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
     def _batch_call_sharded(self, X, y, V, out, alpha, scale):
         self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0])
 
+    # ---- host-resident operands: pipelined upload / download ----------------------------------------
+    #: a kind whose mini-batch product is one engine call with (X, y, V, out) only may stream
+    _STREAMABLE = True
+
+    def matmat_pinned(self, V: Tensor, out: Tensor | None = None, bucket_bytes: int = 48 << 20) -> Tensor:
+        """``A @ V`` for a host-resident flat ``[P, K]`` matrix, returned on the host.
+
+        This is what the reference's SciPy bridge does per product (``_torch_base.py:560-592``: matrix to the
+        device, multiply, result back to the host), but pipelined: V is uploaded in parameter buckets on a copy
+        stream while the forward sweep already runs on the first layers (the engine waits per parameter for its
+        columns), and the result is downloaded bucket by bucket while the backward sweep is still producing the
+        earlier parameters (it finishes the last parameters first).  Use pinned host tensors for truly
+        asynchronous copies; the returned tensor is complete once the current stream has been synchronised.
+        """
+        dev = self.device
+        sizes = [p.numel() for p in self._params.values()]
+        Pn = sum(sizes)
+        if V.ndim != 2 or V.shape[0] != Pn:
+            raise ValueError(f"Expected a flat [P={Pn}, K] matrix, got {tuple(V.shape)}.")
+        K = V.shape[1]
+        _, world = cdist.rank_world()
+        from .engine import MAX_COLUMNS_PER_SWEEP
+
+        if (dev.type != "cuda" or world > 1 or not self._STREAMABLE or K > MAX_COLUMNS_PER_SWEEP
+                or getattr(self, "_mc_samples", 0) > 0):
+            res = (self @ V.to(dev)).to("cpu")  # general path: whole-matrix copies
+            if out is not None:
+                out.copy_(res)
+                return out
+            return res
+        V = V.to(torch.float32)
+        if out is None:
+            out = torch.empty(Pn, K, dtype=torch.float32, pin_memory=True)
+        # buckets of whole parameters, about bucket_bytes each; the first one is small: it gates the start of the
+        # forward sweep on the way in and is the only download that cannot overlap the backward sweep
+        buckets, lo, plist, acc = [], 0, [], 0
+        for i, n in enumerate(sizes):
+            plist.append(i)
+            acc += n
+            limit = min(bucket_bytes, 4 << 20) if not buckets else bucket_bytes
+            if acc * K * 4 >= limit or i == len(sizes) - 1:
+                buckets.append((lo, lo + acc, plist))
+                lo, plist, acc = lo + acc, [], 0
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._copy_streams
+        Vd = torch.empty(Pn, K, dtype=torch.float32, device=dev)
+        outd = torch.zeros(Pn, K, dtype=torch.float32, device=dev)
+        v_ready, out_done, bucket_events = [None] * len(sizes), [None] * len(sizes), []
+        # the first mini-batch goes up BEFORE V: host-to-device copies share one DMA queue, and the forward
+        # sweep needs X first
+        batches = iter(self._loop_over_data(desc="matmat_pinned"))
+        cur = next(batches, None)
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            for blo, bhi, ps in buckets:
+                Vd[blo:bhi].copy_(V[blo:bhi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                for i in ps:
+                    v_ready[i] = e
+        for blo, bhi, ps in buckets:
+            e = torch.cuda.Event()
+            e.record(main)  # materialises the handle; the engine records it again when the rows are final
+            bucket_events.append(e)
+            for i in ps:
+                out_done[i] = e
+        first = True
+        while cur is not None:
+            nxt = next(batches, None)
+            X, y = cur
+            if not isinstance(X, Tensor):
+                raise NotImplementedError("The B200 engine needs tensor inputs X.")
+            self._engine.matmat_batch(self.KIND, X, y, Vd, outd, self._get_normalization_factor(X, y),
+                                      v_ready=v_ready if first else None,
+                                      out_done=out_done if nxt is None else None)
+            first, cur = False, nxt
+        with torch.cuda.stream(s_out):
+            for (blo, bhi, _), e in zip(reversed(buckets), reversed(bucket_events)):
+                s_out.wait_event(e)
+                out[blo:bhi].copy_(outd[blo:bhi], non_blocking=True)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+        Vd.record_stream(s_in)
+        outd.record_stream(s_out)
+        return out
+
     def __getstate__(self):
         # compiled programs / workspaces are per-process handles: rebuild lazily after unpickling
         st = self.__dict__.copy()
         st["_engine"] = None
+        st["_copy_streams"] = None
         return st
 
     def __setstate__(self, st):
@@ -319,6 +408,7 @@ class EFLinearOperator(CurvatureLinearOperator):
 
     SELF_ADJOINT = True
     KIND = capi.KIND_GGN_MC
+    _STREAMABLE = False  # needs the per-sample loss gradients as an extra operand
     SUPPORTED_LOSSES = (MSELoss, CrossEntropyLoss, BCEWithLogitsLoss)
 
     def __init__(self, model_func, loss_func, params, data, progressbar=False, check_deterministic=True,

@@ -146,8 +146,13 @@ class Engine:
 
     # -- the hot call ----------------------------------------------------------------------------
     def matmat_batch(self, kind: int, X: Tensor, y: Tensor | None, V: Tensor, out: Tensor, alpha: float,
-                     mc_grad: Tensor | None = None, scale: float | None = None) -> None:
-        """``out += alpha * (mini-batch matrix) @ V`` with ``V``/``out`` flat ``[P, K]`` fp32 on device."""
+                     mc_grad: Tensor | None = None, scale: float | None = None,
+                     v_ready: list | None = None, out_done: list | None = None) -> None:
+        """``out += alpha * (mini-batch matrix) @ V`` with ``V``/``out`` flat ``[P, K]`` fp32 on device.
+
+        ``v_ready`` / ``out_done``: optional per-parameter ``torch.cuda.Event`` lists (entries may be ``None``) for
+        the streaming entry point ``curv_matmat_batch_sync`` (see ``include/curvb200.h``); needs ``K`` columns
+        that fit one sweep."""
         self._check_supported()
         K = V.shape[-1]
         kc = min(K, MAX_COLUMNS_PER_SWEEP)
@@ -171,6 +176,21 @@ class Engine:
         if mc_grad is not None:
             mc_grad = mc_grad.to(torch.float32).contiguous()
             M = mc_grad.shape[1]
+        if v_ready is not None or out_done is not None:
+            if K > kc:
+                raise ValueError(f"Streaming products take at most {kc} columns per call.")
+            n = len(keep)
+            ev_in = capi.ptr_array([e.cuda_event if e is not None else None for e in (v_ready or [None] * n)])
+            ev_out = capi.ptr_array([e.cuda_event if e is not None else None for e in (out_done or [None] * n)])
+            capi.check(capi.lib().curv_matmat_batch_sync(
+                prog.handle, kind, loss, pptrs, prog.const_ptrs, X.data_ptr(),
+                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
+                V.data_ptr(), out.data_ptr(), K, K, 0, float(scale or 1.0), float(alpha),
+                ws.data_ptr(), ws.numel() * 4, stream,
+                ev_in if v_ready is not None else None, ev_out if out_done is not None else None))
+            del keep
+            return
+
         def launch(Vt: Tensor, outt: Tensor, strm: int) -> None:
             for k0 in range(0, K, kc):
                 kk = min(kc, K - k0)

@@ -136,6 +136,20 @@ int curv_matmat_batch(curv_program* prog, int kind, int loss, const void* const*
                       int k0, float loss_scale, float alpha, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Streaming variant for callers whose V / result live in host memory (the reference's SciPy bridge,
+ * _torch_base.py:560-592, moves the whole [P, K] matrix to the device, multiplies, and moves the result back).
+ * v_ready[n_params] / out_done[n_params] hold cudaEvent_t handles (arrays or single entries may be NULL):
+ *   - the columns of V belonging to parameter p are not read before v_ready[p] has completed (the node owning p
+ *     is prepared lazily inside the forward sweep), so an upload in parameter order overlaps the first layers;
+ *   - out_done[p] is recorded on `stream` as soon as the rows of parameter p in `out` are final (the backward
+ *     sweep finishes the LAST parameters first), so their download overlaps the rest of the sweep.
+ * Everything else as curv_matmat_batch. */
+int curv_matmat_batch_sync(curv_program* prog, int kind, int loss, const void* const* param_ptrs,
+                           const void* const* const_ptrs, const void* X, const void* y,
+                           const float* mc_grad, int mc_samples, const float* V, float* out, int K, int ldk,
+                           int k0, float loss_scale, float alpha, void* workspace, size_t workspace_bytes,
+                           void* stream, void* const* v_ready, void* const* out_done);
+
 /* KFAC-expand factor accumulation for one mini-batch (kfac_hooks.py:176-393):
  *   A_l += wA * sum_{n,s} a~ a~^T        a~ = im2col patch of the layer input (+1 if joint bias)
  *   G_l += wG * sum_{v,n,s} g g^T        g  = backpropagated grad_outputs[v]
