@@ -150,42 +150,63 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
 
 // ------------------------------------------------------------------ forward + tangent
 // y_0 = s*x_0 + t ;  y_k = s*x_k + sdot_k*x_0 + tdot_k     grid.y = slot
-__global__ void affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
-                                  const float* __restrict__ coef, int coef_has_tan,
-                                  float* __restrict__ y, long long y_slot, long long rows, int Cp,
-                                  int relu, unsigned int* __restrict__ amax) {
-  const int slot = blockIdx.y;
-  float am = 0.f;
+// grid.y = slot GROUP: group g handles the tangent slots 1 + 8g .. 8 + 8g (and, for g = 0, the primal slot 0), so the
+// primal input - needed by every slot for the tangent of the coefficients and for the ReLU mask - is read once per
+// group instead of once per slot.
+__global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
+                                                         const float* __restrict__ coef, int coef_has_tan,
+                                                         float* __restrict__ y, long long y_slot, long long rows,
+                                                         int Cp, int relu, int nslots,
+                                                         unsigned int* __restrict__ amax) {
+  const int grp = blockIdx.y;
+  const int k_lo = 1 + 8 * grp;  // first tangent slot of the group
   const int C4 = Cp >> 2;
   const long long total = rows * C4;
+  const long long xs4 = x_slot >> 2, ys4 = y_slot >> 2;
   const float4* x0 = reinterpret_cast<const float4*>(x);
-  const float4* xk = reinterpret_cast<const float4*>(x + slot * x_slot);
-  float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
+  float4* y0 = reinterpret_cast<float4*>(y);
   const float4* s4 = reinterpret_cast<const float4*>(coef);
   const float4* t4 = reinterpret_cast<const float4*>(coef + Cp);
-  const float4* sd4 = reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp);
-  const float4* td4 = reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp + Cp);
+  float am[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) am[j] = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    float4 r;
-    if (slot == 0) {
-      r = f4fma(__ldg(s4 + c4), __ldg(x0 + i), __ldg(t4 + c4));
-      if (relu) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
-    } else {
-      r = f4zero();
-      if (x_has_slots) r = f4mul(__ldg(s4 + c4), __ldg(xk + i));
-      if (coef_has_tan) r = f4add(r, f4fma(__ldg(sd4 + c4), __ldg(x0 + i), __ldg(td4 + c4)));
-      if (relu) {  // fused ReLU: mask with the sign of the primal pre-activation (recomputed, not re-read)
-        const float4 pre = f4fma(__ldg(s4 + c4), __ldg(x0 + i), __ldg(t4 + c4));
-        r = make_float4(pre.x > 0.f ? r.x : 0.f, pre.y > 0.f ? r.y : 0.f, pre.z > 0.f ? r.z : 0.f,
-                        pre.w > 0.f ? r.w : 0.f);
+    const int c4 = (int)(i % C4);
+    const float4 sv = __ldg(s4 + c4), xv = __ldg(x0 + i);
+    const float4 pre = f4fma(sv, xv, __ldg(t4 + c4));
+    if (grp == 0) {
+      const float4 r = relu ? make_float4(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f), fmaxf(pre.z, 0.f), fmaxf(pre.w, 0.f))
+                            : pre;
+      y0[i] = r;
+      am[0] = f4absmax(am[0], r);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = k_lo + j;
+      if (slot < nslots) {
+        float4 r = f4zero();
+        if (x_has_slots) r = f4mul(sv, __ldg(x0 + slot * xs4 + i));
+        if (coef_has_tan) {
+          const float4* sd4 = reinterpret_cast<const float4*>(coef + (long long)slot * 2 * Cp);
+          r = f4add(r, f4fma(__ldg(sd4 + c4), xv, __ldg(sd4 + C4 + c4)));
+        }
+        if (relu)  // fused ReLU: mask with the sign of the primal pre-activation
+          r = make_float4(pre.x > 0.f ? r.x : 0.f, pre.y > 0.f ? r.y : 0.f, pre.z > 0.f ? r.z : 0.f,
+                          pre.w > 0.f ? r.w : 0.f);
+        y0[slot * ys4 + i] = r;
+        am[1 + j] = f4absmax(am[1 + j], r);
       }
     }
-    yo[i] = r;
-    am = f4absmax(am, r);
   }
-  if (amax) block_absmax_commit(am, amax + slot);
+  if (amax) {
+    if (grp == 0) block_absmax_commit(am[0], amax);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __syncthreads();
+      if (k_lo + j < nslots) block_absmax_commit(am[1 + j], amax + k_lo + j);
+    }
+  }
 }
 
 __device__ __forceinline__ float act_apply(int kind, float x) {
@@ -270,51 +291,79 @@ __global__ void axpy_slots_kernel(const float* __restrict__ src, long long src_s
 }
 
 // fused residual join + ReLU:  y_0 = relu(a_0 + b_0),  y_k = [a_0 + b_0 > 0] (a_k + b_k).  grid.y = slot
-__global__ void add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot, int a_has_slots,
-                                    const float* __restrict__ b, long long b_slot, int b_has_slots,
-                                    float* __restrict__ y, long long y_slot, long long n4,
-                                    unsigned int* __restrict__ amax) {
-  const int slot = blockIdx.y;
-  float am = 0.f;
+// grid.y = slot group (see affine_fwd_kernel): the primal sum a_0 + b_0 (the ReLU mask) is formed once per group
+__global__ void __launch_bounds__(256) add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot,
+                                                           int a_has_slots, const float* __restrict__ b,
+                                                           long long b_slot, int b_has_slots, float* __restrict__ y,
+                                                           long long y_slot, long long n4, int nslots,
+                                                           unsigned int* __restrict__ amax) {
+  const int grp = blockIdx.y;
+  const int k_lo = 1 + 8 * grp;
+  const long long as4 = a_slot >> 2, bs4 = b_slot >> 2, ys4 = y_slot >> 2;
   const float4* a0 = reinterpret_cast<const float4*>(a);
   const float4* b0 = reinterpret_cast<const float4*>(b);
-  const float4* ak = reinterpret_cast<const float4*>(a + slot * a_slot);
-  const float4* bk = reinterpret_cast<const float4*>(b + slot * b_slot);
-  float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
+  float4* y0 = reinterpret_cast<float4*>(y);
+  float am[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) am[j] = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 p = f4add(__ldg(a0 + i), __ldg(b0 + i));
-    float4 r;
-    if (slot == 0) {
-      r = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(p.z, 0.f), fmaxf(p.w, 0.f));
-    } else {
-      r = f4zero();
-      if (a_has_slots) r = __ldg(ak + i);
-      if (b_has_slots) r = f4add(r, __ldg(bk + i));
-      r = make_float4(p.x > 0.f ? r.x : 0.f, p.y > 0.f ? r.y : 0.f, p.z > 0.f ? r.z : 0.f, p.w > 0.f ? r.w : 0.f);
+    if (grp == 0) {
+      const float4 r = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(p.z, 0.f), fmaxf(p.w, 0.f));
+      y0[i] = r;
+      am[0] = f4absmax(am[0], r);
     }
-    yo[i] = r;
-    am = f4absmax(am, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = k_lo + j;
+      if (slot < nslots) {
+        float4 r = f4zero();
+        if (a_has_slots) r = __ldg(a0 + slot * as4 + i);
+        if (b_has_slots) r = f4add(r, __ldg(b0 + slot * bs4 + i));
+        r = make_float4(p.x > 0.f ? r.x : 0.f, p.y > 0.f ? r.y : 0.f, p.z > 0.f ? r.z : 0.f, p.w > 0.f ? r.w : 0.f);
+        y0[slot * ys4 + i] = r;
+        am[1 + j] = f4absmax(am[1 + j], r);
+      }
+    }
   }
-  if (amax) block_absmax_commit(am, amax + slot);
+  if (amax) {
+    if (grp == 0) block_absmax_commit(am[0], amax);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __syncthreads();
+      if (k_lo + j < nslots) block_absmax_commit(am[1 + j], amax + k_lo + j);
+    }
+  }
 }
 // adjoint: g = [y_0 > 0] gy_k ;  ga_k (+)= g ;  gb_k (+)= g   (either destination may be null)
-__global__ void add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
-                                    const float* __restrict__ y0, float* __restrict__ ga, long long ga_slot,
-                                    int acc_a, float* __restrict__ gb, long long gb_slot, int acc_b,
-                                    long long n4, int slot0) {
-  const int slot = slot0 + blockIdx.y;
-  const float4* g = reinterpret_cast<const float4*>(gy + slot * gy_slot);
+// grid.y = groups of 8 cotangent slots: the primal output y0 (the ReLU mask) is read once per group
+__global__ void __launch_bounds__(256) add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                                           const float* __restrict__ y0, float* __restrict__ ga,
+                                                           long long ga_slot, int acc_a, float* __restrict__ gb,
+                                                           long long gb_slot, int acc_b, long long n4, int slot0,
+                                                           int nslots) {
+  const int s_lo = slot0 + 8 * blockIdx.y;
+  const int s_hi = min(slot0 + nslots, s_lo + 8);
+  const long long gs4 = gy_slot >> 2, as4 = ga_slot >> 2, bs4 = gb_slot >> 2;
+  const float4* g = reinterpret_cast<const float4*>(gy);
   const float4* p4 = reinterpret_cast<const float4*>(y0);
-  float4* oa = ga ? reinterpret_cast<float4*>(ga + slot * ga_slot) : nullptr;
-  float4* ob = gb ? reinterpret_cast<float4*>(gb + slot * gb_slot) : nullptr;
+  float4* oa = reinterpret_cast<float4*>(ga);
+  float4* ob = reinterpret_cast<float4*>(gb);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(g + i), p = __ldg(p4 + i);
-    const float4 r = make_float4(p.x > 0.f ? v.x : 0.f, p.y > 0.f ? v.y : 0.f, p.z > 0.f ? v.z : 0.f,
-                                 p.w > 0.f ? v.w : 0.f);
-    if (oa) oa[i] = acc_a ? f4add(r, oa[i]) : r;
-    if (ob) ob[i] = acc_b ? f4add(r, ob[i]) : r;
+    const float4 p = __ldg(p4 + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = s_lo + j;
+      if (slot < s_hi) {
+        const float4 v = __ldg(g + slot * gs4 + i);
+        const float4 r = make_float4(p.x > 0.f ? v.x : 0.f, p.y > 0.f ? v.y : 0.f, p.z > 0.f ? v.z : 0.f,
+                                     p.w > 0.f ? v.w : 0.f);
+        if (oa) oa[slot * as4 + i] = acc_a ? f4add(r, oa[slot * as4 + i]) : r;
+        if (ob) ob[slot * bs4 + i] = acc_b ? f4add(r, ob[slot * bs4 + i]) : r;
+      }
+    }
   }
 }
 

@@ -697,9 +697,9 @@ static int forward(const Ctx& c, const void* X, int K) {
       }
       case CURV_OP_AFFINE: {
         long long rows = (long long)P->B * vi.H * vi.W;
-        affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl), 256, 0, st>>>(
+        affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl > 1 ? (nsl + 6) / 8 : 1), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
-            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0,
+            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl,
             hs_fused_absmax(c, c.bits_act(d.out), nsl));
         LAUNCH_CHECK();
         break;
@@ -723,9 +723,9 @@ static int forward(const Ctx& c, const void* X, int K) {
         const Value& vj = P->values[d.in1];
         long long n4 = vo.slot_elems / 4;
         if (d.kh == 2) {  // fused residual join + ReLU
-          add_relu_fwd_kernel<<<dim3(grid1d(n4), nsl), 256, 0, st>>>(
+          add_relu_fwd_kernel<<<dim3(grid1d(n4), nsl > 1 ? (nsl + 6) / 8 : 1), 256, 0, st>>>(
               c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.act(d.in1), vj.slot_elems, vj.tan ? 1 : 0,
-              c.act(d.out), vo.slot_elems, n4, hs_fused_absmax(c, c.bits_act(d.out), nsl));
+              c.act(d.out), vo.slot_elems, n4, nsl, hs_fused_absmax(c, c.bits_act(d.out), nsl));
           LAUNCH_CHECK();
           break;
         }
@@ -955,9 +955,9 @@ static int backward(const Ctx& c, int K) {
         const Value& vj = P->values[d.in1];
         long long n4 = vo.slot_elems / 4;
         if (d.kh == 2) {  // fused residual join + ReLU
-          add_relu_bwd_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(
+          add_relu_bwd_kernel<<<dim3(grid1d(n4), (ns + 7) / 8), 256, 0, st>>>(
               c.grad(d.out), vo.slot_elems, c.act(d.out), vi.tan ? c.grad(d.in0) : nullptr, vi.slot_elems,
-              ginit[d.in0], vj.tan ? c.grad(d.in1) : nullptr, vj.slot_elems, ginit[d.in1], n4, s0);
+              ginit[d.in0], vj.tan ? c.grad(d.in1) : nullptr, vj.slot_elems, ginit[d.in1], n4, s0, ns);
           LAUNCH_CHECK();
           if (vi.tan) ginit[d.in0] = 1;
           if (vj.tan) ginit[d.in1] = 1;
