@@ -65,4 +65,27 @@ inline __host__ __device__ int ceil_div(int a, int b) { return (a + b - 1) / b; 
 inline __host__ __device__ int pad4(int c) { return (c + 3) & ~3; }
 inline __host__ __device__ int pad8(int c) { return (c + 7) & ~7; }
 
+// ---- half-split operand scales (hs_gemm.cuh): one power of two per (tensor, slot)
+constexpr int HS_SH_TARGET = 14;  // scaled maximum in [2^14, 2^15)
+constexpr int HS_SH_CLAMP = 60;   // |sh| <= 60: products of two inverse scales stay normal floats
+
+// scale exponent sh (s = 2^sh) from the bit pattern of the slot's absolute maximum
+__host__ __device__ inline int hs_shift_from_bits(uint32_t bits) {
+  if (bits == 0u) return 0;  // all-zero slot
+  const int e = (int)((bits >> 23) & 0xffu) - 127;
+  int sh = HS_SH_TARGET - e;
+  if (sh > HS_SH_CLAMP) sh = HS_SH_CLAMP;
+  if (sh < -HS_SH_CLAMP) sh = -HS_SH_CLAMP;
+  return sh;
+}
+__host__ __device__ inline float hs_pow2(int sh) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((uint32_t)(sh + 127) << 23);
+#else
+  union { uint32_t u; float f; } c;
+  c.u = (uint32_t)(sh + 127) << 23;
+  return c.f;
+#endif
+}
+
 }  // namespace curv

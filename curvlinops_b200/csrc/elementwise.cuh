@@ -3,6 +3,8 @@
 // apply and the deterministic finishing reductions.  All tensors are [slot][rows][Cp] fp32 with
 // Cp % 4 == 0, so every access is a coalesced float4.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace curv {
@@ -124,7 +126,8 @@ __global__ void pack_vec_kernel(const float* __restrict__ src, long long es, flo
 // aux [2][Cp] = (invstd, mean).   gamma/beta null -> 1 / 0.  gdot/bdot: columns of V (stride ldk).
 __global__ void affine_prep_kernel(const float* gamma, const float* beta, const float* mean,
                                    const float* var, float eps, const float* gdot, const float* bdot,
-                                   long long ldk, int K, int C, int Cp, float* coef, float* aux) {
+                                   long long ldk, int K, int C, int Cp, float* coef, float* aux,
+                                   unsigned int* smax_bits) {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Cp; c += gridDim.x * blockDim.x) {
     float invstd = 0.f, mu = 0.f, s = 0.f, tt = 0.f;
     if (c < C) {
@@ -136,6 +139,7 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
     }
     coef[c] = s; coef[Cp + c] = tt;
     aux[c] = invstd; aux[Cp + c] = mu;
+    if (smax_bits && s != 0.f) atomicMax(smax_bits, __float_as_uint(fabsf(s)));  // max_c |s_c|: bound of the adjoint
     for (int k = 0; k < K; ++k) {
       float sd = 0.f, td = 0.f;
       if (c < C) {
@@ -342,7 +346,12 @@ __global__ void __launch_bounds__(256) add_relu_bwd_kernel(const float* __restri
                                                            const float* __restrict__ y0, float* __restrict__ ga,
                                                            long long ga_slot, int acc_a, float* __restrict__ gb,
                                                            long long gb_slot, int acc_b, long long n4, int slot0,
-                                                           int nslots) {
+                                                           int nslots, unsigned int* __restrict__ amax_a,
+                                                           unsigned int* __restrict__ amax_b) {
+  // amax_a / amax_b (nullable, indexed by absolute slot): fused absmax of what is written to ga / gb
+  float am[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) am[j] = 0.f;
   const int s_lo = slot0 + 8 * blockIdx.y;
   const int s_hi = min(slot0 + nslots, s_lo + 8);
   const long long gs4 = gy_slot >> 2, as4 = ga_slot >> 2, bs4 = gb_slot >> 2;
@@ -362,6 +371,18 @@ __global__ void __launch_bounds__(256) add_relu_bwd_kernel(const float* __restri
                                      p.w > 0.f ? v.w : 0.f);
         if (oa) oa[slot * as4 + i] = acc_a ? f4add(r, oa[slot * as4 + i]) : r;
         if (ob) ob[slot * bs4 + i] = acc_b ? f4add(r, ob[slot * bs4 + i]) : r;
+        am[j] = f4absmax(am[j], r);  // without accumulation both outputs equal r
+      }
+    }
+  }
+  if (amax_a || amax_b) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __syncthreads();
+      if (s_lo + j < s_hi) {
+        if (amax_a) block_absmax_commit(am[j], amax_a + s_lo + j);
+        if (amax_a && amax_b) __syncthreads();
+        if (amax_b) block_absmax_commit(am[j], amax_b + s_lo + j);
       }
     }
   }
@@ -432,7 +453,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot
       am = f4absmax(am, v);
     }
   }
-  if (amax) block_absmax_commit(am, amax + slot);
+  if (amax && !ph) block_absmax_commit(am, amax + slot);
 }
 
 // gx[pixel] (+)= sum over output windows whose argmax is this pixel of gy (gather form: deterministic).
@@ -444,7 +465,10 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
                                                           const unsigned char* __restrict__ idx, int B, int Hs,
                                                           int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh,
                                                           int sw, int ph, int pw, int slot0, int nslots,
-                                                          int accumulate) {
+                                                          int accumulate, unsigned int* __restrict__ amax) {
+  float am[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) am[s] = 0.f;
   const int sfirst = blockIdx.y * 8;
   const int ns = min(8, nslots - sfirst);
   const float4* g = reinterpret_cast<const float4*>(gy + (long long)(slot0 + sfirst) * gy_slot);
@@ -493,7 +517,15 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
         float4 a = acc[s];
         if (accumulate) a = f4add(a, o[s * o4 + i]);
         o[s * o4 + i] = a;
+        am[s] = f4absmax(am[s], a);
       }
+    }
+  }
+  if (amax) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      __syncthreads();
+      if (s < ns) block_absmax_commit(am[s], amax + slot0 + sfirst + s);
     }
   }
 }
@@ -547,7 +579,14 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
     const float* __restrict__ xdot, long long xdot_slot, const float* __restrict__ coef,
     const float* __restrict__ aux, float* __restrict__ gx, long long gx_slot, int write_gx,
     float* __restrict__ partial, int want_partial, long long rows, int Cp, int rows_per_cta,
-    int slot0, int nslots, int rop, int accumulate, int relu, unsigned int* __restrict__ amax) {
+    int slot0, int nslots, int rop, int accumulate, int relu, unsigned int* __restrict__ amax,
+    __half* __restrict__ ph, __half* __restrict__ pl, long long plane_slot,
+    const unsigned int* __restrict__ in_bits, const unsigned int* __restrict__ smax_bits, int write_fp32) {
+  // Planes mode (ph != null; half-split GEMM path): gx is ALSO (write_fp32) or ONLY written as the fp16 hi/lo
+  // planes the producing convolution's wgrad / dgrad read, at slot (slot - slot0) of ph / pl.  The scale comes from
+  // the bound  max|gx_k| <= max_c|s_c| * max|gy_k|  (in_bits: absmax words of gy by absolute slot, smax_bits: one
+  // word); the bound's bit pattern is stored in amax[slot] in place of the exact maximum - any upper bound is a
+  // valid scale, it only moves the 2^-39 absolute floor of the split.
   extern __shared__ float red[];  // [RPP][2][ctile*4]
   float am = 0.f;  // max |gx| written by this thread (amax: fused absmax for the half-split GEMMs)
   const int C4 = Cp >> 2;
@@ -564,7 +603,17 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
   const float4* g0 = reinterpret_cast<const float4*>(gy);
   const float4* xp = reinterpret_cast<const float4*>(x0);
   const float4* xd = (rop && xdot) ? reinterpret_cast<const float4*>(xdot + slot * xdot_slot) : nullptr;
-  float4* o = write_gx ? reinterpret_cast<float4*>(gx + slot * gx_slot) : nullptr;
+  float4* o = (write_gx && write_fp32) ? reinterpret_cast<float4*>(gx + slot * gx_slot) : nullptr;
+  float pscale = 0.f;
+  uint2* oh = nullptr;
+  uint2* ol = nullptr;
+  if (ph) {
+    const float bound = __uint_as_float(__ldg(smax_bits)) * __uint_as_float(__ldg(in_bits + slot));
+    pscale = hs_pow2(hs_shift_from_bits(__float_as_uint(bound)));
+    oh = reinterpret_cast<uint2*>(ph + (long long)slot_idx * plane_slot);
+    ol = reinterpret_cast<uint2*>(pl + (long long)slot_idx * plane_slot);
+    if (blockIdx.x == 0 && threadIdx.x == 0) amax[slot] = __float_as_uint(bound);
+  }
   for (int cbase = 0; cbase < C4; cbase += ctile4) {
     const int c4 = cbase + cl;
     const bool cok = active && c4 < C4;
@@ -602,6 +651,19 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
             if (accumulate) rr = f4add(rr, o[i]);
             o[i] = rr;
             am = f4absmax(am, rr);
+          }
+          if (oh) {  // fp16 hi/lo planes of the scaled cotangent (4 channels = 8 bytes per plane)
+            const float x4[4] = {rr.x * pscale, rr.y * pscale, rr.z * pscale, rr.w * pscale};
+            __half h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = __float2half_rn(x4[e]);
+              l[e] = __float2half_rn(x4[e] - __half2float(h[e]));
+            }
+            oh[i] = make_uint2((unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16),
+                               (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16));
+            ol[i] = make_uint2((unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16),
+                               (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16));
           }
         }
       }

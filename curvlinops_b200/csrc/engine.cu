@@ -26,7 +26,8 @@ static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
 static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
                                 // 4 = gather GEMM with the old two-threads-per-row producer mapping,
-                                // 8, 16 = producer experiments, 32 = no half-split (fp16 hi/lo) kernels:
+                                // 8, 16 = producer experiments, 64 = BN adjoint never writes planes directly,
+                                // 32 = no half-split (fp16 hi/lo) kernels:
                                 // everything eligible runs the 3xTF32 kernels instead
 
 static int fail(int code, const std::string& msg) {
@@ -119,7 +120,7 @@ extern "C" long long curv_launch_count(void) { return g_launches; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 63;
+  g_tc_disable = (mode >> 4) & 127;
   return old;
 }
 
@@ -584,9 +585,10 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
       const float* beta = d.p1 >= 0 ? c.param(d.p1) : (d.c1 >= 0 ? c.cst(d.c1) : nullptr);
       const float* gd = (with_tangents && d.p0 >= 0) ? c.vcol(d.p0) : nullptr;
       const float* bd = (with_tangents && d.p1 >= 0) ? c.vcol(d.p1) : nullptr;
-      affine_prep_kernel<<<grid1d(vi.Cp), 256, 0, st>>>(gamma, beta, c.cst(d.c2), c.cst(d.c3), d.eps, gd, bd,
-                                                       c.ldk, with_tangents ? c.K : 0, vi.C, vi.Cp,
-                                                       c.ws + n.coef_off, c.ws + n.aux_off);
+      affine_prep_kernel<<<grid1d(vi.Cp), 256, 0, st>>>(
+          gamma, beta, c.cst(d.c2), c.cst(d.c3), d.eps, gd, bd, c.ldk, with_tangents ? c.K : 0, vi.C, vi.Cp,
+          c.ws + n.coef_off, c.ws + n.aux_off,
+          c.hs ? c.hsbits() + c.bits_node((int)(&n - P->nodes.data())) : nullptr);  // max_c |s_c| (AFFINE nodes own word 0)
       LAUNCH_CHECK();
     }
   }
@@ -797,6 +799,11 @@ static int backward(const Ctx& c, int K) {
   std::vector<char> ginit(P->values.size(), 0);
   ginit[P->nodes.back().d.out] = 1;
   float* scratch = c.ws + P->scratch_off;
+  int planes_of = -1;  // value whose cotangent slots currently sit in the hs1 planes (written by affine_bwd)
+  // number of kernels that have written (accumulated into) the cotangent of a value: a fused absmax word is only
+  // trusted while its value has a single writer
+  std::vector<int> nwrites(P->values.size(), 0);
+  auto mark_written = [&](int v) { ginit[v] = 1; ++nwrites[v]; };
   for (int ni = (int)P->nodes.size() - 1; ni >= 0; --ni) {
     Node& n = P->nodes[ni];
     const curv_node_desc& d = n.d;
@@ -819,12 +826,13 @@ static int backward(const Ctx& c, int K) {
         const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, ns);
         const bool hs_d = vi.tan && hs_dgr_ok(c, n);
         const int eg = c.bits_grad(d.out);
-        if (hs_w || hs_d) {  // fp16 hi/lo planes of the cotangent slots, shared by wgrad and dgrad
+        if ((hs_w || hs_d) && planes_of != d.out) {  // fp16 hi/lo planes of the cotangent slots (wgrad + dgrad)
           int rc = hs_absmax(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, eg + s0, ns);
           if (!rc) rc = hs_split(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, c.hs1_hi(), c.hs1_lo(),
                                  eg + s0, ns);
           if (rc) return rc;
         }
+        planes_of = -1;
         if (hs_w) {  // weight gradients of all slots on the half-split kernel
           const int ea = c.bits_act(d.in0);
           int rc = hs_absmax(c, c.act(d.in0), 0, vi.slot_elems, ea, 1);
@@ -865,7 +873,7 @@ static int backward(const Ctx& c, int K) {
           long long rows = g.M;
           affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
               c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
-              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0, nullptr);
+              rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 1);
           LAUNCH_CHECK();
           vec_grad_finish_kernel<<<ceil_div(vo.C * K, 256), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 1, vo.C, vo.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
@@ -881,12 +889,16 @@ static int backward(const Ctx& c, int K) {
           h.W_img = reinterpret_cast<const __half*>(c.ws + n.wtimg_off);
           h.w_bits = c.hsbits() + c.bits_node(nidx);
           h.out = c.grad(d.in0); h.out_slot = vi.slot_elems; h.slot0 = s0; h.accumulate = ginit[d.in0];
+          if (!ginit[d.in0]) {  // first writer: track the absmax of the data gradient for its consumers
+            hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns);
+            h.out_bits = c.hsbits() + c.bits_grad(d.in0);
+          }
           {
             ProfScope prof(0, conv_flops(g, vi.C) * ns, st);
             if (hs_launch_gather_gemm(h, ns, st, true, ns)) return fail(CURV_ERR_CUDA, "half-split dgrad GEMM launch failed");
             ++g_launches;
           }
-          ginit[d.in0] = 1;
+          mark_written(d.in0);
         } else if (vi.tan) {  // data gradient
           GatherGemmArgs a;
           memset(&a, 0, sizeof(a));
@@ -902,7 +914,7 @@ static int backward(const Ctx& c, int K) {
           a.slot0 = s0; a.accumulate = ginit[d.in0];
           int rc = launch_gather_gemm(a, ns, st, conv_flops(g, vi.C) * ns * (a.Wt ? 2 : 1));
           if (rc) return rc;
-          ginit[d.in0] = 1;
+          mark_written(d.in0);
         }
         break;
       }
@@ -917,13 +929,36 @@ static int backward(const Ctx& c, int K) {
           hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns);
           amax = c.hsbits() + c.bits_grad(d.in0);
         }
+        // Planes mode: when the convolution that produced this value is the very next node of the sweep and both
+        // of its contractions run on the half-split kernels, the cotangent is written straight as their fp16
+        // hi/lo planes (scaled by a bound derived from the absmax of the incoming cotangent), and the fp32 copy -
+        // which nobody else reads - is skipped together with the separate split pass.
+        bool planes = false;
+        if (amax && !rop && c.kfac_G == nullptr && ni > 0) {
+          const Node& cn = P->nodes[ni - 1];
+          if (cn.d.op == CURV_OP_CONV && cn.d.out == d.in0 && cn.d.p1 < 0) {
+            const bool need_w = cn.d.p0 >= 0, need_d = P->values[cn.d.in0].tan;
+            const bool ok_w = !need_w || hs_wgr_ok(c, cn, ns), ok_d = !need_d || hs_dgr_ok(c, cn);
+            planes = (need_w || need_d) && ok_w && ok_d && vi.slot_elems * ns <= P->hs1_elems &&
+                     !(g_tc_disable & 64);
+          }
+        }
+        if (planes) {  // the bound needs the absmax of the incoming cotangent (fused by its producer, else a pass)
+          if (nwrites[d.out] != 1)
+            for (int sl = 0; sl < ns; ++sl) (*c.hs_valid)[c.bits_grad(d.out) + s0 + sl] = 0;
+          int rc = hs_absmax(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, c.bits_grad(d.out) + s0, ns);
+          if (rc) return rc;
+        }
         affine_bwd_kernel<<<dim3(n.nchunks, ns), 256, 8192, st>>>(
             c.grad(d.out), vo.slot_elems, c.act(d.in0), (rop && vi.tan) ? c.act(d.in0) : nullptr,
             vi.slot_elems, c.ws + n.coef_off, c.ws + n.aux_off, vi.tan ? c.grad(d.in0) : nullptr,
             vi.slot_elems, vi.tan ? 1 : 0, scratch, want_partial, rows, vi.Cp, n.rows_per_cta, s0, ns,
-            rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0, amax);
+            rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0, amax, planes ? c.hs1_hi() : nullptr,
+            planes ? c.hs1_lo() : nullptr, vi.slot_elems, c.hsbits() + c.bits_grad(d.out),
+            c.hsbits() + c.bits_node(ni), planes ? 0 : 1);
         LAUNCH_CHECK();
-        if (vi.tan) ginit[d.in0] = 1;
+        planes_of = planes ? d.in0 : -1;
+        if (vi.tan) mark_written(d.in0);
         if (d.p0 >= 0) {
           vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 0, vi.C, vi.Cp, c.out, P->params[d.p0].offset, c.ldk, c.k0,
@@ -948,7 +983,7 @@ static int backward(const Ctx& c, int K) {
             kind, c.grad(d.out), vo.slot_elems, c.act(d.out), c.grad(d.in0), vi.slot_elems,
             rop ? c.act(d.in0) : nullptr, vi.slot_elems, n4, s0, ginit[d.in0]);
         LAUNCH_CHECK();
-        ginit[d.in0] = 1;
+        mark_written(d.in0);
         break;
       }
       case CURV_OP_ADD: {
@@ -957,23 +992,27 @@ static int backward(const Ctx& c, int K) {
         if (d.kh == 2) {  // fused residual join + ReLU
           add_relu_bwd_kernel<<<dim3(grid1d(n4), (ns + 7) / 8), 256, 0, st>>>(
               c.grad(d.out), vo.slot_elems, c.act(d.out), vi.tan ? c.grad(d.in0) : nullptr, vi.slot_elems,
-              ginit[d.in0], vj.tan ? c.grad(d.in1) : nullptr, vj.slot_elems, ginit[d.in1], n4, s0, ns);
+              ginit[d.in0], vj.tan ? c.grad(d.in1) : nullptr, vj.slot_elems, ginit[d.in1], n4, s0, ns,
+              (c.hs && vi.tan && !ginit[d.in0]) ? (hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns),
+                                                   c.hsbits() + c.bits_grad(d.in0)) : nullptr,
+              (c.hs && vj.tan && !ginit[d.in1]) ? (hs_fused_absmax(c, c.bits_grad(d.in1) + s0, ns),
+                                                   c.hsbits() + c.bits_grad(d.in1)) : nullptr);
           LAUNCH_CHECK();
-          if (vi.tan) ginit[d.in0] = 1;
-          if (vj.tan) ginit[d.in1] = 1;
+          if (vi.tan) mark_written(d.in0);
+          if (vj.tan) mark_written(d.in1);
           break;
         }
         if (vi.tan) {
           axpy_slots_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(c.grad(d.out), vo.slot_elems, c.grad(d.in0),
                                                                   vi.slot_elems, n4, s0, 1.f, ginit[d.in0]);
           LAUNCH_CHECK();
-          ginit[d.in0] = 1;
+          mark_written(d.in0);
         }
         if (vj.tan) {
           axpy_slots_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(c.grad(d.out), vo.slot_elems, c.grad(d.in1),
                                                                   vj.slot_elems, n4, s0, 1.f, ginit[d.in1]);
           LAUNCH_CHECK();
-          ginit[d.in1] = 1;
+          mark_written(d.in1);
         }
         break;
       }
@@ -982,9 +1021,11 @@ static int backward(const Ctx& c, int K) {
         unsigned char* idx = reinterpret_cast<unsigned char*>(c.ws + n.idx_off);
         maxpool_bwd_kernel<<<dim3(grid1d(vi.slot_elems / 4), (ns + 7) / 8), 256, 0, st>>>(
             c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, idx, P->B, vi.H, vi.W, vo.H, vo.W,
-            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ns, ginit[d.in0]);
+            vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ns, ginit[d.in0],
+            (c.hs && !ginit[d.in0]) ? (hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns),
+                                       c.hsbits() + c.bits_grad(d.in0)) : nullptr);
         LAUNCH_CHECK();
-        ginit[d.in0] = 1;
+        mark_written(d.in0);
         break;
       }
       case CURV_OP_AVGPOOL: {
@@ -993,7 +1034,7 @@ static int backward(const Ctx& c, int K) {
             c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, P->B, vi.H * vi.W, vi.Cp, s0,
             ginit[d.in0]);
         LAUNCH_CHECK();
-        ginit[d.in0] = 1;
+        mark_written(d.in0);
         break;
       }
       default:

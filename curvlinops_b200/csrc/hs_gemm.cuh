@@ -34,28 +34,6 @@ namespace curv {
 
 constexpr int HS_BK = 64;        // fp16 reduction elements per stage = one 128-byte swizzle row
 constexpr int HS_FLUSH = 6;      // K stages per main accumulation chunk of gather_gemm_hs (24 MMAs per chain)
-constexpr int HS_SH_TARGET = 14;  // scaled maximum in [2^14, 2^15)
-constexpr int HS_SH_CLAMP = 60;   // |sh| <= 60: products of two inverse scales stay normal floats
-
-// scale exponent sh (s = 2^sh) from the bit pattern of the slot's absolute maximum
-__host__ __device__ inline int hs_shift_from_bits(uint32_t bits) {
-  if (bits == 0u) return 0;  // all-zero slot
-  const int e = (int)((bits >> 23) & 0xffu) - 127;
-  int sh = HS_SH_TARGET - e;
-  if (sh > HS_SH_CLAMP) sh = HS_SH_CLAMP;
-  if (sh < -HS_SH_CLAMP) sh = -HS_SH_CLAMP;
-  return sh;
-}
-__host__ __device__ inline float hs_pow2(int sh) {
-#ifdef __CUDA_ARCH__
-  return __uint_as_float((uint32_t)(sh + 127) << 23);
-#else
-  union { uint32_t u; float f; } c;
-  c.u = (uint32_t)(sh + 127) << 23;
-  return c.f;
-#endif
-}
-
 // ---------------------------------------------------------------------------------------------------
 // absmax + split (streaming, HBM-bound)
 // ---------------------------------------------------------------------------------------------------
@@ -237,6 +215,7 @@ struct HsGatherArgs {
   int accumulate;
   int debug;  // perf experiments only: 1 = producers skip the copies, 2 = the MMA lane skips the MMAs
   int flush;  // K stages per TMEM accumulation chunk (set by the launcher: g_hs_flush)
+  unsigned int* out_bits;  // nullable: fused absmax of the written result, word [slot] (see elementwise.cuh)
   HsParity par;
   // TMA im2col path of the gathered operand (set by hs_launch_gather_gemm when Cs % 64 == 0): 4-d im2col maps
   // (C, W, H, slots*B) of the two planes, one pair per parity class (class 0 = the whole tensor otherwise):
@@ -342,6 +321,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
   const int ntiles = tiles_m * tiles_n * nslots;
   const int nchunks = ceil_div(g.Kd, HS_BK);
   const int cpt = g.Cs / HS_BK;  // K stages per filter tap (parity mode)
+  __shared__ unsigned int s_slotmax[40];  // per-CTA absmax of the written result per slot (out_bits)
+  if (threadIdx.x < 40) s_slotmax[threadIdx.x] = 0u;
   // full barrier: TMA mode = the single expect_tx arrival of the issuing thread
   const uint32_t tmem_base = hs_prologue<BN>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
 
@@ -667,6 +648,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
       float* outp = p.out + (long long)t.slot * p.out_slot;
       int m = t.m0 + quad * 32 + lane;  // GEMM row -> destination pixel
       bool m_ok = m < g.M;
+      float vmax = 0.f;
       if (parity) {
         const int hw = par.Hc[t.cls] * par.Wc[t.cls];
         m_ok = m < g.B * hw;
@@ -692,11 +674,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
           }
           *dst = v;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
+      }
+      if (p.out_bits) {  // one shared-memory atomic per warp and tile, one global atomic per CTA and slot at the end
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0 && vmax > 0.f) atomicMax(&s_slotmax[t.slot], __float_as_uint(vmax));
       }
     }
   }
   hs_teardown(tmem_base);
+  if (p.out_bits && threadIdx.x < 40 && s_slotmax[threadIdx.x] != 0u)
+    atomicMax(p.out_bits + threadIdx.x, s_slotmax[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------------

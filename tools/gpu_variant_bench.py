@@ -18,7 +18,7 @@ L = capi.lib()
 ref = None
 for mode in modes:
     L.curv_set_tensor_core_mode(mode)
-    for _ in range(2):
+    for _ in range(5):  # eager, then CUDA-graph capture for both alternating (V, out) address sets
         out = G @ V
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
