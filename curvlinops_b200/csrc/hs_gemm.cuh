@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) hs_absmax_kernel(const float* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
-    if (m > 0.f) atomicMax(bits + slot, __float_as_uint(m));
+    if (m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile uint32_t*>(bits + slot))
+      atomicMax(bits + slot, __float_as_uint(m));
   }
 }
 
