@@ -141,7 +141,10 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
     }
     coef[c] = s; coef[Cp + c] = tt;
     aux[c] = invstd; aux[Cp + c] = mu;
-    if (smax_bits && s != 0.f) atomicMax(smax_bits, __float_as_uint(fabsf(s)));  // max_c |s_c|: bound of the adjoint
+    // coefficient maxima for the bounds of the planes modes: words [0] = max|s|, [1] = max|t|, [2k], [2k+1] =
+    // max|sdot_k|, max|tdot_k|
+    if (smax_bits && s != 0.f) atomicMax(smax_bits, __float_as_uint(fabsf(s)));
+    if (smax_bits && tt != 0.f) atomicMax(smax_bits + 1, __float_as_uint(fabsf(tt)));
     for (int k = 0; k < K; ++k) {
       float sd = 0.f, td = 0.f;
       if (c < C) {
@@ -150,6 +153,8 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
       }
       coef[(long long)(1 + k) * 2 * Cp + c] = sd;
       coef[(long long)(1 + k) * 2 * Cp + Cp + c] = td;
+      if (smax_bits && sd != 0.f) atomicMax(smax_bits + 2 * (k + 1), __float_as_uint(fabsf(sd)));
+      if (smax_bits && td != 0.f) atomicMax(smax_bits + 2 * (k + 1) + 1, __float_as_uint(fabsf(td)));
     }
   }
 }
@@ -163,7 +168,16 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ coef, int coef_has_tan,
                                                          float* __restrict__ y, long long y_slot, long long rows,
                                                          int Cp, int relu, int nslots,
-                                                         unsigned int* __restrict__ amax) {
+                                                         unsigned int* __restrict__ amax, __half* __restrict__ ph,
+                                                         __half* __restrict__ pl, long long plane_slot,
+                                                         const unsigned int* __restrict__ in_bits,
+                                                         const unsigned int* __restrict__ cbits,
+                                                         int write_fp32_tangents) {
+  // Planes mode (ph != null; half-split GEMM path): the output is ALSO written as the fp16 hi/lo planes the next
+  // convolution gathers (slot s at ph/pl + s * plane_slot), scaled by a power of two derived from the bound
+  //   |y_0| <= max|s| max|x_0| + max|t|,   |y_k| <= max|s| max|x_k| + max|sdot_k| max|x_0| + max|tdot_k|
+  // (in_bits: absmax words of x by slot, cbits: coefficient maxima of affine_prep_kernel); the bound's bit pattern
+  // replaces the exact maximum in amax[slot].  The fp32 tangent slots are skipped when nobody else reads them.
   const int grp = blockIdx.y;
   const int k_lo = 1 + 8 * grp;  // first tangent slot of the group
   const int C4 = Cp >> 2;
@@ -176,6 +190,37 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
   float am[9];
 #pragma unroll
   for (int j = 0; j < 9; ++j) am[j] = 0.f;
+  float psc[9];  // plane scales of slot 0 and of the group's tangent slots
+  if (ph) {
+    const float smax = __uint_as_float(__ldg(cbits)), x0max = __uint_as_float(__ldg(in_bits));
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int slot = j == 0 ? 0 : k_lo + j - 1;
+      float bound = 0.f;
+      if (slot == 0) bound = smax * x0max + __uint_as_float(__ldg(cbits + 1));
+      else if (slot < nslots)
+        bound = (x_has_slots ? smax * __uint_as_float(__ldg(in_bits + slot)) : 0.f) +
+                (coef_has_tan ? __uint_as_float(__ldg(cbits + 2 * slot)) * x0max + __uint_as_float(__ldg(cbits + 2 * slot + 1))
+                              : 0.f);
+      psc[j] = hs_pow2(hs_shift_from_bits(__float_as_uint(bound)));
+      if (blockIdx.x == 0 && threadIdx.x == 0 && slot < nslots && (j > 0 || grp == 0)) amax[slot] = __float_as_uint(bound);
+    }
+  }
+  auto store_planes = [&](int slot, long long i, const float4& r, float sc) {
+    const float x4[4] = {r.x * sc, r.y * sc, r.z * sc, r.w * sc};
+    __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = __float2half_rn(x4[e]);
+      l[e] = __float2half_rn(x4[e] - __half2float(h[e]));
+    }
+    reinterpret_cast<uint2*>(ph + (long long)slot * plane_slot)[i] =
+        make_uint2((unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16),
+                   (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16));
+    reinterpret_cast<uint2*>(pl + (long long)slot * plane_slot)[i] =
+        make_uint2((unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16),
+                   (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16));
+  };
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -186,6 +231,7 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
                             : pre;
       y0[i] = r;
       am[0] = f4absmax(am[0], r);
+      if (ph) store_planes(0, i, r, psc[0]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -200,12 +246,13 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
         if (relu)  // fused ReLU: mask with the sign of the primal pre-activation
           r = make_float4(pre.x > 0.f ? r.x : 0.f, pre.y > 0.f ? r.y : 0.f, pre.z > 0.f ? r.z : 0.f,
                           pre.w > 0.f ? r.w : 0.f);
-        y0[slot * ys4 + i] = r;
+        if (!ph || write_fp32_tangents) y0[slot * ys4 + i] = r;
         am[1 + j] = f4absmax(am[1 + j], r);
+        if (ph) store_planes(slot, i, r, psc[1 + j]);
       }
     }
   }
-  if (amax) {
+  if (amax && !ph) {
     if (grp == 0) block_absmax_commit(am[0], amax);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

@@ -94,7 +94,8 @@ struct curv_program {
   // half-split path (hs_gemm.cuh): plane scratch R1 (all slots of one tensor), R2 (one primal slot), both in
   // floats (hi + lo fp16 planes = 4 bytes per element), and the absmax bit patterns:
   //   value v, act slot s  -> bits[(2 v) (1+kmax) + s],  grad slot s -> bits[(2 v + 1) (1+kmax) + s]
-  //   conv node i, weight 0 / tangent k -> bits[(2 nvalues + i) (1+kmax) + k]
+  //   node i: 2 (1+kmax) words at bits[(2 nvalues + 2 i) (1+kmax)]: conv: weight 0 / tangent k -> word k;
+  //           affine: coefficient maxima (affine_prep_kernel)
   long long hs1_off = 0, hs1_elems = 0, hs2_off = 0, hs2_elems = 0, hsbits_off = 0, hsbits_count = 0;
   size_t ws_bytes = 0;
 };
@@ -275,7 +276,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
     if (P->hs1_elems > 0) {
       P->hs1_off = alloc(P->hs1_elems);
       P->hs2_off = alloc(P->hs2_elems);
-      P->hsbits_count = (long long)(2 * n_values + n_nodes) * (1 + kmax);
+      P->hsbits_count = (long long)(2 * n_values + 2 * n_nodes) * (1 + kmax);
       P->hsbits_off = alloc(P->hsbits_count);
     }
   }
@@ -422,7 +423,7 @@ struct Ctx {
   uint32_t* hsbits() const { return reinterpret_cast<uint32_t*>(ws + P->hsbits_off); }
   int bits_act(int v) const { return (2 * v) * (1 + P->kmax); }
   int bits_grad(int v) const { return (2 * v + 1) * (1 + P->kmax); }
-  int bits_node(int ni) const { return (2 * (int)P->values.size() + ni) * (1 + P->kmax); }
+  int bits_node(int ni) const { return (2 * (int)P->values.size() + 2 * ni) * (1 + P->kmax); }
   __half* hs1_hi() const { return reinterpret_cast<__half*>(ws + P->hs1_off); }
   __half* hs1_lo() const { return reinterpret_cast<__half*>(ws + P->hs1_off) + P->hs1_elems; }
   __half* hs2_hi() const { return reinterpret_cast<__half*>(ws + P->hs2_off); }
@@ -617,6 +618,14 @@ static int signal_out_done(const Ctx& c, const Node& n) {
 static int forward(const Ctx& c, const void* X, int K) {
   curv_program* P = c.P;
   cudaStream_t st = c.st;
+  int planes_of = -1;  // value whose slots currently sit in the hs1 planes (written by affine_fwd, planes mode)
+  // consumers per value: a BN output read only by the next convolution needs no fp32 tangent slots
+  std::vector<int> nuse(P->values.size(), 0);
+  for (const Node& q : P->nodes) {
+    if (q.d.op == CURV_OP_INPUT) continue;
+    ++nuse[q.d.in0];
+    if (q.d.op == CURV_OP_ADD) ++nuse[q.d.in1];
+  }
   for (Node& n : P->nodes) {
     const curv_node_desc& d = n.d;
     if (d.op == CURV_OP_INPUT) {
@@ -640,9 +649,12 @@ static int forward(const Ctx& c, const void* X, int K) {
         if (hs_fwd_ok(c, n)) {  // fp16 hi/lo planes of the input slots, then the half-split gather GEMM
           const int nin = (vi.tan && K > 0) ? 1 + K : 1;
           const int ea = c.bits_act(d.in0);
-          int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, ea, nin);
-          if (!rc) rc = hs_split(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.hs1_hi(), c.hs1_lo(), ea, nin);
-          if (rc) return rc;
+          if (planes_of != d.in0) {  // (else the producing BN kernel already wrote them)
+            int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, ea, nin);
+            if (!rc) rc = hs_split(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.hs1_hi(), c.hs1_lo(), ea, nin);
+            if (rc) return rc;
+          }
+          planes_of = -1;
           if (!vi.tan && nsl > 1 && d.p0 >= 0) {
             // the layer input carries no tangent (the stem): every slot gathers the same operand -> N-stacked
             // kernel, the gather is staged once per group of 256 / BN slots
@@ -674,6 +686,7 @@ static int forward(const Ctx& c, const void* X, int K) {
           h.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
           h.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; h.bias_slot = vo.Cp;
           h.out = c.act(d.out); h.out_slot = vo.slot_elems; h.slot0 = 0; h.accumulate = 0;
+          h.out_bits = hs_fused_absmax(c, c.bits_act(d.out), nsl);  // absmax of the conv output (bounds downstream)
           ProfScope prof(0, fl, st);
           if (hs_launch_gather_gemm(h, nsl, st, true, nin)) return fail(CURV_ERR_CUDA, "half-split gather GEMM launch failed");
           ++g_launches;
@@ -699,11 +712,30 @@ static int forward(const Ctx& c, const void* X, int K) {
       }
       case CURV_OP_AFFINE: {
         long long rows = (long long)P->B * vi.H * vi.W;
+        // Planes mode: the only reader of this output is the convolution that comes next and it runs on the
+        // half-split kernels -> write its fp16 hi/lo operand planes here (scale from a bound, see the kernel) and
+        // skip the fp32 tangent slots and the separate split pass.  (GGN-type sweeps only: the cotangent slots
+        // of the backward sweep reuse the tangent storage, nothing reads the fp32 tangents later.)
+        const int ni = (int)(&n - P->nodes.data());
+        bool planes = false;
+        if (c.hs && K > 0 && !c.rop && !(g_tc_disable & 64) && ni + 1 < (int)P->nodes.size() && nuse[d.out] == 1 &&
+            (c.kind == CURV_KIND_GGN || c.kind == CURV_KIND_GGN_MC)) {
+          const Node& cn = P->nodes[ni + 1];
+          planes = cn.d.op == CURV_OP_CONV && cn.d.in0 == d.out && hs_fwd_ok(c, cn) &&
+                   vo.slot_elems * nsl <= P->hs1_elems && nsl == 1 + K;
+        }
+        if (planes) {  // the bound needs the absmax of the input slots (fused by the producing conv, else a pass)
+          int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.bits_act(d.in0), vi.tan ? nsl : 1);
+          if (rc) return rc;
+        }
         affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl > 1 ? (nsl + 6) / 8 : 1), 256, 0, st>>>(
             c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
             c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl,
-            hs_fused_absmax(c, c.bits_act(d.out), nsl));
+            hs_fused_absmax(c, c.bits_act(d.out), nsl), planes ? c.hs1_hi() : nullptr,
+            planes ? c.hs1_lo() : nullptr, vo.slot_elems, c.hs ? c.hsbits() + c.bits_act(d.in0) : nullptr,
+            c.hs ? c.hsbits() + c.bits_node(ni) : nullptr, 0);
         LAUNCH_CHECK();
+        planes_of = planes ? d.out : -1;
         break;
       }
       case CURV_OP_RELU:

@@ -28,14 +28,14 @@ ref = orc.ggn_matmat(m64, loss, p64, [(X.double(), y)], Vl)
 ref = torch.cat([r.reshape(-1, Kc) for r in ref])
 scale = ref.abs().max().item()
 G = GGNLinearOperator(model, loss, params, [(X, y)], check_deterministic=False)
-for name, mode in [("simt fp32", 0), ("tcgen05 gather+wgrad", 1), ("tcgen05 gather only", 1 | (2 << 4)),
-                   ("tcgen05 wgrad only", 1 | (1 << 4))]:
+for name, mode in [("simt fp32", 0), ("half-split tcgen05 (default)", 1),
+                   ("half-split, split passes (no planes modes)", 0x401), ("3xTF32 tcgen05", 0x201)]:
     capi.lib().curv_set_tensor_core_mode(mode)
     got = (G @ V).double()
     err = (got - ref).abs()
     ok = torch.allclose(got, ref, rtol=1e-4, atol=1e-5 * scale)
     frac_bad = (~torch.isclose(got, ref, rtol=1e-4, atol=1e-5 * scale)).double().mean().item()
-    print(f"[{name:24s}] max|err|/max|ref| = {err.max().item() / scale:.3e}  allclose(1e-4) = {ok}  "
+    print(f"[{name:44s}] max|err|/max|ref| = {err.max().item() / scale:.3e}  allclose(1e-4) = {ok}  "
           f"violations = {frac_bad:.2e}")
     o = 0
     worst = []
