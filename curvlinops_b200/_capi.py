@@ -40,7 +40,7 @@ EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
-    "curv_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
+    "curv_launch_count", "curv_add_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
 ]
 
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
     L.curv_abi_version.restype = i
     L.curv_launch_count.argtypes = []
     L.curv_launch_count.restype = ll
+    L.curv_add_launch_count.argtypes = [ll]
+    L.curv_add_launch_count.restype = None
     L.curv_set_tensor_core_mode.argtypes = [i]
     L.curv_set_tensor_core_mode.restype = i
     L.curv_profile_enable.argtypes = [i]

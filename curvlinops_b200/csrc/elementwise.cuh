@@ -43,6 +43,28 @@ __device__ __forceinline__ void block_absmax_commit(float m, unsigned int* dst) 
   }
 }
 
+// fp16 hi/lo planes of 4 scaled floats at float4-index i of a plane pair.  Adjacent lanes (i even / odd, both
+// active: the element count is even and warps are index-aligned) exchange halves so that every lane issues ONE
+// 16-byte store (even lanes the hi plane, odd lanes the lo plane) instead of two 8-byte ones.
+__device__ __forceinline__ void store_split_planes(__half* __restrict__ ph, __half* __restrict__ pl, long long i,
+                                                   const float4& r, float sc) {
+  // packed conversions: one cvt.rn.f16x2.f32 per pair (the kernels that call this are issue-bound otherwise)
+  const float2 a = make_float2(r.x * sc, r.y * sc), b = make_float2(r.z * sc, r.w * sc);
+  const __half2 ha = __float22half2_rn(a), hb2 = __float22half2_rn(b);
+  const float2 fa = __half22float2(ha), fb = __half22float2(hb2);
+  const __half2 la = __float22half2_rn(make_float2(a.x - fa.x, a.y - fa.y));
+  const __half2 lb2 = __float22half2_rn(make_float2(b.x - fb.x, b.y - fb.y));
+  const unsigned int h0 = *reinterpret_cast<const unsigned int*>(&ha), h1 = *reinterpret_cast<const unsigned int*>(&hb2);
+  const unsigned int l0 = *reinterpret_cast<const unsigned int*>(&la), l1 = *reinterpret_cast<const unsigned int*>(&lb2);
+  const unsigned int mask = __activemask();
+  const bool odd = (i & 1) != 0;
+  // even lane sends its lo words and receives the neighbour's hi words; odd lane the other way round
+  const unsigned int s0 = odd ? h0 : l0, s1 = odd ? h1 : l1;
+  const unsigned int r0 = __shfl_xor_sync(mask, s0, 1), r1 = __shfl_xor_sync(mask, s1, 1);
+  if (!odd) reinterpret_cast<uint4*>(ph)[i >> 1] = make_uint4(h0, h1, r0, r1);
+  else reinterpret_cast<uint4*>(pl)[i >> 1] = make_uint4(r0, r1, l0, l1);
+}
+
 // ------------------------------------------------------------------ layout / packing
 // X [B][C][H][W] -> out [B][H][W][Cp]
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int C,
@@ -164,7 +186,8 @@ __global__ void affine_prep_kernel(const float* gamma, const float* beta, const 
 // grid.y = slot GROUP: group g handles the tangent slots 1 + 8g .. 8 + 8g (and, for g = 0, the primal slot 0), so the
 // primal input - needed by every slot for the tangent of the coefficients and for the ReLU mask - is read once per
 // group instead of once per slot.
-__global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
+template <bool PLANES>
+__global__ void __launch_bounds__(256, PLANES ? 3 : 4) affine_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
                                                          const float* __restrict__ coef, int coef_has_tan,
                                                          float* __restrict__ y, long long y_slot, long long rows,
                                                          int Cp, int relu, int nslots,
@@ -191,7 +214,7 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 9; ++j) am[j] = 0.f;
   float psc[9];  // plane scales of slot 0 and of the group's tangent slots
-  if (ph) {
+  if (PLANES) {
     const float smax = __uint_as_float(__ldg(cbits)), x0max = __uint_as_float(__ldg(in_bits));
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -207,19 +230,7 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
     }
   }
   auto store_planes = [&](int slot, long long i, const float4& r, float sc) {
-    const float x4[4] = {r.x * sc, r.y * sc, r.z * sc, r.w * sc};
-    __half h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      h[e] = __float2half_rn(x4[e]);
-      l[e] = __float2half_rn(x4[e] - __half2float(h[e]));
-    }
-    reinterpret_cast<uint2*>(ph + (long long)slot * plane_slot)[i] =
-        make_uint2((unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16),
-                   (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16));
-    reinterpret_cast<uint2*>(pl + (long long)slot * plane_slot)[i] =
-        make_uint2((unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16),
-                   (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16));
+    store_split_planes(ph + (long long)slot * plane_slot, pl + (long long)slot * plane_slot, i, r, sc);
   };
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -230,8 +241,8 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
       const float4 r = relu ? make_float4(fmaxf(pre.x, 0.f), fmaxf(pre.y, 0.f), fmaxf(pre.z, 0.f), fmaxf(pre.w, 0.f))
                             : pre;
       y0[i] = r;
-      am[0] = f4absmax(am[0], r);
-      if (ph) store_planes(0, i, r, psc[0]);
+      if (PLANES) store_planes(0, i, r, psc[0]);
+      else am[0] = f4absmax(am[0], r);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -246,13 +257,13 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
         if (relu)  // fused ReLU: mask with the sign of the primal pre-activation
           r = make_float4(pre.x > 0.f ? r.x : 0.f, pre.y > 0.f ? r.y : 0.f, pre.z > 0.f ? r.z : 0.f,
                           pre.w > 0.f ? r.w : 0.f);
-        if (!ph || write_fp32_tangents) y0[slot * ys4 + i] = r;
-        am[1 + j] = f4absmax(am[1 + j], r);
-        if (ph) store_planes(slot, i, r, psc[1 + j]);
+        if (!PLANES || write_fp32_tangents) y0[slot * ys4 + i] = r;
+        if (PLANES) store_planes(slot, i, r, psc[1 + j]);
+        else am[1 + j] = f4absmax(am[1 + j], r);
       }
     }
   }
-  if (amax && !ph) {
+  if (amax && !PLANES) {
     if (grp == 0) block_absmax_commit(am[0], amax);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -701,19 +712,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
             o[i] = rr;
             am = f4absmax(am, rr);
           }
-          if (oh) {  // fp16 hi/lo planes of the scaled cotangent (4 channels = 8 bytes per plane)
-            const float x4[4] = {rr.x * pscale, rr.y * pscale, rr.z * pscale, rr.w * pscale};
-            __half h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h[e] = __float2half_rn(x4[e]);
-              l[e] = __float2half_rn(x4[e] - __half2float(h[e]));
-            }
-            oh[i] = make_uint2((unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16),
-                               (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16));
-            ol[i] = make_uint2((unsigned)__half_as_ushort(l[0]) | ((unsigned)__half_as_ushort(l[1]) << 16),
-                               (unsigned)__half_as_ushort(l[2]) | ((unsigned)__half_as_ushort(l[3]) << 16));
-          }
+          if (oh) store_split_planes(reinterpret_cast<__half*>(oh), reinterpret_cast<__half*>(ol), i, rr, pscale);
         }
       }
     }

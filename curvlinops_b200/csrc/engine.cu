@@ -26,7 +26,8 @@ static long long g_launches = 0;
 static int g_tc_mode = 1;       // 0 off, 1 auto, 2 forced (tests)
 static int g_tc_disable = 0;    // debug bitmask: 1 = no tcgen05 gather GEMM, 2 = no tcgen05 wgrad GEMM,
                                 // 4 = gather GEMM with the old two-threads-per-row producer mapping,
-                                // 8, 16 = producer experiments, 64 = BN adjoint never writes planes directly,
+                                // 8, 16 = producer experiments, 64 = BN kernels never write planes directly,
+                                // 128 = no N-stacked kernel for shared-activation layers (the stem),
                                 // 32 = no half-split (fp16 hi/lo) kernels:
                                 // everything eligible runs the 3xTF32 kernels instead
 
@@ -118,10 +119,12 @@ static long long gram_partial_elems(long long rows, int width, int widthp) {
 extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
 extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
 extern "C" long long curv_launch_count(void) { return g_launches; }
+// a host mirror that replays a captured CUDA graph of n of this library's launches reports them here
+extern "C" void curv_add_launch_count(long long n) { g_launches += n; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 127;
+  g_tc_disable = (mode >> 4) & 255;
   return old;
 }
 
@@ -655,7 +658,7 @@ static int forward(const Ctx& c, const void* X, int K) {
             if (rc) return rc;
           }
           planes_of = -1;
-          if (!vi.tan && nsl > 1 && d.p0 >= 0) {
+          if (!vi.tan && nsl > 1 && d.p0 >= 0 && !(g_tc_disable & 128)) {
             // the layer input carries no tangent (the stem): every slot gathers the same operand -> N-stacked
             // kernel, the gather is staged once per group of 256 / BN slots
             HsStackArgs q;
@@ -728,12 +731,20 @@ static int forward(const Ctx& c, const void* X, int K) {
           int rc = hs_absmax(c, c.act(d.in0), vi.slot_elems, vi.slot_elems, c.bits_act(d.in0), vi.tan ? nsl : 1);
           if (rc) return rc;
         }
-        affine_fwd_kernel<<<dim3(grid1d(rows * (vi.Cp / 4)), nsl > 1 ? (nsl + 6) / 8 : 1), 256, 0, st>>>(
-            c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
-            c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl,
-            hs_fused_absmax(c, c.bits_act(d.out), nsl), planes ? c.hs1_hi() : nullptr,
-            planes ? c.hs1_lo() : nullptr, vo.slot_elems, c.hs ? c.hsbits() + c.bits_act(d.in0) : nullptr,
-            c.hs ? c.hsbits() + c.bits_node(ni) : nullptr, 0);
+        {
+          const dim3 grid(grid1d(rows * (vi.Cp / 4)), nsl > 1 ? (nsl + 6) / 8 : 1);
+          unsigned int* am = hs_fused_absmax(c, c.bits_act(d.out), nsl);
+          if (planes)
+            affine_fwd_kernel<true><<<grid, 256, 0, st>>>(
+                c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
+                c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl, am, c.hs1_hi(), c.hs1_lo(),
+                vo.slot_elems, c.hsbits() + c.bits_act(d.in0), c.hsbits() + c.bits_node(ni), 0);
+          else
+            affine_fwd_kernel<false><<<grid, 256, 0, st>>>(
+                c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
+                c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl, am, nullptr, nullptr, 0, nullptr,
+                nullptr, 1);
+        }
         LAUNCH_CHECK();
         planes_of = planes ? d.out : -1;
         break;

@@ -1614,7 +1614,7 @@ static inline int hs_launch_gather_stack(const HsStackArgs& a_in, cudaStream_t s
   a.flush = hs_flush();
   const Geom& g = a.g;
   if (g.mode != 0 || g.Cs % 8 != 0 || a.nslots < 1) return -1;
-  if (ceil_div(g.Kd, HS_BK) <= 8) a.flush = 8;  // short reductions: one main chunk per tile (<= 32 MMAs per chain)
+  if (ceil_div(g.Kd, HS_BK) <= 8 && !getenv("CURV_HS_FLUSH")) a.flush = 8;  // short reductions: one main chunk per tile
   const int BN = tc_bn(g.Nd), G = 256 / BN;
   const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, BN) * ceil_div(a.nslots, G);
   if (BN == 128) gather_gemm_hs_stack<128><<<ntiles < sms ? ntiles : sms, HSN_THREADS, HSN_SMEM_BYTES, st>>>(a);

@@ -219,12 +219,15 @@ class Engine:
             launch(V, out, stream)
             del keep
             return
-        if entry[0] is None:  # second sighting: capture (records the launches, does not run them)
+        if len(entry) == 1:  # second sighting: capture (records the launches, does not run them)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(X.device)
+            n0 = capi.lib().curv_launch_count()
             with torch.cuda.graph(g):
                 launch(V, out, torch.cuda.current_stream(X.device).cuda_stream)
-            entry[0] = g
+            entry[:] = [g, capi.lib().curv_launch_count() - n0]  # the capture counted the first replay
+        else:
+            capi.lib().curv_add_launch_count(entry[1])
         entry[0].replay()
         del keep
 

@@ -183,6 +183,8 @@ const char* curv_last_error(void);
 int curv_abi_version(void);
 /* number of kernel launches issued by this library since process start (bench `gpu_launches`) */
 long long curv_launch_count(void);
+/* replaying a captured CUDA graph that contains n launches of this library: keeps the count truthful */
+void curv_add_launch_count(long long n);
 /* Per-launch CUDA-event timing of the contraction kernels (class 0: gather GEMM = forward/dgrad,
    class 1: wgrad GEMM).  enable(1) clears and starts recording, read() synchronises on the recorded
    events and returns summed milliseconds, algorithmic FLOPs and launch counts per class. */

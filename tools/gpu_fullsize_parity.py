@@ -29,7 +29,8 @@ ref = torch.cat([r.reshape(-1, Kc) for r in ref])
 scale = ref.abs().max().item()
 G = GGNLinearOperator(model, loss, params, [(X, y)], check_deterministic=False)
 for name, mode in [("simt fp32", 0), ("half-split tcgen05 (default)", 1),
-                   ("half-split, split passes (no planes modes)", 0x401), ("3xTF32 tcgen05", 0x201)]:
+                   ("half-split, split passes (no planes modes)", 0x401),
+                   ("half-split, no N-stacked stem kernel", 0x801), ("3xTF32 tcgen05", 0x201)]:
     capi.lib().curv_set_tensor_core_mode(mode)
     got = (G @ V).double()
     err = (got - ref).abs()
