@@ -356,7 +356,7 @@ __global__ void axpy_slots_kernel(const float* __restrict__ src, long long src_s
 
 // fused residual join + ReLU:  y_0 = relu(a_0 + b_0),  y_k = [a_0 + b_0 > 0] (a_k + b_k).  grid.y = slot
 // grid.y = slot group (see affine_fwd_kernel): the primal sum a_0 + b_0 (the ReLU mask) is formed once per group
-__global__ void __launch_bounds__(256) add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot,
+__global__ void __launch_bounds__(256, 4) add_relu_fwd_kernel(const float* __restrict__ a, long long a_slot,
                                                            int a_has_slots, const float* __restrict__ b,
                                                            long long b_slot, int b_has_slots, float* __restrict__ y,
                                                            long long y_slot, long long n4, int nslots,
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) add_relu_fwd_kernel(const float* __restri
 }
 // adjoint: g = [y_0 > 0] gy_k ;  ga_k (+)= g ;  gb_k (+)= g   (either destination may be null)
 // grid.y = groups of 8 cotangent slots: the primal output y0 (the ReLU mask) is read once per group
-__global__ void __launch_bounds__(256) add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+__global__ void __launch_bounds__(256, 4) add_relu_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
                                                            const float* __restrict__ y0, float* __restrict__ ga,
                                                            long long ga_slot, int acc_a, float* __restrict__ gb,
                                                            long long gb_slot, int acc_b, long long n4, int slot0,
@@ -520,7 +520,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, long long x_slot
 // One thread per (input pixel, 4 channels) and up to 8 cotangent slots (grid.y = groups of 8 slots): the window
 // arithmetic and the argmax bytes are shared by the slots; only the <= ceil(K/s)^2 windows that contain the
 // pixel are visited.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+__global__ void __launch_bounds__(256, 3) maxpool_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
                                                           float* __restrict__ gx, long long gx_slot,
                                                           const unsigned char* __restrict__ idx, int B, int Hs,
                                                           int Ws, int Hd, int Wd, int Cp, int KH, int KW, int sh,
