@@ -263,16 +263,18 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         if V.ndim != 2 or V.shape[0] != Pn:
             raise ValueError(f"Expected a flat [P={Pn}, K] matrix, got {tuple(V.shape)}.")
         K = V.shape[1]
-        _, world = cdist.rank_world()
         from .engine import MAX_COLUMNS_PER_SWEEP
 
-        if (dev.type != "cuda" or world > 1 or not self._STREAMABLE or K > MAX_COLUMNS_PER_SWEEP
+        rank, world = cdist.rank_world()
+        if (dev.type != "cuda" or not self._STREAMABLE or K > MAX_COLUMNS_PER_SWEEP
                 or getattr(self, "_mc_samples", 0) > 0):
-            res = (self @ V.to(dev)).to("cpu")  # general path: whole-matrix copies
-            if out is not None:
-                out.copy_(res)
-                return out
-            return res
+            # general path (sharded / sampled / wide products): whole-matrix copies around the resident product,
+            # asynchronous when the host tensors are pinned
+            res = self @ V.to(dev, non_blocking=True)
+            if out is None:
+                out = torch.empty(res.shape, dtype=res.dtype, pin_memory=(dev.type == "cuda"))
+            out.copy_(res, non_blocking=True)
+            return out
         V = V.to(torch.float32)
         if out is None:
             out = torch.empty(Pn, K, dtype=torch.float32, pin_memory=True)
@@ -317,15 +319,28 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
             X, y = cur
             if not isinstance(X, Tensor):
                 raise NotImplementedError("The B200 engine needs tensor inputs X.")
-            self._engine.matmat_batch(self.KIND, X, y, Vd, outd, self._get_normalization_factor(X, y),
-                                      v_ready=v_ready if first else None,
-                                      out_done=out_done if nxt is None else None)
+            alpha = self._get_normalization_factor(X, y)
+            if world > 1:  # data-parallel shard (see _matmat); the result is only final after the all-reduce
+                Xs, ys, scale = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
+                if Xs is not None:
+                    self._engine.matmat_batch(self.KIND, Xs, ys, Vd, outd, alpha, scale=scale[0],
+                                              v_ready=v_ready if first else None)
+                else:
+                    main.wait_stream(s_in)
+            else:
+                self._engine.matmat_batch(self.KIND, X, y, Vd, outd, alpha, v_ready=v_ready if first else None,
+                                          out_done=out_done if nxt is None else None)
             first, cur = False, nxt
-        with torch.cuda.stream(s_out):
-            for (blo, bhi, _), e in zip(reversed(buckets), reversed(bucket_events)):
-                s_out.wait_event(e)
-                out[blo:bhi].copy_(outd[blo:bhi], non_blocking=True)
-        main.wait_stream(s_out)
+        if world > 1:
+            main.wait_stream(s_in)
+            cdist.all_reduce_sum(outd)
+            out.copy_(outd, non_blocking=True)
+        else:
+            with torch.cuda.stream(s_out):
+                for (blo, bhi, _), e in zip(reversed(buckets), reversed(bucket_events)):
+                    s_out.wait_event(e)
+                    out[blo:bhi].copy_(outd[blo:bhi], non_blocking=True)
+            main.wait_stream(s_out)
         main.wait_stream(s_in)
         Vd.record_stream(s_in)
         outd.record_stream(s_out)
