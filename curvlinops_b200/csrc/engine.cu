@@ -2,7 +2,7 @@
 //   forward + Jv      (primal slot 0, tangent slots 1..K)
 //   backward + J^T    (cotangent slots 1..K, written over the dead tangents in GGN mode)
 // behind the C ABI of include/curvb200.h.  Host code only plans and launches; all arithmetic is in the
-// kernels of gemm_simt.cuh / tc_gemm.cuh / elementwise.cuh.
+// kernels of hs_gemm.cuh (default tensor-core path) / tc_gemm.cuh / gemm_simt.cuh / elementwise.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>

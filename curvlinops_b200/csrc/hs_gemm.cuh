@@ -10,14 +10,24 @@
 // Elements smaller than 2^-17 of their slot's maximum lose relative (not absolute) accuracy: the absolute
 // error of an operand is bounded by 2^-39 of the slot maximum.
 //
-// Because the operands are already in their final format in global memory, the producers are pure copies:
-// 16-byte cp.async with zero fill (padding / ragged edges) straight into the swizzled UMMA layout, completion
-// signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) - no register staging, no ALU work.
+// Because the operands are already in their final format in global memory, the producers are pure copies: one TMA
+// im2col box per plane and stage for the gathered activations (cuTensorMapEncodeIm2col: 128 pixels x 64 channels of
+// one filter tap, SWIZZLE_128B = the K-major UMMA tile; zero fill of padding / ragged edges by the hardware), one
+// 3-d tiled TMA box per plane for the cotangent tiles of all slots in the wgrad, one cp.async.bulk for the
+// pre-swizzled weight block; shapes TMA cannot express (C % 64 != 0) use 16-byte cp.async with zero fill,
+// completion signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) - no register staging, no ALU work.
+// The MMA warp runs its loop converged and one elect.sync lane issues the MMAs + commits of a stage.
 //
-//   hs_absmax_kernel / hs_split_kernel   fp32 [slot][n] -> scale bits + hi/lo planes
+//   hs_absmax_kernel / hs_split_kernel   fp32 [slot][n] -> scale bits + hi/lo planes (the BN kernels of
+//                                        elementwise.cuh write planes directly where a bound gives the scale)
 //   hs_pack_image_kernel                 packed fp32 weights [N][Kd] -> K-major SWIZZLE_128B image (hi, lo)
-//   gather_gemm_hs<BN>                   forward conv + tangents, dgrad   (contract of gather_gemm_tc)
+//   gather_gemm_hs<BN>                   forward conv + tangents, dgrad   (contract of gather_gemm_tc); main and
+//                                        cross-term accumulators in separate TMEM buffers, parity-class
+//                                        decomposition of strided dgrads
+//   gather_gemm_hs_stack<BN>             shared-activation segment of a group of slots stacked along N (the stem)
 //   wgrad_gemm_hs                        weight gradients of all K slots  (contract of wgrad_gemm_tc_ms)
+// tools/hs_selftest.cu checks all of them against a CPU double reference; tests/host/hs_host_test.cu the host
+// planning code.  The `debug` fields of the argument structs are timing experiments (results invalid).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>

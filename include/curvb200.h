@@ -193,9 +193,11 @@ int curv_profile_read(double* ms, double* flops, long long* count);
 /* one class at a time; class 2 = the absmax / fp16 hi-lo split passes feeding the half-split kernels */
 int curv_profile_read_class(int cls, double* ms, double* flops, long long* count);
 /* 0: SIMT fp32 contraction kernels only, 1 (default): tcgen05 tensor-core kernels (fp16 hi/lo "half-split"
-   where the channel count allows it, 3xTF32 split otherwise) for layers large enough to fill 128-row
-   tiles, 2: tcgen05 for every contraction (tests).  Bits 4.. are debug switches: 0x10 no tcgen05 gather GEMM,
-   0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead).  Returns the old mode. */
+   where the shape allows it, 3xTF32 split for the Hessian R-op and the KFAC Gram matrices) for layers with at least
+   256 GEMM rows, 2: tcgen05 for every contraction (tests).  Bits 4.. are A/B switches: 0x10 no tcgen05 gather GEMM,
+   0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead), 0x400 BatchNorm kernels never write
+   operand planes directly (separate split passes), 0x800 no N-stacked kernel for shared-activation layers.
+   Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);
 /* Everything global that changes which kernels a call launches: the mode word above | (profiling enabled) << 16.
    Host mirrors that replay captured CUDA graphs of curv_matmat_batch key their caches on it. */
