@@ -11,6 +11,7 @@ from .curvature import (CurvatureLinearOperator, EFLinearOperator, GGNLinearOper
                         HessianLinearOperator)
 from .jacobian import JacobianLinearOperator, TransposedJacobianLinearOperator
 from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
+from .lanczos import fast_lanczos, lanczos_eigsh
 from .linop import PyTorchLinearOperator
 from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
                          FromCanonicalLinearOperator, KroneckerProductLinearOperator,
@@ -21,6 +22,8 @@ __all__ = [
     "CurvatureLinearOperator",
     "GGNLinearOperator",
     "EFLinearOperator",
+    "fast_lanczos",
+    "lanczos_eigsh",
     "HessianLinearOperator",
     "JacobianLinearOperator",
     "TransposedJacobianLinearOperator",

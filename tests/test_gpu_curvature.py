@@ -240,3 +240,20 @@ def test_matmat_pinned_streams_and_matches(name, op):
     torch.cuda.synchronize()
     assert torch.equal(got2, ref)
     assert_parity(got, fx["ggn" if op == "ggn" else "hessian"], params)
+
+
+def test_on_device_lanczos_matches_scipy_eigsh():
+    """``lanczos_eigsh`` (all vectors on the device) vs ``scipy.sparse.linalg.eigsh`` through ``to_scipy()`` on the
+    same GGN operator (reference usage: docs/examples/basic_usage/example_eigenvalues.py:65-77)."""
+    from scipy.sparse.linalg import eigsh
+
+    from curvlinops_b200 import lanczos_eigsh
+
+    model, loss, data, fx, params = _setup("mlp_c1_ce_mean")
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    ev, vec, nprod = lanczos_eigsh(G, k=3, which="LA", tol=1e-5, return_info=True)
+    ref = eigsh(G.to_scipy(), k=3, which="LA", tol=1e-6, return_eigenvectors=False)
+    torch.testing.assert_close(ev.double().cpu(), torch.from_numpy(ref).double().sort().values, rtol=2e-4, atol=1e-6)
+    resid = ((G @ vec) - vec * ev).norm(dim=0) / ev.abs().max()
+    assert bool((resid < 1e-3).all()), resid
+    assert vec.device.type == "cuda" and nprod < 200
