@@ -1,4 +1,7 @@
-"""Full-size parity (run on the GPU box): ResNet-18, B x 3 x 224 x 224, GGN @ 1-2 columns.
+"""TEST INFRASTRUCTURE (manual script, not collected by pytest; it is the only checker that uses the oracle at full
+size, hence it lives under tests/).  Run on the GPU box:  python tests/fullsize_parity_gpu.py [batch]
+
+Full-size parity: ResNet-18, B x 3 x 224 x 224, GGN @ 1-2 columns.
 Reference = the oracle's two-sweep restatement evaluated in float64 on the GPU (same algorithm as
 oracle/curvature_oracle.py, device-agnostic torch ops).  Reports, per engine mode, the max error relative
 to max|ref| and whether allclose(rtol=1e-4, atol=1e-5*max|ref|) holds; per-parameter worst offenders."""
