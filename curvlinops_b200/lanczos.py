@@ -18,34 +18,39 @@ from torch import Tensor
 from .linop import PyTorchLinearOperator
 
 
+def _three_term_recurrence(A: PyTorchLinearOperator, steps: int, start: Tensor) -> tuple[Tensor, Tensor]:
+    """Diagonal / off-diagonal of the Lanczos tridiagonal after ``steps`` products, keeping only the two most
+    recent basis vectors (no re-orthogonalisation)."""
+    diag = torch.empty(steps, device=A.device, dtype=A.dtype)
+    off = torch.empty(max(steps - 1, 0), device=A.device, dtype=A.dtype)
+    q_old, q = torch.zeros_like(start), start / torch.linalg.vector_norm(start)
+    b_old = torch.zeros((), device=A.device, dtype=A.dtype)
+    for j in range(steps):
+        r = A @ q
+        if j > 0:
+            r = r - b_old * q_old
+        diag[j] = torch.dot(r, q)
+        r = r - diag[j] * q
+        if j + 1 < steps:
+            b_old = torch.linalg.vector_norm(r)
+            off[j] = b_old
+            q_old, q = q, r / b_old
+    return diag, off
+
+
 def fast_lanczos(A: PyTorchLinearOperator, ncv: int, use_eigh_tridiagonal: bool = False) -> tuple[Tensor, Tensor]:
-    """Lanczos iterations without re-orthogonalisation; returns ``(evals, evecs)`` of the tridiagonal matrix
-    (same contract and random start ``randn(dim)`` as the reference, ``spectrum.py:413-475``)."""
-    device, dtype = A.device, A.dtype
-    alphas = torch.zeros(ncv, device=device, dtype=dtype)
-    betas = torch.zeros(ncv - 1, device=device, dtype=dtype)
-    dim = A.shape[1]
-    v, v_prev = None, None
-    for m in range(ncv):
-        if m == 0:
-            v = torch.randn(dim, device=device, dtype=dtype)
-            v /= torch.linalg.vector_norm(v)
-            v_next = A @ v
-        else:
-            v_next = A @ v - betas[m - 1] * v_prev
-        alphas[m] = (v_next * v).sum()
-        v_next -= alphas[m] * v
-        if m != ncv - 1:
-            betas[m] = torch.linalg.vector_norm(v_next)
-            v_next /= betas[m]
-            v_prev = v
-            v = v_next
+    """Eigen-decomposition ``(evals, evecs)`` of the ``ncv x ncv`` Lanczos tridiagonal of ``A`` started from a
+    standard-normal vector, without re-orthogonalisation - the contract of the reference's routine of the same name
+    (``spectrum.py:413-475``; ``evecs[:, i]`` belongs to ``evals[i]``).  ``use_eigh_tridiagonal`` selects SciPy's
+    tridiagonal solver (faster, less stable) instead of a dense ``eigh``."""
+    start = torch.randn(A.shape[1], device=A.device, dtype=A.dtype)
+    diag, off = _three_term_recurrence(A, ncv, start)
     if use_eigh_tridiagonal:
         from scipy.linalg import eigh_tridiagonal
 
-        ev, evec = eigh_tridiagonal(alphas.detach().cpu().numpy(), betas.detach().cpu().numpy())
-        return (torch.as_tensor(ev, device=device, dtype=dtype), torch.as_tensor(evec, device=device, dtype=dtype))
-    T = torch.diag_embed(alphas) + torch.diag_embed(betas, offset=1) + torch.diag_embed(betas, offset=-1)
+        w, U = eigh_tridiagonal(diag.cpu().numpy(), off.cpu().numpy())
+        return torch.as_tensor(w, device=A.device, dtype=A.dtype), torch.as_tensor(U, device=A.device, dtype=A.dtype)
+    T = torch.diag(diag) + torch.diag(off, 1) + torch.diag(off, -1)
     return torch.linalg.eigh(T)
 
 
