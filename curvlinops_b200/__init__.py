@@ -2,13 +2,17 @@
 
 Drop-in operator classes (same names / constructor arguments as the reference):
 ``HessianLinearOperator``, ``GGNLinearOperator``, ``EFLinearOperator``, ``KFACLinearOperator``,
-``EKFACLinearOperator``, the Jacobian operators and the
-structured operators they are assembled from.  All arithmetic runs in hand-written sm_100a CUDA kernels
+``EKFACLinearOperator``, the Jacobian operators, the structured operators they are assembled from, and the
+consumers of their products (CG / Neumann / LSMR inverses, Lanczos, randomised trace / diagonal estimators).  All arithmetic runs in hand-written sm_100a CUDA kernels
 behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
 """
 
 from .curvature import (CurvatureLinearOperator, EFLinearOperator, GGNLinearOperator,
                         HessianLinearOperator)
+from .dense import DiagonalLinearOperator, IdentityLinearOperator, TensorLinearOperator
+from .estimators import (hutchinson_diag, hutchinson_squared_fro, hutchinson_trace, hutchpp_trace, xdiag,
+                         xtrace)
+from .inverse import CGInverseLinearOperator, LSMRInverseLinearOperator, NeumannInverseLinearOperator
 from .jacobian import JacobianLinearOperator, TransposedJacobianLinearOperator
 from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
 from .lanczos import fast_lanczos, lanczos_eigsh
@@ -36,4 +40,16 @@ __all__ = [
     "BlockDiagonalLinearOperator",
     "ToCanonicalLinearOperator",
     "FromCanonicalLinearOperator",
+    "TensorLinearOperator",
+    "DiagonalLinearOperator",
+    "IdentityLinearOperator",
+    "CGInverseLinearOperator",
+    "LSMRInverseLinearOperator",
+    "NeumannInverseLinearOperator",
+    "hutchinson_trace",
+    "hutchpp_trace",
+    "xtrace",
+    "hutchinson_diag",
+    "xdiag",
+    "hutchinson_squared_fro",
 ]
