@@ -18,7 +18,7 @@ divisions are guarded by ``eps`` (a column whose ``pᵀAp`` falls below ``eps`` 
 caps the attainable accuracy — the reference's tests pass ``eps=0`` for accurate solves), and the loop stops
 once, after at least 10 iterations, the mean residual norm of the normalised systems is below ``tolerance``.  The parity anchor is the reference's own tests of
 this class (``test/test_inverse.py:29-166``: product with the inverse vs the dense inverse), which
-``tests/test_inverse_cpu.py`` / ``tests/test_gpu_inverse.py`` re-run.
+``tests/test_inverse_cpu.py`` / ``tests/test_gpu_z_consumers.py`` re-run.
 """
 
 from __future__ import annotations
