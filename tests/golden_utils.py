@@ -14,6 +14,8 @@ BUILDERS = {
     "mlp_c1_ce_sum": (lambda: mlp_c1(), lambda: nn.CrossEntropyLoss(reduction="sum")),
     "mlp_c1_mse_mean": (lambda: mlp_c1(), lambda: nn.MSELoss()),
     "miniresnet_ce_mean": (lambda: MiniResNet(), lambda: nn.CrossEntropyLoss()),
+    "mlp_bce_mean": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss()),
+    "mlp_bce_sum": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss(reduction="sum")),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

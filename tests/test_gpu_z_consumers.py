@@ -1,7 +1,10 @@
 """GPU tests of the consumers of the engine's products: CG / Neumann inverses of the
 damped GGN, with a KFAC inverse as preconditioner, and the randomised trace / diagonal estimators.  The checks
 themselves live in ``tests/consumer_checks.py`` and are validated on the CPU against dense operators; here the
-operator is the engine's GGN (fp32) and the dense matrix is that same GGN applied to the identity."""
+operator is the engine's GGN (fp32) and the dense matrix is that same GGN applied to the identity.
+
+Also here: the BCEWithLogitsLoss parity cases.  Everything in this file was written after the round's last GPU
+slot (the file name sorts it behind the suites that have run on the B200)."""
 import pytest
 import torch
 
@@ -35,3 +38,45 @@ def test_inverses_of_damped_ggn(name):
 def test_estimators_on_ggn(name):
     *_, G, dense = _ggn(name)
     check_estimators(G, dense)
+
+
+# ---- BCEWithLogitsLoss (fixtures of oracle/make_golden_bce.py): the third loss of the reference's test matrix ----
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum"]
+
+
+def _parity(got, ref, rtol=1e-4):
+    """rtol 1e-4 (BASELINE tolerance, fp32 engine vs float64 reference), atol 1e-5 * max|ref|."""
+    got, ref = got.detach().double().cpu(), ref.double().cpu()
+    assert torch.allclose(got, ref, rtol=rtol, atol=1e-5 * ref.abs().max().item()), \
+        f"max abs err {(got - ref).abs().max():.3e} vs max|ref| {ref.abs().max():.3e}"
+
+
+@pytest.mark.parametrize("name", BCE_CASES)
+def test_bce_curvature_matches_reference_golden(name):
+    from curvlinops_b200 import EFLinearOperator, HessianLinearOperator
+
+    model, loss, data, fx = load_case(name, dtype=torch.float32, device="cuda")
+    params = dict(model.named_parameters())
+    V = fx["V"].float().cuda()
+    for cls, key in [(GGNLinearOperator, "ggn"), (HessianLinearOperator, "hessian"), (EFLinearOperator, "ef")]:
+        op = cls(model, loss, params, data, check_deterministic=False)
+        _parity(op @ V, fx[key])
+
+
+@pytest.mark.parametrize("name", BCE_CASES)
+@pytest.mark.parametrize("M", [1, 3])
+def test_bce_mc_ggn_with_reference_samples(name, M):
+    """MC-GGN handed the would-be gradients the reference drew (same seed => same CPU stream)."""
+    from oracle import curvature_oracle as orc
+
+    model, loss, data, fx = load_case(name, dtype=torch.float32, device="cuda")
+    params = dict(model.named_parameters())
+    cpu_model = load_case(name)[0]
+    gs = []
+    with torch.random.fork_rng():
+        torch.manual_seed(1234)
+        for X, _ in data:
+            gs.append(orc.mc_grad_outputs(loss, cpu_model(X.double().cpu()).detach(), M).float())
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=M, seed=1234)
+    G._mc_grad_override = gs
+    _parity(G @ fx["V"].float().cuda(), fx[f"ggn_mc{M}"])

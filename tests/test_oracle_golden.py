@@ -6,9 +6,10 @@ from oracle import curvature_oracle as orc
 from tests.golden_utils import flat, load_case, split_like
 
 CASES = ["mlp_c1_ce_mean", "mlp_c1_ce_sum", "mlp_c1_mse_mean", "miniresnet_ce_mean"]
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum"]  # fixtures of oracle/make_golden_bce.py (carry their own "ef")
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + BCE_CASES)
 def test_ggn_and_hessian_match_reference(name):
     model, loss, data, fx = load_case(name)
     params = dict(model.named_parameters())
@@ -19,7 +20,7 @@ def test_ggn_and_hessian_match_reference(name):
                                fx["hessian"], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + BCE_CASES)
 @pytest.mark.parametrize("M", [1, 3])
 def test_mc_ggn_matches_reference_stream(name, M):
     """Same seed => same global-RNG stream as the reference (curvlinops/ggn.py:337-341)."""
@@ -44,3 +45,11 @@ def test_empirical_fisher_matches_reference(name):
     V = split_like(fx["V"], params)
     ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "ef.npz"))[name])
     torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", BCE_CASES)
+def test_empirical_fisher_bce_matches_reference(name):
+    model, loss, data, fx = load_case(name)
+    params = dict(model.named_parameters())
+    V = split_like(fx["V"], params)
+    torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), fx["ef"], rtol=1e-9, atol=1e-12)
