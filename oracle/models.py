@@ -12,6 +12,12 @@ def mlp_c1(classes: int = 10, width: int = 64) -> nn.Sequential:
     )
 
 
+def mlp_smooth(width: int = 16, classes: int = 6) -> nn.Sequential:
+    """Linear-Sigmoid-Linear-Tanh-Linear: smooth activations, so the Hessian has second-order terms."""
+    return nn.Sequential(nn.Linear(width, width), nn.Sigmoid(), nn.Linear(width, width), nn.Tanh(),
+                         nn.Linear(width, classes))
+
+
 class BasicBlock(nn.Module):
     """torchvision-style residual block (conv-bn-relu-conv-bn + shortcut, relu)."""
 

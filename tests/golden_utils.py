@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from oracle.models import ConvNetBias, MiniResNet, mlp_c1
+from oracle.models import ConvNetBias, MiniResNet, mlp_c1, mlp_smooth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -16,6 +16,7 @@ BUILDERS = {
     "miniresnet_ce_mean": (lambda: MiniResNet(), lambda: nn.CrossEntropyLoss()),
     "mlp_bce_mean": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss()),
     "mlp_bce_sum": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss(reduction="sum")),
+    "mlp_sigmoid_tanh_mse_sum": (lambda: mlp_smooth(), lambda: nn.MSELoss(reduction="sum")),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

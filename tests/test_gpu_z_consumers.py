@@ -3,7 +3,7 @@ damped GGN, with a KFAC inverse as preconditioner, and the randomised trace / di
 themselves live in ``tests/consumer_checks.py`` and are validated on the CPU against dense operators; here the
 operator is the engine's GGN (fp32) and the dense matrix is that same GGN applied to the identity.
 
-Also here: the BCEWithLogitsLoss parity cases.  Everything in this file was written after the round's last GPU
+Also here: the BCEWithLogitsLoss and the Sigmoid / Tanh parity cases.  Everything in this file was written after the round's last GPU
 slot (the file name sorts it behind the suites that have run on the B200)."""
 import pytest
 import torch
@@ -40,8 +40,9 @@ def test_estimators_on_ggn(name):
     check_estimators(G, dense)
 
 
-# ---- BCEWithLogitsLoss (fixtures of oracle/make_golden_bce.py): the third loss of the reference's test matrix ----
-BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum"]
+# ---- BCEWithLogitsLoss (fixtures of oracle/make_golden_bce.py): the third loss of the reference's test matrix;
+# Sigmoid / Tanh activations under MSELoss(sum) (oracle/make_golden_act.py): second-order terms of the Hessian R-op
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum"]
 
 
 def _parity(got, ref, rtol=1e-4):

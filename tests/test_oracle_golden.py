@@ -6,7 +6,8 @@ from oracle import curvature_oracle as orc
 from tests.golden_utils import flat, load_case, split_like
 
 CASES = ["mlp_c1_ce_mean", "mlp_c1_ce_sum", "mlp_c1_mse_mean", "miniresnet_ce_mean"]
-BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum"]  # fixtures of oracle/make_golden_bce.py (carry their own "ef")
+# fixtures of oracle/make_golden_bce.py / make_golden_act.py (they carry their own "ef")
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum"]
 
 
 @pytest.mark.parametrize("name", CASES + BCE_CASES)
