@@ -13,6 +13,7 @@ slice of every mini-batch and the ``[P, K]`` result is summed with one NCCL all-
 
 from __future__ import annotations
 
+import copy
 from collections.abc import Callable, Iterable, MutableMapping
 
 import torch
@@ -80,6 +81,10 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         self._data = data
         self._progressbar = progressbar
         self._batch_size_fn = (lambda X: X.shape[0]) if batch_size_fn is None else batch_size_fn
+        self._input_key = None
+        first_X = next(iter(data))[0]
+        if isinstance(first_X, MutableMapping):
+            self._adapt_dict_inputs(first_X)
         self._engine = Engine(self._model_func, loss_func, params)
         self._N_data, self._num_per_example_loss_terms = self._get_data_statistics(
             num_data, num_per_example_loss_terms
@@ -90,6 +95,32 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         PyTorchLinearOperator.__init__(self, shapes, shapes)
         if check_deterministic:
             self._check_deterministic_matvec()
+
+    # ---- dict-like inputs (reference _empirical_risk.py:37-119, test/cases.py:36-60) ------------------
+    def _adapt_dict_inputs(self, first_X: MutableMapping) -> None:
+        """The engine differentiates a function of ONE input tensor.  For dict-like mini-batches the entry that
+        holds it (the only floating-point tensor of shape ``[B, C]`` / ``[B, C, H, W]``) becomes that tensor and
+        the model function is wrapped to put it back into a copy of the mapping; the remaining entries must not
+        be tensors and are taken from the first mini-batch (they are constants of the traced program).  The data
+        loop then yields the tensor, tagged with the batch size ``batch_size_fn`` reports for the mapping."""
+        tensors = {k: v for k, v in first_X.items() if isinstance(v, Tensor)}
+        keys = [k for k, v in tensors.items() if v.is_floating_point() and v.ndim in (2, 4)]
+        if len(keys) != 1 or len(tensors) != 1:
+            raise NotImplementedError(
+                "The B200 engine supports dict-like inputs with exactly one tensor entry (floating point, shape "
+                f"[B, C] or [B, C, H, W]); got tensor entries { {k: tuple(v.shape) for k, v in tensors.items()} }."
+            )
+        (key,) = keys
+        template, inner, user_bs = first_X, self._model_func, self._batch_size_fn
+
+        def model_on_tensor(params, Xt):
+            X = copy.copy(template)
+            X[key] = Xt
+            return inner(params, X)
+
+        self._input_key = key
+        self._model_func = model_on_tensor
+        self._batch_size_fn = lambda X: getattr(X, "_curv_batch_size", None) or user_bs(X)
 
     # ---- properties ----------------------------------------------------------------------------
     @property
@@ -137,6 +168,10 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         for X, y in it:
             if isinstance(X, Tensor):
                 X = X.to(dev)
+            elif self._input_key is not None:
+                Xt = X[self._input_key].to(dev).detach()  # a new tensor object: the tag stays off the caller's
+                Xt._curv_batch_size = self._batch_size_fn(X)
+                X = Xt
             yield X, y.to(dev)
 
     def _get_normalization_factor(self, X, y) -> float:

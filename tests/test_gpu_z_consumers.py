@@ -81,3 +81,31 @@ def test_bce_mc_ggn_with_reference_samples(name, M):
     G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=M, seed=1234)
     G._mc_grad_override = gs
     _parity(G @ fx["V"].float().cuda(), fx[f"ggn_mc{M}"])
+
+
+# ---- dict-like inputs (reference test/cases.py:36-60,148-168): same products as with the tensor itself --------
+def test_dict_like_inputs_match_tensor_inputs():
+    from collections import UserDict
+
+    from curvlinops_b200 import HessianLinearOperator
+
+    model, loss, data, fx = load_case("mlp_c1_ce_mean", dtype=torch.float32, device="cuda")
+    params = dict(model.named_parameters())
+
+    class OnDict(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, batch):
+            return self.net(batch["x"].to(next(self.parameters()).device))
+
+    wrapped = OnDict(model)
+    wparams = dict(wrapped.named_parameters())
+    ddata = [(UserDict({"x": X.cpu(), "note": "kept"}), y.cpu()) for X, y in data]  # host-resident mappings
+    V = fx["V"].float().cuda()
+    for cls in (GGNLinearOperator, HessianLinearOperator):
+        ref = cls(model, loss, params, data, check_deterministic=False) @ V
+        got = cls(wrapped, loss, wparams, ddata, check_deterministic=True,
+                  batch_size_fn=lambda b: b["x"].shape[0]) @ V
+        assert torch.equal(got, ref)

@@ -168,3 +168,54 @@ def test_linop_formats_and_errors():
         op @ op
     with pytest.raises(ValueError, match="Dtype mismatch"):
         op + _Dense(A.float(), in_shape, out_shape)
+
+
+def test_dict_like_inputs_are_adapted_to_the_tensor_entry():
+    """Dict-like mini-batches (reference test/cases.py:36-60, 148-168): the single tensor entry becomes the engine's
+    input, ``batch_size_fn`` still sees the mapping, other entries are constants of the traced model function."""
+    from collections import UserDict
+
+    import pytest
+    from torch import nn
+
+    from curvlinops_b200 import GGNLinearOperator
+    from curvlinops_b200.capture import capture
+
+    class DictModel(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = nn.Sequential(nn.Linear(10, 5), nn.ReLU(), nn.Linear(5, 3))
+
+        def forward(self, data):
+            assert data["tag"] == "a"
+            return self.net(data["x"].to(next(self.parameters()).device))
+
+    torch.manual_seed(0)
+    m = DictModel().eval()
+    data = [(UserDict({"x": torch.rand(3, 10), "tag": "a"}), torch.randint(0, 3, (3,))),
+            (UserDict({"x": torch.rand(4, 10), "tag": "a"}), torch.randint(0, 3, (4,)))]
+    params = dict(m.named_parameters())
+    with pytest.raises(ValueError, match="`batch_size_fn` is required"):
+        GGNLinearOperator(m, nn.CrossEntropyLoss(), params, data, check_deterministic=False)
+    seen = []
+
+    def batch_size_fn(X):
+        seen.append(type(X).__name__)
+        return X["x"].shape[0]
+
+    G = GGNLinearOperator(m, nn.CrossEntropyLoss(), params, data, check_deterministic=False,
+                          batch_size_fn=batch_size_fn)
+    assert G._N_data == 7 and set(seen) == {"UserDict"}
+    batches = list(G._loop_over_data())
+    assert [tuple(X.shape) for X, _ in batches] == [(3, 10), (4, 10)]
+    assert [G._batch_size_fn(X) for X, _ in batches] == [3, 4]
+    assert abs(G._get_normalization_factor(*batches[1]) - 4 / 7) < 1e-12
+    assert not hasattr(data[0][0]["x"], "_curv_batch_size")  # the caller's tensors stay untouched
+    torch.testing.assert_close(G._model_func(params, batches[1][0]), m(data[1][0]))
+    lp = capture(G._model_func, params, batches[0][0])
+    assert [n["op"] for n in lp.nodes] == [capi.OP_INPUT, capi.OP_CONV, capi.OP_RELU, capi.OP_CONV]
+
+    two = [(UserDict({"x": torch.rand(3, 10), "mask": torch.ones(3, 10)}), torch.randint(0, 3, (3,)))]
+    with pytest.raises(NotImplementedError, match="exactly one tensor entry"):
+        GGNLinearOperator(m, nn.CrossEntropyLoss(), params, two, check_deterministic=False,
+                          batch_size_fn=batch_size_fn)
