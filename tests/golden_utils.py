@@ -17,6 +17,7 @@ BUILDERS = {
     "mlp_bce_mean": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss()),
     "mlp_bce_sum": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss(reduction="sum")),
     "mlp_sigmoid_tanh_mse_sum": (lambda: mlp_smooth(), lambda: nn.MSELoss(reduction="sum")),
+    "cnn_bias_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

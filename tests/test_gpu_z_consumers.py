@@ -42,7 +42,8 @@ def test_estimators_on_ggn(name):
 
 # ---- BCEWithLogitsLoss (fixtures of oracle/make_golden_bce.py): the third loss of the reference's test matrix;
 # Sigmoid / Tanh activations under MSELoss(sum) (oracle/make_golden_act.py): second-order terms of the Hessian R-op
-BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum"]
+# plain CNN with conv biases, stride-2 un-padded conv, flatten -> Linear over a 3x3 map (oracle/make_golden_cnn.py)
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum", "cnn_bias_ce_mean"]
 
 
 def _parity(got, ref, rtol=1e-4):

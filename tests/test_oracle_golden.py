@@ -6,8 +6,8 @@ from oracle import curvature_oracle as orc
 from tests.golden_utils import flat, load_case, split_like
 
 CASES = ["mlp_c1_ce_mean", "mlp_c1_ce_sum", "mlp_c1_mse_mean", "miniresnet_ce_mean"]
-# fixtures of oracle/make_golden_bce.py / make_golden_act.py (they carry their own "ef")
-BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum"]
+# fixtures of oracle/make_golden_bce.py / make_golden_act.py / make_golden_cnn.py (they carry their own "ef")
+BCE_CASES = ["mlp_bce_mean", "mlp_bce_sum", "mlp_sigmoid_tanh_mse_sum", "cnn_bias_ce_mean"]
 
 
 @pytest.mark.parametrize("name", CASES + BCE_CASES)
