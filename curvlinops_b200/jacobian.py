@@ -21,6 +21,8 @@ class _JacobianBase(CurvatureLinearOperator):
 
     def __init__(self, model_func, params, data, progressbar=False, check_deterministic=True, num_data=None,
                  batch_size_fn=None):
+        if not isinstance(next(iter(data))[0], Tensor):
+            raise NotImplementedError("The Jacobian operators of the B200 engine need tensor inputs X.")
         self._ctor_args = dict(progressbar=progressbar, batch_size_fn=batch_size_fn)
         super().__init__(model_func, None, params, data, progressbar=progressbar,
                          check_deterministic=check_deterministic, num_data=num_data, batch_size_fn=batch_size_fn)

@@ -215,6 +215,11 @@ def test_dict_like_inputs_are_adapted_to_the_tensor_entry():
     lp = capture(G._model_func, params, batches[0][0])
     assert [n["op"] for n in lp.nodes] == [capi.OP_INPUT, capi.OP_CONV, capi.OP_RELU, capi.OP_CONV]
 
+    from curvlinops_b200 import JacobianLinearOperator
+
+    with pytest.raises(NotImplementedError, match="need tensor inputs"):
+        JacobianLinearOperator(m, params, data, check_deterministic=False, batch_size_fn=batch_size_fn)
+
     two = [(UserDict({"x": torch.rand(3, 10), "mask": torch.ones(3, 10)}), torch.randint(0, 3, (3,)))]
     with pytest.raises(NotImplementedError, match="exactly one tensor entry"):
         GGNLinearOperator(m, nn.CrossEntropyLoss(), params, two, check_deterministic=False,
