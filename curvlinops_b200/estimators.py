@@ -17,10 +17,6 @@ from __future__ import annotations
 import torch
 from torch import Tensor
 
-from .linop import PyTorchLinearOperator
-
-Operator = "PyTorchLinearOperator | Tensor"
-
 
 # ---- probe vectors (reference sampling.py) -------------------------------------------------------
 def rademacher(dim: int, device, dtype) -> Tensor:
