@@ -10,8 +10,8 @@ mini-batch is sharded over the ranks (strong scaling: total work fixed) and the 
 with one NCCL all-reduce.  ``e2e`` is the same product through the public operator API with HOST
 buffers (``matmat_pinned``: pinned X, y and V copied to the device and the result copied back inside the timed
 region, V / result pipelined in parameter buckets against the sweeps).
-``--impl reference`` times the CPU oracle port (the reference is pure Python and cannot travel to the
-GPU box) on the host cores, on a bounded sample of the same workload.
+``--impl reference`` times the UNMODIFIED reference (``oracle/_ref``, copied from /root/reference by
+``oracle/build_ref.py``; git-ignored, travels with the snapshot) on the host cores at full size.
 """
 import argparse
 import json
@@ -104,29 +104,84 @@ def ncu_traffic_per_launch():
     return tot / n if n else None
 
 
-def cpu_reference_run(torch, steps, warmup, sample_batch=32, sample_k=2):
-    """Oracle port of the reference's CPU path on a bounded sample: `sample_batch` of the 128 samples and
-    `sample_k` of the 8 columns; throughput extrapolated linearly in batch and columns
-    (cost is linear in both: independent samples, independent columns)."""
-    from oracle import curvature_oracle as orc
+def config_dict(n_gpus):
+    """The workload both arms are measured on (identical dict in the product and the reference line)."""
+    return {"workload": WORKLOAD, "params": 11689512, "columns": K, "batch": B,
+            "parallelism": f"dp{n_gpus} (mini-batch sharded over the ranks, one all-reduce of [P,K])",
+            "l2": "working set (GBs of activations) far exceeds the 126 MB L2; no flush needed"}
 
-    model, X, y = build_problem(torch, sample_batch)
+
+def host_threads():
+    """Threads the CPU arm may use: every core this process is allowed on (torchrun exports OMP_NUM_THREADS=1,
+    which would otherwise pin the reference to one thread)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_ggn(torch, device, batch, k, repeats, warmup=0):
+    """The UNMODIFIED reference (`oracle/_ref`, built by oracle/build_ref.py) through its own public API:
+    ``GGNLinearOperator(model, CrossEntropyLoss(), params, [(X, y)]) @ V`` on `device`, same seeds / inputs as the
+    GPU arm (benchmark protocol of docs/examples/basic_usage/benchmark_execute.py:287-302: synchronize on both sides,
+    minimum over the repeats).  Returns (seconds per product, P)."""
+    from oracle.build_ref import import_reference
+
+    ref = import_reference()
+    model, X, y = build_problem(torch, batch)
+    model = model.to(device)
+    X, y = X.to(device), y.to(device)
     params = dict(model.named_parameters())
     P = sum(p.numel() for p in params.values())
-    V = [torch.rand(*p.shape, sample_k) for p in params.values()]
-    loss = torch.nn.CrossEntropyLoss()
+    torch.manual_seed(1)
+    V = torch.rand(P, k).to(device)
+    G = ref.GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False,
+                              num_data=batch)
+    sync = torch.cuda.synchronize if device.type == "cuda" else (lambda: None)
     times = []
-    for i in range(warmup + steps):
+    for i in range(warmup + repeats):
+        sync()
         t0 = time.perf_counter()
-        orc.ggn_matmat(model, loss, params, [(X, y)], V, n_data=sample_batch)
+        G @ V
+        sync()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    t_full = t * (B / sample_batch) * (K / sample_k)  # one full step of the workload
+    return min(times), P
+
+
+def cpu_reference_run(torch, repeats, sample_batch=B, sample_k=K):
+    """Reference on the host cores.  Full size by default (`--impl reference`); the GPU arm's `cpu_baseline` leg uses a
+    bounded sample of the mini-batch (samples are independent, so the cost is linear in the batch) with all K
+    columns."""
+    torch.set_num_threads(host_threads())
+    t, P = reference_ggn(torch, torch.device("cpu"), sample_batch, sample_k, repeats)
+    t_full = t * (B / sample_batch) * (K / sample_k)
+    full = sample_batch == B and sample_k == K
     return P * K / t_full, t_full, {
-        "kind": "port", "cores": torch.get_num_threads(),
-        "sample": f"{sample_batch} of {B} samples, {sample_k} of {K} columns per step, "
-                  f"{len(times)} steps, extrapolated linearly to the full step"}
+        "kind": "reference", "cores": torch.get_num_threads(),
+        "sample": (f"full step (B={B}, K={K}), best of {repeats}" if full else
+                   f"{sample_batch} of {B} samples, {sample_k} of {K} columns, best of {repeats}, "
+                   "extrapolated linearly to the full step")}
+
+
+def gpu_library_baseline(torch, dev, repeats=3):
+    """Second bar: the unmodified reference on THIS B200 through torch CUDA (cuDNN / cuBLAS,
+    eager autograd), full size, strict fp32 and with TF32 allowed."""
+    out = {"what": "unmodified reference GGNLinearOperator @ V on the same GPU via torch CUDA (eager), "
+                   f"B={B}, K={K}, min of {repeats} after 1 warm-up", "unit": UNIT}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            t, P = reference_ggn(torch, dev, B, K, repeats, warmup=1)
+            out[name] = {"ms_per_step": t * 1e3, "value": P * K / t}
+            torch.cuda.empty_cache()
+    except Exception as e:  # reported, never fatal: the product arm has already been measured
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
 
 
 def main():
@@ -137,6 +192,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.impl == "reference":  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it may
+        for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ.pop(v, None)
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -146,14 +204,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        value, t_full, cb = cpu_reference_run(torch, steps, warmup)
+        # the reference's own CPU path at FULL size (one product takes tens of seconds on the host cores): best of
+        # at most 2 products, no separate warm-up (stated in the line), so the run ends within a few minutes
+        steps = max(1, min(args.steps, 2))
+        # CURV_BENCH_REF_SAMPLE=<samples>: contract test of this arm on a build container (the line then says so)
+        value, t_full, cb = cpu_reference_run(torch, steps, sample_batch=int(os.environ.get("CURV_BENCH_REF_SAMPLE", B)))
         cb["value"] = value
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": 0, "ms_per_step": t_full * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference algorithm"},
+            "config": config_dict(args.gpus),
+            "note": "unmodified reference (oracle/_ref) on the host cores, torch CPU kernels, full size; "
+                    "ms_per_step is the best of `steps` products; no GPU is used by this arm",
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -281,9 +344,7 @@ def main():
         "metric": METRIC, "value": P * K / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "params": P, "columns": K, "batch": B,
-                   "parallelism": f"dp{world} (mini-batch sharded, one all-reduce of [P,K])",
-                   "l2": "working set (GBs of activations) far exceeds the 126 MB L2; no flush needed"},
+        "config": config_dict(world),
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": P * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(X_host.numel() * 4 + y_host.numel() * 8 + V_host.numel() * 4),
@@ -293,7 +354,8 @@ def main():
                        "note": "default (half-split tcgen05) path vs the exact-fp32 SIMT kernels, full size"},
     }
     if not args.no_cpu_baseline and world == 1:
-        value, t_full, cb = cpu_reference_run(torch, 1, 0)
+        out["gpu_library_baseline"] = gpu_library_baseline(torch, dev)
+        value, t_full, cb = cpu_reference_run(torch, 1, sample_batch=32)
         cb["value"], cb["unit"] = value, UNIT
         out["cpu_baseline"] = cb
     print(json.dumps(out))

@@ -86,7 +86,7 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         return model_func(p, x)
 
     with torch.no_grad():
-        gm = make_fx(functionalize(f), tracing_mode="real")(params, X)
+        gm = make_fx(functionalize(f), tracing_mode="fake", _allow_non_fake_inputs=True)(params, X)
 
     prog = LayerProgram()
     env: dict = {}
@@ -114,6 +114,26 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             continue
         live.add(n)
         stack.extend(a for a in n.all_input_nodes)
+
+    # Consumers per ENGINE value: detach / alias / clone / contiguous / view / getitem nodes resolve to the value of
+    # their input, so the readers of a value are the non-alias users of every FX node of its alias class.
+    alias_targets = (aten.detach.default, aten.alias.default, aten.clone.default, aten.contiguous.default,
+                     aten.view.default, aten._unsafe_view.default, aten.reshape.default, aten.flatten.using_ints)
+
+    def is_alias(n):
+        return n.op == "call_function" and (n.target in alias_targets or "getitem" in str(n.target))
+
+    def alias_root(n):
+        while is_alias(n) and isinstance(n.args[0], torch.fx.Node):
+            n = n.args[0]
+        return n
+
+    readers: dict = {}
+    for n in gm.graph.nodes:
+        if n.op == "placeholder" or is_alias(n) or (n.op != "output" and n not in live):
+            continue
+        for r in {alias_root(i) for i in n.all_input_nodes}:
+            readers[r] = readers.get(r, 0) + 1
 
     def shape_of(ref):
         return prog.values[ref.value]
@@ -238,7 +258,7 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             xr = a[0]
             src = node.args[0]
             prod = producer.get(xr.value) if xr.kind == "act" else None
-            if (fuse_relu and t == aten.relu.default and prod is not None and len(src.users) == 1
+            if (fuse_relu and t == aten.relu.default and prod is not None and readers.get(alias_root(src), 0) == 1
                     and prog.nodes[prod]["op"] in (capi.OP_AFFINE, capi.OP_ADD) and prog.nodes[prod]["kh"] != 2):
                 prog.nodes[prod]["kh"] = 2  # fused: the producing node now writes relu(...)
                 env[node] = _Ref("act", value=xr.value, flat=xr.flat)

@@ -26,14 +26,25 @@ from .engine import Engine
 from .linop import PyTorchLinearOperator, report_allclose
 
 
+class _FunctionalCall:
+    """``(params, X) -> module(X)`` as a picklable callable (operators are saved with ``torch.save``)."""
+
+    def __init__(self, module: Module):
+        self.module = module
+
+    def __call__(self, params: dict[str, Tensor], *inputs):
+        return torch.func.functional_call(self.module, params, inputs)
+
+
 def make_functional_call(module: Module) -> Callable:
     """``(params, X) -> module(X)`` with ``params`` overriding the module's own tensors
     (role of ``curvlinops/utils.py:267-297``)."""
+    return _FunctionalCall(module)
 
-    def call(params: dict[str, Tensor], *inputs):
-        return torch.func.functional_call(module, params, inputs)
 
-    return call
+def _leading_dim(X) -> int:
+    """Default ``batch_size_fn`` (``_empirical_risk.py:83-85``); a named function so operators stay picklable."""
+    return X.shape[0]
 
 
 class CurvatureLinearOperator(PyTorchLinearOperator):
@@ -80,7 +91,7 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         self._loss_func = loss_func
         self._data = data
         self._progressbar = progressbar
-        self._batch_size_fn = (lambda X: X.shape[0]) if batch_size_fn is None else batch_size_fn
+        self._batch_size_fn = _leading_dim if batch_size_fn is None else batch_size_fn
         self._input_key = None
         first_X = next(iter(data))[0]
         if isinstance(first_X, MutableMapping):

@@ -7,6 +7,7 @@ reference (``curvlinops/_torch_base.py:946-989``) -- by calls into ``libcurvb200
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 import os
 
@@ -54,12 +55,16 @@ def loss_scale(loss_func, batch: int, classes: int) -> float:
     return 1.0 / batch if isinstance(loss_func, CrossEntropyLoss) else 1.0 / (batch * classes)
 
 
+_program_serial = itertools.count()
+
+
 class CompiledProgram:
     """A layer program planned for one (input shape, kmax, hessian) combination."""
 
     def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool):
         self.lp: LayerProgram = capture(model_func, params, X, fuse_relu=not (int(hessian) & 1))
         self.kmax = kmax
+        self.serial = next(_program_serial)  # CUDA-graph cache key (an id() could be reused after a rebuild)
         self.batch = X.shape[0]
         self.device = X.device
         lp = self.lp
@@ -130,6 +135,8 @@ class Engine:
         key = (tuple(X.shape), hessian)
         prog = self._programs.get(key)
         if prog is None or prog.kmax < kmax:
+            if prog is not None:  # graphs captured for the replaced program bake in its plan: drop them
+                self._graphs = {k: v for k, v in self._graphs.items() if k[0] != prog.serial}
             prog = CompiledProgram(self.model_func, self.params, X, kmax, hessian)
             self._programs[key] = prog
         return prog
@@ -137,6 +144,7 @@ class Engine:
     def workspace(self, nbytes: int, device) -> Tensor:
         if self._ws is None or self._ws.numel() * 4 < nbytes or self._ws.device != device:
             self._ws = None
+            self._graphs.clear()  # captured graphs bake in the old workspace address
             self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
         return self._ws
 
@@ -154,6 +162,10 @@ class Engine:
         the streaming entry point ``curv_matmat_batch_sync`` (see ``include/curvb200.h``); needs ``K`` columns
         that fit one sweep."""
         self._check_supported()
+        with torch.cuda.device(X.device if X.device.type == "cuda" else V.device):
+            self._matmat_batch(kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done)
+
+    def _matmat_batch(self, kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done) -> None:
         K = V.shape[-1]
         kc = min(K, MAX_COLUMNS_PER_SWEEP)
         X = X.to(torch.float32).contiguous()
@@ -208,7 +220,7 @@ class Engine:
         # The graph is keyed on every pointer it bakes in - including V and out: in steady state the caching
         # allocator hands a caller that builds V / out per product the same blocks again, so replays need no
         # staging copies; a different address is simply another key (eager first, captured on its second sighting).
-        key = (id(prog), kind, loss, K, float(scale or 1.0), float(alpha), X.data_ptr(),
+        key = (prog.serial, kind, loss, K, float(scale or 1.0), float(alpha), X.data_ptr(),
                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
                tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg, V.data_ptr(), out.data_ptr())
         entry = self._graphs.get(key)
@@ -234,6 +246,10 @@ class Engine:
     def predict(self, X: Tensor) -> Tensor:
         """Primal forward through the engine; returns the prediction ``[B, C]`` (a copy)."""
         self._check_supported()
+        with torch.cuda.device(X.device):
+            return self._predict(X)
+
+    def _predict(self, X: Tensor) -> Tensor:
         X = X.to(torch.float32).contiguous()
         prog = self.program(X, 1, False)
         ws = self.workspace(prog.ws_bytes, X.device)

