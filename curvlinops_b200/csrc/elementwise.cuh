@@ -3,6 +3,7 @@
 // apply and the deterministic finishing reductions.  All tensors are [slot][rows][Cp] fp32 with
 // Cp % 4 == 0, so every access is a coalesced float4.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -50,6 +51,12 @@ __device__ __forceinline__ void store_split_planes(__half* __restrict__ ph, __ha
                                                    const float4& r, float sc) {
   // packed conversions: one cvt.rn.f16x2.f32 per pair (the kernels that call this are issue-bound otherwise)
   const float2 a = make_float2(r.x * sc, r.y * sc), b = make_float2(r.z * sc, r.w * sc);
+  if (pl == nullptr) {  // bf16 mode: ONE plane of bf16 values (one 8-byte store per lane, adjacent lanes contiguous)
+    const __nv_bfloat162 ba = __floats2bfloat162_rn(a.x, a.y), bb = __floats2bfloat162_rn(b.x, b.y);
+    reinterpret_cast<uint2*>(ph)[i] = make_uint2(*reinterpret_cast<const unsigned int*>(&ba),
+                                                 *reinterpret_cast<const unsigned int*>(&bb));
+    return;
+  }
   const __half2 ha = __float22half2_rn(a), hb2 = __float22half2_rn(b);
   const float2 fa = __half22float2(ha), fb = __half22float2(hb2);
   const __half2 la = __float22half2_rn(make_float2(a.x - fa.x, a.y - fa.y));
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(256, PLANES ? 3 : 4) affine_fwd_kernel(const f
     }
   }
   auto store_planes = [&](int slot, long long i, const float4& r, float sc) {
-    store_split_planes(ph + (long long)slot * plane_slot, pl + (long long)slot * plane_slot, i, r, sc);
+    store_split_planes(ph + (long long)slot * plane_slot, pl ? pl + (long long)slot * plane_slot : nullptr, i, r, sc);
   };
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -671,7 +678,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
     const float bound = __uint_as_float(__ldg(smax_bits)) * __uint_as_float(__ldg(in_bits + slot));
     pscale = hs_pow2(hs_shift_from_bits(__float_as_uint(bound)));
     oh = reinterpret_cast<uint2*>(ph + (long long)slot_idx * plane_slot);
-    ol = reinterpret_cast<uint2*>(pl + (long long)slot_idx * plane_slot);
+    ol = pl ? reinterpret_cast<uint2*>(pl + (long long)slot_idx * plane_slot) : nullptr;  // null: bf16 mode
     if (blockIdx.x == 0 && threadIdx.x == 0) amax[slot] = __float_as_uint(bound);
   }
   for (int cbase = 0; cbase < C4; cbase += ctile4) {

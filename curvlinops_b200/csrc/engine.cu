@@ -422,6 +422,7 @@ struct Ctx {
   void* const* out_done = nullptr;
   // half-split path: enabled per call; hs_valid[e] = absmax entry e already computed in this call
   bool hs = false;
+  int planes = 2;  // operand planes of the tcgen05 contraction kernels: 2 = fp16 hi/lo (fp32-grade), 1 = bf16 (program flag 4)
   std::vector<char>* hs_valid = nullptr;
   uint32_t* hsbits() const { return reinterpret_cast<uint32_t*>(ws + P->hsbits_off); }
   int bits_act(int v) const { return (2 * v) * (1 + P->kmax); }
@@ -465,6 +466,10 @@ static int hs_absmax(const Ctx& c, const float* x, long long slot_stride, long l
   bool need = false;
   for (int i = 0; i < count; ++i) need = need || !(*c.hs_valid)[entry + i];
   if (!need) return CURV_OK;
+  if (c.planes == 1) {  // bf16 planes need no scale: an absmax word that nobody tracked stays 0 = scale 1
+    for (int i = 0; i < count; ++i) (*c.hs_valid)[entry + i] = 1;
+    return CURV_OK;
+  }
   ProfScope prof(2, 0, c.st);
   if (hs_launch_absmax(x, slot_stride, n, c.hsbits() + entry, count, c.st))
     return fail(CURV_ERR_CUDA, "half-split absmax launch failed");
@@ -482,7 +487,7 @@ static unsigned int* hs_fused_absmax(const Ctx& c, int entry, int count) {
 static int hs_split(const Ctx& c, const float* x, long long slot_stride, long long n, __half* hi, __half* lo,
                     int entry, int count) {
   ProfScope prof(2, 0, c.st);
-  if (hs_launch_split(x, slot_stride, n, hi, lo, n, c.hsbits() + entry, count, c.st))
+  if (hs_launch_split(x, slot_stride, n, hi, c.planes == 1 ? nullptr : lo, n, c.hsbits() + entry, count, c.st))
     return fail(CURV_ERR_CUDA, "half-split split launch failed");
   ++g_launches;
   return CURV_OK;
@@ -533,19 +538,19 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
         int bad = 0;
         if (hsf) {
           bad |= hs_launch_pack_image(c.ws + n.wk_off, 0, reinterpret_cast<__half*>(c.ws + n.wimg_off), 0, g.N,
-                                      g.Nd, g.Kd, 1, c.hsbits() + e0, st);
+                                      g.Nd, g.Kd, 1, c.hsbits() + e0, st, c.planes);
           ++g_launches;
           if (wt) {
             bad |= hs_launch_pack_image(c.ws + n.wkt_off, n.wsize, reinterpret_cast<__half*>(c.ws + n.wimgt_off),
-                                        hs_image_halves(g.Nd, g.Kd), g.N, g.Nd, g.Kd, c.K, c.hsbits() + e0 + 1,
-                                        st);
+                                        hs_image_halves(g.Nd, g.Kd, c.planes), g.N, g.Nd, g.Kd, c.K,
+                                        c.hsbits() + e0 + 1, st, c.planes);
             ++g_launches;
           }
         }
         if (hsd) {
           const Geom& q = n.dgr;
           bad |= hs_launch_pack_image(c.ws + n.wt_off, 0, reinterpret_cast<__half*>(c.ws + n.wtimg_off), 0, q.N,
-                                      q.Nd, q.Kd, 1, c.hsbits() + e0, st);
+                                      q.Nd, q.Kd, 1, c.hsbits() + e0, st, c.planes);
           ++g_launches;
         }
         if (bad) return fail(CURV_ERR_CUDA, "half-split weight image packing failed");
@@ -667,7 +672,8 @@ static int forward(const Ctx& c, const void* X, int K) {
             q.Ah = c.hs1_hi(); q.Al = c.hs1_lo(); q.a_bits = c.hsbits() + ea;
             q.W_img = reinterpret_cast<const __half*>(c.ws + n.wimg_off);
             q.Wt_img = reinterpret_cast<const __half*>(c.ws + n.wimgt_off);
-            q.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd);
+            q.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd, c.planes);
+            q.planes = c.planes;
             q.w_bits = c.hsbits() + c.bits_node((int)(&n - P->nodes.data()));
             q.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
             q.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; q.bias_slot = vo.Cp;
@@ -684,7 +690,8 @@ static int forward(const Ctx& c, const void* X, int K) {
           h.a_has_slots = vi.tan ? 1 : 0; h.a_bits = c.hsbits() + ea;
           h.W_img = reinterpret_cast<const __half*>(c.ws + n.wimg_off);
           h.Wt_img = (d.p0 >= 0 && K > 0) ? reinterpret_cast<const __half*>(c.ws + n.wimgt_off) : nullptr;
-          h.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd);
+          h.Wt_img_slot = hs_image_halves(n.fwd.Nd, n.fwd.Kd, c.planes);
+          h.planes = c.planes;
           h.w_bits = c.hsbits() + c.bits_node((int)(&n - P->nodes.data()));
           h.bias = n.bias_off >= 0 ? c.ws + n.bias_off : nullptr;
           h.bias_t = n.biast_off >= 0 ? c.ws + n.biast_off : nullptr; h.bias_slot = vo.Cp;
@@ -737,7 +744,8 @@ static int forward(const Ctx& c, const void* X, int K) {
           if (planes)
             affine_fwd_kernel<true><<<grid, 256, 0, st>>>(
                 c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
-                c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl, am, c.hs1_hi(), c.hs1_lo(),
+                c.act(d.out), vo.slot_elems, rows, vi.Cp, d.kh == 2 ? 1 : 0, nsl, am, c.hs1_hi(),
+                c.planes == 1 ? nullptr : c.hs1_lo(),
                 vo.slot_elems, c.hsbits() + c.bits_act(d.in0), c.hsbits() + c.bits_node(ni), 0);
           else
             affine_fwd_kernel<false><<<grid, 256, 0, st>>>(
@@ -887,6 +895,7 @@ static int backward(const Ctx& c, int K) {
           h.Gh = c.hs1_hi(); h.Gl = c.hs1_lo(); h.G_slot = vo.slot_elems; h.Ng = vo.Cp; h.g_bits = c.hsbits() + eg;
           h.Ih = c.hs2_hi(); h.Il = c.hs2_lo(); h.i_bits = c.hsbits() + ea;
           h.partial = scratch; h.nsplit = n.nsplit; h.nslots = ns; h.slot0 = s0; h.m_per_split = n.m_per_split;
+          h.planes = c.planes;
           {
             ProfScope prof(1, conv_flops(g, vi.C) * ns, st);
             if (hs_launch_wgrad(h, st)) return fail(CURV_ERR_CUDA, "half-split wgrad GEMM launch failed");
@@ -932,6 +941,7 @@ static int backward(const Ctx& c, int K) {
           h.W_img = reinterpret_cast<const __half*>(c.ws + n.wtimg_off);
           h.w_bits = c.hsbits() + c.bits_node(nidx);
           h.out = c.grad(d.in0); h.out_slot = vi.slot_elems; h.slot0 = s0; h.accumulate = ginit[d.in0];
+          h.planes = c.planes;
           if (!ginit[d.in0]) {  // first writer: track the absmax of the data gradient for its consumers
             hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns);
             h.out_bits = c.hsbits() + c.bits_grad(d.in0);
@@ -997,7 +1007,7 @@ static int backward(const Ctx& c, int K) {
             vi.slot_elems, c.ws + n.coef_off, c.ws + n.aux_off, vi.tan ? c.grad(d.in0) : nullptr,
             vi.slot_elems, vi.tan ? 1 : 0, scratch, want_partial, rows, vi.Cp, n.rows_per_cta, s0, ns,
             rop ? 1 : 0, ginit[d.in0], d.kh == 2 ? 1 : 0, amax, planes ? c.hs1_hi() : nullptr,
-            planes ? c.hs1_lo() : nullptr, vi.slot_elems, c.hsbits() + c.bits_grad(d.out),
+            (planes && c.planes == 2) ? c.hs1_lo() : nullptr, vi.slot_elems, c.hsbits() + c.bits_grad(d.out),
             c.hsbits() + c.bits_node(ni), planes ? 0 : 1);
         LAUNCH_CHECK();
         planes_of = planes ? d.in0 : -1;
@@ -1145,6 +1155,7 @@ static int matmat_batch_impl(curv_program* P, int kind, int loss, const void* co
   std::vector<char> hs_valid;
   if (g_tc_mode && !(g_tc_disable & 32) && !c.rop && P->hs1_elems > 0 && hs_ready() > 0) {
     c.hs = true;
+    c.planes = (P->hessian & 4) ? 1 : 2;
     hs_valid.assign((size_t)P->hsbits_count, 0);
     c.hs_valid = &hs_valid;
     CHECK_CUDA(cudaMemsetAsync(c.hsbits(), 0, (size_t)P->hsbits_count * sizeof(uint32_t), c.st));

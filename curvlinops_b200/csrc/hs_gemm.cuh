@@ -30,6 +30,7 @@
 // planning code.  The `debug` fields of the argument structs are timing experiments (results invalid).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -87,7 +88,17 @@ __device__ __forceinline__ void hs_split8(const float4& v0, const float4& v1, fl
   lo = make_uint4(hs_pack2(l[0], l[1]), hs_pack2(l[2], l[3]), hs_pack2(l[4], l[5]), hs_pack2(l[6], l[7]));
 }
 
-// x [slot][n] fp32 -> hi/lo [slot][n] fp16 (n = 8*n8), scale from bits[slot].  grid.y = slots
+// bf16 mode (one plane, one MMA per product; BASELINE bf16 configs): 8 consecutive floats -> one 16-byte chunk of
+// the single bf16 plane (stored through the __half* plane pointers: the planes are raw 16-bit words to the copy paths)
+__device__ __forceinline__ uint4 hs_bf16x8(const float4& v0, const float4& v1, float s) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v0.x * s, v0.y * s), b = __floats2bfloat162_rn(v0.z * s, v0.w * s);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(v1.x * s, v1.y * s), d = __floats2bfloat162_rn(v1.z * s, v1.w * s);
+  return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                    *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+}
+
+// x [slot][n] fp32 -> hi/lo [slot][n] fp16 (n = 8*n8), scale from bits[slot].  grid.y = slots.
+// lo == nullptr: bf16 mode, only the (bf16) hi plane is written
 __global__ void __launch_bounds__(256) hs_split_kernel(const float* __restrict__ x, long long slot_stride,
                                                        __half* __restrict__ hi, __half* __restrict__ lo,
                                                        long long out_slot_stride, long long n8,
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(256) hs_split_kernel(const float* __restrict__
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 v0 = __ldg(p + 2 * i), v1 = __ldg(p + 2 * i + 1);
+    if (lo == nullptr) { ph[i] = hs_bf16x8(v0, v1, s); continue; }
     uint4 h, l;
     hs_split8(v0, v1, s, h, l);
     ph[i] = h;
@@ -109,9 +121,10 @@ __global__ void __launch_bounds__(256) hs_split_kernel(const float* __restrict__
 
 // Weight image for gather_gemm_hs: src [N][Kd] fp32 row-major (slots along grid.y, scale bits[slot]).
 //   block (tn, kc) = [hi plane: BN rows x 128 B (64 fp16), 128B-swizzled][lo plane], blocks ordered tn-major.
+//   planes == 1 (bf16 mode): blocks hold the single bf16 plane only.
 __global__ void hs_pack_image_kernel(const float* __restrict__ src, long long src_slot,
                                      __half* __restrict__ dst, long long dst_slot, int N, int Kd, int BN,
-                                     int tiles_n, int nchunks, const uint32_t* __restrict__ bits) {
+                                     int tiles_n, int nchunks, const uint32_t* __restrict__ bits, int planes) {
   src += blockIdx.y * src_slot;
   dst += blockIdx.y * dst_slot;
   const float s = hs_pow2(hs_shift_from_bits(bits[blockIdx.y]));
@@ -130,10 +143,11 @@ __global__ void hs_pack_image_kernel(const float* __restrict__ src, long long sr
       v0 = __ldg(q);
       if (k + 4 < Kd) v1 = __ldg(q + 1);
     }
+    __half* blk = dst + ((long long)tn * nchunks + kc) * (planes * BN * HS_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 1;  // in halves
+    if (planes == 1) { *reinterpret_cast<uint4*>(blk + o) = hs_bf16x8(v0, v1, s); continue; }
     uint4 h, l;
     hs_split8(v0, v1, s, h, l);
-    __half* blk = dst + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
-    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 1;  // in halves
     *reinterpret_cast<uint4*>(blk + o) = h;
     *reinterpret_cast<uint4*>(blk + BN * HS_BK + o) = l;
   }
@@ -174,8 +188,10 @@ __device__ __forceinline__ void hs_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       : "memory");
 }
 // instruction descriptor: D = f32, A = B = f16, M = 128, N; majors: 0 = K-major, 1 = MN-major
-__host__ __device__ constexpr uint32_t hs_idesc(int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// bf16 != 0: A = B = bf16 (format code 1 in bits 7-9 / 10-12)
+__host__ __device__ constexpr uint32_t hs_idesc(int N, int a_mn_major, int b_mn_major, int bf16 = 0) {
+  return (1u << 4) | ((uint32_t)(bf16 ? 1 : 0) << 7) | ((uint32_t)(bf16 ? 1 : 0) << 10) |
+         ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 // MN-major 16-bit operand, SWIZZLE_128B: atoms of 8 reduction rows x 128 bytes (64 MN-contiguous fp16),
@@ -234,6 +250,7 @@ struct HsGatherArgs {
   // pixel is (w, h) = (tma_w0 + x*tma_sw, tma_h0 + y*tma_sh) for destination / class coordinates (x, y);
   // the filter tap enters as the instruction's im2col offsets (tma_offw/h; per class in parity mode).
   int use_tma;
+  int planes;  // 2 (0 = default): fp16 hi/lo planes; 1: one bf16 plane (Al unused), one MMA per product
   int tma_w0[4], tma_h0[4], tma_sw, tma_sh;
   unsigned char tma_offw[4][HS_PAR_TAPS], tma_offh[4][HS_PAR_TAPS];
   alignas(64) CUtensorMap tmA[4][2];  // [class][plane]
@@ -256,9 +273,20 @@ struct HsTile { int slot, m0, tn, cls, T; };  // T = K stages per segment
 // cross terms are 2^-10 of the result: their chain may span a whole segment (drained once), and keeping them out
 // of the main accumulator cuts the main chain to one MMA per K step - chunks can be 3x longer for the same bias,
 // and draining a chunk (64 KB of TMEM reads that compete with the MMAs) happens 3x less often.
-template <int BN>
+// PL = operand planes per tensor: 2 = fp16 hi/lo (half-split, three MMAs per product), 1 = one bf16 plane (bf16
+// arithmetic: ONE MMA per product, no cross accumulators; the freed shared memory deepens the stage ring)
+template <int BN, int PL>
+struct HsCfg {
+  static constexpr int A_BYTES = TC_BM * 128;  // per plane
+  static constexpr int B_BYTES = BN * 128;     // per plane
+  static constexpr int STAGE_BYTES = PL * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = PL == 2 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 7);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+};
+
+template <int BN, int PL>
 struct HsSmem {
-  using Cfg = TcCfg<BN>;
+  using Cfg = HsCfg<BN, PL>;
   static constexpr int NB = 512 / BN;
   static constexpr int NM = NB - 2;  // main ring
   uint32_t base, bar_base;
@@ -274,17 +302,17 @@ struct HsSmem {
   __device__ uint32_t cempty(int a) const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NM + 2 + a); }
   __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * Cfg::STAGES + 2 * NM + 4); }
   __device__ uint32_t stageA(int s) const { return base + s * Cfg::STAGE_BYTES; }
-  __device__ uint32_t stageB(int s) const { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; }
+  __device__ uint32_t stageB(int s) const { return base + s * Cfg::STAGE_BYTES + PL * Cfg::A_BYTES; }
 };
-static_assert(8 * (2 * 4 + 2 * 6 + 4 + 1) <= 256, "barrier block of HsSmem must fit the 256 bytes reserved by TcCfg");
+static_assert(8 * (2 * 7 + 2 * 6 + 4 + 1) <= 512, "barrier block of HsSmem must fit the 512 bytes reserved by HsCfg");
 
-template <int BN>
-__device__ __forceinline__ uint32_t hs_prologue(const HsSmem<BN>& S, uint8_t* raw, int full_count) {
-  using Cfg = TcCfg<BN>;
+template <int BN, int PL>
+__device__ __forceinline__ uint32_t hs_prologue(const HsSmem<BN, PL>& S, uint8_t* raw, int full_count) {
+  using Cfg = HsCfg<BN, PL>;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(S.full(s), full_count); mbar_init(S.empty(s), 1); }
-    for (int a = 0; a < HsSmem<BN>::NM; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
+    for (int a = 0; a < HsSmem<BN, PL>::NM; ++a) { mbar_init(S.tfull(a), 1); mbar_init(S.tempty(a), 256); }
     for (int a = 0; a < 2; ++a) { mbar_init(S.cfull(a), 1); mbar_init(S.cempty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -316,13 +344,13 @@ __device__ __forceinline__ void hs_tma_load_im2col(uint32_t dst, const CUtensorM
       : "memory");
 }
 
-template <int BN>
+template <int BN, int PL>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_constant__ HsGatherArgs p, int nslots) {
-  using Cfg = TcCfg<BN>;  // same stage bytes: 128 rows x 128 B per plane
+  using Cfg = HsCfg<BN, PL>;  // stage: 128 rows x 128 B per plane of A, BN rows x 128 B per plane of W
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NM = HsSmem<BN>::NM;  // main accumulator ring (TMEM buffers 2..), buffers 0/1 = cross terms
+  constexpr int NM = HsSmem<BN, PL>::NM;  // main accumulator ring (TMEM buffers 2..), buffers 0/1 = cross terms
   extern __shared__ uint8_t smem_raw[];
-  const HsSmem<BN> S(smem_raw);
+  const HsSmem<BN, PL> S(smem_raw);
   const Geom& g = p.g;
   const HsParity& par = p.par;
   const bool parity = par.nclass > 0;
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
   __shared__ unsigned int s_slotmax[40];  // per-CTA absmax of the written result per slot (out_bits)
   if (threadIdx.x < 40) s_slotmax[threadIdx.x] = 0u;
   // full barrier: TMA mode = the single expect_tx arrival of the issuing thread
-  const uint32_t tmem_base = hs_prologue<BN>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
+  const uint32_t tmem_base = hs_prologue<BN, PL>(S, smem_raw, p.use_tma == 1 ? 1 : TC_PRODUCERS + 1);
 
   auto decode_tile = [&](int tile, HsTile& t) {
     const int si = tile % nslots;
@@ -367,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
     if (warp == 5 && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = 2 * Cfg::A_BYTES + 2 * Cfg::B_BYTES;
+      const uint32_t bytes = PL * (Cfg::A_BYTES + Cfg::B_BYTES);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         HsTile t;
         decode_tile(tile, t);
@@ -403,12 +431,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
               const uint32_t sA = S.stageA(stage);
               const unsigned short ow = p.tma_offw[t.cls][ti], oh = p.tma_offh[t.cls][ti];
               hs_tma_load_im2col(sA, &p.tmA[t.cls][0], cb, w0, h0, n0, ow, oh, S.full(stage));
-              hs_tma_load_im2col(sA + Cfg::A_BYTES, &p.tmA[t.cls][1], cb, w0, h0, n0, ow, oh, S.full(stage));
-              const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (2 * BN * HS_BK);
+              if (PL == 2)
+                hs_tma_load_im2col(sA + Cfg::A_BYTES, &p.tmA[t.cls][1], cb, w0, h0, n0, ow, oh, S.full(stage));
+              const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (PL * BN * HS_BK);
               asm volatile(
                   "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                       S.stageB(stage)),
-                  "l"(wsrc), "r"((uint32_t)(2 * Cfg::B_BYTES)), "r"(S.full(stage))
+                  "l"(wsrc), "r"((uint32_t)(PL * Cfg::B_BYTES)), "r"(S.full(stage))
                   : "memory");
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -461,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
       }
       // hybrid mode (use_tma == 2): the hi plane of the stage comes by TMA im2col (thread 0), only the lo plane
       // by cp.async: the two paths have separate throughput limits (TMA row rate / LSU miss path)
-      const bool hybrid = p.use_tma == 2;
+      const bool hybrid = PL == 2 && p.use_tma == 2;
       int tw0 = 0, th0 = 0, tb = 0;
       if (hybrid && pt == 0) {
         int x, y;
@@ -505,8 +534,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
           mbar_wait(S.empty(stage), phase ^ 1);
           const uint32_t sA = S.stageA(stage);
           if (pt == 0) {
-            const uint32_t bytes = 2 * Cfg::B_BYTES;
-            const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (2 * BN * HS_BK);
+            const uint32_t bytes = PL * Cfg::B_BYTES;
+            const __half* wsrc = Wimg + ((long long)t.tn * nchunks + wblk) * (PL * BN * HS_BK);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.full(stage)),
                          "r"(bytes + (hybrid ? (uint32_t)Cfg::A_BYTES : 0u))
                          : "memory");
@@ -535,7 +564,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
               const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
               const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
               if (!hybrid) hs_cp16(o, Ah + eo, ok);
-              hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
+              if (PL == 2) hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
             }
           } else {  // strided dgrad, generic: source pixel = (dest + pad - tap) / stride when divisible
 #pragma unroll
@@ -547,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
               const long long eo = ok ? ((long long)(rowoff[i] + hs * g.Ws + ws) * g.Cs + c) : 0;
               const uint32_t o = sA + a_off + (uint32_t)(i * 4096);
               hs_cp16(o, Ah + eo, ok);
-              hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
+              if (PL == 2) hs_cp16(o + Cfg::A_BYTES, Al + eo, ok);
             }
           }
           hs_cp_arrive(S.full(stage));
@@ -562,7 +591,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
     // The whole warp runs the (uniform) loop and waits on the barriers; one elected lane issues the MMAs and
     // the commits of a stage in one predicated block.
     {
-      constexpr uint32_t idesc = hs_idesc(BN, 0, 0);
+      constexpr uint32_t idesc = hs_idesc(BN, 0, 0, PL == 1);
       int stage = 0, acc = 0, xb = 0;
       uint32_t phase = 0, acc_phase = 0, xb_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -570,7 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
         decode_tile(tile, t);
         const int nseg = num_segments(t.slot);
         for (int seg = 0; seg < nseg && t.T > 0; ++seg) {
-          mbar_wait(S.cempty(xb), xb_phase ^ 1);  // cross accumulator of this segment drained
+          if (PL == 2) mbar_wait(S.cempty(xb), xb_phase ^ 1);  // cross accumulator of this segment drained
           const uint32_t d_cross = tmem_base + (uint32_t)(xb * BN);
           for (int t0 = 0; t0 < t.T; t0 += p.flush) {  // one chunk of the main accumulation
             mbar_wait(S.tempty(acc), acc_phase ^ 1);
@@ -590,14 +619,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
                   for (int ks = 0; ks < HS_BK / 16; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // +32 bytes inside the 128-byte row
                     hs_mma_f16(d_main, dAh + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-                    hs_mma_f16(d_cross, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
-                    hs_mma_f16(d_cross, dAh + adv, dBl + adv, idesc, 1u);
+                    if (PL == 2) {
+                      hs_mma_f16(d_cross, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
+                      hs_mma_f16(d_cross, dAh + adv, dBl + adv, idesc, 1u);
+                    }
                   }
                 }
                 tc_commit(S.empty(stage));                       // frees the smem stage when these MMAs retire
                 if (it + 1 == T) {
                   tc_commit(S.tfull(acc));                       // main chunk complete -> epilogue
-                  if (t0 + T == t.T) tc_commit(S.cfull(xb));     // segment complete -> cross terms to the epilogue
+                  if (PL == 2 && t0 + T == t.T) tc_commit(S.cfull(xb));  // segment complete -> cross terms to the epilogue
                 }
               }
               __syncwarp();
@@ -648,10 +679,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_hs(const __grid_con
           mbar_arrive(S.tempty(acc));
           if (++acc == NM) { acc = 0; acc_phase ^= 1; }
         }
-        mbar_wait(S.cfull(xb), xb_phase);
-        tc_fence_after();
-        drain(xb, inv);
-        mbar_arrive(S.cempty(xb));
+        if (PL == 2) {
+          mbar_wait(S.cfull(xb), xb_phase);
+          tc_fence_after();
+          drain(xb, inv);
+          mbar_arrive(S.cempty(xb));
+        }
         if (++xb == 2) { xb = 0; xb_phase ^= 1; }
       }
       const float* bias = (t.slot == 0) ? p.bias
@@ -732,18 +765,24 @@ struct HsStackArgs {
   int slot_lo, nslots;     // slots slot_lo .. slot_lo + nslots - 1
   int accumulate;
   int flush;
+  int planes;              // 2 (0 = default) or 1 (bf16), see HsGatherArgs
 };
 
 constexpr int HSN_THREADS = 20 * 32;  // 20 warps: 65536 / 640 leaves 96 registers per thread for the epilogue
 constexpr int HSN_PRODUCERS = 96;
-constexpr int HSN_STAGES = 2;
 constexpr int HSN_A_BYTES = TC_BM * 128;            // per plane
 constexpr int HSN_B_BYTES = 256 * 128;              // per plane (up to 256 stacked rows)
-constexpr int HSN_STAGE_BYTES = 2 * HSN_A_BYTES + 2 * HSN_B_BYTES;  // 96 KB
-constexpr int HSN_SMEM_BYTES = HSN_STAGES * HSN_STAGE_BYTES + 1024 + 256;
+template <int PL>
+struct HsnCfg {  // PL = 2: 2 stages of 96 KB; PL = 1 (bf16): 4 stages of 48 KB
+  static constexpr int STAGES = PL == 2 ? 2 : 4;
+  static constexpr int STAGE_BYTES = PL * (HSN_A_BYTES + HSN_B_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
-template <int BN>
+template <int BN, int PL>
 __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsStackArgs p) {
+  constexpr int HSN_STAGES = HsnCfg<PL>::STAGES;
+  constexpr int HSN_STAGE_BYTES = HsnCfg<PL>::STAGE_BYTES;
   constexpr int G = 256 / BN;  // slots per group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -822,26 +861,27 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
         }
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sA = sbase + stage * HSN_STAGE_BYTES;
-        const uint32_t sB = sA + 2 * HSN_A_BYTES;
+        const uint32_t sB = sA + PL * HSN_A_BYTES;
         if (pt == 0) {  // weight blocks of the group's slots, stacked along N: hi planes, then lo planes
           const uint32_t blk = (uint32_t)BN * 128u;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(stage)),
-                       "r"(2u * blk * (uint32_t)cnt)
+                       "r"((uint32_t)PL * blk * (uint32_t)cnt)
                        : "memory");
           for (int j = 0; j < cnt; ++j) {
             const int s = s_first + j;
             const __half* Wimg = (s == 0) ? p.W_img : p.Wt_img + (long long)(s - 1) * p.Wt_img_slot;
-            const __half* wsrc = Wimg + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+            const __half* wsrc = Wimg + ((long long)tn * nchunks + kc) * (PL * BN * HS_BK);
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                     sB + (uint32_t)j * blk),
                 "l"(wsrc), "r"(blk), "r"(full_bar(stage))
                 : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    sB + (uint32_t)HSN_B_BYTES + (uint32_t)j * blk),
-                "l"(wsrc + BN * HS_BK), "r"(blk), "r"(full_bar(stage))
-                : "memory");
+            if (PL == 2)
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      sB + (uint32_t)HSN_B_BYTES + (uint32_t)j * blk),
+                  "l"(wsrc + BN * HS_BK), "r"(blk), "r"(full_bar(stage))
+                  : "memory");
           }
         }
         const int tapoff = (dy * g.Ws + dx) * g.Cs + c;
@@ -854,7 +894,7 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
           const long long eo = ok ? (long long)(rowoff[i] + tapoff) : 0;
           const uint32_t o = sA + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((a_c ^ (r & 7)) << 4));
           hs_cp16(o, p.Ah + eo, ok);
-          hs_cp16(o + HSN_A_BYTES, p.Al + eo, ok);
+          if (PL == 2) hs_cp16(o + HSN_A_BYTES, p.Al + eo, ok);
         }
         hs_cp_arrive(full_bar(stage));
         if (++stage == HSN_STAGES) { stage = 0; phase ^= 1; }
@@ -870,8 +910,8 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
       int grp, m0, tn;
       decode_tile(tile, grp, m0, tn);
       const int cnt = min(G, p.nslots - grp * G);
-      const uint32_t idesc = hs_idesc(cnt * BN, 0, 0);
-      mbar_wait(cempty, cphase ^ 1);  // cross accumulator of the previous tile drained
+      const uint32_t idesc = hs_idesc(cnt * BN, 0, 0, PL == 1);
+      if (PL == 2) mbar_wait(cempty, cphase ^ 1);  // cross accumulator of the previous tile drained
       for (int t0 = 0; t0 < nchunks; t0 += p.flush) {
         mbar_wait(tempty, tphase ^ 1);  // main accumulator of the previous chunk drained
         tc_fence_after();
@@ -879,7 +919,7 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
         for (int it = 0; it < T; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sA = sbase + stage * HSN_STAGE_BYTES, sB = sA + 2 * HSN_A_BYTES;
+          const uint32_t sA = sbase + stage * HSN_STAGE_BYTES, sB = sA + PL * HSN_A_BYTES;
           const uint64_t dAh = make_kmajor_sw128_desc(sA), dAl = make_kmajor_sw128_desc(sA + HSN_A_BYTES);
           const uint64_t dBh = make_kmajor_sw128_desc(sB), dBl = make_kmajor_sw128_desc(sB + HSN_B_BYTES);
           if (hs_elect_one()) {
@@ -888,13 +928,15 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
             for (int ks = 0; ks < HS_BK / 16; ++ks) {
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);
               hs_mma_f16(tmem_base, dAh + adv, dBh + adv, idesc, (it | ks) != 0 ? 1u : 0u);
-              hs_mma_f16(tmem_base + 256u, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
-              hs_mma_f16(tmem_base + 256u, dAh + adv, dBl + adv, idesc, 1u);
+              if (PL == 2) {
+                hs_mma_f16(tmem_base + 256u, dAl + adv, dBh + adv, idesc, (t0 | it | ks) != 0 ? 1u : 0u);
+                hs_mma_f16(tmem_base + 256u, dAh + adv, dBl + adv, idesc, 1u);
+              }
             }
             tc_commit(empty_bar(stage));
             if (it + 1 == T) {
               tc_commit(tfull);
-              if (t0 + T == nchunks) tc_commit(cfull);
+              if (PL == 2 && t0 + T == nchunks) tc_commit(cfull);
             }
           }
           __syncwarp();
@@ -941,10 +983,12 @@ __global__ void __launch_bounds__(HSN_THREADS, 1) gather_gemm_hs_stack(const HsS
         mbar_arrive(tempty);
         tphase ^= 1;
       }
-      mbar_wait(cfull, cphase);
-      tc_fence_after();
-      drain(256u);
-      mbar_arrive(cempty);
+      if (PL == 2) {
+        mbar_wait(cfull, cphase);
+        tc_fence_after();
+        drain(256u);
+        mbar_arrive(cempty);
+      }
       cphase ^= 1;
       if (!active) continue;
       const float* bias = (slot == 0) ? p.bias : (p.bias_t ? p.bias_t + (long long)(slot - 1) * p.bias_slot : nullptr);
@@ -1052,6 +1096,7 @@ struct HsWgradArgs {
   // TMA path of the G operand (set by hs_launch_wgrad): 3-d tiled maps (Ng, M, slots) of the two planes, box
   // (64 channels, 16 pixels, all slots) with SWIZZLE_128B = per slot one MN atom x two K atoms of the stage.
   int use_tma;
+  int planes;              // 2 (0 = default) or 1 (bf16, Gl / Il unused), see HsGatherArgs
   alignas(64) CUtensorMap tmGh;
   alignas(64) CUtensorMap tmGl;
 };
@@ -1059,10 +1104,13 @@ struct HsWgradArgs {
 constexpr int HSW_ROWS = 16;
 constexpr int HSW_A_BYTES = 128 * HSW_ROWS * 2;   // 4 KB per plane
 constexpr int HSW_B_BYTES = 256 * HSW_ROWS * 2;   // 8 KB per plane and slot group
-constexpr int HSW_STAGE_BYTES = 2 * HSW_A_BYTES + 4 * HSW_B_BYTES;  // 40 KB
-constexpr int HSW_STAGES = 5;
+template <int PL>
+struct HswCfg {  // PL = 2: 5 stages of 40 KB; PL = 1 (bf16): 7 stages of 20 KB (one gather warp per ring slot: warps 6-12)
+  static constexpr int STAGE_BYTES = PL * (HSW_A_BYTES + 2 * HSW_B_BYTES);
+  static constexpr int STAGES = PL == 2 ? 5 : 7;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 constexpr int HSW_FLUSH = 256;
-constexpr int HSW_SMEM_BYTES = HSW_STAGES * HSW_STAGE_BYTES + 1024 + 256;
 
 // 3-d tiled TMA load global -> shared, completion on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void hs_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -1073,7 +1121,10 @@ __device__ __forceinline__ void hs_tma_load_3d(uint32_t dst, const CUtensorMap* 
       : "memory");
 }
 
+template <int PL>
 __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_constant__ HsWgradArgs p) {
+  constexpr int HSW_STAGES = HswCfg<PL>::STAGES;
+  constexpr int HSW_STAGE_BYTES = HswCfg<PL>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = sbase + HSW_STAGES * HSW_STAGE_BYTES;
@@ -1135,7 +1186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t bytes = (uint32_t)NS * 2u * 2048u;
+        const uint32_t bytes = (uint32_t)NS * (uint32_t)PL * 2048u;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
           int split, i0, j0;
           decode_tile(tile, split, i0, j0);
@@ -1143,7 +1194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
           const int nst = stages_of(split);
           for (int st = 0; st < nst; ++st) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t sB = sbase + stage * HSW_STAGE_BYTES + 2 * HSW_A_BYTES;
+            const uint32_t sB = sbase + stage * HSW_STAGE_BYTES + PL * HSW_A_BYTES;
             if (p.debug & 1) {
               mbar_arrive(full_bar(stage));
             } else {
@@ -1151,7 +1202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
                            "r"(bytes)
                            : "memory");
               hs_tma_load_3d(sB, &p.tmGh, j0, mb + st * HSW_ROWS, 0, full_bar(stage));
-              hs_tma_load_3d(sB + 2 * HSW_B_BYTES, &p.tmGl, j0, mb + st * HSW_ROWS, 0, full_bar(stage));
+              if (PL == 2) hs_tma_load_3d(sB + 2 * HSW_B_BYTES, &p.tmGl, j0, mb + st * HSW_ROWS, 0, full_bar(stage));
             }
             if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -1199,7 +1250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
             for (int c = 0; c < 8; ++c) {
               const uint32_t o = sA + (uint32_t)((c ^ (ir & 7)) << 4);
               hs_cp16(o, p.Ih + eo + (ok ? c * 8 : 0), ok);
-              hs_cp16(o + HSW_A_BYTES, p.Il + eo + (ok ? c * 8 : 0), ok);
+              if (PL == 2) hs_cp16(o + HSW_A_BYTES, p.Il + eo + (ok ? c * 8 : 0), ok);
             }
           } else {
 #pragma unroll 1
@@ -1213,7 +1264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
               const long long eo = ok ? (((long long)bimg * g.Hs + hs) * g.Ws + ws) * g.Cs + ic : 0;
               const uint32_t o = sA + (uint32_t)((c ^ (ir & 7)) << 4);
               hs_cp16(o, p.Ih + eo, ok);
-              hs_cp16(o + HSW_A_BYTES, p.Il + eo, ok);
+              if (PL == 2) hs_cp16(o + HSW_A_BYTES, p.Il + eo, ok);
             }
           }
           hs_cp_arrive(full_bar(stage));
@@ -1264,17 +1315,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
         const long long eoG = okG ? (long long)mg * p.Ng + ch : 0;
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
-        const uint32_t sB = sA + 2 * HSW_A_BYTES;
+        const uint32_t sB = sA + PL * HSW_A_BYTES;
         if (p.debug & 1) {
           mbar_arrive(full_bar(stage));
           if (++stage == HSW_STAGES) { stage = 0; phase ^= 1; }
           continue;
         }
         hs_cp16(sA + offI, p.Ih + eoI, okI);
-        hs_cp16(sA + HSW_A_BYTES + offI, p.Il + eoI, okI);
+        if (PL == 2) hs_cp16(sA + HSW_A_BYTES + offI, p.Il + eoI, okI);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-          if (s < NS) {
+          if (s < NS && (PL == 2 || gp == 0)) {
             // slot s: group s >> 2, MN atom s & 3 inside the group's plane
             const uint32_t o = sB + (uint32_t)(gp * 2 * HSW_B_BYTES + s * 2048) + offG;
             hs_cp16(o, Gplane + (long long)s * p.G_slot + eoG, okG);
@@ -1290,8 +1341,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
     {
       const int n0 = NS >= 4 ? 256 : 64 * NS;            // N of slot group 0
       const int n1 = NS > 4 ? 64 * (NS - 4) : 0;         // N of slot group 1
-      const uint32_t idesc0 = hs_idesc(n0, 1, 1);
-      const uint32_t idesc1 = hs_idesc(n1 > 0 ? n1 : 64, 1, 1);
+      const uint32_t idesc0 = hs_idesc(n0, 1, 1, PL == 1);
+      const uint32_t idesc1 = hs_idesc(n1 > 0 ? n1 : 64, 1, 1, PL == 1);
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1306,7 +1357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
-            const uint32_t sB = sA + 2 * HSW_A_BYTES;
+            const uint32_t sB = sA + PL * HSW_A_BYTES;
             const uint64_t dAh = hs_mnmajor_desc(sA, 2048, 1024), dAl = hs_mnmajor_desc(sA + HSW_A_BYTES, 2048, 1024);
             // the two slot groups accumulate into independent TMEM regions: interleave them so that consecutive
             // MMAs never depend on each other's accumulator
@@ -1317,12 +1368,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
             if (hs_elect_one()) {
               fence_async_proxy();  // cp.async (generic proxy) writes of the gathered tile -> tensor-core reads
               if (!(p.debug & 2)) {
-                hs_mma_f16(tmem_base, dAl, dBh0, idesc0, accf);
-                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAl, dBh1, idesc1, accf);
-                hs_mma_f16(tmem_base, dAh, dBl0, idesc0, 1u);
-                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBl1, idesc1, 1u);
-                hs_mma_f16(tmem_base, dAh, dBh0, idesc0, 1u);
-                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBh1, idesc1, 1u);
+                if (PL == 2) {
+                  hs_mma_f16(tmem_base, dAl, dBh0, idesc0, accf);
+                  if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAl, dBh1, idesc1, accf);
+                  hs_mma_f16(tmem_base, dAh, dBl0, idesc0, 1u);
+                  if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBl1, idesc1, 1u);
+                }
+                hs_mma_f16(tmem_base, dAh, dBh0, idesc0, PL == 2 ? 1u : accf);
+                if (n1 > 0) hs_mma_f16(tmem_base + 256u, dAh, dBh1, idesc1, PL == 2 ? 1u : accf);
               }
               tc_commit(empty_bar(stage));
               if (st + 1 == cend) tc_commit(tfull_bar);
@@ -1396,9 +1449,9 @@ static inline bool hs_gather_shape_ok(const Geom& g) {
 }
 static inline bool hs_wgrad_shape_ok(const Geom& g, int Ng) { return g.Cs % 8 == 0 && Ng % 8 == 0; }
 // size (halves) of the weight image of an [N][Kd] matrix
-static inline long long hs_image_halves(int Nd, int Kd) {
+static inline long long hs_image_halves(int Nd, int Kd, int planes = 2) {
   const int BN = tc_bn(Nd);
-  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, HS_BK) * (2 * BN * HS_BK);
+  return (long long)ceil_div(Nd, BN) * ceil_div(Kd, HS_BK) * (planes * BN * HS_BK);
 }
 
 static int hs_ready() {
@@ -1406,16 +1459,20 @@ static int hs_ready() {
   if (ready == -1) {
     ready = 0;
     if (tc_sm_count() > 0) {
-      bool ok = cudaFuncSetAttribute(gather_gemm_hs<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TcCfg<128>::SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(gather_gemm_hs<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      TcCfg<64>::SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(wgrad_gemm_hs, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      HSW_SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(gather_gemm_hs_stack<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      HSN_SMEM_BYTES) == cudaSuccess;
-      ok = ok && cudaFuncSetAttribute(gather_gemm_hs_stack<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      HSN_SMEM_BYTES) == cudaSuccess;
+      bool ok = true;
+      auto attr = [&](auto* fn, int bytes) {
+        ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      };
+      attr(gather_gemm_hs<128, 2>, HsCfg<128, 2>::SMEM_BYTES);
+      attr(gather_gemm_hs<64, 2>, HsCfg<64, 2>::SMEM_BYTES);
+      attr(gather_gemm_hs<128, 1>, HsCfg<128, 1>::SMEM_BYTES);
+      attr(gather_gemm_hs<64, 1>, HsCfg<64, 1>::SMEM_BYTES);
+      attr(wgrad_gemm_hs<2>, HswCfg<2>::SMEM_BYTES);
+      attr(wgrad_gemm_hs<1>, HswCfg<1>::SMEM_BYTES);
+      attr(gather_gemm_hs_stack<64, 2>, HsnCfg<2>::SMEM_BYTES);
+      attr(gather_gemm_hs_stack<128, 2>, HsnCfg<2>::SMEM_BYTES);
+      attr(gather_gemm_hs_stack<64, 1>, HsnCfg<1>::SMEM_BYTES);
+      attr(gather_gemm_hs_stack<128, 1>, HsnCfg<1>::SMEM_BYTES);
       ready = ok ? 1 : 0;
     }
   }
@@ -1445,12 +1502,12 @@ static inline int hs_launch_split(const float* x, long long slot_stride, long lo
 // pack [N][Kd] fp32 (nslots matrices src_slot apart, scales bits[slot]) into weight images
 static inline int hs_launch_pack_image(const float* src, long long src_slot, __half* dst, long long dst_slot,
                                        int N, int Nd, int Kd, int nslots, const uint32_t* bits,
-                                       cudaStream_t st) {
+                                       cudaStream_t st, int planes = 2) {
   const int BN = tc_bn(Nd);
   const int tiles_n = ceil_div(Nd, BN), nchunks = ceil_div(Kd, HS_BK);
   const long long total = (long long)tiles_n * nchunks * BN * 8;
   hs_pack_image_kernel<<<dim3(hs_grid(total), nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
-                                                                    tiles_n, nchunks, bits);
+                                                                    tiles_n, nchunks, bits, planes);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -1476,7 +1533,7 @@ static inline hs_encode_im2col_fn hs_encode_im2col() {
 // im2col map over an fp16 plane [images][H][W][C]: box = 64 channels x 128 pixels, base pixels inside
 // [lower, dim + upper) traversed with the given strides
 static inline bool hs_make_im2col_map(CUtensorMap* map, const __half* base, int C, int W, int H, long long images,
-                                      int lw, int lh, int uw, int uh, int sw, int sh) {
+                                      int lw, int lh, int uw, int uh, int sw, int sh, bool bf16 = false) {
   hs_encode_im2col_fn enc = hs_encode_im2col();
   if (!enc) return false;
   if (lw < -128 || lw > 127 || lh < -128 || lh > 127 || uw < -128 || uw > 127 || uh < -128 || uh > 127) return false;
@@ -1485,7 +1542,8 @@ static inline bool hs_make_im2col_map(CUtensorMap* map, const __half* base, int 
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   const int lower[2] = {lw, lh}, upper[2] = {uw, uh};
   const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, lower, upper, 64,
+  return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+             const_cast<__half*>(base), dims, strides, lower, upper, 64,
              TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1496,6 +1554,7 @@ static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
   a.use_tma = 0;
   if (g.Cs % HS_BK != 0 || a.A_slot != (long long)g.B * g.Hs * g.Ws * g.Cs) return false;
   const long long images = (long long)a_plane_slots * g.B;
+  const int npl = a.planes == 1 ? 1 : 2;
   if (a.par.nclass > 0) {
     for (int c = 0; c < a.par.nclass; ++c) {
       if (a.par.ntap[c] == 0) continue;  // class without taps: never loaded
@@ -1507,8 +1566,9 @@ static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
       }
       a.tma_w0[c] = lw; a.tma_h0[c] = lh;
       const int uw = a.par.Wc[c] - g.Ws + lw, uh = a.par.Hc[c] - g.Hs + lh;
-      for (int pl = 0; pl < 2; ++pl)
-        if (!hs_make_im2col_map(&a.tmA[c][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, lw, lh, uw, uh, 1, 1))
+      for (int pl = 0; pl < npl; ++pl)
+        if (!hs_make_im2col_map(&a.tmA[c][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, lw, lh, uw, uh, 1, 1,
+                                npl == 1))
           return false;
     }
     a.tma_sw = 1; a.tma_sh = 1;
@@ -1517,9 +1577,9 @@ static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
     for (int kh = 0; kh < g.KH; ++kh)
       for (int kw = 0; kw < g.KW; ++kw) { a.tma_offh[0][kh * g.KW + kw] = (unsigned char)kh; a.tma_offw[0][kh * g.KW + kw] = (unsigned char)kw; }
     a.tma_w0[0] = -g.pw; a.tma_h0[0] = -g.ph; a.tma_sw = g.sw; a.tma_sh = g.sh;
-    for (int pl = 0; pl < 2; ++pl)
+    for (int pl = 0; pl < npl; ++pl)
       if (!hs_make_im2col_map(&a.tmA[0][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, -g.pw, -g.ph,
-                              g.pw - (g.KW - 1), g.ph - (g.KH - 1), g.sw, g.sh))
+                              g.pw - (g.KW - 1), g.ph - (g.KH - 1), g.sw, g.sh, npl == 1))
         return false;
   } else if (g.sh == 1 && g.sw == 1) {  // stride-1 dgrad: source = dest + pad - tap = (dest + lower) + (K-1-tap)
     if (g.KH * g.KW > HS_PAR_TAPS) return false;
@@ -1530,9 +1590,9 @@ static inline bool hs_setup_gather_tma(HsGatherArgs& a, int a_plane_slots) {
         a.tma_offw[0][kh * g.KW + kw] = (unsigned char)(g.KW - 1 - kw);
       }
     a.tma_w0[0] = lw; a.tma_h0[0] = lh; a.tma_sw = 1; a.tma_sh = 1;
-    for (int pl = 0; pl < 2; ++pl)
+    for (int pl = 0; pl < npl; ++pl)
       if (!hs_make_im2col_map(&a.tmA[0][pl], pl ? a.Al : a.Ah, g.Cs, g.Ws, g.Hs, images, lw, lh, g.Wd - g.Ws + lw,
-                              g.Hd - g.Hs + lh, 1, 1))
+                              g.Hd - g.Hs + lh, 1, 1, npl == 1))
         return false;
   } else {
     return false;
@@ -1566,16 +1626,22 @@ static inline int hs_launch_gather_gemm(const HsGatherArgs& a_in, int nslots, cu
   const Geom& g = a.g;
   if (!allow_parity || !hs_make_parity(g, a.par)) a.par.nclass = 0;
   a.use_tma = 0;
-  a.flush = hs_flush();
+  a.flush = a.planes == 1 ? 64 : hs_flush();  // bf16: truncation bias is far below the format's own rounding
   if (a_plane_slots > 0 && g_hs_gather_tma_mode > 0 && hs_setup_gather_tma(a, a_plane_slots))
     a.use_tma = g_hs_gather_tma_mode;
   const int tiles_m = a.par.nclass > 0 ? a.par.tile0[a.par.nclass] : ceil_div(g.M, TC_BM);
   if (tc_bn(g.Nd) == 128) {
     const int ntiles = tiles_m * ceil_div(g.Nd, 128) * nslots;
-    gather_gemm_hs<128><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(a, nslots);
+    if (a.planes == 1)
+      gather_gemm_hs<128, 1><<<ntiles < sms ? ntiles : sms, TC_THREADS, HsCfg<128, 1>::SMEM_BYTES, st>>>(a, nslots);
+    else
+      gather_gemm_hs<128, 2><<<ntiles < sms ? ntiles : sms, TC_THREADS, HsCfg<128, 2>::SMEM_BYTES, st>>>(a, nslots);
   } else {
     const int ntiles = tiles_m * ceil_div(g.Nd, 64) * nslots;
-    gather_gemm_hs<64><<<ntiles < sms ? ntiles : sms, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(a, nslots);
+    if (a.planes == 1)
+      gather_gemm_hs<64, 1><<<ntiles < sms ? ntiles : sms, TC_THREADS, HsCfg<64, 1>::SMEM_BYTES, st>>>(a, nslots);
+    else
+      gather_gemm_hs<64, 2><<<ntiles < sms ? ntiles : sms, TC_THREADS, HsCfg<64, 2>::SMEM_BYTES, st>>>(a, nslots);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -1603,7 +1669,7 @@ static inline hs_encode_tiled_fn hs_encode_tiled() {
 
 // 3-d tiled tensor map over an fp16 plane [slots][rows][width] with box (64, 16, slots), SWIZZLE_128B
 static inline bool hs_make_plane_map(CUtensorMap* map, const __half* base, int width, long long rows, int slots,
-                                     long long slot_stride_elems) {
+                                     long long slot_stride_elems, bool bf16 = false) {
   hs_encode_tiled_fn enc = hs_encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)slots};
@@ -1611,7 +1677,8 @@ static inline bool hs_make_plane_map(CUtensorMap* map, const __half* base, int w
   const cuuint32_t box[3] = {64, (cuuint32_t)HSW_ROWS, (cuuint32_t)slots};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (slots > 1 && strides[1] % 16 != 0) return false;
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+  return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+             const_cast<__half*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1621,14 +1688,20 @@ static inline int hs_launch_gather_stack(const HsStackArgs& a_in, cudaStream_t s
   if (hs_ready() <= 0) return -1;
   const int sms = tc_sm_count();
   HsStackArgs a = a_in;
-  a.flush = hs_flush();
+  a.flush = a.planes == 1 ? 64 : hs_flush();
   const Geom& g = a.g;
   if (g.mode != 0 || g.Cs % 8 != 0 || a.nslots < 1) return -1;
-  if (ceil_div(g.Kd, HS_BK) <= 8 && !getenv("CURV_HS_FLUSH")) a.flush = 8;  // short reductions: one main chunk per tile
+  if (a.planes != 1 && ceil_div(g.Kd, HS_BK) <= 8 && !getenv("CURV_HS_FLUSH")) a.flush = 8;  // short reductions: one main chunk per tile
   const int BN = tc_bn(g.Nd), G = 256 / BN;
   const int ntiles = ceil_div(g.M, TC_BM) * ceil_div(g.Nd, BN) * ceil_div(a.nslots, G);
-  if (BN == 128) gather_gemm_hs_stack<128><<<ntiles < sms ? ntiles : sms, HSN_THREADS, HSN_SMEM_BYTES, st>>>(a);
-  else gather_gemm_hs_stack<64><<<ntiles < sms ? ntiles : sms, HSN_THREADS, HSN_SMEM_BYTES, st>>>(a);
+  const int grid = ntiles < sms ? ntiles : sms;
+  if (a.planes == 1) {
+    if (BN == 128) gather_gemm_hs_stack<128, 1><<<grid, HSN_THREADS, HsnCfg<1>::SMEM_BYTES, st>>>(a);
+    else gather_gemm_hs_stack<64, 1><<<grid, HSN_THREADS, HsnCfg<1>::SMEM_BYTES, st>>>(a);
+  } else {
+    if (BN == 128) gather_gemm_hs_stack<128, 2><<<grid, HSN_THREADS, HsnCfg<2>::SMEM_BYTES, st>>>(a);
+    else gather_gemm_hs_stack<64, 2><<<grid, HSN_THREADS, HsnCfg<2>::SMEM_BYTES, st>>>(a);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -1638,12 +1711,14 @@ static inline int hs_launch_wgrad(const HsWgradArgs& a_in, cudaStream_t st, bool
   const int sms = tc_sm_count();
   HsWgradArgs a = a_in;
   a.use_tma = 0;
+  const bool bf = a.planes == 1;
   if (allow_tma && a.g.M >= HSW_ROWS &&
-      hs_make_plane_map(&a.tmGh, a.Gh, a.Ng, a.g.M, a.nslots, a.G_slot) &&
-      hs_make_plane_map(&a.tmGl, a.Gl, a.Ng, a.g.M, a.nslots, a.G_slot))
+      hs_make_plane_map(&a.tmGh, a.Gh, a.Ng, a.g.M, a.nslots, a.G_slot, bf) &&
+      (bf || hs_make_plane_map(&a.tmGl, a.Gl, a.Ng, a.g.M, a.nslots, a.G_slot)))
     a.use_tma = 1;
   const int ntiles = ceil_div(a.g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nsplit;
-  wgrad_gemm_hs<<<ntiles < sms ? ntiles : sms, TC_THREADS, HSW_SMEM_BYTES, st>>>(a);
+  if (bf) wgrad_gemm_hs<1><<<ntiles < sms ? ntiles : sms, TC_THREADS, HswCfg<1>::SMEM_BYTES, st>>>(a);
+  else wgrad_gemm_hs<2><<<ntiles < sms ? ntiles : sms, TC_THREADS, HswCfg<2>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -61,7 +61,8 @@ _program_serial = itertools.count()
 class CompiledProgram:
     """A layer program planned for one (input shape, kmax, hessian) combination."""
 
-    def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool):
+    def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool | int):
+        # `hessian` is the flag word of curv_program_create: 1 = R-op storage, 2 = KFAC scratch, 4 = bf16 arithmetic
         self.lp: LayerProgram = capture(model_func, params, X, fuse_relu=not (int(hessian) & 1))
         self.kmax = kmax
         self.serial = next(_program_serial)  # CUDA-graph cache key (an id() could be reused after a rebuild)
@@ -116,14 +117,18 @@ class Engine:
         self._programs: dict = {}
         self._ws: Tensor | None = None
         self._graphs: dict = {}    # key (all baked-in pointers) -> [CUDAGraph | None]
+        self._p32: dict = {}       # bf16 operators: name -> (data_ptr, version, fp32 copy of the parameter)
         capi.lib()  # fail loudly if the CUDA library has not been built
 
     # -- plumbing ------------------------------------------------------------------------------
     def _check_supported(self):
+        dtypes = {p.dtype for p in self.params.values()}
+        if len(dtypes) > 1:
+            raise RuntimeError(f"Could not infer data type. Parameters have types {dtypes}.")
         for n, p in self.params.items():
-            if p.dtype != torch.float32:
+            if p.dtype not in (torch.float32, torch.bfloat16):
                 raise NotImplementedError(
-                    f"The B200 engine computes in float32; parameter {n!r} has dtype {p.dtype}."
+                    f"The B200 engine computes in float32 or bfloat16; parameter {n!r} has dtype {p.dtype}."
                 )
             if p.device.type != "cuda":
                 raise RuntimeError(
@@ -131,7 +136,15 @@ class Engine:
                     f"{n!r} lives on {p.device}."
                 )
 
-    def program(self, X: Tensor, kmax: int, hessian: bool) -> CompiledProgram:
+    @property
+    def bf16(self) -> bool:
+        """bf16 operator (``_torch_base.py:586-589``: bf16 in, bf16 out): the contractions run as ONE bf16
+        ``tcgen05.mma`` per product with fp32 accumulation (program flag 4) instead of the three fp16 hi/lo MMAs of
+        the fp32-grade path; everything between the contractions stays fp32."""
+        return next(iter(self.params.values())).dtype == torch.bfloat16
+
+    def program(self, X: Tensor, kmax: int, hessian: bool | int) -> CompiledProgram:
+        hessian = int(hessian) | (4 if self.bf16 else 0)
         key = (tuple(X.shape), hessian)
         prog = self._programs.get(key)
         if prog is None or prog.kmax < kmax:
@@ -149,7 +162,16 @@ class Engine:
         return self._ws
 
     def _param_ptrs(self):
-        ps = [p if p.is_contiguous() else p.contiguous() for p in self.params.values()]
+        if self.bf16:  # the library reads fp32 parameters: exact upcasts, refreshed when a parameter changes
+            ps = []
+            for n, p in self.params.items():
+                hit = self._p32.get(n)
+                if hit is None or hit[0] != p.data_ptr() or hit[1] != p._version:
+                    hit = (p.data_ptr(), p._version, p.detach().to(torch.float32).contiguous())
+                    self._p32[n] = hit
+                ps.append(hit[2])
+        else:
+            ps = [p if p.is_contiguous() else p.contiguous() for p in self.params.values()]
         return ps, capi.ptr_array([p.data_ptr() for p in ps])
 
     # -- the hot call ----------------------------------------------------------------------------

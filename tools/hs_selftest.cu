@@ -57,6 +57,20 @@ static double gather_ref(const Geom& g, const float* A, int m, int r) {
 static int n_fail = 0;
 static int g_debug = 0;
 static bool g_tma = true;
+// HS_PLANES=1: bf16 mode of the kernels (one bf16 plane per operand, one MMA per product).  The test data is rounded to
+// bf16 on the host first, so the device-side rounding is exact and the same tight tolerances apply (x10 for the
+// longer TMEM accumulation chains of that mode).
+static int g_planes = 2;
+static float tolx() { return g_planes == 1 ? 10.f : 1.f; }
+static void q(std::vector<float>& v) {
+  if (g_planes != 1) return;
+  for (auto& x : v) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;  // round to nearest even bf16
+    memcpy(&x, &u, 4);
+  }
+}
 
 // slots: slot 0 primal, 1..K tangents.  a_has_slots / with_wt choose the segments.
 static void test_gather(const char* name, Geom g, int K, int a_has_slots, int with_wt, int slot0, int accumulate,
@@ -76,6 +90,7 @@ static void test_gather(const char* name, Geom g, int K, int a_has_slots, int wi
   }
   for (auto& v : out0) v = frand();
   for (auto& v : bias) v = frand();
+  q(A); q(W);
   float *dA = dev(A), *dW = dev(W), *dout = dev(out0), *dbias = dev(bias);
   const int nslots = 1 + K - slot0;
   // scales + planes + images
@@ -83,7 +98,7 @@ static void test_gather(const char* name, Geom g, int K, int a_has_slots, int wi
   uint32_t *abits = dev(zero), *wbits = dev(zero);
   __half *Ah, *Al, *Wimg;
   CK(cudaMalloc(&Ah, a_elems * nA * 2 + 256)); CK(cudaMalloc(&Al, a_elems * nA * 2 + 256));
-  const long long img = hs_image_halves(g.Nd, g.Kd);
+  const long long img = hs_image_halves(g.Nd, g.Kd, g_planes);
   CK(cudaMalloc(&Wimg, img * (1 + K) * 2 + 256));
   const int a_first = a_has_slots ? slot0 : 0;          // first A slot stored in the planes
   const int a_cnt = a_has_slots ? 1 + K - slot0 : 1;
@@ -91,11 +106,12 @@ static void test_gather(const char* name, Geom g, int K, int a_has_slots, int wi
   if (a_has_slots && slot0 > 0 && with_wt) {  // segment 2 gathers slot 0: not supported by the plane layout here
     printf("bad test config\n"); exit(3);
   }
-  if (hs_launch_split(dA + a_first * a_elems, a_elems, a_elems, Ah, Al, a_elems, abits + a_first, a_cnt, 0)) exit(3);
+  if (hs_launch_split(dA + a_first * a_elems, a_elems, a_elems, Ah, g_planes == 1 ? nullptr : Al, a_elems, abits + a_first, a_cnt, 0)) exit(3);
   if (hs_launch_absmax(dW, w_elems, w_elems, wbits, 1 + K, 0)) exit(3);
-  if (hs_launch_pack_image(dW, w_elems, Wimg, img, g.N, g.Nd, g.Kd, 1 + K, wbits, 0)) exit(3);
+  if (hs_launch_pack_image(dW, w_elems, Wimg, img, g.N, g.Nd, g.Kd, 1 + K, wbits, 0, g_planes)) exit(3);
   HsGatherArgs a;
   memset(&a, 0, sizeof(a));
+  a.planes = g_planes;
   a.g = g; a.Ah = Ah; a.Al = Al; a.A_slot = a_elems; a.a_slot_base = a_first; a.a_has_slots = a_has_slots;
   a.a_bits = abits; a.W_img = Wimg; a.Wt_img = with_wt ? Wimg + img : nullptr; a.Wt_img_slot = img;
   a.w_bits = wbits; a.bias = with_bias ? dbias : nullptr; a.bias_t = with_bias ? dbias + g.Nd : nullptr;
@@ -132,7 +148,7 @@ static void test_gather(const char* name, Geom g, int K, int a_has_slots, int wi
     }
     worst = fmax(worst, maxerr / (maxref + 1e-300));
   }
-  const bool ok = worst < 2e-6;
+  const bool ok = worst < 2e-6 * tolx();
   printf("%-44s M=%6d N=%4d Kd=%5d slots=%d  max rel err %.3e  %s\n", name, g.M, g.N, g.Kd, nslots, worst,
          ok ? "PASS" : "FAIL");
   if (!ok) ++n_fail;
@@ -167,19 +183,21 @@ static void test_stack(const char* name, Geom g, int K, int slot_lo, int nslots,
   }
   for (auto& v : out0) v = frand();
   for (auto& v : bias) v = frand();
+  q(A); q(W);
   float *dA = dev(A), *dW = dev(W), *dout = dev(out0), *dbias = dev(bias);
   std::vector<uint32_t> zero(64, 0);
   uint32_t *abits = dev(zero), *wbits = dev(zero);
   __half *Ah, *Al, *Wimg;
   CK(cudaMalloc(&Ah, a_elems * 2 + 256)); CK(cudaMalloc(&Al, a_elems * 2 + 256));
-  const long long img = hs_image_halves(g.Nd, g.Kd);
+  const long long img = hs_image_halves(g.Nd, g.Kd, g_planes);
   CK(cudaMalloc(&Wimg, img * (1 + K) * 2 + 256));
   if (hs_launch_absmax(dA, 0, a_elems, abits, 1, 0)) exit(3);
-  if (hs_launch_split(dA, 0, a_elems, Ah, Al, 0, abits, 1, 0)) exit(3);
+  if (hs_launch_split(dA, 0, a_elems, Ah, g_planes == 1 ? nullptr : Al, 0, abits, 1, 0)) exit(3);
   if (hs_launch_absmax(dW, w_elems, w_elems, wbits, 1 + K, 0)) exit(3);
-  if (hs_launch_pack_image(dW, w_elems, Wimg, img, g.N, g.Nd, g.Kd, 1 + K, wbits, 0)) exit(3);
+  if (hs_launch_pack_image(dW, w_elems, Wimg, img, g.N, g.Nd, g.Kd, 1 + K, wbits, 0, g_planes)) exit(3);
   HsStackArgs a;
   memset(&a, 0, sizeof(a));
+  a.planes = g_planes;
   a.g = g; a.Ah = Ah; a.Al = Al; a.a_bits = abits; a.W_img = Wimg; a.Wt_img = Wimg + img; a.Wt_img_slot = img;
   a.w_bits = wbits; a.bias = with_bias ? dbias : nullptr; a.bias_t = with_bias ? dbias + g.Nd : nullptr;
   a.bias_slot = g.Nd; a.out = dout; a.out_slot = o_elems; a.slot_lo = slot_lo; a.nslots = nslots;
@@ -213,7 +231,7 @@ static void test_stack(const char* name, Geom g, int K, int slot_lo, int nslots,
     }
     worst = fmax(worst, maxerr / (maxref + 1e-300));
   }
-  const bool ok = worst < 2e-6;
+  const bool ok = worst < 2e-6 * tolx();
   printf("%-44s M=%6d N=%4d Kd=%5d slots=%d..%d  max rel err %.3e  %s\n", name, g.M, g.N, g.Kd, slot_lo,
          slot_lo + nslots - 1, worst, ok ? "PASS" : "FAIL");
   if (!ok) ++n_fail;
@@ -231,6 +249,8 @@ static void test_wgrad(const char* name, Geom g, int NS, int slot0, int nsplit, 
     const float sc = powf(10.f, -2.f * s);
     for (long long i = 0; i < g_elems; ++i) G[s * g_elems + i] = frand() * sc;
   }
+  q(In); q(G);
+  tol *= tolx();
   float *dIn = dev(In), *dG = dev(G);
   std::vector<uint32_t> zero(64, 0);
   uint32_t *ibits = dev(zero), *gbits = dev(zero);
@@ -238,12 +258,13 @@ static void test_wgrad(const char* name, Geom g, int NS, int slot0, int nsplit, 
   CK(cudaMalloc(&Ih, i_elems * 2 + 256)); CK(cudaMalloc(&Il, i_elems * 2 + 256));
   CK(cudaMalloc(&Gh, g_elems * NS * 2 + 256)); CK(cudaMalloc(&Gl, g_elems * NS * 2 + 256));
   if (hs_launch_absmax(dIn, 0, i_elems, ibits, 1, 0)) exit(3);
-  if (hs_launch_split(dIn, 0, i_elems, Ih, Il, 0, ibits, 1, 0)) exit(3);
+  if (hs_launch_split(dIn, 0, i_elems, Ih, g_planes == 1 ? nullptr : Il, 0, ibits, 1, 0)) exit(3);
   // G slots carry absolute slot indices slot0 .. slot0+NS-1 (their scale bits live at gbits[slot])
   if (hs_launch_absmax(dG, g_elems, g_elems, gbits + slot0, NS, 0)) exit(3);
-  if (hs_launch_split(dG, g_elems, g_elems, Gh, Gl, g_elems, gbits + slot0, NS, 0)) exit(3);
+  if (hs_launch_split(dG, g_elems, g_elems, Gh, g_planes == 1 ? nullptr : Gl, g_elems, gbits + slot0, NS, 0)) exit(3);
   HsWgradArgs a;
   memset(&a, 0, sizeof(a));
+  a.planes = g_planes;
   a.g = g; a.Gh = Gh; a.Gl = Gl; a.G_slot = g_elems; a.Ng = Ng; a.g_bits = gbits; a.Ih = Ih; a.Il = Il;
   a.i_bits = ibits; a.nslots = NS; a.slot0 = slot0;
   a.m_per_split = (ceil_div(g.M, nsplit) + 15) / 16 * 16;
@@ -306,7 +327,7 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
   CK(cudaMalloc(&Oh, o_elems * (1 + K) * 2)); CK(cudaMalloc(&Ol, o_elems * (1 + K) * 2));
   CK(cudaMemset(Ah, 0, a_elems * (1 + K) * 2)); CK(cudaMemset(Al, 0, a_elems * (1 + K) * 2));
   CK(cudaMemset(Oh, 0, o_elems * (1 + K) * 2)); CK(cudaMemset(Ol, 0, o_elems * (1 + K) * 2));
-  const long long img = hs_image_halves(f.Nd, f.Kd), timg = hs_image_halves(q.Nd, q.Kd);
+  const long long img = hs_image_halves(f.Nd, f.Kd, g_planes), timg = hs_image_halves(q.Nd, q.Kd, g_planes);
   CK(cudaMalloc(&Wimg, img * (1 + K) * 2)); CK(cudaMalloc(&Wtimg, timg * 2));
   CK(cudaMemset(Wimg, 0, img * (1 + K) * 2)); CK(cudaMemset(Wtimg, 0, timg * 2));
   const int nsplit = std::max(1, std::min(64, (2 * 148) / (ceil_div(f.Kd, 128) * ceil_div(Cout, 64))));
@@ -327,20 +348,23 @@ static void bench_layer(const char* name, int B, int H, int C, int Cout, int k, 
   // split pass (absmax + split of 1+K input slots)
   float t_split = timeit([&] {
     hs_launch_absmax(dA, a_elems, a_elems, abits, 1 + K, 0);
-    hs_launch_split(dA, a_elems, a_elems, Ah, Al, a_elems, abits, 1 + K, 0);
+    hs_launch_split(dA, a_elems, a_elems, Ah, g_planes == 1 ? nullptr : Al, a_elems, abits, 1 + K, 0);
   });
   HsGatherArgs a;
   memset(&a, 0, sizeof(a));
+  a.planes = g_planes;
   a.g = f; a.Ah = Ah; a.Al = Al; a.A_slot = a_elems; a.a_has_slots = 1; a.a_bits = abits; a.W_img = Wimg;
   a.Wt_img = Wimg + img; a.Wt_img_slot = img; a.w_bits = wbits; a.out = dO; a.out_slot = o_elems; a.debug = g_debug;
   float t_fwd = timeit([&] { hs_launch_gather_gemm(a, 1 + K, 0, true, g_tma ? 1 + K : 0); });
   HsGatherArgs d;
   memset(&d, 0, sizeof(d));
+  d.planes = g_planes;
   d.g = q; d.Ah = Oh; d.Al = Ol; d.A_slot = o_elems; d.a_slot_base = 1; d.a_has_slots = 1; d.a_bits = obits;
   d.W_img = Wtimg; d.w_bits = wbits; d.out = dA; d.out_slot = a_elems; d.slot0 = 1; d.debug = g_debug;
   float t_dgr = timeit([&] { hs_launch_gather_gemm(d, K, 0, true, g_tma ? K : 0); });
   HsWgradArgs w;
   memset(&w, 0, sizeof(w));
+  w.planes = g_planes;
   w.g = f; w.Gh = Oh; w.Gl = Ol; w.G_slot = o_elems; w.Ng = Cout; w.g_bits = obits; w.Ih = Ah; w.Il = Al;
   w.i_bits = abits; w.partial = dpart; w.nslots = K; w.slot0 = 1; w.m_per_split = mps; w.nsplit = ceil_div(f.M, mps); w.debug = g_debug;
   float t_wgr = timeit([&] { hs_launch_wgrad(w, 0, g_tma); });
@@ -355,6 +379,7 @@ int main(int argc, char** argv) {
   g_debug = argc > 2 ? atoi(argv[2]) : 0;
   g_tma = argc > 3 ? atoi(argv[3]) != 0 : true;
   if (argc > 3) g_hs_gather_tma_mode = atoi(argv[3]);
+  if (getenv("HS_PLANES") && atoi(getenv("HS_PLANES")) == 1) { g_planes = 1; printf("bf16 mode: one plane, one MMA per product\n"); }
   if (g_debug) printf("debug knob = %d (timings only, results invalid)\n", g_debug);
   if (hs_ready() <= 0) { printf("half-split kernels unavailable on this device\n"); return 1; }
   if (which & 1) {
@@ -407,7 +432,7 @@ int main(int argc, char** argv) {
       const int K = 8;
       Geom f = conv_geom(B, H, H, C, Cout, k, s, k / 2);
       const long long a_elems = (long long)B * H * H * C, o_elems = (long long)f.M * Cout;
-      const long long img = hs_image_halves(f.Nd, f.Kd);
+      const long long img = hs_image_halves(f.Nd, f.Kd, g_planes);
       __half *Ah, *Al, *Wimg; float* dO;
       CK(cudaMalloc(&Ah, a_elems * 2)); CK(cudaMalloc(&Al, a_elems * 2)); CK(cudaMalloc(&Wimg, img * (1 + K) * 2));
       CK(cudaMalloc(&dO, o_elems * (1 + K) * 4));
@@ -416,6 +441,7 @@ int main(int argc, char** argv) {
       uint32_t *abits = dev(zero), *wbits = dev(zero);
       HsStackArgs a;
       memset(&a, 0, sizeof(a));
+      a.planes = g_planes;
       a.g = f; a.Ah = Ah; a.Al = Al; a.a_bits = abits; a.W_img = Wimg; a.Wt_img = Wimg + img; a.Wt_img_slot = img;
       a.w_bits = wbits; a.out = dO; a.out_slot = o_elems; a.slot_lo = slot_lo; a.nslots = ns;
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
