@@ -27,7 +27,14 @@ sys.path.insert(0, ROOT)
 METRIC = "ggn_matvec_throughput"
 UNIT = "param*vec/s"
 B, K = 128, 8
-WORKLOAD = "ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, fp32"
+#: --config: c2 = BASELINE.json configs[1] (the configuration the metric is quoted on; default);
+#: c2-bf16 = the same workload as a bf16 operator (bf16 parameters / data / vectors, the dtype of configs[2:])
+WORKLOADS = {
+    "c2": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, fp32", "f32"),
+    "c2-bf16": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, bf16", "bf16"),
+}
+CONFIG = "c2"
+WORKLOAD = WORKLOADS[CONFIG][0]
 
 
 def build_problem(torch, batch):
@@ -37,6 +44,8 @@ def build_problem(torch, batch):
     model = torchvision.models.resnet18().eval()
     X = torch.rand(batch, 3, 224, 224)
     y = torch.randint(0, 1000, (batch,))
+    if WORKLOADS[CONFIG][1] == "bf16":
+        model, X = model.to(torch.bfloat16), X.to(torch.bfloat16)
     return model, X, y
 
 
@@ -134,7 +143,7 @@ def reference_ggn(torch, device, batch, k, repeats, warmup=0):
     params = dict(model.named_parameters())
     P = sum(p.numel() for p in params.values())
     torch.manual_seed(1)
-    V = torch.rand(P, k).to(device)
+    V = torch.rand(P, k).to(device).to(next(iter(params.values())).dtype)
     G = ref.GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False,
                               num_data=batch)
     sync = torch.cuda.synchronize if device.type == "cuda" else (lambda: None)
@@ -154,14 +163,19 @@ def cpu_reference_run(torch, repeats, sample_batch=B, sample_k=K):
     bounded sample of the mini-batch (samples are independent, so the cost is linear in the batch) with all K
     columns."""
     torch.set_num_threads(host_threads())
-    t, P = reference_ggn(torch, torch.device("cpu"), sample_batch, sample_k, repeats)
+    global CONFIG
+    cfg, CONFIG = CONFIG, "c2"  # bf16 configs are timed in fp32 on the CPU (BASELINE.md section 4: CPU bf16
+    try:                        # convolutions are not representative; the reference's inverse cannot run in bf16)
+        t, P = reference_ggn(torch, torch.device("cpu"), sample_batch, sample_k, repeats)
+    finally:
+        CONFIG = cfg
     t_full = t * (B / sample_batch) * (K / sample_k)
     full = sample_batch == B and sample_k == K
     return P * K / t_full, t_full, {
         "kind": "reference", "cores": torch.get_num_threads(),
         "sample": (f"full step (B={B}, K={K}), best of {repeats}" if full else
                    f"{sample_batch} of {B} samples, {sample_k} of {K} columns, best of {repeats}, "
-                   "extrapolated linearly to the full step")}
+                   "extrapolated linearly to the full step") + (", fp32 on the CPU" if cfg != "c2" else "")}
 
 
 def gpu_library_baseline(torch, dev, repeats=3):
@@ -171,7 +185,7 @@ def gpu_library_baseline(torch, dev, repeats=3):
                    f"B={B}, K={K}, min of {repeats} after 1 warm-up", "unit": UNIT}
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     try:
-        for name, tf32 in (("fp32", False), ("tf32", True)):
+        for name, tf32 in ((("bf16", True),) if WORKLOADS[CONFIG][1] == "bf16" else (("fp32", False), ("tf32", True))):
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.backends.cudnn.allow_tf32 = tf32
             t, P = reference_ggn(torch, dev, B, K, repeats, warmup=1)
@@ -191,7 +205,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global CONFIG, WORKLOAD
+    CONFIG, WORKLOAD = args.config, WORKLOADS[args.config][0]
+    DTYPE = WORKLOADS[CONFIG][1]
     if args.impl == "reference":  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it may
         for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ.pop(v, None)
@@ -213,7 +231,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": 0, "ms_per_step": t_full * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": config_dict(args.gpus),
             "note": "unmodified reference (oracle/_ref) on the host cores, torch CPU kernels, full size; "
                     "ms_per_step is the best of `steps` products; no GPU is used by this arm",
@@ -237,7 +255,7 @@ def main():
     params = dict(model.named_parameters())
     P = sum(p.numel() for p in params.values())
     torch.manual_seed(1)
-    V_host = torch.rand(P, K).pin_memory()
+    V_host = torch.rand(P, K).to(next(iter(params.values())).dtype).pin_memory()
     X_host, y_host = X.pin_memory(), y.pin_memory()
     Xd, yd, Vd = X.to(dev), y.to(dev), V_host.to(dev)
     loss = torch.nn.CrossEntropyLoss()
@@ -266,7 +284,7 @@ def main():
     def step_device():
         return G @ Vd
 
-    out_host = torch.empty(P, K).pin_memory()
+    out_host = torch.empty(P, K, dtype=V_host.dtype).pin_memory()
 
     def step_e2e():
         # public host-operand API: V (pinned) in, result (pinned) out, X / y uploaded from pinned memory inside;
@@ -303,12 +321,12 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
 
-    # self-check outside the timed region: tcgen05 (3xTF32) path vs the exact-fp32 SIMT kernels, full size
+    # self-check outside the timed region: default tcgen05 path vs the exact-fp32 SIMT kernels, full size
     got = G @ Vd[:, :2]
     old_mode = capi.lib().curv_set_tensor_core_mode(0)
     ref = G @ Vd[:, :2]
     capi.lib().curv_set_tensor_core_mode(old_mode)
-    self_check = float((got - ref).abs().max() / ref.abs().max())
+    self_check = float((got.float() - ref.float()).abs().max() / ref.float().abs().max())
 
     if rank != 0:
         if world > 1:
@@ -329,11 +347,20 @@ def main():
         "traffic": ncu_traffic_per_launch(),
         "peak_source": peak_src, "launches_timed": int(cnt[dom]),
         "share_of_step": (ms[dom] / nprof) / ms_step,
-        "note": "fp32-grade result: every product is 3 fp16 tcgen05 MMAs on hi/lo split operands (half-split), "
-                "so the tensor-pipe ceiling for algorithmic FLOPs is peak/3; peak is the measured dense bf16/fp16 rate",
-        "frac_of_split_ceiling": ach / (peak_tf / 3.0),
-        "traffic_note": "bytes of DRAM traffic per gather-GEMM launch (ncu, forward launches of one step; equals the "
-                        "algorithmic bytes of those launches: fp16 hi/lo planes in, fp32 result out, nothing re-read)",
+        "note": ("bf16 operator: one bf16 tcgen05 MMA per product, fp32 accumulation in tensor memory"
+                 if DTYPE == "bf16" else
+                 "fp32-grade result: every product is 3 fp16 tcgen05 MMAs on hi/lo split operands (half-split), "
+                 "so the tensor-pipe ceiling for algorithmic FLOPs is peak/3; peak is the measured dense bf16/fp16 rate"),
+        "frac_of_split_ceiling": None if DTYPE == "bf16" else ach / (peak_tf / 3.0),
+        "traffic_note": "bytes of DRAM traffic per gather-GEMM launch (ncu --set full capture of forward launches of one "
+                        "fp32 step, profiles/; equals the algorithmic bytes of those launches: fp16 hi/lo planes in, "
+                        "fp32 result out, nothing re-read)",
+        # whole step against both roofs (15.33 TFLOP and 50.4 GB algorithmic per C2 product)
+        "step": {"algorithmic_tflop": 15.33, "tflops": 15.33 / (ms_step / 1e3),
+                 "frac_of_tensor_peak": 15.33 / (ms_step / 1e3) / peak_tf,
+                 "algorithmic_gb": 50.4 if DTYPE != "bf16" else 25.6,
+                 "gbs": (50.4 if DTYPE != "bf16" else 25.6) / (ms_step / 1e3),
+                 "frac_of_hbm_peak": (50.4 if DTYPE != "bf16" else 25.6) / (ms_step / 1e3) / peaks.get("hbm_gbs", 6550.0)},
         "other": {"kernel": ["gather_gemm", "wgrad_gemm"][1 - dom],
                   "tflops": (fl[1 - dom] / 1e12) / (ms[1 - dom] / 1e3) if ms[1 - dom] > 0 else 0.0,
                   "share_of_step": (ms[1 - dom] / nprof) / ms_step},
@@ -343,15 +370,17 @@ def main():
     out = {
         "metric": METRIC, "value": P * K / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": config_dict(world),
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": P * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(X_host.numel() * 4 + y_host.numel() * 8 + V_host.numel() * 4),
-                "d2h_bytes_per_step": int(P * K * 4)},
+                "h2d_bytes_per_step": int(X_host.numel() * X_host.element_size() + y_host.numel() * 8
+                                          + V_host.numel() * V_host.element_size()),
+                "d2h_bytes_per_step": int(P * K * out_host.element_size())},
         "roofline": roof,
         "self_check": {"tcgen05_vs_fp32_simt_max_rel_err": self_check, "columns": 2,
-                       "note": "default (half-split tcgen05) path vs the exact-fp32 SIMT kernels, full size"},
+                       "note": "default tcgen05 path vs the exact-fp32 SIMT kernels on the same inputs, full size "
+                               "(tolerance of the config: 1e-4 fp32, 1e-2 bf16)"},
     }
     if not args.no_cpu_baseline and world == 1:
         out["gpu_library_baseline"] = gpu_library_baseline(torch, dev)

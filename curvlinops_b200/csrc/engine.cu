@@ -124,7 +124,7 @@ extern "C" void curv_add_launch_count(long long n) { g_launches += n; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 255;
+  g_tc_disable = (mode >> 4) & 0xFFF;  // 512 (mode bit 0x2000): tangent-weight images through the packed fp32 copy
   return old;
 }
 
@@ -213,6 +213,9 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         if (!(hessian & 1)) {
           // multi-slot kernels: at most 2048 pixels (384 MMAs per accumulator on the fp16 path) per split, so the
           // tensor core's truncating accumulation stays below ~1e-5 and no tile needs an in-kernel TMEM flush
+          // (measured, round 2: flushing in the kernel instead -- HSW_FLUSH = 128 stages, splits only to fill the
+          // SMs -- halves the partial traffic but doubles the kernel time: the single-buffered accumulators stall
+          // the MMA warp for every read-modify-write drain)
           const int by_len = ceil_div(g.M, 2048);
           if (by_len > n.nsplit) n.nsplit = by_len;
         }
@@ -401,6 +404,16 @@ static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, dou
   return CURV_OK;
 }
 
+// split-K finish of a weight gradient: partial [split][slot][n][tap][cp] -> out rows of the parameter (K minor)
+static int launch_wgrad_finish(const float* partial, int nsplit, int ns, int kskip, int N, int C, int Cp, int taps,
+                               float* out, long long off, int ldk, int k0, float alpha, long long wsize,
+                               cudaStream_t st) {
+  wgrad_finish_kernel<<<grid1d(wsize, 32), dim3(32, ns - kskip), 0, st>>>(partial, nsplit, ns, kskip, N, C, Cp, taps,
+                                                                          out, off, ldk, k0, alpha);
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
+
 struct Ctx {
   curv_program* P;
   float* ws;
@@ -517,7 +530,10 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
                                                                      g.KH, g.KW, vi.Cp, g.Nd, 1);
         LAUNCH_CHECK();
       }
-      if (with_tangents && d.p0 >= 0) {
+      // the half-split / bf16 forward reads the tangent weights only as images, which are built straight from the
+      // columns of V below: no packed fp32 copy of the K tangent weights
+      const bool images_from_v = hs_fwd_ok(c, n) && c.K <= 8 && !(g_tc_disable & 512);
+      if (with_tangents && d.p0 >= 0 && !images_from_v) {
         pack_weight_kernel<<<dim3(grid1d(n.wsize), c.K), 256, 0, st>>>(
             c.vcol(d.p0), c.ldk, c.ws + n.wkt_off, n.wsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 0);
         LAUNCH_CHECK();
@@ -533,14 +549,20 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
         const int e0 = c.bits_node(ni);
         const bool wt = with_tangents && d.p0 >= 0;
         int rc = hs_absmax(c, c.ws + n.wk_off, 0, n.wsize, e0, 1);
-        if (!rc && wt && hsf) rc = hs_absmax(c, c.ws + n.wkt_off, n.wsize, n.wsize, e0 + 1, c.K);
+        if (!rc && wt && hsf && !images_from_v) rc = hs_absmax(c, c.ws + n.wkt_off, n.wsize, n.wsize, e0 + 1, c.K);
         if (rc) return rc;
         int bad = 0;
         if (hsf) {
           bad |= hs_launch_pack_image(c.ws + n.wk_off, 0, reinterpret_cast<__half*>(c.ws + n.wimg_off), 0, g.N,
                                       g.Nd, g.Kd, 1, c.hsbits() + e0, st, c.planes);
           ++g_launches;
-          if (wt) {
+          if (wt && images_from_v) {
+            bad |= hs_launch_pack_image_cols(c.vcol(d.p0), c.ldk, c.K, reinterpret_cast<__half*>(c.ws + n.wimgt_off),
+                                             hs_image_halves(g.Nd, g.Kd, c.planes), g.N, Cin, g.KH * g.KW, vi.Cp,
+                                             g.Nd, c.hsbits() + e0 + 1, st, c.planes);
+            g_launches += c.planes == 1 ? 1 : 2;
+            for (int k = 0; k < c.K; ++k) (*c.hs_valid)[e0 + 1 + k] = 1;
+          } else if (wt) {
             bad |= hs_launch_pack_image(c.ws + n.wkt_off, n.wsize, reinterpret_cast<__half*>(c.ws + n.wimgt_off),
                                         hs_image_halves(g.Nd, g.Kd, c.planes), g.N, g.Nd, g.Kd, c.K,
                                         c.hsbits() + e0 + 1, st, c.planes);
@@ -901,10 +923,11 @@ static int backward(const Ctx& c, int K) {
             if (hs_launch_wgrad(h, st)) return fail(CURV_ERR_CUDA, "half-split wgrad GEMM launch failed");
             ++g_launches;
           }
-          wgrad_finish_kernel<<<grid1d(n.wsize, 32), dim3(32, ns - kskip), 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
-                                                              vi.Cp, g.KH * g.KW, c.out,
-                                                              P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
-          LAUNCH_CHECK();
+          {
+            int rc2 = launch_wgrad_finish(scratch, n.nsplit, ns, kskip, g.N, vi.C, vi.Cp, g.KH * g.KW, c.out,
+                                          P->params[d.p0].offset, c.ldk, c.k0, c.alpha, n.wsize, st);
+            if (rc2) return rc2;
+          }
         } else if (c.kfac_G == nullptr && d.p0 >= 0) {  // weight gradient
           WgradArgs a;
           memset(&a, 0, sizeof(a));
@@ -916,10 +939,11 @@ static int backward(const Ctx& c, int K) {
           a.m_per_split = n.m_per_split;
           int rc = launch_wgrad(a, n.wbm, n.wbn, st, conv_flops(g, vi.C) * ns * (a.second_seg ? 2 : 1));
           if (rc) return rc;
-          wgrad_finish_kernel<<<grid1d(n.wsize, 32), dim3(32, ns - kskip), 0, st>>>(scratch, n.nsplit, ns, kskip, g.N, vi.C,
-                                                              vi.Cp, g.KH * g.KW, c.out,
-                                                              P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
-          LAUNCH_CHECK();
+          {
+            int rc2 = launch_wgrad_finish(scratch, n.nsplit, ns, kskip, g.N, vi.C, vi.Cp, g.KH * g.KW, c.out,
+                                          P->params[d.p0].offset, c.ldk, c.k0, c.alpha, n.wsize, st);
+            if (rc2) return rc2;
+          }
         }
         if (c.kfac_G == nullptr && d.p1 >= 0) {  // bias gradient: column sums of the cotangent
           long long rows = g.M;

@@ -153,6 +153,78 @@ __global__ void hs_pack_image_kernel(const float* __restrict__ src, long long sr
   }
 }
 
+// Tangent-weight images straight from the columns of V (no packed fp32 intermediate): the rows of V that belong to a
+// conv weight [N][C][taps] hold its K tangent directions side by side (K minor, row stride ldk).
+//   hs_vcol_absmax_kernel      bits[k] = max_rows |V[row][k]|  (the per-(tensor, column) scale of the images)
+//   hs_pack_image_cols_kernel  image k (dst + k*dst_slot) of the weight matrix [N][taps*Cp] of column k, same block /
+//                              swizzle layout as hs_pack_image_kernel; the 8 elements of a 16-byte chunk are channels
+//                              cp0..cp0+7 of one filter tap, i.e. 8 rows of V whose K columns are read together
+__global__ void __launch_bounds__(256) hs_vcol_absmax_kernel(const float* __restrict__ V, long long rows, int ldk,
+                                                            int K, uint32_t* __restrict__ bits) {
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* r = V + i * ldk;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < K) m[k] = fmaxf(m[k], fabsf(__ldg(r + k)));
+  }
+  __shared__ float wm[8][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = m[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v = fmaxf(v, wm[w][threadIdx.x]);
+    if (v > 0.f && __float_as_uint(v) > *reinterpret_cast<volatile uint32_t*>(bits + threadIdx.x))
+      atomicMax(bits + threadIdx.x, __float_as_uint(v));
+  }
+}
+
+__global__ void __launch_bounds__(256) hs_pack_image_cols_kernel(const float* __restrict__ V, int ldk, int K,
+                                                                __half* __restrict__ dst, long long dst_slot, int N,
+                                                                int C, int taps, int Cp, int BN, int tiles_n,
+                                                                int nchunks, const uint32_t* __restrict__ bits,
+                                                                int planes) {
+  const int Kd = taps * Cp;
+  const long long total = (long long)tiles_n * nchunks * BN * 8;  // 16-byte chunks per plane
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    long long t = e >> 3;
+    const int r = (int)(t % BN); t /= BN;
+    const int kc = (int)(t % nchunks);
+    const int tn = (int)(t / nchunks);
+    const int n = tn * BN + r, k = kc * HS_BK + c * 8;
+    const int tap = k / Cp, cp0 = k - tap * Cp;
+    const bool ok = n < N && k < Kd;
+    const float* src = V + (((long long)n * C + cp0) * taps + tap) * ldk;  // row of element (n, cp0, tap)
+    const long long rstep = (long long)taps * ldk;                           // next channel
+    const long long blk_off = ((long long)tn * nchunks + kc) * (planes * BN * HS_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 1;  // in halves
+    for (int slot = 0; slot < K; ++slot) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (ok && cp0 + j < C) ? __ldg(src + j * rstep + slot) : 0.f;
+      const float sc = hs_pow2(hs_shift_from_bits(bits[slot]));
+      const float4 v0 = make_float4(x[0], x[1], x[2], x[3]), v1 = make_float4(x[4], x[5], x[6], x[7]);
+      __half* blk = dst + (long long)slot * dst_slot + blk_off;
+      if (planes == 1) { *reinterpret_cast<uint4*>(blk + o) = hs_bf16x8(v0, v1, sc); continue; }
+      uint4 h, l;
+      hs_split8(v0, v1, sc, h, l);
+      *reinterpret_cast<uint4*>(blk + o) = h;
+      *reinterpret_cast<uint4*>(blk + BN * HS_BK + o) = l;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
@@ -1110,7 +1182,7 @@ struct HswCfg {  // PL = 2: 5 stages of 40 KB; PL = 1 (bf16): 7 stages of 20 KB 
   static constexpr int STAGES = PL == 2 ? 5 : 7;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
-constexpr int HSW_FLUSH = 256;
+constexpr int HSW_FLUSH = 256;  // stages (of 16 pixels) per TMEM accumulation chunk
 
 // 3-d tiled TMA load global -> shared, completion on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void hs_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -1508,6 +1580,23 @@ static inline int hs_launch_pack_image(const float* src, long long src_slot, __h
   const long long total = (long long)tiles_n * nchunks * BN * 8;
   hs_pack_image_kernel<<<dim3(hs_grid(total), nslots), 256, 0, st>>>(src, src_slot, dst, dst_slot, N, Kd, BN,
                                                                     tiles_n, nchunks, bits, planes);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// images of the K tangent weights of a conv [N][C][taps] from the K columns of V (rows = N*C*taps, stride ldk);
+// bits[k] receives / holds the absmax of column k (computed here unless planes == 1: bf16 planes are unscaled)
+static inline int hs_launch_pack_image_cols(const float* V, int ldk, int K, __half* dst, long long dst_slot, int N,
+                                            int C, int taps, int Cp, int Nd, uint32_t* bits, cudaStream_t st,
+                                            int planes) {
+  if (K < 1 || K > 8) return 1;
+  const int Kd = taps * Cp;
+  const int BN = tc_bn(Nd);
+  const int tiles_n = ceil_div(Nd, BN), nchunks = ceil_div(Kd, HS_BK);
+  const long long rows = (long long)N * C * taps;
+  if (planes != 1) hs_vcol_absmax_kernel<<<hs_grid(rows), 256, 0, st>>>(V, rows, ldk, K, bits);
+  const long long total = (long long)tiles_n * nchunks * BN * 8;
+  hs_pack_image_cols_kernel<<<hs_grid(total), 256, 0, st>>>(V, ldk, K, dst, dst_slot, N, C, taps, Cp, BN, tiles_n,
+                                                           nchunks, bits, planes);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

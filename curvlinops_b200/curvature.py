@@ -169,21 +169,22 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
             num_per_example_loss_terms = t_acc // N
         return N, num_per_example_loss_terms
 
-    def _loop_over_data(self, desc: str | None = None):
+    def _loop_over_data(self, desc: str | None = None, to_device: bool = True):
         it = self._data
-        dev = self.device
+        dev = self.device if to_device else None
         if self._progressbar:
             from tqdm import tqdm
 
             it = tqdm(it, desc=f"{self.__class__.__name__}{'' if desc is None else '.' + desc} (on {dev})")
         for X, y in it:
             if isinstance(X, Tensor):
-                X = X.to(dev)
+                X = X.to(dev) if to_device else X
             elif self._input_key is not None:
-                Xt = X[self._input_key].to(dev).detach()  # a new tensor object: the tag stays off the caller's
+                Xt = X[self._input_key]
+                Xt = (Xt.to(dev) if to_device else Xt).detach()  # a new tensor object: the tag stays off the caller's
                 Xt._curv_batch_size = self._batch_size_fn(X)
                 X = Xt
-            yield X, y.to(dev)
+            yield X, (y.to(dev) if to_device else y)
 
     def _get_normalization_factor(self, X, y) -> float:
         return {"sum": 1.0, "mean": self._batch_size_fn(X) / self._N_data}[self._loss_func.reduction]
@@ -269,25 +270,108 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         self._engine.matmat_batch(self.KIND, X, y, V, out, alpha)
 
     def _matmat(self, M: list[Tensor]) -> list[Tensor]:
-        V = self._flat_matrix(M)
+        return self._unflatten(self._product(self._flat_matrix(M)), M)
+
+    def _matmat_flat(self, V: Tensor) -> Tensor:
+        """``A @ V`` for a flat ``[P, K]`` matrix without the split into per-parameter views and the two
+        concatenations of the list format (``_torch_base.py:289-298,414-422``): the engine works on this layout."""
+        return self._product(V.to(torch.float32).contiguous()).to(V.dtype)
+
+    def _local_batches(self, desc: str):
+        """Mini-batches as this rank processes them: ``(X, y, alpha, scales)`` on the operator's device.  With batch
+        sharding on, only the rank's contiguous slice of each mini-batch is moved to the device (``X`` is ``None``
+        for a rank whose slice is empty); ``alpha`` and the loss-Hessian constants stay those of the GLOBAL batch."""
+        rank, world = cdist.rank_world()
+        dev = self.device
+        for X, y in self._loop_over_data(desc=desc, to_device=(world == 1)):
+            alpha = self._get_normalization_factor(X, y)
+            if world == 1:
+                yield X, y, alpha, None
+                continue
+            Xs, ys, scales = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
+            if Xs is not None:
+                Xs, ys = Xs.to(dev, non_blocking=True), ys.to(dev, non_blocking=True)
+            yield Xs, ys, alpha, scales
+
+    def _param_buckets(self, K: int, bucket_bytes: int, first_bytes: int | None = None):
+        """Row ranges ``(lo, hi, [param indices])`` of the flat ``[P, K]`` matrices made of whole parameters, about
+        ``bucket_bytes`` each (the first one at most ``first_bytes``: it is the piece that cannot overlap)."""
+        sizes = [p.numel() for p in self._params.values()]
+        buckets, lo, plist, acc = [], 0, [], 0
+        for i, n in enumerate(sizes):
+            plist.append(i)
+            acc += n
+            limit = min(bucket_bytes, first_bytes) if (not buckets and first_bytes) else bucket_bytes
+            if acc * K * 4 >= limit or i == len(sizes) - 1:
+                buckets.append((lo, lo + acc, plist))
+                lo, plist, acc = lo + acc, [], 0
+        return buckets
+
+    #: with batch sharding on: sum the [P, K] result in parameter buckets on a side stream, each bucket as soon as
+    #: the backward sweep has finished its rows (it finishes the LAST parameters first), instead of one blocking
+    #: all-reduce after the last kernel
+    OVERLAP_ALLREDUCE = True
+
+    def _product(self, V: Tensor) -> Tensor:
+        """``[P, K]`` fp32 -> ``[P, K]`` fp32: the loop over mini-batches (``_torch_base.py:937-944``)."""
+        from .engine import MAX_COLUMNS_PER_SWEEP
+
         out = torch.zeros_like(V)
         rank, world = cdist.rank_world()
-        for X, y in self._loop_over_data(desc="_matmat"):
-            alpha = self._get_normalization_factor(X, y)
+        K = V.shape[1]
+        overlap = (world > 1 and self.OVERLAP_ALLREDUCE and V.device.type == "cuda" and K <= MAX_COLUMNS_PER_SWEEP)
+        batches = iter(self._local_batches("_matmat"))
+        cur = next(batches, None)
+        reduced = False
+        while cur is not None:
+            nxt = next(batches, None)
+            X, y, alpha, scales = cur
             if world > 1:  # data-parallel shard of this mini-batch, weights stay global
-                Xs, ys, scale = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
-                if Xs is not None:
-                    self._batch_call_sharded(Xs, ys, V, out, alpha, scale)
+                if overlap and nxt is None:
+                    self._last_batch_with_overlapped_all_reduce(X, y, V, out, alpha, scales)
+                    reduced = True
+                elif X is not None:
+                    self._batch_call_sharded(X, y, V, out, alpha, scales)
             else:
                 if not isinstance(X, Tensor):
                     raise NotImplementedError("The B200 engine needs tensor inputs X.")
                 self._batch_call(X, y, V, out, alpha)
-        if world > 1:
+            cur = nxt
+        if world > 1 and not reduced:
             cdist.all_reduce_sum(out)
-        return self._unflatten(out, M)
+        return out
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
-        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0])
+    def _last_batch_with_overlapped_all_reduce(self, X, y, V, out, alpha, scales, bucket_bytes: int = 64 << 20):
+        dev = V.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(dev)
+        comm = self._comm_stream
+        # buckets in parameter (= forward) order; the sweep completes them back to front.  Every rank builds the same
+        # list, so the sequence of collectives matches even for a rank without samples.
+        buckets = self._param_buckets(V.shape[1], bucket_bytes, first_bytes=8 << 20)
+        n = len(self._params)
+        out_done, events = [None] * n, []
+        for blo, bhi, ps in buckets:
+            e = torch.cuda.Event()
+            e.record(main)  # materialises the handle; the engine re-records it when the bucket's rows are final
+            events.append(e)
+            for i in ps:
+                out_done[i] = e
+        if X is not None:
+            self._batch_call_sharded(X, y, V, out, alpha, scales, out_done=out_done)
+        tail = torch.cuda.Event()
+        tail.record(main)
+        with torch.cuda.stream(comm):
+            for (blo, bhi, _), e in zip(reversed(buckets), reversed(events)):
+                comm.wait_event(e if X is not None else tail)
+                cdist.all_reduce_sum(out[blo:bhi])
+        main.wait_stream(comm)
+        out.record_stream(comm)
+
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
+        kw = {} if out_done is None else {"out_done": out_done}
+        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0], **kw)
 
     # ---- host-resident operands: pipelined upload / download ----------------------------------------
     #: a kind whose mini-batch product is one engine call with (X, y, V, out) only may stream
@@ -321,9 +405,13 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
                 out = torch.empty(res.shape, dtype=res.dtype, pin_memory=(dev.type == "cuda"))
             out.copy_(res, non_blocking=True)
             return out
-        V = V.to(torch.float32)
+        # bf16 operators keep V / the result in bf16 on the host (half the PCIe bytes); the engine's fp32 matrices
+        # are filled / drained by conversions on the copy streams
+        lowp = V.dtype == torch.bfloat16
+        if not lowp:
+            V = V.to(torch.float32)
         if out is None:
-            out = torch.empty(Pn, K, dtype=torch.float32, pin_memory=True)
+            out = torch.empty(Pn, K, dtype=V.dtype, pin_memory=True)
         # buckets of whole parameters, about bucket_bytes each; the first one is small: it gates the start of the
         # forward sweep on the way in and is the only download that cannot overlap the backward sweep
         buckets, lo, plist, acc = [], 0, [], 0
@@ -340,6 +428,8 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         s_in, s_out = self._copy_streams
         Vd = torch.empty(Pn, K, dtype=torch.float32, device=dev)
         outd = torch.zeros(Pn, K, dtype=torch.float32, device=dev)
+        Vlow = torch.empty(Pn, K, dtype=V.dtype, device=dev) if lowp else None
+        outlow = torch.empty(Pn, K, dtype=out.dtype, device=dev) if out.dtype != torch.float32 else None
         v_ready, out_done, bucket_events = [None] * len(sizes), [None] * len(sizes), []
         # the first mini-batch goes up BEFORE V: host-to-device copies share one DMA queue, and the forward
         # sweep needs X first
@@ -348,7 +438,11 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         s_in.wait_stream(main)
         with torch.cuda.stream(s_in):
             for blo, bhi, ps in buckets:
-                Vd[blo:bhi].copy_(V[blo:bhi], non_blocking=True)
+                if lowp:
+                    Vlow[blo:bhi].copy_(V[blo:bhi], non_blocking=True)
+                    Vd[blo:bhi].copy_(Vlow[blo:bhi])
+                else:
+                    Vd[blo:bhi].copy_(V[blo:bhi], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(s_in)
                 for i in ps:
@@ -380,16 +474,24 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         if world > 1:
             main.wait_stream(s_in)
             cdist.all_reduce_sum(outd)
-            out.copy_(outd, non_blocking=True)
+            out.copy_(outd if outlow is None else outlow.copy_(outd), non_blocking=True)
         else:
             with torch.cuda.stream(s_out):
                 for (blo, bhi, _), e in zip(reversed(buckets), reversed(bucket_events)):
                     s_out.wait_event(e)
-                    out[blo:bhi].copy_(outd[blo:bhi], non_blocking=True)
+                    if outlow is not None:
+                        outlow[blo:bhi].copy_(outd[blo:bhi])
+                        out[blo:bhi].copy_(outlow[blo:bhi], non_blocking=True)
+                    else:
+                        out[blo:bhi].copy_(outd[blo:bhi], non_blocking=True)
             main.wait_stream(s_out)
         main.wait_stream(s_in)
         Vd.record_stream(s_in)
         outd.record_stream(s_out)
+        if Vlow is not None:
+            Vlow.record_stream(s_in)
+        if outlow is not None:
+            outlow.record_stream(s_out)
         return out
 
     def __getstate__(self):
@@ -428,14 +530,14 @@ class GGNLinearOperator(CurvatureLinearOperator):
                          check_deterministic=check_deterministic, num_data=num_data,
                          batch_size_fn=batch_size_fn)
 
-    def _matmat(self, M):
+    def _product(self, V):
         if self._mc_samples > 0:
             self._batch_index = 0
             dev = self.device
             with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
                 torch.manual_seed(self._seed)  # same stream as the reference (ggn.py:337-341)
-                return super()._matmat(M)
-        return super()._matmat(M)
+                return super()._product(V)
+        return super()._product(V)
 
     def _mc_scale(self, batch: int) -> float:
         return 1.0 / batch if self._loss_func.reduction == "mean" else 1.0
@@ -451,11 +553,12 @@ class GGNLinearOperator(CurvatureLinearOperator):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
                                   scale=self._mc_scale(X.shape[0]))
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
         if self._mc_samples == 0:
-            return super()._batch_call_sharded(X, y, V, out, alpha, scale)
+            return super()._batch_call_sharded(X, y, V, out, alpha, scale, out_done=out_done)
         g = self._engine.mc_grad_outputs(X, self._mc_samples)
-        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1])
+        kw = {} if out_done is None else {"out_done": out_done}
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1], **kw)
 
 
 class EFLinearOperator(CurvatureLinearOperator):
@@ -499,9 +602,10 @@ class EFLinearOperator(CurvatureLinearOperator):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
                                   scale=loss_scale(self._loss_func, X.shape[0], g.shape[-1]))
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale):
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
+        kw = {} if out_done is None else {"out_done": out_done}
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=self._grad_outputs(X, y),
-                                  scale=scale[0])
+                                  scale=scale[0], **kw)
 
 
 class HessianLinearOperator(CurvatureLinearOperator):

@@ -63,7 +63,10 @@ class CompiledProgram:
 
     def __init__(self, model_func, params: dict[str, Tensor], X: Tensor, kmax: int, hessian: bool | int):
         # `hessian` is the flag word of curv_program_create: 1 = R-op storage, 2 = KFAC scratch, 4 = bf16 arithmetic
-        self.lp: LayerProgram = capture(model_func, params, X, fuse_relu=not (int(hessian) & 1))
+        # traced in the parameters' dtype (the engine itself is handed fp32 copies of bf16 data)
+        pdt = next(iter(params.values())).dtype if params else X.dtype
+        self.lp: LayerProgram = capture(model_func, params, X if X.dtype == pdt else X.to(pdt),
+                                        fuse_relu=not (int(hessian) & 1))
         self.kmax = kmax
         self.serial = next(_program_serial)  # CUDA-graph cache key (an id() could be reused after a rebuild)
         self.batch = X.shape[0]

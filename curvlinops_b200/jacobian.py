@@ -18,6 +18,7 @@ from .linop import PyTorchLinearOperator
 class _JacobianBase(CurvatureLinearOperator):
     SELF_ADJOINT = False
     FIXED_DATA_ORDER = True
+    _matmat_flat = None  # not a square parameter-space operator: no flat [P, K] fast path
 
     def __init__(self, model_func, params, data, progressbar=False, check_deterministic=True, num_data=None,
                  batch_size_fn=None):

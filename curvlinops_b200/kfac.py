@@ -69,6 +69,7 @@ class KFACComputer(CurvatureLinearOperator):
     _SUPPORTED_FISHER_TYPE = tuple(FisherType)
     NEEDS_NUM_PER_EXAMPLE_LOSS_TERMS = True
     _TEST_GRAD_OUTPUTS = None
+    _matmat_flat = None  # the computer is not itself an operator
 
     def __init__(self, model_func, loss_func, params, data, progressbar=False, check_deterministic=True,
                  seed: int = 2_147_483_647, fisher_type: str = FisherType.MC, mc_samples: int = 1,
@@ -230,7 +231,7 @@ class KFACComputer(CurvatureLinearOperator):
         key = (tuple(X.shape), "kfac")
         prog = eng._programs.get(key)
         if prog is None:
-            prog = CompiledProgram(eng.model_func, eng.params, X, 8, 2)
+            prog = CompiledProgram(eng.model_func, eng.params, X, 8, 2 | (4 if eng.bf16 else 0))
             eng._programs[key] = prog
             if prog.lp.tied:
                 raise NotImplementedError(

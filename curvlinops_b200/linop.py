@@ -140,6 +140,12 @@ class PyTorchLinearOperator:
             lhs = tuple(self) if isinstance(self, _ChainPyTorchLinearOperator) else (self,)
             rhs = tuple(X) if isinstance(X, _ChainPyTorchLinearOperator) else (X,)
             return _ChainPyTorchLinearOperator(*lhs, *rhs)
+        flat = getattr(self, "_matmat_flat", None)
+        if (flat is not None and isinstance(X, Tensor) and X.ndim in (1, 2) and X.shape[0] == self.shape[1]
+                and X.device == self.device and X.dtype == self.dtype):
+            # operators that work on the flat [P, K] layout skip the per-parameter split / re-concatenation
+            Y = flat(X if X.ndim == 2 else X.unsqueeze(1))
+            return Y.squeeze(1) if X.ndim == 1 else Y
         Xl, was_list, was_vec, K = self._to_list(X, self._in_shape, leading=False)
         return self._from_list(self._matmat(Xl), self._out_shape, False, was_list, was_vec, K)
 

@@ -103,7 +103,11 @@ typedef struct curv_node_desc {
 typedef struct curv_program curv_program;
 
 /* Build the execution plan (host side only) for mini-batches of `batch` samples and up to `kmax`
-   simultaneous columns.  `hessian` != 0 reserves the extra cotangent storage the R-op needs.
+   simultaneous columns.  `hessian` is a flag word: 1 reserves the extra cotangent storage the R-op needs
+   (CURV_KIND_HESSIAN), 2 the scratch of curv_kfac_accumulate_batch, 4 selects bf16 arithmetic for the
+   tensor-core contractions (bf16 operators, _torch_base.py:586-589: operands rounded to bf16, ONE
+   tcgen05.mma.kind::f16 per product, fp32 accumulation; parameters / X / V / out stay fp32 at this boundary --
+   the host mirrors keep exact fp32 copies of bf16 tensors).
    values[0] must be the network input; nodes are in topological order; the last node's `out` is the
    prediction and must have H=W=1. */
 int curv_program_create(const curv_value_desc* values, int n_values, const curv_node_desc* nodes,
@@ -196,7 +200,8 @@ int curv_profile_read_class(int cls, double* ms, double* flops, long long* count
    where the shape allows it, 3xTF32 split for the Hessian R-op and the KFAC Gram matrices) for layers with at least
    256 GEMM rows, 2: tcgen05 for every contraction (tests).  Bits 4.. are A/B switches: 0x10 no tcgen05 gather GEMM,
    0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead), 0x400 BatchNorm kernels never write
-   operand planes directly (separate split passes), 0x800 no N-stacked kernel for shared-activation layers.
+   operand planes directly (separate split passes), 0x800 no N-stacked kernel for shared-activation layers,
+   0x2000 tangent-weight images through a packed fp32 copy of the columns of V.
    Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);
 /* Everything global that changes which kernels a call launches: the mode word above | (profiling enabled) << 16.

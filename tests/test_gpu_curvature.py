@@ -257,3 +257,22 @@ def test_on_device_lanczos_matches_scipy_eigsh():
     resid = ((G @ vec) - vec * ev).norm(dim=0) / ev.abs().max()
     assert bool((resid < 1e-3).all()), resid
     assert vec.device.type == "cuda" and nprod < 200
+
+
+def test_parameter_space_glue_variants_are_bit_identical():
+    """Building the tangent-weight images straight from the columns of V computes exactly what the two-step path
+    (packed fp32 copy, then image; mode bit 0x2000) computes: same scales, same roundings."""
+    from curvlinops_b200 import _capi as capi
+
+    model, loss, data, fx, params = _setup("miniresnet_ce_mean")
+    V = fx["V"].float().cuda()
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    old = capi.lib().curv_set_tensor_core_mode(2)
+    try:
+        new = G @ V
+        capi.lib().curv_set_tensor_core_mode(2 | 0x2000)
+        ref = G @ V
+    finally:
+        capi.lib().curv_set_tensor_core_mode(old)
+    assert torch.equal(new, ref)
+    assert_parity(new, fx["ggn"], params)
