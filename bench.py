@@ -255,7 +255,23 @@ def main():
     params = dict(model.named_parameters())
     P = sum(p.numel() for p in params.values())
     torch.manual_seed(1)
-    V_host = torch.rand(P, K).to(next(iter(params.values())).dtype).pin_memory()
+    pdt = next(iter(params.values())).dtype
+    shm = None
+    if world > 1:
+        # one copy of V / of the result in host memory for all ranks of the box (POSIX shared memory registered as
+        # pinned): each rank moves 1/world of the bytes over PCIe, NVLink does the rest
+        shm = f"curvbench_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            V_host = cdist.shared_pinned_tensor(shm + "_V", (P, K), pdt)
+            V_host.copy_(torch.rand(P, K).to(pdt))
+            out_host = cdist.shared_pinned_tensor(shm + "_out", (P, K), pdt)
+        dist.barrier()
+        if rank != 0:
+            V_host = cdist.shared_pinned_tensor(shm + "_V", (P, K), pdt)
+            out_host = cdist.shared_pinned_tensor(shm + "_out", (P, K), pdt)
+    else:
+        V_host = torch.rand(P, K).to(pdt).pin_memory()
+        out_host = torch.empty(P, K, dtype=pdt).pin_memory()
     X_host, y_host = X.pin_memory(), y.pin_memory()
     Xd, yd, Vd = X.to(dev), y.to(dev), V_host.to(dev)
     loss = torch.nn.CrossEntropyLoss()
@@ -283,8 +299,6 @@ def main():
 
     def step_device():
         return G @ Vd
-
-    out_host = torch.empty(P, K, dtype=V_host.dtype).pin_memory()
 
     def step_e2e():
         # public host-operand API: V (pinned) in, result (pinned) out, X / y uploaded from pinned memory inside;
@@ -328,6 +342,13 @@ def main():
     capi.lib().curv_set_tensor_core_mode(old_mode)
     self_check = float((got.float() - ref.float()).abs().max() / ref.float().abs().max())
 
+    if world > 1:  # the shared result must equal the device-resident product
+        barrier()
+        e2e_check = float((out_host.to(dev).float() - (G @ Vd).float()).abs().max() / out_host.float().abs().max())
+        barrier()
+        if rank == 0:
+            cdist.release_shared(shm + "_V")
+            cdist.release_shared(shm + "_out")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,7 +397,11 @@ def main():
         "e2e": {"value": P * K / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(X_host.numel() * X_host.element_size() + y_host.numel() * 8
                                           + V_host.numel() * V_host.element_size()),
-                "d2h_bytes_per_step": int(P * K * out_host.element_size())},
+                "d2h_bytes_per_step": int(P * K * out_host.element_size()),
+                **({"vs_resident_max_rel_diff": e2e_check,
+                    "note": "V and the result live once in shared pinned host memory; every rank moves its 1/N row "
+                            "block (H2D + NCCL all-gather, reduce-scatter + D2H); byte counts are per job"}
+                   if world > 1 else {})},
         "roofline": roof,
         "self_check": {"tcgen05_vs_fp32_simt_max_rel_err": self_check, "columns": 2,
                        "note": "default tcgen05 path vs the exact-fp32 SIMT kernels on the same inputs, full size "

@@ -405,6 +405,8 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
                 out = torch.empty(res.shape, dtype=res.dtype, pin_memory=(dev.type == "cuda"))
             out.copy_(res, non_blocking=True)
             return out
+        if world > 1:
+            return self._matmat_pinned_sharded(V, out, rank, world)
         # bf16 operators keep V / the result in bf16 on the host (half the PCIe bytes); the engine's fp32 matrices
         # are filled / drained by conversions on the copy streams
         lowp = V.dtype == torch.bfloat16
@@ -492,6 +494,48 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
             Vlow.record_stream(s_in)
         if outlow is not None:
             outlow.record_stream(s_out)
+        return out
+
+    def _matmat_pinned_sharded(self, V: Tensor, out: Tensor | None, rank: int, world: int) -> Tensor:
+        """Host-operand product on several ranks of one box: the host matrices are moved ONCE in total, not once per
+        rank.  Rank r uploads rows ``row_block(r)`` of V (1/world of the bytes) and NCCL all-gathers the blocks over
+        NVLink; after the sweeps a reduce-scatter leaves rank r with rows ``row_block(r)`` of the summed result,
+        which it downloads into ``out[row_block(r)]``.  Hand every rank a view of the SAME host buffers
+        (:func:`curvlinops_b200.dist.shared_pinned_tensor`) and ``out`` holds the whole result once all ranks have
+        synchronised; with private buffers each rank's ``out`` holds its row block only (the other rows are left
+        untouched)."""
+        dev = self.device
+        Pn, K = V.shape
+        chunk = -(-Pn // world)
+        lo, hi = min(Pn, rank * chunk), min(Pn, (rank + 1) * chunk)
+        if out is None:
+            out = torch.zeros(Pn, K, dtype=V.dtype, pin_memory=True)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, _ = self._copy_streams
+        Vd = torch.empty(world * chunk, K, dtype=torch.float32, device=dev)
+        outd = torch.zeros(world * chunk, K, dtype=torch.float32, device=dev)
+        part = torch.zeros(chunk, K, dtype=torch.float32, device=dev)
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):  # upload + all-gather on the side stream: X goes up on the main stream meanwhile
+            if hi > lo:
+                stage = torch.empty(hi - lo, K, dtype=V.dtype, device=dev)
+                stage.copy_(V[lo:hi], non_blocking=True)
+                part[: hi - lo].copy_(stage)
+            cdist.all_gather_rows(Vd, part)
+        batches = list(self._local_batches("matmat_pinned"))
+        main.wait_stream(s_in)
+        for X, y, alpha, scales in batches:
+            if X is not None:
+                self._batch_call_sharded(X, y, Vd[:Pn], outd[:Pn], alpha, scales)
+        res = torch.empty(chunk, K, dtype=torch.float32, device=dev)
+        cdist.reduce_scatter_rows(res, outd)
+        if hi > lo:
+            out[lo:hi].copy_(res[: hi - lo] if out.dtype == torch.float32 else res[: hi - lo].to(out.dtype),
+                             non_blocking=True)
+        for t in (Vd, part):
+            t.record_stream(s_in)
         return out
 
     def __getstate__(self):

@@ -58,3 +58,40 @@ def shard_batch(X: Tensor, y: Tensor, rank: int, world: int, loss_func, engine=N
 def all_reduce_sum(t: Tensor) -> None:
     """In-place sum over ranks (one collective per matmat / factor build)."""
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)
+
+
+def all_gather_rows(full: Tensor, part: Tensor) -> None:
+    """``full[r * n:(r + 1) * n] = part`` of rank ``r`` (``part``: ``[n, K]``, ``full``: ``[world * n, K]``)."""
+    dist.all_gather_into_tensor(full, part, group=_group)
+
+
+def reduce_scatter_rows(part: Tensor, full: Tensor) -> None:
+    """``part`` of rank ``r`` = sum over ranks of ``full[r * n:(r + 1) * n]``."""
+    dist.reduce_scatter_tensor(part, full, op=dist.ReduceOp.SUM, group=_group)
+
+
+def shared_pinned_tensor(name: str, shape, dtype=torch.float32, device=None) -> Tensor:
+    """A host tensor backed by POSIX shared memory (``/dev/shm/<name>``) that every rank of one box can map, registered
+    with CUDA as pinned memory: one copy of V / of the result in host memory feeds all GPUs of the box (each rank
+    moves its row block, see ``CurvatureLinearOperator.matmat_pinned``).  The first caller creates the file; remove it
+    with :func:`release_shared` when done."""
+    import math
+
+    n = math.prod(shape)
+    t = torch.from_file(f"/dev/shm/{name}", shared=True, size=n, dtype=dtype).view(*shape)
+    if torch.cuda.is_available():
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * t.element_size(), 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed with code {int(rc)}")
+    return t
+
+
+def release_shared(name: str, tensor: Tensor | None = None) -> None:
+    import os
+
+    if tensor is not None and torch.cuda.is_available():
+        torch.cuda.cudart().cudaHostUnregister(tensor.data_ptr())
+    try:
+        os.unlink(f"/dev/shm/{name}")
+    except FileNotFoundError:
+        pass
