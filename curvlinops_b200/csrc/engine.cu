@@ -116,6 +116,8 @@ static long long gram_partial_elems(long long rows, int width, int widthp) {
   return (long long)gram_nsplit(rows, width, widthp) * width * widthp + 64;
 }
 
+static long long gram_hs_plan_elems(long long rows, int ld, int planes);  // kfac.cuh
+
 extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
 extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
 extern "C" long long curv_launch_count(void) { return g_launches; }
@@ -124,7 +126,8 @@ extern "C" void curv_add_launch_count(long long n) { g_launches += n; }
 extern "C" int curv_set_tensor_core_mode(int mode) {
   int old = g_tc_mode | (g_tc_disable << 4);
   g_tc_mode = mode & 3;
-  g_tc_disable = (mode >> 4) & 0xFFF;  // 512 (mode bit 0x2000): tangent-weight images through the packed fp32 copy
+  g_tc_disable = (mode >> 4) & 0xFFF;  // 512 (mode bit 0x2000): tangent-weight images through the packed fp32 copy,
+                                      // 1024 (0x4000): KFAC Gram matrices on the SIMT / 3xTF32 kernels
   return old;
 }
 
@@ -230,6 +233,12 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         long long needG = gram_partial_elems((long long)g.M * kmax, vo.C, vo.Cp);
         if (needA > scratch) scratch = needA;
         if (needG > scratch) scratch = needG;
+        // tensor-core Gram path (kfac.cuh): patch planes (2 bytes per element and plane) + partials
+        const int planes = (hessian & 4) ? 1 : 2, ld = pad8(width);
+        long long needH = align_up((long long)g.M * ld + 1024, 128) * planes / 2 + gram_hs_plan_elems(g.M, ld, planes);
+        long long needHG = gram_hs_plan_elems(g.M, vo.Cp, planes);
+        if (needH > scratch) scratch = needH;
+        if (needHG > scratch) scratch = needHG;
       }
       if (d.p1 >= 0) {  // bias grad = column sum of the output cotangent
         long long rows = g.M;
@@ -858,6 +867,12 @@ static int forward(const Ctx& c, const void* X, int K) {
 
 static int gram_accumulate(const float* X, long long rows, int width, int widthp, float* F, float w,
                            float* partial, long long partial_elems, cudaStream_t st);
+namespace curv {
+__global__ void hs_bits_fill_kernel(uint32_t* dst, int n, const uint32_t* src, uint32_t floor_bits);
+}
+static int gram_hs(const __half* Xh, const __half* Xl, int planes, long long rows, int width, int ld,
+                   const uint32_t* sbits, int C, int taps, float* F, float w, float* partial,
+                   long long partial_elems, cudaStream_t st);
 
 // backward sweep over cotangent slots [s0, s0+ns) of the grad storage.
 //   GGN / VJP: s0 = 1, ns = K.      Hessian R-op: s0 = 0, ns = K+1 (slot 0 = plain backward).
@@ -888,24 +903,38 @@ static int backward(const Ctx& c, int K) {
     switch (d.op) {
       case CURV_OP_CONV: {
         const Geom& g = n.fwd;
-        if (c.kfac_G != nullptr) {  // KFAC: Gram matrix of the K stacked cotangent slots, no parameter grads
-          if (c.kfac_G[ni] != nullptr) {
-            int rc = gram_accumulate(c.grad(d.out, 1), (long long)K * g.M, vo.C, vo.Cp, c.kfac_G[ni],
-                                     c.kfac_wG, scratch, P->scratch_elems, st);
-            if (rc) return rc;
-          }
+        // KFAC: Gram matrix of the cotangent slots instead of parameter gradients; on the tensor cores (from the
+        // operand planes the dgrad reads as well) when the layer is large enough, else fp32 SIMT / 3xTF32
+        const bool kfac_g = c.kfac_G != nullptr && c.kfac_G[ni] != nullptr;
+        const bool hs_g = kfac_g && c.hs && g.M >= 256 && vo.C >= 16 && vo.Cp % 8 == 0 && !(g_tc_disable & 1024) &&
+                          vo.slot_elems * ns <= P->hs1_elems;
+        if (kfac_g && !hs_g) {
+          int rc = gram_accumulate(c.grad(d.out, 1), (long long)K * g.M, vo.C, vo.Cp, c.kfac_G[ni],
+                                   c.kfac_wG, scratch, P->scratch_elems, st);
+          if (rc) return rc;
         }
         const int nidx = ni;
         const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, ns);
         const bool hs_d = vi.tan && hs_dgr_ok(c, n);
         const int eg = c.bits_grad(d.out);
-        if ((hs_w || hs_d) && planes_of != d.out) {  // fp16 hi/lo planes of the cotangent slots (wgrad + dgrad)
+        if ((hs_w || hs_d || hs_g) && planes_of != d.out) {  // fp16 hi/lo planes of the cotangent slots (wgrad + dgrad)
           int rc = hs_absmax(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, eg + s0, ns);
           if (!rc) rc = hs_split(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, c.hs1_hi(), c.hs1_lo(),
                                  eg + s0, ns);
           if (rc) return rc;
         }
         planes_of = -1;
+        if (hs_g) {  // one Gram per slot (the slots carry different scales)
+          uint32_t* sb = c.hsbits() + c.bits_node(nidx) + (1 + P->kmax);
+          for (int sl = 0; sl < ns; ++sl) {
+            hs_bits_fill_kernel<<<1, 32, 0, st>>>(sb, 8, c.hsbits() + eg + s0 + sl, 0u);
+            LAUNCH_CHECK();
+            int rc = gram_hs(c.hs1_hi() + (long long)sl * vo.slot_elems,
+                             c.planes == 1 ? nullptr : c.hs1_lo() + (long long)sl * vo.slot_elems, c.planes, g.M, vo.C,
+                             vo.Cp, sb, vo.C, 1, c.kfac_G[nidx], c.kfac_wG, scratch, P->scratch_elems, st);
+            if (rc) return rc;
+          }
+        }
         if (hs_w) {  // weight gradients of all slots on the half-split kernel
           const int ea = c.bits_act(d.in0);
           int rc = hs_absmax(c, c.act(d.in0), 0, vi.slot_elems, ea, 1);

@@ -1157,6 +1157,8 @@ struct HsWgradArgs {
   const __half* Gh;        // cotangent planes [slot - slot0][M*Ng]  (slot0 first)
   const __half* Gl;
   long long G_slot;        // elements
+  long long G_ld;          // row stride of G in elements (0: Ng).  With G_ld > Ng and G_slot = Ng the "slots" are
+                           // adjacent column blocks of ONE matrix: the Gram matrices of kfac.cuh
   int Ng;
   const uint32_t* g_bits;  // indexed by absolute slot
   const __half* Ih;        // primal input planes [B*Hs*Ws*Cs]
@@ -1284,7 +1286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
     } else if (warp < 6 + HSW_STAGES) {
       const int gw = warp - 6;               // ring slot owned by this warp
       const int ir = lane >> 1, half = lane & 1;
-      const bool uniform = (g.Cs % 64) == 0;  // the 64 columns of a half lie inside one filter tap
+      const bool uniform = (g.Cs % 64) == 0 || g.KH * g.KW == 1;  // the 64 columns of a half lie inside one filter tap
       const uint32_t offRow = (uint32_t)(half * 2048 + (ir >> 3) * 1024 + (ir & 7) * 128);
       int q0 = 0;  // stages of this CTA before the current tile
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1384,7 +1386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_hs(const __grid_cons
         }
         const int mg = mb + st * HSW_ROWS + gr;
         const bool okG = chok && mg < me;
-        const long long eoG = okG ? (long long)mg * p.Ng + ch : 0;
+        const long long eoG = okG ? (long long)mg * (p.G_ld ? p.G_ld : p.Ng) + ch : 0;
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sA = sbase + stage * HSW_STAGE_BYTES;
         const uint32_t sB = sA + PL * HSW_A_BYTES;
@@ -1758,11 +1760,13 @@ static inline hs_encode_tiled_fn hs_encode_tiled() {
 
 // 3-d tiled tensor map over an fp16 plane [slots][rows][width] with box (64, 16, slots), SWIZZLE_128B
 static inline bool hs_make_plane_map(CUtensorMap* map, const __half* base, int width, long long rows, int slots,
-                                     long long slot_stride_elems, bool bf16 = false) {
+                                     long long slot_stride_elems, bool bf16 = false, long long row_stride_elems = 0) {
   hs_encode_tiled_fn enc = hs_encode_tiled();
   if (!enc) return false;
+  if (row_stride_elems == 0) row_stride_elems = width;
+  if ((row_stride_elems * 2) % 16 != 0) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)slots};
-  const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)slot_stride_elems * 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2, (cuuint64_t)slot_stride_elems * 2};
   const cuuint32_t box[3] = {64, (cuuint32_t)HSW_ROWS, (cuuint32_t)slots};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (slots > 1 && strides[1] % 16 != 0) return false;
@@ -1802,8 +1806,8 @@ static inline int hs_launch_wgrad(const HsWgradArgs& a_in, cudaStream_t st, bool
   a.use_tma = 0;
   const bool bf = a.planes == 1;
   if (allow_tma && a.g.M >= HSW_ROWS &&
-      hs_make_plane_map(&a.tmGh, a.Gh, a.Ng, a.g.M, a.nslots, a.G_slot, bf) &&
-      (bf || hs_make_plane_map(&a.tmGl, a.Gl, a.Ng, a.g.M, a.nslots, a.G_slot)))
+      hs_make_plane_map(&a.tmGh, a.Gh, a.Ng, a.g.M, a.nslots, a.G_slot, bf, a.G_ld) &&
+      (bf || hs_make_plane_map(&a.tmGl, a.Gl, a.Ng, a.g.M, a.nslots, a.G_slot, false, a.G_ld)))
     a.use_tma = 1;
   const int ntiles = ceil_div(a.g.Kd, TC_BM) * ceil_div(a.Ng, 64) * a.nsplit;
   if (bf) wgrad_gemm_hs<1><<<ntiles < sms ? ntiles : sms, TC_THREADS, HswCfg<1>::SMEM_BYTES, st>>>(a);

@@ -54,7 +54,129 @@ __global__ void gram_finish_kernel(const float* __restrict__ partial, int nsplit
   }
 }
 
+// ---- tensor-core Gram path (round 2): the tall matrix lives as operand planes (fp16 hi/lo, or one bf16 plane in
+// bf16 programs) and X^T X runs on wgrad_gemm_hs: the gathered "input" operand is X itself (1x1 geometry, 128
+// columns i per tile) and the "cotangent slots" are up to 8 adjacent column blocks of W8 columns of the SAME
+// matrix (G_ld = ld, G_slot = W8), so one N = 256 MMA multiplies a 128-column tile against 256 other columns.
+
+// patch planes P[m][tap*C + c] = s * in[src(m, tap)][c] (columns in (tap, c) order: 8-column chunks are channel
+// runs of one tap when C % 8 == 0; the factor is permuted to F.unfold's (c, tap) order by gram_hs_finish_kernel),
+// column taps*C = s * 1 if joint, up to ld zero.  lo == nullptr: one bf16 plane.
+__global__ void __launch_bounds__(256) im2col_planes_kernel(const float* __restrict__ in, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, Geom g, int C, int joint, int ld,
+                                                           const uint32_t* __restrict__ bits) {
+  const int taps = g.KH * g.KW;
+  const int Kreal = C * taps;
+  const int chunks = ld >> 3;
+  const float sc = hs_pow2(hs_shift_from_bits(bits[0]));
+  const long long total = (long long)g.M * chunks;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    const int m = (int)(e / chunks);
+    const int b = m / (g.Hd * g.Wd);
+    const int rem = m - b * (g.Hd * g.Wd);
+    const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = ch * 8 + j;
+      float v = 0.f;
+      if (col < Kreal) {
+        const int tap = col / C, c = col - tap * C;
+        const int kh = tap / g.KW, kw = tap - kh * g.KW;
+        const int hs = hd * g.sh - g.ph + kh, ws = wd * g.sw - g.pw + kw;
+        if (hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws)
+          v = __ldg(in + (((long long)b * g.Hs + hs) * g.Ws + ws) * g.Cs + c);
+      } else if (col == Kreal && joint) {
+        v = 1.f;
+      }
+      x[j] = v;
+    }
+    const float4 v0 = make_float4(x[0], x[1], x[2], x[3]), v1 = make_float4(x[4], x[5], x[6], x[7]);
+    if (lo == nullptr) { reinterpret_cast<uint4*>(hi)[e] = hs_bf16x8(v0, v1, sc); continue; }
+    uint4 h, l;
+    hs_split8(v0, v1, sc, h, l);
+    reinterpret_cast<uint4*>(hi)[e] = h;
+    reinterpret_cast<uint4*>(lo)[e] = l;
+  }
+}
+
+// dst[0..n) = max(*src, floor_bits)   (bit patterns of non-negative floats; src may be null)
+__global__ void hs_bits_fill_kernel(uint32_t* dst, int n, const uint32_t* src, uint32_t floor_bits) {
+  const uint32_t v = src ? max(*src, floor_bits) : floor_bits;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = v;
+}
+
+// F[r][q] += w * sum_splits partial[sp][col(r)][col(q)], partial split = [rows_per_split][ld] floats.
+// taps > 1: F is in (c, tap) order, the planes in (tap, c) order (joint column last in both).
+__global__ void gram_hs_finish_kernel(const float* __restrict__ partial, int nsplit, long long split_elems, int ld,
+                                      int width, int C, int taps, float* __restrict__ F, float w) {
+  const long long total = (long long)width * width;
+  const int Kreal = C * taps;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(e % width);
+    const int r = (int)(e / width);
+    const int cr = r < Kreal ? (r % taps) * C + r / taps : r;
+    const int cq = q < Kreal ? (q % taps) * C + q / taps : q;
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += __ldg(partial + sp * split_elems + (long long)cr * ld + cq);
+    F[e] += w * s;
+  }
+}
+
 }  // namespace curv
+
+// plan of the tensor-core Gram: column block width W8, blocks NS, splits
+struct GramHsPlan { int W8, NS, nsplit, m_per_split; long long partial_elems; };
+static GramHsPlan gram_hs_plan(long long rows, int ld, int planes) {
+  GramHsPlan p;
+  p.W8 = 64 * ceil_div(ld, 512);
+  p.NS = ceil_div(ld, p.W8);
+  const long long tiles = (long long)ceil_div(ld, 128) * (p.W8 / 64);
+  long long want = (2 * 148 + tiles - 1) / tiles;
+  const long long by_len = (rows + (planes == 1 ? 4096 : 2048) - 1) / (planes == 1 ? 4096 : 2048);
+  long long ns = want > by_len ? want : by_len;
+  const long long maxsplit = (rows + 255) / 256;
+  if (ns > maxsplit) ns = maxsplit;
+  if (ns < 1) ns = 1;
+  p.m_per_split = (int)(((rows + ns - 1) / ns + 15) / 16 * 16);
+  p.nsplit = (int)((rows + p.m_per_split - 1) / p.m_per_split);
+  p.partial_elems = (long long)p.nsplit * p.NS * p.W8 * ld;
+  return p;
+}
+static long long gram_hs_plan_elems(long long rows, int ld, int planes) {
+  return gram_hs_plan(rows, ld, planes).partial_elems + 64;
+}
+// F[width][width] += w * X^T X for X given as planes [rows][ld] (scale word sbits, replicated in sbits[0..8));
+// (C, taps): column permutation of gram_hs_finish_kernel (taps = 1: none)
+static int gram_hs(const __half* Xh, const __half* Xl, int planes, long long rows, int width, int ld,
+                   const uint32_t* sbits, int C, int taps, float* F, float w, float* partial,
+                   long long partial_elems, cudaStream_t st) {
+  if (rows >= (1LL << 31) - 4096) return fail(CURV_ERR_INVALID, "too many rows for a Gram matrix");
+  const GramHsPlan pl = gram_hs_plan(rows, ld, planes);
+  if (pl.partial_elems > partial_elems)
+    return fail(CURV_ERR_WORKSPACE, "KFAC scratch too small (program not created with the kfac flag?)");
+  HsWgradArgs a;
+  memset(&a, 0, sizeof(a));
+  Geom& g = a.g;
+  g.B = (int)rows; g.Hs = g.Ws = g.Hd = g.Wd = 1; g.Cs = ld; g.KH = g.KW = 1; g.sh = g.sw = 1;
+  g.ph = g.pw = 0; g.mode = 0; g.N = pl.W8; g.Nd = pl.W8; g.Kd = ld; g.M = (int)rows;
+  a.Gh = Xh; a.Gl = Xl; a.G_slot = pl.W8; a.G_ld = ld; a.Ng = pl.W8; a.g_bits = sbits;
+  a.Ih = Xh; a.Il = Xl; a.i_bits = sbits;
+  a.partial = partial; a.nsplit = pl.nsplit; a.nslots = pl.NS; a.slot0 = 0; a.m_per_split = pl.m_per_split;
+  a.planes = planes;
+  {
+    ProfScope prof(1, 2.0 * (double)rows * width * width, st);
+    if (hs_launch_wgrad(a, st)) return fail(CURV_ERR_CUDA, "tensor-core Gram launch failed");
+    ++g_launches;
+  }
+  gram_hs_finish_kernel<<<grid1d((long long)width * width), 256, 0, st>>>(
+      partial, pl.nsplit, (long long)pl.NS * pl.W8 * ld, ld, width, C, taps, F, w);
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
 
 // Gram matrix of X [rows][widthp] (first `width` columns real): F += w * X^T X
 static int gram_accumulate(const float* X, long long rows, int width, int widthp, float* F, float w,
@@ -104,6 +226,7 @@ extern "C" int curv_kfac_accumulate_batch(curv_program* P, const void* const* pa
   std::vector<char> hs_valid;
   if (g_tc_mode && !(g_tc_disable & 32) && P->hs1_elems > 0 && hs_ready() > 0) {
     c.hs = true;
+    c.planes = (P->hessian & 4) ? 1 : 2;
     hs_valid.assign((size_t)P->hsbits_count, 0);
     c.hs_valid = &hs_valid;
     CHECK_CUDA(cudaMemsetAsync(c.hsbits(), 0, (size_t)P->hsbits_count * sizeof(uint32_t), c.st));
@@ -121,6 +244,31 @@ extern "C" int curv_kfac_accumulate_batch(curv_program* P, const void* const* pa
     const Value& vi = P->values[n.d.in0];
     const Geom& g = n.fwd;
     const int width = vi.C * g.KH * g.KW + (joint_bias[i] ? 1 : 0);
+    if (c.hs && g.M >= 256 && width >= 16 && !(g_tc_disable & 1024)) {
+      // tensor-core Gram: patch matrix as operand planes in the scratch region, partials behind it
+      const int ld = pad8(width);
+      const long long plane_halves = align_up((long long)g.M * ld + 1024, 128);  // + slack: blocks read past a row end
+      const long long plane_floats = plane_halves * c.planes / 2;
+      const GramHsPlan pl = gram_hs_plan(g.M, ld, c.planes);
+      if (plane_floats + pl.partial_elems > P->scratch_elems)
+        return fail(CURV_ERR_WORKSPACE, "KFAC scratch too small for the patch planes");
+      __half* ph = reinterpret_cast<__half*>(scratch);
+      __half* plo = c.planes == 1 ? nullptr : ph + plane_halves;
+      const int ni = layer_nodes[i];
+      uint32_t* sb = c.hsbits() + c.bits_node(ni) + (1 + P->kmax);  // 8 copies of the patch scale
+      if ((rc = hs_absmax(c, c.act(n.d.in0), 0, vi.slot_elems, c.bits_act(n.d.in0), 1))) return rc;
+      hs_bits_fill_kernel<<<1, 32, 0, st>>>(sb, 8, c.planes == 1 ? nullptr : c.hsbits() + c.bits_act(n.d.in0),
+                                            (c.planes == 1 || !joint_bias[i]) ? 0u : 0x3f800000u);
+      LAUNCH_CHECK();
+      im2col_planes_kernel<<<grid1d((long long)g.M * (ld / 8)), 256, 0, st>>>(c.act(n.d.in0), ph, plo, g, vi.C,
+                                                                            joint_bias[i] ? 1 : 0, ld, sb);
+      LAUNCH_CHECK();
+      const float w = wA / (float)(g.Hd * g.Wd);
+      if ((rc = gram_hs(ph, plo, c.planes, g.M, width, ld, sb, vi.C, g.KH * g.KW, A_ptrs[i], w,
+                        scratch + plane_floats, P->scratch_elems - plane_floats, st)))
+        return rc;
+      continue;
+    }
     const int widthp = pad4(width);
     const long long pelems = (long long)g.M * widthp;
     if (pelems > P->scratch_elems) return fail(CURV_ERR_WORKSPACE, "KFAC scratch too small for patches");

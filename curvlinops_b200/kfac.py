@@ -31,7 +31,8 @@ from .curvature import CurvatureLinearOperator
 from .engine import CompiledProgram
 from .linop import _ChainPyTorchLinearOperator
 from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
-                         KroneckerProductLinearOperator, ToCanonicalLinearOperator, dense_matmul)
+                         KroneckerProductLinearOperator, ToCanonicalLinearOperator, dense_matmul,
+                         with_fp32_master)
 
 
 class _MetaEnum(EnumMeta):
@@ -224,7 +225,8 @@ class KFACComputer(CurvatureLinearOperator):
                 p = self._params[next(iter(group.values()))]
                 G[tuple(group.values())] = torch.eye(p.shape[0], dtype=p.dtype, device=dev)
         dt = self.dtype
-        return ({k: v.to(dt) for k, v in A.items()}, {k: v.to(dt) for k, v in G.items()}, self._mapping)
+        return ({k: with_fp32_master(v, dt) for k, v in A.items()}, {k: with_fp32_master(v, dt) for k, v in G.items()},
+                self._mapping)
 
     def _kfac_program(self, X: Tensor) -> CompiledProgram:
         eng = self._engine
@@ -362,12 +364,13 @@ class EKFACComputer(KFACComputer):
 
     def compute(self):
         A, G, mapping = super().compute()
-        QA = {k: torch.linalg.eigh(v.float()).eigenvectors for k, v in A.items()}
-        QG = {k: torch.linalg.eigh(v.float()).eigenvectors for k, v in G.items()}
+        f32 = lambda v: getattr(v, "_curv_fp32", v).float()  # bf16 operators: factorise the fp32 masters
+        QA = {k: torch.linalg.eigh(f32(v)).eigenvectors for k, v in A.items()}
+        QG = {k: torch.linalg.eigh(f32(v)).eigenvectors for k, v in G.items()}
         lam = self._eigenvalue_correction(QA, QG, mapping)
         dt = self.dtype
-        return ({k: v.to(dt) for k, v in QA.items()}, {k: v.to(dt) for k, v in QG.items()},
-                {k: v.to(dt) for k, v in lam.items()}, mapping)
+        return ({k: with_fp32_master(v, dt) for k, v in QA.items()}, {k: with_fp32_master(v, dt) for k, v in QG.items()},
+                {k: with_fp32_master(v, dt) for k, v in lam.items()}, mapping)
 
     def _eigenvalue_correction(self, QA, QG, mapping):
         """Second pass: per-example gradients in the Kronecker eigenbasis, squared and summed.

@@ -38,10 +38,28 @@ def _one(values, what):
     return vals.pop()
 
 
+def with_fp32_master(v32: Tensor, dtype: torch.dtype) -> Tensor:
+    """Factor in the operator's dtype.  For bf16 operators the tensor handed out is bf16 (the reference's factors have
+    the parameter dtype, ``kfac_hooks.py:350-353``) but it carries the fp32 matrix it was rounded from: the engine's
+    contract for bf16 is fp32 factors / fp32 Cholesky and eigh (the reference cannot factorise bf16 matrices at all,
+    ``kronecker.py:356-373``), so products and inverses of these operators read the master."""
+    if dtype == v32.dtype:
+        return v32
+    t = v32.to(dtype)
+    t._curv_fp32 = v32
+    return t
+
+
+def _fp32_master(t: Tensor) -> Tensor | None:
+    m = getattr(t, "_curv_fp32", None)
+    return m if isinstance(m, Tensor) and m.shape == t.shape and m.device == t.device else None
+
+
 def _cuda_f32(t: Tensor, what: str) -> Tensor:
     if t.device.type != "cuda":
         raise RuntimeError(f"curvlinops_b200 applies {what} on CUDA devices only (no CPU fallback); got {t.device}.")
-    return t.to(torch.float32).contiguous()
+    m = _fp32_master(t)
+    return (t if m is None else m).to(torch.float32).contiguous()
 
 
 def _stream(t: Tensor):
@@ -182,6 +200,12 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
 
     @staticmethod
     def _damped_cholesky_inverse(A: Tensor, damping, retry_double_precision: bool) -> Tensor:
+        if A.dtype in (torch.bfloat16, torch.float16):  # factorise in fp32 (from the fp32 master when there is one)
+            m = _fp32_master(A)
+            inv32 = KroneckerProductLinearOperator._damped_cholesky_inverse(
+                A.to(torch.float32) if m is None else m, damping, retry_double_precision)
+            return with_fp32_master(inv32, A.dtype)
+
         def chol(M: Tensor) -> Tensor:
             return torch.linalg.cholesky(torch.diagonal_scatter(M, M.diag() + damping))
 

@@ -201,6 +201,7 @@ int curv_profile_read_class(int cls, double* ms, double* flops, long long* count
    256 GEMM rows, 2: tcgen05 for every contraction (tests).  Bits 4.. are A/B switches: 0x10 no tcgen05 gather GEMM,
    0x20 no tcgen05 wgrad GEMM, 0x200 no half-split kernels (3xTF32 instead), 0x400 BatchNorm kernels never write
    operand planes directly (separate split passes), 0x800 no N-stacked kernel for shared-activation layers,
+   0x4000 KFAC Gram matrices on the SIMT / 3xTF32 kernels instead of the tensor-core Gram path,
    0x2000 tangent-weight images through a packed fp32 copy of the columns of V.
    Returns the old mode. */
 int curv_set_tensor_core_mode(int mode);

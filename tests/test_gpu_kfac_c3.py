@@ -1,0 +1,90 @@
+"""KFAC at the shapes of BASELINE.json configs[2] (C3): ResNet-18 at 3 x 224 x 224, Conv2d / Linear parameters only,
+joint weight+bias groups, MC Fisher with one sample, damped inverse 1e-3 -- as fp32 and as bf16 operator.
+
+Oracle: ``oracle.curvature_oracle.kfac_factors`` in float64 on the GPU with the SAME would-be gradients (drawn once
+here and handed to both sides), then the Kronecker apply ``G [W|b] A^T`` and the damped-inverse apply in float64
+(for bf16 the oracle is the reference arithmetic in higher precision on identical bf16-representable
+inputs -- the reference itself cannot invert in bf16, ``kronecker.py:356-373``).  B = 16 keeps the float64 patch
+matrices of the oracle small; the factor kernels see the full C3 layer shapes (21 groups, A up to 4608^2).
+Tolerances: north_star rtol 1e-4 (fp32) / 1e-2 (bf16) relative to the largest entry; the damped inverse amplifies the
+factor rounding by the condition number (<= max eig / 1e-3), hence 5e-3 / 5e-2 there."""
+import pytest
+import torch
+
+from curvlinops_b200 import KFACLinearOperator
+from curvlinops_b200.kfac import KFACComputer
+from oracle import curvature_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    return ((got.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kfac_resnet18_c3_shapes(dtype, monkeypatch):
+    import torchvision
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    B = 16
+    model = torchvision.models.resnet18().eval().to(dev)
+    X = torch.rand(B, 3, 224, 224, device=dev)
+    if dtype == torch.bfloat16:
+        model, X = model.to(dtype), X.to(dtype)
+    y = torch.randint(0, 1000, (B,), device=dev)
+    m64 = torchvision.models.resnet18().eval().to(dev).double()
+    m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    X64 = X.double()
+    mods = dict(model.named_modules())
+    layer_names = [n for n, m in mods.items() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+    params = {f"{n}.{pn}": p for n in layer_names for pn, p in mods[n].named_parameters(recurse=False)}
+    loss = torch.nn.CrossEntropyLoss()
+    # one would-be gradient per datum, shared by both sides
+    with torch.no_grad():
+        p = torch.softmax(m64(X64), 1)
+    yhat = p.multinomial(1)
+    gos = (p.unsqueeze(1) - torch.nn.functional.one_hot(yhat, 1000).double()).permute(1, 0, 2).contiguous()
+    monkeypatch.setattr(KFACComputer, "_TEST_GRAD_OUTPUTS", [gos.float()])
+    Kop = KFACLinearOperator(model, loss, params, [(X, y)], fisher_type="mc", mc_samples=1,
+                             separate_weight_and_bias=False, check_deterministic=False, num_data=B)
+    A64, G64 = orc.kfac_factors(m64, loss, layer_names, [(X64, y)], n_data=B, fisher_type="mc", joint_bias=True,
+                                grad_outputs=[gos])
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    _, K, _ = Kop
+    assert len(K) == len(layer_names) == 21
+    worst = 0.0
+    for name, block in zip(layer_names, K):
+        Gf, Af = list(block)
+        eg, ea = _rel(Gf, G64[name]), _rel(Af, A64[name])
+        worst = max(worst, eg, ea)
+        assert Af.shape == A64[name].shape and eg < tol and ea < tol, (name, eg, ea)
+    print(f"{dtype}: 42 factors, worst max|err|/max|ref| = {worst:.3e}")
+    # apply and damped-inverse apply on a random vector, per layer in float64
+    P = sum(p.numel() for p in params.values())
+    v = torch.rand(P, device=dev).to(dtype)
+    got, got_inv = Kop @ v, Kop.inverse(damping=1e-3) @ v
+    assert got.dtype == dtype
+    parts, inv_parts, o = [], [], 0
+    eye = lambda n: torch.eye(n, device=dev, dtype=torch.float64)
+    for name in layer_names:
+        m = mods[name]
+        W = v[o:o + m.weight.numel()].double().reshape(m.weight.shape[0], -1)
+        o += m.weight.numel()
+        if m.bias is not None:
+            W = torch.cat([W, v[o:o + m.bias.numel()].double().unsqueeze(1)], 1)
+            o += m.bias.numel()
+        for store, Gm, Am in ((parts, G64[name], A64[name]),
+                              (inv_parts, torch.linalg.inv(G64[name] + 1e-3 * eye(G64[name].shape[0])),
+                               torch.linalg.inv(A64[name] + 1e-3 * eye(A64[name].shape[0])))):
+            R = Gm @ W @ Am.T
+            if m.bias is not None:
+                store += [R[:, :-1].reshape(-1), R[:, -1]]
+            else:
+                store.append(R.reshape(-1))
+    ref, ref_inv = torch.cat(parts), torch.cat(inv_parts)
+    e_apply, e_inv = _rel(got, ref), _rel(got_inv, ref_inv)
+    print(f"{dtype}: KFAC apply max|err|/max|ref| = {e_apply:.3e}, inverse(1e-3) apply = {e_inv:.3e}")
+    assert e_apply < tol, e_apply
+    assert e_inv < 50 * tol, e_inv
