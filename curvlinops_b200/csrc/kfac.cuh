@@ -78,6 +78,23 @@ __global__ void __launch_bounds__(256) im2col_planes_kernel(const float* __restr
     const int rem = m - b * (g.Hd * g.Wd);
     const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
     float x[8];
+    if ((C & 7) == 0 && ch * 8 < Kreal) {  // 8 consecutive channels of one filter tap: two 16-byte loads
+      const int col = ch * 8;
+      const int tap = col / C, c = col - tap * C;
+      const int kh = tap / g.KW, kw = tap - kh * g.KW;
+      const int hs = hd * g.sh - g.ph + kh, ws = wd * g.sw - g.pw + kw;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws) {
+        const float4* q = reinterpret_cast<const float4*>(in + (((long long)b * g.Hs + hs) * g.Ws + ws) * g.Cs + c);
+        v0 = __ldg(q); v1 = __ldg(q + 1);
+      }
+      if (lo == nullptr) { reinterpret_cast<uint4*>(hi)[e] = hs_bf16x8(v0, v1, sc); continue; }
+      uint4 h, l;
+      hs_split8(v0, v1, sc, h, l);
+      reinterpret_cast<uint4*>(hi)[e] = h;
+      reinterpret_cast<uint4*>(lo)[e] = l;
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = ch * 8 + j;

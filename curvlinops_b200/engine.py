@@ -10,6 +10,7 @@ import ctypes as C
 import itertools
 import math
 import os
+import weakref
 
 import torch
 from torch import Tensor
@@ -57,6 +58,30 @@ def loss_scale(loss_func, batch: int, classes: int) -> float:
 
 _program_serial = itertools.count()
 
+#: Layer programs are a function of (model, parameter selection, input shape / dtype) only: operators built
+#: repeatedly on the same module (a KFAC operator per optimisation step, the three operators of a comparison) share
+#: one trace.  Keyed on the identity AND the version counters of every tensor the module owns, so a module whose
+#: buffers / parameters were modified in place is traced again (constants are baked into the program).
+_CAPTURE_CACHE: dict = {}
+_CAPTURE_CACHE_MAX = 16
+
+
+def _cached_capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool) -> LayerProgram:
+    module = getattr(model_func, "module", None)
+    if not isinstance(module, torch.nn.Module):
+        return capture(model_func, params, X, fuse_relu=fuse_relu)
+    state = tuple((id(t), t._version) for t in itertools.chain(module.parameters(), module.buffers()))
+    key = (id(module), module.training, tuple(params), tuple(id(p) for p in params.values()), tuple(X.shape), X.dtype,
+           str(X.device), fuse_relu, state)
+    hit = _CAPTURE_CACHE.get(key)
+    if hit is not None and hit[0]() is module:
+        return hit[1]
+    lp = capture(model_func, params, X, fuse_relu=fuse_relu)
+    if len(_CAPTURE_CACHE) >= _CAPTURE_CACHE_MAX:
+        _CAPTURE_CACHE.pop(next(iter(_CAPTURE_CACHE)))
+    _CAPTURE_CACHE[key] = (weakref.ref(module), lp)
+    return lp
+
 
 class CompiledProgram:
     """A layer program planned for one (input shape, kmax, hessian) combination."""
@@ -65,8 +90,8 @@ class CompiledProgram:
         # `hessian` is the flag word of curv_program_create: 1 = R-op storage, 2 = KFAC scratch, 4 = bf16 arithmetic
         # traced in the parameters' dtype (the engine itself is handed fp32 copies of bf16 data)
         pdt = next(iter(params.values())).dtype if params else X.dtype
-        self.lp: LayerProgram = capture(model_func, params, X if X.dtype == pdt else X.to(pdt),
-                                        fuse_relu=not (int(hessian) & 1))
+        self.lp: LayerProgram = _cached_capture(model_func, params, X if X.dtype == pdt else X.to(pdt),
+                                                fuse_relu=not (int(hessian) & 1))
         self.kmax = kmax
         self.serial = next(_program_serial)  # CUDA-graph cache key (an id() could be reused after a rebuild)
         self.batch = X.shape[0]

@@ -224,6 +224,10 @@ class KFACComputer(CurvatureLinearOperator):
             for group in self._mapping:
                 p = self._params[next(iter(group.values()))]
                 G[tuple(group.values())] = torch.eye(p.shape[0], dtype=p.dtype, device=dev)
+        # the two triangles of a Gram matrix come from different tiles of the contraction kernel and agree to rounding
+        # only: hand out exactly symmetric factors (what they are mathematically)
+        A = {k: (v + v.T).mul_(0.5) for k, v in A.items()}
+        G = {k: (v + v.T).mul_(0.5) for k, v in G.items()}
         dt = self.dtype
         return ({k: with_fp32_master(v, dt) for k, v in A.items()}, {k: with_fp32_master(v, dt) for k, v in G.items()},
                 self._mapping)

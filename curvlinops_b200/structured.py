@@ -62,6 +62,11 @@ def _cuda_f32(t: Tensor, what: str) -> Tensor:
     return (t if m is None else m).to(torch.float32).contiguous()
 
 
+#: blocks with both sides at least this wide run on the tensor-core apply (``curv_kron_apply_tc``), smaller ones on the
+#: fp32 SIMT kernels
+TENSOR_CORE_MIN_DIM = 32
+
+
 def _stream(t: Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -131,10 +136,48 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
             return Y.reshape(-1, K).to(x.dtype)
         d_out, d_in = G.shape[0], A.shape[0]
         Y = torch.empty(d_out * d_in, K, device=x32.device, dtype=torch.float32)
+        if min(d_out, d_in) >= TENSOR_CORE_MIN_DIM:
+            # blocks of real networks: both contractions on the tcgen05 kernel; it takes the TRANSPOSED factors
+            # (symmetric ones as they are).  Operands as fp16 hi/lo planes (fp32-grade) for bf16 operators too: rows of
+            # a gradient covariance sum to ~0 against smooth vectors, and bf16-rounded operands (measured on ResNet-18:
+            # 4e-2 of the result) do not survive that cancellation; the apply is ~3 ms either way.
+            planes = 2
+            Gt, At = self._transposed(0, transpose), self._transposed(1, transpose)
+            for k0 in range(0, K, 8):
+                kk = min(8, K - k0)
+                xk = x32 if kk == K else x32[:, k0:k0 + kk].contiguous()
+                yk = Y if kk == K else torch.empty(d_out * d_in, kk, device=x32.device, dtype=torch.float32)
+                nbytes = capi.lib().curv_kron_apply_tc_workspace(d_out, d_in, kk, planes)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x32.device)
+                capi.check(capi.lib().curv_kron_apply_tc(Gt.data_ptr(), At.data_ptr(), d_out, d_in, kk, xk.data_ptr(),
+                                                         yk.data_ptr(), planes, ws.data_ptr(), nbytes, _stream(x32)))
+                if kk != K:
+                    Y[:, k0:k0 + kk] = yk
+            return Y.to(x.dtype)
         tmp = torch.empty_like(Y)
         capi.check(capi.lib().curv_kron_apply(G.data_ptr(), A.data_ptr(), d_out, d_in, K, x32.data_ptr(),
                                               Y.data_ptr(), tmp.data_ptr(), _stream(x32)))
         return Y.to(x.dtype)
+
+    def _transposed(self, index: int, adjoint: bool) -> Tensor:
+        """The factor the operator applies (``f``, or ``f^H`` for the adjoint product), TRANSPOSED, as a contiguous
+        fp32 matrix for ``curv_kron_apply_tc``: symmetric factors (Kronecker factors and their inverses) and the
+        adjoint case need no copy.  Cached per factor object / version."""
+        src = self._factors[index]
+        f32 = _cuda_f32(src, "Kronecker products")
+        if adjoint:
+            return f32
+        key = (index, id(src), src._version)
+        cache = self.__dict__.setdefault("_t_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            # EXACT symmetry only: an asymmetry at rounding level would be amplified by the cancellation inside the
+            # product (KFAC's computer symmetrises its factors; Cholesky inverses are symmetric by construction)
+            hit = f32 if torch.equal(f32, f32.T) else f32.T.contiguous()
+            for k in [k for k in cache if k[0] == index]:
+                del cache[k]
+            cache[key] = hit
+        return hit
 
     def _matmat(self, X: list[Tensor]) -> list[Tensor]:
         (x,) = X

@@ -179,6 +179,16 @@ int curv_eigh_apply(const float* Qg, const float* Qa, const float* lambda, float
                     int d_out, int d_in, int K, const float* X, float* Y, float* tmp, float* tmp2,
                     void* stream);
 
+/* The same two-sided product on the tcgen05 contraction kernel (csrc/kron_tc.cuh), for the block sizes of real
+   networks:  Y[d_out, d_in, K] = Gt^T . X . At  with the TRANSPOSED factors Gt = G^T [d_out,d_out], At = A^T
+   [d_in,d_in] (symmetric Kronecker factors and their damped inverses, kronecker.py:250-373, are their own
+   transposes; with eigenvector matrices as factors these are the rotations of eigh.py:98-104).  1 <= K <= 8.
+   planes = 2: fp32-grade (operands as fp16 hi/lo planes, three MMAs per product); planes = 1: bf16 operands (bf16
+   operators).  ws: caller-owned scratch of curv_kron_apply_tc_workspace(...) bytes. */
+size_t curv_kron_apply_tc_workspace(int d_out, int d_in, int K, int planes);
+int curv_kron_apply_tc(const float* Gt, const float* At, int d_out, int d_in, int K, const float* X, float* Y,
+                       int planes, void* ws, size_t ws_bytes, void* stream);
+
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major, hand-written kernels (no cuBLAS).  */
 int curv_gemm(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, void* stream);
