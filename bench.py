@@ -32,6 +32,11 @@ B, K = 128, 8
 WORKLOADS = {
     "c2": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, fp32", "f32"),
     "c2-bf16": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, bf16", "bf16"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case; pure latency (6.6 MFLOP per product)
+    "c1": ("3-layer MLP (D=64, 4 Linear+ReLU, CE loss), batch=32, HessianLinearOperator @ 1 vector", "f32"),
+    # BASELINE.json configs[2]: its own metric (a step = one factor build), printed as an extra line
+    "c3": ("ResNet-18 random-init, synthetic 128x3x224x224, KFACLinearOperator factor build (Conv2d/Linear params, "
+           "joint bias, MC Fisher 1 sample) + damped inverse 1e-3 + inverse apply @ 1 vector, bf16", "bf16"),
 }
 CONFIG = "c2"
 WORKLOAD = WORKLOADS[CONFIG][0]
@@ -198,6 +203,211 @@ def gpu_library_baseline(torch, dev, repeats=3):
     return out
 
 
+def kfac_problem(torch, batch, dtype, device):
+    model, X, y = build_problem(torch, batch)
+    model, X, y = model.to(device).to(dtype), X.to(device).to(dtype), y.to(device)
+    mods = dict(model.named_modules())
+    names = [n for n, m in mods.items() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+    params = {f"{n}.{pn}": p for n in names for pn, p in mods[n].named_parameters(recurse=False)}
+    return model, X, y, params
+
+
+def run_c1(torch, args):
+    """C1: Hessian-vector product of the 13 130-parameter MLP, one vector: latency (CUDA-graph replay of the R-op
+    sweeps) next to the reference on the host cores (its own protocol: minimum of 10, benchmark_execute.py:287-302)."""
+    from curvlinops_b200 import HessianLinearOperator, _capi as capi
+    from oracle.models import mlp_c1
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    model = mlp_c1()
+    X, y = torch.randn(32, 64), torch.randint(0, 10, (32,))
+    loss = torch.nn.CrossEntropyLoss()
+    md = mlp_c1().to(dev)
+    md.load_state_dict(model.state_dict())
+    params = dict(md.named_parameters())
+    P = sum(p.numel() for p in params.values())
+    H = HessianLinearOperator(md, loss, params, [(X.to(dev), y.to(dev))], check_deterministic=False)
+    torch.manual_seed(1)
+    v_host = torch.rand(P).pin_memory()
+    v = v_host.to(dev)
+    for _ in range(max(3, args.warmup) + 2):
+        H @ v
+    L0 = capi.lib().curv_launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 50)
+    e0.record()
+    for _ in range(steps):
+        H @ v
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = capi.lib().curv_launch_count() - L0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = (H @ v_host.to(dev, non_blocking=True)).cpu()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    line = {
+        "metric": "hessian_matvec_latency", "value": ms, "unit": "ms", "n_gpus": 1, "steps": steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "params": P, "columns": 1, "batch": 32,
+                   "l2": "latency-bound: the whole problem (13 130 parameters, 32 x 64 inputs) sits in L2; the product is "
+                         "one CUDA-graph replay of ~60 small launches"},
+        "gpu_launches": int(launches), "param_vec_per_s": P / (ms / 1e3),
+        "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": P * 4, "d2h_bytes_per_step": P * 4,
+                "what": "host vector in, host result out (wall clock, includes the synchronising download)"},
+        "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "6.6 MFLOP and ~0.2 MB per product: launch / latency territory, no roofline applies "
+                             "(SURVEY 8d)"},
+    }
+    if not args.no_cpu_baseline:
+        from oracle.build_ref import import_reference
+
+        ref = import_reference()
+        torch.set_num_threads(host_threads())
+        Hr = ref.HessianLinearOperator(model, loss, dict(model.named_parameters()), [(X, y)], check_deterministic=False)
+        vr = torch.rand(P)
+        Hr @ vr
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            Hr @ vr
+            ts.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": min(ts) * 1e3, "unit": "ms", "cores": torch.get_num_threads(),
+                                "kind": "reference", "sample": "the full C1 product, minimum of 10 after 1 warm-up"}
+    print(json.dumps(line))
+
+
+def run_c3(torch, args):
+    """C3: KFAC factor build (value), damped inverse, inverse apply; reference times beside (BASELINE.md section 4:
+    19.1 s / 4.43 s / 0.252 s on 8 CPU cores; the reference cannot invert in bf16, so its arms run in fp32)."""
+    import ctypes as C
+
+    from curvlinops_b200 import KFACLinearOperator, _capi as capi
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    model, X, y, params = kfac_problem(torch, B, torch.bfloat16, dev)
+    P = sum(p.numel() for p in params.values())
+    loss = torch.nn.CrossEntropyLoss()
+    kw = dict(fisher_type="mc", mc_samples=1, separate_weight_and_bias=False, check_deterministic=False, num_data=B)
+    build = lambda: KFACLinearOperator(model, loss, params, [(X, y)], **kw)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, r
+
+    for _ in range(max(3, args.warmup)):
+        build()
+    sampler = ClockSampler(0)
+    sampler.start()
+    L0 = capi.lib().curv_launch_count()
+    ms_build, Kop = timed(build, args.steps)
+    launches = capi.lib().curv_launch_count() - L0
+    clocks = sampler.stop()
+    ms_inv, Kinv = timed(lambda: Kop.inverse(damping=1e-3), 3)
+    torch.manual_seed(1)
+    v_host = torch.rand(P).to(torch.bfloat16).pin_memory()
+    out_host = torch.empty(P, dtype=torch.bfloat16).pin_memory()
+    v = v_host.to(dev)
+    Kinv @ v
+    ms_apply, _ = timed(lambda: Kinv @ v, 10)
+    # per-launch timing of the Gram contractions (class 1 = wgrad-type kernel) of one build
+    capi.lib().curv_profile_enable(1)
+    build()
+    torch.cuda.synchronize()
+    ms, fl, cnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+    capi.lib().curv_profile_read(ms, fl, cnt)
+    capi.lib().curv_profile_enable(0)
+    X_host, y_host = X.cpu().pin_memory(), y.cpu().pin_memory()
+
+    def e2e():  # host data in, preconditioned host vector out
+        Xd, yd = X_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)
+        Kd = KFACLinearOperator(model, loss, params, [(Xd, yd)], **kw).inverse(damping=1e-3)
+        out_host.copy_(Kd @ v_host.to(dev, non_blocking=True), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e()
+    ms_e2e, _ = timed(e2e, 2)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    gram_tf = (fl[1] / 1e12) / (ms[1] / 1e3) if ms[1] > 0 else 0.0
+    out = {
+        "metric": "kfac_factor_build_time", "value": ms_build, "unit": "ms", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_build, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "params": P, "batch": B, "factors": 42,
+                   "l2": "activations and patch planes (GBs) far exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "phases_ms": {"factor_build": ms_build, "damped_inverse_cusolver": ms_inv, "inverse_apply_1_vector": ms_apply,
+                      "note": "factor build and apply are this repo's kernels; the Cholesky factorisation / inversion "
+                              "of the 42 factors is torch.linalg (cuSOLVER), a stated library call"},
+        "e2e": {"value": ms_e2e, "unit": "ms", "what": "host X, y, v -> factor build -> damped inverse -> apply -> host",
+                "h2d_bytes_per_step": int(X_host.numel() * 2 + y_host.numel() * 8 + P * 2),
+                "d2h_bytes_per_step": int(P * 2)},
+        "roofline": {"bound": "tensor", "kernel": "wgrad_gemm_hs<1> as Gram kernel (A and G factors)",
+                     "achieved": gram_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gram_tf / peak_tf, "traffic": None,
+                     "launches_timed": int(cnt[1]), "share_of_step": ms[1] / ms_build,
+                     "note": "algorithmic Gram FLOPs 2 * rows * width^2 per factor (both triangles are computed: "
+                             "3.81 TFLOP per build, SURVEY 8d) / CUDA-event time of the launches",
+                     "step": {"algorithmic_tflop": 3.81, "tflops": 3.81 / (ms_build / 1e3)}},
+    }
+    if not args.no_cpu_baseline:
+        from oracle.build_ref import import_reference
+
+        ref = import_reference()
+        rkw = dict(fisher_type=ref.FisherType.MC, mc_samples=1, separate_weight_and_bias=False,
+                   check_deterministic=False, num_data=B)
+        try:  # second bar: the unmodified reference on this GPU (fp32: it cannot invert bf16 factors)
+            m32, X32, y32, p32 = kfac_problem(torch, B, torch.float32, dev)
+            rb = lambda: ref.KFACLinearOperator(m32, loss, p32, [(X32, y32)], **rkw)
+            rb()
+            t_b, Kr = timed(rb, 2)
+            t_i, Kri = timed(lambda: Kr.inverse(damping=1e-3), 2)
+            vr = torch.rand(P, device=dev)
+            Kri @ vr
+            t_a, _ = timed(lambda: Kri @ vr, 5)
+            out["gpu_library_baseline"] = {"what": "unmodified reference KFACLinearOperator on the same GPU (torch CUDA, "
+                                                   "fp32, hooks backend)", "factor_build_ms": t_b,
+                                           "damped_inverse_ms": t_i, "inverse_apply_ms": t_a}
+            del Kr, Kri, m32, X32
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.set_num_threads(host_threads())
+        sb = 16  # bounded CPU sample: the factor build is linear in the batch, inverse / apply do not depend on it
+        mc, Xc, yc, pc = kfac_problem(torch, sb, torch.float32, torch.device("cpu"))
+        t0 = time.perf_counter()
+        Kc = ref.KFACLinearOperator(mc, loss, pc, [(Xc, yc)], **{**rkw, "num_data": sb})
+        t1 = time.perf_counter()
+        Kci = Kc.inverse(damping=1e-3)
+        t2 = time.perf_counter()
+        vc = torch.rand(P)
+        Kci @ vc
+        t3 = time.perf_counter()
+        Kci @ vc
+        t4 = time.perf_counter()
+        out["cpu_baseline"] = {"value": (t1 - t0) * 1e3 * B / sb, "unit": "ms", "cores": torch.get_num_threads(),
+                               "kind": "reference",
+                               "sample": f"factor build on {sb} of {B} samples (fp32 on the CPU), extrapolated linearly; "
+                                         "inverse and apply at full size",
+                               "damped_inverse_ms": (t2 - t1) * 1e3, "inverse_apply_ms": (t4 - t3) * 1e3}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +425,10 @@ def main():
             os.environ.pop(v, None)
     import torch
 
+    if CONFIG in ("c1", "c3") and args.impl != "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            (run_c3 if CONFIG == "c3" else run_c1)(torch, args)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -14,6 +14,7 @@ slice of every mini-batch and the ``[P, K]`` result is summed with one NCCL all-
 from __future__ import annotations
 
 import copy
+import os
 from collections.abc import Callable, Iterable, MutableMapping
 
 import torch
@@ -277,11 +278,12 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         concatenations of the list format (``_torch_base.py:289-298,414-422``): the engine works on this layout."""
         return self._product(V.to(torch.float32).contiguous()).to(V.dtype)
 
-    def _local_batches(self, desc: str):
+    def _local_batches(self, desc: str, shard: tuple[int, int] | None = None):
         """Mini-batches as this rank processes them: ``(X, y, alpha, scales)`` on the operator's device.  With batch
         sharding on, only the rank's contiguous slice of each mini-batch is moved to the device (``X`` is ``None``
-        for a rank whose slice is empty); ``alpha`` and the loss-Hessian constants stay those of the GLOBAL batch."""
-        rank, world = cdist.rank_world()
+        for a rank whose slice is empty); ``alpha`` and the loss-Hessian constants stay those of the GLOBAL batch.
+        ``shard = (index, count)`` of the batch shard (default: rank / world)."""
+        rank, world = cdist.rank_world() if shard is None else shard
         dev = self.device
         for X, y in self._loop_over_data(desc=desc, to_device=(world == 1)):
             alpha = self._get_normalization_factor(X, y)
@@ -310,7 +312,10 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
     #: with batch sharding on: sum the [P, K] result in parameter buckets on a side stream, each bucket as soon as
     #: the backward sweep has finished its rows (it finishes the LAST parameters first), instead of one blocking
     #: all-reduce after the last kernel
-    OVERLAP_ALLREDUCE = True
+    #: (measured at 8 x B200, round 2: 15.9 ms with the overlap vs 14.8 ms with one blocking all-reduce after a
+    #: CUDA-graph replay -- the persistent contraction kernels own every SM with a static tile schedule, so NCCL's
+    #: CTAs delay whole kernels, and the streaming entry point cannot be graph-replayed.  Off by default.)
+    OVERLAP_ALLREDUCE = os.environ.get("CURV_OVERLAP_ALLREDUCE", "0") != "0"
 
     def _product(self, V: Tensor) -> Tensor:
         """``[P, K]`` fp32 -> ``[P, K]`` fp32: the loop over mini-batches (``_torch_base.py:937-944``)."""
@@ -319,8 +324,12 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         out = torch.zeros_like(V)
         rank, world = cdist.rank_world()
         K = V.shape[1]
-        overlap = (world > 1 and self.OVERLAP_ALLREDUCE and V.device.type == "cuda" and K <= MAX_COLUMNS_PER_SWEEP)
-        batches = iter(self._local_batches("_matmat"))
+        # 2-d sharding (batch x columns) from 4 ranks on, see dist.grid
+        n_bg, n_cg = cdist.grid(world, K)
+        cols = None if n_cg == 1 else ((rank % n_cg) * (K // n_cg), K // n_cg)
+        overlap = (world > 1 and self.OVERLAP_ALLREDUCE and V.device.type == "cuda" and K <= MAX_COLUMNS_PER_SWEEP
+                   and cols is None)
+        batches = iter(self._local_batches("_matmat", None if world == 1 else (rank // n_cg, n_bg)))
         cur = next(batches, None)
         reduced = False
         while cur is not None:
@@ -331,7 +340,7 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
                     self._last_batch_with_overlapped_all_reduce(X, y, V, out, alpha, scales)
                     reduced = True
                 elif X is not None:
-                    self._batch_call_sharded(X, y, V, out, alpha, scales)
+                    self._batch_call_sharded(X, y, V, out, alpha, scales, **({} if cols is None else {"cols": cols}))
             else:
                 if not isinstance(X, Tensor):
                     raise NotImplementedError("The B200 engine needs tensor inputs X.")
@@ -369,9 +378,15 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         main.wait_stream(comm)
         out.record_stream(comm)
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
+    @staticmethod
+    def _shard_kw(out_done, cols) -> dict:
         kw = {} if out_done is None else {"out_done": out_done}
-        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0], **kw)
+        if cols is not None:
+            kw["cols"] = cols
+        return kw
+
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None, cols=None):
+        self._engine.matmat_batch(self.KIND, X, y, V, out, alpha, scale=scale[0], **self._shard_kw(out_done, cols))
 
     # ---- host-resident operands: pipelined upload / download ----------------------------------------
     #: a kind whose mini-batch product is one engine call with (X, y, V, out) only may stream
@@ -524,11 +539,13 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
                 stage.copy_(V[lo:hi], non_blocking=True)
                 part[: hi - lo].copy_(stage)
             cdist.all_gather_rows(Vd, part)
-        batches = list(self._local_batches("matmat_pinned"))
+        n_bg, n_cg = cdist.grid(world, K)
+        cols = None if n_cg == 1 else ((rank % n_cg) * (K // n_cg), K // n_cg)
+        batches = list(self._local_batches("matmat_pinned", (rank // n_cg, n_bg)))
         main.wait_stream(s_in)
         for X, y, alpha, scales in batches:
             if X is not None:
-                self._batch_call_sharded(X, y, Vd[:Pn], outd[:Pn], alpha, scales)
+                self._batch_call_sharded(X, y, Vd[:Pn], outd[:Pn], alpha, scales, cols=cols)
         res = torch.empty(chunk, K, dtype=torch.float32, device=dev)
         cdist.reduce_scatter_rows(res, outd)
         if hi > lo:
@@ -597,12 +614,12 @@ class GGNLinearOperator(CurvatureLinearOperator):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
                                   scale=self._mc_scale(X.shape[0]))
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None, cols=None):
         if self._mc_samples == 0:
-            return super()._batch_call_sharded(X, y, V, out, alpha, scale, out_done=out_done)
+            return super()._batch_call_sharded(X, y, V, out, alpha, scale, out_done=out_done, cols=cols)
         g = self._engine.mc_grad_outputs(X, self._mc_samples)
-        kw = {} if out_done is None else {"out_done": out_done}
-        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1], **kw)
+        self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1],
+                                  **self._shard_kw(out_done, cols))
 
 
 class EFLinearOperator(CurvatureLinearOperator):
@@ -646,10 +663,9 @@ class EFLinearOperator(CurvatureLinearOperator):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
                                   scale=loss_scale(self._loss_func, X.shape[0], g.shape[-1]))
 
-    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None):
-        kw = {} if out_done is None else {"out_done": out_done}
+    def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None, cols=None):
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=self._grad_outputs(X, y),
-                                  scale=scale[0], **kw)
+                                  scale=scale[0], **self._shard_kw(out_done, cols))
 
 
 class HessianLinearOperator(CurvatureLinearOperator):

@@ -31,6 +31,18 @@ def rank_world() -> tuple[int, int]:
     return 0, 1
 
 
+def grid(world: int, K: int) -> tuple[int, int]:
+    """``(batch groups, column groups)`` of the 2-d sharding of one product over ``world`` ranks.  Rank ``r`` takes
+    batch shard ``r // column_groups`` and the columns of group ``r % column_groups``; the one all-reduce of ``[P, K]``
+    then sums over the batch groups and fills in the other groups' columns (they are zero on this rank).  Splitting
+    the columns as well keeps twice the samples per rank (fuller tiles) and halves the per-product work that does not
+    depend on the batch (packing the K tangent weights, split-K finishes); it costs one extra primal forward per column
+    group (+3 % FLOPs for K = 8), so it is only used from 4 ranks on and keeps at least 4 columns per rank (the
+    multi-slot weight-gradient kernel multiplies 4 slots per MMA)."""
+    cg = 2 if (world >= 4 and world % 2 == 0 and K % 2 == 0 and K // 2 >= 4) else 1
+    return world // cg, cg
+
+
 def shard_bounds(batch: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous slice ``[lo, hi)`` of a mini-batch owned by ``rank`` (sizes differ by at most 1)."""
     base, rem = divmod(batch, world)

@@ -205,19 +205,22 @@ class Engine:
     # -- the hot call ----------------------------------------------------------------------------
     def matmat_batch(self, kind: int, X: Tensor, y: Tensor | None, V: Tensor, out: Tensor, alpha: float,
                      mc_grad: Tensor | None = None, scale: float | None = None,
-                     v_ready: list | None = None, out_done: list | None = None) -> None:
+                     v_ready: list | None = None, out_done: list | None = None,
+                     cols: tuple[int, int] | None = None) -> None:
         """``out += alpha * (mini-batch matrix) @ V`` with ``V``/``out`` flat ``[P, K]`` fp32 on device.
 
         ``v_ready`` / ``out_done``: optional per-parameter ``torch.cuda.Event`` lists (entries may be ``None``) for
         the streaming entry point ``curv_matmat_batch_sync`` (see ``include/curvb200.h``); needs ``K`` columns
-        that fit one sweep."""
+        that fit one sweep.  ``cols = (first, count)``: only these columns of ``V`` / ``out`` are processed (2-d
+        sharding over ranks: batch x columns)."""
         self._check_supported()
         with torch.cuda.device(X.device if X.device.type == "cuda" else V.device):
-            self._matmat_batch(kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done)
+            self._matmat_batch(kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done, cols)
 
-    def _matmat_batch(self, kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done) -> None:
+    def _matmat_batch(self, kind, X, y, V, out, alpha, mc_grad, scale, v_ready, out_done, cols=None) -> None:
         K = V.shape[-1]
-        kc = min(K, MAX_COLUMNS_PER_SWEEP)
+        c0, cn = (0, K) if cols is None else cols
+        kc = min(cn, MAX_COLUMNS_PER_SWEEP)
         X = X.to(torch.float32).contiguous()
         prog = self.program(X, kc, kind == capi.KIND_HESSIAN)
         ws = self.workspace(prog.ws_bytes, X.device)
@@ -254,8 +257,8 @@ class Engine:
             return
 
         def launch(Vt: Tensor, outt: Tensor, strm: int) -> None:
-            for k0 in range(0, K, kc):
-                kk = min(kc, K - k0)
+            for k0 in range(c0, c0 + cn, kc):
+                kk = min(kc, c0 + cn - k0)
                 capi.check(capi.lib().curv_matmat_batch(
                     prog.handle, kind, loss, pptrs, prog.const_ptrs, X.data_ptr(),
                     0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
@@ -270,7 +273,7 @@ class Engine:
         # The graph is keyed on every pointer it bakes in - including V and out: in steady state the caching
         # allocator hands a caller that builds V / out per product the same blocks again, so replays need no
         # staging copies; a different address is simply another key (eager first, captured on its second sighting).
-        key = (prog.serial, kind, loss, K, float(scale or 1.0), float(alpha), X.data_ptr(),
+        key = (prog.serial, kind, loss, K, c0, cn, float(scale or 1.0), float(alpha), X.data_ptr(),
                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
                tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg, V.data_ptr(), out.data_ptr())
         entry = self._graphs.get(key)

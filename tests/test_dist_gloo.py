@@ -28,13 +28,14 @@ class _FakeEngine:
     def __init__(self, W):
         self.W = W
 
-    def matmat_batch(self, kind, X, y, V, out, alpha, mc_grad=None, scale=None):
+    def matmat_batch(self, kind, X, y, V, out, alpha, mc_grad=None, scale=None, cols=None):
         o, i = self.W.shape
         if scale is None:
             scale = 1.0 / (X.shape[0] * o)
         A = X.T @ X  # [i, i]
-        Vm = V.reshape(o, i, -1)
-        out += (alpha * 2.0 * scale) * torch.einsum("ij,ojk->oik", A, Vm).reshape(o * i, -1)
+        c0, cn = (0, V.shape[1]) if cols is None else cols
+        Vm = V[:, c0:c0 + cn].reshape(o, i, -1)
+        out[:, c0:c0 + cn] += (alpha * 2.0 * scale) * torch.einsum("ij,ojk->oik", A, Vm).reshape(o * i, -1)
 
     def _check_supported(self):
         pass
@@ -49,7 +50,7 @@ def _worker(rank, world, port, ret):
         torch.manual_seed(0)
         W = torch.rand(3, 5)
         data = [(torch.rand(7, 5), torch.rand(7, 3)), (torch.rand(4, 5), torch.rand(4, 3))]
-        V = torch.rand(15, 2)
+        V = torch.rand(15, 8 if world == 4 else 2)  # world 4, K = 8: 2-d sharding (2 batch groups x 2 column groups)
 
         def build():
             op = GGNLinearOperator.__new__(GGNLinearOperator)
@@ -79,12 +80,19 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_sharded_matmat_equals_single_process():
+def test_grid():
+    assert cdist.grid(1, 8) == (1, 1) and cdist.grid(2, 8) == (2, 1)
+    assert cdist.grid(4, 8) == (2, 2) and cdist.grid(8, 8) == (4, 2)
+    assert cdist.grid(8, 4) == (8, 1) and cdist.grid(8, 1) == (8, 1) and cdist.grid(5, 8) == (5, 1)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_matmat_equals_single_process(world):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    port = 29500 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 1000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
