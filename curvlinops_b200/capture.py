@@ -7,9 +7,13 @@ KFAC IO collector uses, ``curvlinops/computers/io_collector/collector.py:107``) 
 the fixed op set the CUDA kernels implement.  Anything outside that set raises
 ``NotImplementedError`` -- there is no autograd / CPU fallback.
 
-Supported ATen ops: convolution (groups=1, dilation=1), addmm / mm (+t) i.e. ``nn.Linear`` on 2-d
-inputs, native_batch_norm in eval mode, relu / sigmoid / tanh, add.Tensor (residual), max_pool2d,
-mean over (H, W) / adaptive_avg_pool2d(1), view / flatten / reshape between 4-d and 2-d, detach.
+Supported ATen ops: convolution (groups=1, dilation=1), addmm / mm (+t) i.e. ``nn.Linear`` on 2-d inputs and on
+token sequences ``[B, T, D]`` (a 1x1 convolution over the tokens), native_batch_norm in eval mode, native_layer_norm
+over the last dimension of ``[B, D]`` / ``[B, T, D]`` tensors, relu / sigmoid / tanh / gelu (exact), add.Tensor
+(residual), max_pool2d, mean over (H, W) or over the tokens / adaptive_avg_pool2d(1), view / flatten / reshape
+between 4-d and 2-d and between ``[B, T, D]`` and ``[B*T, D]``, detach.
+
+Activations are stored channels-last (``[B, H, W, C]``); a token sequence ``[B, T, D]`` is the map H = 1, W = T, C = D.
 """
 
 from __future__ import annotations
@@ -37,6 +41,7 @@ class LayerProgram:
     bias_nodes: dict = field(default_factory=dict)  # bias param name -> node index
     out_features: int = 0
     tied: set = field(default_factory=set)  # parameters used by more than one layer
+    tokens_input: bool = False  # the network input is a token sequence [B, T, D] (handed to the engine as [B, D, 1, T])
 
     def add_value(self, C, H, W, tan):
         self.values.append([int(C), int(H), int(W), bool(tan)])
@@ -75,9 +80,9 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
     tensor the function touches becomes a constant, exactly like ``functional_call`` falls back to the
     module's own parameters and buffers (reference ``curvlinops/utils.py:267-297``).
     """
-    if not isinstance(X, Tensor) or X.ndim not in (2, 4):
+    if not isinstance(X, Tensor) or X.ndim not in (2, 3, 4):
         raise NotImplementedError(
-            f"The B200 engine supports tensor inputs of shape [B, C] or [B, C, H, W]; got {type(X).__name__}"
+            f"The B200 engine supports tensor inputs of shape [B, C], [B, T, C] or [B, C, H, W]; got {type(X).__name__}"
             + (f" {tuple(X.shape)}" if isinstance(X, Tensor) else "") + "."
         )
     names = list(params.keys())
@@ -99,10 +104,21 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
     xin = placeholders[-1]
     if X.ndim == 4:
         v = prog.add_value(X.shape[1], X.shape[2], X.shape[3], False)
+    elif X.ndim == 3:  # tokens [B, T, D]: already channels-last, the engine reads it as [B, D, 1, T] NCHW ... see below
+        v = prog.add_value(X.shape[2], 1, X.shape[1], False)
     else:
         v = prog.add_value(X.shape[1], 1, 1, False)
     prog.add_node(capi.OP_INPUT, out=v)
-    env[xin] = _Ref("act", value=v, flat=False)
+    prog.tokens_input = X.ndim == 3
+    env[xin] = _Ref("act", value=v, flat=False, tok=3 if X.ndim == 3 else None)
+    Bsz = int(X.shape[0])
+
+    def tok_of(ref):
+        """None: [B, C, H, W] / [B, C] tensor; 3: token sequence [B, T, D]; 2: its [B*T, D] view."""
+        return getattr(ref, "tok", None)
+
+    def like(xr, value):
+        return _Ref("act", value=value, flat=xr.flat, tok=tok_of(xr))
 
     # liveness: only lower nodes the output depends on
     out_node = [n for n in gm.graph.nodes if n.op == "output"][0]
@@ -180,6 +196,14 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         w = wref.base
         C, H, W, _ = shape_of(xr)
         wshape = w.shape if w.kind == "param" else tuple(w.tensor.shape)
+        if tok_of(xr) == 2:  # Linear applied to every token: a 1x1 convolution over the [1, T] token map
+            if len(wshape) != 2 or wshape[1] != C:
+                unsupported(node, f"weight shape {wshape} does not match token features {C}")
+            out = emit_conv(node, xr, w, bref, 1, 1, 1, 1, 0, 0, wshape[0], H, W)
+            out.tok = 2
+            return out
+        if tok_of(xr) == 3:
+            unsupported(node, "matmul on a [B, T, D] tensor that was not flattened to [B*T, D]")
         if len(wshape) != 2 or wshape[1] != C * H * W:
             unsupported(node, f"weight shape {wshape} does not match input features {C * H * W}")
         if (H, W) != (1, 1) and not xr.flat:
@@ -206,8 +230,8 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             env[node] = _Ref(a[0].kind + "T", base=a[0])
         elif t == aten.convolution.default:
             xr, wref, bref, stride, padding, dilation, transposed, _outpad, groups = a
-            if xr.kind != "act" or transposed or groups != 1 or _pair(dilation) != (1, 1):
-                unsupported(node, "only plain 2-d convolutions (groups=1, dilation=1)")
+            if xr.kind != "act" or transposed or groups != 1 or _pair(dilation) != (1, 1) or tok_of(xr):
+                unsupported(node, "only plain 2-d convolutions (groups=1, dilation=1) of [B, C, H, W] tensors")
             wshape = wref.shape if wref.kind == "param" else tuple(wref.tensor.shape)
             if len(wshape) != 4:
                 unsupported(node, "only 2-d convolutions")
@@ -236,6 +260,8 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
                 xr, wref, bref, rm, rv, training, _mom, eps = a
             else:
                 xr, wref, bref, rm, rv, training, _mom, eps = a
+            if tok_of(xr):
+                unsupported(node, "BatchNorm on a token sequence")
             if training or rm is None or rv is None:
                 raise NotImplementedError(
                     "BatchNorm in training mode couples the samples of a mini-batch; put the model in"
@@ -254,6 +280,24 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             if src.kind != "tuple":
                 unsupported(node)
             env[node] = src.items[idx]
+        elif t == aten.native_layer_norm.default:
+            xr, nshape, wref, bref, eps = a
+            C, H, W, _ = shape_of(xr)
+            if xr.kind != "act" or [int(d) for d in nshape] != [C] or (tok_of(xr) is None and (H, W) != (1, 1)):
+                unsupported(node, "LayerNorm over anything but the last dimension of a [B, D] / [B, T, D] tensor")
+            p0, c0 = weight_slots(wref)
+            p1, c1 = weight_slots(bref)
+            ov = prog.add_value(C, H, W, tan_of(xr) or p0 >= 0 or p1 >= 0)
+            prog.add_node(capi.OP_LAYERNORM, in0=xr.value, out=ov, p0=p0, p1=p1, c0=c0, c1=c1, eps=float(eps))
+            env[node] = _Ref("tuple", items=[like(xr, ov), None, None])
+        elif t == aten.gelu.default:
+            xr = a[0]
+            if node.kwargs.get("approximate", "none") != "none" or (len(a) > 1 and a[1] != "none"):
+                unsupported(node, "only the exact (erf) GELU")
+            C, H, W, tan = shape_of(xr)
+            ov = prog.add_value(C, H, W, tan)
+            prog.add_node(capi.OP_GELU, in0=xr.value, out=ov)
+            env[node] = like(xr, ov)
         elif t in (aten.relu.default, aten.sigmoid.default, aten.tanh.default):
             xr = a[0]
             src = node.args[0]
@@ -261,26 +305,28 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             if (fuse_relu and t == aten.relu.default and prod is not None and readers.get(alias_root(src), 0) == 1
                     and prog.nodes[prod]["op"] in (capi.OP_AFFINE, capi.OP_ADD) and prog.nodes[prod]["kh"] != 2):
                 prog.nodes[prod]["kh"] = 2  # fused: the producing node now writes relu(...)
-                env[node] = _Ref("act", value=xr.value, flat=xr.flat)
+                env[node] = like(xr, xr.value)
                 continue
             op = {aten.relu.default: capi.OP_RELU, aten.sigmoid.default: capi.OP_SIGMOID,
                   aten.tanh.default: capi.OP_TANH}[t]
             C, H, W, tan = shape_of(xr)
             ov = prog.add_value(C, H, W, tan)
             prog.add_node(op, in0=xr.value, out=ov)
-            env[node] = _Ref("act", value=ov, flat=xr.flat)
+            env[node] = like(xr, ov)
         elif t == aten.add.Tensor:
             xr, yr = a[0], a[1]
             alpha = node.kwargs.get("alpha", 1)
             if not (isinstance(xr, _Ref) and isinstance(yr, _Ref) and xr.kind == yr.kind == "act") \
-                    or alpha != 1 or shape_of(xr)[:3] != shape_of(yr)[:3]:
+                    or alpha != 1 or shape_of(xr)[:3] != shape_of(yr)[:3] or tok_of(xr) != tok_of(yr):
                 unsupported(node, "only additions of two activations of equal shape")
             C, H, W, _ = shape_of(xr)
             ov = prog.add_value(C, H, W, tan_of(xr, yr))
             prog.add_node(capi.OP_ADD, in0=xr.value, in1=yr.value, out=ov)
-            env[node] = _Ref("act", value=ov, flat=xr.flat)
+            env[node] = like(xr, ov)
         elif t == aten.max_pool2d_with_indices.default:
             xr = a[0]
+            if tok_of(xr):
+                unsupported(node, "pooling windows on a token sequence")
             ks = _pair(a[1])
             st = _pair(a[2]) if len(a) > 2 and a[2] else ks
             pd = _pair(a[3]) if len(a) > 3 else (0, 0)
@@ -296,7 +342,13 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         elif t in (aten.mean.dim, aten._adaptive_avg_pool2d.default, aten.adaptive_avg_pool2d.default):
             xr = a[0]
             C, H, W, tan = shape_of(xr)
-            if t == aten.mean.dim:
+            if t == aten.mean.dim and tok_of(xr) == 3:
+                if sorted(d % 3 for d in a[1]) != [1] or (len(a) > 2 and a[2]):
+                    unsupported(node, "mean of a [B, T, D] tensor over anything but the tokens")
+                keep = False
+            elif tok_of(xr):
+                unsupported(node, "pooling of a flattened token sequence")
+            elif t == aten.mean.dim:
                 dims = sorted(d % 4 for d in a[1])
                 if dims != [2, 3]:
                     unsupported(node, "mean over dims other than (H, W)")
@@ -317,7 +369,14 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             oshape = tuple(node.meta["val"].shape) if "val" in node.meta else None
             if oshape is None:
                 unsupported(node, "missing shape metadata")
-            if len(oshape) == 2 and oshape[1] == C * H * W:
+            if tok_of(xr):  # token sequences: [B, T, D] <-> [B*T, D]
+                if len(oshape) == 2 and tuple(oshape) == (Bsz * W, C):
+                    env[node] = _Ref("act", value=xr.value, flat=False, tok=2)
+                elif len(oshape) == 3 and tuple(oshape) == (Bsz, W, C):
+                    env[node] = _Ref("act", value=xr.value, flat=False, tok=3)
+                else:
+                    unsupported(node, f"reshape of a token sequence to {tuple(oshape)}")
+            elif len(oshape) == 2 and oshape[1] == C * H * W:
                 env[node] = _Ref("act", value=xr.value, flat=True)
             elif len(oshape) == 4 and tuple(oshape[1:]) == (C, H, W):
                 env[node] = _Ref("act", value=xr.value, flat=False)

@@ -10,7 +10,7 @@
 
 namespace curv {
 
-enum ActKind { ACT_RELU = 0, ACT_SIGMOID = 1, ACT_TANH = 2 };
+enum ActKind { ACT_RELU = 0, ACT_SIGMOID = 1, ACT_TANH = 2, ACT_GELU = 3 };  // GELU: exact (erf) form
 
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
@@ -140,6 +140,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, long long es, 
     if (n < N && c < C) v = __ldg(src + (((long long)n * C + c) * taps + tap) * es);
     dst[i] = v;
   }
+}
+
+// dst[i] = i < n ? v : 0 for i < np
+__global__ void fill_kernel(float* __restrict__ dst, int n, float v, int np) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) dst[i] = i < n ? v : 0.f;
 }
 
 // vector [n] (element stride es) -> dst[k][Np] zero padded.  grid.y = k
@@ -283,16 +288,21 @@ __global__ void __launch_bounds__(256, PLANES ? 3 : 4) affine_fwd_kernel(const f
 __device__ __forceinline__ float act_apply(int kind, float x) {
   if (kind == ACT_RELU) return fmaxf(x, 0.f);
   if (kind == ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  if (kind == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
   return tanhf(x);
 }
-// derivative expressed through the OUTPUT y = phi(x)
+// derivative expressed through the OUTPUT y = phi(x) -- except GELU, whose derivatives take the INPUT x (the callers
+// hand these functions the primal input for that kind)
 __device__ __forceinline__ float act_d1(int kind, float y) {
+  if (kind == ACT_GELU)  // Phi(x) + x phi(x)
+    return 0.5f * (1.f + erff(y * 0.70710678118654752f)) + y * 0.3989422804014327f * expf(-0.5f * y * y);
   if (kind == ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (kind == ACT_SIGMOID) return y * (1.f - y);
   return 1.f - y * y;
 }
 __device__ __forceinline__ float act_d2(int kind, float y) {
   if (kind == ACT_RELU) return 0.f;
+  if (kind == ACT_GELU) return 0.3989422804014327f * expf(-0.5f * y * y) * (2.f - y * y);  // phi(x) (2 - x^2)
   if (kind == ACT_SIGMOID) return y * (1.f - y) * (1.f - 2.f * y);
   return -2.f * y * (1.f - y * y);
 }
@@ -303,7 +313,7 @@ __global__ void act_fwd_kernel(int kind, const float* __restrict__ x, long long 
                                float* __restrict__ y, long long y_slot, long long n4, int slot0) {
   const int slot = slot0 + blockIdx.y;
   const float4* xs = reinterpret_cast<const float4*>(x + slot * x_slot);
-  const float4* y0 = reinterpret_cast<const float4*>(y);
+  const float4* y0 = reinterpret_cast<const float4*>(kind == ACT_GELU ? x : y);  // what act_d1 is evaluated at
   float4* yo = reinterpret_cast<float4*>(y + slot * y_slot);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -748,6 +758,171 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(
   if (amax) block_absmax_commit(am, amax + slot);
 }
 
+// ------------------------------------------------------------------ LayerNorm over the channels of a pixel / token
+//   xhat = (x - mean) * rstd,  y_0 = gamma xhat + beta
+//   y_k  = gamma * rstd (xdot_k - mean(xdot_k) - xhat mean(xhat xdot_k)) + gammadot_k xhat + betadot_k
+// One warp per row (channel reductions by warp shuffles), Cp <= 1024: lane l holds channels 4 l + 128 j.
+// coef [(1+K)][2][Cp]: slot 0 = (gamma, beta), slot k = (gammadot_k, betadot_k); aux [rows][2] = (mean, rstd).
+constexpr int LN_MAXJ = 8;
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long x_slot, int x_has_slots,
+                                                          const float* __restrict__ coef, int coef_has_tan,
+                                                          float* __restrict__ y, long long y_slot, float* __restrict__ aux,
+                                                          long long rows, int C, int Cp, float eps, int nslots) {
+  const int lane = threadIdx.x & 31;
+  const int nj = (Cp + 127) / 128;
+  const float invC = 1.f / (float)C;
+  for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
+    float4 xh[LN_MAXJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      const int c = lane * 4 + 128 * j;
+      xh[j] = (j < nj && c < Cp) ? __ldg(reinterpret_cast<const float4*>(x + r * Cp + c)) : f4zero();
+      s += (xh[j].x + xh[j].y) + (xh[j].z + xh[j].w);  // pad lanes hold zeros
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      const int c = lane * 4 + 128 * j;
+      if (j < nj && c < Cp) {
+        float4 d = make_float4(c < C ? xh[j].x - mean : 0.f, c + 1 < C ? xh[j].y - mean : 0.f,
+                               c + 2 < C ? xh[j].z - mean : 0.f, c + 3 < C ? xh[j].w - mean : 0.f);
+        xh[j] = d;
+        q += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    if (lane == 0) { aux[2 * r] = mean; aux[2 * r + 1] = rstd; }
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      const int c = lane * 4 + 128 * j;
+      if (j < nj && c < Cp) {
+        xh[j] = make_float4(xh[j].x * rstd, xh[j].y * rstd, xh[j].z * rstd, xh[j].w * rstd);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(coef + c)), b = __ldg(reinterpret_cast<const float4*>(coef + Cp + c));
+        *reinterpret_cast<float4*>(y + r * Cp + c) = f4fma(g, xh[j], b);
+      }
+    }
+    for (int k = 1; k < nslots; ++k) {
+      float4 xd[LN_MAXJ];
+      float m1 = 0.f, m2 = 0.f;
+      if (x_has_slots) {
+#pragma unroll
+        for (int j = 0; j < LN_MAXJ; ++j) {
+          const int c = lane * 4 + 128 * j;
+          xd[j] = (j < nj && c < Cp) ? __ldg(reinterpret_cast<const float4*>(x + k * x_slot + r * Cp + c)) : f4zero();
+          m1 += (xd[j].x + xd[j].y) + (xd[j].z + xd[j].w);
+          m2 += (xd[j].x * xh[j].x + xd[j].y * xh[j].y) + (xd[j].z * xh[j].z + xd[j].w * xh[j].w);
+        }
+        m1 = warp_sum(m1) * invC;
+        m2 = warp_sum(m2) * invC;
+      }
+#pragma unroll
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = lane * 4 + 128 * j;
+        if (j < nj && c < Cp) {
+          float4 o = f4zero();
+          if (x_has_slots) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(coef + c));
+            o = make_float4(c < C ? g.x * rstd * (xd[j].x - m1 - xh[j].x * m2) : 0.f,
+                            c + 1 < C ? g.y * rstd * (xd[j].y - m1 - xh[j].y * m2) : 0.f,
+                            c + 2 < C ? g.z * rstd * (xd[j].z - m1 - xh[j].z * m2) : 0.f,
+                            c + 3 < C ? g.w * rstd * (xd[j].w - m1 - xh[j].w * m2) : 0.f);
+          }
+          if (coef_has_tan) {
+            const float* ck = coef + (long long)k * 2 * Cp;
+            o = f4add(o, f4fma(__ldg(reinterpret_cast<const float4*>(ck + c)), xh[j],
+                               __ldg(reinterpret_cast<const float4*>(ck + Cp + c))));
+          }
+          *reinterpret_cast<float4*>(y + k * y_slot + r * Cp + c) = o;
+        }
+      }
+    }
+  }
+}
+
+// gx_k (+)= rstd (gh - mean(gh) - xhat mean(gh xhat)),  gh = gamma gy_k;  partial[chunk][k][0][c] = sum_rows gy_k xhat
+// (gamma grad), partial[chunk][k][1][c] = sum_rows gy_k (beta grad).  grid = (chunks, slots), 8 warps = 8 rows at a time
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ gy, long long gy_slot,
+                                                          const float* __restrict__ x0, const float* __restrict__ aux,
+                                                          const float* __restrict__ coef, float* __restrict__ gx,
+                                                          long long gx_slot, int write_gx, int accumulate,
+                                                          float* __restrict__ partial, int want_partial, long long rows,
+                                                          int C, int Cp, int rows_per_cta, int slot0, int nslots) {
+  __shared__ float red[2 * 1024];  // [2][Cp]: the warps add their parameter partials one after the other (fixed order)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nj = (Cp + 127) / 128;
+  const float invC = 1.f / (float)C;
+  const int k = blockIdx.y, slot = slot0 + k;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float4 pg[LN_MAXJ], pb[LN_MAXJ];
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; ++j) { pg[j] = f4zero(); pb[j] = f4zero(); }
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    const float mean = aux[2 * r], rstd = aux[2 * r + 1];
+    float4 xh[LN_MAXJ], gh[LN_MAXJ];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; ++j) {
+      const int c = lane * 4 + 128 * j;
+      if (j < nj && c < Cp) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + r * Cp + c));
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gy + slot * gy_slot + r * Cp + c));
+        xh[j] = make_float4(c < C ? (xv.x - mean) * rstd : 0.f, c + 1 < C ? (xv.y - mean) * rstd : 0.f,
+                            c + 2 < C ? (xv.z - mean) * rstd : 0.f, c + 3 < C ? (xv.w - mean) * rstd : 0.f);
+        pg[j] = f4fma(g, xh[j], pg[j]);
+        pb[j] = f4add(pb[j], g);
+        gh[j] = f4mul(__ldg(reinterpret_cast<const float4*>(coef + c)), g);
+        m1 += (gh[j].x + gh[j].y) + (gh[j].z + gh[j].w);
+        m2 += (gh[j].x * xh[j].x + gh[j].y * xh[j].y) + (gh[j].z * xh[j].z + gh[j].w * xh[j].w);
+      } else { xh[j] = f4zero(); gh[j] = f4zero(); }
+    }
+    m1 = warp_sum(m1) * invC;
+    m2 = warp_sum(m2) * invC;
+    if (write_gx) {
+#pragma unroll
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = lane * 4 + 128 * j;
+        if (j < nj && c < Cp) {
+          float4 o = make_float4(c < C ? rstd * (gh[j].x - m1 - xh[j].x * m2) : 0.f,
+                                 c + 1 < C ? rstd * (gh[j].y - m1 - xh[j].y * m2) : 0.f,
+                                 c + 2 < C ? rstd * (gh[j].z - m1 - xh[j].z * m2) : 0.f,
+                                 c + 3 < C ? rstd * (gh[j].w - m1 - xh[j].w * m2) : 0.f);
+          float4* dst = reinterpret_cast<float4*>(gx + slot * gx_slot + r * Cp + c);
+          if (accumulate) o = f4add(o, *dst);
+          *dst = o;
+        }
+      }
+    }
+  }
+  if (!want_partial) return;
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < LN_MAXJ; ++j) {
+        const int c = lane * 4 + 128 * j;
+        if (j < nj && c < Cp) {
+          float4* a = reinterpret_cast<float4*>(red + c);
+          float4* b = reinterpret_cast<float4*>(red + 1024 + c);
+          *a = w == 0 ? pg[j] : f4add(*a, pg[j]);
+          *b = w == 0 ? pb[j] : f4add(*b, pb[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = partial + ((long long)blockIdx.x * nslots + k) * 2 * Cp;  // [chunk][k][which][c]
+  for (int e = threadIdx.x; e < 2 * Cp; e += blockDim.x) {
+    const int which = e / Cp, c = e - which * Cp;
+    dst[e] = red[which * 1024 + c];
+  }
+}
+
 // out[(off + c)*ldk + k0 + k] += alpha * sum_chunks partial[chunk][k][which][c]
 // (slot indices kskip .. nslots-1 of the partial buffer map to columns 0 .. nslots-kskip-1)
 __global__ void vec_grad_finish_kernel(const float* __restrict__ partial, int nchunks, int nslots,
@@ -777,26 +952,54 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nspli
                                     long long off, int ldk, int k0, float alpha) {
   // block = (32 weight elements, nslots - kskip columns): a warp reads 128 contiguous bytes of one slot's
   // partial per split; the splits are summed in a fixed order with four independent chains (deterministic).
+  // The 32 x nk sums are transposed through shared memory so that the K-minor rows of `out` are updated with
+  // 16-byte read-modify-writes (one row = nk consecutive floats) instead of nk scattered 4-byte ones.
+  __shared__ float tile[32][33];
   const long long per = (long long)N * taps * Cp;
+  const int nk = blockDim.y;
   const int k = kskip + threadIdx.y;
   const long long stride = (long long)nslots * per;
-  for (long long i = blockIdx.x * 32LL + threadIdx.x; i < per; i += (long long)gridDim.x * 32) {
-    int c = (int)(i % Cp);
-    if (c >= C) continue;
-    long long r = i / Cp;
-    int tap = (int)(r % taps);
-    int n = (int)(r / taps);
-    const float* q = partial + (long long)k * per + i;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int sp = 0;
-    for (; sp + 4 <= nsplit; sp += 4) {
-      s0 += __ldg(q + (long long)sp * stride);
-      s1 += __ldg(q + (long long)(sp + 1) * stride);
-      s2 += __ldg(q + (long long)(sp + 2) * stride);
-      s3 += __ldg(q + (long long)(sp + 3) * stride);
+  const bool vec = (nk & 3) == 0 && (ldk & 3) == 0 && (k0 & 3) == 0 &&
+                   (reinterpret_cast<unsigned long long>(out) & 15ull) == 0;
+  for (long long i0 = blockIdx.x * 32LL; i0 < per; i0 += (long long)gridDim.x * 32) {
+    const long long i = i0 + threadIdx.x;
+    const int c = (int)(i % Cp);
+    const bool ok = i < per && c < C;
+    float v = 0.f;
+    if (ok) {
+      const float* q = partial + (long long)k * per + i;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int sp = 0;
+      for (; sp + 4 <= nsplit; sp += 4) {
+        s0 += __ldg(q + (long long)sp * stride);
+        s1 += __ldg(q + (long long)(sp + 1) * stride);
+        s2 += __ldg(q + (long long)(sp + 2) * stride);
+        s3 += __ldg(q + (long long)(sp + 3) * stride);
+      }
+      for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
+      v = alpha * ((s0 + s1) + (s2 + s3));
     }
-    for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
-    out[(off + ((long long)n * C + c) * taps + tap) * ldk + k0 + k - kskip] += alpha * ((s0 + s1) + (s2 + s3));
+    if (!vec) {
+      if (ok) {
+        const long long r = i / Cp;
+        out[(off + ((r / taps) * C + c) * taps + (r % taps)) * ldk + k0 + k - kskip] += v;
+      }
+      continue;  // uniform per block: `vec` does not depend on the thread
+    }
+    tile[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    // thread (x, y) updates float4 number y of the row of element i0 + x (rows have nk / 4 float4s)
+    for (int q4 = threadIdx.y; q4 < (nk >> 2); q4 += nk) {
+      if (ok) {
+        const long long r = i / Cp;
+        float4* dst = reinterpret_cast<float4*>(out + (off + ((r / taps) * C + c) * taps + (r % taps)) * ldk + k0) + q4;
+        float4 o = *dst;
+        o.x += tile[4 * q4 + 0][threadIdx.x]; o.y += tile[4 * q4 + 1][threadIdx.x];
+        o.z += tile[4 * q4 + 2][threadIdx.x]; o.w += tile[4 * q4 + 3][threadIdx.x];
+        *dst = o;
+      }
+    }
+    __syncthreads();
   }
 }
 

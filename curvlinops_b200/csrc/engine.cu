@@ -258,6 +258,18 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
       long long need = (long long)n.nchunks * (kmax + 1) * 2 * vi.Cp;
       if (need > scratch) scratch = need;
+    } else if (d.op == CURV_OP_LAYERNORM) {
+      const Value& vi = P->values[d.in0];
+      if (hessian & 1) { delete P; return fail(CURV_ERR_UNSUPPORTED, "LayerNorm is not supported by the Hessian R-op program"); }
+      if (vi.Cp > 1024) { delete P; return fail(CURV_ERR_UNSUPPORTED, "LayerNorm over more than 1024 channels"); }
+      n.coef_off = alloc((long long)(1 + kmax) * 2 * vi.Cp);
+      long long rows = (long long)batch * vi.H * vi.W;
+      n.aux_off = alloc(2 * rows);
+      n.rows_per_cta = (int)((rows + 2 * 148 - 1) / (2 * 148));
+      if (n.rows_per_cta < 32) n.rows_per_cta = 32;
+      n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
+      long long need = (long long)n.nchunks * (kmax + 1) * 2 * vi.Cp;
+      if (need > scratch) scratch = need;
     } else if (d.op == CURV_OP_MAXPOOL) {
       const Value& vo = P->values[d.out];
       n.idx_off = alloc((vo.slot_elems + 3) / 4);  // float offset of a byte buffer (1 byte per element)
@@ -523,7 +535,7 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
     const curv_node_desc& d = n.d;
     if (c.v_ready && with_tangents) {  // streaming call: the columns of V of this node's parameters must have landed
       for (int p : {d.p0, d.p1})
-        if ((d.op == CURV_OP_CONV || d.op == CURV_OP_AFFINE) && p >= 0 && c.v_ready[p])
+        if ((d.op == CURV_OP_CONV || d.op == CURV_OP_AFFINE || d.op == CURV_OP_LAYERNORM) && p >= 0 && c.v_ready[p])
           CHECK_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)c.v_ready[p], 0));
     }
     if (d.op == CURV_OP_CONV) {
@@ -619,6 +631,24 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
                                                                 g.Nd, g.N, g.Nd);
         LAUNCH_CHECK();
       }
+    } else if (d.op == CURV_OP_LAYERNORM) {  // coef slot 0 = (gamma, beta) [defaults 1, 0], slot k = their tangents
+      const Value& vi = P->values[d.in0];
+      const float* gamma = d.p0 >= 0 ? c.param(d.p0) : (d.c0 >= 0 ? c.cst(d.c0) : nullptr);
+      const float* beta = d.p1 >= 0 ? c.param(d.p1) : (d.c1 >= 0 ? c.cst(d.c1) : nullptr);
+      float* coef = c.ws + n.coef_off;
+      fill_kernel<<<grid1d(vi.Cp), 256, 0, st>>>(coef, vi.C, 1.f, vi.Cp);  // gamma default 1 (pad lanes 0)
+      LAUNCH_CHECK();
+      CHECK_CUDA(cudaMemsetAsync(coef + vi.Cp, 0, sizeof(float) * vi.Cp * (1 + 2 * (size_t)(with_tangents ? c.K : 0)), st));
+      if (gamma) { pack_vec_kernel<<<dim3(grid1d(vi.Cp), 1), 256, 0, st>>>(gamma, 1, coef, 0, vi.C, vi.Cp); LAUNCH_CHECK(); }
+      if (beta) { pack_vec_kernel<<<dim3(grid1d(vi.Cp), 1), 256, 0, st>>>(beta, 1, coef + vi.Cp, 0, vi.C, vi.Cp); LAUNCH_CHECK(); }
+      if (with_tangents && d.p0 >= 0) {
+        pack_vec_kernel<<<dim3(grid1d(vi.Cp), c.K), 256, 0, st>>>(c.vcol(d.p0), c.ldk, coef + 2 * vi.Cp, 2 * vi.Cp, vi.C, vi.Cp);
+        LAUNCH_CHECK();
+      }
+      if (with_tangents && d.p1 >= 0) {
+        pack_vec_kernel<<<dim3(grid1d(vi.Cp), c.K), 256, 0, st>>>(c.vcol(d.p1), c.ldk, coef + 3 * vi.Cp, 2 * vi.Cp, vi.C, vi.Cp);
+        LAUNCH_CHECK();
+      }
     } else if (d.op == CURV_OP_AFFINE) {
       const Value& vi = P->values[d.in0];
       const float* gamma = d.p0 >= 0 ? c.param(d.p0) : (d.c0 >= 0 ? c.cst(d.c0) : nullptr);
@@ -648,7 +678,7 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
 static int signal_out_done(const Ctx& c, const Node& n) {
   if (!c.out_done) return CURV_OK;
   for (int p : {n.d.p0, n.d.p1})
-    if ((n.d.op == CURV_OP_CONV || n.d.op == CURV_OP_AFFINE) && p >= 0 && c.out_done[p])
+    if ((n.d.op == CURV_OP_CONV || n.d.op == CURV_OP_AFFINE || n.d.op == CURV_OP_LAYERNORM) && p >= 0 && c.out_done[p])
       CHECK_CUDA(cudaEventRecord((cudaEvent_t)c.out_done[p], c.st));
   return CURV_OK;
 }
@@ -788,10 +818,20 @@ static int forward(const Ctx& c, const void* X, int K) {
         planes_of = planes ? d.out : -1;
         break;
       }
+      case CURV_OP_LAYERNORM: {
+        const long long rows = (long long)P->B * vi.H * vi.W;
+        layernorm_fwd_kernel<<<(int)std::min<long long>((rows + 7) / 8, 148 * 8), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, c.ws + n.coef_off, (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0,
+            c.act(d.out), vo.slot_elems, c.ws + n.aux_off, rows, vi.C, vi.Cp, d.eps, nsl);
+        LAUNCH_CHECK();
+        break;
+      }
       case CURV_OP_RELU:
       case CURV_OP_SIGMOID:
+      case CURV_OP_GELU:
       case CURV_OP_TANH: {
-        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID : ACT_TANH);
+        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID
+                                                      : (d.op == CURV_OP_GELU ? ACT_GELU : ACT_TANH));
         long long n4 = vo.slot_elems / 4;
         act_fwd_kernel<<<dim3(grid1d(n4), 1), 256, 0, st>>>(kind, c.act(d.in0), vi.slot_elems, c.act(d.out),
                                                             vo.slot_elems, n4, 0);
@@ -1079,14 +1119,37 @@ static int backward(const Ctx& c, int K) {
         }
         break;
       }
+      case CURV_OP_LAYERNORM: {
+        const long long rows = (long long)P->B * vi.H * vi.W;
+        const int want_partial = (d.p0 >= 0 || d.p1 >= 0) ? 1 : 0;
+        if (!vi.tan && !want_partial) break;
+        layernorm_bwd_kernel<<<dim3(n.nchunks, ns), 256, 0, st>>>(
+            c.grad(d.out), vo.slot_elems, c.act(d.in0), c.ws + n.aux_off, c.ws + n.coef_off,
+            vi.tan ? c.grad(d.in0) : nullptr, vi.slot_elems, vi.tan ? 1 : 0, ginit[d.in0], scratch, want_partial, rows,
+            vi.C, vi.Cp, n.rows_per_cta, s0, ns);
+        LAUNCH_CHECK();
+        if (vi.tan) mark_written(d.in0);
+        if (c.kfac_G == nullptr) {
+          for (int which = 0; which < 2; ++which) {
+            const int pi = which == 0 ? d.p0 : d.p1;
+            if (pi < 0) continue;
+            vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+                scratch, n.nchunks, ns, kskip, which, vi.C, vi.Cp, c.out, P->params[pi].offset, c.ldk, c.k0, c.alpha);
+            LAUNCH_CHECK();
+          }
+        }
+        break;
+      }
       case CURV_OP_RELU:
       case CURV_OP_SIGMOID:
+      case CURV_OP_GELU:
       case CURV_OP_TANH: {
         if (!vi.tan) break;
-        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID : ACT_TANH);
+        int kind = d.op == CURV_OP_RELU ? ACT_RELU : (d.op == CURV_OP_SIGMOID ? ACT_SIGMOID
+                                                      : (d.op == CURV_OP_GELU ? ACT_GELU : ACT_TANH));
         long long n4 = vo.slot_elems / 4;
         act_bwd_kernel<<<dim3(grid1d(n4), ns), 256, 0, st>>>(
-            kind, c.grad(d.out), vo.slot_elems, c.act(d.out), c.grad(d.in0), vi.slot_elems,
+            kind, c.grad(d.out), vo.slot_elems, kind == ACT_GELU ? c.act(d.in0) : c.act(d.out), c.grad(d.in0), vi.slot_elems,
             rop ? c.act(d.in0) : nullptr, vi.slot_elems, n4, s0, ginit[d.in0]);
         LAUNCH_CHECK();
         mark_written(d.in0);

@@ -124,6 +124,11 @@ class CompiledProgram:
         except Exception:
             pass
 
+    def engine_input(self, X: Tensor) -> Tensor:
+        """The network input as the library reads it: NCHW / [B, C]; a token sequence [B, T, D] is handed over as
+        [B, D, 1, T] (one transposed copy per call: the library's input kernel expects channels-first)."""
+        return X.transpose(1, 2).contiguous() if self.lp.tokens_input else X
+
     def value_view(self, ws: Tensor, value_id: int, nslots: int) -> Tensor:
         """``[nslots, B, H, W, Cp]`` view of a value's storage inside the workspace (tests / MC draw)."""
         off, sb, cp = C.c_size_t(), C.c_size_t(), C.c_int()
@@ -223,6 +228,7 @@ class Engine:
         kc = min(cn, MAX_COLUMNS_PER_SWEEP)
         X = X.to(torch.float32).contiguous()
         prog = self.program(X, kc, kind == capi.KIND_HESSIAN)
+        X = prog.engine_input(X)
         ws = self.workspace(prog.ws_bytes, X.device)
         keep, pptrs = self._param_ptrs()
         loss = 0
@@ -305,6 +311,7 @@ class Engine:
     def _predict(self, X: Tensor) -> Tensor:
         X = X.to(torch.float32).contiguous()
         prog = self.program(X, 1, False)
+        X = prog.engine_input(X)
         ws = self.workspace(prog.ws_bytes, X.device)
         keep, pptrs = self._param_ptrs()
         stream = torch.cuda.current_stream(X.device).cuda_stream

@@ -286,7 +286,7 @@ class KFACComputer(CurvatureLinearOperator):
         n = len(nodes)
         keep, pptrs = self._engine._param_ptrs()
         rc = L.curv_kfac_accumulate_batch(
-            prog.handle, pptrs, prog.const_ptrs, X.data_ptr(), (C.c_int * n)(*nodes), n,
+            prog.handle, pptrs, prog.const_ptrs, prog.engine_input(X).data_ptr(), (C.c_int * n)(*nodes), n,
             capi.ptr_array(a_ptrs), capi.ptr_array(g_ptrs), (C.c_int * n)(*joint),
             seeds.data_ptr() if V > 0 else 0, V, 1.0 / self._N_data, float(corr), ws.data_ptr(),
             ws.numel() * 4, torch.cuda.current_stream(dev).cuda_stream)

@@ -56,7 +56,11 @@ enum curv_op {
   CURV_OP_MAXPOOL = 5,
   CURV_OP_AVGPOOL = 6,  /* global average pool (AdaptiveAvgPool2d(1) / mean over H,W)               */
   CURV_OP_SIGMOID = 7,
-  CURV_OP_TANH = 8
+  CURV_OP_TANH = 8,
+  CURV_OP_LAYERNORM = 9, /* LayerNorm over the channels of each pixel / token (aten.native_layer_norm over the last
+                            dimension): p0 / c0 = weight, p1 / c1 = bias, eps.  GGN / MC / Jacobian kinds; not part
+                            of Hessian (R-op) programs                                                          */
+  CURV_OP_GELU = 10      /* exact (erf) GELU                                                                     */
 };
 
 enum curv_loss { CURV_LOSS_CE = 0, CURV_LOSS_MSE = 1, CURV_LOSS_BCE = 2 };

@@ -84,3 +84,29 @@ class ConvNetBias(nn.Module):
         x = torch.relu(self.c1(x))
         x = torch.relu(self.c2(x))
         return self.fc(torch.flatten(x, 1))
+
+
+def mlp_ln_gelu(width: int = 16, classes: int = 6) -> nn.Sequential:
+    """Linear-LayerNorm-GELU-Linear-LayerNorm-ReLU-Linear (north_star layer set + GELU)."""
+    return nn.Sequential(nn.Linear(width, 20), nn.LayerNorm(20), nn.GELU(), nn.Linear(20, 12), nn.LayerNorm(12),
+                         nn.ReLU(), nn.Linear(12, classes))
+
+
+def mlp_gelu(width: int = 16, classes: int = 6) -> nn.Sequential:
+    """Linear-GELU-Linear-GELU-Linear: smooth activation, the Hessian has second-order terms."""
+    return nn.Sequential(nn.Linear(width, width), nn.GELU(), nn.Linear(width, width), nn.GELU(),
+                         nn.Linear(width, classes))
+
+
+class TokenMLP(nn.Module):
+    """Token sequence [B, T, D] -> pre-norm MLP block with a residual, LayerNorm, mean over tokens, linear head: the
+    Linear / LayerNorm / GELU / residual pattern of a transformer block without the attention."""
+
+    def __init__(self, dim: int = 12, hidden: int = 20, classes: int = 5):
+        super().__init__()
+        self.ln1, self.fc1, self.fc2 = nn.LayerNorm(dim), nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+        self.ln2, self.head = nn.LayerNorm(dim), nn.Linear(dim, classes)
+
+    def forward(self, x):
+        x = x + self.fc2(torch.nn.functional.gelu(self.fc1(self.ln1(x))))
+        return self.head(self.ln2(x).mean(1))

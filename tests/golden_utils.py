@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from oracle.models import ConvNetBias, MiniResNet, mlp_c1, mlp_smooth
+from oracle.models import ConvNetBias, MiniResNet, TokenMLP, mlp_c1, mlp_gelu, mlp_ln_gelu, mlp_smooth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -18,6 +18,9 @@ BUILDERS = {
     "mlp_bce_sum": (lambda: mlp_c1(classes=6, width=16), lambda: nn.BCEWithLogitsLoss(reduction="sum")),
     "mlp_sigmoid_tanh_mse_sum": (lambda: mlp_smooth(), lambda: nn.MSELoss(reduction="sum")),
     "cnn_bias_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
+    "mlp_ln_gelu_ce_mean": (lambda: mlp_ln_gelu(), lambda: nn.CrossEntropyLoss()),
+    "token_mlp_ce_mean": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
+    "mlp_gelu_mse_sum": (lambda: mlp_gelu(), lambda: nn.MSELoss(reduction="sum")),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

@@ -54,3 +54,22 @@ def test_empirical_fisher_bce_matches_reference(name):
     params = dict(model.named_parameters())
     V = split_like(fx["V"], params)
     torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), fx["ef"], rtol=1e-9, atol=1e-12)
+
+
+# fixtures of oracle/make_golden_ln.py: LayerNorm / GELU networks, 2-d inputs and token sequences [B, T, D]
+LN_CASES = ["mlp_ln_gelu_ce_mean", "token_mlp_ce_mean", "mlp_gelu_mse_sum"]
+
+
+@pytest.mark.parametrize("name", LN_CASES)
+def test_layernorm_gelu_cases_match_reference(name):
+    model, loss, data, fx = load_case(name)
+    params = dict(model.named_parameters())
+    V = split_like(fx["V"], params)
+    torch.testing.assert_close(flat(orc.ggn_matmat(model, loss, params, data, V)), fx["ggn"], rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), fx["ef"], rtol=1e-9, atol=1e-12)
+    if "hessian" in fx:
+        torch.testing.assert_close(flat(orc.hessian_matmat(model, loss, params, data, V)), fx["hessian"],
+                                   rtol=1e-9, atol=1e-12)
+    for M in (1, 3):
+        got = flat(orc.ggn_matmat(model, loss, params, data, V, mc_samples=M, seed=1234))
+        torch.testing.assert_close(got, fx[f"ggn_mc{M}"], rtol=1e-9, atol=1e-12)
