@@ -98,10 +98,13 @@ class ClockSampler:
 
 def ncu_traffic_per_launch():
     """Mean dram__bytes_read + dram__bytes_write per launch of the gather GEMM kernels, from the committed
-    `ncu --set full` capture of one C2 step (profiles/r1_s2_hs_kernels_ncu_full_final.txt; tools/gpu_one_step.py)."""
+    `ncu --set full` capture of the first contraction launches of one step of this configuration
+    (profiles/r2_hs_kernels_ncu_full_{fp32,bf16}.txt, made by tools/r2_gpu_job.sh with tools/gpu_one_step.py in the
+    same commit as the kernels; a profiler cannot run inside the timed bench)."""
     import re
 
-    path = os.path.join(ROOT, "profiles", "r1_s2_hs_kernels_ncu_full_final.txt")
+    path = os.path.join(ROOT, "profiles", "r2_hs_kernels_ncu_full_%s.txt" % ("bf16" if WORKLOADS[CONFIG][1] == "bf16"
+                                                                              else "fp32"))
     try:
         blocks = open(path).read().split("---")
     except OSError:
@@ -314,6 +317,7 @@ def run_c3(torch, args):
     ms_build, Kop = timed(build, args.steps)
     launches = capi.lib().curv_launch_count() - L0
     clocks = sampler.stop()
+    Kop.inverse(damping=1e-3)  # first call initialises cuSOLVER
     ms_inv, Kinv = timed(lambda: Kop.inverse(damping=1e-3), 3)
     torch.manual_seed(1)
     v_host = torch.rand(P).to(torch.bfloat16).pin_memory()

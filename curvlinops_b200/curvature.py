@@ -292,8 +292,15 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
                 continue
             Xs, ys, scales = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
             if Xs is not None:
+                shard_info = Xs._curv_shard
                 Xs, ys = Xs.to(dev, non_blocking=True), ys.to(dev, non_blocking=True)
+                Xs._curv_shard = shard_info
+            else:
+                self._on_empty_shard(X, y)
             yield Xs, ys, alpha, scales
+
+    def _on_empty_shard(self, X, y) -> None:
+        """This rank holds no sample of the mini-batch (fewer samples than ranks)."""
 
     def _param_buckets(self, K: int, bucket_bytes: int, first_bytes: int | None = None):
         """Row ranges ``(lo, hi, [param indices])`` of the flat ``[P, K]`` matrices made of whole parameters, about
@@ -600,6 +607,12 @@ class GGNLinearOperator(CurvatureLinearOperator):
                 return super()._product(V)
         return super()._product(V)
 
+    def _on_empty_shard(self, X, y) -> None:
+        if self._mc_samples > 0:  # consume the variates of this mini-batch: the stream stays aligned across ranks
+            B, M, dev = X.shape[0], self._mc_samples, self.device
+            n = B * M if isinstance(self._loss_func, CrossEntropyLoss) else B * M * y.shape[-1]
+            (torch.randn if isinstance(self._loss_func, MSELoss) else torch.rand)(n, device=dev)
+
     def _mc_scale(self, batch: int) -> float:
         return 1.0 / batch if self._loss_func.reduction == "mean" else 1.0
 
@@ -617,7 +630,7 @@ class GGNLinearOperator(CurvatureLinearOperator):
     def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None, cols=None):
         if self._mc_samples == 0:
             return super()._batch_call_sharded(X, y, V, out, alpha, scale, out_done=out_done, cols=cols)
-        g = self._engine.mc_grad_outputs(X, self._mc_samples)
+        g = self._engine.mc_grad_outputs(X, self._mc_samples, shard=getattr(X, "_curv_shard", None))
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1],
                                   **self._shard_kw(out_done, cols))
 

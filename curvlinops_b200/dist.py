@@ -64,7 +64,9 @@ def shard_batch(X: Tensor, y: Tensor, rank: int, world: int, loss_func, engine=N
         scales = (1.0 / (B * y.shape[-1]), 1.0 / B)
     if hi == lo:
         return None, None, scales
-    return X[lo:hi], y[lo:hi], scales
+    Xs = X[lo:hi]
+    Xs._curv_shard = (lo, hi, B)  # global sample indices of the slice (Monte-Carlo draws are keyed on them)
+    return Xs, y[lo:hi], scales
 
 
 def all_reduce_sum(t: Tensor) -> None:

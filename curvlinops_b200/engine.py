@@ -321,23 +321,34 @@ class Engine:
         del keep
         return prog.value_view(ws, prog.out_value, 1)[0, :, 0, 0, : prog.classes].clone()
 
-    def mc_grad_outputs(self, X: Tensor, mc_samples: int) -> Tensor:
-        """Would-be gradients ``[B, M, C] / sqrt(M)`` drawn from the global RNG with the reference's own
-        calls (``ggn_utils.py:220-262,369-372``), on the operator's device."""
+    def mc_grad_outputs(self, X: Tensor, mc_samples: int, shard: tuple[int, int, int] | None = None) -> Tensor:
+        """Would-be gradients ``[B, M, C] / sqrt(M)`` of the samples in ``X`` (``ggn_utils.py:174-271,369-372``), drawn
+        from the global RNG of the operator's device.
+
+        The draw is keyed on the GLOBAL sample index: uniform / normal variates are generated for every sample of the
+        whole mini-batch (``shard = (lo, hi, B_global)``: ``X`` holds samples ``lo..hi`` of it) and the labels follow
+        by inverse-CDF sampling, so a rank that processes a slice of the mini-batch draws exactly what a single
+        process draws for those samples: Monte-Carlo products do not depend on the number of ranks.
+        (The reference's ``multinomial`` consumes the stream differently; parity with ITS samples is tested by handing
+        the engine the reference's draws.)"""
         f = self.predict(X)
         B, Cc = f.shape
+        lo, hi, Bg = (0, B, B) if shard is None else shard
         lf = self.loss_func
         if isinstance(lf, CrossEntropyLoss):
             p = torch.softmax(f, dim=1)
-            yhat = p.multinomial(mc_samples, replacement=True)
+            u = torch.rand(Bg, mc_samples, dtype=f.dtype, device=f.device)[lo:hi]
+            cdf = p.cumsum(1)
+            yhat = torch.searchsorted(cdf, u * cdf[:, -1:]).clamp_(max=Cc - 1)
             g = p.unsqueeze(1) - torch.nn.functional.one_hot(yhat, num_classes=Cc).to(f.dtype)
         elif isinstance(lf, MSELoss):
             c = 1.0 / Cc if lf.reduction == "mean" else 1.0
-            g = torch.normal(torch.zeros(B, mc_samples, Cc, dtype=f.dtype, device=f.device), math.sqrt(2 * c))
+            g = torch.randn(Bg, mc_samples, Cc, dtype=f.dtype, device=f.device)[lo:hi] * math.sqrt(2 * c)
         elif isinstance(lf, BCEWithLogitsLoss):
             c = 1.0 / Cc if lf.reduction == "mean" else 1.0
             s = torch.sigmoid(f).unsqueeze(1).expand(B, mc_samples, Cc)
-            g = math.sqrt(c) * (s - s.bernoulli())
+            u = torch.rand(Bg, mc_samples, Cc, dtype=f.dtype, device=f.device)[lo:hi]
+            g = math.sqrt(c) * (s - (u < s).to(f.dtype))
         else:
             raise NotImplementedError(f"MC sampling for {lf}.")
         return g / math.sqrt(mc_samples)

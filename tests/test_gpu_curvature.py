@@ -276,3 +276,19 @@ def test_parameter_space_glue_variants_are_bit_identical():
         capi.lib().curv_set_tensor_core_mode(old)
     assert torch.equal(new, ref)
     assert_parity(new, fx["ggn"], params)
+
+
+@pytest.mark.parametrize("name", ["mlp_c1_ce_mean", "mlp_c1_mse_mean", "mlp_bce_mean"])
+def test_mc_draws_are_keyed_on_the_global_sample_index(name):
+    """A rank that holds samples lo..hi of a mini-batch draws exactly the would-be gradients a single process draws
+    for those samples (Monte-Carlo products must not depend on the number of ranks)."""
+    model, loss, data, fx, params = _setup(name)
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=3)
+    X = data[0][0]
+    B = X.shape[0]
+    torch.manual_seed(5)
+    full = G._engine.mc_grad_outputs(X, 3)
+    for lo, hi in ((0, 2), (2, B), (1, B - 1)):
+        torch.manual_seed(5)
+        part = G._engine.mc_grad_outputs(X[lo:hi], 3, shard=(lo, hi, B))
+        assert torch.equal(part, full[lo:hi])

@@ -11,10 +11,11 @@ from curvlinops_b200 import GGNLinearOperator
 B, K = int(os.environ.get("CURV_B", 128)), 8
 torch.manual_seed(0)
 dev = torch.device("cuda")
-model = torchvision.models.resnet18().eval().to(dev)
-X, y = torch.rand(B, 3, 224, 224, device=dev), torch.randint(0, 1000, (B,), device=dev)
+dt = torch.bfloat16 if os.environ.get("CURV_DTYPE") == "bf16" else torch.float32  # CURV_DTYPE=bf16: the c2-bf16 step
+model = torchvision.models.resnet18().eval().to(dev).to(dt)
+X, y = torch.rand(B, 3, 224, 224, device=dev).to(dt), torch.randint(0, 1000, (B,), device=dev)
 params = dict(model.named_parameters())
-V = torch.rand(sum(p.numel() for p in params.values()), K, device=dev)
+V = torch.rand(sum(p.numel() for p in params.values()), K, device=dev).to(dt)
 G = GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=B)
 out = G @ V  # warm-up (one-time initialisation)
 torch.cuda.synchronize()
@@ -22,4 +23,4 @@ torch.cuda.profiler.start()
 out = G @ V
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("checksum", float(out.abs().sum()))
+print("checksum", float(out.float().abs().sum()))

@@ -10,11 +10,12 @@ mode = int(sys.argv[1], 0) if len(sys.argv) > 1 else 1
 B, K = int(os.environ.get("CURV_B", 128)), 8
 torch.manual_seed(0)
 dev = torch.device("cuda")
-model = torchvision.models.resnet18().eval().to(dev)
-X, y = torch.rand(B, 3, 224, 224, device=dev), torch.randint(0, 1000, (B,), device=dev)
+dt = torch.bfloat16 if os.environ.get("CURV_DTYPE") == "bf16" else torch.float32
+model = torchvision.models.resnet18().eval().to(dev).to(dt)
+X, y = torch.rand(B, 3, 224, 224, device=dev).to(dt), torch.randint(0, 1000, (B,), device=dev)
 params = dict(model.named_parameters())
 P = sum(p.numel() for p in params.values())
-V = torch.rand(P, K, device=dev)
+V = torch.rand(P, K, device=dev).to(dt)
 G = GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=B)
 capi.lib().curv_set_tensor_core_mode(mode)
 for _ in range(2):
@@ -26,7 +27,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
 rows.sort(key=lambda r: -r[2])
 tot = sum(r[2] for r in rows)
-print(f"# one C2 step (ResNet-18, B={B}, K=8, fp32), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
+print(f"# one C2 step (ResNet-18, B={B}, K=8, {dt}), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
 for k, n, ms in rows[:40]:
     print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:110]}")
 # per-launch durations of the contraction kernels, in launch order (layer attribution by position)
