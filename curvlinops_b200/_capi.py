@@ -39,7 +39,8 @@ class NodeDesc(C.Structure):
 EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
-    "curv_kron_apply", "curv_kron_apply_tc", "curv_kron_apply_tc_workspace", "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
+    "curv_kron_apply", "curv_kron_apply_tc", "curv_kron_apply_tc_workspace", "curv_kron_apply_tc_factor_bytes",
+    "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_add_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
 ]
@@ -80,10 +81,12 @@ def lib() -> C.CDLL:
     L.curv_kfac_accumulate_batch.restype = i
     L.curv_kron_apply.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.curv_kron_apply.restype = i
-    L.curv_kron_apply_tc.argtypes = [vp, vp, i, i, i, vp, vp, i, vp, C.c_size_t, vp]
+    L.curv_kron_apply_tc.argtypes = [vp, vp, i, i, i, vp, vp, vp, C.c_size_t, i, vp, C.c_size_t, vp]
     L.curv_kron_apply_tc.restype = i
-    L.curv_kron_apply_tc_workspace.argtypes = [i, i, i, i]
+    L.curv_kron_apply_tc_workspace.argtypes = [i, i, i]
     L.curv_kron_apply_tc_workspace.restype = C.c_size_t
+    L.curv_kron_apply_tc_factor_bytes.argtypes = [i, i]
+    L.curv_kron_apply_tc_factor_bytes.restype = C.c_size_t
     L.curv_eigh_apply.argtypes = [vp, vp, vp, f, i, i, i, i, vp, vp, vp, vp, vp]
     L.curv_eigh_apply.restype = i
     L.curv_gemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i, vp]

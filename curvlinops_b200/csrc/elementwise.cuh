@@ -925,25 +925,24 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 // out[(off + c)*ldk + k0 + k] += alpha * sum_chunks partial[chunk][k][which][c]
 // (slot indices kskip .. nslots-1 of the partial buffer map to columns 0 .. nslots-kskip-1)
-__global__ void vec_grad_finish_kernel(const float* __restrict__ partial, int nchunks, int nslots,
-                                       int kskip, int which, int C, int Cp, float* __restrict__ out,
-                                       long long off, int ldk, int k0, float alpha) {
-  int nk = nslots - kskip;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per output: the lanes stride over the chunks (a few hundred dependent loads per output were pure latency
+// with one thread per output: 41 launches x 30 us per C2 step), then a shuffle tree in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) vec_grad_finish_kernel(const float* __restrict__ partial, int nchunks, int nslots,
+                                                            int kskip, int which, int C, int Cp,
+                                                            float* __restrict__ out, long long off, int ldk, int k0,
+                                                            float alpha) {
+  const int nk = nslots - kskip;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= C * nk) return;
-  int k = i % nk, c = i / nk;
-  // eight independent chains (fixed order => deterministic): the loop is pure load latency otherwise
+  const int k = i % nk, c = i / nk;
   const float* q = partial + ((long long)(kskip + k) * 2 + which) * Cp + c;
   const long long stride = (long long)nslots * 2 * Cp;
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int ch = 0;
-  for (; ch + 8 <= nchunks; ch += 8) {
+  float a = 0.f;
+  for (int ch = lane; ch < nchunks; ch += 32) a += __ldg(q + (long long)ch * stride);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += __ldg(q + (long long)(ch + j) * stride);
-  }
-  for (; ch < nchunks; ++ch) a[0] += __ldg(q + (long long)ch * stride);
-  const float s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  out[(off + c) * ldk + k0 + k] += alpha * s;
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[(off + c) * ldk + k0 + k] += alpha * a;
 }
 
 // out[(off + ((n*C + c)*taps + tap))*ldk + k0 + k] += alpha * sum_splits partial[split][k][n][tap][cp]
@@ -952,54 +951,29 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nspli
                                     long long off, int ldk, int k0, float alpha) {
   // block = (32 weight elements, nslots - kskip columns): a warp reads 128 contiguous bytes of one slot's
   // partial per split; the splits are summed in a fixed order with four independent chains (deterministic).
-  // The 32 x nk sums are transposed through shared memory so that the K-minor rows of `out` are updated with
-  // 16-byte read-modify-writes (one row = nk consecutive floats) instead of nk scattered 4-byte ones.
-  __shared__ float tile[32][33];
+  // (Round 2 tried two variants of the K-minor update -- a CTA tile transposed through shared memory with
+  // contiguous row writes, and 16-byte row read-modify-writes after a 32 x nk transpose: 6.2 ms and 2.7 ms per C2
+  // step against 2.3 ms for this one; the L2 merges the nk 4-byte updates of a row.)
   const long long per = (long long)N * taps * Cp;
-  const int nk = blockDim.y;
   const int k = kskip + threadIdx.y;
   const long long stride = (long long)nslots * per;
-  const bool vec = (nk & 3) == 0 && (ldk & 3) == 0 && (k0 & 3) == 0 &&
-                   (reinterpret_cast<unsigned long long>(out) & 15ull) == 0;
-  for (long long i0 = blockIdx.x * 32LL; i0 < per; i0 += (long long)gridDim.x * 32) {
-    const long long i = i0 + threadIdx.x;
-    const int c = (int)(i % Cp);
-    const bool ok = i < per && c < C;
-    float v = 0.f;
-    if (ok) {
-      const float* q = partial + (long long)k * per + i;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int sp = 0;
-      for (; sp + 4 <= nsplit; sp += 4) {
-        s0 += __ldg(q + (long long)sp * stride);
-        s1 += __ldg(q + (long long)(sp + 1) * stride);
-        s2 += __ldg(q + (long long)(sp + 2) * stride);
-        s3 += __ldg(q + (long long)(sp + 3) * stride);
-      }
-      for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
-      v = alpha * ((s0 + s1) + (s2 + s3));
+  for (long long i = blockIdx.x * 32LL + threadIdx.x; i < per; i += (long long)gridDim.x * 32) {
+    int c = (int)(i % Cp);
+    if (c >= C) continue;
+    long long r = i / Cp;
+    int tap = (int)(r % taps);
+    int n = (int)(r / taps);
+    const float* q = partial + (long long)k * per + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= nsplit; sp += 4) {
+      s0 += __ldg(q + (long long)sp * stride);
+      s1 += __ldg(q + (long long)(sp + 1) * stride);
+      s2 += __ldg(q + (long long)(sp + 2) * stride);
+      s3 += __ldg(q + (long long)(sp + 3) * stride);
     }
-    if (!vec) {
-      if (ok) {
-        const long long r = i / Cp;
-        out[(off + ((r / taps) * C + c) * taps + (r % taps)) * ldk + k0 + k - kskip] += v;
-      }
-      continue;  // uniform per block: `vec` does not depend on the thread
-    }
-    tile[threadIdx.y][threadIdx.x] = v;
-    __syncthreads();
-    // thread (x, y) updates float4 number y of the row of element i0 + x (rows have nk / 4 float4s)
-    for (int q4 = threadIdx.y; q4 < (nk >> 2); q4 += nk) {
-      if (ok) {
-        const long long r = i / Cp;
-        float4* dst = reinterpret_cast<float4*>(out + (off + ((r / taps) * C + c) * taps + (r % taps)) * ldk + k0) + q4;
-        float4 o = *dst;
-        o.x += tile[4 * q4 + 0][threadIdx.x]; o.y += tile[4 * q4 + 1][threadIdx.x];
-        o.z += tile[4 * q4 + 2][threadIdx.x]; o.w += tile[4 * q4 + 3][threadIdx.x];
-        *dst = o;
-      }
-    }
-    __syncthreads();
+    for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
+    out[(off + ((long long)n * C + c) * taps + tap) * ldk + k0 + k - kskip] += alpha * ((s0 + s1) + (s2 + s3));
   }
 }
 

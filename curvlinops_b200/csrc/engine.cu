@@ -1020,7 +1020,7 @@ static int backward(const Ctx& c, int K) {
               c.grad(d.out), vo.slot_elems, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, scratch, 1,
               rows, vo.Cp, n.rows_per_cta, s0, ns, 0, 0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 1);
           LAUNCH_CHECK();
-          vec_grad_finish_kernel<<<ceil_div(vo.C * K, 256), 256, 0, st>>>(
+          vec_grad_finish_kernel<<<ceil_div(vo.C * K, 8), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 1, vo.C, vo.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
               c.alpha);
           LAUNCH_CHECK();
@@ -1106,13 +1106,13 @@ static int backward(const Ctx& c, int K) {
         planes_of = planes ? d.in0 : -1;
         if (vi.tan) mark_written(d.in0);
         if (d.p0 >= 0) {
-          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 8), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 0, vi.C, vi.Cp, c.out, P->params[d.p0].offset, c.ldk, c.k0,
               c.alpha);
           LAUNCH_CHECK();
         }
         if (d.p1 >= 0) {
-          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+          vec_grad_finish_kernel<<<ceil_div(vi.C * K, 8), 256, 0, st>>>(
               scratch, n.nchunks, ns, kskip, 1, vi.C, vi.Cp, c.out, P->params[d.p1].offset, c.ldk, c.k0,
               c.alpha);
           LAUNCH_CHECK();
@@ -1133,7 +1133,7 @@ static int backward(const Ctx& c, int K) {
           for (int which = 0; which < 2; ++which) {
             const int pi = which == 0 ? d.p0 : d.p1;
             if (pi < 0) continue;
-            vec_grad_finish_kernel<<<ceil_div(vi.C * K, 256), 256, 0, st>>>(
+            vec_grad_finish_kernel<<<ceil_div(vi.C * K, 8), 256, 0, st>>>(
                 scratch, n.nchunks, ns, kskip, which, vi.C, vi.Cp, c.out, P->params[pi].offset, c.ldk, c.k0, c.alpha);
             LAUNCH_CHECK();
           }

@@ -1,17 +1,20 @@
-// Two-sided Kronecker-factor apply on the tcgen05 contraction kernel (included at the end of engine.cu):
+// Two-sided Kronecker-factor apply on the tcgen05 contraction kernels (included at the end of engine.cu):
 //     Y[a][B][z] = sum_{a', b} G[a][a'] X[a'][b][z] A[B][b]             (kronecker.py:141-153 'abZ,Aa,Bb->ABZ')
 // for X, Y of shape [d_out, d_in, K] (K minor) -- the per-layer block of KFAC / its damped inverse, and (with the
-// eigenvector matrices as factors) the two rotations of the EKFAC apply (eigh.py:98-104).
+// eigenvector matrices as factors) the two rotations of the EKFAC apply (eigh.py:98-104).  Any square G, A.
 //
-// wgrad_gemm_hs computes D[i][n] = sum_m In[m][i] * Gm[m][n], i.e. In^T Gm with BOTH operands stored reduction-row
-// major (MN-major tcgen05 descriptors), and stores D transposed ([n][i]).  Written with the TRANSPOSED factors
-// Gt = G^T, At = A^T (symmetric Kronecker factors and their inverses are their own transposes) the apply is two
-// such products with no data transposition in between:
-//   step 1   In = Gt [d_out x d_out],  Gm = X [d_out x (d_in K)]      ->  stored [(b,z)][a]  = T^T,  T = G X
-//   step 2   In = At [d_in x d_in],    Gm = T^T rows (b, z), slot z   ->  stored [z][a][B]   = Y_z = T_z A^T
-// and the split-K finish kernel of the weight gradients writes Y K-minor.  Operands are fp16 hi/lo planes (fp32-grade,
-// three MMAs per product) or one bf16 plane (bf16 operators).  The "slots" of the kernel are column blocks of X in
-// step 1 (N = 256 MMAs) and the K columns in step 2.
+// Both products are plain GEMMs  out[m][n] = sum_r Act[m][r] W[n][r]  = a 1x1 "convolution" of gather_gemm_hs
+// (K-major operands, TMA-fed, TMEM accumulation in chunks of HS_FLUSH stages summed in registers with
+// round-to-nearest adds -- which is what keeps the tensor core's truncating accumulator harmless here: Kronecker
+// factors of a softmax layer make G X cancel to ~1/30 of its terms):
+//   step 1   T_z = G X_z        Act = G (one shared slot),  W_z = X_z^T as weight images, one per column z
+//   step 2   Y_z = T_z A^T      Act = T_z (slot z),         W   = A     as weight image
+// Operands are fp16 hi/lo planes / images (fp32-grade, three MMAs per product) also for bf16 operators (bf16-rounded
+// operands gave 4e-2 on a softmax layer's block).  The operand forms of the FACTORS (planes of G, image of A, their
+// scale words) depend only on the factors: they live in a caller-owned buffer and are built once per operator.
+// Round-2 history: a first version ran both products on the MN-major wgrad kernel with split-K partials; its
+// accumulation chains had to be cut to 64 rows against the truncation bias, the drains then dominated (8.9 ms for the
+// 21 ResNet-18 blocks against 2.0 ms for the cuBLAS-backed reference einsum).
 
 namespace curv {
 
@@ -47,167 +50,189 @@ __global__ void __launch_bounds__(256) kron_split_pad_kernel(const float* __rest
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = ch * 8 + j < cols ? __ldg(src + r * ld_src + ch * 8 + j) : 0.f;
-    const float4 v0 = make_float4(x[0], x[1], x[2], x[3]), v1 = make_float4(x[4], x[5], x[6], x[7]);
-    if (lo == nullptr) { reinterpret_cast<uint4*>(hi)[e] = hs_bf16x8(v0, v1, sc); continue; }
     uint4 h, l;
-    hs_split8(v0, v1, sc, h, l);
+    hs_split8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), sc, h, l);
     reinterpret_cast<uint4*>(hi)[e] = h;
     reinterpret_cast<uint4*>(lo)[e] = l;
   }
 }
 
-// out[i] = sum_s part[s * n + i], fixed order (split-K partials of step 1)
-__global__ void __launch_bounds__(256) kron_sum_splits_kernel(const float* __restrict__ part, int nsplit, long long n,
-                                                             float* __restrict__ out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) s += __ldg(part + sp * n + i);
-    out[i] = s;
+// Weight image (layout of hs_pack_image_kernel: blocks (tn, kc) = [hi: BN rows x 64 halves, 128B-swizzled][lo]) of the
+// matrix  Wm[n][k] = src[n * sn + k * sk]  (n < N, k < Kreal; zero beyond), one image per grid.y slot (src += slot *
+// s_slot, dst += slot * dst_slot), scale bits[slot].  (sn, sk) = (ld, 1): row-major source; = (K, d_in K): X_z^T.
+__global__ void __launch_bounds__(256) kron_pack_image_kernel(const float* __restrict__ src, long long sn, long long sk,
+                                                             long long s_slot, __half* __restrict__ dst, long long dst_slot,
+                                                             int N, int Kreal, int BN, int tiles_n, int nchunks,
+                                                             const uint32_t* __restrict__ bits) {
+  src += blockIdx.y * s_slot;
+  dst += blockIdx.y * dst_slot;
+  const float sc = hs_pow2(hs_shift_from_bits(bits[blockIdx.y]));
+  const long long total = (long long)tiles_n * nchunks * BN * 8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 7);
+    long long t = e >> 3;
+    const int r = (int)(t % BN); t /= BN;
+    const int kc = (int)(t % nchunks);
+    const int tn = (int)(t / nchunks);
+    const int n = tn * BN + r, k = kc * HS_BK + c * 8;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (n < N && k + j < Kreal) ? __ldg(src + n * sn + (k + j) * sk) : 0.f;
+    uint4 h, l;
+    hs_split8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), sc, h, l);
+    __half* blk = dst + ((long long)tn * nchunks + kc) * (2 * BN * HS_BK);
+    const int o = ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) >> 1;
+    *reinterpret_cast<uint4*>(blk + o) = h;
+    *reinterpret_cast<uint4*>(blk + BN * HS_BK + o) = l;
+  }
+}
+
+// Y[(a * d_in + b) * K + z] = Yz[z][a][b]  (row stride ld of Yz)
+__global__ void kron_interleave_kernel(const float* __restrict__ Yz, long long slot, int ld, int d_out, int d_in, int K,
+                                       float* __restrict__ Y) {
+  const long long total = (long long)d_out * d_in * K;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(e % K);
+    const long long ab = e / K;
+    const int b = (int)(ab % d_in);
+    const long long a = ab / d_in;
+    Y[e] = __ldg(Yz + z * slot + a * ld + b);
   }
 }
 
 }  // namespace curv
 
+static inline int pad64(int x) { return (x + 63) & ~63; }
+
 struct KronTcPlan {
-  int ldG, ldA, ldX, W8, NS1, nsplit1, mps1, nsplit2, mps2;
-  long long part1_elems, off_P1;
-  long long halves_G, halves_A, halves_X, halves_T;   // per plane, incl. slack
-  long long t_elems, part2_elems;                     // floats
-  long long off_bits, off_G, off_A, off_X, off_T, off_Tp, off_P2, total_bytes;
+  int ldG, ldT, NdY;                // row strides: G planes (= reduction of step 1), T (= reduction of step 2), Y_z
+  long long g_halves, a_img_halves;  // factor operands (per plane / whole image)
+  long long x_img_halves;           // per column image of X_z^T
+  long long t_elems, y_elems;       // per column
+  long long f_bits, f_G, f_A, factor_bytes;
+  long long off_bits, off_X, off_T, off_Tp, off_Y, total_bytes;
 };
-static KronTcPlan kron_tc_plan(int d_out, int d_in, int K, int planes) {
+static KronTcPlan kron_tc_plan(int d_out, int d_in, int K) {
   KronTcPlan p;
-  p.ldG = pad8(d_out); p.ldA = pad8(d_in); p.ldX = pad8(d_in * K);
-  p.W8 = 64 * ceil_div(p.ldX, 512);
-  p.NS1 = ceil_div(p.ldX, p.W8);
-  auto slack = [](long long h) { return align_up(h + 8192, 128); };
-  p.halves_G = slack((long long)d_out * p.ldG);
-  p.halves_A = slack((long long)d_in * p.ldA);
-  p.halves_X = slack((long long)d_out * p.ldX);
-  p.t_elems = align_up((long long)p.NS1 * p.W8 * p.ldG + 1024, 64);  // T^T: rows (b, z) [+ block padding], ld = ldG
-  {  // step 1 reduces over d_out rows: short chains there too (see below), partials summed by kron_sum_splits_kernel
-    long long ns1 = planes == 1 ? 1 : ceil_div(d_out, 64);
-    const long long cap1 = std::max<long long>(1, (1LL << 27) / p.t_elems);
-    if (ns1 > cap1) ns1 = cap1;
-    p.mps1 = (int)((ceil_div(d_out, (int)ns1) + 15) / 16 * 16);
-    p.nsplit1 = ceil_div(d_out, p.mps1);
-    p.part1_elems = p.nsplit1 > 1 ? (long long)p.nsplit1 * p.t_elems : 0;
-  }
-  p.halves_T = slack(p.t_elems);
-  const long long tiles = (long long)ceil_div(p.ldA, 128) * ceil_div(p.ldG, 64);
-  long long want = (2 * 148 + tiles - 1) / tiles;
-  // Short accumulation chains: the tensor core adds into its fp32 accumulator with truncation, a bias of ~0.25 ulp
-  // per MMA that does not average out, and Kronecker factors make it visible -- the rows of a softmax layer's gradient
-  // covariance sum to zero, so G X A^T cancels to ~1/30 of its terms (measured on the fc block of ResNet-18: 1.3e-4
-  // of the result with 171-row chains = 33 MMAs; strict-fp32 FMA accumulation: 2e-6).  64 rows = 12 MMAs per chain;
-  // the extra split-K partials are a few GB/s-milliseconds on these small matrices (capped at 1 GiB of scratch).
-  const long long by_len = ceil_div(d_in, planes == 1 ? 4096 : 64);
-  long long ns = want > by_len ? want : by_len;
-  const long long maxsplit = ceil_div(d_in, planes == 1 ? 256 : 32);
-  const long long cap = std::max<long long>(1, (1LL << 28) / ((long long)K * d_out * p.ldA));
-  if (ns > maxsplit) ns = maxsplit;
-  if (ns > cap) ns = cap;
-  if (ns < 1) ns = 1;
-  p.mps2 = (int)((ceil_div(d_in, (int)ns) + 15) / 16 * 16);
-  p.nsplit2 = ceil_div(d_in, p.mps2);
-  p.part2_elems = (long long)p.nsplit2 * K * d_out * p.ldA + 64;
+  p.ldG = pad64(d_out); p.ldT = pad64(d_in); p.NdY = pad4(d_in);
+  p.g_halves = align_up((long long)d_out * p.ldG + 8192, 128);
+  p.a_img_halves = hs_image_halves(pad4(d_in), p.ldT);       // A as weights [N = d_in][Kd = ldT]
+  p.x_img_halves = hs_image_halves(p.ldT, p.ldG);            // X_z^T as weights [N = d_in (rows up to ldT)][Kd = ldG]
+  p.t_elems = (long long)d_out * p.ldT;
+  p.y_elems = (long long)d_out * p.NdY;
   long long o = 0;
   auto take = [&](long long bytes) { long long r = o; o = align_up(o + bytes, 1024); return r; };
+  p.f_bits = take(64 * 4);
+  p.f_G = take(p.g_halves * 2 * 2);
+  p.f_A = take(p.a_img_halves * 2);
+  p.factor_bytes = o;
+  o = 0;
   p.off_bits = take(64 * 4);
-  p.off_G = take(p.halves_G * 2 * planes);
-  p.off_A = take(p.halves_A * 2 * planes);
-  p.off_X = take(p.halves_X * 2 * planes);
-  p.off_T = take(p.t_elems * 4);
-  p.off_Tp = take(p.halves_T * 2 * planes);
-  p.off_P2 = take(p.part2_elems * 4);
-  p.off_P1 = take(p.part1_elems * 4);
+  p.off_X = take(p.x_img_halves * 2 * K);
+  p.off_T = take(p.t_elems * 4 * K);
+  p.off_Tp = take((align_up(p.t_elems * K + 8192, 128)) * 2 * 2);
+  p.off_Y = take(p.y_elems * 4 * K);
   p.total_bytes = o;
   return p;
 }
 
-extern "C" size_t curv_kron_apply_tc_workspace(int d_out, int d_in, int K, int planes) {
+extern "C" size_t curv_kron_apply_tc_workspace(int d_out, int d_in, int K) {
   if (d_out < 1 || d_in < 1 || K < 1 || K > 8) return 0;
-  return (size_t)kron_tc_plan(d_out, d_in, K, planes == 1 ? 1 : 2).total_bytes;
+  return (size_t)kron_tc_plan(d_out, d_in, K).total_bytes;
+}
+extern "C" size_t curv_kron_apply_tc_factor_bytes(int d_out, int d_in) {
+  if (d_out < 1 || d_in < 1) return 0;
+  return (size_t)kron_tc_plan(d_out, d_in, 1).factor_bytes;
 }
 
-extern "C" int curv_kron_apply_tc(const float* Gt, const float* At, int d_out, int d_in, int K, const float* X,
-                                  float* Y, int planes, void* ws, size_t ws_bytes, void* stream) {
-  if (!Gt || !At || !X || !Y || d_out < 1 || d_in < 1 || K < 1 || K > 8)
+extern "C" int curv_kron_apply_tc(const float* G, const float* A, int d_out, int d_in, int K, const float* X,
+                                  float* Y, void* factor_ws, size_t factor_bytes, int factors_ready, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  if (!G || !A || !X || !Y || d_out < 1 || d_in < 1 || K < 1 || K > 8)
     return fail(CURV_ERR_INVALID, "curv_kron_apply_tc: bad arguments (two factors, 1 <= K <= 8)");
-  planes = planes == 1 ? 1 : 2;
-  if (hs_ready() <= 0) return fail(CURV_ERR_CUDA, "no CUDA device / tcgen05 kernels unavailable: curvb200 has no CPU fallback");
-  const KronTcPlan p = kron_tc_plan(d_out, d_in, K, planes);
-  if (!ws || ws_bytes < (size_t)p.total_bytes) return fail(CURV_ERR_WORKSPACE, "curv_kron_apply_tc: workspace too small");
+  if (hs_ready() <= 0)
+    return fail(CURV_ERR_CUDA, "no CUDA device / tcgen05 kernels unavailable: curvb200 has no CPU fallback");
+  const KronTcPlan p = kron_tc_plan(d_out, d_in, K);
+  if (!ws || ws_bytes < (size_t)p.total_bytes || !factor_ws || factor_bytes < (size_t)p.factor_bytes)
+    return fail(CURV_ERR_WORKSPACE, "curv_kron_apply_tc: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  char* fb = (char*)factor_ws;
   char* base = (char*)ws;
-  uint32_t* bits = (uint32_t*)(base + p.off_bits);  // [0] G, [8] A, [16..24) X, [32..40) T
-  auto hi = [&](long long off) { return (__half*)(base + off); };
-  auto lo = [&](long long off, long long halves) { return planes == 1 ? (__half*)nullptr : (__half*)(base + off) + halves; };
-  CHECK_CUDA(cudaMemsetAsync(bits, 0, 64 * 4, st));
-  // slack regions of the planes are read (never used) by blocks that reach past a row end: keep them finite
-  CHECK_CUDA(cudaMemsetAsync(base + p.off_G, 0, (size_t)(p.off_T - p.off_G), st));
-  CHECK_CUDA(cudaMemsetAsync(base + p.off_Tp, 0, (size_t)(p.off_P2 - p.off_Tp), st));
-  CHECK_CUDA(cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)d_out * d_in * K, st));
-  if (planes == 2) {
-    kron_absmax_kernel<<<grid1d((long long)d_out * d_out), 256, 0, st>>>(Gt, (long long)d_out * d_out, bits, 1);
-    kron_absmax_kernel<<<grid1d((long long)d_in * d_in), 256, 0, st>>>(At, (long long)d_in * d_in, bits + 8, 1);
-    kron_absmax_kernel<<<grid1d((long long)d_out * d_in * K), 256, 0, st>>>(X, (long long)d_out * d_in * K, bits + 16, 8);
-    g_launches += 3;
-  }
-  kron_split_pad_kernel<<<grid1d((long long)d_out * (p.ldG / 8)), 256, 0, st>>>(Gt, d_out, d_out, d_out, hi(p.off_G),
-                                                                             lo(p.off_G, p.halves_G), p.ldG, bits);
-  kron_split_pad_kernel<<<grid1d((long long)d_in * (p.ldA / 8)), 256, 0, st>>>(At, d_in, d_in, d_in, hi(p.off_A),
-                                                                            lo(p.off_A, p.halves_A), p.ldA, bits + 8);
-  kron_split_pad_kernel<<<grid1d((long long)d_out * (p.ldX / 8)), 256, 0, st>>>(
-      X, (long long)d_in * K, d_out, d_in * K, hi(p.off_X), lo(p.off_X, p.halves_X), p.ldX, bits + 16);
-  g_launches += 3;
-  LAUNCH_CHECK();
-  // ---- step 1: T^T[(b,z)][a] = sum_a' X[a'][(b,z)] Gt[a'][a]
-  float* Tt = (float*)(base + p.off_T);
-  {
-    HsWgradArgs a;
-    memset(&a, 0, sizeof(a));
-    Geom& g = a.g;
-    g.B = d_out; g.Hs = g.Ws = g.Hd = g.Wd = 1; g.Cs = p.ldG; g.KH = g.KW = 1; g.sh = g.sw = 1;
-    g.mode = 0; g.N = p.W8; g.Nd = p.W8; g.Kd = p.ldG; g.M = d_out;
-    a.Gh = hi(p.off_X); a.Gl = lo(p.off_X, p.halves_X); a.G_slot = p.W8; a.G_ld = p.ldX; a.Ng = p.W8;
-    a.g_bits = bits + 16; a.Ih = hi(p.off_G); a.Il = lo(p.off_G, p.halves_G); a.i_bits = bits;
-    a.partial = p.nsplit1 > 1 ? (float*)(base + p.off_P1) : Tt;
-    a.nsplit = p.nsplit1; a.nslots = p.NS1; a.slot0 = 0; a.m_per_split = p.mps1;
-    a.planes = planes;
-    ProfScope prof(1, 2.0 * d_out * (double)d_out * d_in * K, st);
-    if (hs_launch_wgrad(a, st)) return fail(CURV_ERR_CUDA, "Kronecker apply: step-1 contraction launch failed");
-    ++g_launches;
-  }
-  if (p.nsplit1 > 1) {
-    const long long n1 = (long long)p.NS1 * p.W8 * p.ldG;  // one split's partial: [NS1][W8][ldG]
-    kron_sum_splits_kernel<<<grid1d(n1), 256, 0, st>>>((const float*)(base + p.off_P1), p.nsplit1, n1, Tt);
+  uint32_t* fbits = (uint32_t*)(fb + p.f_bits);  // [0] G, [8] A
+  __half* Gh = (__half*)(fb + p.f_G);
+  __half* Gl = Gh + p.g_halves;
+  __half* Aimg = (__half*)(fb + p.f_A);
+  uint32_t* bits = (uint32_t*)(base + p.off_bits);  // [0..8) X columns, [16..24) T columns
+  const int BN_T = tc_bn(p.ldT), BN_Y = tc_bn(pad4(d_in));
+  if (!factors_ready) {  // operand forms of the factors: once per operator
+    CHECK_CUDA(cudaMemsetAsync(fb, 0, (size_t)p.factor_bytes, st));
+    kron_absmax_kernel<<<grid1d((long long)d_out * d_out), 256, 0, st>>>(G, (long long)d_out * d_out, fbits, 1);
+    kron_absmax_kernel<<<grid1d((long long)d_in * d_in), 256, 0, st>>>(A, (long long)d_in * d_in, fbits + 8, 1);
+    kron_split_pad_kernel<<<grid1d((long long)d_out * (p.ldG / 8)), 256, 0, st>>>(G, d_out, d_out, d_out, Gh, Gl, p.ldG,
+                                                                               fbits);
+    const int tiles_n = ceil_div(pad4(d_in), BN_Y), nchunks = p.ldT / HS_BK;
+    kron_pack_image_kernel<<<dim3(hs_grid((long long)tiles_n * nchunks * BN_Y * 8), 1), 256, 0, st>>>(
+        A, d_in, 1, 0, Aimg, 0, d_in, d_in, BN_Y, tiles_n, nchunks, fbits + 8);
+    g_launches += 4;
     LAUNCH_CHECK();
   }
-  const long long t_used = (long long)d_in * K * p.ldG;  // rows (b, z) of T^T that exist
-  if (planes == 2) {
-    kron_absmax_kernel<<<grid1d(t_used), 256, 0, st>>>(Tt, t_used, bits + 32, 8);
-    ++g_launches;
-  }
-  kron_split_pad_kernel<<<grid1d((long long)d_in * K * (p.ldG / 8)), 256, 0, st>>>(
-      Tt, p.ldG, d_in * K, p.ldG, hi(p.off_Tp), lo(p.off_Tp, p.halves_T), p.ldG, bits + 32);
-  LAUNCH_CHECK();
-  // ---- step 2: Y_z[a][B] = sum_b At[b][B] T^T[(b,z)][a]
-  float* part = (float*)(base + p.off_P2);
+  CHECK_CUDA(cudaMemsetAsync(bits, 0, 64 * 4, st));
+  // ---- X: per-column scale (one word for all columns: they come from one vector), images of X_z^T
+  kron_absmax_kernel<<<grid1d((long long)d_out * d_in * K), 256, 0, st>>>(X, (long long)d_out * d_in * K, bits, 8);
   {
-    HsWgradArgs a;
-    memset(&a, 0, sizeof(a));
-    Geom& g = a.g;
-    g.B = d_in; g.Hs = g.Ws = g.Hd = g.Wd = 1; g.Cs = p.ldA; g.KH = g.KW = 1; g.sh = g.sw = 1;
-    g.mode = 0; g.N = d_out; g.Nd = p.ldG; g.Kd = p.ldA; g.M = d_in;
-    a.Gh = hi(p.off_Tp); a.Gl = lo(p.off_Tp, p.halves_T); a.G_slot = p.ldG; a.G_ld = (long long)K * p.ldG; a.Ng = p.ldG;
-    a.g_bits = bits + 32; a.Ih = hi(p.off_A); a.Il = lo(p.off_A, p.halves_A); a.i_bits = bits + 8;
-    a.partial = part; a.nsplit = p.nsplit2; a.nslots = K; a.slot0 = 0; a.m_per_split = p.mps2;
-    a.planes = planes;
-    ProfScope prof(1, 2.0 * d_out * (double)d_in * d_in * K, st);
-    if (hs_launch_wgrad(a, st)) return fail(CURV_ERR_CUDA, "Kronecker apply: step-2 contraction launch failed");
+    const int tiles_n = ceil_div(p.ldT, BN_T), nchunks = p.ldG / HS_BK;
+    // W_z[n = b][k = a'] = X[(a' * d_in + b) * K + z]:  sn = K, sk = d_in * K, slot stride 1
+    kron_pack_image_kernel<<<dim3(hs_grid((long long)tiles_n * nchunks * BN_T * 8), K), 256, 0, st>>>(
+        X, K, (long long)d_in * K, 1, (__half*)(base + p.off_X), p.x_img_halves, d_in, d_out, BN_T, tiles_n, nchunks,
+        bits);
+  }
+  g_launches += 2;
+  LAUNCH_CHECK();
+  // ---- step 1: T_z[a][b] = sum_a' G[a][a'] X_z[a'][b]      (shared activation G, one weight image per column)
+  float* T = (float*)(base + p.off_T);
+  {
+    HsGatherArgs h;
+    memset(&h, 0, sizeof(h));
+    Geom& g = h.g;
+    g.B = d_out; g.Hs = g.Ws = g.Hd = g.Wd = 1; g.Cs = p.ldG; g.KH = g.KW = 1; g.sh = g.sw = 1; g.mode = 0;
+    g.N = d_in; g.Nd = p.ldT; g.Kd = p.ldG; g.M = d_out;
+    h.Ah = Gh; h.Al = Gl; h.A_slot = (long long)d_out * p.ldG; h.a_slot_base = 0; h.a_has_slots = 0; h.a_bits = fbits;
+    h.W_img = (const __half*)(base + p.off_X);
+    h.Wt_img = K > 1 ? (const __half*)(base + p.off_X) + p.x_img_halves : nullptr;
+    h.Wt_img_slot = p.x_img_halves;
+    h.w_bits = bits;
+    h.out = T; h.out_slot = p.t_elems; h.slot0 = 0; h.accumulate = 0; h.planes = 2;
+    ProfScope prof(0, 2.0 * d_out * (double)d_out * d_in * K, st);
+    if (hs_launch_gather_gemm(h, K, st, false, 1)) return fail(CURV_ERR_CUDA, "Kronecker apply: step-1 launch failed");
     ++g_launches;
   }
-  return launch_wgrad_finish(part, p.nsplit2, K, 0, d_out, d_in, p.ldA, 1, Y, 0, K, 0, 1.f,
-                             (long long)d_out * p.ldA, st);
+  // ---- T planes (per-column scales)
+  __half* Th = (__half*)(base + p.off_Tp);
+  __half* Tl = Th + align_up(p.t_elems * K + 8192, 128);
+  CHECK_CUDA(cudaMemsetAsync(Th + p.t_elems * K, 0, 8192 * 2, st));
+  CHECK_CUDA(cudaMemsetAsync(Tl + p.t_elems * K, 0, 8192 * 2, st));
+  if (hs_launch_absmax(T, p.t_elems, p.t_elems, bits + 16, K, st) ||
+      hs_launch_split(T, p.t_elems, p.t_elems, Th, Tl, p.t_elems, bits + 16, K, st))
+    return fail(CURV_ERR_CUDA, "Kronecker apply: split of the intermediate failed");
+  g_launches += 2;
+  // ---- step 2: Y_z[a][B] = sum_b T_z[a][b] A[B][b]
+  float* Yz = (float*)(base + p.off_Y);
+  {
+    HsGatherArgs h;
+    memset(&h, 0, sizeof(h));
+    Geom& g = h.g;
+    g.B = d_out; g.Hs = g.Ws = g.Hd = g.Wd = 1; g.Cs = p.ldT; g.KH = g.KW = 1; g.sh = g.sw = 1; g.mode = 0;
+    g.N = d_in; g.Nd = p.NdY; g.Kd = p.ldT; g.M = d_out;
+    h.Ah = Th; h.Al = Tl; h.A_slot = p.t_elems; h.a_slot_base = 0; h.a_has_slots = 1; h.a_bits = bits + 16;
+    h.W_img = Aimg; h.Wt_img = nullptr; h.w_bits = fbits + 8;
+    h.out = Yz; h.out_slot = p.y_elems; h.slot0 = 0; h.accumulate = 0; h.planes = 2;
+    ProfScope prof(0, 2.0 * d_out * (double)d_in * d_in * K, st);
+    if (hs_launch_gather_gemm(h, K, st, false, K)) return fail(CURV_ERR_CUDA, "Kronecker apply: step-2 launch failed");
+    ++g_launches;
+  }
+  kron_interleave_kernel<<<grid1d((long long)d_out * d_in * K), 256, 0, st>>>(Yz, p.y_elems, p.NdY, d_out, d_in, K, Y);
+  LAUNCH_CHECK();
+  return CURV_OK;
 }

@@ -121,7 +121,8 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
 
     def _apply(self, x: Tensor, transpose: bool) -> Tensor:
         """``x`` is ``[D_in, K]``; returns ``[D_out, K]`` (einsum 'abZ,Aa,Bb->ABZ' of the reference)."""
-        fs = [f.mH if transpose else f for f in self._factors]
+        base = [f if _fp32_master(f) is None else _fp32_master(f) for f in self._factors]
+        fs = [f.mH if transpose else f for f in base]
         K = x.shape[-1]
         x32 = _cuda_f32(x, "Kronecker products")
         if len(fs) == 1:
@@ -137,20 +138,21 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
         d_out, d_in = G.shape[0], A.shape[0]
         Y = torch.empty(d_out * d_in, K, device=x32.device, dtype=torch.float32)
         if min(d_out, d_in) >= TENSOR_CORE_MIN_DIM:
-            # blocks of real networks: both contractions on the tcgen05 kernel; it takes the TRANSPOSED factors
-            # (symmetric ones as they are).  Operands as fp16 hi/lo planes (fp32-grade) for bf16 operators too: rows of
-            # a gradient covariance sum to ~0 against smooth vectors, and bf16-rounded operands (measured on ResNet-18:
-            # 4e-2 of the result) do not survive that cancellation; the apply is ~3 ms either way.
-            planes = 2
-            Gt, At = self._transposed(0, transpose), self._transposed(1, transpose)
+            # blocks of real networks: both contractions on the tcgen05 kernel, operands as fp16 hi/lo planes
+            # (fp32-grade) for bf16 operators too: rows of a gradient covariance sum to ~0 against smooth vectors, and
+            # bf16-rounded operands (measured on ResNet-18: 4e-2 of the result) do not survive that cancellation.
+            # The operand forms of the two factors are built once and cached (they only change with the factors).
+            fws, ready = self._factor_operands(transpose, G, A)
             for k0 in range(0, K, 8):
                 kk = min(8, K - k0)
                 xk = x32 if kk == K else x32[:, k0:k0 + kk].contiguous()
                 yk = Y if kk == K else torch.empty(d_out * d_in, kk, device=x32.device, dtype=torch.float32)
-                nbytes = capi.lib().curv_kron_apply_tc_workspace(d_out, d_in, kk, planes)
+                nbytes = capi.lib().curv_kron_apply_tc_workspace(d_out, d_in, kk)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=x32.device)
-                capi.check(capi.lib().curv_kron_apply_tc(Gt.data_ptr(), At.data_ptr(), d_out, d_in, kk, xk.data_ptr(),
-                                                         yk.data_ptr(), planes, ws.data_ptr(), nbytes, _stream(x32)))
+                capi.check(capi.lib().curv_kron_apply_tc(G.data_ptr(), A.data_ptr(), d_out, d_in, kk, xk.data_ptr(),
+                                                         yk.data_ptr(), fws.data_ptr(), fws.numel(), int(ready),
+                                                         ws.data_ptr(), nbytes, _stream(x32)))
+                ready = True
                 if kk != K:
                     Y[:, k0:k0 + kk] = yk
             return Y.to(x.dtype)
@@ -159,25 +161,18 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
                                               Y.data_ptr(), tmp.data_ptr(), _stream(x32)))
         return Y.to(x.dtype)
 
-    def _transposed(self, index: int, adjoint: bool) -> Tensor:
-        """The factor the operator applies (``f``, or ``f^H`` for the adjoint product), TRANSPOSED, as a contiguous
-        fp32 matrix for ``curv_kron_apply_tc``: symmetric factors (Kronecker factors and their inverses) and the
-        adjoint case need no copy.  Cached per factor object / version."""
-        src = self._factors[index]
-        f32 = _cuda_f32(src, "Kronecker products")
-        if adjoint:
-            return f32
-        key = (index, id(src), src._version)
-        cache = self.__dict__.setdefault("_t_cache", {})
-        hit = cache.get(key)
-        if hit is None:
-            # EXACT symmetry only: an asymmetry at rounding level would be amplified by the cancellation inside the
-            # product (KFAC's computer symmetrises its factors; Cholesky inverses are symmetric by construction)
-            hit = f32 if torch.equal(f32, f32.T) else f32.T.contiguous()
-            for k in [k for k in cache if k[0] == index]:
-                del cache[k]
-            cache[key] = hit
-        return hit
+    def _factor_operands(self, adjoint: bool, G: Tensor, A: Tensor):
+        """Device buffer with the tensor-core operand forms of the two factors (``curv_kron_apply_tc`` fills it on first
+        use) and whether it is current: keyed on the factor objects and their version counters."""
+        key = tuple((id(f), f._version) for f in self._factors) + (G.data_ptr(), A.data_ptr())
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        hit = cache.get(adjoint)
+        if hit is not None and hit[0] == key:
+            return hit[1], True
+        nbytes = capi.lib().curv_kron_apply_tc_factor_bytes(G.shape[0], A.shape[0])
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=G.device)
+        cache[adjoint] = (key, buf, G, A)  # G / A kept alive: their addresses are part of the key
+        return buf, False
 
     def _matmat(self, X: list[Tensor]) -> list[Tensor]:
         (x,) = X
@@ -260,7 +255,7 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
             warn(f"Failed to compute Cholesky decomposition in {A.dtype} precision with error {error}. "
                  "Retrying in double precision...", stacklevel=2)
             L = chol(A.to(torch.float64)).to(A.dtype)
-        return torch.cholesky_inverse(L)
+        return torch.cholesky_inverse(L).contiguous()  # (LAPACK-ordered result: row-major once, not on every product)
 
 
 class EighDecomposedLinearOperator(PyTorchLinearOperator):

@@ -183,15 +183,19 @@ int curv_eigh_apply(const float* Qg, const float* Qa, const float* lambda, float
                     int d_out, int d_in, int K, const float* X, float* Y, float* tmp, float* tmp2,
                     void* stream);
 
-/* The same two-sided product on the tcgen05 contraction kernel (csrc/kron_tc.cuh), for the block sizes of real
-   networks:  Y[d_out, d_in, K] = Gt^T . X . At  with the TRANSPOSED factors Gt = G^T [d_out,d_out], At = A^T
-   [d_in,d_in] (symmetric Kronecker factors and their damped inverses, kronecker.py:250-373, are their own
-   transposes; with eigenvector matrices as factors these are the rotations of eigh.py:98-104).  1 <= K <= 8.
-   planes = 2: fp32-grade (operands as fp16 hi/lo planes, three MMAs per product); planes = 1: bf16 operands (bf16
-   operators).  ws: caller-owned scratch of curv_kron_apply_tc_workspace(...) bytes. */
-size_t curv_kron_apply_tc_workspace(int d_out, int d_in, int K, int planes);
-int curv_kron_apply_tc(const float* Gt, const float* At, int d_out, int d_in, int K, const float* X, float* Y,
-                       int planes, void* ws, size_t ws_bytes, void* stream);
+/* The same two-sided product on the tcgen05 contraction kernels (csrc/kron_tc.cuh), for the block sizes of real
+   networks (KFAC and its damped inverse, kronecker.py:250-373; with eigenvector matrices as factors the rotations of
+   eigh.py:98-104):  Y[d_out, d_in, K] = G . X . A^T for any square G [d_out,d_out], A [d_in,d_in], 1 <= K <= 8, as two
+   K-major GEMMs (T_z = G X_z with X_z^T as weight images; Y_z = T_z A^T with A as weight image), fp32-grade (operands
+   as fp16 hi/lo planes, three MMAs per product, chunked tensor-memory accumulation).
+   factor_ws: caller-owned buffer of curv_kron_apply_tc_factor_bytes(d_out, d_in) bytes holding the operand forms of the
+   two factors; the call fills it unless factors_ready != 0 (build once per operator, reuse for every product).
+   ws: caller-owned scratch of curv_kron_apply_tc_workspace(d_out, d_in, K) bytes. */
+size_t curv_kron_apply_tc_workspace(int d_out, int d_in, int K);
+size_t curv_kron_apply_tc_factor_bytes(int d_out, int d_in);
+int curv_kron_apply_tc(const float* G, const float* A, int d_out, int d_in, int K, const float* X, float* Y,
+                       void* factor_ws, size_t factor_bytes, int factors_ready, void* ws, size_t ws_bytes,
+                       void* stream);
 
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major, hand-written kernels (no cuBLAS).  */
 int curv_gemm(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,

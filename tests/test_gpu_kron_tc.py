@@ -1,6 +1,6 @@
-"""The two-sided Kronecker apply on the tcgen05 kernel (``curv_kron_apply_tc``, reference ``kronecker.py:141-153``)
-against float64 on random blocks at the shapes of real layers, including non-symmetric factors (the transposed copies
-the host mirror hands over), K > 8 (chunked), and a factor whose rows sum to zero (a gradient covariance under the
+"""The two-sided Kronecker apply on the tcgen05 kernels (``curv_kron_apply_tc``, reference ``kronecker.py:141-153``)
+against float64 on random blocks at the shapes of real layers, including non-symmetric factors, the adjoint product,
+K > 8 (chunked), repeated products (cached factor operands), and a factor whose rows sum to zero (a gradient covariance under the
 softmax: the product then cancels to far below its terms and every fp32 evaluation loses digits -- the strict-fp32
 cuBLAS product is printed as the yardstick).  Tolerance: 1e-4 of the largest entry (fp32), 2x the yardstick under
 cancellation."""
@@ -79,3 +79,19 @@ def test_kron_apply_on_kfac_like_factors(which):
     e = _kfac_like(which)
     print(f"[fc block, KFAC-like {which}] engine {e:.2e}")
     assert e < 1e-4, e
+
+
+def test_kron_adjoint_and_cached_factor_operands():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    G, A = torch.randn(96, 96, device="cuda", generator=g), torch.randn(200, 200, device="cuda", generator=g)
+    X = torch.rand(96 * 200, 2, device="cuda", generator=g)
+    op = KroneckerProductLinearOperator(G, A)
+    dense = torch.kron(G.double(), A.double())
+    ref = dense @ X.double()
+    atol = 1e-5 * ref.abs().max().item()
+    for _ in range(2):  # second product: factor operands come from the cache
+        torch.testing.assert_close((op @ X).double(), ref, rtol=1e-4, atol=atol)
+        torch.testing.assert_close((X.T @ op).double(), X.double().T @ dense, rtol=1e-4, atol=atol)
+    assert op._tc_cache[False][0][:2] == tuple((id(f), f._version) for f in op)
+    op[0] = G * 2.0  # a replaced factor invalidates the cached operands
+    torch.testing.assert_close((op @ X).double(), 2.0 * ref, rtol=1e-4, atol=2 * atol)
