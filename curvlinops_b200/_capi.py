@@ -40,7 +40,7 @@ EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_kron_apply_tc", "curv_kron_apply_tc_workspace", "curv_kron_apply_tc_factor_bytes",
-    "curv_eigh_apply", "curv_gemm", "curv_last_error", "curv_abi_version",
+    "curv_eigh_apply", "curv_gemm", "curv_gemm_batched", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_add_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
 ]
@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
     L.curv_eigh_apply.restype = i
     L.curv_gemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i, vp]
     L.curv_gemm.restype = i
+    L.curv_gemm_batched.argtypes = [i, i, i, i, i, f, vp, i, ll, vp, i, ll, f, vp, i, ll, i, vp]
+    L.curv_gemm_batched.restype = i
     L.curv_last_error.argtypes = []
     L.curv_last_error.restype = C.c_char_p
     L.curv_abi_version.argtypes = []

@@ -1326,6 +1326,16 @@ extern "C" int curv_gemm(int transA, int transB, int M, int N, int Kd, float alp
                     (cudaStream_t)stream);
 }
 
+// `batch` independent products C_b = alpha op(A_b) op(B_b) + beta C_b with element strides sA / sB / sC between them
+// (one launch; the per-example contractions of the EKFAC eigenvalue correction, ekfac_hooks.py:215-236)
+extern "C" int curv_gemm_batched(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
+                                 long long sA, const float* B, int ldb, long long sB, float beta, float* C, int ldc,
+                                 long long sC, int batch, void* stream) {
+  if (batch < 1 || batch > 65535) return fail(CURV_ERR_INVALID, "curv_gemm_batched: 1 <= batch <= 65535");
+  return dense_gemm(transA, transB, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, batch, sA, sB, sC,
+                    (cudaStream_t)stream);
+}
+
 // X, Y: [d_out][d_in][K] (K minor).  Y = G X A^T per column.
 //   step 1: T[a][(b,z)] = sum_a' G[a][a'] X[a'][(b,z)]           plain GEMM, N = d_in*K
 //   step 2: Y[a][B][z]  = sum_b  A[B][b] T[a][b][z]              batched over a: A (d_in x d_in) @ T_a (d_in x K)

@@ -31,8 +31,8 @@ from .curvature import CurvatureLinearOperator
 from .engine import CompiledProgram
 from .linop import _ChainPyTorchLinearOperator
 from .structured import (BlockDiagonalLinearOperator, EighDecomposedLinearOperator,
-                         KroneckerProductLinearOperator, ToCanonicalLinearOperator, dense_matmul,
-                         with_fp32_master)
+                         KroneckerProductLinearOperator, ToCanonicalLinearOperator, batched_matmul_tn,
+                         dense_matmul, with_fp32_master)
 
 
 class _MetaEnum(EnumMeta):
@@ -410,8 +410,7 @@ class EKFACComputer(KFACComputer):
                             a = torch.cat([a, a.new_ones(*a.shape[:-1], 1)], dim=-1)
                         at = dense_matmul(a.reshape(-1, a.shape[-1]), QA[key]).reshape(a.shape)
                         # per-example gradient in the eigenbasis: E_n = gt_n^T at_n  (sum over S)
-                        E = torch.stack([dense_matmul(gt[n].t().contiguous(), at[n]) for n in range(B)]) \
-                            if gt.shape[1] > 1 else gt[:, 0, :, None] * at[:, 0, None, :]
+                        E = batched_matmul_tn(gt, at) if gt.shape[1] > 1 else gt[:, 0, :, None] * at[:, 0, None, :]
                     else:
                         E = gt.sum(1)
                     cur = (E ** 2).sum(0) * corr

@@ -89,6 +89,20 @@ def dense_matmul(A: Tensor, X: Tensor, transpose_a: bool = False) -> Tensor:
     return Y.to(X.dtype)
 
 
+def batched_matmul_tn(A: Tensor, B: Tensor) -> Tensor:
+    """``C[n] = A[n]^T @ B[n]`` for fp32 CUDA tensors ``A [N, S, P]``, ``B [N, S, Q]`` -> ``[N, P, Q]`` in ONE launch of the
+    hand-written batched kernel (``curv_gemm_batched``; no cuBLAS)."""
+    A32, B32 = _cuda_f32(A, "batched products"), _cuda_f32(B, "batched products")
+    N, S, P = A32.shape
+    Q = B32.shape[2]
+    out = torch.empty(N, P, Q, device=A32.device, dtype=torch.float32)
+    for n0 in range(0, N, 65535):
+        nb = min(65535, N - n0)
+        capi.check(capi.lib().curv_gemm_batched(1, 0, P, Q, S, 1.0, A32[n0:].data_ptr(), P, S * P, B32[n0:].data_ptr(), Q,
+                                                S * Q, 0.0, out[n0:].data_ptr(), Q, P * Q, nb, _stream(A32)))
+    return out
+
+
 class KroneckerProductLinearOperator(PyTorchLinearOperator):
     r"""``S_1 \otimes S_2`` (one or two factors) acting on ``vec`` of a row-major ``[d_1, d_2]`` matrix."""
 
@@ -121,13 +135,12 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
 
     def _apply(self, x: Tensor, transpose: bool) -> Tensor:
         """``x`` is ``[D_in, K]``; returns ``[D_out, K]`` (einsum 'abZ,Aa,Bb->ABZ' of the reference)."""
-        base = [f if _fp32_master(f) is None else _fp32_master(f) for f in self._factors]
-        fs = [f.mH if transpose else f for f in base]
+        fs = [self._f32(i, transpose) for i in range(len(self._factors))]
         K = x.shape[-1]
         x32 = _cuda_f32(x, "Kronecker products")
         if len(fs) == 1:
             return dense_matmul(fs[0], x32).to(x.dtype)
-        G, A = (_cuda_f32(f, "Kronecker products") for f in fs)
+        G, A = fs
         if G.shape[0] != G.shape[1] or A.shape[0] != A.shape[1]:
             # rectangular factors: two plain products  Y = G (X A^T)
             d_out_in, d_in_in = G.shape[1], A.shape[1]
@@ -160,6 +173,20 @@ class KroneckerProductLinearOperator(PyTorchLinearOperator):
         capi.check(capi.lib().curv_kron_apply(G.data_ptr(), A.data_ptr(), d_out, d_in, K, x32.data_ptr(),
                                               Y.data_ptr(), tmp.data_ptr(), _stream(x32)))
         return Y.to(x.dtype)
+
+    def _f32(self, index: int, transpose: bool) -> Tensor:
+        """Factor ``index`` (its fp32 master for bf16 operators), transposed for the adjoint product, as a contiguous
+        fp32 CUDA matrix; cached per factor object / version so that repeated products see the same buffer."""
+        f = self._factors[index]
+        key = (id(f), f._version)
+        cache = self.__dict__.setdefault("_f32_cache", {})
+        hit = cache.get((index, transpose))
+        if hit is None or hit[0] != key:
+            m = _fp32_master(f)
+            base = f if m is None else m
+            hit = (key, _cuda_f32(base.mH if transpose else base, "Kronecker products"))
+            cache[(index, transpose)] = hit
+        return hit[1]
 
     def _factor_operands(self, adjoint: bool, G: Tensor, A: Tensor):
         """Device buffer with the tensor-core operand forms of the two factors (``curv_kron_apply_tc`` fills it on first
@@ -309,6 +336,11 @@ class EighDecomposedLinearOperator(PyTorchLinearOperator):
             return [dense_matmul(fs[0], lam32.unsqueeze(1) * QTx).to(x.dtype)]
         Qg, Qa = fs
         d_out, d_in = Qg.shape[0], Qa.shape[0]
+        if (isinstance(Q, KroneckerProductLinearOperator) and min(d_out, d_in) >= TENSOR_CORE_MIN_DIM
+                and Qg.shape[0] == Qg.shape[1] and Qa.shape[0] == Qa.shape[1]):
+            # the two rotations of eigh.py:98-104 on the tensor-core Kronecker apply: (Qg (x) Qa)^T x, scale, back
+            rot = Q._apply(x32, transpose=True)
+            return [Q._apply(lam32.unsqueeze(1) * rot, transpose=False).to(x.dtype)]
         Y = torch.empty(d_out * d_in, K, device=x32.device, dtype=torch.float32)
         t1, t2 = torch.empty_like(Y), torch.empty_like(Y)
         capi.check(capi.lib().curv_eigh_apply(Qg.data_ptr(), Qa.data_ptr(), lam32.data_ptr(), 0.0, 0, d_out,

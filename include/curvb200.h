@@ -201,6 +201,11 @@ int curv_kron_apply_tc(const float* G, const float* A, int d_out, int d_in, int 
 int curv_gemm(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, void* stream);
 
+/* `batch` independent products with element strides sA / sB / sC between consecutive operands (one launch). */
+int curv_gemm_batched(int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
+                      long long sA, const float* B, int ldb, long long sB, float beta, float* C, int ldc,
+                      long long sC, int batch, void* stream);
+
 const char* curv_last_error(void);
 int curv_abi_version(void);
 /* number of kernel launches issued by this library since process start (bench `gpu_launches`) */

@@ -78,9 +78,12 @@ def test_capture_flatten_linear_becomes_valid_conv():
 
 
 def test_capture_rejects_unsupported():
-    model = nn.Sequential(nn.Linear(4, 4), nn.GELU(), nn.Linear(4, 2))
+    model = nn.Sequential(nn.Linear(4, 4), nn.Softplus(), nn.Linear(4, 2))
     with pytest.raises(NotImplementedError, match="not supported by the B200"):
         capture(make_functional_call(model), dict(model.named_parameters()), torch.rand(2, 4))
+    tanh_gelu = nn.Sequential(nn.Linear(4, 4), nn.GELU(approximate="tanh"), nn.Linear(4, 2))
+    with pytest.raises(NotImplementedError, match="exact"):
+        capture(make_functional_call(tanh_gelu), dict(tanh_gelu.named_parameters()), torch.rand(2, 4))
     bn = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4)).train()
     with pytest.raises(NotImplementedError, match="eval"):
         capture(make_functional_call(bn), dict(bn.named_parameters()), torch.rand(2, 3, 8, 8))
@@ -262,3 +265,24 @@ def test_functional_call_and_default_batch_size_fn_are_picklable():
     f = pickle.loads(pickle.dumps(make_functional_call(nn.Linear(3, 2))))
     assert f({}, torch.ones(1, 3)).shape == (1, 2)
     assert pickle.loads(pickle.dumps(_leading_dim))(torch.ones(5, 1)) == 5
+
+
+def test_capture_layernorm_gelu_tokens():
+    from oracle.models import TokenMLP, mlp_ln_gelu
+
+    m = TokenMLP().eval()
+    lp = capture(make_functional_call(m), dict(m.named_parameters()), torch.rand(3, 7, 12))
+    ops = [n["op"] for n in lp.nodes]
+    assert lp.tokens_input and ops.count(capi.OP_LAYERNORM) == 2 and ops.count(capi.OP_GELU) == 1
+    assert ops.count(capi.OP_CONV) == 3 and ops.count(capi.OP_ADD) == 1 and ops.count(capi.OP_AVGPOOL) == 1
+    assert lp.values[0][:3] == [12, 1, 7] and lp.values[lp.nodes[-1]["out"]][:3] == [5, 1, 1]  # tokens = the W axis
+    ln = [n for n in lp.nodes if n["op"] == capi.OP_LAYERNORM][0]
+    assert ln["p0"] >= 0 and ln["p1"] >= 0 and abs(ln["eps"] - 1e-5) < 1e-12
+    m2 = mlp_ln_gelu().eval()
+    lp2 = capture(make_functional_call(m2), dict(m2.named_parameters()), torch.rand(4, 16))
+    assert [n["op"] for n in lp2.nodes] == [capi.OP_INPUT, capi.OP_CONV, capi.OP_LAYERNORM, capi.OP_GELU, capi.OP_CONV,
+                                           capi.OP_LAYERNORM, capi.OP_RELU, capi.OP_CONV]
+    # LayerNorm over the width of an image tensor is not the channel axis: rejected
+    bad = nn.Sequential(nn.Conv2d(3, 4, 3), nn.LayerNorm(6), nn.Flatten(), nn.Linear(4 * 6 * 6, 2))
+    with pytest.raises(NotImplementedError, match="LayerNorm"):
+        capture(make_functional_call(bad), dict(bad.named_parameters()), torch.rand(2, 3, 8, 8))
