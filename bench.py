@@ -24,7 +24,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "ggn_matvec_throughput"
+METRIC = "ggn_matvec_throughput"  # ("hessian_matvec_throughput" for --config c2-hessian)
 UNIT = "param*vec/s"
 B, K = 128, 8
 #: --config: c2 = BASELINE.json configs[1] (the configuration the metric is quoted on; default);
@@ -32,6 +32,8 @@ B, K = 128, 8
 WORKLOADS = {
     "c2": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, fp32", "f32"),
     "c2-bf16": ("ResNet-18 random-init, synthetic 128x3x224x224, GGNLinearOperator @ 8 vectors, bf16", "bf16"),
+    # the C2 workload with the full Hessian (hand-written R-op, 3xTF32 tensor-core kernels) instead of the GGN
+    "c2-hessian": ("ResNet-18 random-init, synthetic 128x3x224x224, HessianLinearOperator @ 8 vectors, fp32", "f32"),
     # BASELINE.json configs[0]: the reference's own CPU-runnable case; pure latency (6.6 MFLOP per product)
     "c1": ("3-layer MLP (D=64, 4 Linear+ReLU, CE loss), batch=32, HessianLinearOperator @ 1 vector", "f32"),
     # BASELINE.json configs[2]: its own metric (a step = one factor build), printed as an extra line
@@ -152,8 +154,8 @@ def reference_ggn(torch, device, batch, k, repeats, warmup=0):
     P = sum(p.numel() for p in params.values())
     torch.manual_seed(1)
     V = torch.rand(P, k).to(device).to(next(iter(params.values())).dtype)
-    G = ref.GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False,
-                              num_data=batch)
+    RefOp = ref.HessianLinearOperator if CONFIG == "c2-hessian" else ref.GGNLinearOperator
+    G = RefOp(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=batch)
     sync = torch.cuda.synchronize if device.type == "cuda" else (lambda: None)
     times = []
     for i in range(warmup + repeats):
@@ -172,7 +174,7 @@ def cpu_reference_run(torch, repeats, sample_batch=B, sample_k=K):
     columns."""
     torch.set_num_threads(host_threads())
     global CONFIG
-    cfg, CONFIG = CONFIG, "c2"  # bf16 configs are timed in fp32 on the CPU (BASELINE.md section 4: CPU bf16
+    cfg, CONFIG = CONFIG, ("c2" if CONFIG == "c2-bf16" else CONFIG)  # bf16 is timed in fp32 on the CPU (BASELINE.md 4: CPU bf16
     try:                        # convolutions are not representative; the reference's inverse cannot run in bf16)
         t, P = reference_ggn(torch, torch.device("cpu"), sample_batch, sample_k, repeats)
     finally:
@@ -183,7 +185,7 @@ def cpu_reference_run(torch, repeats, sample_batch=B, sample_k=K):
         "kind": "reference", "cores": torch.get_num_threads(),
         "sample": (f"full step (B={B}, K={K}), best of {repeats}" if full else
                    f"{sample_batch} of {B} samples, {sample_k} of {K} columns, best of {repeats}, "
-                   "extrapolated linearly to the full step") + (", fp32 on the CPU" if cfg != "c2" else "")}
+                   "extrapolated linearly to the full step") + (", fp32 on the CPU" if cfg == "c2-bf16" else "")}
 
 
 def gpu_library_baseline(torch, dev, repeats=3):
@@ -424,6 +426,9 @@ def main():
     global CONFIG, WORKLOAD
     CONFIG, WORKLOAD = args.config, WORKLOADS[args.config][0]
     DTYPE = WORKLOADS[CONFIG][1]
+    global METRIC
+    if CONFIG == "c2-hessian":
+        METRIC = "hessian_matvec_throughput"
     if args.impl == "reference":  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it may
         for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ.pop(v, None)
@@ -460,8 +465,10 @@ def main():
 
     import torch.distributed as dist
 
-    from curvlinops_b200 import GGNLinearOperator, _capi as capi
+    from curvlinops_b200 import GGNLinearOperator, HessianLinearOperator, _capi as capi
     from curvlinops_b200 import dist as cdist
+
+    Operator = HessianLinearOperator if CONFIG == "c2-hessian" else GGNLinearOperator
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -493,8 +500,8 @@ def main():
     X_host, y_host = X.pin_memory(), y.pin_memory()
     Xd, yd, Vd = X.to(dev), y.to(dev), V_host.to(dev)
     loss = torch.nn.CrossEntropyLoss()
-    G = GGNLinearOperator(model, loss, params, [(Xd, yd)], check_deterministic=False, num_data=B)
-    G_host = GGNLinearOperator(model, loss, params, [(X_host, y_host)], check_deterministic=False, num_data=B)
+    G = Operator(model, loss, params, [(Xd, yd)], check_deterministic=False, num_data=B)
+    G_host = Operator(model, loss, params, [(X_host, y_host)], check_deterministic=False, num_data=B)
     G_host._engine = G._engine  # share compiled program + workspace
 
     def barrier():

@@ -40,7 +40,7 @@ EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_kron_apply_tc", "curv_kron_apply_tc_workspace", "curv_kron_apply_tc_factor_bytes",
-    "curv_eigh_apply", "curv_gemm", "curv_gemm_batched", "curv_last_error", "curv_abi_version",
+    "curv_eigh_apply", "curv_gemm", "curv_gemm_batched", "curv_ekfac_correction_batch", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_add_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
 ]
@@ -79,6 +79,9 @@ def lib() -> C.CDLL:
                                              C.POINTER(vp), C.POINTER(vp), C.POINTER(i), vp, i, f, f,
                                              vp, C.c_size_t, vp]
     L.curv_kfac_accumulate_batch.restype = i
+    L.curv_ekfac_correction_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(i), i, C.POINTER(vp),
+                                              C.POINTER(vp), C.POINTER(vp), C.POINTER(i), vp, i, f, vp, C.c_size_t, vp]
+    L.curv_ekfac_correction_batch.restype = i
     L.curv_kron_apply.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.curv_kron_apply.restype = i
     L.curv_kron_apply_tc.argtypes = [vp, vp, i, i, i, vp, vp, vp, C.c_size_t, i, vp, C.c_size_t, vp]

@@ -117,6 +117,7 @@ static long long gram_partial_elems(long long rows, int width, int widthp) {
 }
 
 static long long gram_hs_plan_elems(long long rows, int ld, int planes);  // kfac.cuh
+static long long ekfac_scratch_elems(long long M, int B, int S, int d_in_width, int Cp_out);  // ekfac.cuh
 
 extern "C" const char* curv_last_error(void) { return g_err.c_str(); }
 extern "C" int curv_abi_version(void) { return CURV_ABI_VERSION; }
@@ -239,6 +240,10 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         long long needHG = gram_hs_plan_elems(g.M, vo.Cp, planes);
         if (needH > scratch) scratch = needH;
         if (needHG > scratch) scratch = needHG;
+        if (!(hessian & 4)) {  // EKFAC eigenvalue correction (fp32 operators): rotated operands + per-example partials
+          long long needE = ekfac_scratch_elems(g.M, batch, vo.H * vo.W, width, vo.Cp);
+          if (needE > scratch) scratch = needE;
+        }
       }
       if (d.p1 >= 0) {  // bias grad = column sum of the output cotangent
         long long rows = g.M;
@@ -449,6 +454,8 @@ struct Ctx {
   bool rop;  // Hessian R-op: slot 0 of the cotangent storage holds the plain backward
   float** kfac_G = nullptr;  // KFAC mode: per node, the G factor to accumulate into (or null); no param grads
   float kfac_wG = 0.f;
+  // EKFAC eigenvalue-correction mode (ekfac.cuh): per node the eigenvector matrices and the lambda to accumulate into
+  const struct EkfacJob* ekfac = nullptr;
   // streaming calls (curv_matmat_batch_sync): per-parameter events.  v_ready[p]: the rows of V of parameter p are
   // on the device (waited for before the node that owns p is prepared, lazily, inside the forward sweep);
   // out_done[p]: recorded once the rows of `out` of parameter p are final (after the node's finish kernels).
@@ -913,6 +920,21 @@ __global__ void hs_bits_fill_kernel(uint32_t* dst, int n, const uint32_t* src, u
 static int gram_hs(const __half* Xh, const __half* Xl, int planes, long long rows, int width, int ld,
                    const uint32_t* sbits, int C, int taps, float* F, float w, float* partial,
                    long long partial_elems, cudaStream_t st);
+// EKFAC eigenvalue correction (ekfac.cuh)
+struct EkfacEntry {
+  int node;
+  const float *Qa, *Qg;
+  float* lam;
+  int joint;      // ones column appended to the patches (joint weight + bias group)
+  int bias_only;  // bias group: the "patch" is the ones column alone (Qa = [[1]], lambda is [d_out, 1])
+};
+struct EkfacJob {
+  std::vector<EkfacEntry> entries;
+  std::vector<char> has;  // per node: some entry collects it
+  float w = 0.f;
+};
+struct Ctx;
+static int ekfac_layer(const Ctx& c, const struct Node& n, const EkfacEntry& e, int slot_index, int abs_slot);
 
 // backward sweep over cotangent slots [s0, s0+ns) of the grad storage.
 //   GGN / VJP: s0 = 1, ns = K.      Hessian R-op: s0 = 0, ns = K+1 (slot 0 = plain backward).
@@ -956,8 +978,9 @@ static int backward(const Ctx& c, int K) {
         const int nidx = ni;
         const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, ns);
         const bool hs_d = vi.tan && hs_dgr_ok(c, n);
+        const bool ek = c.ekfac != nullptr && c.ekfac->has[ni];
         const int eg = c.bits_grad(d.out);
-        if ((hs_w || hs_d || hs_g) && planes_of != d.out) {  // fp16 hi/lo planes of the cotangent slots (wgrad + dgrad)
+        if ((hs_w || hs_d || hs_g || ek) && planes_of != d.out) {  // fp16 hi/lo planes of the cotangent slots (wgrad + dgrad)
           int rc = hs_absmax(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, eg + s0, ns);
           if (!rc) rc = hs_split(c, c.grad(d.out, s0), vo.slot_elems, vo.slot_elems, c.hs1_hi(), c.hs1_lo(),
                                  eg + s0, ns);
@@ -973,6 +996,15 @@ static int backward(const Ctx& c, int K) {
                              c.planes == 1 ? nullptr : c.hs1_lo() + (long long)sl * vo.slot_elems, c.planes, g.M, vo.C,
                              vo.Cp, sb, vo.C, 1, c.kfac_G[nidx], c.kfac_wG, scratch, P->scratch_elems, st);
             if (rc) return rc;
+          }
+        }
+        if (ek) {  // EKFAC: per-example gradients in the Kronecker eigenbasis, squared and summed (one slot at a time)
+          for (const EkfacEntry& e : c.ekfac->entries) {
+            if (e.node != nidx) continue;
+            for (int sl = 0; sl < ns; ++sl) {
+              int rc = ekfac_layer(c, n, e, sl, s0 + sl);
+              if (rc) return rc;
+            }
           }
         }
         if (hs_w) {  // weight gradients of all slots on the half-split kernel
@@ -1416,3 +1448,4 @@ extern "C" int curv_eigh_apply(const float* Qg, const float* Qa, const float* la
 
 #include "kfac.cuh"
 #include "kron_tc.cuh"
+#include "ekfac.cuh"

@@ -376,7 +376,88 @@ class EKFACComputer(KFACComputer):
         return ({k: with_fp32_master(v, dt) for k, v in QA.items()}, {k: with_fp32_master(v, dt) for k, v in QG.items()},
                 {k: with_fp32_master(v, dt) for k, v in lam.items()}, mapping)
 
+    #: run the eigenvalue correction on the device (``curv_ekfac_correction_batch``); False: the host-orchestrated
+    #: round-1 path (F.unfold + per-group dense products), kept as a cross-check for the tests
+    DEVICE_CORRECTION = True
+
     def _eigenvalue_correction(self, QA, QG, mapping):
+        """Second pass: per-example gradients in the Kronecker eigenbasis, squared and summed
+        (``ekfac_hooks.py:25-238``), on the tensor-core kernels: see ``csrc/ekfac.cuh``."""
+        if not self.DEVICE_CORRECTION:
+            return self._eigenvalue_correction_host(QA, QG, mapping)
+        dev = self.device
+        eng = self._engine
+        rank, world = cdist.rank_world()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(self._seed)
+        N = self._N_data
+        lam, qa32, qg32 = {}, {}, {}
+        one = torch.ones(1, 1, device=dev, dtype=torch.float32)
+        for group in mapping:
+            key = tuple(group.values())
+            qg32[key] = QG[key].float().contiguous()
+            if "W" in group:
+                qa32[key] = QA[key].float().contiguous()
+                lam[key] = torch.zeros(qg32[key].shape[0], qa32[key].shape[0], device=dev, dtype=torch.float32)
+            else:
+                qa32[key] = one
+                lam[key] = torch.zeros(qg32[key].shape[0], 1, device=dev, dtype=torch.float32)
+        L = capi.lib()
+        for bi, (X, y) in enumerate(self._loop_over_data(desc="EKFAC eigenvalue correction")):
+            if not isinstance(X, Tensor):
+                raise NotImplementedError("The B200 engine needs tensor inputs X.")
+            B_glob = X.shape[0]
+            lo, hi = (0, B_glob) if world == 1 else cdist.shard_bounds(B_glob, rank, world)
+            if hi == lo:
+                continue
+            X = X[lo:hi].to(torch.float32).contiguous()
+            prog = self._correction_program(X)
+            ws = eng.workspace(prog.ws_bytes, dev)
+            f = eng.predict(X)
+            gos = (self._grad_outputs_override[bi].to(dev).float()[:, lo:hi] if self._grad_outputs_override is not None
+                   else self._grad_outputs(f, y[lo:hi], gen))
+            red = self._loss_func.reduction
+            scale = 1.0 / B_glob if red == "mean" else 1.0
+            corr = B_glob * B_glob / N if red == "mean" else 1.0
+            seeds = (gos * scale).permute(1, 2, 0).contiguous()  # [B, C, V]
+            nodes, qa_p, qg_p, lam_p, kinds = [], [], [], [], []
+            for group in mapping:
+                key = tuple(group.values())
+                nodes.append(self._group_node(prog, group))
+                qa_p.append(qa32[key].data_ptr()); qg_p.append(qg32[key].data_ptr()); lam_p.append(lam[key].data_ptr())
+                kinds.append(2 if "W" not in group else (1 if "b" in group else 0))
+            n = len(nodes)
+            keep, pptrs = eng._param_ptrs()
+            capi.check(L.curv_ekfac_correction_batch(
+                prog.handle, pptrs, prog.const_ptrs, prog.engine_input(X).data_ptr(), (C.c_int * n)(*nodes), n,
+                capi.ptr_array(qa_p), capi.ptr_array(qg_p), capi.ptr_array(lam_p), (C.c_int * n)(*kinds),
+                seeds.data_ptr(), seeds.shape[2], float(corr), ws.data_ptr(), ws.numel() * 4,
+                torch.cuda.current_stream(dev).cuda_stream))
+            del keep
+        if world > 1:
+            flat = torch.cat([t.reshape(-1) for t in lam.values()])
+            cdist.all_reduce_sum(flat)
+            o = 0
+            for t in lam.values():
+                t.copy_(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+        return {k: (v if "W" in g else v[:, 0]) for (k, v), g in zip(lam.items(), mapping)}
+
+    def _correction_program(self, X: Tensor) -> CompiledProgram:
+        """fp32 program with the KFAC / EKFAC scratch (bf16 operators run the correction in fp32: the engine is handed
+        exact fp32 parameter copies anyway)."""
+        eng = self._engine
+        key = (tuple(X.shape), "ekfac")
+        prog = eng._programs.get(key)
+        if prog is None:
+            prog = CompiledProgram(eng.model_func, eng.params, X, 8, 2)
+            eng._programs[key] = prog
+            if prog.lp.tied:
+                raise NotImplementedError(
+                    f"Weight tying ({sorted(prog.lp.tied)}) is not supported by the EKFAC correction kernels.")
+        return prog
+
+    def _eigenvalue_correction_host(self, QA, QG, mapping):
         """Second pass: per-example gradients in the Kronecker eigenbasis, squared and summed.
 
         The rotations ``g Q_g`` and ``a~ Q_a`` and the per-example contraction over the shared positions run

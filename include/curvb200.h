@@ -173,6 +173,23 @@ int curv_kfac_accumulate_batch(curv_program* prog, const void* const* param_ptrs
                                const int* joint_bias, const float* grad_outputs, int V, float wA,
                                float wG, void* workspace, size_t workspace_bytes, void* stream);
 
+/* EKFAC eigenvalue correction for one mini-batch (ekfac_hooks.py:25-238), fp32 programs created with flag 2:
+ *   lambda_l[i][j] += w * sum_{v, n} ( sum_s (g_{v,n,s} Qg_l)[i] * (a~_{n,s} Qa_l)[j] )^2
+ * -- per-example gradients in the Kronecker eigenbasis, squared and summed, on the tensor-core kernels (rotations as
+ * K-major GEMMs, the per-example contraction as a split-at-the-example-boundaries run of the weight-gradient kernel).
+ *  joint_bias[l]   0: weight group, 1: joint weight + bias group, 2: bias-only group
+ *  QA_ptrs[l]      [w_l, w_l] eigenvectors of A_l as columns, rows in F.unfold (c, kh, kw) order (+ joint ones row),
+ *                  w_l = d_in (+1 if joint); bias-only groups: the 1 x 1 matrix [[1]], w_l = 1
+ *  QG_ptrs[l]      [d_out, d_out] eigenvectors of G_l
+ *  lambda_ptrs[l]  [d_out, w_l] fp32, accumulated
+ *  grad_outputs    [V, batch, C] seeds (already scaled by the caller)
+ * Entries with a NULL lambda pointer are skipped. */
+int curv_ekfac_correction_batch(curv_program* prog, const void* const* param_ptrs, const void* const* const_ptrs,
+                                const void* X, const int* layer_nodes, int n_layers, const float* const* QA_ptrs,
+                                const float* const* QG_ptrs, float* const* lambda_ptrs, const int* joint_bias,
+                                const float* grad_outputs, int V, float w, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* Y[d_out, d_in, K] = G[d_out,d_out] . X[d_out, d_in, K] . A[d_in,d_in]^T  per column
    (kronecker.py:141-153 'abZ,Aa,Bb->ABZ').  tmp needs d_out*d_in*K floats.  A or G may be NULL
    (identity).  If lambda != NULL this is the eigen-basis apply of eigh.py:98-104:

@@ -140,3 +140,34 @@ def test_kfac_type2_on_tensor_core_kernels(name):
         close(Kop @ fx["v"].float().cuda(), fx["kfac_type2_joint"])
     finally:
         capi.lib().curv_set_tensor_core_mode(old)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_ekfac_device_correction_matches_host_path(sep, monkeypatch):
+    """The eigenvalue correction on the tensor-core kernels (csrc/ekfac.cuh: rotations as GEMMs, per-example contraction
+    split at the example boundaries) against the host-orchestrated path of round 1 (F.unfold + dense products) on a
+    small residual CNN: conv / linear groups with and without joint bias, bias-only groups, several positions."""
+    from curvlinops_b200.kfac import EKFACComputer
+    from oracle.models import MiniResNet, randomize_bn_
+
+    torch.manual_seed(0)
+    model = MiniResNet().eval()
+    randomize_bn_(model, torch.Generator().manual_seed(0))
+    model = model.cuda()
+    mods = dict(model.named_modules())
+    names = [n for n, m in mods.items() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+    params = {f"{n}.{pn}": p for n in names for pn, p in mods[n].named_parameters(recurse=False)}
+    X, y = torch.rand(6, 3, 32, 32, device="cuda"), torch.randint(0, 10, (6,), device="cuda")
+    loss = torch.nn.CrossEntropyLoss()
+    res = {}
+    for device_path in (True, False):
+        monkeypatch.setattr(EKFACComputer, "DEVICE_CORRECTION", device_path)
+        comp = EKFACComputer(model, loss, params, [(X, y)], fisher_type="type-2", separate_weight_and_bias=sep,
+                             check_deterministic=False)
+        res[device_path] = comp.compute()
+    QA1, QG1, lam_dev, mapping = res[True]
+    _, _, lam_host, _ = res[False]
+    assert set(lam_dev) == set(lam_host)
+    for k in lam_dev:
+        assert lam_dev[k].shape == lam_host[k].shape, k
+        close(lam_dev[k], lam_host[k], rtol=1e-4, atol_scale=1e-5)
