@@ -64,3 +64,27 @@ tot = sum(r[2] for r in rows)
 print(f"# one inverse apply: sum of kernel times {tot:.3f} ms over {sum(r[1] for r in rows)} launches")
 for k, n, ms in rows[:12]:
     print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:100]}")
+
+# ---- EKFAC: eigendecomposition (torch.linalg.eigh, library) + eigenvalue correction (csrc/ekfac.cuh)
+if os.environ.get("CURV_EKFAC", "1") != "0":
+    from curvlinops_b200 import EKFACLinearOperator
+    from curvlinops_b200.kfac import EKFACComputer
+
+    comp = EKFACComputer(model, loss, params, [(X, y)], fisher_type="mc", mc_samples=1, separate_weight_and_bias=False,
+                         check_deterministic=False, num_data=B)
+    A, G, mapping = super(EKFACComputer, comp).compute()
+    f32 = lambda v_: getattr(v_, "_curv_fp32", v_).float()
+    t_eigh, (QA, QG) = timed(lambda: ({k: torch.linalg.eigh(f32(v_)).eigenvectors for k, v_ in A.items()},
+                                      {k: torch.linalg.eigh(f32(v_)).eigenvectors for k, v_ in G.items()}), reps=1)
+    comp._eigenvalue_correction(QA, QG, mapping)
+    t_corr, lam = timed(lambda: comp._eigenvalue_correction(QA, QG, mapping), reps=2)
+    print(f"# EKFAC {dt} B={B}: eigh of the 42 factors (cuSOLVER) {t_eigh:.1f} ms, eigenvalue correction {t_corr:.2f} ms")
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        comp._eigenvalue_correction(QA, QG, mapping)
+        torch.cuda.synchronize()
+    rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
+    rows.sort(key=lambda r: -r[2])
+    tot = sum(r[2] for r in rows)
+    print(f"# one eigenvalue correction: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
+    for k, n, ms in rows[:14]:
+        print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:100]}")
