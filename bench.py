@@ -39,6 +39,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: its own metric (a step = one factor build), printed as an extra line
     "c3": ("ResNet-18 random-init, synthetic 128x3x224x224, KFACLinearOperator factor build (Conv2d/Linear params, "
            "joint bias, MC Fisher 1 sample) + damped inverse 1e-3 + inverse apply @ 1 vector, bf16", "bf16"),
+    # BASELINE.json configs[4]: its own metric (matvecs/s of the GGN under a Lanczos eigensolver), printed as an extra line
+    "c5": ("ResNet-50 random-init, synthetic (64 per GPU)x3x224x224, GGNLinearOperator matvecs under Lanczos "
+           "eigsh(k=10), bf16", "bf16"),
 }
 CONFIG = "c2"
 WORKLOAD = WORKLOADS[CONFIG][0]
@@ -414,6 +417,185 @@ def run_c3(torch, args):
     print(json.dumps(out))
 
 
+def run_c5(torch, args):
+    """C5: GGN of a bf16 ResNet-50 feeding a Lanczos eigensolver (k = 10); metric matvecs/s.  Weak scaling: 64 examples
+    per GPU (512 on 8, the configuration's global batch), the mini-batch sharded over the ranks, one all-reduce of the
+    [P] result per product.  `value` = device-resident products per second inside `lanczos_eigsh` (products + the
+    fp32 Lanczos vector algebra); `e2e` = the reference's own usage, `scipy.sparse.linalg.eigsh(G.to_scipy(), k=10)`:
+    every product takes a host NumPy vector and returns one (host<->device copies inside)."""
+    import numpy
+    import torch.distributed as dist
+    import torchvision
+    from scipy.sparse.linalg import ArpackNoConvergence, eigsh
+
+    from curvlinops_b200 import GGNLinearOperator, _capi as capi
+    from curvlinops_b200 import dist as cdist
+    from curvlinops_b200.lanczos import lanczos_eigsh
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        cdist.enable(True)
+    PB = int(os.environ.get("CURV_C5_PER_GPU", 64))
+    GB = PB * world
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50().eval().to(torch.bfloat16).to(dev)
+    X = torch.rand(GB, 3, 224, 224).to(torch.bfloat16)
+    y = torch.randint(0, 1000, (GB,))
+    X_host, y_host = X.pin_memory(), y.pin_memory()
+    Xd, yd = X.to(dev), y.to(dev)
+    params = dict(model.named_parameters())
+    P = sum(p.numel() for p in params.values())
+    loss = torch.nn.CrossEntropyLoss()
+    G = GGNLinearOperator(model, loss, params, [(Xd, yd)], check_deterministic=False, num_data=GB)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, r
+
+    torch.manual_seed(1)
+    v = torch.rand(P, device=dev).to(torch.bfloat16)
+    if world > 1:
+        dist.broadcast(v, 0)
+    for _ in range(max(3, args.warmup)):
+        G @ v
+    ms_mv, _ = timed(lambda: G @ v, max(args.steps, 5))
+    # the eigensolver: a fixed number of Lanczos steps (tol=0 never stops early, so every rank does the same work)
+    m_steps = int(os.environ.get("CURV_C5_LANCZOS_STEPS", 30))
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    L0 = capi.lib().curv_launch_count()
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ms_run, (evals, _, m_done) = timed(lambda: lanczos_eigsh(G, k=10, ncv=m_steps, maxiter=m_steps, tol=0.0,
+                                                                return_info=True), 1)
+    launches = capi.lib().curv_launch_count() - L0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: ARPACK on the host drives the operator through the SciPy bridge (rank 0's vectors broadcast to the others)
+    count = [0]
+    G_host = GGNLinearOperator(model, loss, params, [(X_host, y_host)], check_deterministic=False, num_data=GB)
+    G_host._engine = G._engine  # host-resident data (uploaded by every product), shared compiled program
+    bridge = G_host.to_scipy(dtype=numpy.float32)
+    stop = torch.zeros(1, device=dev)
+
+    def mv(x):  # rank 0: called by ARPACK; the other ranks serve products until rank 0 says stop
+        count[0] += 1
+        if world > 1:
+            dist.broadcast(stop, 0)
+            xt = torch.from_numpy(numpy.ascontiguousarray(x, dtype=numpy.float32)).to(dev)
+            dist.broadcast(xt, 0)
+        return bridge.matvec(x)
+
+    def e2e_run():  # host mini-batch uploaded by every product; Ritz pairs copied back to the host at the end
+        ev, vecs, mm = lanczos_eigsh(G_host, k=10, ncv=m_steps, maxiter=m_steps, tol=0.0, return_info=True)
+        return ev.cpu(), vecs.cpu(), mm
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ms_e2e, (_, vecs_host, m_e2e) = timed(e2e_run, 1)
+    t_e2e = None
+    if rank == 0:
+        from scipy.sparse.linalg import LinearOperator as SL
+
+        Aop = SL((P, P), matvec=mv, dtype=numpy.float32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        try:
+            ev_sp = eigsh(Aop, k=10, ncv=m_steps, maxiter=1, tol=1e-2, which="LA",
+                          v0=numpy.ones(P, dtype=numpy.float32), return_eigenvectors=False)
+        except ArpackNoConvergence as e:
+            ev_sp = e.eigenvalues
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            stop.fill_(1.0)
+            dist.broadcast(stop, 0)
+    else:
+        while True:
+            dist.broadcast(stop, 0)
+            if stop.item() > 0:
+                break
+            xt = torch.empty(P, device=dev)
+            dist.broadcast(xt, 0)
+            G_host @ xt.to(torch.bfloat16)
+    if world > 1:
+        barrier()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    lam = [float(e) for e in evals.float().cpu()]
+    out = {
+        "metric": "ggn_lanczos_matvecs_per_s", "value": m_done / (ms_run / 1e3), "unit": "matvec/s", "n_gpus": world,
+        "steps": 1, "warmup": max(3, args.warmup), "ms_per_step": ms_run / m_done, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "params": P, "global_batch": GB, "lanczos_steps": m_done, "k": 10,
+                   "parallelism": f"dp{world} (mini-batch sharded over the ranks, one all-reduce of [P] per product)",
+                   "l2": "activations (GBs) far exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "matvec_only": {"ms": ms_mv, "matvec_per_s": 1e3 / ms_mv,
+                        "note": "G @ v alone, device-resident; the rest of a Lanczos step is the fp32 three-term "
+                                "recurrence and the full re-orthogonalisation (torch GEMVs on [m, P])"},
+        "largest_ritz_values": lam[-3:],
+        "e2e": {"value": m_e2e / (ms_e2e / 1e3), "unit": "matvec/s", "matvecs": m_e2e,
+                "what": "lanczos_eigsh(G, k=10) with the mini-batch in pinned host memory (uploaded by every product), "
+                        "the 10 Ritz pairs copied to the host at the end; a step = one product",
+                "h2d_bytes_per_step": int(X_host.numel() * 2 + y_host.numel() * 8),
+                "d2h_bytes_per_step": int(vecs_host.numel() * 2 // m_e2e)},
+        "scipy_eigsh_bridge": {"value": count[0] / t_e2e, "unit": "matvec/s", "matvecs": count[0],
+                               "what": "the reference's own usage, scipy.sparse.linalg.eigsh(G.to_scipy(), k=10, ncv=%d, "
+                                       "one restart cycle): host NumPy vector in / out per product, ARPACK's "
+                                       "single-threaded vector algebra on the host included" % m_steps,
+                               "h2d_bytes_per_step": int(P * 4 + X_host.numel() * 2 + y_host.numel() * 8),
+                               "d2h_bytes_per_step": int(P * 4)},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.build_ref import import_reference
+
+        ref = import_reference()
+        try:  # the unmodified reference on this GPU, same model / data / dtype
+            Gr = ref.GGNLinearOperator(model, loss, params, [(Xd, yd)], check_deterministic=False, num_data=GB)
+            Gr @ v
+            t_r, _ = timed(lambda: Gr @ v, 3)
+            out["gpu_library_baseline"] = {"what": "unmodified reference GGNLinearOperator @ v on the same GPU "
+                                                   "(torch CUDA, bf16)", "ms": t_r, "matvec_per_s": 1e3 / t_r}
+            del Gr
+        except Exception as e:
+            out["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.set_num_threads(host_threads())
+        sb = 8  # bounded CPU sample: the product is linear in the batch
+        mc = torchvision.models.resnet50().eval()
+        Xc, yc = torch.rand(sb, 3, 224, 224), torch.randint(0, 1000, (sb,))
+        pc = dict(mc.named_parameters())
+        Gc = ref.GGNLinearOperator(mc, loss, pc, [(Xc, yc)], check_deterministic=False, num_data=sb)
+        vc = torch.rand(P)
+        t0 = time.perf_counter()
+        Gc @ vc
+        t1 = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / (t1 * GB / sb), "unit": "matvec/s", "cores": torch.get_num_threads(),
+                               "kind": "reference",
+                               "sample": f"one product on {sb} of {GB} samples (fp32 on the CPU), extrapolated linearly"}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +616,8 @@ def main():
             os.environ.pop(v, None)
     import torch
 
+    if CONFIG == "c5" and args.impl != "reference":
+        return run_c5(torch, args)
     if CONFIG in ("c1", "c3") and args.impl != "reference":
         if int(os.environ.get("RANK", "0")) == 0:
             (run_c3 if CONFIG == "c3" else run_c1)(torch, args)

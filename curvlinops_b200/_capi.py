@@ -40,7 +40,8 @@ EXPORTS = [
     "curv_program_create", "curv_program_destroy", "curv_program_workspace_bytes",
     "curv_program_value_layout", "curv_matmat_batch", "curv_matmat_batch_sync", "curv_kfac_accumulate_batch",
     "curv_kron_apply", "curv_kron_apply_tc", "curv_kron_apply_tc_workspace", "curv_kron_apply_tc_factor_bytes",
-    "curv_eigh_apply", "curv_gemm", "curv_gemm_batched", "curv_ekfac_correction_batch", "curv_last_error", "curv_abi_version",
+    "curv_eigh_apply", "curv_gemm", "curv_gemm_batched", "curv_ekfac_correction_batch",
+    "curv_lanczos_reorth", "curv_lanczos_reorth_workspace", "curv_last_error", "curv_abi_version",
     "curv_launch_count", "curv_add_launch_count", "curv_set_tensor_core_mode", "curv_profile_enable", "curv_profile_read",
     "curv_profile_read_class", "curv_launch_config",
 ]
@@ -96,6 +97,10 @@ def lib() -> C.CDLL:
     L.curv_gemm.restype = i
     L.curv_gemm_batched.argtypes = [i, i, i, i, i, f, vp, i, ll, vp, i, ll, f, vp, i, ll, i, vp]
     L.curv_gemm_batched.restype = i
+    L.curv_lanczos_reorth_workspace.argtypes = [i, ll]
+    L.curv_lanczos_reorth_workspace.restype = ll
+    L.curv_lanczos_reorth.argtypes = [vp, ll, i, vp, ll, i, vp, vp, ll, vp]
+    L.curv_lanczos_reorth.restype = i
     L.curv_last_error.argtypes = []
     L.curv_last_error.restype = C.c_char_p
     L.curv_abi_version.argtypes = []

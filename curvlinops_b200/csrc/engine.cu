@@ -1449,3 +1449,4 @@ extern "C" int curv_eigh_apply(const float* Qg, const float* Qa, const float* la
 #include "kfac.cuh"
 #include "kron_tc.cuh"
 #include "ekfac.cuh"
+#include "lanczos.cuh"

@@ -149,7 +149,8 @@ class Engine:
         self.params = params
         self._programs: dict = {}
         self._ws: Tensor | None = None
-        self._graphs: dict = {}    # key (all baked-in pointers) -> [CUDAGraph | None]
+        self._graphs: dict = {}    # baked-in pointers except V / out -> {"first", "exact", "staged"} (see _matmat_batch)
+        self._x32: list = []       # bf16 operators: [(data_ptr, version, shape, fp32 copy of the mini-batch input)]
         self._p32: dict = {}       # bf16 operators: name -> (data_ptr, version, fp32 copy of the parameter)
         capi.lib()  # fail loudly if the CUDA library has not been built
 
@@ -207,6 +208,20 @@ class Engine:
             ps = [p if p.is_contiguous() else p.contiguous() for p in self.params.values()]
         return ps, capi.ptr_array([p.data_ptr() for p in ps])
 
+    def _input32(self, X: Tensor) -> Tensor:
+        """fp32 contiguous view of a mini-batch input.  Low-precision / strided inputs are converted once per
+        (storage, version) and kept (4 most recent): the copy keeps its address from product to product, which the
+        CUDA-graph key needs, and an eigensolver that revisits the same batches does not pay for it again."""
+        if X.dtype == torch.float32 and X.is_contiguous():
+            return X
+        for hit in self._x32:
+            if hit[0] == X.data_ptr() and hit[1] == X._version and hit[2] == (tuple(X.shape), X.dtype, X.device):
+                return hit[3]
+        X32 = X.to(torch.float32).contiguous()
+        if X.device.type == "cuda":
+            self._x32 = self._x32[-3:] + [(X.data_ptr(), X._version, (tuple(X.shape), X.dtype, X.device), X32)]
+        return X32
+
     # -- the hot call ----------------------------------------------------------------------------
     def matmat_batch(self, kind: int, X: Tensor, y: Tensor | None, V: Tensor, out: Tensor, alpha: float,
                      mc_grad: Tensor | None = None, scale: float | None = None,
@@ -226,7 +241,7 @@ class Engine:
         K = V.shape[-1]
         c0, cn = (0, K) if cols is None else cols
         kc = min(cn, MAX_COLUMNS_PER_SWEEP)
-        X = X.to(torch.float32).contiguous()
+        X = self._input32(X)
         prog = self.program(X, kc, kind == capi.KIND_HESSIAN)
         X = prog.engine_input(X)
         ws = self.workspace(prog.ws_bytes, X.device)
@@ -276,30 +291,52 @@ class Engine:
             launch(V, out, stream)
             del keep
             return
-        # The graph is keyed on every pointer it bakes in - including V and out: in steady state the caching
-        # allocator hands a caller that builds V / out per product the same blocks again, so replays need no
-        # staging copies; a different address is simply another key (eager first, captured on its second sighting).
-        key = (prog.serial, kind, loss, K, c0, cn, float(scale or 1.0), float(alpha), X.data_ptr(),
-               0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
-               tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg, V.data_ptr(), out.data_ptr())
-        entry = self._graphs.get(key)
-        if entry is None:  # first sighting: eager (also warms up one-time initialisation inside the library)
-            if len(self._graphs) >= _MAX_GRAPHS:
-                self._graphs.pop(next(iter(self._graphs)))
-            self._graphs[key] = [None]
-            launch(V, out, stream)
-            del keep
-            return
-        if len(entry) == 1:  # second sighting: capture (records the launches, does not run them)
+        # Two kinds of captured graph per product (`base` = everything baked in except the V / out addresses).
+        # EXACT: in steady state the caching allocator hands a caller that builds V / out per product the same blocks
+        # again; when the second call repeats the first call's addresses the graph is captured on them and replays
+        # need no copies.  STAGED: a caller whose V / out addresses move (an eigensolver allocating vectors of its own
+        # between products) gets ONE graph on engine-owned V / out buffers, replayed between two device copies
+        # ([P, K] floats each way) - never a capture per address pair.
+        base = (prog.serial, kind, loss, K, c0, cn, float(scale or 1.0), float(alpha), X.data_ptr(),
+                0 if y is None else y.data_ptr(), 0 if mc_grad is None else mc_grad.data_ptr(), M,
+                tuple(p.data_ptr() for p in keep), ws.data_ptr(), cfg)
+        addr = (V.data_ptr(), out.data_ptr())
+
+        def captured(Vt, outt):
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(X.device)
             n0 = capi.lib().curv_launch_count()
             with torch.cuda.graph(g):
-                launch(V, out, torch.cuda.current_stream(X.device).cuda_stream)
-            entry[:] = [g, capi.lib().curv_launch_count() - n0]  # the capture counted the first replay
+                launch(Vt, outt, torch.cuda.current_stream(X.device).cuda_stream)
+            return [g, capi.lib().curv_launch_count() - n0]  # the capture counted the first replay
+
+        entry = self._graphs.get(base)
+        if entry is None:  # first sighting: eager (also warms up one-time initialisation inside the library)
+            if len(self._graphs) >= _MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[base] = {"first": addr, "exact": None, "staged": None}
+            launch(V, out, stream)
+            del keep
+            return
+        if entry["exact"] is None and entry["staged"] is None and entry["first"] == addr:
+            entry["exact"] = captured(V, out)  # records the launches, does not run them
+            entry["exact"][0].replay()
+        elif entry["exact"] is not None and entry["first"] == addr:
+            capi.lib().curv_add_launch_count(entry["exact"][1])
+            entry["exact"][0].replay()
         else:
-            capi.lib().curv_add_launch_count(entry[1])
-        entry[0].replay()
+            st = entry["staged"]
+            if st is None:
+                Vs, outs = torch.empty_like(V), torch.empty_like(out)
+                Vs.copy_(V)
+                outs.copy_(out)
+                st = entry["staged"] = captured(Vs, outs) + [Vs, outs]
+            else:
+                st[2].copy_(V)
+                st[3].copy_(out)
+                capi.lib().curv_add_launch_count(st[1])
+            st[0].replay()
+            out.copy_(st[3])
         del keep
 
     def predict(self, X: Tensor) -> Tensor:

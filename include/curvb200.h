@@ -223,6 +223,16 @@ int curv_gemm_batched(int transA, int transB, int M, int N, int Kd, float alpha,
                       long long sA, const float* B, int ldb, long long sB, float beta, float* C, int ldc,
                       long long sC, int batch, void* stream);
 
+/* Full re-orthogonalisation of a Lanczos vector (the eigensolver consumer of the products, BASELINE.json configs[4];
+   the reference leaves this to ARPACK on the host behind PyTorchLinearOperator.to_scipy, _torch_base.py:560-592):
+   `rounds` times  c = Q[:m] w ;  w -= Q[:m]^T c  with Q [m, n] fp32 rows of leading dimension ldq, w [n] fp32, all on
+   the device.  coeff (may be NULL): [m] floats receiving the coefficients summed over the rounds (coeff[m-1] is the
+   Lanczos alpha when w = A q_{m-1}).  Two streaming passes over Q[:m] per round, fixed-order sums (repeatable).
+   ws: curv_lanczos_reorth_workspace(m, n) bytes. */
+long long curv_lanczos_reorth_workspace(int m, long long n);
+int curv_lanczos_reorth(const float* Q, long long ldq, int m, float* w, long long n, int rounds, float* coeff,
+                        void* ws, long long ws_bytes, void* stream);
+
 const char* curv_last_error(void);
 int curv_abi_version(void);
 /* number of kernel launches issued by this library since process start (bench `gpu_launches`) */

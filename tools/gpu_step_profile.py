@@ -11,7 +11,7 @@ B, K = int(os.environ.get("CURV_B", 128)), int(os.environ.get("CURV_K", 8))
 torch.manual_seed(0)
 dev = torch.device("cuda")
 dt = torch.bfloat16 if os.environ.get("CURV_DTYPE") == "bf16" else torch.float32
-model = torchvision.models.resnet18().eval().to(dev).to(dt)
+model = getattr(torchvision.models, os.environ.get("CURV_MODEL", "resnet18"))().eval().to(dev).to(dt)
 X, y = torch.rand(B, 3, 224, 224, device=dev).to(dt), torch.randint(0, 1000, (B,), device=dev)
 params = dict(model.named_parameters())
 P = sum(p.numel() for p in params.values())
@@ -27,7 +27,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
 rows.sort(key=lambda r: -r[2])
 tot = sum(r[2] for r in rows)
-print(f"# one C2 step (ResNet-18, B={B}, K={K}, {dt}), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
+print(f"# one step ({os.environ.get('CURV_MODEL', 'resnet18')}, B={B}, K={K}, {dt}), mode={mode:#x}: sum of kernel times {tot:.2f} ms over {sum(r[1] for r in rows)} launches")
 for k, n, ms in rows[:40]:
     print(f"{100*ms/tot:6.2f}% {ms:9.3f} ms  n={n:4d}  {k[:110]}")
 # per-launch durations of the contraction kernels, in launch order (layer attribution by position)
