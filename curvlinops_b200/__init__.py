@@ -1,7 +1,8 @@
 """curvlinops_b200: B200-native engine for the curvature-matvec hot path of f-dangel/curvlinops.
 
 Drop-in operator classes (same names / constructor arguments as the reference):
-``HessianLinearOperator``, ``GGNLinearOperator``, ``EFLinearOperator``, ``KFACLinearOperator``,
+``HessianLinearOperator``, ``GGNLinearOperator``, ``EFLinearOperator``, ``GGNDiagonalLinearOperator``,
+``KFACLinearOperator``,
 ``EKFACLinearOperator``, the Jacobian operators, the structured operators they are assembled from, and the
 consumers of their products (CG / Neumann / LSMR inverses, Lanczos, randomised trace / diagonal estimators).  All arithmetic runs in hand-written sm_100a CUDA kernels
 behind the C ABI of ``include/curvb200.h``; there is no CPU fallback.
@@ -12,6 +13,7 @@ from .curvature import (CurvatureLinearOperator, EFLinearOperator, GGNLinearOper
 from .dense import DiagonalLinearOperator, IdentityLinearOperator, TensorLinearOperator
 from .estimators import (hutchinson_diag, hutchinson_squared_fro, hutchinson_trace, hutchpp_trace, xdiag,
                          xtrace)
+from .ggn_diagonal import GGNDiagonalComputer, GGNDiagonalLinearOperator
 from .inverse import CGInverseLinearOperator, LSMRInverseLinearOperator, NeumannInverseLinearOperator
 from .jacobian import JacobianLinearOperator, TransposedJacobianLinearOperator
 from .kfac import EKFACLinearOperator, FisherType, KFACLinearOperator, KFACType
@@ -26,6 +28,8 @@ __all__ = [
     "CurvatureLinearOperator",
     "GGNLinearOperator",
     "EFLinearOperator",
+    "GGNDiagonalLinearOperator",
+    "GGNDiagonalComputer",
     "fast_lanczos",
     "lanczos_eigsh",
     "HessianLinearOperator",

@@ -15,13 +15,17 @@
 namespace curv {
 
 // lam[r][j] += w * sum_n ( sum_{c < cps} partial[(n * cps + c) * split_elems + r * ld + j] )^2
+// perm_taps > 1: lam is in the canonical (channel, tap) column order while the partials are in the (tap, channel)
+// order of the patch planes (the un-rotated use: exact / MC GGN diagonal); columns >= perm_C * perm_taps (joint) stay.
 __global__ void __launch_bounds__(256) ekfac_finish_kernel(const float* __restrict__ partial, int nsamples, int cps,
                                                           long long split_elems, int ld, int d_out, int width,
-                                                          float* __restrict__ lam, float w) {
+                                                          float* __restrict__ lam, float w, int perm_C, int perm_taps) {
   const long long total = (long long)d_out * width;
+  const int CT = perm_C * perm_taps;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % width);
+    int j = (int)(e % width);
+    if (perm_taps > 1 && j < CT) j = (j % perm_taps) * perm_C + j / perm_taps;
     const long long r = e / width;
     const float* q = partial + r * ld + j;
     float acc = 0.f;
@@ -85,20 +89,21 @@ struct EkfacPlan {
   long long p_halves, qa_img, qg_img, at_elems, gt_elems, at_halves, gt_halves, split_elems, partial_elems;
   long long o_bits, o_P, o_QA, o_QG, o_atF, o_atP, o_gtF, o_gtP, o_part, total_floats;
 };
-static EkfacPlan ekfac_plan(long long M, int B, int S, int width, int Cp_out) {
+// identity: no rotation (Q_a = Q_g = I) - the contraction reads the patch planes and the cotangent planes directly
+static EkfacPlan ekfac_plan(long long M, int B, int S, int width, int Cp_out, bool identity = false) {
   EkfacPlan p;
   p.width = width;
   p.ldp = (width + 63) & ~63;       // patch planes = reduction of the at-GEMM: multiples of 64 take the TMA producers
-  p.lda = pad8(width);              // rows of at (output of that GEMM, gathered operand of the contraction)
+  p.lda = identity ? p.ldp : pad8(width);  // rows of at (output of that GEMM, gathered operand of the contraction)
   p.ldg = pad8(Cp_out);             // gt rows
   p.W8 = 64 * ceil_div(p.ldg, 512);
   p.NS = ceil_div(p.ldg, p.W8);
   p.cps = ekfac_chunks_per_sample(S);
   p.p_halves = align_up(M * p.ldp + 8192, 128);
-  p.qa_img = hs_image_halves(p.lda, p.ldp);
-  p.qg_img = hs_image_halves(p.ldg, Cp_out);
-  p.at_elems = M * p.lda;
-  p.gt_elems = M * p.ldg;
+  p.qa_img = identity ? 0 : hs_image_halves(p.lda, p.ldp);
+  p.qg_img = identity ? 0 : hs_image_halves(p.ldg, Cp_out);
+  p.at_elems = identity ? 0 : M * p.lda;
+  p.gt_elems = identity ? 0 : M * p.ldg;
   p.at_halves = align_up(p.at_elems + 8192, 128);
   p.gt_halves = align_up(p.gt_elems + 8192, 128);
   p.split_elems = (long long)p.NS * p.W8 * p.lda;
@@ -118,7 +123,9 @@ static EkfacPlan ekfac_plan(long long M, int B, int S, int width, int Cp_out) {
   return p;
 }
 static long long ekfac_scratch_elems(long long M, int B, int S, int d_in_width, int Cp_out) {
-  return ekfac_plan(M, B, S, d_in_width, Cp_out).total_floats + 64;
+  const long long a = ekfac_plan(M, B, S, d_in_width, Cp_out).total_floats;
+  const long long b = ekfac_plan(M, B, S, d_in_width, Cp_out, true).total_floats;
+  return (a > b ? a : b) + 64;
 }
 
 // one layer, one back-propagated vector (cotangent slot `slot_index` of the planes in hs1, absolute slot `abs_slot`)
@@ -133,7 +140,9 @@ static int ekfac_layer(const Ctx& c, const Node& n, const EkfacEntry& en, int sl
   const int Cin = en.bias_only ? 0 : vi.C;            // bias group: the patch is the ones column alone
   const int joint = (en.bias_only || en.joint) ? 1 : 0;
   const int width = Cin * g.KH * g.KW + joint;
-  const EkfacPlan p = ekfac_plan(g.M, P->B, S, width, vo.Cp);
+  const bool identity = en.identity != 0;
+  const EkfacPlan p = ekfac_plan(g.M, P->B, S, width, vo.Cp, identity);
+  if (identity && pad8(vo.Cp) != vo.Cp) return fail(CURV_ERR_UNSUPPORTED, "GGN diagonal: channel padding");
   if (!c.hs || c.planes != 2) return fail(CURV_ERR_UNSUPPORTED, "EKFAC correction needs the fp32 tensor-core path");
   if (p.cps == 0) return fail(CURV_ERR_UNSUPPORTED, "EKFAC correction: output map cannot be split at example boundaries");
   if (p.total_floats > P->scratch_elems) return fail(CURV_ERR_WORKSPACE, "EKFAC scratch too small");
@@ -159,6 +168,7 @@ static int ekfac_layer(const Ctx& c, const Node& n, const EkfacEntry& en, int sl
   CHECK_CUDA(cudaMemsetAsync(Pl + g.M * p.ldp, 0, 8192 * 2, st));
   im2col_planes_kernel<<<grid1d((long long)g.M * (p.ldp / 8)), 256, 0, st>>>(c.act(n.d.in0), Ph, Pl, g, Cin, joint,
                                                                            p.ldp, bits);
+  if (!identity) {
   // ---- 2a. at = patches . Q_a (rows of Q_a permuted to the plane order)
   kron_absmax_kernel<<<grid1d((long long)width * width), 256, 0, st>>>(en.Qa, (long long)width * width, bits + 1, 1);
   {
@@ -210,6 +220,7 @@ static int ekfac_layer(const Ctx& c, const Node& n, const EkfacEntry& en, int sl
     return fail(CURV_ERR_CUDA, "EKFAC: split of the rotated operands failed");
   g_launches += 4;
   LAUNCH_CHECK();
+  }
   // ---- 3. per-example contraction: splits at the example boundaries
   {
     HsWgradArgs a;
@@ -219,6 +230,13 @@ static int ekfac_layer(const Ctx& c, const Node& n, const EkfacEntry& en, int sl
     q.N = p.W8; q.Nd = p.W8; q.Kd = p.lda; q.M = g.M;
     a.Gh = gtH; a.Gl = gtL; a.G_slot = p.W8; a.G_ld = p.ldg; a.Ng = p.W8; a.g_bits = bits + 16;
     a.Ih = atH; a.Il = atL; a.i_bits = bits + 8;
+    if (identity) {  // un-rotated: the patch planes and the cotangent planes of this slot are the operands
+      a.Gh = c.hs1_hi() + (long long)slot_index * vo.slot_elems;
+      a.Gl = c.hs1_lo() + (long long)slot_index * vo.slot_elems;
+      hs_bits_fill_kernel<<<1, 32, 0, st>>>(bits + 16, 8, c.hsbits() + c.bits_grad(n.d.out) + abs_slot, 0u);
+      LAUNCH_CHECK();
+      a.Ih = Ph; a.Il = Pl; a.i_bits = bits;
+    }
     a.partial = part; a.nsplit = P->B * p.cps; a.nslots = p.NS; a.slot0 = 0; a.m_per_split = S / p.cps;
     a.planes = 2;
     ProfScope prof(1, 2.0 * g.M * (double)vo.C * width, st);
@@ -227,7 +245,8 @@ static int ekfac_layer(const Ctx& c, const Node& n, const EkfacEntry& en, int sl
   }
   // ---- 4. square and sum over the examples
   ekfac_finish_kernel<<<grid1d((long long)vo.C * width), 256, 0, st>>>(part, P->B, p.cps, p.split_elems, p.lda, vo.C,
-                                                                     width, en.lam, job.w);
+                                                                     width, en.lam, job.w, identity ? Cin : 0,
+                                                                     identity ? g.KH * g.KW : 1);
   LAUNCH_CHECK();
   return CURV_OK;
 }
@@ -265,10 +284,14 @@ extern "C" int curv_ekfac_correction_batch(curv_program* P, const void* const* p
     const int ni = layer_nodes[i];
     if (ni < 0 || ni >= (int)P->nodes.size() || P->nodes[ni].d.op != CURV_OP_CONV)
       return fail(CURV_ERR_INVALID, "layer_nodes must reference CONV nodes");
-    if (!QG_ptrs[i] || !lambda_ptrs[i]) continue;
-    // joint_bias[i]: 0 weight group, 1 joint weight + bias group, 2 bias-only group (QA_ptrs[i] = [[1]])
-    if (!QA_ptrs[i]) return fail(CURV_ERR_INVALID, "curv_ekfac_correction_batch: QA missing (bias groups take [[1]])");
-    job.entries.push_back({ni, QA_ptrs[i], QG_ptrs[i], lambda_ptrs[i], joint_bias[i] == 1, joint_bias[i] == 2});
+    // joint_bias[i] & 3: 0 weight group, 1 joint weight + bias group, 2 bias-only group (QA_ptrs[i] = [[1]]);
+    // | 4: no rotation (Q_a = Q_g = I, the pointers are ignored): lambda = sum of squared per-example gradients, the
+    // exact / MC GGN diagonal of the layer (curvlinops/computers/ggn_diagonal.py:49-75)
+    const int ident = (joint_bias[i] & 4) ? 1 : 0, jb = joint_bias[i] & 3;
+    if (!lambda_ptrs[i] || (!ident && !QG_ptrs[i])) continue;
+    if (!ident && !QA_ptrs[i])
+      return fail(CURV_ERR_INVALID, "curv_ekfac_correction_batch: QA missing (bias groups take [[1]])");
+    job.entries.push_back({ni, QA_ptrs[i], QG_ptrs[i], lambda_ptrs[i], jb == 1, jb == 2, ident});
     job.has[ni] = 1;
   }
   int rc;

@@ -927,6 +927,7 @@ struct EkfacEntry {
   float* lam;
   int joint;      // ones column appended to the patches (joint weight + bias group)
   int bias_only;  // bias group: the "patch" is the ones column alone (Qa = [[1]], lambda is [d_out, 1])
+  int identity;   // no rotation: squared per-example gradients (GGN diagonal)
 };
 struct EkfacJob {
   std::vector<EkfacEntry> entries;

@@ -380,10 +380,13 @@ class EKFACComputer(KFACComputer):
     #: round-1 path (F.unfold + per-group dense products), kept as a cross-check for the tests
     DEVICE_CORRECTION = True
 
-    def _eigenvalue_correction(self, QA, QG, mapping):
+    def _eigenvalue_correction(self, QA, QG, mapping, identity: bool = False):
         """Second pass: per-example gradients in the Kronecker eigenbasis, squared and summed
-        (``ekfac_hooks.py:25-238``), on the tensor-core kernels: see ``csrc/ekfac.cuh``."""
-        if not self.DEVICE_CORRECTION:
+        (``ekfac_hooks.py:25-238``), on the tensor-core kernels: see ``csrc/ekfac.cuh``.
+
+        ``identity``: no rotation (``QA`` / ``QG`` ignored) - the squared per-example gradients themselves, i.e. the
+        GGN diagonal of the grouped layers in canonical ``[d_out, d_in (+1)]`` layout (``ggn_diagonal.py``)."""
+        if not self.DEVICE_CORRECTION and not identity:
             return self._eigenvalue_correction_host(QA, QG, mapping)
         dev = self.device
         eng = self._engine
@@ -395,6 +398,12 @@ class EKFACComputer(KFACComputer):
         one = torch.ones(1, 1, device=dev, dtype=torch.float32)
         for group in mapping:
             key = tuple(group.values())
+            if identity:
+                first = self._params[next(iter(group.values()))]
+                width = (self._params[group["W"]][0].numel() + (1 if "b" in group else 0)) if "W" in group else 1
+                qa32[key] = qg32[key] = one
+                lam[key] = torch.zeros(first.shape[0], width, device=dev, dtype=torch.float32)
+                continue
             qg32[key] = QG[key].float().contiguous()
             if "W" in group:
                 qa32[key] = QA[key].float().contiguous()
@@ -425,7 +434,7 @@ class EKFACComputer(KFACComputer):
                 key = tuple(group.values())
                 nodes.append(self._group_node(prog, group))
                 qa_p.append(qa32[key].data_ptr()); qg_p.append(qg32[key].data_ptr()); lam_p.append(lam[key].data_ptr())
-                kinds.append(2 if "W" not in group else (1 if "b" in group else 0))
+                kinds.append((2 if "W" not in group else (1 if "b" in group else 0)) | (4 if identity else 0))
             n = len(nodes)
             keep, pptrs = eng._param_ptrs()
             capi.check(L.curv_ekfac_correction_batch(

@@ -177,7 +177,11 @@ int curv_kfac_accumulate_batch(curv_program* prog, const void* const* param_ptrs
  *   lambda_l[i][j] += w * sum_{v, n} ( sum_s (g_{v,n,s} Qg_l)[i] * (a~_{n,s} Qa_l)[j] )^2
  * -- per-example gradients in the Kronecker eigenbasis, squared and summed, on the tensor-core kernels (rotations as
  * K-major GEMMs, the per-example contraction as a split-at-the-example-boundaries run of the weight-gradient kernel).
- *  joint_bias[l]   0: weight group, 1: joint weight + bias group, 2: bias-only group
+ *  joint_bias[l]   0: weight group, 1: joint weight + bias group, 2: bias-only group;
+ *                  | 4: NO rotation (QA / QG ignored, may be NULL): lambda_l += w * sum_{v,n} (per-example gradient)^2,
+ *                  the exact / MC GGN diagonal of the layer in canonical [d_out, d_in (+1)] layout
+ *                  (curvlinops/computers/ggn_diagonal.py:49-109) - the contraction reads the patch planes and the
+ *                  cotangent planes directly
  *  QA_ptrs[l]      [w_l, w_l] eigenvectors of A_l as columns, rows in F.unfold (c, kh, kw) order (+ joint ones row),
  *                  w_l = d_in (+1 if joint); bias-only groups: the 1 x 1 matrix [[1]], w_l = 1
  *  QG_ptrs[l]      [d_out, d_out] eigenvectors of G_l

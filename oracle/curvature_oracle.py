@@ -381,6 +381,52 @@ def kfac_grad_outputs(model, loss_func, data, fisher_type="mc", mc_samples=1, se
     return res
 
 
+def loss_hessian_sqrt_columns(loss_func, f: Tensor) -> Tensor:
+    """``[C', B, C]``: per datum the columns of ``S`` with ``S S^T`` = Hessian of the loss w.r.t. the prediction, without
+    the 1/B of a mean reduction (reference ``curvlinops/ggn_utils.py:29-171``)."""
+    B, C = f.shape
+    c = 1.0 / C if (loss_func.reduction == "mean" and not isinstance(loss_func, torch.nn.CrossEntropyLoss)) else 1.0
+    if isinstance(loss_func, torch.nn.CrossEntropyLoss):
+        p = torch.softmax(f, 1)
+        S = torch.diag_embed(p.sqrt()) - p.unsqueeze(2) * p.sqrt().unsqueeze(1)  # [B, C, C']
+    elif isinstance(loss_func, torch.nn.MSELoss):
+        S = (math.sqrt(2 * c) * torch.eye(C, dtype=f.dtype, device=f.device)).expand(B, C, C)
+    elif isinstance(loss_func, torch.nn.BCEWithLogitsLoss):
+        s = torch.sigmoid(f)
+        S = math.sqrt(c) * torch.diag_embed((s * (1 - s)).sqrt())
+    else:
+        raise NotImplementedError(type(loss_func))
+    return S.permute(2, 0, 1).contiguous()
+
+
+def ggn_diagonal(model_func, loss_func, params: dict[str, Tensor], data: Iterable[tuple[Tensor, Tensor]],
+                 grad_outputs: list[Tensor] | None = None, n_data: int | None = None) -> list[Tensor]:
+    """Diagonal of the GGN, one tensor per parameter (reference ``curvlinops/computers/ggn_diagonal.py:49-109,207-232``):
+    ``w * sum_{n, v} (J_n^T g'_{n,v})^2`` with ``g'`` the loss-Hessian square-root columns (exact) or the given
+    ``grad_outputs`` (one ``[V, B, C]`` tensor per mini-batch, e.g. MC samples), ``w = 1/N`` (mean) or 1 (sum).
+    Plain loops over data points and columns: small cases only."""
+    f_fn = _as_callable(model_func)
+    data = list(data)
+    N = n_data if n_data is not None else sum(X.shape[0] for X, _ in data)
+    ps = list(params.values())
+    out = [torch.zeros_like(p) for p in ps]
+    w = 1.0 / N if loss_func.reduction == "mean" else 1.0
+    for bi, (X, y) in enumerate(data):
+        with torch.enable_grad():
+            f = f_fn(params, X)
+            seeds = loss_hessian_sqrt_columns(loss_func, f.detach()) if grad_outputs is None else grad_outputs[bi]
+            for n in range(X.shape[0]):
+                for v in range(seeds.shape[0]):
+                    if not bool(seeds[v, n].any()):
+                        continue
+                    gs = torch.autograd.grad(f[n], ps, grad_outputs=seeds[v, n].to(f.dtype), retain_graph=True,
+                                             allow_unused=True)
+                    for o, g in zip(out, gs):
+                        if g is not None:
+                            o.add_(g.detach() ** 2, alpha=w)
+    return out
+
+
 def damped_inverse(S: Tensor, damping: float) -> Tensor:
     """``(S + damping I)^-1`` via Cholesky (reference ``curvlinops/kronecker.py:328-373``)."""
     L = torch.linalg.cholesky(S + damping * torch.eye(S.shape[0], dtype=S.dtype))

@@ -21,6 +21,9 @@ BUILDERS = {
     "mlp_ln_gelu_ce_mean": (lambda: mlp_ln_gelu(), lambda: nn.CrossEntropyLoss()),
     "token_mlp_ce_mean": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
     "mlp_gelu_mse_sum": (lambda: mlp_gelu(), lambda: nn.MSELoss(reduction="sum")),
+    "ggn_diag_mlp_ce_mean": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
+    "ggn_diag_mlp_mse_sum": (lambda: mlp_c1(classes=4, width=12), lambda: nn.MSELoss(reduction="sum")),
+    "ggn_diag_cnn_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

@@ -73,3 +73,12 @@ def test_layernorm_gelu_cases_match_reference(name):
     for M in (1, 3):
         got = flat(orc.ggn_matmat(model, loss, params, data, V, mc_samples=M, seed=1234))
         torch.testing.assert_close(got, fx[f"ggn_mc{M}"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["ggn_diag_mlp_ce_mean", "ggn_diag_mlp_mse_sum", "ggn_diag_cnn_ce_mean"])
+def test_ggn_diagonal_matches_reference(name):
+    """oracle.ggn_diagonal vs the reference's GGNDiagonalLinearOperator (fixtures of oracle/make_golden_diag.py)."""
+    model, loss, data, fx = load_case(name)
+    params = dict(model.named_parameters())
+    got = torch.cat([d.reshape(-1) for d in orc.ggn_diagonal(model, loss, params, data)])
+    torch.testing.assert_close(got, fx["diag"], rtol=1e-9, atol=1e-13)
