@@ -948,22 +948,23 @@ __global__ void __launch_bounds__(256) vec_grad_finish_kernel(const float* __res
 // out[(off + ((n*C + c)*taps + tap))*ldk + k0 + k] += alpha * sum_splits partial[split][k][n][tap][cp]
 __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nsplit, int nslots,
                                     int kskip, int N, int C, int Cp, int taps, float* __restrict__ out,
-                                    long long off, int ldk, int k0, float alpha) {
+                                    long long off, int ldk, int k0, float alpha, int nrows) {
   // block = (32 weight elements, nslots - kskip columns): a warp reads 128 contiguous bytes of one slot's
   // partial per split; the splits are summed in a fixed order with four independent chains (deterministic).
   // (Round 2 tried two variants of the K-minor update -- a CTA tile transposed through shared memory with
   // contiguous row writes, and 16-byte row read-modify-writes after a 32 x nk transpose: 6.2 ms and 2.7 ms per C2
   // step against 2.3 ms for this one; the L2 merges the nk 4-byte updates of a row.)
   const long long per = (long long)N * taps * Cp;
+  const long long per_slot = (long long)(nrows > 0 ? nrows : N) * taps * Cp;
   const int k = kskip + threadIdx.y;
-  const long long stride = (long long)nslots * per;
+  const long long stride = (long long)nslots * per_slot;
   for (long long i = blockIdx.x * 32LL + threadIdx.x; i < per; i += (long long)gridDim.x * 32) {
     int c = (int)(i % Cp);
     if (c >= C) continue;
     long long r = i / Cp;
     int tap = (int)(r % taps);
     int n = (int)(r / taps);
-    const float* q = partial + (long long)k * per + i;
+    const float* q = partial + (long long)k * per_slot + i;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int sp = 0;
     for (; sp + 4 <= nsplit; sp += 4) {

@@ -207,14 +207,13 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         n.wbm = g.N > 64 ? 128 : 64;
         n.wbn = g.Kd > 64 ? 128 : 64;
         int nsl = kmax + ((hessian & 1) ? 1 : 0);
-        long long tiles = (long long)ceil_div(g.N, n.wbm) * ceil_div(g.Kd, n.wbn) * nsl;
-        if (!(hessian & 1))  // multi-slot tcgen05 wgrad: the slots live inside one tile
-          tiles = (long long)ceil_div(g.Kd, 128) * ceil_div(vo.Cp, 64);
+        // multi-slot tcgen05 wgrad: the slots live inside one tile
+        long long tiles = (long long)ceil_div(g.Kd, 128) * ceil_div(vo.Cp, 64);
         int want = (int)((2 * 148 + tiles - 1) / tiles);
         int maxsplit = ceil_div(g.M, 512);
         n.nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
         if (n.nsplit > 64) n.nsplit = 64;
-        if (!(hessian & 1)) {
+        {
           // multi-slot kernels: at most 2048 pixels (384 MMAs per accumulator on the fp16 path) per split, so the
           // tensor core's truncating accumulation stays below ~1e-5 and no tile needs an in-kernel TMEM flush
           // (measured, round 2: flushing in the kernel instead -- HSW_FLUSH = 128 stages, splits only to fill the
@@ -294,21 +293,21 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
   }
   P->scratch_elems = scratch;
   P->scratch_off = alloc(scratch);
-  if (!(hessian & 1)) {  // half-split planes for the GGN / JVP / VJP sweeps
+  {  // half-split planes for the sweeps (the Hessian R-op keeps K + 1 cotangent slots)
     for (const Node& n : P->nodes) {
       if (n.d.op != CURV_OP_CONV) continue;
       const Value& vi = P->values[n.d.in0];
       const Value& vo = P->values[n.d.out];
       if (!hs_gather_shape_ok(n.fwd)) continue;
       const long long fwd_need = vi.slot_elems * vi.nslots;
-      const long long bwd_need = (vo.Cp % 8 == 0) ? vo.slot_elems * kmax : 0;
+      const long long bwd_need = (vo.Cp % 8 == 0) ? vo.slot_elems * (kmax + ((hessian & 1) ? 1 : 0)) : 0;
       P->hs1_elems = std::max(P->hs1_elems, std::max(fwd_need, bwd_need));
       P->hs2_elems = std::max(P->hs2_elems, vi.slot_elems);
     }
     if (P->hs1_elems > 0) {
       P->hs1_off = alloc(P->hs1_elems);
       P->hs2_off = alloc(P->hs2_elems);
-      P->hsbits_count = (long long)(2 * n_values + 2 * n_nodes) * (1 + kmax);
+      P->hsbits_count = (long long)(2 * n_values + 2 * n_nodes) * (1 + kmax) + 16;  // + 16 words of per-launch scratch
       P->hsbits_off = alloc(P->hsbits_count);
     }
   }
@@ -431,11 +430,12 @@ static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, dou
 }
 
 // split-K finish of a weight gradient: partial [split][slot][n][tap][cp] -> out rows of the parameter (K minor)
+// nrows: rows per slot of the partials (0: N; larger when the slots were column blocks padded to the block width)
 static int launch_wgrad_finish(const float* partial, int nsplit, int ns, int kskip, int N, int C, int Cp, int taps,
                                float* out, long long off, int ldk, int k0, float alpha, long long wsize,
-                               cudaStream_t st) {
+                               cudaStream_t st, int nrows = 0) {
   wgrad_finish_kernel<<<grid1d(wsize, 32), dim3(32, ns - kskip), 0, st>>>(partial, nsplit, ns, kskip, N, C, Cp, taps,
-                                                                          out, off, ldk, k0, alpha);
+                                                                          out, off, ldk, k0, alpha, nrows);
   LAUNCH_CHECK();
   return CURV_OK;
 }
@@ -565,11 +565,11 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
         pack_weight_kernel<<<dim3(grid1d(n.wsize), c.K), 256, 0, st>>>(
             c.vcol(d.p0), c.ldk, c.ws + n.wkt_off, n.wsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 0);
         LAUNCH_CHECK();
-        if (n.wtt_off >= 0) {
-          pack_weight_kernel<<<dim3(grid1d(n.wtsize), c.K), 256, 0, st>>>(
-              c.vcol(d.p0), c.ldk, c.ws + n.wtt_off, n.wtsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 1);
-          LAUNCH_CHECK();
-        }
+      }
+      if (with_tangents && d.p0 >= 0 && n.wtt_off >= 0 && c.rop) {  // R-op: transposed tangent weights (dgrad term)
+        pack_weight_kernel<<<dim3(grid1d(n.wtsize), c.K), 256, 0, st>>>(
+            c.vcol(d.p0), c.ldk, c.ws + n.wtt_off, n.wtsize, g.N, Cin, g.KH, g.KW, vi.Cp, g.Nd, 1);
+        LAUNCH_CHECK();
       }
       const int ni = (int)(&n - P->nodes.data());
       const bool hsf = hs_fwd_ok(c, n), hsd = vi.tan && hs_dgr_ok(c, n);
@@ -602,6 +602,14 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
           bad |= hs_launch_pack_image(c.ws + n.wt_off, 0, reinterpret_cast<__half*>(c.ws + n.wtimg_off), 0, q.N,
                                       q.Nd, q.Kd, 1, c.hsbits() + e0, st, c.planes);
           ++g_launches;
+          if (c.rop && wt && n.wtimgt_off >= 0 && n.wtt_off >= 0) {  // R-op dgrad term  dW_k^T . delta_0
+            if (!images_from_v || !hsf) rc = hs_absmax(c, c.ws + n.wtt_off, n.wtsize, n.wtsize, e0 + 1, c.K);
+            if (rc) return rc;
+            bad |= hs_launch_pack_image(c.ws + n.wtt_off, n.wtsize, reinterpret_cast<__half*>(c.ws + n.wtimgt_off),
+                                        hs_image_halves(q.Nd, q.Kd, c.planes), q.N, q.Nd, q.Kd, c.K,
+                                        c.hsbits() + e0 + 1, st, c.planes);
+            ++g_launches;
+          }
         }
         if (bad) return fail(CURV_ERR_CUDA, "half-split weight image packing failed");
       }
@@ -977,7 +985,9 @@ static int backward(const Ctx& c, int K) {
           if (rc) return rc;
         }
         const int nidx = ni;
-        const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, ns);
+        const int wns = rop ? K : ns;  // slots whose weight gradient is wanted
+        const bool hs_w = c.kfac_G == nullptr && d.p0 >= 0 && hs_wgr_ok(c, n, wns) &&
+                          vo.slot_elems * ns <= P->hs1_elems;
         const bool hs_d = vi.tan && hs_dgr_ok(c, n);
         const bool ek = c.ekfac != nullptr && c.ekfac->has[ni];
         const int eg = c.bits_grad(d.out);
@@ -1013,22 +1023,55 @@ static int backward(const Ctx& c, int K) {
           int rc = hs_absmax(c, c.act(d.in0), 0, vi.slot_elems, ea, 1);
           if (!rc) rc = hs_split(c, c.act(d.in0), 0, vi.slot_elems, c.hs2_hi(), c.hs2_lo(), ea, 1);
           if (rc) return rc;
+          // R-op: the weight gradient of the plain backward (slot 0) is not part of H v; the planes hold slot 0 first
+          const int wskip = rop ? 1 : 0;
           HsWgradArgs h;
           memset(&h, 0, sizeof(h));
           h.g = g;
-          h.Gh = c.hs1_hi(); h.Gl = c.hs1_lo(); h.G_slot = vo.slot_elems; h.Ng = vo.Cp; h.g_bits = c.hsbits() + eg;
+          h.Gh = c.hs1_hi() + (long long)wskip * vo.slot_elems; h.Gl = c.hs1_lo() + (long long)wskip * vo.slot_elems;
+          h.G_slot = vo.slot_elems; h.Ng = vo.Cp; h.g_bits = c.hsbits() + eg;
           h.Ih = c.hs2_hi(); h.Il = c.hs2_lo(); h.i_bits = c.hsbits() + ea;
-          h.partial = scratch; h.nsplit = n.nsplit; h.nslots = ns; h.slot0 = s0; h.m_per_split = n.m_per_split;
+          h.partial = scratch; h.nsplit = n.nsplit; h.nslots = wns; h.slot0 = s0 + wskip; h.m_per_split = n.m_per_split;
           h.planes = c.planes;
           {
-            ProfScope prof(1, conv_flops(g, vi.C) * ns, st);
+            ProfScope prof(1, conv_flops(g, vi.C) * wns, st);
             if (hs_launch_wgrad(h, st)) return fail(CURV_ERR_CUDA, "half-split wgrad GEMM launch failed");
             ++g_launches;
           }
           {
-            int rc2 = launch_wgrad_finish(scratch, n.nsplit, ns, kskip, g.N, vi.C, vi.Cp, g.KH * g.KW, c.out,
+            int rc2 = launch_wgrad_finish(scratch, n.nsplit, wns, 0, g.N, vi.C, vi.Cp, g.KH * g.KW, c.out,
                                           P->params[d.p0].offset, c.ldk, c.k0, c.alpha, n.wsize, st);
             if (rc2) return rc2;
+          }
+          if (rop && vi.tan) {
+            // R-op second term  delta_0^T . da_k  (k = 1..K): the plain-backward cotangent is the shared operand, the
+            // tangent activations change per column -> one launch per column with the COLUMN BLOCKS of delta_0 as the
+            // kernel's slots (full-width MMAs, as the Gram kernels of kfac.cuh)
+            const int W8 = 64 * ceil_div(vo.Cp, 512), NS = ceil_div(vo.Cp, W8);
+            uint32_t* sb = c.hsbits() + (P->hsbits_count - 16);
+            hs_bits_fill_kernel<<<1, 32, 0, st>>>(sb, 8, c.planes == 1 ? nullptr : c.hsbits() + eg, 0u);
+            LAUNCH_CHECK();
+            for (int k = 1; k <= K; ++k) {
+              rc = hs_absmax(c, c.act(d.in0, k), 0, vi.slot_elems, ea + k, 1);
+              if (!rc) rc = hs_split(c, c.act(d.in0, k), 0, vi.slot_elems, c.hs2_hi(), c.hs2_lo(), ea + k, 1);
+              if (rc) return rc;
+              HsWgradArgs a;
+              memset(&a, 0, sizeof(a));
+              a.g = g; a.g.N = W8; a.g.Nd = W8;
+              a.Gh = c.hs1_hi(); a.Gl = c.hs1_lo(); a.G_slot = W8; a.G_ld = vo.Cp; a.Ng = W8; a.g_bits = sb;
+              a.Ih = c.hs2_hi(); a.Il = c.hs2_lo(); a.i_bits = c.hsbits() + ea + k;
+              a.partial = scratch; a.nsplit = n.nsplit; a.nslots = NS; a.slot0 = 0; a.m_per_split = n.m_per_split;
+              a.planes = c.planes;
+              {
+                ProfScope prof(1, conv_flops(g, vi.C), st);
+                if (hs_launch_wgrad(a, st)) return fail(CURV_ERR_CUDA, "half-split R-op wgrad GEMM launch failed");
+                ++g_launches;
+              }
+              int rc2 = launch_wgrad_finish(scratch, n.nsplit, 1, 0, g.N, vi.C, vi.Cp, g.KH * g.KW, c.out,
+                                            P->params[d.p0].offset, c.ldk, c.k0 + k - 1, c.alpha, n.wsize, st,
+                                            NS * W8);
+              if (rc2) return rc2;
+            }
           }
         } else if (c.kfac_G == nullptr && d.p0 >= 0) {  // weight gradient
           WgradArgs a;
@@ -1065,6 +1108,10 @@ static int backward(const Ctx& c, int K) {
           h.Ah = c.hs1_hi(); h.Al = c.hs1_lo(); h.A_slot = vo.slot_elems; h.a_slot_base = s0; h.a_has_slots = 1;
           h.a_bits = c.hsbits() + eg;
           h.W_img = reinterpret_cast<const __half*>(c.ws + n.wtimg_off);
+          if (rop && d.p0 >= 0 && n.wtimgt_off >= 0) {  // R-op: + dW_k^T . delta_0 (second segment of slot k >= 1)
+            h.Wt_img = reinterpret_cast<const __half*>(c.ws + n.wtimgt_off);
+            h.Wt_img_slot = hs_image_halves(n.dgr.Nd, n.dgr.Kd, c.planes);
+          }
           h.w_bits = c.hsbits() + c.bits_node(nidx);
           h.out = c.grad(d.in0); h.out_slot = vi.slot_elems; h.slot0 = s0; h.accumulate = ginit[d.in0];
           h.planes = c.planes;
@@ -1073,7 +1120,7 @@ static int backward(const Ctx& c, int K) {
             h.out_bits = c.hsbits() + c.bits_grad(d.in0);
           }
           {
-            ProfScope prof(0, conv_flops(g, vi.C) * ns, st);
+            ProfScope prof(0, conv_flops(g, vi.C) * (ns + (h.Wt_img ? K : 0)), st);
             if (hs_launch_gather_gemm(h, ns, st, true, ns)) return fail(CURV_ERR_CUDA, "half-split dgrad GEMM launch failed");
             ++g_launches;
           }
@@ -1302,7 +1349,7 @@ static int matmat_batch_impl(curv_program* P, int kind, int loss, const void* co
   c.rop = kind == CURV_KIND_HESSIAN;
   c.v_ready = v_ready; c.out_done = out_done;
   std::vector<char> hs_valid;
-  if (g_tc_mode && !(g_tc_disable & 32) && !c.rop && P->hs1_elems > 0 && hs_ready() > 0) {
+  if (g_tc_mode && !(g_tc_disable & 32) && !(c.rop && (g_tc_disable & 2048)) && P->hs1_elems > 0 && hs_ready() > 0) {
     c.hs = true;
     c.planes = (P->hessian & 4) ? 1 : 2;
     hs_valid.assign((size_t)P->hsbits_count, 0);

@@ -136,3 +136,42 @@ def test_resnet18_full_batch_properties():
     assert (lhs - rhs).abs().max().item() <= 1e-4 * rhs.abs().max().item()
     # positive semi-definiteness (up to rounding): diagonal of V^T G V is non-negative
     assert (torch.diagonal(S) >= -1e-6 * S.abs().max()).all()
+
+
+@pytest.mark.parametrize("batch,K", [(16, 2), (8, 8)])
+def test_resnet18_hessian_matches_float64_oracle(batch, K):
+    """The Hessian R-op on the half-split tensor-core kernels (forward, both dgrad terms, both wgrad terms) at
+    ResNet-18 layer shapes against the oracle's float64 forward-over-reverse restatement on the GPU; K = 8 fills all
+    K + 1 cotangent slots.  Also: the same product on the 3xTF32 kernels (mode bit 0x8000) agrees."""
+    import torchvision
+
+    from curvlinops_b200 import HessianLinearOperator, _capi as capi
+
+    model, X, y = _problem(batch)
+    dev = X.device
+    params = dict(model.named_parameters())
+    P = sum(p.numel() for p in params.values())
+    V = torch.rand(P, K, device=dev)
+    loss = torch.nn.CrossEntropyLoss()
+    m64 = torchvision.models.resnet18().eval().to(dev).double()
+    m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    p64 = dict(m64.named_parameters())
+    ref = []
+    for k0 in range(0, K, 2):  # two columns at a time bounds the double-backward graph memory
+        Vl = [v[..., k0:k0 + 2].reshape(*p.shape, -1).double()
+              for v, p in zip(V.split([p.numel() for p in p64.values()]), p64.values())]
+        ref.append(torch.cat([r.reshape(r.shape[0] if r.ndim == 1 else -1, r.shape[-1]).reshape(-1, r.shape[-1])
+                              for r in orc.hessian_matmat(m64, loss, p64, [(X.double(), y)], Vl)]))
+    ref = torch.cat(ref, dim=1)
+    H = HessianLinearOperator(model, loss, params, [(X, y)], check_deterministic=False)
+    got = (H @ V).double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    old = capi.lib().curv_set_tensor_core_mode(1 | 0x8000)
+    try:
+        got3 = (H @ V).double()
+    finally:
+        capi.lib().curv_set_tensor_core_mode(old)
+    err3 = (got3 - ref).abs().max().item() / ref.abs().max().item()
+    print(f"ResNet-18 Hessian, B={batch}, K={K}: max|err|/max|ref| = {err:.3e} (half-split), {err3:.3e} (3xTF32)")
+    assert err < 1e-4, err
+    assert err3 < 5e-4, err3  # the round-1 kernels (A/B switch only): TF32 splits of badly scaled cotangents

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torchvision
 from torch.profiler import profile, ProfilerActivity
-from curvlinops_b200 import GGNLinearOperator, _capi as capi
+from curvlinops_b200 import GGNLinearOperator, HessianLinearOperator, _capi as capi
 
 mode = int(sys.argv[1], 0) if len(sys.argv) > 1 else 1
 B, K = int(os.environ.get("CURV_B", 128)), int(os.environ.get("CURV_K", 8))
@@ -16,7 +16,8 @@ X, y = torch.rand(B, 3, 224, 224, device=dev).to(dt), torch.randint(0, 1000, (B,
 params = dict(model.named_parameters())
 P = sum(p.numel() for p in params.values())
 V = torch.rand(P, K, device=dev).to(dt)
-G = GGNLinearOperator(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=B)
+Op = HessianLinearOperator if os.environ.get('CURV_OP') == 'hessian' else GGNLinearOperator
+G = Op(model, torch.nn.CrossEntropyLoss(), params, [(X, y)], check_deterministic=False, num_data=B)
 capi.lib().curv_set_tensor_core_mode(mode)
 for _ in range(2):
     out = G @ V
