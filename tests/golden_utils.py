@@ -25,6 +25,7 @@ BUILDERS = {
     "ggn_diag_mlp_mse_sum": (lambda: mlp_c1(classes=4, width=12), lambda: nn.MSELoss(reduction="sum")),
     "ggn_diag_cnn_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
+    "kfac_tokens": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }
 

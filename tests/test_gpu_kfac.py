@@ -11,7 +11,8 @@ from oracle import curvature_oracle as orc
 from tests.golden_utils import load_case
 
 pytestmark = pytest.mark.gpu
-CASES = ["kfac_mlp", "kfac_cnn"]
+# kfac_tokens: Linear layers shared over the T positions of [B, T, D] sequences (KFAC-expand weight sharing)
+CASES = ["kfac_mlp", "kfac_cnn", "kfac_tokens"]
 
 
 def close(got, ref, rtol=1e-4, atol_scale=1e-5):
