@@ -945,36 +945,79 @@ __global__ void __launch_bounds__(256) vec_grad_finish_kernel(const float* __res
   if (lane == 0) out[(off + c) * ldk + k0 + k] += alpha * a;
 }
 
+// First level of the split-K sum when there are many splits of a small weight tensor (layer1: 196 splits of 37 K
+// weights - one thread per weight would walk 196 x 8 strided loads with a handful of warps per SM):
+// partial[ch * L][j] = sum_{sp in [ch * L, min(nsplit, (ch + 1) * L))} partial[sp][j], j < split_elems, fixed order;
+// grid (x, chunks).  The finish kernel then sums the chunk heads (split_step = L).
+__global__ void __launch_bounds__(256) wgrad_presum_kernel(float* __restrict__ partial, int nsplit, int L,
+                                                          long long split_elems) {
+  const int s0 = blockIdx.y * L, s1 = min(nsplit, s0 + L);
+  float4* base = reinterpret_cast<float4*>(partial + (long long)s0 * split_elems);
+  const long long n4 = split_elems >> 2;  // split_elems is a multiple of 4 (Cp % 8 == 0)
+  for (long long j = blockIdx.x * 256LL + threadIdx.x; j < n4; j += (long long)gridDim.x * 256) {
+    float4 a = base[j];
+    int sp = s0 + 1;
+    for (; sp + 2 <= s1; sp += 2) {
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(partial + (long long)sp * split_elems) + j);
+      const float4 c = __ldcs(reinterpret_cast<const float4*>(partial + (long long)(sp + 1) * split_elems) + j);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    }
+    for (; sp < s1; ++sp) {
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(partial + (long long)sp * split_elems) + j);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    base[j] = a;
+  }
+}
+
 // out[(off + ((n*C + c)*taps + tap))*ldk + k0 + k] += alpha * sum_splits partial[split][k][n][tap][cp]
-__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int nsplit, int nslots,
-                                    int kskip, int N, int C, int Cp, int taps, float* __restrict__ out,
-                                    long long off, int ldk, int k0, float alpha, int nrows) {
-  // block = (32 weight elements, nslots - kskip columns): a warp reads 128 contiguous bytes of one slot's
-  // partial per split; the splits are summed in a fixed order with four independent chains (deterministic).
-  // (Round 2 tried two variants of the K-minor update -- a CTA tile transposed through shared memory with
-  // contiguous row writes, and 16-byte row read-modify-writes after a 32 x nk transpose: 6.2 ms and 2.7 ms per C2
-  // step against 2.3 ms for this one; the L2 merges the nk 4-byte updates of a row.)
+// One thread per weight element (output row): it sums the splits of every column in a fixed order (reads coalesced
+// over the warp for each (split, column)) and updates the nk <= 8 adjacent floats of its row with one 16- or 32-byte
+// read-modify-write when the row is aligned.  (Round 2 tried a CTA tile transposed through shared memory, 6.2 ms per
+// C2 step, and a 32 x nk register transpose, 2.7 ms, against 2.3 ms for the column-per-warp kernel this replaces,
+// whose 4-byte updates used one eighth of every 32-byte sector.)
+// split_step: distance between the splits to sum, in splits (> 1 after wgrad_presum_kernel)
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ partial, int nsplit, int nslots,
+                                                          int kskip, int N, int C, int Cp, int taps,
+                                                          float* __restrict__ out, long long off, int ldk, int k0,
+                                                          float alpha, int nrows, int split_step) {
   const long long per = (long long)N * taps * Cp;
   const long long per_slot = (long long)(nrows > 0 ? nrows : N) * taps * Cp;
-  const int k = kskip + threadIdx.y;
-  const long long stride = (long long)nslots * per_slot;
-  for (long long i = blockIdx.x * 32LL + threadIdx.x; i < per; i += (long long)gridDim.x * 32) {
-    int c = (int)(i % Cp);
+  const long long stride = (long long)nslots * per_slot * split_step;
+  const int nk = nslots - kskip;
+  const bool vec = (ldk % 4 == 0) && (k0 % 4 == 0) && (nk % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < per; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % Cp);
     if (c >= C) continue;
-    long long r = i / Cp;
-    int tap = (int)(r % taps);
-    int n = (int)(r / taps);
-    const float* q = partial + (long long)k * per_slot + i;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int sp = 0;
-    for (; sp + 4 <= nsplit; sp += 4) {
-      s0 += __ldg(q + (long long)sp * stride);
-      s1 += __ldg(q + (long long)(sp + 1) * stride);
-      s2 += __ldg(q + (long long)(sp + 2) * stride);
-      s3 += __ldg(q + (long long)(sp + 3) * stride);
+    const long long r = i / Cp;
+    const int tap = (int)(r % taps);
+    const int n = (int)(r / taps);
+    const float* q = partial + (long long)kskip * per_slot + i;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float* qs = q + (long long)sp * stride;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nk) acc[k] += __ldg(qs + (long long)k * per_slot);
     }
-    for (; sp < nsplit; ++sp) s0 += __ldg(q + (long long)sp * stride);
-    out[(off + ((long long)n * C + c) * taps + tap) * ldk + k0 + k - kskip] += alpha * ((s0 + s1) + (s2 + s3));
+    float* o = out + (off + ((long long)n * C + c) * taps + tap) * ldk + k0;
+    if (vec) {
+#pragma unroll
+      for (int k = 0; k < 8; k += 4) {
+        if (k < nk) {
+          float4 v = *reinterpret_cast<float4*>(o + k);
+          v.x += alpha * acc[k]; v.y += alpha * acc[k + 1]; v.z += alpha * acc[k + 2]; v.w += alpha * acc[k + 3];
+          *reinterpret_cast<float4*>(o + k) = v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nk) o[k] += alpha * acc[k];
+    }
   }
 }
 

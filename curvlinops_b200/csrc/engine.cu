@@ -430,12 +430,26 @@ static int launch_wgrad(const WgradArgs& a, int bm, int bn, cudaStream_t st, dou
 }
 
 // split-K finish of a weight gradient: partial [split][slot][n][tap][cp] -> out rows of the parameter (K minor)
-// nrows: rows per slot of the partials (0: N; larger when the slots were column blocks padded to the block width)
-static int launch_wgrad_finish(const float* partial, int nsplit, int ns, int kskip, int N, int C, int Cp, int taps,
+// nrows: rows per slot of the partials (0: N; larger when the slots were column blocks padded to the block width).
+// The partials are consumed (many splits are first summed in place, chunk by chunk).
+static int launch_wgrad_finish(float* partial, int nsplit, int ns, int kskip, int N, int C, int Cp, int taps,
                                float* out, long long off, int ldk, int k0, float alpha, long long wsize,
                                cudaStream_t st, int nrows = 0) {
-  wgrad_finish_kernel<<<grid1d(wsize, 32), dim3(32, ns - kskip), 0, st>>>(partial, nsplit, ns, kskip, N, C, Cp, taps,
-                                                                          out, off, ldk, k0, alpha, nrows);
+  if (ns - kskip > 8) return fail(CURV_ERR_INVALID, "wgrad finish: more than 8 columns");
+  const long long split_elems = (long long)ns * (nrows > 0 ? nrows : N) * taps * Cp;
+  int step = 1;
+  if (nsplit >= 12 && split_elems % 4 == 0) {
+    int L = 2;
+    while ((long long)L * L < nsplit) ++L;
+    const int nch = ceil_div(nsplit, L);
+    const int gx = std::max(1, std::min(grid1d(split_elems / 4), (148 * 16) / nch));
+    wgrad_presum_kernel<<<dim3(gx, nch), 256, 0, st>>>(partial, nsplit, L, split_elems);
+    LAUNCH_CHECK();
+    step = L;
+    nsplit = nch;
+  }
+  wgrad_finish_kernel<<<grid1d((long long)N * taps * Cp), 256, 0, st>>>(partial, nsplit, ns, kskip, N, C, Cp, taps, out,
+                                                                        off, ldk, k0, alpha, nrows, step);
   LAUNCH_CHECK();
   return CURV_OK;
 }
