@@ -41,6 +41,8 @@ class LayerProgram:
     bias_nodes: dict = field(default_factory=dict)  # bias param name -> node index
     out_features: int = 0
     tied: set = field(default_factory=set)  # parameters used by more than one layer
+    conv_usages: dict = field(default_factory=dict)  # weight param name -> [node indices] (several: weight tying)
+    bias_usages: dict = field(default_factory=dict)  # bias param name -> [node indices]
     tokens_input: bool = False  # the network input is a token sequence [B, T, D] (handed to the engine as [B, D, 1, T])
 
     def add_value(self, C, H, W, tan):
@@ -185,8 +187,10 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             if names[p0] in prog.conv_nodes:
                 prog.tied.add(names[p0])
             prog.conv_nodes[names[p0]] = ni
+            prog.conv_usages.setdefault(names[p0], []).append(ni)
         if p1 >= 0:
             prog.bias_nodes[names[p1]] = ni
+            prog.bias_usages.setdefault(names[p1], []).append(ni)
         return _Ref("act", value=ov, flat=False)
 
     def emit_linear(node, xr, wref, bref):

@@ -239,10 +239,6 @@ class KFACComputer(CurvatureLinearOperator):
         if prog is None:
             prog = CompiledProgram(eng.model_func, eng.params, X, 8, 2 | (4 if eng.bf16 else 0))
             eng._programs[key] = prog
-            if prog.lp.tied:
-                raise NotImplementedError(
-                    f"Weight tying ({sorted(prog.lp.tied)}) is not supported by the KFAC factor kernels."
-                )
         return prog
 
     def _group_node(self, prog: CompiledProgram, group: dict[str, str]) -> int:
@@ -251,15 +247,29 @@ class KFACComputer(CurvatureLinearOperator):
             return lp.conv_nodes[group["W"]]
         return lp.bias_nodes[group["b"]]
 
+    def _group_usages(self, prog: CompiledProgram, group: dict[str, str]) -> list[int]:
+        """Nodes that use the group's parameters: one, or several under weight tying (the usages are concatenated
+        along the weight-sharing axis, reference ``io_collector/groups.py:123-168``)."""
+        lp = prog.lp
+        if "W" not in group:
+            return list(lp.bias_usages[group["b"]])
+        nodes = list(lp.conv_usages[group["W"]])
+        if "b" in group and sorted(lp.bias_usages.get(group["b"], [])) != sorted(nodes):
+            raise NotImplementedError(
+                f"Weight {group['W']!r} and bias {group['b']!r} are not used by the same layers; "
+                "use separate_weight_and_bias=True.")
+        return nodes
+
     def _accumulate(self, prog, ws, X, gos, scale, corr, A, G):
         dev = X.device
         L = capi.lib()
         nodes, a_ptrs, g_ptrs, joint = [], [], [], []
-        per_node_G: dict = {}
+        owner: dict = {}      # usage tuple -> key of the group whose G the kernels accumulate into
+        tied_A: list = []     # (key, [(temporary A of one usage, positions of that usage)])
         for group in self._mapping:
             key = tuple(group.values())
-            ni = self._group_node(prog, group)
-            node = prog.lp.nodes[ni]
+            usages = self._group_usages(prog, group)
+            node = prog.lp.nodes[usages[0]]
             cin, _, _, _ = prog.lp.values[node["in0"]]
             cout = prog.lp.values[node["out"]][0]
             has_joint = "W" in group and "b" in group
@@ -267,19 +277,27 @@ class KFACComputer(CurvatureLinearOperator):
                 width = cin * node["kh"] * node["kw"] + (1 if has_joint else 0)
                 if key not in A:
                     A[key] = torch.zeros(width, width, device=dev, dtype=torch.float32)
-                a_ptr = A[key].data_ptr()
-            else:
-                a_ptr = 0
             if key not in G:
                 G[key] = torch.zeros(cout, cout, device=dev, dtype=torch.float32)
             # the weight and the bias group of a layer share one G: accumulate once, copy afterwards
-            if ni in per_node_G:
-                g_ptr = 0
-            else:
-                per_node_G[ni] = key
-                g_ptr = G[key].data_ptr()
-            nodes.append(ni); a_ptrs.append(a_ptr); g_ptrs.append(g_ptr); joint.append(int(has_joint))
-        before = {ni: G[key].clone() for ni, key in per_node_G.items()}
+            first = tuple(usages) not in owner
+            if first:
+                owner[tuple(usages)] = key
+            temps = []
+            for ni in usages:
+                if "W" not in group:
+                    a_ptr = 0
+                elif len(usages) == 1:
+                    a_ptr = A[key].data_ptr()
+                else:  # tied: every usage is normalised by its own number of positions; re-weighted below
+                    vo = prog.lp.values[prog.lp.nodes[ni]["out"]]
+                    temps.append((torch.zeros_like(A[key]), vo[1] * vo[2]))
+                    a_ptr = temps[-1][0].data_ptr()
+                nodes.append(ni); a_ptrs.append(a_ptr); g_ptrs.append(G[key].data_ptr() if first else 0)
+                joint.append(int(has_joint))
+            if temps:
+                tied_A.append((key, temps))
+        before = {key: G[key].clone() for key in owner.values()}
         V = 0 if gos is None else gos.shape[0]
         if V > 0:
             seeds = (gos * scale).permute(1, 2, 0).contiguous()  # [B, C, V]
@@ -292,11 +310,15 @@ class KFACComputer(CurvatureLinearOperator):
             ws.numel() * 4, torch.cuda.current_stream(dev).cuda_stream)
         capi.check(rc)
         del keep
+        for key, temps in tied_A:  # A = sum over usages / (N * total positions)
+            total = sum(S for _, S in temps)
+            for t, S in temps:
+                A[key].add_(t, alpha=S / total)
         for group in self._mapping:  # second group of a layer: add the same increment
             key = tuple(group.values())
-            ni = self._group_node(prog, group)
-            if per_node_G[ni] != key:
-                G[key] += G[per_node_G[ni]] - before[ni]
+            own = owner[tuple(self._group_usages(prog, group))]
+            if own != key:
+                G[key] += G[own] - before[own]
 
 
 class KFACLinearOperator(_ChainPyTorchLinearOperator):

@@ -49,7 +49,7 @@ def curvature_cases(name, model, data, loss, K):
     save(name, model, data, extra)
 
 
-def kfac_cases(name, model, data, loss, damping=1e-2):
+def kfac_cases(name, model, data, loss, damping=1e-2, backend="hooks", ekfac=True):
     params = {n: p for n, p in model.named_parameters()
               if isinstance(dict(model.named_modules())[n.rsplit(".", 1)[0]], (nn.Linear, nn.Conv2d))}
     P = sum(p.numel() for p in params.values())
@@ -61,7 +61,7 @@ def kfac_cases(name, model, data, loss, damping=1e-2):
             tag = f"{ft.replace('-', '')}_{'sep' if sep else 'joint'}"
             Kop = KFACLinearOperator(model, loss, params, data, check_deterministic=False,
                                      fisher_type=ft, mc_samples=(2 if ft == 'mc' else 1), seed=77,
-                                     separate_weight_and_bias=sep)
+                                     separate_weight_and_bias=sep, backend=backend)
             extra[f"kfac_{tag}"] = Kop @ v
             extra[f"kfacinv_{tag}"] = Kop.inverse(damping=damping) @ v
             if ft == "type-2":
@@ -69,8 +69,10 @@ def kfac_cases(name, model, data, loss, damping=1e-2):
                 for bi, blk in enumerate(Kb):
                     for fi, fac in enumerate(blk):
                         extra[f"factor_{tag}_{bi}_{fi}"] = fac
+                if not ekfac:
+                    continue
                 E = EKFACLinearOperator(model, loss, params, data, check_deterministic=False,
-                                        fisher_type=ft, separate_weight_and_bias=sep)
+                                        fisher_type=ft, separate_weight_and_bias=sep, backend=backend)
                 extra[f"ekfac_{tag}"] = E @ v
                 extra[f"ekfacinv_{tag}"] = E.inverse(damping=damping) @ v
     save(name, model, data, extra)

@@ -110,3 +110,23 @@ class TokenMLP(nn.Module):
     def forward(self, x):
         x = x + self.fc2(torch.nn.functional.gelu(self.fc1(self.ln1(x))))
         return self.head(self.ln2(x).mean(1))
+
+
+class TiedNet(nn.Module):
+    """Weight tying: one Conv2d and one Linear applied twice each (reference io_collector/groups.py:123-168 concatenates
+    the usages of a tied parameter along the weight-sharing axis)."""
+
+    def __init__(self, classes: int = 5):
+        super().__init__()
+        self.stem = nn.Conv2d(3, 4, 3, padding=1)
+        self.conv = nn.Conv2d(4, 4, 3, padding=1)
+        self.fc = nn.Linear(4, 4)
+        self.head = nn.Linear(4, classes)
+
+    def forward(self, x):
+        x = torch.tanh(self.stem(x))
+        x = torch.nn.functional.max_pool2d(torch.tanh(self.conv(x)), 2)   # first usage on 8 x 8, second on 4 x 4
+        x = torch.tanh(self.conv(x))
+        x = torch.nn.functional.adaptive_avg_pool2d(x, 1).flatten(1)
+        x = torch.tanh(self.fc(torch.tanh(self.fc(x))))
+        return self.head(x)

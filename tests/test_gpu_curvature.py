@@ -307,3 +307,46 @@ def test_mc_sampler_draws_from_the_softmax():
     freq = (p.unsqueeze(1) - g).mean(1)                    # mean of the one-hot draws
     se = (p * (1 - p) / M).sqrt()
     assert ((freq - p).abs() <= 5 * se + 1e-6).all()
+
+
+class _TiedNet(torch.nn.Module):
+    """One Linear and one Conv2d used twice each (weight tying): the engine reads the same columns of V for both
+    usages and accumulates both gradients into the same rows of the result."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(4, 4, 3, padding=1)
+        self.stem = torch.nn.Conv2d(3, 4, 3, padding=1)
+        self.fc = torch.nn.Linear(4, 4)
+        self.head = torch.nn.Linear(4, 5)
+
+    def forward(self, x):
+        x = torch.tanh(self.stem(x))
+        x = torch.tanh(self.conv(x))
+        x = torch.tanh(self.conv(x))
+        x = torch.nn.functional.adaptive_avg_pool2d(x, 1).flatten(1)
+        x = torch.tanh(self.fc(x))
+        x = torch.tanh(self.fc(x))
+        return self.head(x)
+
+
+@pytest.mark.parametrize("op", ["ggn", "hessian"])
+def test_weight_tying_matches_float64_oracle(op):
+    torch.manual_seed(3)
+    model = _TiedNet().cuda().eval()
+    data = [(torch.rand(6, 3, 8, 8, device="cuda"), torch.randint(0, 5, (6,), device="cuda")),
+            (torch.rand(3, 3, 8, 8, device="cuda"), torch.randint(0, 5, (3,), device="cuda"))]
+    loss = torch.nn.CrossEntropyLoss()
+    params = dict(model.named_parameters())
+    m64 = _TiedNet().double().eval()
+    m64.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    p64 = dict(m64.named_parameters())
+    data64 = [(X.double().cpu(), y.cpu()) for X, y in data]
+    V = torch.rand(sum(p.numel() for p in params.values()), 3, dtype=torch.float64)
+    if op == "ggn":
+        ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V, p64)))
+        A = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    else:
+        ref = flat(orc.hessian_matmat(m64, loss, p64, data64, split_like(V, p64)))
+        A = HessianLinearOperator(model, loss, params, data, check_deterministic=False)
+    assert_parity(A @ V.float().cuda(), ref, params)

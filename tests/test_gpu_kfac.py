@@ -13,6 +13,9 @@ from tests.golden_utils import load_case
 pytestmark = pytest.mark.gpu
 # kfac_tokens: Linear layers shared over the T positions of [B, T, D] sequences (KFAC-expand weight sharing)
 CASES = ["kfac_mlp", "kfac_cnn", "kfac_tokens"]
+# kfac_tied: one Conv2d and one Linear used twice each; fixture from the reference's make_fx backend (usages concatenated
+# along the weight-sharing axis).  KFAC only: the eigenvalue correction rejects tied weights.
+KFAC_CASES = CASES + ["kfac_tied"]
 
 
 def close(got, ref, rtol=1e-4, atol_scale=1e-5):
@@ -30,7 +33,7 @@ def setup(name):
     return model, loss, data, fx, params
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", KFAC_CASES)
 @pytest.mark.parametrize("sep", [False, True])
 def test_kfac_type2(name, sep):
     model, loss, data, fx, params = setup(name)
@@ -50,7 +53,7 @@ def test_kfac_type2(name, sep):
     torch.testing.assert_close(Kop.frobenius_norm().double(), dense.norm(), rtol=1e-4, atol=1e-8)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", KFAC_CASES)
 @pytest.mark.parametrize("ft", ["mc", "empirical"])
 def test_kfac_sampled_and_empirical(name, ft, monkeypatch):
     """MC: the engine is handed the would-be gradients the reference drew (same generator stream)."""
@@ -123,7 +126,7 @@ def test_unsupported_params_raise():
         KFACLinearOperator(model, loss, dict(model.named_parameters()), data, fisher_type="nope")
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", KFAC_CASES)
 def test_kfac_type2_on_tensor_core_kernels(name):
     """Same factors with every contraction forced onto the tcgen05 kernels (half-split forward / dgrad sweeps,
     3xTF32 Gram matrices): exercises the tensor-core paths at the fixtures' small shapes."""
@@ -172,3 +175,9 @@ def test_ekfac_device_correction_matches_host_path(sep, monkeypatch):
     for k in lam_dev:
         assert lam_dev[k].shape == lam_host[k].shape, k
         close(lam_dev[k], lam_host[k], rtol=1e-4, atol_scale=1e-5)
+
+
+def test_ekfac_rejects_tied_weights():
+    model, loss, data, fx, params = setup("kfac_tied")
+    with pytest.raises(NotImplementedError, match="Weight tying"):
+        EKFACLinearOperator(model, loss, params, data, fisher_type="type-2", check_deterministic=False)
