@@ -72,6 +72,16 @@ def _pair(x):
     return (int(x[0]), int(x[1])) if len(x) == 2 else (int(x[0]), int(x[0]))
 
 
+def _simple_token_view(node, ref, B, prog) -> bool:
+    """The two reshapes the plain table handles itself: [B, T, C] <-> [B*T, C] of a token activation."""
+    if ref.kind != "act" or node.target not in (aten.view.default, aten._unsafe_view.default, aten.reshape.default):
+        return False
+    C, H, W, _ = prog.values[ref.value]
+    shape = tuple(int(d) for d in node.meta["val"].shape) if "val" in node.meta else None
+    tk = getattr(ref, "tok", None)
+    return (tk == 3 and shape == (B * W, C)) or (tk == 2 and shape == (B, W, C))
+
+
 def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = True) -> LayerProgram:
     """Trace ``model_func(params, X)`` and lower it to a :class:`LayerProgram`.
 
@@ -121,6 +131,58 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
 
     def like(xr, value):
         return _Ref("act", value=value, flat=xr.flat, tok=tok_of(xr))
+
+    # ---- layout bookkeeping of token tensors ---------------------------------------------------------------------
+    # The engine stores a token value as [B, T, C] whatever the traced program does with it.  nn.MultiheadAttention
+    # works sequence-first and splits heads through a chain of view / transpose / select nodes; instead of pattern
+    # matching that chain, a "lazy" reference carries an explicit index map: an integer tensor shaped like the traced
+    # tensor whose entries are the flat positions in the engine value it reads.  View-like nodes are applied to the
+    # map; as soon as the map equals one of the layouts a layer can consume, the reference becomes an ordinary
+    # activation again with the tag tok = 3 ([B, T, C]), 2 ([B*T, C]), "t3" ([T, B, C]) or "t2" ([T*B, C]).
+    def token_maps(value):
+        C, H, W, _ = prog.values[value]
+        base = torch.arange(Bsz * W * C, dtype=torch.int32).view(Bsz, W, C)
+        return {3: base, 2: base.reshape(Bsz * W, C), "t3": base.transpose(0, 1), "t2": base.transpose(0, 1).reshape(W * Bsz, C)}
+
+    def to_lazy(ref):
+        if ref.kind == "lazy":
+            return ref
+        if ref.kind != "act":
+            return None
+        C, H, W, _ = shape_of(ref)
+        tk = tok_of(ref)
+        if tk is not None:
+            return _Ref("lazy", value=ref.value, idx=token_maps(ref.value)[tk])
+        return None
+
+    def resolve(lz):
+        """lazy -> tagged activation if its map is one of the consumable layouts, else the lazy reference itself."""
+        C, H, W, _ = prog.values[lz.value]
+        if H != 1:
+            return lz
+        for tag, m in token_maps(lz.value).items():
+            if tuple(m.shape) == tuple(lz.idx.shape) and torch.equal(m, lz.idx):
+                return _Ref("act", value=lz.value, flat=False, tok=tag)
+        return lz
+
+    VIEW_LIKE = {aten.view.default, aten._unsafe_view.default, aten.reshape.default, aten.unsqueeze.default,
+                 aten.squeeze.dim, aten.transpose.int, aten.permute.default, aten.select.int}
+
+    def apply_view(node, lz):
+        t, args = node.target, node.args
+        if t in (aten.view.default, aten._unsafe_view.default, aten.reshape.default):
+            idx = lz.idx.reshape(tuple(int(d) for d in node.meta["val"].shape))
+        elif t == aten.unsqueeze.default:
+            idx = lz.idx.unsqueeze(int(args[1]))
+        elif t == aten.squeeze.dim:
+            idx = lz.idx.squeeze(int(args[1]))
+        elif t == aten.transpose.int:
+            idx = lz.idx.transpose(int(args[1]), int(args[2]))
+        elif t == aten.permute.default:
+            idx = lz.idx.permute(*[int(d) for d in args[1]])
+        else:
+            idx = lz.idx.select(int(args[1]), int(args[2]))
+        return resolve(_Ref("lazy", value=lz.value, idx=idx))
 
     # liveness: only lower nodes the output depends on
     out_node = [n for n in gm.graph.nodes if n.op == "output"][0]
@@ -200,13 +262,13 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         w = wref.base
         C, H, W, _ = shape_of(xr)
         wshape = w.shape if w.kind == "param" else tuple(w.tensor.shape)
-        if tok_of(xr) == 2:  # Linear applied to every token: a 1x1 convolution over the [1, T] token map
+        if tok_of(xr) in (2, "t2"):  # Linear applied to every token: a 1x1 convolution over the [1, T] token map
             if len(wshape) != 2 or wshape[1] != C:
                 unsupported(node, f"weight shape {wshape} does not match token features {C}")
             out = emit_conv(node, xr, w, bref, 1, 1, 1, 1, 0, 0, wshape[0], H, W)
-            out.tok = 2
+            out.tok = tok_of(xr)  # rows in the same order as the input's
             return out
-        if tok_of(xr) == 3:
+        if tok_of(xr) in (3, "t3"):
             unsupported(node, "matmul on a [B, T, D] tensor that was not flattened to [B*T, D]")
         if len(wshape) != 2 or wshape[1] != C * H * W:
             unsupported(node, f"weight shape {wshape} does not match input features {C * H * W}")
@@ -215,6 +277,30 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         # Linear after flatten of a [C, H, W] map == 'valid' HxW convolution (NCHW flatten order
         # (c, h, w) is exactly the conv weight layout [out, C, H, W]).
         return emit_conv(node, xr, w, bref, H, W, 1, 1, 0, 0, wshape[0], 1, 1)
+
+    def emit_attention(node, a):
+        """scaled_dot_product_attention on the head-split views of one packed projection -> OP_ATTENTION."""
+        schema = [arg.name for arg in node.target._schema.arguments]
+        vals = dict(zip(schema, node.args))  # arguments left at their defaults are absent
+        vals.update(node.kwargs)
+        if vals.get("dropout_p") not in (None, 0, 0.0) or vals.get("is_causal") or vals.get("scale") is not None \
+                or vals.get("attn_mask") is not None or vals.get("attn_bias") is not None:
+            unsupported(node, "attention with dropout, masks, causal masking or a custom scale")
+        q, k, v = (to_lazy(r) if isinstance(r, _Ref) else None for r in a[:3])
+        if q is None or k is None or v is None or not (q.value == k.value == v.value) or q.idx.ndim != 4:
+            unsupported(node, "attention whose query / key / value are not head-split views of one packed projection")
+        C3, H, T, tan = prog.values[q.value]
+        heads, E = int(q.idx.shape[1]), C3 // 3
+        if H != 1 or C3 % 3 or E % heads or E % 8:
+            unsupported(node, "attention needs a packed [B, T, 3E] projection with E a multiple of 8 and of the head count")
+        grid = torch.arange(Bsz * T * C3, dtype=torch.int32).view(Bsz, T, 3, heads, E // heads)
+        for j, r in enumerate((q, k, v)):
+            if not torch.equal(r.idx, grid[:, :, j].permute(0, 2, 1, 3)):
+                unsupported(node, "attention operands are not the q / k / v thirds of the packed projection, split into heads")
+        ov = prog.add_value(E, 1, T, tan)
+        prog.add_node(capi.OP_ATTENTION, in0=q.value, out=ov, kh=heads)
+        out_idx = torch.arange(Bsz * T * E, dtype=torch.int32).view(Bsz, T, heads, E // heads).permute(0, 2, 1, 3)
+        return _Ref("tuple", items=[_Ref("lazy", value=ov, idx=out_idx)] + [None] * 9)
 
     for node in gm.graph.nodes:
         if node.op in ("placeholder", "output") or node not in live:
@@ -228,6 +314,11 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         a = [env.get(x, x) if isinstance(x, torch.fx.Node) else x for x in node.args]
         if t in (aten.detach.default, aten.alias.default, aten.clone.default, aten.contiguous.default):
             env[node] = a[0]
+        elif (t in VIEW_LIKE and isinstance(a[0], _Ref) and (a[0].kind == "lazy" or (a[0].kind == "act" and tok_of(a[0])))
+              and not _simple_token_view(node, a[0], Bsz, prog)):
+            env[node] = apply_view(node, to_lazy(a[0]))
+        elif "_scaled_dot_product" in str(t):
+            env[node] = emit_attention(node, a)
         elif t == aten.t.default or (t == aten.transpose.int and a[0].kind in ("param", "const")):
             if a[0].kind not in ("param", "const"):
                 unsupported(node, "transpose of an activation")
@@ -317,6 +408,24 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             ov = prog.add_value(C, H, W, tan)
             prog.add_node(op, in0=xr.value, out=ov)
             env[node] = like(xr, ov)
+        elif t == aten.add.Tensor and isinstance(a[0], _Ref) and isinstance(a[1], _Ref) and a[0].kind == "act" \
+                and a[1].kind in ("param", "const") and node.kwargs.get("alpha", 1) == 1:
+            # x @ W^T traced as mm followed by "+ bias" (nn.MultiheadAttention's packed projection): fold the bias
+            # into the producing layer
+            xr, bref = a[0], a[1]
+            prod = producer.get(xr.value)
+            bshape = bref.shape if bref.kind == "param" else tuple(bref.tensor.shape)
+            if (prod is None or prog.nodes[prod]["op"] != capi.OP_CONV or prog.nodes[prod]["p1"] >= 0
+                    or prog.nodes[prod]["c1"] >= 0 or tuple(bshape) != (shape_of(xr)[0],)
+                    or readers.get(alias_root(node.args[0]), 0) != 1):
+                unsupported(node, "adding a parameter to an activation (other than the bias of the layer that produced it)")
+            p1, c1 = weight_slots(bref)
+            prog.nodes[prod]["p1"], prog.nodes[prod]["c1"] = p1, c1
+            if p1 >= 0:
+                prog.bias_nodes[names[p1]] = prod
+                prog.bias_usages.setdefault(names[p1], []).append(prod)
+                prog.values[xr.value][3] = True
+            env[node] = xr
         elif t == aten.add.Tensor:
             xr, yr = a[0], a[1]
             alpha = node.kwargs.get("alpha", 1)

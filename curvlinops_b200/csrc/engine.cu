@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
+#include "attention.cuh"
 #include "tc_gemm.cuh"
 #include "hs_gemm.cuh"
 
@@ -274,6 +275,17 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
       long long need = (long long)n.nchunks * (kmax + 1) * 2 * vi.Cp;
       if (need > scratch) scratch = need;
+    } else if (d.op == CURV_OP_ATTENTION) {
+      const Value& vi = P->values[d.in0];
+      const Value& vo = P->values[d.out];
+      if (hessian & 1) { delete P; return fail(CURV_ERR_UNSUPPORTED, "attention is not supported by the Hessian R-op program"); }
+      if (d.kh < 1 || vo.C % d.kh != 0 || vi.C != 3 * vo.C || vi.H != 1 || vo.H != 1 || vi.W != vo.W ||
+          vi.Cp != vi.C || vo.Cp != vo.C) {
+        delete P; return fail(CURV_ERR_INVALID, "attention node: in0 must be [B, T, 3E], out [B, T, E], E a multiple of 8 and of the head count");
+      }
+      const long long pt = (long long)batch * d.kh * vi.W * vi.W;  // softmax matrices of one slot
+      n.aux_off = alloc(pt);
+      if (pt * kmax > scratch) scratch = pt * kmax;
     } else if (d.op == CURV_OP_MAXPOOL) {
       const Value& vo = P->values[d.out];
       n.idx_off = alloc((vo.slot_elems + 3) / 4);  // float offset of a byte buffer (1 byte per element)
@@ -712,6 +724,138 @@ static int signal_out_done(const Ctx& c, const Node& n) {
   return CURV_OK;
 }
 
+// ---- multi-head attention core (attention.cuh): batched over (slot, example, head) with three-level strides
+static int attn_gemm(cudaStream_t st, Bgemm3 p, int n0) {
+  if (n0 < 1) return CURV_OK;
+  const long long nz = (long long)n0 * p.n1 * p.n2;
+  if (nz > 65535) return fail(CURV_ERR_UNSUPPORTED, "attention: more than 65535 (slot, example, head) triples per launch");
+  attn_bgemm_kernel<<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)nz), 256, 0, st>>>(p);
+  LAUNCH_CHECK();
+  return CURV_OK;
+}
+struct AttnDims {
+  int T, E, H, dh, B;
+  long long lin, lout, pt;  // slot strides of in / out, softmax elements per slot
+  float scale;
+};
+static AttnDims attn_dims(const Ctx& c, const Node& n) {
+  const Value& vi = c.P->values[n.d.in0];
+  const Value& vo = c.P->values[n.d.out];
+  AttnDims a;
+  a.T = vi.W; a.E = vo.C; a.H = n.d.kh; a.dh = a.E / a.H; a.B = c.P->B;
+  a.lin = vi.slot_elems; a.lout = vo.slot_elems; a.pt = (long long)a.B * a.H * a.T * a.T;
+  a.scale = 1.f / sqrtf((float)a.dh);
+  return a;
+}
+// operand descriptors: activations [slot][b][t][3E or E] (head h at column offset col0 + h * dh), softmax-shaped
+// buffers [slot][b][h][T][T]
+static void attn_act(const AttnDims& a, const float* base, int ld, long long slot_stride, int col0, const float*& ptr,
+                     int& ldo, long long s[3]) {
+  ptr = base + col0; ldo = ld; s[0] = slot_stride; s[1] = (long long)a.T * ld; s[2] = a.dh;
+}
+static void attn_sm(const AttnDims& a, const float* base, bool per_slot, const float*& ptr, int& ldo, long long s[3]) {
+  ptr = base; ldo = a.T; s[0] = per_slot ? a.pt : 0; s[1] = (long long)a.H * a.T * a.T; s[2] = (long long)a.T * a.T;
+}
+static int attention_forward(const Ctx& c, const Node& n, int K) {
+  cudaStream_t st = c.st;
+  const AttnDims a = attn_dims(c, n);
+  const int E = a.E, T = a.T, ldi = 3 * E;
+  const float* in = c.act(n.d.in0);
+  float* out = c.act(n.d.out);
+  float* Pm = c.ws + n.aux_off;
+  float* D = c.ws + c.P->scratch_off;
+  int rc;
+  Bgemm3 g;
+  memset(&g, 0, sizeof(g));
+  g.n1 = a.B; g.n2 = a.H;
+  // S = scale Q K^T
+  g.transA = 0; g.transB = 1; g.M = T; g.N = T; g.Kd = a.dh; g.alpha = a.scale; g.beta = 0.f;
+  attn_act(a, in, ldi, 0, 0, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, E, g.B, g.ldb, g.sB);
+  { const float* q; attn_sm(a, Pm, false, q, g.ldc, g.sC); g.C = Pm; }
+  if ((rc = attn_gemm(st, g, 1))) return rc;
+  attn_softmax_kernel<<<(unsigned)(((long long)a.B * a.H * T + 7) / 8), 256, 0, st>>>(Pm, (long long)a.B * a.H * T, T);
+  LAUNCH_CHECK();
+  // O = P V
+  g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = 1.f; g.beta = 0.f;
+  attn_sm(a, Pm, false, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, 2 * E, g.B, g.ldb, g.sB);
+  { const float* q; attn_act(a, out, E, 0, 0, q, g.ldc, g.sC); g.C = out; }
+  if ((rc = attn_gemm(st, g, 1))) return rc;
+  if (K < 1) return CURV_OK;
+  if (a.pt * K > c.P->scratch_elems) return fail(CURV_ERR_WORKSPACE, "attention scratch too small");
+  const float* tin = in + a.lin;    // tangent slots 1..K
+  float* tout = out + a.lout;
+  // dS = scale (dQ K^T + Q dK^T)
+  g.transA = 0; g.transB = 1; g.M = T; g.N = T; g.Kd = a.dh; g.alpha = a.scale; g.beta = 0.f;
+  attn_act(a, tin, ldi, a.lin, 0, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, E, g.B, g.ldb, g.sB);
+  { const float* q; attn_sm(a, D, true, q, g.ldc, g.sC); g.C = D; }
+  if ((rc = attn_gemm(st, g, K))) return rc;
+  g.beta = 1.f;
+  attn_act(a, in, ldi, 0, 0, g.A, g.lda, g.sA);
+  attn_act(a, tin, ldi, a.lin, E, g.B, g.ldb, g.sB);
+  if ((rc = attn_gemm(st, g, K))) return rc;
+  const long long rows = (long long)K * a.B * a.H * T;
+  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T);
+  LAUNCH_CHECK();
+  // dO = dP V + P dV
+  g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = 1.f; g.beta = 0.f;
+  attn_sm(a, D, true, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, 2 * E, g.B, g.ldb, g.sB);
+  { const float* q; attn_act(a, tout, E, a.lout, 0, q, g.ldc, g.sC); g.C = tout; }
+  if ((rc = attn_gemm(st, g, K))) return rc;
+  g.beta = 1.f;
+  attn_sm(a, Pm, false, g.A, g.lda, g.sA);
+  attn_act(a, tin, ldi, a.lin, 2 * E, g.B, g.ldb, g.sB);
+  return attn_gemm(st, g, K);
+}
+// cotangent slots [s0, s0 + ns) of out -> the same slots of in (accumulated if `accumulate`)
+static int attention_backward(const Ctx& c, const Node& n, int s0, int ns, int accumulate) {
+  cudaStream_t st = c.st;
+  const AttnDims a = attn_dims(c, n);
+  const int E = a.E, T = a.T, ldi = 3 * E;
+  const float* in = c.act(n.d.in0);            // primal q | k | v
+  const float* go = c.grad(n.d.out, s0);
+  float* gi = c.grad(n.d.in0, s0);
+  float* Pm = c.ws + n.aux_off;
+  float* D = c.ws + c.P->scratch_off;
+  if (a.pt * ns > c.P->scratch_elems) return fail(CURV_ERR_WORKSPACE, "attention scratch too small");
+  const float beta = accumulate ? 1.f : 0.f;
+  int rc;
+  Bgemm3 g;
+  memset(&g, 0, sizeof(g));
+  g.n1 = a.B; g.n2 = a.H;
+  // gP = gO V^T
+  g.transA = 0; g.transB = 1; g.M = T; g.N = T; g.Kd = a.dh; g.alpha = 1.f; g.beta = 0.f;
+  attn_act(a, go, E, a.lout, 0, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, 2 * E, g.B, g.ldb, g.sB);
+  { const float* q; attn_sm(a, D, true, q, g.ldc, g.sC); g.C = D; }
+  if ((rc = attn_gemm(st, g, ns))) return rc;
+  // gV = P^T gO
+  g.transA = 1; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = 1.f; g.beta = beta;
+  attn_sm(a, Pm, false, g.A, g.lda, g.sA);
+  attn_act(a, go, E, a.lout, 0, g.B, g.ldb, g.sB);
+  { const float* q; attn_act(a, gi, ldi, a.lin, 2 * E, q, g.ldc, g.sC); g.C = gi + 2 * E; }
+  if ((rc = attn_gemm(st, g, ns))) return rc;
+  // gS = P o (gP - rowsum(P o gP))
+  const long long rows = (long long)ns * a.B * a.H * T;
+  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T);
+  LAUNCH_CHECK();
+  // gQ = scale gS K
+  g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = a.scale; g.beta = beta;
+  attn_sm(a, D, true, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, E, g.B, g.ldb, g.sB);
+  { const float* q; attn_act(a, gi, ldi, a.lin, 0, q, g.ldc, g.sC); g.C = gi; }
+  if ((rc = attn_gemm(st, g, ns))) return rc;
+  // gK = scale gS^T Q
+  g.transA = 1;
+  attn_sm(a, D, true, g.A, g.lda, g.sA);
+  attn_act(a, in, ldi, 0, 0, g.B, g.ldb, g.sB);
+  { const float* q; attn_act(a, gi, ldi, a.lin, E, q, g.ldc, g.sC); g.C = gi + E; }
+  return attn_gemm(st, g, ns);
+}
+
 // forward sweep: primal only (K = 0) or primal + K tangents
 static int forward(const Ctx& c, const void* X, int K) {
   curv_program* P = c.P;
@@ -919,6 +1063,13 @@ static int forward(const Ctx& c, const void* X, int K) {
               vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1, c.hs ? c.hsbits() + c.bits_act(d.out) : nullptr);
           LAUNCH_CHECK();
         }
+        break;
+      }
+      case CURV_OP_ATTENTION: {
+        int rc = attention_forward(c, n, vi.tan ? nsl - 1 : 0);
+        if (rc) return rc;
+        if (nsl > 1 && !vi.tan)
+          CHECK_CUDA(cudaMemsetAsync(c.act(d.out, 1), 0, sizeof(float) * vo.slot_elems * (nsl - 1), st));
         break;
       }
       case CURV_OP_AVGPOOL: {
@@ -1288,6 +1439,13 @@ static int backward(const Ctx& c, int K) {
             (c.hs && !ginit[d.in0]) ? (hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns),
                                        c.hsbits() + c.bits_grad(d.in0)) : nullptr);
         LAUNCH_CHECK();
+        mark_written(d.in0);
+        break;
+      }
+      case CURV_OP_ATTENTION: {
+        if (!vi.tan) break;
+        int rc = attention_backward(c, n, s0, ns, ginit[d.in0]);
+        if (rc) return rc;
         mark_written(d.in0);
         break;
       }

@@ -60,7 +60,11 @@ enum curv_op {
   CURV_OP_LAYERNORM = 9, /* LayerNorm over the channels of each pixel / token (aten.native_layer_norm over the last
                             dimension): p0 / c0 = weight, p1 / c1 = bias, eps.  GGN / MC / Jacobian kinds; not part
                             of Hessian (R-op) programs                                                          */
-  CURV_OP_GELU = 10      /* exact (erf) GELU                                                                     */
+  CURV_OP_GELU = 10,     /* exact (erf) GELU                                                                     */
+  CURV_OP_ATTENTION = 11 /* multi-head self-attention core softmax(Q K^T / sqrt(d)) V of nn.MultiheadAttention /
+                            scaled_dot_product_attention (no mask, no dropout): in0 = packed projections
+                            [B, T, 3E] (q | k | v thirds, head h at columns h*d..h*d+d of each), out = [B, T, E],
+                            kh = number of heads; E a multiple of 8.  GGN / Jacobian sweeps (not the Hessian R-op) */
 };
 
 enum curv_loss { CURV_LOSS_CE = 0, CURV_LOSS_MSE = 1, CURV_LOSS_BCE = 2 };

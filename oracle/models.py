@@ -130,3 +130,26 @@ class TiedNet(nn.Module):
         x = torch.nn.functional.adaptive_avg_pool2d(x, 1).flatten(1)
         x = torch.tanh(self.fc(torch.tanh(self.fc(x))))
         return self.head(x)
+
+
+class TransformerBlock(nn.Module):
+    """Pre-norm transformer encoder block on token sequences [B, T, D] (LayerNorm, nn.MultiheadAttention with
+    batch_first, residuals, Linear-GELU-Linear), mean over tokens, linear head: the ViT encoder layer without the
+    class token / position embedding."""
+
+    def __init__(self, dim: int = 16, heads: int = 2, hidden: int = 32, classes: int = 5, layers: int = 1):
+        super().__init__()
+        self.blocks = nn.ModuleList()
+        for _ in range(layers):
+            blk = nn.Module()
+            blk.ln1, blk.attn, blk.ln2 = nn.LayerNorm(dim), nn.MultiheadAttention(dim, heads, batch_first=True), nn.LayerNorm(dim)
+            blk.fc1, blk.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+            self.blocks.append(blk)
+        self.ln, self.head = nn.LayerNorm(dim), nn.Linear(dim, classes)
+
+    def forward(self, x):
+        for blk in self.blocks:
+            y = blk.ln1(x)
+            x = x + blk.attn(y, y, y, need_weights=False)[0]
+            x = x + blk.fc2(torch.nn.functional.gelu(blk.fc1(blk.ln2(x))))
+        return self.head(self.ln(x).mean(1))

