@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcurvb200.so")
 
 # enums (keep in sync with include/curvb200.h)
 (OP_INPUT, OP_CONV, OP_AFFINE, OP_RELU, OP_ADD, OP_MAXPOOL, OP_AVGPOOL, OP_SIGMOID, OP_TANH, OP_LAYERNORM, OP_GELU,
- OP_ATTENTION) = range(12)
+ OP_ATTENTION, OP_RESHAPE, OP_CLSCAT, OP_POSADD, OP_TOKSEL) = range(16)
 LOSS_CE, LOSS_MSE, LOSS_BCE = range(3)
 KIND_GGN, KIND_GGN_MC, KIND_HESSIAN, KIND_JVP, KIND_VJP, KIND_FORWARD = range(6)
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 1, 2, 3, 4

@@ -72,13 +72,16 @@ def _pair(x):
     return (int(x[0]), int(x[1])) if len(x) == 2 else (int(x[0]), int(x[0]))
 
 
-def _simple_token_view(node, ref, B, prog) -> bool:
-    """The two reshapes the plain table handles itself: [B, T, C] <-> [B*T, C] of a token activation."""
+def _simple_view(node, ref, B, prog) -> bool:
+    """Reshapes the plain table handles itself: [B, T, C] <-> [B*T, C] of a token activation; flatten of a feature map
+    to [B, C*H*W] and back to [B, C, H, W]."""
     if ref.kind != "act" or node.target not in (aten.view.default, aten._unsafe_view.default, aten.reshape.default):
         return False
     C, H, W, _ = prog.values[ref.value]
     shape = tuple(int(d) for d in node.meta["val"].shape) if "val" in node.meta else None
     tk = getattr(ref, "tok", None)
+    if tk is None:
+        return shape in ((B, C * H * W), (B, C, H, W))
     return (tk == 3 and shape == (B * W, C)) or (tk == 2 and shape == (B, W, C))
 
 
@@ -153,16 +156,34 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         tk = tok_of(ref)
         if tk is not None:
             return _Ref("lazy", value=ref.value, idx=token_maps(ref.value)[tk])
-        return None
+        # feature map: the traced tensor is [B, C, H, W] (or its flattening), the engine stores [B, H, W, C]
+        idx = torch.arange(Bsz * H * W * C, dtype=torch.int32).view(Bsz, H, W, C).permute(0, 3, 1, 2)
+        return _Ref("lazy", value=ref.value, idx=idx.reshape(Bsz, C * H * W) if ref.flat else idx)
 
     def resolve(lz):
         """lazy -> tagged activation if its map is one of the consumable layouts, else the lazy reference itself."""
-        C, H, W, _ = prog.values[lz.value]
+        C, H, W, tan = prog.values[lz.value]
+        shape = tuple(lz.idx.shape)
+        if shape == (Bsz, H * W, C) and (H != 1 or True) and lz.idx.is_contiguous() is not None \
+                and torch.equal(lz.idx, torch.arange(Bsz * H * W * C, dtype=torch.int32).view(Bsz, H * W, C)):
+            if H == 1:
+                return _Ref("act", value=lz.value, flat=False, tok=3)
+            # [B, C, H, W] patch map read as a [B, H*W, C] token sequence: same elements of the channels-last storage
+            ov = prog.add_value(C, 1, H * W, tan)
+            prog.add_node(capi.OP_RESHAPE, in0=lz.value, out=ov)
+            return _Ref("act", value=ov, flat=False, tok=3)
         if H != 1:
             return lz
-        for tag, m in token_maps(lz.value).items():
-            if tuple(m.shape) == tuple(lz.idx.shape) and torch.equal(m, lz.idx):
+        maps = token_maps(lz.value)
+        for tag, m in maps.items():
+            if tuple(m.shape) == shape and torch.equal(m, lz.idx):
                 return _Ref("act", value=lz.value, flat=False, tok=tag)
+        if shape == (Bsz, C):  # one token of every sequence (the class-token read-out)
+            t0 = int(lz.idx[0, 0]) // C
+            if 0 <= t0 < W and torch.equal(lz.idx, maps[3][:, t0, :]):
+                ov = prog.add_value(C, 1, 1, tan)
+                prog.add_node(capi.OP_TOKSEL, in0=lz.value, out=ov, kw=t0)
+                return _Ref("act", value=ov, flat=True)
         return lz
 
     VIEW_LIKE = {aten.view.default, aten._unsafe_view.default, aten.reshape.default, aten.unsqueeze.default,
@@ -314,9 +335,26 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         a = [env.get(x, x) if isinstance(x, torch.fx.Node) else x for x in node.args]
         if t in (aten.detach.default, aten.alias.default, aten.clone.default, aten.contiguous.default):
             env[node] = a[0]
-        elif (t in VIEW_LIKE and isinstance(a[0], _Ref) and (a[0].kind == "lazy" or (a[0].kind == "act" and tok_of(a[0])))
-              and not _simple_token_view(node, a[0], Bsz, prog)):
+        elif (t in VIEW_LIKE and isinstance(a[0], _Ref) and a[0].kind in ("lazy", "act")
+              and not _simple_view(node, a[0], Bsz, prog)):
             env[node] = apply_view(node, to_lazy(a[0]))
+        elif t == aten.expand.default and isinstance(a[0], _Ref) and a[0].kind in ("param", "const"):
+            env[node] = _Ref("expand", base=a[0], shape=tuple(int(d) for d in node.meta["val"].shape))
+        elif t == aten.cat.default:
+            items = [env.get(x) for x in node.args[0]]
+            dim = node.args[1] if len(node.args) > 1 else 0
+            if (len(items) != 2 or items[0] is None or items[1] is None or items[0].kind != "expand"
+                    or items[1].kind != "act" or tok_of(items[1]) != 3 or dim != 1):
+                unsupported(node, "only cat([class_token.expand(B, -1, -1), tokens], dim=1)")
+            C, H, W, tan = shape_of(items[1])
+            base = items[0].base
+            bshape = base.shape if base.kind == "param" else tuple(base.tensor.shape)
+            if tuple(bshape) != (1, 1, C) or items[0].shape != (Bsz, 1, C) or C % 8:
+                unsupported(node, "class token must be [1, 1, C] with C a multiple of 8")
+            p0, c0 = weight_slots(base)
+            ov = prog.add_value(C, 1, W + 1, tan or p0 >= 0)
+            prog.add_node(capi.OP_CLSCAT, in0=items[1].value, out=ov, p0=p0, c0=c0)
+            env[node] = _Ref("act", value=ov, flat=False, tok=3)
         elif "_scaled_dot_product" in str(t):
             env[node] = emit_attention(node, a)
         elif t == aten.t.default or (t == aten.transpose.int and a[0].kind in ("param", "const")):
@@ -415,6 +453,13 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
             xr, bref = a[0], a[1]
             prod = producer.get(xr.value)
             bshape = bref.shape if bref.kind == "param" else tuple(bref.tensor.shape)
+            if tok_of(xr) == 3 and tuple(bshape) == (1, shape_of(xr)[2], shape_of(xr)[0]) and shape_of(xr)[0] % 8 == 0:
+                C, H, W, tan = shape_of(xr)  # position embedding, broadcast over the batch
+                p0, c0 = weight_slots(bref)
+                ov = prog.add_value(C, 1, W, tan or p0 >= 0)
+                prog.add_node(capi.OP_POSADD, in0=xr.value, out=ov, p0=p0, c0=c0)
+                env[node] = _Ref("act", value=ov, flat=False, tok=3)
+                continue
             if (prod is None or prog.nodes[prod]["op"] != capi.OP_CONV or prog.nodes[prod]["p1"] >= 0
                     or prog.nodes[prod]["c1"] >= 0 or tuple(bshape) != (shape_of(xr)[0],)
                     or readers.get(alias_root(node.args[0]), 0) != 1):

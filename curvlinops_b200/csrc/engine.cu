@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "attention.cuh"
+#include "token_ops.cuh"
 #include "tc_gemm.cuh"
 #include "hs_gemm.cuh"
 
@@ -275,6 +276,23 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
       n.nchunks = (int)((rows + n.rows_per_cta - 1) / n.rows_per_cta);
       long long need = (long long)n.nchunks * (kmax + 1) * 2 * vi.Cp;
       if (need > scratch) scratch = need;
+    } else if (d.op == CURV_OP_RESHAPE || d.op == CURV_OP_CLSCAT || d.op == CURV_OP_POSADD || d.op == CURV_OP_TOKSEL) {
+      Value& vi = P->values[d.in0];
+      Value& vo = P->values[d.out];
+      if (hessian & 1) { delete P; return fail(CURV_ERR_UNSUPPORTED, "token ops are not supported by the Hessian R-op program"); }
+      if (vi.C != vi.Cp || vo.C != vi.C) { delete P; return fail(CURV_ERR_INVALID, "token ops need a channel count that is a multiple of 8"); }
+      bool ok = true;
+      if (d.op == CURV_OP_RESHAPE) {
+        ok = vi.slot_elems == vo.slot_elems && vi.tan == vo.tan;
+        if (ok) { vo.act_off = vi.act_off; vo.grad_off = vi.grad_off; }  // alias: same elements, other (H, W)
+      } else if (d.op == CURV_OP_CLSCAT) {
+        ok = vi.H == 1 && vo.H == 1 && vo.W == vi.W + 1 && (d.p0 >= 0 || d.c0 >= 0);
+      } else if (d.op == CURV_OP_POSADD) {
+        ok = vi.H == 1 && vo.H == 1 && vo.W == vi.W && (d.p0 >= 0 || d.c0 >= 0);
+      } else {
+        ok = vi.H == 1 && vo.H == 1 && vo.W == 1 && d.kw >= 0 && d.kw < vi.W;
+      }
+      if (!ok) { delete P; return fail(CURV_ERR_INVALID, "token op: value shapes do not match"); }
     } else if (d.op == CURV_OP_ATTENTION) {
       const Value& vi = P->values[d.in0];
       const Value& vo = P->values[d.out];
@@ -568,7 +586,8 @@ static int prepare_node(const Ctx& c, Node& n, bool with_tangents) {
     const curv_node_desc& d = n.d;
     if (c.v_ready && with_tangents) {  // streaming call: the columns of V of this node's parameters must have landed
       for (int p : {d.p0, d.p1})
-        if ((d.op == CURV_OP_CONV || d.op == CURV_OP_AFFINE || d.op == CURV_OP_LAYERNORM) && p >= 0 && c.v_ready[p])
+        if ((d.op == CURV_OP_CONV || d.op == CURV_OP_AFFINE || d.op == CURV_OP_LAYERNORM || d.op == CURV_OP_CLSCAT ||
+             d.op == CURV_OP_POSADD) && p >= 0 && c.v_ready[p])
           CHECK_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)c.v_ready[p], 0));
     }
     if (d.op == CURV_OP_CONV) {
@@ -719,7 +738,8 @@ static int prepare_params(const Ctx& c, bool with_tangents) {
 static int signal_out_done(const Ctx& c, const Node& n) {
   if (!c.out_done) return CURV_OK;
   for (int p : {n.d.p0, n.d.p1})
-    if ((n.d.op == CURV_OP_CONV || n.d.op == CURV_OP_AFFINE || n.d.op == CURV_OP_LAYERNORM) && p >= 0 && c.out_done[p])
+    if ((n.d.op == CURV_OP_CONV || n.d.op == CURV_OP_AFFINE || n.d.op == CURV_OP_LAYERNORM || n.d.op == CURV_OP_CLSCAT ||
+         n.d.op == CURV_OP_POSADD) && p >= 0 && c.out_done[p])
       CHECK_CUDA(cudaEventRecord((cudaEvent_t)c.out_done[p], c.st));
   return CURV_OK;
 }
@@ -1063,6 +1083,30 @@ static int forward(const Ctx& c, const void* X, int K) {
               vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, 1, c.hs ? c.hsbits() + c.bits_act(d.out) : nullptr);
           LAUNCH_CHECK();
         }
+        break;
+      }
+      case CURV_OP_RESHAPE:
+        break;  // the output aliases the input
+      case CURV_OP_CLSCAT: {
+        const float* cls = d.p0 >= 0 ? c.param(d.p0) : c.cst(d.c0);
+        clscat_fwd_kernel<<<dim3(grid1d(vo.slot_elems), nsl), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, cls, (d.p0 >= 0 && K > 0) ? c.vcol(d.p0) : nullptr, c.ldk,
+            c.act(d.out), vo.slot_elems, P->B, vi.W, vi.C, nsl);
+        LAUNCH_CHECK();
+        break;
+      }
+      case CURV_OP_POSADD: {
+        const float* pos = d.p0 >= 0 ? c.param(d.p0) : c.cst(d.c0);
+        posadd_fwd_kernel<<<dim3(grid1d(vo.slot_elems), nsl), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, vi.tan ? 1 : 0, pos, (d.p0 >= 0 && K > 0) ? c.vcol(d.p0) : nullptr, c.ldk,
+            c.act(d.out), vo.slot_elems, P->B, (long long)vi.W * vi.C, nsl);
+        LAUNCH_CHECK();
+        break;
+      }
+      case CURV_OP_TOKSEL: {
+        toksel_fwd_kernel<<<dim3(grid1d(vo.slot_elems), nsl), 256, 0, st>>>(
+            c.act(d.in0), vi.slot_elems, c.act(d.out), vo.slot_elems, P->B, vi.W, vi.C, d.kw);
+        LAUNCH_CHECK();
         break;
       }
       case CURV_OP_ATTENTION: {
@@ -1438,6 +1482,39 @@ static int backward(const Ctx& c, int K) {
             vo.Cp, d.kh, d.kw, d.sh, d.sw, d.ph, d.pw, s0, ns, ginit[d.in0],
             (c.hs && !ginit[d.in0]) ? (hs_fused_absmax(c, c.bits_grad(d.in0) + s0, ns),
                                        c.hsbits() + c.bits_grad(d.in0)) : nullptr);
+        LAUNCH_CHECK();
+        mark_written(d.in0);
+        break;
+      }
+      case CURV_OP_RESHAPE:
+        if (vi.tan) mark_written(d.in0);  // same storage: the cotangent of the output IS the input's
+        break;
+      case CURV_OP_CLSCAT:
+      case CURV_OP_POSADD: {
+        const bool cat = d.op == CURV_OP_CLSCAT;
+        if (d.p0 >= 0 && c.kfac_G == nullptr) {  // parameter gradient: cotangent summed over the batch
+          const long long elems = cat ? vo.C : (long long)vo.W * vo.C;
+          batch_sum_grad_kernel<<<grid1d(elems * ns), 256, 0, st>>>(
+              c.grad(d.out), vo.slot_elems, P->B, (long long)vo.W * vo.C, elems, s0, ns, c.out,
+              P->params[d.p0].offset, c.ldk, c.k0, c.alpha);
+          LAUNCH_CHECK();
+        }
+        if (!vi.tan) break;
+        if (cat) {
+          clscat_bwd_kernel<<<dim3(grid1d(vi.slot_elems), ns), 256, 0, st>>>(
+              c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, P->B, vi.W, vi.C, s0, ginit[d.in0]);
+        } else {
+          axpy_slots_kernel<<<dim3(grid1d(vo.slot_elems / 4), ns), 256, 0, st>>>(
+              c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, vo.slot_elems / 4, s0, 1.f, ginit[d.in0]);
+        }
+        LAUNCH_CHECK();
+        mark_written(d.in0);
+        break;
+      }
+      case CURV_OP_TOKSEL: {
+        if (!vi.tan) break;
+        toksel_bwd_kernel<<<dim3(grid1d(vi.slot_elems), ns), 256, 0, st>>>(
+            c.grad(d.out), vo.slot_elems, c.grad(d.in0), vi.slot_elems, P->B, vi.W, vi.C, d.kw, s0, ginit[d.in0]);
         LAUNCH_CHECK();
         mark_written(d.in0);
         break;

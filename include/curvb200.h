@@ -61,10 +61,16 @@ enum curv_op {
                             dimension): p0 / c0 = weight, p1 / c1 = bias, eps.  GGN / MC / Jacobian kinds; not part
                             of Hessian (R-op) programs                                                          */
   CURV_OP_GELU = 10,     /* exact (erf) GELU                                                                     */
-  CURV_OP_ATTENTION = 11 /* multi-head self-attention core softmax(Q K^T / sqrt(d)) V of nn.MultiheadAttention /
+  CURV_OP_ATTENTION = 11, /* multi-head self-attention core softmax(Q K^T / sqrt(d)) V of nn.MultiheadAttention /
                             scaled_dot_product_attention (no mask, no dropout): in0 = packed projections
                             [B, T, 3E] (q | k | v thirds, head h at columns h*d..h*d+d of each), out = [B, T, E],
                             kh = number of heads; E a multiple of 8.  GGN / Jacobian sweeps (not the Hessian R-op) */
+  /* Token glue of a vision transformer (values [B, T, C] with C a multiple of 8; not in R-op programs):           */
+  CURV_OP_RESHAPE = 12,  /* same elements, other (C, H, W): [B, C, H, W] patch map read as [B, H*W, C] tokens.  The
+                            output value ALIASES the input's storage (no copy)                                      */
+  CURV_OP_CLSCAT = 13,   /* out[b] = cat(class_token, in[b]) along the tokens; p0 / c0 = class token [C]          */
+  CURV_OP_POSADD = 14,   /* out[b] = in[b] + pos, pos [T, C] broadcast over the batch; p0 / c0 = position embedding */
+  CURV_OP_TOKSEL = 15    /* out[b] = in[b, kw, :]  (read-out of one token, kw = its index); out is [B, C]           */
 };
 
 enum curv_loss { CURV_LOSS_CE = 0, CURV_LOSS_MSE = 1, CURV_LOSS_BCE = 2 };

@@ -97,3 +97,62 @@ def test_bf16_operator():
     assert got.dtype == torch.bfloat16
     err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-2, err
+
+
+def _mini_vit(dtype=torch.float32, seed=0, layers=2):
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    torch.manual_seed(seed)
+    kw = dict(image_size=32, patch_size=8, num_layers=layers, num_heads=2, hidden_dim=32, mlp_dim=64, num_classes=5)
+    model = VisionTransformer(**kw).cuda().eval()
+    with torch.no_grad():  # torchvision zero-initialises the head; give every parameter a generic value
+        model.heads.head.weight.normal_(0.0, 0.3)
+        model.heads.head.bias.normal_(0.0, 0.1)
+        model.class_token.normal_(0.0, 0.5)
+        model.encoder.pos_embedding.normal_(0.0, 0.5)
+        for blk in model.encoder.layers:
+            blk.self_attention.in_proj_weight.mul_(3.0)
+            blk.self_attention.in_proj_bias.normal_(0.0, 0.3)
+    model = model.to(dtype)
+    m64 = VisionTransformer(**kw).cuda().double().eval()
+    m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    data = [(torch.rand(4, 3, 32, 32, device="cuda").to(dtype), torch.randint(0, 5, (4,), device="cuda")),
+            (torch.rand(3, 3, 32, 32, device="cuda").to(dtype), torch.randint(0, 5, (3,), device="cuda"))]
+    return model, m64, data, [(X.double(), y) for X, y in data]
+
+
+def test_vision_transformer_ggn_matches_float64_oracle():
+    """torchvision's VisionTransformer end to end: patch convolution read as tokens, class token, position embedding,
+    encoder blocks with attention, class-token read-out; every parameter (incl. class_token / pos_embedding)."""
+    model, m64, data, data64 = _mini_vit()
+    loss = nn.CrossEntropyLoss()
+    params, p64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    V = torch.rand(sum(p.numel() for p in params.values()), 3, device="cuda", dtype=torch.float64)
+    ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V, p64)))
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False)
+    got = G @ V.float()
+    print("ViT GGN err", _close(got, ref, 1e-4))
+    # per-parameter check of the two broadcast parameters
+    o = 0
+    for n, p in params.items():
+        if n in ("class_token", "encoder.pos_embedding"):
+            blk = slice(o, o + p.numel())
+            assert ref[blk].abs().max() > 0
+            _close(got[blk], ref[blk], 1e-4)
+        o += p.numel()
+
+
+def test_vision_transformer_bf16_mc_and_subset():
+    model, m64, data, data64 = _mini_vit(dtype=torch.bfloat16, seed=1)
+    loss = nn.CrossEntropyLoss()
+    params, p64 = dict(model.named_parameters()), dict(m64.named_parameters())
+    V = torch.rand(sum(p.numel() for p in params.values()), 2, device="cuda").to(torch.bfloat16)
+    ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V.double(), p64)))
+    got = GGNLinearOperator(model, loss, params, data, check_deterministic=False) @ V
+    err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert got.dtype == torch.bfloat16 and err < 2e-2, err
+    # class token and position embedding constant, encoder weights only; MC-GGN runs and is repeatable
+    sub = {n: p for n, p in params.items() if "mlp" in n or "in_proj" in n}
+    G = GGNLinearOperator(model, loss, sub, data, check_deterministic=False, mc_samples=2, seed=11)
+    v = torch.rand(G.shape[1], device="cuda").to(torch.bfloat16)
+    assert torch.equal(G @ v, G @ v)
