@@ -39,6 +39,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: its own metric (a step = one factor build), printed as an extra line
     "c3": ("ResNet-18 random-init, synthetic 128x3x224x224, KFACLinearOperator factor build (Conv2d/Linear params, "
            "joint bias, MC Fisher 1 sample) + damped inverse 1e-3 + inverse apply @ 1 vector, bf16", "bf16"),
+    # BASELINE.json configs[3]: ViT-B/16, MC-GGN (1 sample), 4 vectors, bf16, 32 samples per GPU (256 on 8)
+    "c4": ("ViT-B/16 random-init, synthetic (32 per GPU)x3x224x224, GGNLinearOperator(mc_samples=1) @ 4 vectors, bf16",
+           "bf16"),
     # BASELINE.json configs[4]: its own metric (matvecs/s of the GGN under a Lanczos eigensolver), printed as an extra line
     "c5": ("ResNet-50 random-init, synthetic (64 per GPU)x3x224x224, GGNLinearOperator matvecs under Lanczos "
            "eigsh(k=10), bf16", "bf16"),
@@ -417,6 +420,150 @@ def run_c3(torch, args):
     print(json.dumps(out))
 
 
+def run_c4(torch, args):
+    """C4: MC-GGN (one sample) of a bf16 ViT-B/16 applied to 4 vectors; weak scaling, 32 examples per GPU (256 on 8: the
+    configuration's global batch); mini-batch sharded over the ranks, one all-reduce of [P, 4] per product."""
+    import torch.distributed as dist
+    import torchvision
+
+    from curvlinops_b200 import GGNLinearOperator, _capi as capi
+    from curvlinops_b200 import dist as cdist
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        cdist.enable(True)
+    PB, KV = int(os.environ.get("CURV_C4_PER_GPU", 32)), 4
+    GB = PB * world
+    torch.manual_seed(0)
+    model = torchvision.models.vit_b_16().eval()
+    with torch.no_grad():  # torchvision zero-initialises the classification head: the GGN would vanish
+        model.heads.head.weight.normal_(0.0, 0.02)
+    model = model.to(torch.bfloat16).to(dev)
+    X = torch.rand(GB, 3, 224, 224).to(torch.bfloat16)
+    y = torch.randint(0, 1000, (GB,))
+    X_host, y_host = X.pin_memory(), y.pin_memory()
+    Xd, yd = X.to(dev), y.to(dev)
+    params = dict(model.named_parameters())
+    P = sum(p.numel() for p in params.values())
+    loss = torch.nn.CrossEntropyLoss()
+    kw = dict(check_deterministic=False, num_data=GB, mc_samples=1)
+    G = GGNLinearOperator(model, loss, params, [(Xd, yd)], **kw)
+    G_host = GGNLinearOperator(model, loss, params, [(X_host, y_host)], **kw)
+    G_host._engine = G._engine
+    torch.manual_seed(1)
+    V_host = torch.rand(P, KV).to(torch.bfloat16).pin_memory()
+    out_host = torch.empty(P, KV, dtype=torch.bfloat16).pin_memory()
+    Vd = V_host.to(dev)
+    if world > 1:
+        dist.broadcast(Vd, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    def step_e2e():  # host X / y (uploaded inside), host V in, host result out
+        out_host.copy_(G_host @ V_host.to(dev, non_blocking=True), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    t0 = time.perf_counter()
+    G @ Vd
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    for _ in range(max(3, args.warmup)):
+        G @ Vd
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    L0 = capi.lib().curv_launch_count()
+    ms_step = timed(lambda: G @ Vd, args.steps)
+    launches = capi.lib().curv_launch_count() - L0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
+    # repeatability (same seed -> same draws) and positive semi-definiteness on the timed operator
+    a, b = G @ Vd[:, :1], G @ Vd[:, :1]
+    same = bool(torch.equal(a, b))
+    quad = float((Vd[:, 0].float() * a[:, 0].float()).sum())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {
+        "metric": "ggn_matvec_throughput", "value": P * KV / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "params": P, "columns": KV, "global_batch": GB, "mc_samples": 1,
+                   "parallelism": f"dp{world} (mini-batch sharded over the ranks, one all-reduce of [P,4] per product)",
+                   "l2": "activations (GBs) far exceed the 126 MB L2; no flush needed"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "first_product_s": t_first,
+        "e2e": {"value": P * KV / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(X_host.numel() * 2 + y_host.numel() * 8 + V_host.numel() * 2 * world),
+                "d2h_bytes_per_step": int(P * KV * 2)},
+        "self_check": {"repeatable": same, "vT_G_v": quad},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.build_ref import import_reference
+
+        ref = import_reference()
+        try:  # the unmodified reference on this GPU (needs train() with p = 0 and the math attention path: SURVEY 8c)
+            from torch.nn.attention import SDPBackend, sdpa_kernel
+
+            model.train()
+            with sdpa_kernel(SDPBackend.MATH):
+                Gr = ref.GGNLinearOperator(model, loss, params, [(Xd, yd)], check_deterministic=False, num_data=GB,
+                                           mc_samples=1)
+                Gr @ Vd
+                t_r = timed(lambda: Gr @ Vd, 2)
+            out["gpu_library_baseline"] = {"what": "unmodified reference GGNLinearOperator(mc_samples=1) @ V on the same GPU "
+                                                   "(torch CUDA, bf16, math attention path)", "ms": t_r,
+                                           "value": P * KV / (t_r / 1e3), "unit": UNIT}
+            del Gr
+        except Exception as e:
+            out["gpu_library_baseline"] = {"bf16_error": f"{type(e).__name__}: {e}"[:300]}
+            try:  # the reference does not run this configuration in bf16 here: time it in fp32 with TF32 allowed
+                from torch.nn.attention import SDPBackend, sdpa_kernel
+
+                torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+                m32 = torchvision.models.vit_b_16().train().to(dev)
+                p32 = dict(m32.named_parameters())
+                with sdpa_kernel(SDPBackend.MATH):
+                    Gr = ref.GGNLinearOperator(m32, loss, p32, [(Xd.float(), yd)], check_deterministic=False,
+                                               num_data=GB, mc_samples=1)
+                    V32 = Vd.float()
+                    Gr @ V32
+                    t_r = timed(lambda: Gr @ V32, 2)
+                out["gpu_library_baseline"].update({
+                    "what": "unmodified reference GGNLinearOperator(mc_samples=1) @ V on the same GPU (torch CUDA, fp32 "
+                            "parameters with TF32 matmuls allowed, math attention path)", "ms": t_r,
+                    "value": P * KV / (t_r / 1e3), "unit": UNIT})
+                del Gr, m32
+            except Exception as e2:
+                out["gpu_library_baseline"]["fp32_error"] = f"{type(e2).__name__}: {e2}"[:300]
+        model.eval()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_c5(torch, args):
     """C5: GGN of a bf16 ResNet-50 feeding a Lanczos eigensolver (k = 10); metric matvecs/s.  Weak scaling: 64 examples
     per GPU (512 on 8, the configuration's global batch), the mini-batch sharded over the ranks, one all-reduce of the
@@ -620,6 +767,8 @@ def main():
 
     if CONFIG == "c5" and args.impl != "reference":
         return run_c5(torch, args)
+    if CONFIG == "c4" and args.impl != "reference":
+        return run_c4(torch, args)
     if CONFIG in ("c1", "c3") and args.impl != "reference":
         if int(os.environ.get("RANK", "0")) == 0:
             (run_c3 if CONFIG == "c3" else run_c1)(torch, args)

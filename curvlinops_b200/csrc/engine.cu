@@ -301,7 +301,7 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
           vi.Cp != vi.C || vo.Cp != vo.C) {
         delete P; return fail(CURV_ERR_INVALID, "attention node: in0 must be [B, T, 3E], out [B, T, E], E a multiple of 8 and of the head count");
       }
-      const long long pt = (long long)batch * d.kh * vi.W * vi.W;  // softmax matrices of one slot
+      const long long pt = (long long)batch * d.kh * vi.W * ((vi.W + 3) & ~3);  // softmax matrices of one slot (rows padded to 16 bytes)
       n.aux_off = alloc(pt);
       if (pt * kmax > scratch) scratch = pt * kmax;
     } else if (d.op == CURV_OP_MAXPOOL) {
@@ -745,16 +745,30 @@ static int signal_out_done(const Ctx& c, const Node& n) {
 }
 
 // ---- multi-head attention core (attention.cuh): batched over (slot, example, head) with three-level strides
+static bool g_attn_mma = false;  // set per call: bf16 operators multiply on the tensor cores (mma.sync, bf16 operands)
 static int attn_gemm(cudaStream_t st, Bgemm3 p, int n0) {
   if (n0 < 1) return CURV_OK;
   const long long nz = (long long)n0 * p.n1 * p.n2;
   if (nz > 65535) return fail(CURV_ERR_UNSUPPORTED, "attention: more than 65535 (slot, example, head) triples per launch");
-  attn_bgemm_kernel<<<dim3(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)nz), 256, 0, st>>>(p);
+  const dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)nz);
+  const size_t smem = attn_sgemm_smem(p.M, p.N, p.Kd);
+  if (g_attn_mma && smem <= 200 * 1024) {  // whole (slot, example, head) product per CTA
+    static bool attr_set = false;
+    if (!attr_set) {
+      CHECK_CUDA(cudaFuncSetAttribute(attn_sgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    attn_sgemm_kernel<<<(unsigned)nz, ATTN_SG_THREADS, smem, st>>>(p);
+    LAUNCH_CHECK();
+    return CURV_OK;
+  }
+  if (g_attn_mma) attn_bgemm_kernel<true><<<grid, 256, 0, st>>>(p);
+  else attn_bgemm_kernel<false><<<grid, 256, 0, st>>>(p);
   LAUNCH_CHECK();
   return CURV_OK;
 }
 struct AttnDims {
-  int T, E, H, dh, B;
+  int T, Tp, E, H, dh, B;  // Tp: row pitch of the softmax-shaped buffers
   long long lin, lout, pt;  // slot strides of in / out, softmax elements per slot
   float scale;
 };
@@ -762,8 +776,8 @@ static AttnDims attn_dims(const Ctx& c, const Node& n) {
   const Value& vi = c.P->values[n.d.in0];
   const Value& vo = c.P->values[n.d.out];
   AttnDims a;
-  a.T = vi.W; a.E = vo.C; a.H = n.d.kh; a.dh = a.E / a.H; a.B = c.P->B;
-  a.lin = vi.slot_elems; a.lout = vo.slot_elems; a.pt = (long long)a.B * a.H * a.T * a.T;
+  a.T = vi.W; a.Tp = (a.T + 3) & ~3; a.E = vo.C; a.H = n.d.kh; a.dh = a.E / a.H; a.B = c.P->B;
+  a.lin = vi.slot_elems; a.lout = vo.slot_elems; a.pt = (long long)a.B * a.H * a.T * a.Tp;
   a.scale = 1.f / sqrtf((float)a.dh);
   return a;
 }
@@ -774,10 +788,11 @@ static void attn_act(const AttnDims& a, const float* base, int ld, long long slo
   ptr = base + col0; ldo = ld; s[0] = slot_stride; s[1] = (long long)a.T * ld; s[2] = a.dh;
 }
 static void attn_sm(const AttnDims& a, const float* base, bool per_slot, const float*& ptr, int& ldo, long long s[3]) {
-  ptr = base; ldo = a.T; s[0] = per_slot ? a.pt : 0; s[1] = (long long)a.H * a.T * a.T; s[2] = (long long)a.T * a.T;
+  ptr = base; ldo = a.Tp; s[0] = per_slot ? a.pt : 0; s[1] = (long long)a.H * a.T * a.Tp; s[2] = (long long)a.T * a.Tp;
 }
 static int attention_forward(const Ctx& c, const Node& n, int K) {
   cudaStream_t st = c.st;
+  g_attn_mma = (c.P->hessian & 4) && g_tc_mode && !(g_tc_disable & 32);
   const AttnDims a = attn_dims(c, n);
   const int E = a.E, T = a.T, ldi = 3 * E;
   const float* in = c.act(n.d.in0);
@@ -794,7 +809,7 @@ static int attention_forward(const Ctx& c, const Node& n, int K) {
   attn_act(a, in, ldi, 0, E, g.B, g.ldb, g.sB);
   { const float* q; attn_sm(a, Pm, false, q, g.ldc, g.sC); g.C = Pm; }
   if ((rc = attn_gemm(st, g, 1))) return rc;
-  attn_softmax_kernel<<<(unsigned)(((long long)a.B * a.H * T + 7) / 8), 256, 0, st>>>(Pm, (long long)a.B * a.H * T, T);
+  attn_softmax_kernel<<<(unsigned)(((long long)a.B * a.H * T + 7) / 8), 256, 0, st>>>(Pm, (long long)a.B * a.H * T, T, a.Tp);
   LAUNCH_CHECK();
   // O = P V
   g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = 1.f; g.beta = 0.f;
@@ -817,7 +832,7 @@ static int attention_forward(const Ctx& c, const Node& n, int K) {
   attn_act(a, tin, ldi, a.lin, E, g.B, g.ldb, g.sB);
   if ((rc = attn_gemm(st, g, K))) return rc;
   const long long rows = (long long)K * a.B * a.H * T;
-  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T);
+  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T, a.Tp);
   LAUNCH_CHECK();
   // dO = dP V + P dV
   g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = 1.f; g.beta = 0.f;
@@ -833,6 +848,7 @@ static int attention_forward(const Ctx& c, const Node& n, int K) {
 // cotangent slots [s0, s0 + ns) of out -> the same slots of in (accumulated if `accumulate`)
 static int attention_backward(const Ctx& c, const Node& n, int s0, int ns, int accumulate) {
   cudaStream_t st = c.st;
+  g_attn_mma = (c.P->hessian & 4) && g_tc_mode && !(g_tc_disable & 32);
   const AttnDims a = attn_dims(c, n);
   const int E = a.E, T = a.T, ldi = 3 * E;
   const float* in = c.act(n.d.in0);            // primal q | k | v
@@ -860,7 +876,7 @@ static int attention_backward(const Ctx& c, const Node& n, int s0, int ns, int a
   if ((rc = attn_gemm(st, g, ns))) return rc;
   // gS = P o (gP - rowsum(P o gP))
   const long long rows = (long long)ns * a.B * a.H * T;
-  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T);
+  attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T, a.Tp);
   LAUNCH_CHECK();
   // gQ = scale gS K
   g.transA = 0; g.transB = 0; g.M = T; g.N = a.dh; g.Kd = T; g.alpha = a.scale; g.beta = beta;

