@@ -338,6 +338,11 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         elif (t in VIEW_LIKE and isinstance(a[0], _Ref) and a[0].kind in ("lazy", "act")
               and not _simple_view(node, a[0], Bsz, prog)):
             env[node] = apply_view(node, to_lazy(a[0]))
+        elif t == aten.unbind.int and isinstance(a[0], _Ref) and a[0].kind in ("lazy", "act"):
+            lz = to_lazy(a[0])  # q, k, v = qkv.unbind(0): one select per item
+            dim = int(a[1]) if len(a) > 1 else 0
+            env[node] = _Ref("tuple", items=[resolve(_Ref("lazy", value=lz.value, idx=lz.idx.select(dim, i)))
+                                             for i in range(lz.idx.shape[dim])])
         elif t == aten.expand.default and isinstance(a[0], _Ref) and a[0].kind in ("param", "const"):
             env[node] = _Ref("expand", base=a[0], shape=tuple(int(d) for d in node.meta["val"].shape))
         elif t == aten.cat.default:

@@ -286,3 +286,59 @@ def test_capture_layernorm_gelu_tokens():
     bad = nn.Sequential(nn.Conv2d(3, 4, 3), nn.LayerNorm(6), nn.Flatten(), nn.Linear(4 * 6 * 6, 2))
     with pytest.raises(NotImplementedError, match="LayerNorm"):
         capture(make_functional_call(bad), dict(bad.named_parameters()), torch.rand(2, 3, 8, 8))
+
+
+def test_capture_attention_and_vision_transformer():
+    """nn.MultiheadAttention's traced view chain is recognised through index maps; torchvision's VisionTransformer lowers
+    to conv -> reshape (alias) -> class-token concat -> position add -> encoder blocks -> token read-out -> head; the plans
+    build on the host; R-op programs and unsupported attention variants are rejected."""
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    from oracle.models import TransformerBlock
+
+    m = TransformerBlock(dim=16, heads=2, hidden=32, layers=2).eval()
+    params = dict(m.named_parameters())
+    lp = capture(make_functional_call(m), params, torch.rand(3, 7, 16))
+    ops = [n["op"] for n in lp.nodes]
+    assert ops.count(capi.OP_ATTENTION) == 2 and ops.count(capi.OP_CONV) == 2 * 4 + 1 and ops.count(capi.OP_ADD) == 4
+    att = [n for n in lp.nodes if n["op"] == capi.OP_ATTENTION][0]
+    assert att["kh"] == 2 and lp.values[att["in0"]][:3] == [48, 1, 7] and lp.values[att["out"]][:3] == [16, 1, 7]
+    inproj = lp.nodes[lp.conv_nodes["blocks.0.attn.in_proj_weight"]]
+    assert list(params)[inproj["p1"]] == "blocks.0.attn.in_proj_bias"  # "mm + bias" folded into the layer
+    prog = CompiledProgram(make_functional_call(m), params, torch.rand(3, 7, 16), 4, False)
+    assert prog.ws_bytes > 0
+    with pytest.raises(NotImplementedError, match="R-op"):
+        CompiledProgram(make_functional_call(m), params, torch.rand(3, 7, 16), 4, True)
+
+    vit = VisionTransformer(image_size=32, patch_size=8, num_layers=1, num_heads=4, hidden_dim=32, mlp_dim=64,
+                            num_classes=5).eval()
+    vp = dict(vit.named_parameters())
+    lp = capture(make_functional_call(vit), vp, torch.rand(2, 3, 32, 32))
+    ops = [n["op"] for n in lp.nodes]
+    assert ops[:5] == [capi.OP_INPUT, capi.OP_CONV, capi.OP_RESHAPE, capi.OP_CLSCAT, capi.OP_POSADD]
+    assert ops[-2:] == [capi.OP_TOKSEL, capi.OP_CONV] and ops.count(capi.OP_ATTENTION) == 1
+    names = list(vp)
+    assert names[lp.nodes[3]["p0"]] == "class_token" and names[lp.nodes[4]["p0"]] == "encoder.pos_embedding"
+    assert lp.values[lp.nodes[3]["out"]][:3] == [32, 1, 17] and lp.nodes[-2]["kw"] == 0
+    assert CompiledProgram(make_functional_call(vit), vp, torch.rand(2, 3, 32, 32), 2, False).ws_bytes > 0
+    # parameters left out of `params` become constants
+    sub = {n: p for n, p in vp.items() if "mlp" in n}
+    lp = capture(make_functional_call(vit), sub, torch.rand(2, 3, 32, 32))
+    assert lp.nodes[3]["p0"] == -1 and lp.nodes[3]["c0"] >= 0 and not lp.values[lp.nodes[4]["out"]][3]
+
+    class OwnAttention(nn.Module):  # the timm-style spelling: reshape / permute / unbind around F.scaled_dot_product_attention
+        def __init__(self, causal):
+            super().__init__()
+            self.qkv, self.head, self.causal = nn.Linear(16, 48), nn.Linear(16, 3), causal
+
+        def forward(self, x):
+            q, k, v = self.qkv(x).view(x.shape[0], x.shape[1], 3, 2, 8).permute(2, 0, 3, 1, 4)
+            o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=self.causal)
+            return self.head(o.permute(0, 2, 1, 3).reshape(x.shape[0], x.shape[1], 16).mean(1))
+
+    own = OwnAttention(False).eval()
+    lp = capture(make_functional_call(own), dict(own.named_parameters()), torch.rand(2, 5, 16))
+    assert [n["op"] for n in lp.nodes] == [capi.OP_INPUT, capi.OP_CONV, capi.OP_ATTENTION, capi.OP_AVGPOOL, capi.OP_CONV]
+    bad = OwnAttention(True).eval()
+    with pytest.raises(NotImplementedError, match="causal"):
+        capture(make_functional_call(bad), dict(bad.named_parameters()), torch.rand(2, 5, 16))
