@@ -158,3 +158,23 @@ def test_vision_transformer_bf16_mc_and_subset():
     G = GGNLinearOperator(model, loss, sub, data, check_deterministic=False, mc_samples=2, seed=11)
     v = torch.rand(G.shape[1], device="cuda").to(torch.bfloat16)
     assert torch.equal(G @ v, G @ v)
+
+
+def test_kfac_factors_of_vision_transformer_layers():
+    """KFAC (type-2, joint weight + bias) of the Linear / Conv2d layers of a vision transformer -- the patch convolution,
+    the MLP layers (weights shared over the 17 tokens) and the head -- with the attention, LayerNorm, class token and
+    position embedding as constants in between: factors vs the oracle's hook-based float64 restatement on the GPU."""
+    from curvlinops_b200 import KFACLinearOperator
+
+    model, m64, data, data64 = _mini_vit(seed=5, layers=1)
+    loss = nn.CrossEntropyLoss()
+    layers = ["conv_proj", "encoder.layers.encoder_layer_0.mlp.0", "encoder.layers.encoder_layer_0.mlp.3", "heads.head"]
+    params = {f"{n}.{r}": dict(model.named_parameters())[f"{n}.{r}"] for n in layers for r in ("weight", "bias")}
+    A64, G64 = orc.kfac_factors(m64, loss, layers, data64, fisher_type="type2", joint_bias=True)
+    K = KFACLinearOperator(model, loss, params, data, fisher_type="type-2", separate_weight_and_bias=False,
+                           check_deterministic=False)
+    _, blocks, _ = K
+    for n, blk in zip(layers, blocks):
+        Gf, Af = list(blk)
+        _close(Af, A64[n], 1e-4)
+        _close(Gf, G64[n], 1e-4)
