@@ -142,10 +142,15 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
     # tensor whose entries are the flat positions in the engine value it reads.  View-like nodes are applied to the
     # map; as soon as the map equals one of the layouts a layer can consume, the reference becomes an ordinary
     # activation again with the tag tok = 3 ([B, T, C]), 2 ([B*T, C]), "t3" ([T, B, C]) or "t2" ([T*B, C]).
+    _maps: dict = {}
+
     def token_maps(value):
         C, H, W, _ = prog.values[value]
-        base = torch.arange(Bsz * W * C, dtype=torch.int32).view(Bsz, W, C)
-        return {3: base, 2: base.reshape(Bsz * W, C), "t3": base.transpose(0, 1), "t2": base.transpose(0, 1).reshape(W * Bsz, C)}
+        if (W, C) not in _maps:
+            base = torch.arange(Bsz * W * C, dtype=torch.int32).view(Bsz, W, C)
+            _maps[(W, C)] = {3: base, 2: base.reshape(Bsz * W, C), "t3": base.transpose(0, 1),
+                             "t2": base.transpose(0, 1).reshape(W * Bsz, C)}
+        return _maps[(W, C)]
 
     def to_lazy(ref):
         if ref.kind == "lazy":
@@ -164,8 +169,7 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
         """lazy -> tagged activation if its map is one of the consumable layouts, else the lazy reference itself."""
         C, H, W, tan = prog.values[lz.value]
         shape = tuple(lz.idx.shape)
-        if shape == (Bsz, H * W, C) and (H != 1 or True) and lz.idx.is_contiguous() is not None \
-                and torch.equal(lz.idx, torch.arange(Bsz * H * W * C, dtype=torch.int32).view(Bsz, H * W, C)):
+        if shape == (Bsz, H * W, C) and torch.equal(lz.idx, torch.arange(Bsz * H * W * C, dtype=torch.int32).view(shape)):
             if H == 1:
                 return _Ref("act", value=lz.value, flat=False, tok=3)
             # [B, C, H, W] patch map read as a [B, H*W, C] token sequence: same elements of the channels-last storage
@@ -245,8 +249,9 @@ def capture(model_func, params: dict[str, Tensor], X: Tensor, fuse_relu: bool = 
     def unsupported(node, why=""):
         raise NotImplementedError(
             f"Operation {node.target} is not supported by the B200 curvature engine"
-            f"{': ' + why if why else ''}. Supported layers: Linear, Conv2d, BatchNorm2d (eval), ReLU,"
-            " Sigmoid, Tanh, MaxPool2d, global average pooling, residual adds, flatten."
+            f"{': ' + why if why else ''}. Supported layers: Linear, Conv2d, BatchNorm2d (eval), LayerNorm, ReLU,"
+            " Sigmoid, Tanh, GELU, MaxPool2d, global average pooling, residual adds, flatten, token sequences with"
+            " multi-head self-attention, class token and position embedding."
         )
 
     def weight_slots(ref):

@@ -20,6 +20,11 @@ struct Bgemm3 {
   const float* B; int ldb; long long sB[3];
   float* C; int ldc; long long sC[3];
   int n1, n2;  // blockIdx.z = (i0 * n1 + i1) * n2 + i2
+  // optional second product added to the first (C = alpha (op(A) op(B) + op(A2) op(B2)) + beta C): the two terms of a
+  // product rule (dQ K^T + Q dK^T, dP V + P dV) in ONE pass over C.  A2 == nullptr: absent.  Same M, N, own Kd2.
+  int transA2, transB2, Kd2;
+  const float* A2; int lda2; long long sA2[3];
+  const float* B2; int ldb2; long long sB2[3];
 };
 
 __device__ __forceinline__ uint32_t attn_pack_bf16(float lo, float hi) {
@@ -193,7 +198,8 @@ __device__ __forceinline__ void attn_stage(__nv_bfloat16* __restrict__ dst, int 
   // 32 warps: the staging loads of a lone resident CTA need the parallelism
 __global__ void __launch_bounds__(ATTN_SG_THREADS) attn_sgemm_kernel(const Bgemm3 p) {
   extern __shared__ __align__(16) unsigned char attn_smem[];
-  const int Mp = (p.M + 15) & ~15, Np = (p.N + 31) & ~31, Kp = (p.Kd + 15) & ~15, pitch = Kp + 8;
+  const int Mp = (p.M + 15) & ~15, Np = (p.N + 31) & ~31, Kp1 = (p.Kd + 15) & ~15;
+  const int Kp = Kp1 + (p.A2 ? ((p.Kd2 + 15) & ~15) : 0), pitch = Kp + 8;  // the second product extends the reduction
   __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(attn_smem);
   __nv_bfloat16* Bs = As + (size_t)Mp * pitch;
   const int z = blockIdx.x;
@@ -203,10 +209,19 @@ __global__ void __launch_bounds__(ATTN_SG_THREADS) attn_sgemm_kernel(const Bgemm
   float* C = p.C + i0 * p.sC[0] + i1 * p.sC[1] + i2 * p.sC[2];
   const int t = threadIdx.x;
   // ---- stage both operands: 16-byte loads along the contiguous axis of the source where it is aligned
-  if (p.transA) attn_stage<false>(As, pitch, A, p.lda, p.M, Mp, p.Kd, Kp, t);
-  else attn_stage<true>(As, pitch, A, p.lda, p.M, Mp, p.Kd, Kp, t);
-  if (p.transB) attn_stage<true>(Bs, pitch, B, p.ldb, p.N, Np, p.Kd, Kp, t);
-  else attn_stage<false>(Bs, pitch, B, p.ldb, p.N, Np, p.Kd, Kp, t);
+  if (p.transA) attn_stage<false>(As, pitch, A, p.lda, p.M, Mp, p.Kd, Kp1, t);
+  else attn_stage<true>(As, pitch, A, p.lda, p.M, Mp, p.Kd, Kp1, t);
+  if (p.transB) attn_stage<true>(Bs, pitch, B, p.ldb, p.N, Np, p.Kd, Kp1, t);
+  else attn_stage<false>(Bs, pitch, B, p.ldb, p.N, Np, p.Kd, Kp1, t);
+  if (p.A2) {
+    const float* A2 = p.A2 + i0 * p.sA2[0] + i1 * p.sA2[1] + i2 * p.sA2[2];
+    const float* B2 = p.B2 + i0 * p.sB2[0] + i1 * p.sB2[1] + i2 * p.sB2[2];
+    const int Kp2 = Kp - Kp1;
+    if (p.transA2) attn_stage<false>(As + Kp1, pitch, A2, p.lda2, p.M, Mp, p.Kd2, Kp2, t);
+    else attn_stage<true>(As + Kp1, pitch, A2, p.lda2, p.M, Mp, p.Kd2, Kp2, t);
+    if (p.transB2) attn_stage<true>(Bs + Kp1, pitch, B2, p.ldb2, p.N, Np, p.Kd2, Kp2, t);
+    else attn_stage<false>(Bs + Kp1, pitch, B2, p.ldb2, p.N, Np, p.Kd2, Kp2, t);
+  }
   __syncthreads();
   const int w = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
   const int mtiles = Mp / 16, nstrips = Np / 32;
@@ -248,8 +263,8 @@ __global__ void __launch_bounds__(ATTN_SG_THREADS) attn_sgemm_kernel(const Bgemm
       }
   }
 }
-static inline size_t attn_sgemm_smem(int M, int N, int Kd) {
-  const int Mp = (M + 15) & ~15, Np = (N + 31) & ~31, Kp = (Kd + 15) & ~15;
+static inline size_t attn_sgemm_smem(int M, int N, int Kd, int Kd2 = 0) {
+  const int Mp = (M + 15) & ~15, Np = (N + 31) & ~31, Kp = ((Kd + 15) & ~15) + (Kd2 > 0 ? ((Kd2 + 15) & ~15) : 0);
   return (size_t)(Mp + Np) * (Kp + 8) * 2;
 }
 

@@ -750,12 +750,23 @@ static int attn_gemm(cudaStream_t st, Bgemm3 p, int n0) {
   if (n0 < 1) return CURV_OK;
   const long long nz = (long long)n0 * p.n1 * p.n2;
   if (nz > 65535) return fail(CURV_ERR_UNSUPPORTED, "attention: more than 65535 (slot, example, head) triples per launch");
+  constexpr size_t SMEM_MAX = 227 * 1024;
+  if (p.A2 && !(g_attn_mma && attn_sgemm_smem(p.M, p.N, p.Kd, p.Kd2) <= SMEM_MAX)) {
+    // the fused two-term kernel does not apply: two launches, the second accumulating
+    Bgemm3 a = p, b = p;
+    a.A2 = nullptr; a.B2 = nullptr;
+    b.A = p.A2; b.lda = p.lda2; b.transA = p.transA2; b.B = p.B2; b.ldb = p.ldb2; b.transB = p.transB2; b.Kd = p.Kd2;
+    for (int i = 0; i < 3; ++i) { b.sA[i] = p.sA2[i]; b.sB[i] = p.sB2[i]; }
+    b.A2 = nullptr; b.B2 = nullptr; b.beta = 1.f;
+    int rc = attn_gemm(st, a, n0);
+    return rc ? rc : attn_gemm(st, b, n0);
+  }
   const dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)nz);
-  const size_t smem = attn_sgemm_smem(p.M, p.N, p.Kd);
-  if (g_attn_mma && smem <= 200 * 1024) {  // whole (slot, example, head) product per CTA
+  const size_t smem = attn_sgemm_smem(p.M, p.N, p.Kd, p.A2 ? p.Kd2 : 0);
+  if (g_attn_mma && smem <= SMEM_MAX) {  // whole (slot, example, head) product per CTA
     static bool attr_set = false;
     if (!attr_set) {
-      CHECK_CUDA(cudaFuncSetAttribute(attn_sgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CHECK_CUDA(cudaFuncSetAttribute(attn_sgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
       attr_set = true;
     }
     attn_sgemm_kernel<<<(unsigned)nz, ATTN_SG_THREADS, smem, st>>>(p);
@@ -826,10 +837,9 @@ static int attention_forward(const Ctx& c, const Node& n, int K) {
   attn_act(a, tin, ldi, a.lin, 0, g.A, g.lda, g.sA);
   attn_act(a, in, ldi, 0, E, g.B, g.ldb, g.sB);
   { const float* q; attn_sm(a, D, true, q, g.ldc, g.sC); g.C = D; }
-  if ((rc = attn_gemm(st, g, K))) return rc;
-  g.beta = 1.f;
-  attn_act(a, in, ldi, 0, 0, g.A, g.lda, g.sA);
-  attn_act(a, tin, ldi, a.lin, E, g.B, g.ldb, g.sB);
+  g.transA2 = 0; g.transB2 = 1; g.Kd2 = a.dh;                       // + Q dK^T in the same pass
+  attn_act(a, in, ldi, 0, 0, g.A2, g.lda2, g.sA2);
+  attn_act(a, tin, ldi, a.lin, E, g.B2, g.ldb2, g.sB2);
   if ((rc = attn_gemm(st, g, K))) return rc;
   const long long rows = (long long)K * a.B * a.H * T;
   attn_softmax_jvp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Pm, D, (long long)a.B * a.H * T, rows, T, a.Tp);
@@ -839,10 +849,9 @@ static int attention_forward(const Ctx& c, const Node& n, int K) {
   attn_sm(a, D, true, g.A, g.lda, g.sA);
   attn_act(a, in, ldi, 0, 2 * E, g.B, g.ldb, g.sB);
   { const float* q; attn_act(a, tout, E, a.lout, 0, q, g.ldc, g.sC); g.C = tout; }
-  if ((rc = attn_gemm(st, g, K))) return rc;
-  g.beta = 1.f;
-  attn_sm(a, Pm, false, g.A, g.lda, g.sA);
-  attn_act(a, tin, ldi, a.lin, 2 * E, g.B, g.ldb, g.sB);
+  g.transA2 = 0; g.transB2 = 0; g.Kd2 = T;                          // + P dV in the same pass
+  attn_sm(a, Pm, false, g.A2, g.lda2, g.sA2);
+  attn_act(a, tin, ldi, a.lin, 2 * E, g.B2, g.ldb2, g.sB2);
   return attn_gemm(st, g, K);
 }
 // cotangent slots [s0, s0 + ns) of out -> the same slots of in (accumulated if `accumulate`)
