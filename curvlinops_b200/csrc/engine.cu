@@ -211,18 +211,27 @@ extern "C" int curv_program_create(const curv_value_desc* values, int n_values,
         int nsl = kmax + ((hessian & 1) ? 1 : 0);
         // multi-slot tcgen05 wgrad: the slots live inside one tile
         long long tiles = (long long)ceil_div(g.Kd, 128) * ceil_div(vo.Cp, 64);
-        int want = (int)((2 * 148 + tiles - 1) / tiles);
-        int maxsplit = ceil_div(g.M, 512);
-        n.nsplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
-        if (n.nsplit > 64) n.nsplit = 64;
+        // Split count of the pixel reduction.  Lower bound: at most 2048 pixels (384 MMAs per accumulator on the fp16
+        // path) per split, so the tensor core's truncating accumulation stays below ~1e-5 and no tile needs an in-kernel
+        // TMEM flush (measured, round 2: flushing in the kernel instead -- HSW_FLUSH = 128 stages, splits only to fill
+        // the SMs -- halves the partial traffic but doubles the kernel time: the single-buffered accumulators stall the
+        // MMA warp for every read-modify-write drain); bf16 operators (tolerance 1e-2) take chains of 4096 pixels =
+        // the kernel's flush interval (16384-pixel chains were measured: 6.3 -> 9.5 ms of wgrad per bf16 C2 step,
+        // the drains again).  Above the bound the count is chosen by a cost model: whole waves of
+        // tiles x splits work items over the 148 SMs, an item costing its pixels plus a fixed prologue / epilogue
+        // (~768 pixels' worth), plus the partial traffic of the split-K sums.
         {
-          // multi-slot kernels: at most 2048 pixels (384 MMAs per accumulator on the fp16 path) per split, so the
-          // tensor core's truncating accumulation stays below ~1e-5 and no tile needs an in-kernel TMEM flush
-          // (measured, round 2: flushing in the kernel instead -- HSW_FLUSH = 128 stages, splits only to fill the
-          // SMs -- halves the partial traffic but doubles the kernel time: the single-buffered accumulators stall
-          // the MMA warp for every read-modify-write drain)
-          const int by_len = ceil_div(g.M, 2048);
-          if (by_len > n.nsplit) n.nsplit = by_len;
+          const int lower = std::max(1, ceil_div(g.M, (hessian & 4) ? 4096 : 2048));
+          const int upper = std::max(lower, std::min(ceil_div(g.M, 512), 1024));
+          const double px_ns = (hessian & 4) ? 14.0 * nsl : 42.0 * nsl / 4.0;  // per pixel of one work item
+          const double split_ns = (double)n.wsize * nsl * 8.0 / 6.5e3;          // write + read of one split's partials
+          double best = 1e300;
+          n.nsplit = lower;
+          for (int ns = lower; ns <= upper; ++ns) {
+            const double waves = (double)((tiles * ns + 147) / 148);
+            const double cost = waves * ((double)ceil_div(g.M, ns) + 768.0) * px_ns + ns * split_ns;
+            if (cost < best * 0.999) { best = cost; n.nsplit = ns; }
+          }
         }
         n.m_per_split = (ceil_div(g.M, n.nsplit) + 15) / 16 * 16;
         n.nsplit = ceil_div(g.M, n.m_per_split);
