@@ -567,6 +567,7 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         st = self.__dict__.copy()
         st["_engine"] = None
         st["_copy_streams"] = None
+        st.pop("_mc_cache", None)
         return st
 
     def __setstate__(self, st):
@@ -616,13 +617,34 @@ class GGNLinearOperator(CurvatureLinearOperator):
     def _mc_scale(self, batch: int) -> float:
         return 1.0 / batch if self._loss_func.reduction == "mean" else 1.0
 
+    def _mc_grad(self, X, shard=None):
+        """Would-be gradients of one mini-batch.  Every product re-seeds the generator (same stream as the reference,
+        ``ggn.py:337-341``), so as long as the parameters and the mini-batch are unchanged the draws of batch i are the
+        same tensor every time: they are kept per (batch position, data, parameter versions) and a hit only consumes
+        the variates the draw would have used, which keeps the stream aligned for the batches that follow.  That saves
+        the primal forward pass + softmax + sampling per product (about 14 % of a ViT-B/16 MC-GGN product)."""
+        key = (self._batch_index, self._seed, self._mc_samples, X.data_ptr(), X._version, tuple(X.shape), shard,
+               tuple((p.data_ptr(), p._version) for p in self._params.values()))
+        cache = self.__dict__.setdefault("_mc_cache", {})
+        hit = cache.get(self._batch_index)
+        if hit is not None and hit[0] == key:
+            lo, hi, Bg = (0, X.shape[0], X.shape[0]) if shard is None else shard
+            lf, M, C = self._loss_func, self._mc_samples, hit[1].shape[-1]
+            n = Bg * M if isinstance(lf, CrossEntropyLoss) else Bg * M * C
+            (torch.randn if isinstance(lf, MSELoss) else torch.rand)(n, device=X.device, dtype=hit[1].dtype)
+            return hit[1]
+        g = self._engine.mc_grad_outputs(X, self._mc_samples, shard=shard)
+        if len(cache) < 64:
+            cache[self._batch_index] = (key, g)
+        return g
+
     def _batch_call(self, X, y, V, out, alpha):
         if self._mc_samples == 0:
             return super()._batch_call(X, y, V, out, alpha)
         if self._mc_grad_override is not None:
             g = self._mc_grad_override[self._batch_index].to(X.device)
         else:
-            g = self._engine.mc_grad_outputs(X, self._mc_samples)
+            g = self._mc_grad(X)
         self._batch_index += 1
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g,
                                   scale=self._mc_scale(X.shape[0]))
@@ -630,7 +652,8 @@ class GGNLinearOperator(CurvatureLinearOperator):
     def _batch_call_sharded(self, X, y, V, out, alpha, scale, out_done=None, cols=None):
         if self._mc_samples == 0:
             return super()._batch_call_sharded(X, y, V, out, alpha, scale, out_done=out_done, cols=cols)
-        g = self._engine.mc_grad_outputs(X, self._mc_samples, shard=getattr(X, "_curv_shard", None))
+        g = self._mc_grad(X, shard=getattr(X, "_curv_shard", None))
+        self._batch_index += 1
         self._engine.matmat_batch(capi.KIND_GGN_MC, X, y, V, out, alpha, mc_grad=g, scale=scale[1],
                                   **self._shard_kw(out_done, cols))
 

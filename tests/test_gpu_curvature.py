@@ -350,3 +350,22 @@ def test_weight_tying_matches_float64_oracle(op):
         ref = flat(orc.hessian_matmat(m64, loss, p64, data64, split_like(V, p64)))
         A = HessianLinearOperator(model, loss, params, data, check_deterministic=False)
     assert_parity(A @ V.float().cuda(), ref, params)
+
+
+def test_mc_would_be_gradients_are_cached_without_changing_results():
+    """The MC draws of a mini-batch are kept across products (same seed -> same draws): results are bit-identical to an
+    operator without the cache, also when only part of the batches hit (the stream stays aligned), and a parameter
+    update invalidates the entries."""
+    model, loss, data, fx, params = _setup("mlp_c1_ce_mean")
+    V = fx["V"].float().cuda()[:, :2]
+    mk = lambda: GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=3, seed=5)
+    G = mk()
+    a = G @ V                        # fills the cache (two mini-batches)
+    assert len(G._mc_cache) == 2
+    assert torch.equal(G @ V, a) and torch.equal(mk() @ V, a)
+    G._mc_cache.pop(0)               # batch 0 misses, batch 1 hits
+    assert torch.equal(G @ V, a)
+    with torch.no_grad():
+        next(iter(params.values())).add_(0.01)
+    b = G @ V
+    assert not torch.equal(a, b) and torch.equal(b, mk() @ V)
