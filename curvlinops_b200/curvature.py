@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import copy
 import os
+import weakref
 from collections.abc import Callable, Iterable, MutableMapping
 
 import torch
@@ -170,22 +171,41 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
             num_per_example_loss_terms = t_acc // N
         return N, num_per_example_loss_terms
 
-    def _loop_over_data(self, desc: str | None = None, to_device: bool = True):
+    def _loop_over_data(self, desc: str | None = None, to_device: bool = True, stage: bool = False):
+        """``stage``: uploads land in buffers the operator keeps (see :meth:`_upload`); only the product loops ask for
+        it -- two simultaneous iterations (the determinism probes) must not share buffers."""
         it = self._data
         dev = self.device if to_device else None
         if self._progressbar:
             from tqdm import tqdm
 
             it = tqdm(it, desc=f"{self.__class__.__name__}{'' if desc is None else '.' + desc} (on {dev})")
-        for X, y in it:
+        for i, (X, y) in enumerate(it):
             if isinstance(X, Tensor):
-                X = X.to(dev) if to_device else X
+                X = (self._upload(X, (i, "X")) if stage else X.to(dev)) if to_device else X
             elif self._input_key is not None:
                 Xt = X[self._input_key]
                 Xt = (Xt.to(dev) if to_device else Xt).detach()  # a new tensor object: the tag stays off the caller's
                 Xt._curv_batch_size = self._batch_size_fn(X)
                 X = Xt
-            yield X, (y.to(dev) if to_device else y)
+            yield X, ((self._upload(y, (i, "y")) if stage else y.to(dev)) if to_device else y)
+
+    def _upload(self, t: Tensor, key) -> Tensor:
+        """Host-resident mini-batches are uploaded by every product (``_torch_base.py:937-944`` does the same).  The
+        first few land in device buffers the operator keeps, so their addresses do not change from product to product
+        and the captured CUDA graph of a product stays valid (a fresh allocation per upload made every host-data
+        product run eagerly or re-capture); data loaders with many batches fall back to plain uploads."""
+        dev = self.device
+        if t.device == dev:
+            return t
+        stage = self.__dict__.setdefault("_upload_stage", {})
+        buf = stage.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            if buf is None and len(stage) >= 8:
+                return t.to(dev, non_blocking=True)
+            buf = stage[key] = torch.empty(t.shape, dtype=t.dtype, device=dev)
+        buf.copy_(t, non_blocking=True)
+        return buf
 
     def _get_normalization_factor(self, X, y) -> float:
         return {"sum": 1.0, "mean": self._batch_size_fn(X) / self._N_data}[self._loss_func.reduction]
@@ -285,15 +305,24 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         ``shard = (index, count)`` of the batch shard (default: rank / world)."""
         rank, world = cdist.rank_world() if shard is None else shard
         dev = self.device
-        for X, y in self._loop_over_data(desc=desc, to_device=(world == 1)):
+        for bi, (X, y) in enumerate(self._loop_over_data(desc=desc, to_device=(world == 1), stage=True)):
             alpha = self._get_normalization_factor(X, y)
             if world == 1:
                 yield X, y, alpha, None
                 continue
             Xs, ys, scales = cdist.shard_batch(X, y, rank, world, self._loss_func, self._engine)
-            if Xs is not None:
+            if Xs is not None and Xs.device == dev:
+                # device-resident data: hand out the SAME slice objects product after product (the engine keys its
+                # converted copies on the tensor object)
+                cache = self.__dict__.setdefault("_slice_cache", {})
+                hit = cache.get(bi)
+                if hit is not None and hit[0]() is X and hit[1] == Xs._curv_shard:
+                    Xs, ys = hit[2], hit[3]
+                else:
+                    cache[bi] = (weakref.ref(X), Xs._curv_shard, Xs, ys)
+            elif Xs is not None:
                 shard_info = Xs._curv_shard
-                Xs, ys = Xs.to(dev, non_blocking=True), ys.to(dev, non_blocking=True)
+                Xs, ys = self._upload(Xs, (bi, "Xs")), self._upload(ys, (bi, "ys"))
                 Xs._curv_shard = shard_info
             else:
                 self._on_empty_shard(X, y)
@@ -568,6 +597,8 @@ class CurvatureLinearOperator(PyTorchLinearOperator):
         st["_engine"] = None
         st["_copy_streams"] = None
         st.pop("_mc_cache", None)
+        st.pop("_upload_stage", None)
+        st.pop("_slice_cache", None)
         return st
 
     def __setstate__(self, st):
@@ -634,7 +665,10 @@ class GGNLinearOperator(CurvatureLinearOperator):
             (torch.randn if isinstance(lf, MSELoss) else torch.rand)(n, device=X.device, dtype=hit[1].dtype)
             return hit[1]
         g = self._engine.mc_grad_outputs(X, self._mc_samples, shard=shard)
-        if len(cache) < 64:
+        if hit is not None and hit[1].shape == g.shape and hit[1].dtype == g.dtype:
+            hit[1].copy_(g)  # same address as before: the product's CUDA graph (keyed on it) stays valid
+            g = hit[1]
+        if hit is not None or len(cache) < 64:
             cache[self._batch_index] = (key, g)
         return g
 

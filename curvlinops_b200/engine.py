@@ -214,12 +214,18 @@ class Engine:
         CUDA-graph key needs, and an eigensolver that revisits the same batches does not pay for it again."""
         if X.dtype == torch.float32 and X.is_contiguous():
             return X
-        for hit in self._x32:
-            if hit[0] == X.data_ptr() and hit[1] == X._version and hit[2] == (tuple(X.shape), X.dtype, X.device):
+        sig = (tuple(X.shape), X.dtype, X.device)
+        for i, hit in enumerate(self._x32):
+            # identity of the tensor OBJECT, not its address: a data loader's fresh batch may land on the address of a
+            # freed one with the same version counter
+            if hit[0]() is X and hit[2] == sig:
+                if hit[1] != X._version:  # same buffer, new contents (a host mini-batch uploaded again): convert in
+                    hit[3].copy_(X)       # place, the fp32 copy keeps its address
+                    self._x32[i] = (hit[0], X._version, sig, hit[3])
                 return hit[3]
         X32 = X.to(torch.float32).contiguous()
         if X.device.type == "cuda":
-            self._x32 = self._x32[-3:] + [(X.data_ptr(), X._version, (tuple(X.shape), X.dtype, X.device), X32)]
+            self._x32 = [h for h in self._x32 if h[0]() is not None][-3:] + [(weakref.ref(X), X._version, sig, X32)]
         return X32
 
     # -- the hot call ----------------------------------------------------------------------------
