@@ -796,6 +796,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.impl == "reference" and not CONFIG.startswith("c2"):
+        if rank == 0:  # the reference arm times the C2 workloads; the other configurations carry the reference's own
+            # numbers (same GPU and host cores) in the gpu_library_baseline / cpu_baseline objects of their line
+            print(json.dumps({"impl": "reference", "unavailable": f"--impl reference covers --config c2 / c2-bf16 / "
+                              f"c2-hessian; run `bench.py --config {CONFIG}` for the reference numbers of this configuration"}))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
