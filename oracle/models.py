@@ -137,7 +137,8 @@ class TransformerBlock(nn.Module):
     batch_first, residuals, Linear-GELU-Linear), mean over tokens, linear head: the ViT encoder layer without the
     class token / position embedding."""
 
-    def __init__(self, dim: int = 16, heads: int = 2, hidden: int = 32, classes: int = 5, layers: int = 1):
+    def __init__(self, dim: int = 16, heads: int = 2, hidden: int = 32, classes: int = 5, layers: int = 1,
+                 sharpen: bool = False):
         super().__init__()
         self.blocks = nn.ModuleList()
         for _ in range(layers):
@@ -146,6 +147,11 @@ class TransformerBlock(nn.Module):
             blk.fc1, blk.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
             self.blocks.append(blk)
         self.ln, self.head = nn.LayerNorm(dim), nn.Linear(dim, classes)
+        if sharpen:  # the default initialisation leaves the attention nearly uniform
+            with torch.no_grad():
+                for blk in self.blocks:
+                    blk.attn.in_proj_weight.mul_(3.0)
+                    blk.attn.in_proj_bias.normal_(0.0, 0.3)
 
     def forward(self, x):
         for blk in self.blocks:
@@ -153,3 +159,21 @@ class TransformerBlock(nn.Module):
             x = x + blk.attn(y, y, y, need_weights=False)[0]
             x = x + blk.fc2(torch.nn.functional.gelu(blk.fc1(blk.ln2(x))))
         return self.head(self.ln(x).mean(1))
+
+
+def mini_vit(classes: int = 5, layers: int = 2):
+    """torchvision's VisionTransformer at toy size (32 x 32 images, 8 x 8 patches, 2 heads, width 32) with generic values
+    for the parameters torchvision zero-initialises (classification head) or leaves tiny (class token, positions)."""
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    model = VisionTransformer(image_size=32, patch_size=8, num_layers=layers, num_heads=2, hidden_dim=32, mlp_dim=64,
+                              num_classes=classes)
+    with torch.no_grad():
+        model.heads.head.weight.normal_(0.0, 0.3)
+        model.heads.head.bias.normal_(0.0, 0.1)
+        model.class_token.normal_(0.0, 0.5)
+        model.encoder.pos_embedding.normal_(0.0, 0.5)
+        for blk in model.encoder.layers:
+            blk.self_attention.in_proj_weight.mul_(3.0)
+            blk.self_attention.in_proj_bias.normal_(0.0, 0.3)
+    return model

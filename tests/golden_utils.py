@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from oracle.models import ConvNetBias, MiniResNet, TiedNet, TokenMLP, mlp_c1, mlp_gelu, mlp_ln_gelu, mlp_smooth
+from oracle.models import ConvNetBias, MiniResNet, TiedNet, TokenMLP, TransformerBlock, mini_vit, mlp_c1, mlp_gelu, mlp_ln_gelu, mlp_smooth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -26,6 +26,9 @@ BUILDERS = {
     "ggn_diag_cnn_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_tokens": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
+    "transformer_block_ce_mean": (lambda: TransformerBlock(dim=16, heads=2, hidden=32, layers=2),
+                                  lambda: nn.CrossEntropyLoss()),
+    "mini_vit_ce_mean": (lambda: mini_vit(), lambda: nn.CrossEntropyLoss()),
     "kfac_tied": (lambda: TiedNet(), lambda: nn.CrossEntropyLoss()),
     "kfac_cnn": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
 }

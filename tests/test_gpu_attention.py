@@ -178,3 +178,24 @@ def test_kfac_factors_of_vision_transformer_layers():
         Gf, Af = list(blk)
         _close(Af, A64[n], 1e-4)
         _close(Gf, G64[n], 1e-4)
+
+
+@pytest.mark.parametrize("name", ["transformer_block_ce_mean", "mini_vit_ce_mean"])
+def test_attention_fixtures_generated_by_the_reference(name):
+    """GGN and empirical Fisher against the REFERENCE's own outputs (tests/golden, oracle/make_golden_attention.py), and
+    the MC-GGN with the would-be gradients of the reference's RNG stream handed to the engine."""
+    from curvlinops_b200 import EFLinearOperator
+    from tests.golden_utils import load_case
+
+    model, loss, data, fx = load_case(name, dtype=torch.float32, device="cuda")
+    params = dict(model.named_parameters())
+    V = fx["V"].float().cuda()
+    _close(GGNLinearOperator(model, loss, params, data, check_deterministic=False) @ V, fx["ggn"].cuda(), 1e-4)
+    _close(EFLinearOperator(model, loss, params, data, check_deterministic=False) @ V, fx["ef"].cuda(), 1e-4)
+    cpu_model, _, cpu_data, _ = load_case(name)
+    with torch.random.fork_rng():
+        torch.manual_seed(1234)  # the reference's stream: one multinomial per mini-batch after manual_seed(seed)
+        gs = [orc.mc_grad_outputs(loss, cpu_model(X).detach(), 3) for X, _ in cpu_data]
+    G = GGNLinearOperator(model, loss, params, data, check_deterministic=False, mc_samples=3, seed=1234)
+    G._mc_grad_override = [g.float() for g in gs]
+    _close(G @ V, fx["ggn_mc3"].cuda(), 1e-4)

@@ -82,3 +82,22 @@ def test_ggn_diagonal_matches_reference(name):
     params = dict(model.named_parameters())
     got = torch.cat([d.reshape(-1) for d in orc.ggn_diagonal(model, loss, params, data)])
     torch.testing.assert_close(got, fx["diag"], rtol=1e-9, atol=1e-13)
+
+
+# fixtures of oracle/make_golden_attention.py: nn.MultiheadAttention blocks on token sequences, torchvision's
+# VisionTransformer at toy size (the reference ran them through torch.func on the math attention path)
+ATTN_CASES = ["transformer_block_ce_mean", "mini_vit_ce_mean"]
+
+
+@pytest.mark.parametrize("name", ATTN_CASES)
+def test_attention_cases_match_reference(name):
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    model, loss, data, fx = load_case(name)
+    params = dict(model.named_parameters())
+    V = split_like(fx["V"], params)
+    with sdpa_kernel(SDPBackend.MATH):  # the fused CPU attention kernel has no double backward
+        torch.testing.assert_close(flat(orc.ggn_matmat(model, loss, params, data, V)), fx["ggn"], rtol=1e-9, atol=1e-12)
+        torch.testing.assert_close(flat(orc.ef_matmat(model, loss, params, data, V)), fx["ef"], rtol=1e-9, atol=1e-12)
+        got = flat(orc.ggn_matmat(model, loss, params, data, V, mc_samples=3, seed=1234))
+    torch.testing.assert_close(got, fx["ggn_mc3"], rtol=1e-9, atol=1e-12)
