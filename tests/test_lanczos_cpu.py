@@ -63,3 +63,26 @@ def test_lanczos_argument_errors():
         lanczos_eigsh(A, k=10)
     with pytest.raises(ValueError):
         lanczos_eigsh(A, k=2, which="XX")
+
+
+def test_lanczos_basis_grows_in_blocks_and_warns_without_convergence():
+    """The Lanczos basis is allocated ncv + 1 rows at a time (not maxiter + 1 up front), low-precision operators run
+    their vector algebra in fp32, and a run that stops at maxiter without meeting the residual test says so."""
+    import warnings
+
+    M = _spd(60, seed=3)
+    A = Dense(M)
+    ref = torch.linalg.eigvalsh(M)[-3:]
+    evals, evecs, m = lanczos_eigsh(A, k=3, ncv=8, maxiter=60, tol=1e-10, return_info=True)
+    assert m > 9  # went past the first block of the basis
+    torch.testing.assert_close(evals, ref, rtol=1e-8, atol=1e-10)
+    torch.testing.assert_close(M @ evecs, evecs * evals, rtol=1e-6, atol=1e-8)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        lanczos_eigsh(A, k=3, ncv=4, maxiter=4, tol=0.0)
+    assert any("residual test not met" in str(x.message) for x in w)
+    # bf16 operator: fp32 Lanczos vectors, bf16 results
+    Ab = Dense(M.to(torch.bfloat16))
+    eb, vb = lanczos_eigsh(Ab, k=2, ncv=20, tol=1e-3)
+    assert eb.dtype == torch.bfloat16 and vb.dtype == torch.bfloat16
+    assert ((eb.double() - ref[-2:]).abs() / ref[-1] < 3e-2).all()
