@@ -89,8 +89,7 @@ class KFACComputer(CurvatureLinearOperator):
             )
         if kfac_approx not in KFACType:
             raise ValueError(f"Invalid kfac_approx: {kfac_approx}. Supported: {tuple(KFACType)}.")
-        if KFACType(kfac_approx) != KFACType.EXPAND:
-            raise NotImplementedError("The B200 engine implements KFAC-expand only.")
+        self._kfac_approx = KFACType(kfac_approx)
         if not isinstance(model_func, Module):
             raise ValueError("The KFAC computer requires an nn.Module (as the reference's hooks backend).")
         self._model_module = model_func
@@ -212,7 +211,10 @@ class KFACComputer(CurvatureLinearOperator):
             red = self._loss_func.reduction
             scale = 1.0 / (B_glob * T) if red == "mean" else 1.0
             corr = (B_glob * T) ** 2 / (T * N) if red == "mean" else 1.0
-            self._accumulate(prog, ws, X, gos, scale, corr, A, G)
+            if self._kfac_approx == KFACType.REDUCE:
+                self._accumulate_reduce(X, gos, scale, corr, A, G)
+            else:
+                self._accumulate(prog, ws, X, gos, scale, corr, A, G)
         if world > 1:  # one all-reduce over the concatenated factors
             flat = torch.cat([t.reshape(-1) for t in list(A.values()) + list(G.values())])
             cdist.all_reduce_sum(flat)
@@ -231,6 +233,39 @@ class KFACComputer(CurvatureLinearOperator):
         dt = self.dtype
         return ({k: with_fp32_master(v, dt) for k, v in A.items()}, {k: with_fp32_master(v, dt) for k, v in G.items()},
                 self._mapping)
+
+    def _accumulate_reduce(self, X, gos, scale, corr, A, G):
+        """KFAC-reduce (``kfac_math.py:47-170``): the layer inputs are AVERAGED and the output gradients SUMMED over the
+        weight-sharing positions before the outer products, ``A = sum_n a_n a_n^T / N``, ``G = corr sum_{v,n} g_n g_n^T``.
+        The positions are reduced on the values a VJP sweep of the engine leaves in its workspace (one sweep per
+        back-propagated vector) and the [B, d] Gram matrices go through ``curv_gemm``.  Convolutions average their
+        ``F.unfold`` patches -- the same numbers as the reference's ``extract_averaged_patches``, which needs ``einconv``
+        and therefore could not generate a fixture here: pinned for Linear layers (token sequences) only."""
+        dev = X.device
+        V = 0 if gos is None else gos.shape[0]
+        first = True
+        for v in range(max(V, 1)):
+            seed = gos[v] * scale if V > 0 else torch.zeros(X.shape[0], self._engine.predict(X).shape[1], device=dev)
+            acts, grads, prog = EKFACComputer._layer_io(self, X, seed)
+            if prog.lp.tied:
+                raise NotImplementedError("KFAC-reduce with tied weights is not supported.")
+            for group in self._mapping:
+                key = tuple(group.values())
+                ni = self._group_node(prog, group)
+                if first and "W" in group:
+                    a = acts[ni].mean(1)                                    # [B, d_in]
+                    if "b" in group:
+                        a = torch.cat([a, a.new_ones(a.shape[0], 1)], dim=1)
+                    cur = dense_matmul(a.contiguous(), a.contiguous(), transpose_a=True) / self._N_data
+                    A[key] = cur if key not in A else A[key] + cur
+                if V > 0:
+                    g = grads[ni].sum(1).contiguous()                       # [B, d_out]
+                    cur = dense_matmul(g, g, transpose_a=True) * corr
+                    G[key] = cur if key not in G else G[key] + cur
+                elif key not in G:
+                    cout = grads[ni].shape[-1]
+                    G[key] = torch.zeros(cout, cout, device=dev, dtype=torch.float32)
+            first = False
 
     def _kfac_program(self, X: Tensor) -> CompiledProgram:
         eng = self._engine

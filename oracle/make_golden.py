@@ -49,7 +49,7 @@ def curvature_cases(name, model, data, loss, K):
     save(name, model, data, extra)
 
 
-def kfac_cases(name, model, data, loss, damping=1e-2, backend="hooks", ekfac=True):
+def kfac_cases(name, model, data, loss, damping=1e-2, backend="hooks", ekfac=True, kfac_approx="expand"):
     params = {n: p for n, p in model.named_parameters()
               if isinstance(dict(model.named_modules())[n.rsplit(".", 1)[0]], (nn.Linear, nn.Conv2d))}
     P = sum(p.numel() for p in params.values())
@@ -61,7 +61,7 @@ def kfac_cases(name, model, data, loss, damping=1e-2, backend="hooks", ekfac=Tru
             tag = f"{ft.replace('-', '')}_{'sep' if sep else 'joint'}"
             Kop = KFACLinearOperator(model, loss, params, data, check_deterministic=False,
                                      fisher_type=ft, mc_samples=(2 if ft == 'mc' else 1), seed=77,
-                                     separate_weight_and_bias=sep, backend=backend)
+                                     separate_weight_and_bias=sep, backend=backend, kfac_approx=kfac_approx)
             extra[f"kfac_{tag}"] = Kop @ v
             extra[f"kfacinv_{tag}"] = Kop.inverse(damping=damping) @ v
             if ft == "type-2":
@@ -72,7 +72,8 @@ def kfac_cases(name, model, data, loss, damping=1e-2, backend="hooks", ekfac=Tru
                 if not ekfac:
                     continue
                 E = EKFACLinearOperator(model, loss, params, data, check_deterministic=False,
-                                        fisher_type=ft, separate_weight_and_bias=sep, backend=backend)
+                                        fisher_type=ft, separate_weight_and_bias=sep, backend=backend,
+                                        kfac_approx=kfac_approx)
                 extra[f"ekfac_{tag}"] = E @ v
                 extra[f"ekfacinv_{tag}"] = E.inverse(damping=damping) @ v
     save(name, model, data, extra)

@@ -20,3 +20,10 @@ torch.manual_seed(51)
 kfac_cases("kfac_tokens", TokenMLP().eval(),
            [(torch.rand(4, 7, 12), torch.randint(0, 5, (4,))), (torch.rand(3, 7, 12), torch.randint(0, 5, (3,)))],
            nn.CrossEntropyLoss())
+
+# KFAC-reduce on the same model / data: inputs averaged and output gradients summed over the T positions before the
+# outer products (kfac_math.py:47-170); Linear layers only, so the reference needs no einconv
+torch.manual_seed(51)
+kfac_cases("kfac_tokens_reduce", TokenMLP().eval(),
+           [(torch.rand(4, 7, 12), torch.randint(0, 5, (4,))), (torch.rand(3, 7, 12), torch.randint(0, 5, (3,)))],
+           nn.CrossEntropyLoss(), ekfac=False, kfac_approx="reduce")

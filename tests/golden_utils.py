@@ -26,6 +26,7 @@ BUILDERS = {
     "ggn_diag_cnn_ce_mean": (lambda: ConvNetBias(), lambda: nn.CrossEntropyLoss()),
     "kfac_mlp": (lambda: mlp_c1(classes=4, width=12), lambda: nn.CrossEntropyLoss()),
     "kfac_tokens": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
+    "kfac_tokens_reduce": (lambda: TokenMLP(), lambda: nn.CrossEntropyLoss()),
     "transformer_block_ce_mean": (lambda: TransformerBlock(dim=16, heads=2, hidden=32, layers=2),
                                   lambda: nn.CrossEntropyLoss()),
     "mini_vit_ce_mean": (lambda: mini_vit(), lambda: nn.CrossEntropyLoss()),

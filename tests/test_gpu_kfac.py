@@ -181,3 +181,26 @@ def test_ekfac_rejects_tied_weights():
     model, loss, data, fx, params = setup("kfac_tied")
     with pytest.raises(NotImplementedError, match="Weight tying"):
         EKFACLinearOperator(model, loss, params, data, fisher_type="type-2", check_deterministic=False)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_kfac_reduce_on_token_model(sep, monkeypatch):
+    """KFAC-reduce (inputs averaged, output gradients summed over the T positions) against the reference's own factors
+    and products (fixture kfac_tokens_reduce); type-2, empirical, and MC with the reference's draws."""
+    model, loss, data, fx, params = setup("kfac_tokens_reduce")
+    tag = "sep" if sep else "joint"
+    kw = dict(separate_weight_and_bias=sep, check_deterministic=False, kfac_approx="reduce")
+    Kop = KFACLinearOperator(model, loss, params, data, fisher_type="type-2", **kw)
+    _, K, _ = Kop
+    for bi, block in enumerate(K):
+        for fi, fac in enumerate(block):
+            close(fac, fx[f"factor_type2_{tag}_{bi}_{fi}"])
+    v = fx["v"].float().cuda()
+    close(Kop @ v, fx[f"kfac_type2_{tag}"])
+    close(Kop.inverse(damping=float(fx["damping"])) @ v, fx[f"kfacinv_type2_{tag}"], rtol=1e-3)
+    close(KFACLinearOperator(model, loss, params, data, fisher_type="empirical", **kw) @ v, fx[f"kfac_empirical_{tag}"])
+    cpu_model, _, cpu_data, _ = load_case("kfac_tokens_reduce")
+    gos = orc.kfac_grad_outputs(cpu_model, loss, cpu_data, "mc", mc_samples=2, seed=77)
+    monkeypatch.setattr(KFACComputer, "_TEST_GRAD_OUTPUTS", [g.float() for g in gos])
+    close(KFACLinearOperator(model, loss, params, data, fisher_type="mc", mc_samples=2, seed=77, **kw) @ v,
+          fx[f"kfac_mc_{tag}"])
